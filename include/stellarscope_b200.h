@@ -1,0 +1,177 @@
+/* stellarscope_b200 -- C ABI of the B200-native EM read-reassignment path.
+ *
+ * The reference (nixonlab/stellarscope) is pure Python and has no FFI on this
+ * path; its boundary is a Python class contract.  This
+ * header is the C-ABI a binding for that contract calls.  Each entry point
+ * names the reference code it replaces (paths relative to the reference
+ * checkout, stellarscope/utils/).
+ *
+ * Conventions
+ *  - every function returns an ss_status (0 = ok); the message of the last
+ *    failure on a handle is returned by ss_last_error().  No C++ exception
+ *    crosses the boundary.
+ *  - the CALLER owns every input and output buffer (device pointers unless the
+ *    name ends in _host); the handle owns the tiled layout and its scratch and
+ *    frees them in ss_destroy().
+ *  - all work is enqueued on the caller's cudaStream_t (passed as void*) and is
+ *    asynchronous unless stated; one handle per (process, GPU); a handle is
+ *    not re-entrant.
+ */
+#ifndef STELLARSCOPE_B200_H
+#define STELLARSCOPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS_ABI_VERSION 1
+
+typedef struct ss_handle_s* ss_handle_t;
+
+enum ss_status {
+  SS_OK = 0,
+  SS_ERR_ARG = 1,      /* bad argument (ValueError in the reference, model.py:424-426) */
+  SS_ERR_CUDA = 2,     /* CUDA runtime failure */
+  SS_ERR_STATE = 3,    /* call order (no layout / no fit yet) */
+  SS_ERR_MODEL = 4,    /* StellarscopeError class: empty model, zero denominator (model.py:267-272) */
+  SS_ERR_CAPACITY = 5  /* a read has more alignments than a tile can hold */
+};
+
+/* reassignment modes, order of TelescopeLikelihood.REASSIGN_MODES (model.py:92-100) */
+enum ss_reassign_mode {
+  SS_BEST_EXCLUDE = 0,
+  SS_BEST_CONF = 1,
+  SS_BEST_RANDOM = 2,
+  SS_BEST_AVERAGE = 3,
+  SS_INITIAL_UNIQUE = 4,
+  SS_INITIAL_RANDOM = 5,
+  SS_TOTAL_HITS = 6
+};
+
+/* sizes of the layout held by a handle */
+typedef struct ss_layout_info {
+  int32_t n_rows, n_cols, n_segments, n_tiles, max_row_len, chunk;
+  int32_t n_unique_rows, n_resident_tiles, n_stream_tiles, n_stream_segments;
+  int64_t nnz, n_segcols, tot_ent, tot_row, tot_col, tot_jds;
+  int64_t nnz_ambiguous, rows_ambiguous;
+} ss_layout_info;
+
+/* host-side description of a pre-built layout (debug / test import only;
+ * format specification: stellarscope_b200/layout_host.py) */
+typedef struct ss_host_layout {
+  int32_t N, K, S, n_tiles, maxlen, chunk, n_uniq;
+  int64_t A, n_segcols, tot_ent, tot_row, tot_col, tot_jds;
+  const int64_t* tile_hdr;
+  const uint16_t* e_lcol; const uint16_t* e_cpos; const double* e_q; const int32_t* e_opos;
+  const uint16_t* r_len; const double* r_w; const int32_t* r_orow;
+  const uint16_t* c_ptr; const int32_t* c_scol; const double* c_pisum0; const int32_t* c_nuniq;
+  const uint16_t* j_ptr;
+  const int32_t* seg_tile0; const int32_t* seg_ntiles; const int32_t* seg_col0; const int32_t* seg_ncol;
+  const int32_t* seg_smax; const int32_t* seg_nobs; const int32_t* seg_namb; const int32_t* seg_nuniq;
+  const double* seg_wmax; const double* seg_wtot; const double* seg_wamb; const double* seg_logq_uniq;
+  const int64_t* seg_A; const int64_t* seg_Aamb;
+  const int32_t* sc_gcol; const double* sc_pisum0; const int32_t* sc_nuniq; const int8_t* sc_inamb;
+  const int32_t* u_row; const int32_t* u_pos;
+} ss_host_layout;
+
+int ss_abi_version(void);
+
+/* one handle per (process, GPU) */
+int ss_create(int device, ss_handle_t* out);
+int ss_destroy(ss_handle_t h);
+const char* ss_last_error(ss_handle_t h);
+
+/* Build the tiled segment layout on the device.
+ * Replaces TelescopeLikelihood.__init__ (model.py:102-200: Q = expm1(100*s/s_max),
+ * Y_amb/Y_uni/Y_0, row weights, weight sums, pisum0) for EVERY model of a pooling
+ * mode at once, and the row selection of _fit_pooling_model (model.py:701-743).
+ *   row_ptr[n_rows+1], col_idx[nnz] (ascending within a row), score[nnz] (> 0):
+ *       the N x K uint16 CSR score matrix (st.corrected / st.raw_scores, model.py:749-758)
+ *   row_segment[n_rows]: model index of each row (cell, celltype, 0 for
+ *       pseudobulk), -1 = row belongs to no model.
+ * Synchronises the stream (sizes of the layout are data dependent). */
+int ss_layout_build(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, int64_t nnz,
+                    const int32_t* row_ptr, const int32_t* col_idx, const uint16_t* score,
+                    const int32_t* row_segment, int32_t n_segments);
+
+/* Debug / test: install a layout that was built on the host. Synchronous. */
+int ss_layout_import(ss_handle_t h, void* stream, const ss_host_layout* L);
+
+int ss_layout_get_info(ss_handle_t h, ss_layout_info* out);
+
+/* Copy one named layout array to a caller host buffer (tests: device builder
+ * vs format specification).  Returns the byte size in *bytes when dst_host is
+ * NULL. Synchronous. */
+int ss_layout_export(ss_handle_t h, const char* name, void* dst_host, int64_t* bytes);
+
+/* Run EM to convergence for every segment.
+ * Replaces TelescopeLikelihood.em (model.py:325-373) = estep (:202-226) + mstep
+ * (:229-272) + convergence (:340-355) + calculate_lnl (:276-323), for all models
+ * of _fit_pooling_model (:785-801) in one call. */
+int ss_em_fit(ss_handle_t h, void* stream, double em_epsilon, int32_t max_iter, double pi_prior,
+              double theta_prior, int32_t use_likelihood);
+
+/* Per-segment results of the last fit (any pointer may be NULL):
+ *   iters[S]  number of iterations (len(FitInfo.iterations), statistics.py:280)
+ *   flags[S]  bit0 converged, bit1 reached_max, bit2 model error (SS_ERR_MODEL class)
+ *   lnl[S]    FitInfo.final_lnl (model.py:368-370)
+ *   diffs[S*max_iter] diff_est trace (model.py:340, 359), unused slots = 0
+ *   lnls[S*max_iter]  lnL trace (only with use_likelihood)
+ *   nobs[S], nfeats[S]  FitInfo.nobs / nfeats (statistics.py:289-292) */
+int ss_em_get_results(ss_handle_t h, void* stream, int32_t* iters, int32_t* flags, double* lnl,
+                      double* diffs, double* lnls, int32_t* nobs, int32_t* nfeats);
+
+/* Per segment-column parameters of the last fit: for segment s the slots
+ * seg_col0[s] .. seg_col0[s]+seg_ncol[s]-1 hold the loci gcol[] (ascending)
+ * the model touches, their pi and theta; every other locus of that model has
+ * pi = pi_rest[s], theta = theta_rest[s].  (tl.pi / tl.theta, model.py:357) */
+int ss_em_get_params(ss_handle_t h, void* stream, int32_t* seg_col0, int32_t* seg_ncol, int32_t* gcol,
+                     double* pi, double* theta, double* pi_rest, double* theta_rest);
+
+/* Posterior matrix z of the last E-step in the CSR order of the input matrix
+ * (tl.z, model.py:356; ret_model.z += _z, :790).  Rows outside every model and
+ * empty rows get nothing (their entries do not exist). */
+int ss_em_emit_z(ss_handle_t h, void* stream, double* z /* nnz */);
+
+/* Reassignment pass (TelescopeLikelihood.reassign, model.py:375-507; binmax
+ * sparse_plus.py:134-178).  Works on the CSR order of the input matrix.
+ *   z        posterior (nnz) -- from ss_em_emit_z; ignored by the initial_* / total_hits modes
+ *   flag[nnz] out: 1 where the alignment is selected by the mode (for the two
+ *            *_random modes: 1 on every tied-best alignment; the host replays
+ *            numpy's PCG64 draws, sparse_plus.py:233-238)
+ *   nbest[n_rows] out: number of tied-best alignments of the row (0 for rows without)
+ *   info[4 + 64] out: assigned, ambiguous, unaligned, (reserved), histogram of
+ *            min(nbest, 63)  (ReassignInfo, statistics.py:410-462; model.py:437-440)
+ *   tie_tol  relative tolerance of "equal to the row maximum"; 0 = exact */
+int ss_reassign(ss_handle_t h, void* stream, int32_t mode, double conf_thresh, double tie_tol,
+                int32_t n_rows, const int32_t* row_ptr, const uint16_t* score, const double* z,
+                uint8_t* flag, int32_t* nbest, int64_t* info);
+
+/* Count aggregation (Stellarscope.output_report agg_bc / agg_bc_umi,
+ * model.py:1302-1345; groupby_sum sparse_plus.py:367-396).
+ *   flag/weight: the reassignment matrix in CSR order (weight NULL = 1 per flagged alignment)
+ *   row_cell[n_rows]: output barcode index of the row, -1 = drop
+ *   row_umi[n_rows] or NULL: UMI id of the row (umi_counts mode)
+ * Writes up to cap COO triples (cell, locus, value) sorted by (cell, locus);
+ * *n_out receives the number produced (host value, call synchronises). */
+int ss_count(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, const int32_t* row_ptr,
+             const int32_t* col_idx, const uint8_t* flag, const double* weight, const int32_t* row_cell,
+             const int32_t* row_umi, int64_t cap, int32_t* out_cell, int32_t* out_col, double* out_val,
+             int64_t* n_out);
+
+/* Pseudobulk over several GPUs: install a hook that all-reduces (SUM) a device
+ * buffer of `count` doubles in place on `stream`; the fit calls it once per
+ * iteration on the theta sums (model.py:239) and once at build time on the
+ * segment totals.  NULL removes the hook. */
+typedef int (*ss_allreduce_fn)(void* user, void* stream, double* buf, int64_t count, int32_t op /*0 sum, 1 max*/);
+int ss_set_allreduce(ss_handle_t h, ss_allreduce_fn fn, void* user);
+
+/* number of kernel launches issued by this handle since creation */
+int64_t ss_launch_count(ss_handle_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

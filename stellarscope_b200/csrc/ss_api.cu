@@ -1,0 +1,257 @@
+// extern "C" boundary (include/stellarscope_b200.h).
+#include <cstring>
+#include <new>
+
+#include "ss_handle.h"
+
+using namespace ss;
+
+#define SS_REQUIRE_HANDLE(h) \
+  if (!(h)) return SS_ERR_ARG
+
+extern "C" {
+
+int ss_abi_version(void) { return SS_ABI_VERSION; }
+
+int ss_create(int device, ss_handle_t* out) {
+  if (!out) return SS_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device < 0 || device >= ndev) return SS_ERR_CUDA;
+  ss_handle_s* h = new (std::nothrow) ss_handle_s();
+  if (!h) return SS_ERR_CUDA;
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    delete h;
+    return SS_ERR_CUDA;
+  }
+  int v = 0;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+  h->num_sms = v > 0 ? v : 148;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  h->max_smem_optin = (size_t)v;
+  *out = h;
+  return SS_OK;
+}
+
+int ss_destroy(ss_handle_t h) {
+  SS_REQUIRE_HANDLE(h);
+  cudaSetDevice(h->device);
+  free_fit(h);
+  free_layout(h);
+  delete h;
+  return SS_OK;
+}
+
+const char* ss_last_error(ss_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+
+int ss_layout_build(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, int64_t nnz, const int32_t* row_ptr,
+                    const int32_t* col_idx, const uint16_t* score, const int32_t* row_segment, int32_t n_segments) {
+  SS_REQUIRE_HANDLE(h);
+  if (n_rows < 0 || n_cols <= 0 || nnz < 0 || n_segments < 0 || !row_ptr || !row_segment ||
+      (nnz > 0 && (!col_idx || !score))) {
+    h->set_error("ss_layout_build: bad argument");
+    return SS_ERR_ARG;
+  }
+  if (n_cols > 65535 * 16) {
+    h->set_error("ss_layout_build: more than 1M loci not supported");
+    return SS_ERR_ARG;
+  }
+  cudaSetDevice(h->device);
+  return layout_build(h, (cudaStream_t)stream, n_rows, n_cols, nnz, row_ptr, col_idx, score, row_segment,
+                      n_segments);
+}
+
+int ss_layout_import(ss_handle_t h, void* stream, const ss_host_layout* L) {
+  SS_REQUIRE_HANDLE(h);
+  if (!L) {
+    h->set_error("ss_layout_import: null layout");
+    return SS_ERR_ARG;
+  }
+  cudaSetDevice(h->device);
+  return layout_import(h, (cudaStream_t)stream, L);
+}
+
+int ss_layout_get_info(ss_handle_t h, ss_layout_info* o) {
+  SS_REQUIRE_HANDLE(h);
+  if (!o || !h->has_layout) {
+    h->set_error("ss_layout_get_info: no layout");
+    return SS_ERR_STATE;
+  }
+  const Layout& L = h->L;
+  memset(o, 0, sizeof(*o));
+  o->n_rows = L.N; o->n_cols = L.K; o->n_segments = L.S; o->n_tiles = L.n_tiles;
+  o->max_row_len = L.maxlen; o->chunk = L.chunk; o->n_unique_rows = L.n_uniq;
+  o->n_stream_tiles = h->n_stream_tiles; o->n_stream_segments = h->n_stream_segs;
+  o->n_resident_tiles = L.n_tiles - h->n_stream_tiles;
+  o->nnz = L.A; o->n_segcols = L.n_segcols;
+  o->tot_ent = L.tot_ent; o->tot_row = L.tot_row; o->tot_col = L.tot_col; o->tot_jds = L.tot_jds;
+  o->nnz_ambiguous = h->nnz_amb; o->rows_ambiguous = h->rows_amb;
+  return SS_OK;
+}
+
+int ss_layout_export(ss_handle_t h, const char* name, void* dst, int64_t* bytes) {
+  SS_REQUIRE_HANDLE(h);
+  if (!h->has_layout || !name || !bytes) {
+    h->set_error("ss_layout_export: no layout / bad argument");
+    return SS_ERR_STATE;
+  }
+  const Layout& L = h->L;
+  struct Ent { const char* n; const void* p; size_t b; };
+  const size_t T = (size_t)L.n_tiles, S = (size_t)L.S, NC = (size_t)L.n_segcols;
+  const Ent table[] = {
+      {"tile_hdr", L.tile_hdr, T * HDR_WORDS * 8},
+      {"e_lcol", L.e_lcol, (size_t)L.tot_ent * 2}, {"e_cpos", L.e_cpos, (size_t)L.tot_ent * 2},
+      {"e_q", L.e_q, (size_t)L.tot_ent * 8}, {"e_opos", L.e_opos, (size_t)L.tot_ent * 4},
+      {"r_len", L.r_len, (size_t)L.tot_row * 2}, {"r_w", L.r_w, (size_t)L.tot_row * 8},
+      {"r_orow", L.r_orow, (size_t)L.tot_row * 4},
+      {"c_ptr", L.c_ptr, (size_t)L.tot_col * 2}, {"c_scol", L.c_scol, (size_t)L.tot_col * 4},
+      {"c_pisum0", L.c_pisum0, (size_t)L.tot_col * 8}, {"c_nuniq", L.c_nuniq, (size_t)L.tot_col * 4},
+      {"j_ptr", L.j_ptr, (size_t)L.tot_jds * 2},
+      {"seg_tile0", L.seg_tile0, S * 4}, {"seg_ntiles", L.seg_ntiles, S * 4}, {"seg_col0", L.seg_col0, S * 4},
+      {"seg_ncol", L.seg_ncol, S * 4}, {"seg_smax", L.seg_smax, S * 4}, {"seg_nobs", L.seg_nobs, S * 4},
+      {"seg_namb", L.seg_namb, S * 4}, {"seg_nuniq", L.seg_nuniq, S * 4}, {"seg_wmax", L.seg_wmax, S * 8},
+      {"seg_wtot", L.seg_wtot, S * 8}, {"seg_wamb", L.seg_wamb, S * 8}, {"seg_logq_uniq", L.seg_logq_uniq, S * 8},
+      {"seg_A", L.seg_A, S * 8}, {"seg_Aamb", L.seg_Aamb, S * 8},
+      {"sc_gcol", L.sc_gcol, NC * 4}, {"sc_pisum0", L.sc_pisum0, NC * 8}, {"sc_nuniq", L.sc_nuniq, NC * 4},
+      {"sc_inamb", h->sc_inamb, NC}, {"u_row", L.u_row, (size_t)L.n_uniq * 4}, {"u_pos", L.u_pos, (size_t)L.n_uniq * 4},
+  };
+  for (const Ent& e : table) {
+    if (strcmp(e.n, name) == 0) {
+      if (!dst) {
+        *bytes = (int64_t)e.b;
+        return SS_OK;
+      }
+      if ((size_t)*bytes < e.b) {
+        h->set_error("ss_layout_export: destination too small");
+        return SS_ERR_ARG;
+      }
+      *bytes = (int64_t)e.b;
+      cudaSetDevice(h->device);
+      if (e.b) SS_CUDA_CHECK(h, cudaMemcpy(dst, e.p, e.b, cudaMemcpyDeviceToHost));
+      return SS_OK;
+    }
+  }
+  h->set_error(std::string("ss_layout_export: unknown array ") + name);
+  return SS_ERR_ARG;
+}
+
+int ss_em_fit(ss_handle_t h, void* stream, double em_epsilon, int32_t max_iter, double pi_prior, double theta_prior,
+              int32_t use_likelihood) {
+  SS_REQUIRE_HANDLE(h);
+  cudaSetDevice(h->device);
+  FitParams P;
+  P.eps = em_epsilon;
+  P.max_iter = max_iter;
+  P.pi_prior = pi_prior;
+  P.theta_prior = theta_prior;
+  P.use_likelihood = use_likelihood ? 1 : 0;
+  P.K = h->L.K;
+  return em_fit(h, (cudaStream_t)stream, P);
+}
+
+#define COPY_OUT(dst, src, n, T)                                                                          \
+  if (dst) SS_CUDA_CHECK(h, cudaMemcpyAsync(dst, src, (size_t)(n) * sizeof(T), cudaMemcpyDeviceToDevice, st))
+
+int ss_em_get_results(ss_handle_t h, void* stream, int32_t* iters, int32_t* flags, double* lnl, double* diffs,
+                      double* lnls, int32_t* nobs, int32_t* nfeats) {
+  SS_REQUIRE_HANDLE(h);
+  if (!h->has_fit) {
+    h->set_error("ss_em_get_results: no fit");
+    return SS_ERR_STATE;
+  }
+  cudaSetDevice(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t S = (size_t)h->L.S;
+  COPY_OUT(iters, h->F.seg_iters, S, int);
+  COPY_OUT(flags, h->F.seg_flags, S, int);
+  COPY_OUT(lnl, h->F.seg_lnl, S, double);
+  COPY_OUT(diffs, h->F.seg_diffs, S * h->P.max_iter, double);
+  if (lnls) {
+    if (!h->F.seg_lnls) {
+      h->set_error("ss_em_get_results: lnL trace only exists with use_likelihood");
+      return SS_ERR_STATE;
+    }
+    COPY_OUT(lnls, h->F.seg_lnls, S * h->P.max_iter, double);
+  }
+  COPY_OUT(nobs, h->L.seg_nobs, S, int);
+  COPY_OUT(nfeats, h->L.seg_ncol, S, int);
+  return SS_OK;
+}
+
+__global__ void rest_params_kernel(int S, const double* thpw, const double* pipw, const double* inv_thd,
+                                   const double* inv_pid, double* pi_rest, double* theta_rest) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  if (pi_rest) pi_rest[s] = pipw[s] * inv_pid[s];
+  if (theta_rest) theta_rest[s] = thpw[s] * inv_thd[s];
+}
+
+int ss_em_get_params(ss_handle_t h, void* stream, int32_t* seg_col0, int32_t* seg_ncol, int32_t* gcol, double* pi,
+                     double* theta, double* pi_rest, double* theta_rest) {
+  SS_REQUIRE_HANDLE(h);
+  if (!h->has_fit) {
+    h->set_error("ss_em_get_params: no fit");
+    return SS_ERR_STATE;
+  }
+  cudaSetDevice(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t S = (size_t)h->L.S, NC = (size_t)h->L.n_segcols;
+  COPY_OUT(seg_col0, h->L.seg_col0, S, int);
+  COPY_OUT(seg_ncol, h->L.seg_ncol, S, int);
+  COPY_OUT(gcol, h->L.sc_gcol, NC, int);
+  COPY_OUT(pi, h->F.sc_pi, NC, double);
+  COPY_OUT(theta, h->F.sc_theta, NC, double);
+  if ((pi_rest || theta_rest) && S > 0) {
+    rest_params_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>((int)S, h->F.seg_thpw, h->F.seg_pipw,
+                                                                    h->F.seg_inv_thd, h->F.seg_inv_pid, pi_rest,
+                                                                    theta_rest);
+    h->launches++;
+    SS_CUDA_CHECK(h, cudaGetLastError());
+  }
+  return SS_OK;
+}
+
+int ss_em_emit_z(ss_handle_t h, void* stream, double* z) {
+  SS_REQUIRE_HANDLE(h);
+  if (!z) {
+    h->set_error("ss_em_emit_z: null buffer");
+    return SS_ERR_ARG;
+  }
+  cudaSetDevice(h->device);
+  return em_emit_z(h, (cudaStream_t)stream, z);
+}
+
+int ss_reassign(ss_handle_t h, void* stream, int32_t mode, double conf_thresh, double tie_tol, int32_t n_rows,
+                const int32_t* row_ptr, const uint16_t* score, const double* z, uint8_t* flag, int32_t* nbest,
+                int64_t* info) {
+  SS_REQUIRE_HANDLE(h);
+  cudaSetDevice(h->device);
+  return reassign(h, (cudaStream_t)stream, mode, conf_thresh, tie_tol, n_rows, row_ptr, score, z, flag, nbest,
+                  (long long*)info);
+}
+
+int ss_count(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, const int32_t* row_ptr,
+             const int32_t* col_idx, const uint8_t* flag, const double* weight, const int32_t* row_cell,
+             const int32_t* row_umi, int64_t cap, int32_t* out_cell, int32_t* out_col, double* out_val,
+             int64_t* n_out) {
+  SS_REQUIRE_HANDLE(h);
+  cudaSetDevice(h->device);
+  long long n = 0;
+  int rc = count(h, (cudaStream_t)stream, n_rows, n_cols, row_ptr, col_idx, flag, weight, row_cell, row_umi, cap,
+                 out_cell, out_col, out_val, &n);
+  if (n_out) *n_out = n;
+  return rc;
+}
+
+int ss_set_allreduce(ss_handle_t h, ss_allreduce_fn fn, void* user) {
+  SS_REQUIRE_HANDLE(h);
+  h->allreduce = fn;
+  h->allreduce_user = user;
+  return SS_OK;
+}
+
+int64_t ss_launch_count(ss_handle_t h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,694 @@
+// EM kernels: per-fit preparation, the resident kernel (one CTA owns a whole
+// segment and iterates to convergence out of shared memory), the streaming
+// kernel (cooperative grid, segments that span several tiles, iterates in
+// lockstep with an on-device convergence test), emit (final z + lnL) and the
+// per-segment finalisation.
+//
+// Reference being replaced: TelescopeLikelihood.em / estep / mstep /
+// calculate_lnl, stellarscope/utils/model.py:202-373.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "ss_em.cuh"
+#include "ss_handle.h"
+
+namespace cg = cooperative_groups;
+
+namespace ss {
+
+struct EmArgs {
+  Layout L;
+  FitState F;
+  FitParams P;
+  const int* tile_list;
+  int n_list;
+  double* z_out;
+};
+
+struct StreamArgs {
+  const int* tiles;
+  int n_tiles;
+  const int* segs;
+  int n_segs;
+  const int* col_seg;    // [n_cols] index into segs
+  const int* col_slot;   // [n_cols] absolute slot
+  long long n_cols;
+  int* ctl;              // [0] = number of active segments, [1 + i] = segment i done (iters)
+};
+
+// ---------------------------------------------------------------------------
+// prepare: per segment constants (model.py:189-194) and default parameters of
+// the columns no tile touches.  One warp per segment.
+// ---------------------------------------------------------------------------
+__global__ void fit_prepare_kernel(Layout L, FitState F, FitParams P, const int8_t* __restrict__ sc_inamb) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= L.S) return;
+  const int s = warp;
+  const double K = (double)P.K;
+  const double invK = 1.0 / K;
+  const double wmax = L.seg_wmax[s];
+  const double thpw = P.theta_prior * wmax;
+  const double pipw = P.pi_prior * wmax;
+  const double thd = L.seg_wamb[s] + thpw * K;
+  const double pid = L.seg_wtot[s] + pipw * K;
+  const bool bad = !(thd > 0.0) || !(pid > 0.0);
+  const double inv_thd = bad ? 0.0 : 1.0 / thd;
+  const double inv_pid = bad ? 0.0 : 1.0 / pid;
+  const int c0 = L.seg_col0[s], nc = L.seg_ncol[s];
+  const double th_rest = thpw * inv_thd;
+  const double pi_rest = pipw * inv_pid;
+  double d1 = 0.0, lx = 0.0;
+  for (int j = lane; j < nc; j += 32) {
+    const int slot = c0 + j;
+    const double p1 = (L.sc_pisum0[slot] + pipw) * inv_pid;
+    F.sc_pi[slot] = p1;
+    F.sc_theta[slot] = th_rest;
+    F.sc_ptprev[slot] = invK * invK;
+    F.sc_ptfin[slot] = p1 * th_rest;
+    F.sc_pt[0][slot] = invK * invK;
+    F.sc_pt[1][slot] = invK * invK;
+    F.sc_T[slot] = 0.0;
+    if (!sc_inamb[slot]) {
+      d1 += fabs(p1 - invK);
+      const int nu = L.sc_nuniq[slot];
+      if (nu > 0 && p1 > 0.0) lx += (double)nu * log(p1);
+    }
+  }
+  d1 = warp_sum(d1);
+  lx = warp_sum(lx);
+  if (lane == 0) {
+    d1 += (K - (double)nc) * fabs(pi_rest - invK);
+    F.seg_thpw[s] = thpw;
+    F.seg_pipw[s] = pipw;
+    F.seg_inv_thd[s] = inv_thd;
+    F.seg_inv_pid[s] = inv_pid;
+    F.seg_diff1_extra[s] = d1;
+    F.seg_lnl_extra[s] = lx + L.seg_logq_uniq[s];
+    F.seg_diffacc[s] = 0.0;
+    F.seg_lnl[s] = 0.0;
+    F.seg_iters[s] = 0;
+    F.seg_flags[s] = bad ? 4 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// resident kernel: one CTA per single-tile segment
+// ---------------------------------------------------------------------------
+template <int THREADS, bool LNL>
+__global__ void __launch_bounds__(THREADS) em_resident_kernel(EmArgs a) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  __shared__ double s_red[32];
+  __shared__ uint64_t s_bar;
+  constexpr int NW = THREADS / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t = a.tile_list[blockIdx.x];
+  const TileView v = load_tile_view(a.L.tile_hdr, t);
+  TileSmem s = carve_tile(dsm, v, LNL);
+  const int seg = v.seg;
+
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) tile_issue_loads(a.L, v, s, &s_bar);
+
+  const double invK = 1.0 / (double)a.P.K;       // model.py:164,172
+  for (int c = tid; c < v.ncol; c += THREADS) {
+    s.aux[c] = invK;
+    s.pt[c] = invK * invK;
+  }
+  const double thpw = a.F.seg_thpw[seg], pipw = a.F.seg_pipw[seg];
+  const double inv_thd = a.F.seg_inv_thd[seg], inv_pid = a.F.seg_inv_pid[seg];
+  const double diff1_extra = a.F.seg_diff1_extra[seg];
+  const double lnl_extra = a.F.seg_lnl_extra[seg];
+  const double eps = a.P.eps;
+  const int max_iter = a.P.max_iter;
+  const double* __restrict__ ps0 = a.L.c_pisum0 + v.co;
+  const int* __restrict__ nuq = a.L.c_nuniq + v.co;
+  const int* __restrict__ scol = a.L.c_scol + v.co;
+  double* diffs = a.F.seg_diffs + (long long)seg * max_iter;
+  double* lnls = a.F.seg_lnls ? a.F.seg_lnls + (long long)seg * max_iter : nullptr;
+  mbar_wait(&s_bar, 0);
+  __syncthreads();
+
+  double* pt_cur = s.pt;
+  double* pt_nxt = LNL ? s.pt2 : s.pt;
+  double lnl_prev = INFINITY, lnl_amb = 0.0;
+  int it = 0;
+  bool done = false, conv = false;
+  while (!done) {
+    ++it;
+    tile_phase_a<THREADS>(v, s, pt_cur);
+    __syncthreads();
+    // ---- phase B: thetasum per tile column, new pi, |delta pi| ----
+    double dsum = 0.0;
+    for (int c = warp; c < v.nlong; c += NW) {
+      const double asum = tile_col_sum_warp(s, c, lane);
+      if (lane == 0) {
+        const double T = pt_cur[c] * asum;
+        const double pn = (ps0[c] + T + pipw) * inv_pid;
+        dsum += fabs(pn - s.aux[c]);
+        s.val[s.cptr[c]] = T;
+      }
+    }
+    for (int c = v.nlong + tid; c < v.ncol; c += THREADS) {
+      const double T = pt_cur[c] * tile_col_sum_thread(s, c);
+      const double pn = (ps0[c] + T + pipw) * inv_pid;
+      dsum += fabs(pn - s.aux[c]);
+      s.val[s.cptr[c]] = T;
+    }
+    double diff = block_sum<THREADS>(dsum, s_red);      // contains the barrier that publishes val[]
+    if (it == 1) diff += diff1_extra;
+    const bool reached = it >= max_iter;
+    if (!LNL) {
+      conv = diff < eps;                                 // model.py:351
+      done = conv || reached;
+    }
+    // ---- pass 2: commit pi, theta, x = pi*theta ----
+    if (LNL || !done) {
+      for (int c = tid; c < v.ncol; c += THREADS) {
+        const double T = s.val[s.cptr[c]];
+        const double th = (T + thpw) * inv_thd;
+        const double pn = (ps0[c] + T + pipw) * inv_pid;
+        s.aux[c] = pn;
+        pt_nxt[c] = pn * th;
+      }
+    }
+    if (LNL) {
+      __syncthreads();
+      // lnL with the E-step's z (old x) and the new parameters: model.py:344
+      double l = tile_lnl_pass<THREADS>(v, s, pt_cur, pt_nxt, true, nullptr, nullptr);
+      for (int c = tid; c < v.ncol; c += THREADS) {
+        const int nu = nuq[c];
+        const double pn = s.aux[c];
+        if (nu > 0 && pn > 0.0) l += (double)nu * log(pn);
+      }
+      lnl_amb = block_sum<THREADS>(l, s_red);
+      const double lnl = lnl_amb + lnl_extra;
+      conv = fabs(lnl - lnl_prev) < eps;                 // model.py:345-347
+      lnl_prev = lnl;
+      done = conv || reached;
+      if (tid == 0 && lnls) lnls[it - 1] = lnl;
+    }
+    if (tid == 0) diffs[it - 1] = diff;
+    if (!done) {
+      if (LNL) { double* tmp = pt_cur; pt_cur = pt_nxt; pt_nxt = tmp; }
+      __syncthreads();
+    }
+  }
+  // ---- converged / reached max: publish parameters, final lnL, z ----
+  // non-LNL: pt_cur still holds the x of the last E-step, val[cptr[c]] the last T.
+  double* ptfin = LNL ? pt_nxt : s.aux;
+  for (int c = tid; c < v.ncol; c += THREADS) {
+    const int slot = scol[c];
+    double pn, th;
+    if (LNL) {
+      pn = s.aux[c];
+      const double T = s.val[s.cptr[c]];
+      th = (T + thpw) * inv_thd;
+    } else {
+      const double T = s.val[s.cptr[c]];
+      th = (T + thpw) * inv_thd;
+      pn = (ps0[c] + T + pipw) * inv_pid;
+      s.aux[c] = pn * th;
+    }
+    a.F.sc_pi[slot] = pn;
+    a.F.sc_theta[slot] = th;
+    a.F.sc_ptprev[slot] = pt_cur[c];
+    a.F.sc_ptfin[slot] = pn * th;
+  }
+  __syncthreads();
+  double l = 0.0;
+  if (!LNL || a.z_out) {
+    l = tile_lnl_pass<THREADS>(v, s, pt_cur, ptfin, !LNL, a.z_out, a.L.e_opos + v.eo);
+  }
+  if (!LNL) {
+    l = block_sum<THREADS>(l, s_red);
+  } else {
+    // tile_lnl holds the ambiguous-row part only; the unique-row part is added by finalize
+    double lu = 0.0;
+    for (int c = tid; c < v.ncol; c += THREADS) {
+      const int nu = nuq[c];
+      const double pn = a.F.sc_pi[scol[c]];
+      if (nu > 0 && pn > 0.0) lu += (double)nu * log(pn);
+    }
+    lu = block_sum<THREADS>(lu, s_red);
+    l = lnl_amb - lu;
+  }
+  if (tid == 0) {
+    a.F.tile_lnl[t] = l;
+    a.F.seg_iters[seg] = it;
+    a.F.seg_flags[seg] = (conv ? 1 : 0) | (it >= max_iter ? 2 : 0);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// streaming kernel: cooperative grid over the tiles of multi-tile segments
+// ---------------------------------------------------------------------------
+template <int THREADS, bool LNL>
+__global__ void __launch_bounds__(THREADS) em_stream_kernel(EmArgs a, StreamArgs sa) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  __shared__ double s_red[32];
+  __shared__ uint64_t s_bar;
+  constexpr int NW = THREADS / 32;
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long gtid = (long long)blockIdx.x * THREADS + tid;
+  const long long gthreads = (long long)gridDim.x * THREADS;
+  const int max_iter = a.P.max_iter;
+  const double eps = a.P.eps;
+  uint32_t phase = 0;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  for (int it = 1; it <= max_iter; ++it) {
+    const int cur = (it - 1) & 1;
+    const double* __restrict__ ptg = a.F.sc_pt[cur];
+    // ---- tile pass: phase A + B, partial thetasum -> global accumulators ----
+    for (int i = blockIdx.x; i < sa.n_tiles; i += gridDim.x) {
+      const int t = sa.tiles[i];
+      const TileView v = load_tile_view(a.L.tile_hdr, t);
+      if (a.F.seg_iters[v.seg] != 0) continue;           // segment already finished
+      TileSmem s = carve_tile(dsm, v, false);
+      if (tid == 0) {
+        fence_proxy_async();
+        tile_issue_loads(a.L, v, s, &s_bar);
+      }
+      const int* __restrict__ scol = a.L.c_scol + v.co;
+      for (int c = tid; c < v.ncol; c += THREADS) s.pt[c] = ptg[scol[c]];
+      mbar_wait(&s_bar, phase);
+      phase ^= 1;
+      __syncthreads();
+      tile_phase_a<THREADS>(v, s, s.pt);
+      __syncthreads();
+      for (int c = warp; c < v.nlong; c += NW) {
+        const double asum = tile_col_sum_warp(s, c, lane);
+        if (lane == 0) atomicAdd(&a.F.sc_T[scol[c]], s.pt[c] * asum);
+      }
+      for (int c = v.nlong + tid; c < v.ncol; c += THREADS)
+        atomicAdd(&a.F.sc_T[scol[c]], s.pt[c] * tile_col_sum_thread(s, c));
+      __syncthreads();                                    // smem is reused by the next tile
+    }
+    grid.sync();
+    // ---- update pass over the columns of the active multi-tile segments ----
+    double* __restrict__ ptn = a.F.sc_pt[cur ^ 1];
+    for (long long x0 = (long long)blockIdx.x * THREADS; x0 < sa.n_cols; x0 += gthreads) {
+      const long long x = x0 + tid;
+      double d = 0.0;
+      int si = -1;
+      if (x < sa.n_cols) {
+        si = sa.col_seg[x];
+        const int seg = sa.segs[si];
+        if (a.F.seg_iters[seg] == 0) {
+          const int slot = sa.col_slot[x];
+          const double T = a.F.sc_T[slot];
+          const double th = (T + a.F.seg_thpw[seg]) * a.F.seg_inv_thd[seg];
+          const double pn = (a.L.sc_pisum0[slot] + T + a.F.seg_pipw[seg]) * a.F.seg_inv_pid[seg];
+          // pi of the previous iteration; pi_0 = 1/K for every locus (model.py:164)
+          const double pold = it == 1 ? 1.0 / (double)a.P.K : a.F.sc_pi[slot];
+          d = fabs(pn - pold);
+          a.F.sc_pi[slot] = pn;
+          a.F.sc_theta[slot] = th;
+          ptn[slot] = pn * th;
+          a.F.sc_T[slot] = 0.0;
+        } else {
+          si = -1;
+        }
+      }
+      // warp-aggregate when the whole warp works on one segment
+      const int s0 = __shfl_sync(0xffffffffu, si, 0);
+      if (__all_sync(0xffffffffu, si == s0)) {
+        d = warp_sum(d);
+        if (lane == 0 && s0 >= 0) atomicAdd(&a.F.seg_diffacc[sa.segs[s0]], d);
+      } else if (si >= 0) {
+        atomicAdd(&a.F.seg_diffacc[sa.segs[si]], d);
+      }
+    }
+    grid.sync();
+    if (LNL) {
+      // second tile pass: lnL with z from x_cur and the parameters x_next
+      for (int i = blockIdx.x; i < sa.n_tiles; i += gridDim.x) {
+        const int t = sa.tiles[i];
+        const TileView v = load_tile_view(a.L.tile_hdr, t);
+        if (a.F.seg_iters[v.seg] != 0) continue;
+        TileSmem s = carve_tile(dsm, v, true);
+        if (tid == 0) {
+          fence_proxy_async();
+          tile_issue_loads(a.L, v, s, &s_bar);
+        }
+        const int* __restrict__ scol = a.L.c_scol + v.co;
+        for (int c = tid; c < v.ncol; c += THREADS) {
+          s.pt[c] = ptg[scol[c]];
+          s.pt2[c] = ptn[scol[c]];
+        }
+        mbar_wait(&s_bar, phase);
+        phase ^= 1;
+        __syncthreads();
+        double l = tile_lnl_pass<THREADS>(v, s, s.pt, s.pt2, true, nullptr, nullptr);
+        l = block_sum<THREADS>(l, s_red);
+        if (tid == 0) atomicAdd(&a.F.seg_lnl[v.seg], l);
+        __syncthreads();
+      }
+      // unique-row part over the columns
+      for (long long x = gtid; x < sa.n_cols; x += gthreads) {
+        const int seg = sa.segs[sa.col_seg[x]];
+        if (a.F.seg_iters[seg] != 0) continue;
+        const int slot = sa.col_slot[x];
+        const int nu = a.L.sc_nuniq[slot];
+        const double pn = a.F.sc_pi[slot];
+        if (nu > 0 && pn > 0.0) atomicAdd(&a.F.seg_lnl[seg], (double)nu * log(pn));
+      }
+      grid.sync();
+    }
+    // ---- convergence decision, one thread per segment (block 0 only) ----
+    if (blockIdx.x == 0) {
+      int still = 0;
+      for (int i = tid; i < sa.n_segs; i += THREADS) {
+        const int seg = sa.segs[i];
+        if (a.F.seg_iters[seg] != 0) continue;
+        double diff = a.F.seg_diffacc[seg];
+        a.F.seg_diffacc[seg] = 0.0;
+        if (it == 1) diff += a.F.seg_diff1_extra[seg];
+        a.F.seg_diffs[(long long)seg * max_iter + it - 1] = diff;
+        bool conv;
+        if (LNL) {
+          const double lnl = a.F.seg_lnl[seg] + a.L.seg_logq_uniq[seg];
+          const double prev = it == 1 ? INFINITY : a.F.seg_lnls[(long long)seg * max_iter + it - 2];
+          a.F.seg_lnls[(long long)seg * max_iter + it - 1] = lnl;
+          conv = fabs(lnl - prev) < eps;
+          a.F.seg_lnl[seg] = 0.0;
+        } else {
+          conv = diff < eps;
+        }
+        const bool reached = it >= max_iter;
+        if (conv || reached) {
+          a.F.seg_flags[seg] = (conv ? 1 : 0) | (reached ? 2 : 0);
+          a.F.seg_iters[seg] = it;
+        } else {
+          ++still;
+        }
+      }
+      still = __syncthreads_count(still);
+      if (tid == 0) sa.ctl[0] = still;
+    }
+    grid.sync();
+    if (*((volatile int*)sa.ctl) == 0) break;
+  }
+}
+
+// freeze x_prev / x_final of the multi-tile segments (buffer parity = iteration count)
+__global__ void stream_freeze_kernel(FitState F, StreamArgs sa) {
+  const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= sa.n_cols) return;
+  const int seg = sa.segs[sa.col_seg[x]];
+  const int slot = sa.col_slot[x];
+  const int it = F.seg_iters[seg];
+  F.sc_ptprev[slot] = F.sc_pt[(it - 1) & 1][slot];
+  F.sc_ptfin[slot] = F.sc_pt[it & 1][slot];
+}
+
+// emit for streamed tiles: final lnL part (+ z) from x_prev / x_final
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) emit_tiles_kernel(EmArgs a, int want_lnl) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  __shared__ double s_red[32];
+  __shared__ uint64_t s_bar;
+  const int tid = threadIdx.x;
+  const int t = a.tile_list[blockIdx.x];
+  const TileView v = load_tile_view(a.L.tile_hdr, t);
+  TileSmem s = carve_tile(dsm, v, true);
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) tile_issue_loads(a.L, v, s, &s_bar);
+  const int* __restrict__ scol = a.L.c_scol + v.co;
+  for (int c = tid; c < v.ncol; c += THREADS) {
+    s.pt[c] = a.F.sc_ptprev[scol[c]];
+    s.pt2[c] = a.F.sc_ptfin[scol[c]];
+  }
+  mbar_wait(&s_bar, 0);
+  __syncthreads();
+  double l = tile_lnl_pass<THREADS>(v, s, s.pt, s.pt2, want_lnl != 0, a.z_out, a.L.e_opos + v.eo);
+  if (want_lnl) {
+    l = block_sum<THREADS>(l, s_red);
+    if (tid == 0) a.F.tile_lnl[t] = l;
+  }
+}
+
+// z of unique rows: u * (1/u) (norm(1), sparse_plus.py:64) -- 1 up to rounding; 0 if pi_j == 0
+__global__ void emit_unique_kernel(Layout L, double* __restrict__ z_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L.n_uniq) return;
+  z_out[L.u_pos[i]] = 1.0;
+}
+
+// per segment: final lnL = sum of tile parts + unique-row part; segments without tiles
+// (no ambiguous rows) are solved in closed form.  One warp per segment.
+__global__ void fit_finalize_kernel(Layout L, FitState F, FitParams P) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= L.S) return;
+  const int s = warp;
+  if (F.seg_flags[s] & 4) return;
+  const int nt = L.seg_ntiles[s], t0 = L.seg_tile0[s];
+  const int c0 = L.seg_col0[s], nc = L.seg_ncol[s];
+  double l = 0.0;
+  for (int j = lane; j < nc; j += 32) {
+    const int nu = L.sc_nuniq[c0 + j];
+    const double p = F.sc_pi[c0 + j];
+    if (nu > 0 && p > 0.0) l += (double)nu * log(p);
+  }
+  l = warp_sum(l);
+  double lt = 0.0;
+  for (int t = lane; t < nt; t += 32) lt += F.tile_lnl[t0 + t];
+  lt = warp_sum(lt);
+  if (lane == 0) {
+    F.seg_lnl[s] = lt + l + L.seg_logq_uniq[s];
+    if (nt == 0) {
+      // T = 0 in every iteration: pi is constant after iteration 1
+      const double d1 = F.seg_diff1_extra[s];
+      double* diffs = F.seg_diffs + (long long)s * P.max_iter;
+      int it = 1;
+      bool conv;
+      if (P.use_likelihood) {
+        // lnL is the same in iterations 1 and 2 -> converged at 2
+        double* lnls = F.seg_lnls + (long long)s * P.max_iter;
+        diffs[0] = d1;
+        lnls[0] = F.seg_lnl[s];
+        conv = false;
+        while (!conv && it < P.max_iter) {
+          ++it;
+          diffs[it - 1] = 0.0;
+          lnls[it - 1] = F.seg_lnl[s];
+          conv = 0.0 < P.eps;
+        }
+      } else {
+        diffs[0] = d1;
+        conv = d1 < P.eps;
+        while (!conv && it < P.max_iter) {
+          ++it;
+          diffs[it - 1] = 0.0;
+          conv = 0.0 < P.eps;
+        }
+      }
+      F.seg_iters[s] = it;
+      F.seg_flags[s] = (conv ? 1 : 0) | (it >= P.max_iter ? 2 : 0);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+void free_fit(ss_handle_s* h) {
+  for (void* p : h->fit_allocs) cudaFree(p);
+  h->fit_allocs.clear();
+  h->F = FitState();
+  h->stream_ctl = nullptr;
+  h->has_fit = false;
+}
+
+
+template <int THREADS>
+static cudaError_t launch_resident(ss_handle_s* h, cudaStream_t st, const EmArgs& a, int n, size_t smem, bool lnl) {
+  if (n == 0) return cudaSuccess;
+  cudaError_t e;
+  if (lnl) {
+    e = cudaFuncSetAttribute(em_resident_kernel<THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    em_resident_kernel<THREADS, true><<<n, THREADS, smem, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(em_resident_kernel<THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    em_resident_kernel<THREADS, false><<<n, THREADS, smem, st>>>(a);
+  }
+  h->launches++;
+  return cudaGetLastError();
+}
+
+constexpr int STREAM_THREADS = 512;
+
+int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
+  if (!h->has_layout) {
+    h->set_error("ss_em_fit: no layout (call ss_layout_build first)");
+    return SS_ERR_STATE;
+  }
+  if (P.max_iter < 1 || !(P.eps == P.eps)) {
+    h->set_error("ss_em_fit: max_iter must be >= 1 and em_epsilon a number");
+    return SS_ERR_ARG;
+  }
+  free_fit(h);
+  Layout& L = h->L;
+  FitState& F = h->F;
+  const size_t S = (size_t)L.S, NC = (size_t)L.n_segcols, MI = (size_t)P.max_iter;
+  auto& pool = h->fit_allocs;
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_thpw, S));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_pipw, S));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_inv_thd, S));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_inv_pid, S));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_diff1_extra, S));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_lnl_extra, S));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_pi, NC));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_pt[0], NC));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_pt[1], NC));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_ptprev, NC));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_ptfin, NC));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_theta, NC));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_T, NC));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_iters, S));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_flags, S));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_lnl, S));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_diffs, S * MI));
+  SS_CUDA_CHECK(h, cudaMemsetAsync(F.seg_diffs, 0, S * MI * sizeof(double), st));
+  if (P.use_likelihood) {
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_lnls, S * MI));
+    SS_CUDA_CHECK(h, cudaMemsetAsync(F.seg_lnls, 0, S * MI * sizeof(double), st));
+  }
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_diffacc, S));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &F.tile_lnl, (size_t)L.n_tiles));
+  SS_CUDA_CHECK(h, cudaMemsetAsync(F.tile_lnl, 0, (size_t)std::max(1, L.n_tiles) * sizeof(double), st));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &h->stream_ctl, 4));
+  h->P = P;
+  h->P.K = L.K;
+
+  if (L.S > 0) {
+    const int warps_per_block = 8;
+    fit_prepare_kernel<<<(L.S + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+        L, F, h->P, h->sc_inamb);
+    h->launches++;
+    SS_CUDA_CHECK(h, cudaGetLastError());
+  }
+
+  EmArgs a;
+  a.L = L;
+  a.F = F;
+  a.P = h->P;
+  a.z_out = nullptr;
+  const bool lnl = P.use_likelihood != 0;
+
+  // streaming kernel first (long running, cooperative), then the resident classes
+  if (h->n_stream_tiles > 0) {
+    StreamArgs sa;
+    sa.tiles = h->stream_tiles;
+    sa.n_tiles = h->n_stream_tiles;
+    sa.segs = h->stream_segs;
+    sa.n_segs = h->n_stream_segs;
+    sa.col_seg = h->stream_col_seg;
+    sa.col_slot = h->stream_col_slot;
+    sa.n_cols = h->n_stream_cols;
+    sa.ctl = h->stream_ctl;
+    SS_CUDA_CHECK(h, cudaMemsetAsync(h->stream_ctl, 0, 4 * sizeof(int), st));
+    const size_t smem = h->stream_smem[lnl ? 1 : 0];
+    void* fn = lnl ? (void*)em_stream_kernel<STREAM_THREADS, true> : (void*)em_stream_kernel<STREAM_THREADS, false>;
+    SS_CUDA_CHECK(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    SS_CUDA_CHECK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, STREAM_THREADS, smem));
+    if (occ < 1) {
+      h->set_error("streaming kernel does not fit on an SM");
+      return SS_ERR_CAPACITY;
+    }
+    int grid = std::min(h->n_stream_tiles, occ * h->num_sms);
+    a.tile_list = h->stream_tiles;
+    a.n_list = h->n_stream_tiles;
+    void* args[] = {(void*)&a, (void*)&sa};
+    SS_CUDA_CHECK(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(STREAM_THREADS), args, smem, st));
+    h->launches++;
+    stream_freeze_kernel<<<(unsigned)((h->n_stream_cols + 255) / 256), 256, 0, st>>>(F, sa);
+    h->launches++;
+    SS_CUDA_CHECK(h, cudaGetLastError());
+  }
+  for (int c = SS_NUM_CLASSES - 1; c >= 0; --c) {
+    a.tile_list = h->cls_tiles[c];
+    a.n_list = h->cls_count[c];
+    const size_t smem = h->cls_smem[c][lnl ? 1 : 0];
+    cudaError_t e = cudaSuccess;
+    switch (c) {
+      case 0: e = launch_resident<128>(h, st, a, h->cls_count[c], smem, lnl); break;
+      case 1: e = launch_resident<256>(h, st, a, h->cls_count[c], smem, lnl); break;
+      case 2: e = launch_resident<512>(h, st, a, h->cls_count[c], smem, lnl); break;
+      default: e = launch_resident<1024>(h, st, a, h->cls_count[c], smem, lnl); break;
+    }
+    SS_CUDA_CHECK(h, e);
+  }
+  // final lnL of the streamed tiles (not needed in likelihood mode: the trace has it)
+  if (h->n_stream_tiles > 0) {
+    a.tile_list = h->stream_tiles;
+    a.n_list = h->n_stream_tiles;
+    const size_t smem = h->stream_smem[1];
+    SS_CUDA_CHECK(h, cudaFuncSetAttribute(emit_tiles_kernel<STREAM_THREADS>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    emit_tiles_kernel<STREAM_THREADS><<<h->n_stream_tiles, STREAM_THREADS, smem, st>>>(a, 1);
+    h->launches++;
+    SS_CUDA_CHECK(h, cudaGetLastError());
+  }
+  if (L.S > 0) {
+    const int warps_per_block = 8;
+    fit_finalize_kernel<<<(L.S + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(L, F, h->P);
+    h->launches++;
+    SS_CUDA_CHECK(h, cudaGetLastError());
+  }
+  h->has_fit = true;
+  return SS_OK;
+}
+
+// z in the CSR order of the input matrix
+int em_emit_z(ss_handle_s* h, cudaStream_t st, double* z) {
+  if (!h->has_fit) {
+    h->set_error("ss_em_emit_z: no fit");
+    return SS_ERR_STATE;
+  }
+  Layout& L = h->L;
+  SS_CUDA_CHECK(h, cudaMemsetAsync(z, 0, (size_t)L.A * sizeof(double), st));
+  if (L.n_tiles > 0) {
+    EmArgs a;
+    a.L = L;
+    a.F = h->F;
+    a.P = h->P;
+    a.z_out = z;
+    a.tile_list = h->all_tiles;
+    a.n_list = L.n_tiles;
+    const size_t smem = h->all_smem;
+    SS_CUDA_CHECK(h, cudaFuncSetAttribute(emit_tiles_kernel<STREAM_THREADS>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    emit_tiles_kernel<STREAM_THREADS><<<L.n_tiles, STREAM_THREADS, smem, st>>>(a, 0);
+    h->launches++;
+    SS_CUDA_CHECK(h, cudaGetLastError());
+  }
+  if (L.n_uniq > 0) {
+    emit_unique_kernel<<<(L.n_uniq + 255) / 256, 256, 0, st>>>(L, z);
+    h->launches++;
+    SS_CUDA_CHECK(h, cudaGetLastError());
+  }
+  return SS_OK;
+}
+
+}  // namespace ss

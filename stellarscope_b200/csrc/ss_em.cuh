@@ -1,0 +1,173 @@
+// Tile-level E+M primitives shared by the resident and the streaming kernels.
+//
+// One EM iteration of a tile (reference: TelescopeLikelihood.estep model.py:207-210,
+// mstep :236-246), with x_j = pi_j * theta_j taken from `pt`:
+//   phase A (row pass, one thread per JDS row):
+//       r_i  = sum_j Q_ij x_j                      (row sum of the un-normalised E-step)
+//       s_i  = w_i / r_i                           (w_i = max_j Q_ij, model.py:183)
+//       val[cpos(i,j)] = Q_ij s_i                  (= w_i z_ij / x_j, scattered to column-major order)
+//   phase B (column pass, one thread -- or one warp for long columns -- per tile column):
+//       T_j  = x_j * sum_i val[i,j]                (= sum_i w_i z_ij = thetasum_j, model.py:239)
+// Every sum runs in a fixed order that depends only on the sparsity pattern, so two
+// loci that always co-occur with equal scores get bit-identical T.
+#pragma once
+#include "ss_common.cuh"
+
+namespace ss {
+
+struct TileView {
+  int seg, nrows, nent, ncol, maxlen, nlong;
+  int pe, pr, pc, pj;
+  long long eo, ro, co, jo;
+};
+
+__device__ __forceinline__ TileView load_tile_view(const long long* __restrict__ tile_hdr, int t) {
+  const long long* h = tile_hdr + (long long)HDR_WORDS * t;
+  TileView v;
+  v.seg = (int)h[H_SEG];
+  v.nrows = (int)h[H_NROWS];
+  v.nent = (int)h[H_NENT];
+  v.ncol = (int)h[H_NCOL];
+  v.maxlen = (int)h[H_MAXLEN];
+  v.nlong = (int)h[H_NLONG];
+  v.eo = h[H_ENT_OFF];
+  v.ro = h[H_ROW_OFF];
+  v.co = h[H_COL_OFF];
+  v.jo = h[H_JDS_OFF];
+  v.pe = pad8(v.nent);
+  v.pr = pad8(v.nrows);
+  v.pc = pad8(v.ncol + 1);
+  v.pj = pad8(v.maxlen + 1);
+  return v;
+}
+
+// shared-memory image of a tile
+struct TileSmem {
+  double* q;       // pe  alignment weights Q_ij, JDS order
+  double* val;     // pe  scratch, column-major order
+  double* w;       // pr  row weights
+  double* pt;      // pc  x_j of the current E-step
+  double* aux;     // pc  resident: pi_j ; streaming: unused
+  double* pt2;     // pc  (likelihood mode) x_j after the M-step
+  uint16_t* lcol;  // pe  tile-local column of each alignment
+  uint16_t* cpos;  // pe  column-major slot of each alignment
+  uint16_t* rlen;  // pr
+  uint16_t* cptr;  // pc  column-major start of each tile column (ncol+1 used)
+  uint16_t* jptr;  // pj  JDS start of each in-row position (maxlen+1 used)
+};
+
+__host__ __device__ inline size_t tile_smem_bytes(int nent, int nrows, int ncol, int maxlen, bool lnl) {
+  const size_t pe = pad8(nent), pr = pad8(nrows), pc = pad8(ncol + 1), pj = pad8(maxlen + 1);
+  return 8 * (2 * pe + pr + 2 * pc + (lnl ? pc : 0)) + 2 * (2 * pe + pr + pc + pj);
+}
+
+__device__ __forceinline__ TileSmem carve_tile(unsigned char* base, const TileView& v, bool lnl) {
+  TileSmem s;
+  double* d = reinterpret_cast<double*>(base);
+  s.q = d;            d += v.pe;
+  s.val = d;          d += v.pe;
+  s.w = d;            d += v.pr;
+  s.pt = d;           d += v.pc;
+  s.aux = d;          d += v.pc;
+  s.pt2 = d;          if (lnl) d += v.pc;
+  uint16_t* u = reinterpret_cast<uint16_t*>(d);
+  s.lcol = u;         u += v.pe;
+  s.cpos = u;         u += v.pe;
+  s.rlen = u;         u += v.pr;
+  s.cptr = u;         u += v.pc;
+  s.jptr = u;
+  return s;
+}
+
+// issue the TMA bulk copies of a tile's read-only arrays (one thread)
+__device__ __forceinline__ void tile_issue_loads(const Layout& L, const TileView& v, const TileSmem& s,
+                                                 uint64_t* bar) {
+  const uint32_t bytes = 8u * v.pe + 8u * v.pr + 2u * (2u * v.pe + v.pr + v.pc + v.pj);
+  mbar_expect_tx(bar, bytes);
+  bulk_g2s(s.q, L.e_q + v.eo, 8u * v.pe, bar);
+  bulk_g2s(s.w, L.r_w + v.ro, 8u * v.pr, bar);
+  bulk_g2s(s.lcol, L.e_lcol + v.eo, 2u * v.pe, bar);
+  bulk_g2s(s.cpos, L.e_cpos + v.eo, 2u * v.pe, bar);
+  bulk_g2s(s.rlen, L.r_len + v.ro, 2u * v.pr, bar);
+  bulk_g2s(s.cptr, L.c_ptr + v.co, 2u * v.pc, bar);
+  bulk_g2s(s.jptr, L.j_ptr + v.jo, 2u * v.pj, bar);
+}
+
+// phase A: row pass
+template <int THREADS>
+__device__ __forceinline__ void tile_phase_a(const TileView& v, const TileSmem& s, const double* __restrict__ pt) {
+  for (int r = threadIdx.x; r < v.nrows; r += THREADS) {
+    const int len = s.rlen[r];
+    double acc = 0.0;
+    for (int p = 0; p < len; ++p) {
+      const int e = s.jptr[p] + r;
+      acc = fma(s.q[e], pt[s.lcol[e]], acc);
+    }
+    const double sc = acc > 0.0 ? s.w[r] * (1.0 / acc) : 0.0;
+    for (int p = 0; p < len; ++p) {
+      const int e = s.jptr[p] + r;
+      s.val[s.cpos[e]] = s.q[e] * sc;
+    }
+  }
+}
+
+// phase B helper: sum of the column-major slots of tile column c
+__device__ __forceinline__ double tile_col_sum_thread(const TileSmem& s, int c) {
+  const int b = s.cptr[c], e = s.cptr[c + 1];
+  double a = 0.0;
+  for (int k = b; k < e; ++k) a += s.val[k];
+  return a;
+}
+__device__ __forceinline__ double tile_col_sum_warp(const TileSmem& s, int c, int lane) {
+  const int b = s.cptr[c], e = s.cptr[c + 1];
+  double a = 0.0;
+  for (int k = b + lane; k < e; k += 32) a += s.val[k];
+  return warp_sum(a);
+}
+
+// lnL contribution of the tile's (ambiguous) rows and optional z output
+// (calculate_lnl model.py:291-317 with z from `ptold`, parameters `ptnew`).
+template <int THREADS>
+__device__ __forceinline__ double tile_lnl_pass(const TileView& v, const TileSmem& s,
+                                                const double* __restrict__ ptold,
+                                                const double* __restrict__ ptnew, bool want_lnl,
+                                                double* __restrict__ z_out, const int* __restrict__ opos) {
+  double l = 0.0;
+  for (int r = threadIdx.x; r < v.nrows; r += THREADS) {
+    const int len = s.rlen[r];
+    double acc = 0.0;
+    for (int p = 0; p < len; ++p) {
+      const int e = s.jptr[p] + r;
+      acc = fma(s.q[e], ptold[s.lcol[e]], acc);
+    }
+    const double inv = acc > 0.0 ? 1.0 / acc : 0.0;
+    for (int p = 0; p < len; ++p) {
+      const int e = s.jptr[p] + r;
+      const int c = s.lcol[e];
+      const double q = s.q[e];
+      const double z = (q * ptold[c]) * inv;
+      if (want_lnl) {
+        const double pn = ptnew[c];
+        if (z > 0.0 && pn > 0.0) l = fma(z, log(q * pn), l);
+      }
+      if (z_out) z_out[opos[e]] = z;
+    }
+  }
+  return l;
+}
+
+// deterministic block sum: every thread returns the same value
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double* red /* >= THREADS/32 doubles */) {
+  constexpr int NW = THREADS / 32;
+  v = warp_sum(v);
+  __syncthreads();  // protect `red` from the previous use
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) t += red[i];
+  return t;
+}
+
+}  // namespace ss

@@ -1,0 +1,81 @@
+// Handle behind the C ABI (include/stellarscope_b200.h).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/stellarscope_b200.h"
+#include "ss_common.cuh"
+
+constexpr int SS_NUM_CLASSES = 4;
+
+struct ss_handle_s {
+  int device = 0;
+  int num_sms = 148;
+  size_t max_smem_optin = 0;
+  std::string err;
+  long long launches = 0;
+
+  // ---- layout ----
+  bool has_layout = false;
+  ss::Layout L;
+  std::vector<void*> layout_allocs;
+  std::vector<long long> hdr_host;            // tile headers, HDR_WORDS per tile
+  std::vector<int> seg_ntiles_host, seg_tile0_host;
+  // launch plan
+  int* cls_tiles[SS_NUM_CLASSES] = {nullptr, nullptr, nullptr, nullptr};  // device tile lists (single-tile segments)
+  int cls_count[SS_NUM_CLASSES] = {0, 0, 0, 0};
+  size_t cls_smem[SS_NUM_CLASSES][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // [class][lnl]
+  int* stream_tiles = nullptr;    // device: tiles of multi-tile segments
+  int n_stream_tiles = 0;
+  int* stream_segs = nullptr;     // device: multi-tile segment ids
+  int n_stream_segs = 0;
+  int* stream_col_seg = nullptr;  // device: for every column of a multi-tile segment, index into stream_segs
+  int* stream_col_slot = nullptr; // device: its absolute slot
+  long long n_stream_cols = 0;
+  size_t stream_smem[2] = {0, 0};
+  int* all_tiles = nullptr;       // device: 0 .. n_tiles-1
+  size_t all_smem = 0;            // smem of the largest tile (likelihood-mode carve)
+  int8_t* sc_inamb = nullptr;     // device: segment column is touched by a tile
+  long long nnz_amb = 0, rows_amb = 0;
+
+  // ---- fit ----
+  bool has_fit = false;
+  ss::FitState F;
+  ss::FitParams P;
+  std::vector<void*> fit_allocs;
+  int* stream_ctl = nullptr;      // device control words of the streaming kernel
+
+  // multi-GPU hook
+  ss_allreduce_fn allreduce = nullptr;
+  void* allreduce_user = nullptr;
+
+  void set_error(const std::string& m) { err = m; }
+};
+
+namespace ss {
+// ss_em.cu
+int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P);
+int em_emit_z(ss_handle_s* h, cudaStream_t st, double* z);
+void free_fit(ss_handle_s* h);
+// ss_layout.cu
+int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long long nnz, const int* row_ptr,
+                 const int* col_idx, const uint16_t* score, const int* row_segment, int n_segments);
+int layout_import(ss_handle_s* h, cudaStream_t st, const ss_host_layout* HL);
+int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_ncol, const std::vector<int>& seg_col0);
+void free_layout(ss_handle_s* h);
+// ss_reassign.cu
+int reassign(ss_handle_s* h, cudaStream_t st, int mode, double conf, double tol, int n_rows, const int* row_ptr,
+             const uint16_t* score, const double* z, uint8_t* flag, int* nbest, long long* info);
+int count(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, const int* row_ptr, const int* col_idx,
+          const uint8_t* flag, const double* weight, const int* row_cell, const int* row_umi, long long cap,
+          int* out_cell, int* out_col, double* out_val, long long* n_out);
+
+template <class T>
+inline cudaError_t dev_alloc(std::vector<void*>& pool, T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+  if (e == cudaSuccess) pool.push_back(*p);
+  return e;
+}
+}  // namespace ss

@@ -1,0 +1,174 @@
+// Layout management: import of a host-built layout (debug/test), the launch plan
+// (which tile goes to which kernel) and -- below -- the device builder.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "ss_em.cuh"
+#include "ss_handle.h"
+
+namespace ss {
+
+void free_layout(ss_handle_s* h) {
+  for (void* p : h->layout_allocs) cudaFree(p);
+  h->layout_allocs.clear();
+  h->L = Layout();
+  h->hdr_host.clear();
+  h->seg_ntiles_host.clear();
+  h->seg_tile0_host.clear();
+  for (int c = 0; c < SS_NUM_CLASSES; ++c) {
+    h->cls_tiles[c] = nullptr;
+    h->cls_count[c] = 0;
+    h->cls_smem[c][0] = h->cls_smem[c][1] = 0;
+  }
+  h->stream_tiles = h->stream_segs = h->stream_col_seg = h->stream_col_slot = nullptr;
+  h->n_stream_tiles = h->n_stream_segs = 0;
+  h->n_stream_cols = 0;
+  h->all_tiles = nullptr;
+  h->sc_inamb = nullptr;
+  h->has_layout = false;
+}
+
+template <class T>
+static cudaError_t upload(std::vector<void*>& pool, T** dst, const T* src, size_t n, cudaStream_t st) {
+  cudaError_t e = dev_alloc(pool, dst, n);
+  if (e != cudaSuccess || n == 0) return e;
+  return cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+int layout_import(ss_handle_s* h, cudaStream_t st, const ss_host_layout* HL) {
+  free_fit(h);
+  free_layout(h);
+  Layout& L = h->L;
+  auto& pool = h->layout_allocs;
+  L.N = HL->N; L.K = HL->K; L.S = HL->S; L.n_tiles = HL->n_tiles; L.maxlen = HL->maxlen; L.chunk = HL->chunk;
+  L.n_uniq = HL->n_uniq; L.A = HL->A; L.n_segcols = HL->n_segcols;
+  L.tot_ent = HL->tot_ent; L.tot_row = HL->tot_row; L.tot_col = HL->tot_col; L.tot_jds = HL->tot_jds;
+  const size_t T = (size_t)L.n_tiles, S = (size_t)L.S, NC = (size_t)L.n_segcols;
+  SS_CUDA_CHECK(h, upload(pool, &L.tile_hdr, (const long long*)HL->tile_hdr, T * HDR_WORDS, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.e_lcol, HL->e_lcol, (size_t)L.tot_ent, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.e_cpos, HL->e_cpos, (size_t)L.tot_ent, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.e_q, HL->e_q, (size_t)L.tot_ent, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.e_opos, HL->e_opos, (size_t)L.tot_ent, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.r_len, HL->r_len, (size_t)L.tot_row, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.r_w, HL->r_w, (size_t)L.tot_row, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.r_orow, HL->r_orow, (size_t)L.tot_row, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.c_ptr, HL->c_ptr, (size_t)L.tot_col, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.c_scol, HL->c_scol, (size_t)L.tot_col, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.c_pisum0, HL->c_pisum0, (size_t)L.tot_col, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.c_nuniq, HL->c_nuniq, (size_t)L.tot_col, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.j_ptr, HL->j_ptr, (size_t)L.tot_jds, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.seg_tile0, HL->seg_tile0, S, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.seg_ntiles, HL->seg_ntiles, S, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.seg_col0, HL->seg_col0, S, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.seg_ncol, HL->seg_ncol, S, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.seg_smax, HL->seg_smax, S, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.seg_nobs, HL->seg_nobs, S, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.seg_namb, HL->seg_namb, S, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.seg_nuniq, HL->seg_nuniq, S, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.seg_wmax, HL->seg_wmax, S, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.seg_wtot, HL->seg_wtot, S, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.seg_wamb, HL->seg_wamb, S, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.seg_logq_uniq, HL->seg_logq_uniq, S, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.seg_A, (const long long*)HL->seg_A, S, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.seg_Aamb, (const long long*)HL->seg_Aamb, S, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.sc_gcol, HL->sc_gcol, NC, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.sc_pisum0, HL->sc_pisum0, NC, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.sc_nuniq, HL->sc_nuniq, NC, st));
+  SS_CUDA_CHECK(h, upload(pool, &h->sc_inamb, HL->sc_inamb, NC, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.u_row, HL->u_row, (size_t)L.n_uniq, st));
+  SS_CUDA_CHECK(h, upload(pool, &L.u_pos, HL->u_pos, (size_t)L.n_uniq, st));
+  h->hdr_host.assign((const long long*)HL->tile_hdr, (const long long*)HL->tile_hdr + T * HDR_WORDS);
+  h->seg_ntiles_host.assign(HL->seg_ntiles, HL->seg_ntiles + S);
+  h->seg_tile0_host.assign(HL->seg_tile0, HL->seg_tile0 + S);
+  std::vector<int> ncol_host(HL->seg_ncol, HL->seg_ncol + S), col0_host(HL->seg_col0, HL->seg_col0 + S);
+  int rc = layout_plan(h, st, ncol_host, col0_host);
+  if (rc != SS_OK) return rc;
+  SS_CUDA_CHECK(h, cudaStreamSynchronize(st));
+  h->has_layout = true;
+  return SS_OK;
+}
+
+// Decide which kernel runs each tile.  Tiles of single-tile segments go to the
+// resident kernel, binned by shared-memory need (CTAs per SM); tiles of larger
+// segments go to the streaming kernel.
+int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_ncol,
+                const std::vector<int>& seg_col0) {
+  Layout& L = h->L;
+  auto& pool = h->layout_allocs;
+  const int T = L.n_tiles;
+  static const size_t CLS_LIMIT[SS_NUM_CLASSES] = {24 * 1024, 56 * 1024, 112 * 1024, (size_t)-1};
+  std::vector<int> cls[SS_NUM_CLASSES], stream, all(T);
+  std::iota(all.begin(), all.end(), 0);
+  size_t all_smem = 0;
+  h->nnz_amb = 0;
+  h->rows_amb = 0;
+  for (int c = 0; c < SS_NUM_CLASSES; ++c) h->cls_smem[c][0] = h->cls_smem[c][1] = 0;
+  h->stream_smem[0] = h->stream_smem[1] = 0;
+  for (int t = 0; t < T; ++t) {
+    const long long* hd = &h->hdr_host[(size_t)t * HDR_WORDS];
+    const int seg = (int)hd[H_SEG], nrows = (int)hd[H_NROWS], nent = (int)hd[H_NENT], ncol = (int)hd[H_NCOL],
+              maxlen = (int)hd[H_MAXLEN];
+    h->nnz_amb += nent;
+    h->rows_amb += nrows;
+    const size_t b0 = tile_smem_bytes(nent, nrows, ncol, maxlen, false);
+    const size_t b1 = tile_smem_bytes(nent, nrows, ncol, maxlen, true);
+    all_smem = std::max(all_smem, b1);
+    if (b1 + 1024 > h->max_smem_optin) {
+      h->set_error("tile exceeds the shared-memory capacity");
+      return SS_ERR_CAPACITY;
+    }
+    if (h->seg_ntiles_host[seg] == 1) {
+      int c = 0;
+      while (b0 > CLS_LIMIT[c]) ++c;
+      cls[c].push_back(t);
+      h->cls_smem[c][0] = std::max(h->cls_smem[c][0], b0);
+      h->cls_smem[c][1] = std::max(h->cls_smem[c][1], b1);
+    } else {
+      stream.push_back(t);
+      h->stream_smem[0] = std::max(h->stream_smem[0], b0);
+      h->stream_smem[1] = std::max(h->stream_smem[1], b1);
+    }
+  }
+  h->all_smem = all_smem;
+  auto by_size = [&](int a, int b) {
+    const long long ea = h->hdr_host[(size_t)a * HDR_WORDS + H_NENT], eb = h->hdr_host[(size_t)b * HDR_WORDS + H_NENT];
+    return ea != eb ? ea > eb : a < b;
+  };
+  for (int c = 0; c < SS_NUM_CLASSES; ++c) {
+    std::sort(cls[c].begin(), cls[c].end(), by_size);
+    h->cls_count[c] = (int)cls[c].size();
+    SS_CUDA_CHECK(h, upload(pool, &h->cls_tiles[c], (const int*)cls[c].data(), cls[c].size(), st));
+  }
+  std::sort(stream.begin(), stream.end(), by_size);
+  h->n_stream_tiles = (int)stream.size();
+  SS_CUDA_CHECK(h, upload(pool, &h->stream_tiles, (const int*)stream.data(), stream.size(), st));
+  SS_CUDA_CHECK(h, upload(pool, &h->all_tiles, (const int*)all.data(), all.size(), st));
+  // multi-tile segments and their columns
+  std::vector<int> segs, col_seg, col_slot;
+  for (int s = 0; s < L.S; ++s) {
+    if (h->seg_ntiles_host[s] > 1) {
+      const int si = (int)segs.size();
+      segs.push_back(s);
+      for (int j = 0; j < seg_ncol[s]; ++j) {
+        col_seg.push_back(si);
+        col_slot.push_back(seg_col0[s] + j);
+      }
+    }
+  }
+  h->n_stream_segs = (int)segs.size();
+  h->n_stream_cols = (long long)col_seg.size();
+  SS_CUDA_CHECK(h, upload(pool, &h->stream_segs, (const int*)segs.data(), segs.size(), st));
+  SS_CUDA_CHECK(h, upload(pool, &h->stream_col_seg, (const int*)col_seg.data(), col_seg.size(), st));
+  SS_CUDA_CHECK(h, upload(pool, &h->stream_col_slot, (const int*)col_slot.data(), col_slot.size(), st));
+  SS_CUDA_CHECK(h, cudaStreamSynchronize(st));  // host vectors go out of scope
+  return SS_OK;
+}
+
+int layout_build(ss_handle_s* h, cudaStream_t, int, int, long long, const int*, const int*, const uint16_t*,
+                 const int*, int) {
+  h->set_error("ss_layout_build: device builder not compiled in yet");
+  return SS_ERR_STATE;
+}
+
+}  // namespace ss

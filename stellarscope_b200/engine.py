@@ -1,0 +1,281 @@
+"""Thin host wrapper over the C ABI: owns the handle and the torch device
+buffers that are handed to it (PyTorch is only the allocator / stream provider).
+
+All arithmetic happens in libstellarscope_b200.so; nothing here computes the
+model on the CPU.  Using this module without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MODES
+
+
+class EngineError(RuntimeError):
+    """Failure inside the native library (status code in ``.status``)."""
+
+    def __init__(self, status, msg):
+        super().__init__(f'[ss status {status}] {msg}')
+        self.status = status
+
+
+class ModelError(EngineError):
+    """SS_ERR_MODEL -- the class of failures the reference raises as
+    ``StellarscopeError`` (model.py:267-272, 454-457)."""
+
+
+def _np(x, dtype):
+    return np.ascontiguousarray(np.asarray(x), dtype=dtype)
+
+
+class Engine:
+    """One handle on one GPU."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('stellarscope_b200 needs a CUDA device (there is no CPU fallback)')
+        self.lib = _lib.load()
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            torch.cuda.init()
+            torch.zeros(1, device=self.device)          # make sure the primary context exists
+            rc = self.lib.ss_create(self.device.index, C.byref(h))
+        if rc != 0:
+            raise EngineError(rc, 'ss_create failed')
+        self.h = h
+        self._keep = {}
+        self.N = self.K = self.S = self.A = 0
+        self.max_iter = 0
+
+    # -- plumbing ------------------------------------------------------------
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.ss_destroy(self.h)
+            self.h = None
+            self._keep = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.ss_last_error(self.h).decode()
+            raise (ModelError if rc == _lib.SS_ERR_MODEL else EngineError)(rc, msg)
+
+    def _to_dev(self, arr, dtype, pinned=True):
+        a = _np(arr, dtype)
+        t = torch.from_numpy(a)
+        if pinned and a.nbytes:
+            t = t.pin_memory()
+        return t.to(self.device, non_blocking=True)
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+    def launch_count(self):
+        return int(self.lib.ss_launch_count(self.h))
+
+    # -- layout --------------------------------------------------------------
+    def set_matrix(self, indptr, indices, scores, K):
+        """Upload the N x K uint16 CSR score matrix (host arrays) to the device."""
+        self.N = len(indptr) - 1
+        self.K = int(K)
+        self.A = int(indptr[-1])
+        with torch.cuda.device(self.device):
+            self._keep['row_ptr'] = self._to_dev(indptr, np.int32)
+            self._keep['col_idx'] = self._to_dev(indices, np.int32)
+            self._keep['score'] = self._to_dev(scores, np.uint16)
+        self.h2d_bytes = 4 * (self.N + 1) + 6 * self.A
+
+    def set_matrix_device(self, row_ptr, col_idx, score, K):
+        """Use device tensors that are already resident (int32, int32, uint16)."""
+        self.N = row_ptr.numel() - 1
+        self.K = int(K)
+        self.A = col_idx.numel()
+        self._keep['row_ptr'], self._keep['col_idx'], self._keep['score'] = row_ptr, col_idx, score
+        self.h2d_bytes = 0
+
+    def build_layout(self, row_segment, n_segments):
+        """ss_layout_build on the uploaded matrix; ``row_segment`` host or device int32[N]."""
+        with torch.cuda.device(self.device):
+            if isinstance(row_segment, torch.Tensor) and row_segment.is_cuda:
+                rs = row_segment
+            else:
+                rs = self._to_dev(row_segment, np.int32)
+                self.h2d_bytes += 4 * self.N
+            self._keep['row_seg'] = rs
+            k = self._keep
+            rc = self.lib.ss_layout_build(self.h, self._stream(), self.N, self.K, self.A,
+                                          self._p(k['row_ptr']), self._p(k['col_idx']), self._p(k['score']),
+                                          self._p(rs), int(n_segments))
+        self._check(rc)
+        self.S = int(n_segments)
+
+    def import_layout(self, hl):
+        """Install a host-built layout (stellarscope_b200.layout_host.HostLayout). Test/debug."""
+        c = _lib.HostLayoutC()
+        keep = []
+
+        def ptr(arr, dtype, ctype):
+            a = _np(arr, dtype)
+            keep.append(a)
+            return a.ctypes.data_as(C.POINTER(ctype))
+        c.N, c.K, c.S, c.n_tiles, c.maxlen, c.chunk = hl.N, hl.K, hl.S, hl.n_tiles, hl.maxlen, hl.chunk
+        c.n_uniq = len(hl.u_row)
+        c.A, c.n_segcols = hl.A, len(hl.sc_gcol)
+        c.tot_ent, c.tot_row, c.tot_col, c.tot_jds = len(hl.e_q), len(hl.r_w), len(hl.c_scol), len(hl.j_ptr)
+        c.tile_hdr = ptr(hl.tile_hdr, np.int64, C.c_int64)
+        for name, dt, ct in (
+                ('e_lcol', np.uint16, C.c_uint16), ('e_cpos', np.uint16, C.c_uint16),
+                ('e_q', np.float64, C.c_double), ('e_opos', np.int32, C.c_int32),
+                ('r_len', np.uint16, C.c_uint16), ('r_w', np.float64, C.c_double),
+                ('r_orow', np.int32, C.c_int32), ('c_ptr', np.uint16, C.c_uint16),
+                ('c_scol', np.int32, C.c_int32), ('c_pisum0', np.float64, C.c_double),
+                ('c_nuniq', np.int32, C.c_int32), ('j_ptr', np.uint16, C.c_uint16),
+                ('seg_tile0', np.int32, C.c_int32), ('seg_ntiles', np.int32, C.c_int32),
+                ('seg_col0', np.int32, C.c_int32), ('seg_ncol', np.int32, C.c_int32),
+                ('seg_smax', np.int32, C.c_int32), ('seg_nobs', np.int32, C.c_int32),
+                ('seg_namb', np.int32, C.c_int32), ('seg_nuniq', np.int32, C.c_int32),
+                ('seg_wmax', np.float64, C.c_double), ('seg_wtot', np.float64, C.c_double),
+                ('seg_wamb', np.float64, C.c_double), ('seg_logq_uniq', np.float64, C.c_double),
+                ('seg_A', np.int64, C.c_int64), ('seg_Aamb', np.int64, C.c_int64),
+                ('sc_gcol', np.int32, C.c_int32), ('sc_pisum0', np.float64, C.c_double),
+                ('sc_nuniq', np.int32, C.c_int32), ('sc_inamb', np.int8, C.c_int8),
+                ('u_row', np.int32, C.c_int32), ('u_pos', np.int32, C.c_int32)):
+            setattr(c, name, ptr(getattr(hl, name), dt, ct))
+        with torch.cuda.device(self.device):
+            rc = self.lib.ss_layout_import(self.h, self._stream(), C.byref(c))
+        self._check(rc)
+        self.N, self.K, self.S, self.A = hl.N, hl.K, hl.S, hl.A
+
+    def layout_info(self):
+        info = _lib.LayoutInfo()
+        self._check(self.lib.ss_layout_get_info(self.h, C.byref(info)))
+        return info.as_dict()
+
+    def export_layout_array(self, name, dtype):
+        n = C.c_int64(0)
+        self._check(self.lib.ss_layout_export(self.h, name.encode(), None, C.byref(n)))
+        out = np.empty(n.value // np.dtype(dtype).itemsize, dtype=dtype)
+        if n.value:
+            self._check(self.lib.ss_layout_export(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return out
+
+    # -- fit -----------------------------------------------------------------
+    def fit(self, em_epsilon=1e-7, max_iter=100, pi_prior=0.0, theta_prior=200000.0, use_likelihood=False):
+        """ss_em_fit: enqueue EM for every segment (asynchronous)."""
+        self.max_iter = int(max_iter)
+        self.use_likelihood = bool(use_likelihood)
+        with torch.cuda.device(self.device):
+            rc = self.lib.ss_em_fit(self.h, self._stream(), float(em_epsilon), int(max_iter), float(pi_prior),
+                                    float(theta_prior), int(bool(use_likelihood)))
+        self._check(rc)
+
+    def results(self, traces=True):
+        """Per-segment results as numpy arrays (synchronises)."""
+        S, MI, dev = self.S, self.max_iter, self.device
+        with torch.cuda.device(dev):
+            iters = torch.empty(S, dtype=torch.int32, device=dev)
+            flags = torch.empty(S, dtype=torch.int32, device=dev)
+            lnl = torch.empty(S, dtype=torch.float64, device=dev)
+            nobs = torch.empty(S, dtype=torch.int32, device=dev)
+            nfeats = torch.empty(S, dtype=torch.int32, device=dev)
+            diffs = torch.empty(S * MI, dtype=torch.float64, device=dev) if traces else None
+            lnls = torch.empty(S * MI, dtype=torch.float64, device=dev) if traces and self.use_likelihood else None
+            rc = self.lib.ss_em_get_results(self.h, self._stream(), self._p(iters), self._p(flags), self._p(lnl),
+                                            self._p(diffs), self._p(lnls), self._p(nobs), self._p(nfeats))
+            self._check(rc)
+            out = dict(iters=iters.cpu().numpy(), flags=flags.cpu().numpy(), lnl=lnl.cpu().numpy(),
+                       nobs=nobs.cpu().numpy(), nfeats=nfeats.cpu().numpy())
+            if diffs is not None:
+                out['diffs'] = diffs.cpu().numpy().reshape(S, MI)
+            if lnls is not None:
+                out['lnls'] = lnls.cpu().numpy().reshape(S, MI)
+        return out
+
+    def params(self):
+        """Per segment-column parameters (synchronises)."""
+        S, dev = self.S, self.device
+        nc = self.layout_info()['n_segcols']
+        with torch.cuda.device(dev):
+            col0 = torch.empty(S, dtype=torch.int32, device=dev)
+            ncol = torch.empty(S, dtype=torch.int32, device=dev)
+            gcol = torch.empty(nc, dtype=torch.int32, device=dev)
+            pi = torch.empty(nc, dtype=torch.float64, device=dev)
+            theta = torch.empty(nc, dtype=torch.float64, device=dev)
+            pi_rest = torch.empty(S, dtype=torch.float64, device=dev)
+            th_rest = torch.empty(S, dtype=torch.float64, device=dev)
+            rc = self.lib.ss_em_get_params(self.h, self._stream(), self._p(col0), self._p(ncol), self._p(gcol),
+                                           self._p(pi), self._p(theta), self._p(pi_rest), self._p(th_rest))
+            self._check(rc)
+            return dict(seg_col0=col0.cpu().numpy(), seg_ncol=ncol.cpu().numpy(), gcol=gcol.cpu().numpy(),
+                        pi=pi.cpu().numpy(), theta=theta.cpu().numpy(), pi_rest=pi_rest.cpu().numpy(),
+                        theta_rest=th_rest.cpu().numpy())
+
+    def dense_params(self, seg):
+        """Full-length (K) pi and theta of one segment, like ``tl.pi`` / ``tl.theta``."""
+        p = self._params_cache = getattr(self, '_params_cache', None) or self.params()
+        a, n = int(p['seg_col0'][seg]), int(p['seg_ncol'][seg])
+        pi = np.full(self.K, p['pi_rest'][seg])
+        th = np.full(self.K, p['theta_rest'][seg])
+        pi[p['gcol'][a:a + n]] = p['pi'][a:a + n]
+        th[p['gcol'][a:a + n]] = p['theta'][a:a + n]
+        return pi, th
+
+    def emit_z(self):
+        """Device tensor with z in the CSR order of the input matrix."""
+        with torch.cuda.device(self.device):
+            z = torch.empty(max(self.A, 1), dtype=torch.float64, device=self.device)
+            self._check(self.lib.ss_em_emit_z(self.h, self._stream(), self._p(z)))
+        return z[:self.A]
+
+    # -- reassign / count ------------------------------------------------------
+    def reassign(self, mode, z=None, conf_thresh=0.9, tie_tol=0.0):
+        """ss_reassign.  Returns (flag uint8[A] device, nbest int32[N] device, info numpy int64[68])."""
+        if mode not in MODES:
+            raise ValueError(f'Argument "method" should be one of {list(MODES)}')
+        dev = self.device
+        k = self._keep
+        with torch.cuda.device(dev):
+            flag = torch.empty(max(self.A, 1), dtype=torch.uint8, device=dev)
+            nbest = torch.zeros(max(self.N, 1), dtype=torch.int32, device=dev)
+            info = torch.zeros(68, dtype=torch.int64, device=dev)
+            rc = self.lib.ss_reassign(self.h, self._stream(), MODES[mode],
+                                      float(conf_thresh if conf_thresh is not None else 0.0), float(tie_tol),
+                                      self.N, self._p(k['row_ptr']), self._p(k['score']), self._p(z),
+                                      self._p(flag), self._p(nbest), self._p(info))
+            self._check(rc)
+            return flag[:self.A], nbest[:self.N], info.cpu().numpy()
+
+    def count(self, flag, row_cell, weight=None, row_umi=None, cap=None):
+        """ss_count.  Returns COO (cell, col, val) numpy arrays sorted by (cell, col)."""
+        dev = self.device
+        k = self._keep
+        with torch.cuda.device(dev):
+            rc_t = row_cell if isinstance(row_cell, torch.Tensor) else self._to_dev(row_cell, np.int32)
+            ru_t = None
+            if row_umi is not None:
+                ru_t = row_umi if isinstance(row_umi, torch.Tensor) else self._to_dev(row_umi, np.int32)
+            cap = int(cap if cap is not None else max(self.A, 1))
+            oc = torch.empty(cap, dtype=torch.int32, device=dev)
+            ol = torch.empty(cap, dtype=torch.int32, device=dev)
+            ov = torch.empty(cap, dtype=torch.float64, device=dev)
+            n = C.c_int64(0)
+            rc = self.lib.ss_count(self.h, self._stream(), self.N, self.K, self._p(k['row_ptr']),
+                                   self._p(k['col_idx']), self._p(flag), self._p(weight), self._p(rc_t),
+                                   self._p(ru_t), cap, self._p(oc), self._p(ol), self._p(ov), C.byref(n))
+            self._check(rc)
+            m = n.value
+            return oc[:m].cpu().numpy(), ol[:m].cpu().numpy(), ov[:m].cpu().numpy()
