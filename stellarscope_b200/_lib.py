@@ -81,6 +81,8 @@ SIGNATURES = {
                            c_i64p]),
     'ss_set_allreduce': (C.c_int, [C.c_void_p, ALLREDUCE_FN, C.c_void_p]),
     'ss_launch_count': (C.c_int64, [C.c_void_p]),
+    'ss_set_timing': (C.c_int, [C.c_void_p, C.c_int32]),
+    'ss_get_timings': (C.c_int, [C.c_void_p, c_f64p, C.c_int32]),
 }
 
 _lib = None

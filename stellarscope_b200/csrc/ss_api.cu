@@ -40,6 +40,8 @@ int ss_destroy(ss_handle_t h) {
   cudaSetDevice(h->device);
   free_fit(h);
   free_layout(h);
+  for (int i = 0; i < 6; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
   return SS_OK;
 }
@@ -253,5 +255,30 @@ int ss_set_allreduce(ss_handle_t h, ss_allreduce_fn fn, void* user) {
 }
 
 int64_t ss_launch_count(ss_handle_t h) { return h ? h->launches : 0; }
+
+int ss_set_timing(ss_handle_t h, int32_t enabled) {
+  SS_REQUIRE_HANDLE(h);
+  cudaSetDevice(h->device);
+  h->timing = enabled != 0;
+  if (h->timing && !h->ev[0])
+    for (int i = 0; i < 6; ++i) SS_CUDA_CHECK(h, cudaEventCreate(&h->ev[i]));
+  return SS_OK;
+}
+
+int ss_get_timings(ss_handle_t h, double* ms, int32_t n) {
+  SS_REQUIRE_HANDLE(h);
+  if (!ms || n < 5 || !h->ev_valid) {
+    h->set_error("ss_get_timings: timing not enabled / no fit / buffer too small");
+    return SS_ERR_STATE;
+  }
+  cudaSetDevice(h->device);
+  SS_CUDA_CHECK(h, cudaEventSynchronize(h->ev[5]));
+  for (int i = 0; i < 5; ++i) {
+    float t = 0.f;
+    SS_CUDA_CHECK(h, cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]));
+    ms[i] = t;
+  }
+  return SS_OK;
+}
 
 }  // extern "C"

@@ -1,0 +1,918 @@
+// Device builder of the tiled segment layout (ss_layout_build).
+//
+// Replaces, for all models of a pooling mode at once, TelescopeLikelihood.__init__
+// (reference utils/model.py:102-200) and the row selection of _fit_pooling_model
+// (:701-743).  The construction is specified by stellarscope_b200/layout_host.py;
+// this file produces the same arrays on the device.  Device-wide sorts / scans use
+// CUB (library code, one-time build step); the per-tile work (JDS ordering, tile
+// column discovery, column-major slots) is a hand-written CTA-per-tile kernel.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <vector>
+
+#include "ss_em.cuh"
+#include "ss_handle.h"
+
+namespace ss {
+
+namespace {
+
+struct TmpPool {
+  std::vector<void*> p;
+  ~TmpPool() {
+    for (void* q : p) cudaFree(q);
+  }
+  template <class T>
+  cudaError_t get(T** out, size_t n) {
+    return dev_alloc(p, out, n);
+  }
+};
+
+#define CUB_CALL(call_with_tmp)                \
+  do {                                         \
+    void* d_tmp = nullptr;                     \
+    size_t tmp_bytes = 0;                      \
+    SS_CUDA_CHECK(h, (call_with_tmp));         \
+    unsigned char* _t;                         \
+    SS_CUDA_CHECK(h, tmp.get(&_t, tmp_bytes)); \
+    d_tmp = _t;                                \
+    SS_CUDA_CHECK(h, (call_with_tmp));         \
+    h->launches++;                             \
+  } while (0)
+
+// ---- step 1: classify rows, per-segment integer statistics --------------------
+// counters: [0] = max row length among ambiguous rows
+__global__ void row_class_kernel(int n_rows, const int* __restrict__ row_ptr, const uint16_t* __restrict__ score,
+                                 const int* __restrict__ row_seg, int n_seg, uint8_t* __restrict__ is_amb,
+                                 uint8_t* __restrict__ is_uni, int* __restrict__ seg_smax, int* __restrict__ seg_nobs,
+                                 int* __restrict__ seg_namb, int* __restrict__ seg_nuniq,
+                                 unsigned long long* __restrict__ seg_A, unsigned long long* __restrict__ seg_Aamb,
+                                 int* __restrict__ counters) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  int seg = -1, len = 0, rmax = 0;
+  if (row < n_rows) {
+    seg = row_seg[row];
+    if (seg >= n_seg) seg = -1;
+    const int b = row_ptr[row], e = row_ptr[row + 1];
+    len = e - b;
+    if (seg >= 0)
+      for (int k = b; k < e; ++k) rmax = max(rmax, (int)score[k]);
+    is_amb[row] = seg >= 0 && len > 1;
+    is_uni[row] = seg >= 0 && len == 1;
+  }
+  const bool fitted = seg >= 0 && len > 0;
+  // warp aggregation when the whole warp works on one segment (rows of a cell are usually adjacent)
+  const unsigned full = 0xffffffffu;
+  const int s0 = __shfl_sync(full, seg, 0);
+  if (__all_sync(full, seg == s0)) {
+    if (s0 >= 0) {
+      const int wmax = __reduce_max_sync(full, rmax);
+      const int nobs = __reduce_add_sync(full, fitted ? 1 : 0);
+      const int namb = __reduce_add_sync(full, (fitted && len > 1) ? 1 : 0);
+      const int nuni = __reduce_add_sync(full, (fitted && len == 1) ? 1 : 0);
+      const int a_all = __reduce_add_sync(full, fitted ? len : 0);
+      const int a_amb = __reduce_add_sync(full, (fitted && len > 1) ? len : 0);
+      const int lmax = __reduce_max_sync(full, (fitted && len > 1) ? len : 0);
+      if ((threadIdx.x & 31) == 0) {
+        if (wmax) atomicMax(&seg_smax[s0], wmax);
+        if (nobs) atomicAdd(&seg_nobs[s0], nobs);
+        if (namb) atomicAdd(&seg_namb[s0], namb);
+        if (nuni) atomicAdd(&seg_nuniq[s0], nuni);
+        if (a_all) atomicAdd(&seg_A[s0], (unsigned long long)a_all);
+        if (a_amb) atomicAdd(&seg_Aamb[s0], (unsigned long long)a_amb);
+        if (lmax) atomicMax(&counters[0], lmax);
+      }
+    }
+  } else if (fitted) {
+    atomicMax(&seg_smax[seg], rmax);
+    atomicAdd(&seg_nobs[seg], 1);
+    atomicAdd(&seg_A[seg], (unsigned long long)len);
+    if (len > 1) {
+      atomicAdd(&seg_namb[seg], 1);
+      atomicAdd(&seg_Aamb[seg], (unsigned long long)len);
+      atomicMax(&counters[0], len);
+    } else {
+      atomicAdd(&seg_nuniq[seg], 1);
+    }
+  }
+}
+
+__global__ void iota_kernel(int n, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+
+__global__ void gather_seg_len_kernel(int n, const int* __restrict__ rows, const int* __restrict__ row_seg,
+                                      const int* __restrict__ row_ptr, int* __restrict__ seg_out,
+                                      long long* __restrict__ len_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = rows[i];
+  if (seg_out) seg_out[i] = row_seg[r];
+  if (len_out) len_out[i] = row_ptr[r + 1] - row_ptr[r];
+}
+
+// per segment: first sorted ambiguous row, first entry offset, number of tiles
+__global__ void seg_tiles_kernel(int n_seg, int n_amb, const long long* __restrict__ seg_row0 /* exclusive scan of namb */,
+                                 const int* __restrict__ seg_namb, const long long* __restrict__ pre /* n_amb+1 */,
+                                 int chunk, long long* __restrict__ seg_ntiles64, long long* __restrict__ seg_ent0) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg) return;
+  const long long r0 = seg_row0[s];
+  const int n = seg_namb[s];
+  const long long e0 = pre[min(r0, (long long)n_amb)];
+  seg_ent0[s] = e0;
+  if (n == 0) {
+    seg_ntiles64[s] = 0;
+  } else {
+    const long long last_start = pre[r0 + n - 1] - e0;
+    seg_ntiles64[s] = last_start / chunk + 1;
+  }
+}
+
+// tile of every sorted ambiguous row and the first row of every tile
+__global__ void row_tile_kernel(int n_amb, const int* __restrict__ aseg, const long long* __restrict__ pre,
+                                const long long* __restrict__ seg_ent0, const long long* __restrict__ seg_tile0,
+                                int chunk, int* __restrict__ rtile) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_amb) return;
+  const int s = aseg[k];
+  rtile[k] = (int)(seg_tile0[s] + (pre[k] - seg_ent0[s]) / chunk);
+}
+__global__ void tile_heads_kernel(int n_amb, int n_tiles, const int* __restrict__ rtile, int* __restrict__ tile_row0) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) tile_row0[n_tiles] = n_amb;
+  if (k >= n_amb) return;
+  if (k == 0 || rtile[k] != rtile[k - 1]) tile_row0[rtile[k]] = k;
+}
+
+// padded sizes known before the tile kernel
+__global__ void tile_sizes_kernel(int n_tiles, const int* __restrict__ tile_row0, const long long* __restrict__ pre,
+                                  long long* __restrict__ pad_ent, long long* __restrict__ pad_row) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const int a = tile_row0[t], b = tile_row0[t + 1];
+  pad_ent[t] = pad8((int)(pre[b] - pre[a]));
+  pad_row[t] = pad8(b - a);
+}
+
+// ---- block-wide helpers ----------------------------------------------------------
+// bitonic sort of n (power of two) 64-bit keys in shared memory, ascending
+__device__ void bitonic_sort(unsigned long long* keys, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], b = keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            keys[i] = b;
+            keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+__device__ __forceinline__ int next_pow2(int n) {
+  int p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+// exclusive scan of n ints in shared memory, in place; returns the total. scratch: blockDim.x ints
+__device__ int block_excl_scan(int* data, int n, int* scratch) {
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int per = (n + T - 1) / T;
+  const int b = min(n, tid * per), e = min(n, b + per);
+  int s = 0;
+  for (int i = b; i < e; ++i) s += data[i];
+  scratch[tid] = s;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int i = 0; i < T; ++i) {
+      const int v = scratch[i];
+      scratch[i] = run;
+      run += v;
+    }
+    scratch[T] = run;
+  }
+  __syncthreads();
+  int run = scratch[tid];
+  for (int i = b; i < e; ++i) {
+    const int v = data[i];
+    data[i] = run;
+    run += v;
+  }
+  const int total = scratch[T];
+  __syncthreads();
+  return total;
+}
+
+constexpr int BUILD_THREADS = 256;
+constexpr int R_CAP = E_HARD / 2;
+
+struct TileBuildArgs {
+  const int* row_ptr;
+  const int* col_idx;
+  const uint16_t* score;
+  const int* ar;            // sorted ambiguous rows
+  const int* aseg;
+  const int* tile_row0;
+  const long long* pre;
+  const long long* ent_off; // exclusive scans of the padded sizes
+  const long long* row_off;
+  const int* seg_smax;
+  int n_tiles;
+  // outputs at their final offsets
+  uint16_t *e_lcol, *e_cpos;
+  double* e_q;
+  int* e_opos;
+  uint16_t* r_len;
+  double* r_w;
+  int* r_orow;
+  // outputs at temporary (upper bound) offsets: column arrays at ent_off[t] + 8 t, jds at (maxlen_pad) * t
+  uint16_t* tmp_cptr;
+  int* tmp_gcol;
+  uint16_t* tmp_jptr;
+  int jds_stride;
+  // per tile scalars
+  int *t_ncol, *t_maxlen, *t_nlong, *t_seg, *t_nrows, *t_nent;
+  double* t_wsum;
+};
+
+// ---- step 5: one CTA per tile ---------------------------------------------------
+__global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs a) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(dsm);   // E_HARD
+  unsigned long long* ckeys = keys + E_HARD;                                // E_HARD
+  int* colidx = reinterpret_cast<int*>(ckeys + E_HARD);                     // E_HARD: column (gcol order) of each sorted entry
+  int* colstart = colidx + E_HARD;                                          // E_HARD + 1
+  int* rank_of = colstart + E_HARD + 1;                                     // E_HARD
+  int* cptr = rank_of + E_HARD;                                             // E_HARD + 1
+  int* rrow = cptr + E_HARD + 1;                                            // R_CAP  original row of JDS row r
+  int* rlen = rrow + R_CAP;                                                 // R_CAP
+  int* jptr = rlen + R_CAP;                                                 // R_CAP + 2 (maxlen <= E_HARD/2)
+  int* scratch = jptr + R_CAP + 2;                                          // BUILD_THREADS + 1
+  __shared__ double s_red[32];
+  const int tid = threadIdx.x;
+  const int t = blockIdx.x;
+  const int row0 = a.tile_row0[t], nrows = a.tile_row0[t + 1] - row0;
+  const int nent = (int)(a.pre[row0 + nrows] - a.pre[row0]);
+  const int seg = a.aseg[row0];
+  const long long eo = a.ent_off[t], ro = a.row_off[t];
+
+  // (a) JDS row order: (len desc, rank asc)
+  const int np2 = next_pow2(nrows);
+  int lmax = 0;
+  for (int r = tid; r < np2; r += BUILD_THREADS) {
+    if (r < nrows) {
+      const int row = a.ar[row0 + r];
+      const int len = a.row_ptr[row + 1] - a.row_ptr[row];
+      keys[r] = ((unsigned long long)(unsigned)(E_HARD - len) << 32) | (unsigned)r;
+    } else {
+      keys[r] = ~0ull;
+    }
+  }
+  __syncthreads();
+  bitonic_sort(keys, np2);
+  for (int r = tid; r < nrows; r += BUILD_THREADS) {
+    const int rank = (int)(keys[r] & 0xffffffffu);
+    const int len = E_HARD - (int)(keys[r] >> 32);
+    rrow[r] = a.ar[row0 + rank];
+    rlen[r] = len;
+  }
+  __syncthreads();
+  lmax = rlen[0];
+  // (b) jptr[p] = sum_{p' < p} #(rows with len > p'); rows are sorted, so #(len > p) = first r with len <= p
+  for (int p = tid; p <= lmax; p += BUILD_THREADS) jptr[p] = 0;
+  __syncthreads();
+  for (int p = tid; p < lmax; p += BUILD_THREADS) {
+    int lo = 0, hi = nrows;                  // first r with rlen[r] <= p
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (rlen[mid] > p) lo = mid + 1; else hi = mid;
+    }
+    jptr[p] = lo;
+  }
+  __syncthreads();
+  block_excl_scan(jptr, lmax + 1, scratch);   // jptr[lmax] = nent
+  // (c) entries
+  const double inv = 1.0 / (double)a.seg_smax[seg];
+  double wsum = 0.0;
+  for (int r = tid; r < nrows; r += BUILD_THREADS) {
+    const int row = rrow[r], len = rlen[r];
+    const int b = a.row_ptr[row];
+    double w = 0.0;
+    for (int p = 0; p < len; ++p) {
+      const int e = jptr[p] + r;
+      const int g = a.col_idx[b + p];
+      const double q = expm1(((double)a.score[b + p] * inv) * 100.0);   // model.py:129-130, sparse_plus.py:128
+      w = fmax(w, q);
+      a.e_q[eo + e] = q;
+      a.e_opos[eo + e] = b + p;
+      keys[e] = ((unsigned long long)(unsigned)g << 32) | ((unsigned long long)(unsigned)r << 16) | (unsigned)e;
+    }
+    a.r_len[ro + r] = (uint16_t)len;
+    a.r_w[ro + r] = w;
+    a.r_orow[ro + r] = row;
+    wsum += w;
+  }
+  {
+    // deterministic block sum of the row weights
+    double v = warp_sum(wsum);
+    if ((tid & 31) == 0) s_red[tid >> 5] = v;
+  }
+  const int ep2 = next_pow2(nent);
+  for (int e = nent + tid; e < ep2; e += BUILD_THREADS) keys[e] = ~0ull;
+  // zero the padding of the entry / row arrays
+  for (int e = nent + tid; e < pad8(nent); e += BUILD_THREADS) {
+    a.e_q[eo + e] = 0.0; a.e_opos[eo + e] = 0; a.e_lcol[eo + e] = 0; a.e_cpos[eo + e] = 0;
+  }
+  for (int r = nrows + tid; r < pad8(nrows); r += BUILD_THREADS) {
+    a.r_len[ro + r] = 0; a.r_w[ro + r] = 0.0; a.r_orow[ro + r] = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double tsum = 0.0;
+    for (int i = 0; i < BUILD_THREADS / 32; ++i) tsum += s_red[i];
+    a.t_wsum[t] = tsum;
+  }
+  // (d) tile columns: sort by (locus, JDS row)
+  bitonic_sort(keys, ep2);
+  for (int i = tid; i < nent; i += BUILD_THREADS)
+    colidx[i] = (i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32)) ? 1 : 0;
+  __syncthreads();
+  const int ncol = block_excl_scan(colidx, nent, scratch);   // colidx[i] = (#heads before i); head i has the column index
+  // the scan is exclusive: column of entry i = colidx[i] + head(i) - 1 -> recompute head
+  for (int i = tid; i < nent; i += BUILD_THREADS) {
+    const bool head = (i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32));
+    const int ci = colidx[i] + (head ? 1 : 0) - 1;
+    colidx[i] = ci;
+    if (head) colstart[ci] = i;
+  }
+  if (tid == 0) colstart[ncol] = nent;
+  __syncthreads();
+  // order columns by (count desc, locus asc)
+  const int cp2 = next_pow2(ncol);
+  for (int c = tid; c < cp2; c += BUILD_THREADS) {
+    if (c < ncol) {
+      const int cnt = colstart[c + 1] - colstart[c];
+      const unsigned long long g = keys[colstart[c]] >> 32;
+      ckeys[c] = ((unsigned long long)(unsigned)(E_HARD - cnt) << 48) | (g << 16) | (unsigned)c;
+    } else {
+      ckeys[c] = ~0ull;
+    }
+  }
+  __syncthreads();
+  bitonic_sort(ckeys, cp2);
+  int nlong_local = 0;
+  const long long co_tmp = eo + 8LL * t;
+  for (int lc = tid; lc < ncol; lc += BUILD_THREADS) {
+    const int c = (int)(ckeys[lc] & 0xffffu);
+    const int cnt = E_HARD - (int)(ckeys[lc] >> 48);
+    rank_of[c] = lc;
+    cptr[lc] = cnt;
+    a.tmp_gcol[co_tmp + lc] = (int)((ckeys[lc] >> 16) & 0xffffffffu);
+    nlong_local += cnt > LONG_COL;
+  }
+  if (tid == 0) cptr[ncol] = 0;
+  __syncthreads();
+  block_excl_scan(cptr, ncol + 1, scratch);     // cptr[ncol] = nent
+  for (int i = tid; i < nent; i += BUILD_THREADS) {
+    const int ci = colidx[i];
+    const int lc = rank_of[ci];
+    const int e = (int)(keys[i] & 0xffffu);
+    a.e_lcol[eo + e] = (uint16_t)lc;
+    a.e_cpos[eo + e] = (uint16_t)(cptr[lc] + (i - colstart[ci]));
+  }
+  for (int lc = tid; lc <= ncol; lc += BUILD_THREADS) a.tmp_cptr[co_tmp + lc] = (uint16_t)cptr[lc];
+  for (int p = tid; p <= lmax; p += BUILD_THREADS) a.tmp_jptr[(long long)a.jds_stride * t + p] = (uint16_t)jptr[p];
+  // number of long columns: block reduce
+  {
+    int v = nlong_local;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((tid & 31) == 0) scratch[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int i = 0; i < BUILD_THREADS / 32; ++i) tot += scratch[i];
+      a.t_nlong[t] = tot;
+      a.t_ncol[t] = ncol;
+      a.t_maxlen[t] = lmax;
+      a.t_seg[t] = seg;
+      a.t_nrows[t] = nrows;
+      a.t_nent[t] = nent;
+    }
+  }
+}
+
+__global__ void tile_pad2_kernel(int n_tiles, const int* __restrict__ t_ncol, const int* __restrict__ t_maxlen,
+                                 long long* __restrict__ pad_col, long long* __restrict__ pad_jds) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  pad_col[t] = pad8(t_ncol[t] + 1);
+  pad_jds[t] = pad8(t_maxlen[t] + 1);
+}
+
+__global__ void tile_hdr_kernel(int n_tiles, const int* t_seg, const int* t_nrows, const int* t_nent, const int* t_ncol,
+                                const int* t_maxlen, const int* t_nlong, const long long* ent_off,
+                                const long long* row_off, const long long* col_off, const long long* jds_off,
+                                long long* __restrict__ hdr) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  long long* h = hdr + (long long)HDR_WORDS * t;
+  h[H_SEG] = t_seg[t]; h[H_NROWS] = t_nrows[t]; h[H_NENT] = t_nent[t]; h[H_NCOL] = t_ncol[t];
+  h[H_MAXLEN] = t_maxlen[t]; h[H_NLONG] = t_nlong[t];
+  h[H_ENT_OFF] = ent_off[t]; h[H_ROW_OFF] = row_off[t]; h[H_COL_OFF] = col_off[t]; h[H_JDS_OFF] = jds_off[t];
+}
+
+// copy cptr / jptr to their final offsets, emit (seg, locus) keys of the tile columns
+__global__ void tile_compact_kernel(int n_tiles, const long long* __restrict__ hdr, const uint16_t* __restrict__ tmp_cptr,
+                                    const int* __restrict__ tmp_gcol, const uint16_t* __restrict__ tmp_jptr,
+                                    int jds_stride, const long long* __restrict__ ent_off,
+                                    const long long* __restrict__ key_off, uint16_t* __restrict__ c_ptr,
+                                    uint16_t* __restrict__ j_ptr, unsigned long long* __restrict__ keys_out) {
+  const int t = blockIdx.x;
+  const long long* h = hdr + (long long)HDR_WORDS * t;
+  const int ncol = (int)h[H_NCOL], maxlen = (int)h[H_MAXLEN], seg = (int)h[H_SEG];
+  const long long co = h[H_COL_OFF], jo = h[H_JDS_OFF], src = ent_off[t] + 8LL * t, ko = key_off[t];
+  for (int c = threadIdx.x; c < pad8(ncol + 1); c += blockDim.x) c_ptr[co + c] = c <= ncol ? tmp_cptr[src + c] : 0;
+  for (int p = threadIdx.x; p < pad8(maxlen + 1); p += blockDim.x)
+    j_ptr[jo + p] = p <= maxlen ? tmp_jptr[(long long)jds_stride * t + p] : 0;
+  for (int c = threadIdx.x; c < ncol; c += blockDim.x)
+    keys_out[ko + c] = ((unsigned long long)(unsigned)seg << 32) | (unsigned)tmp_gcol[src + c];
+}
+
+// (seg, locus) keys of the unique rows
+__global__ void uniq_keys_kernel(int n, const int* __restrict__ u_row, const int* __restrict__ row_ptr,
+                                 const int* __restrict__ col_idx, const int* __restrict__ row_seg,
+                                 int* __restrict__ u_pos, unsigned long long* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = u_row[i];
+  const int p = row_ptr[r];
+  u_pos[i] = p;
+  keys[i] = ((unsigned long long)(unsigned)row_seg[r] << 32) | (unsigned)col_idx[p];
+}
+
+__device__ __forceinline__ long long lower_bound_u64(const unsigned long long* a, long long n, unsigned long long v) {
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void seg_cols_kernel(int n_seg, const unsigned long long* __restrict__ sc_key, long long n_sc,
+                                int* __restrict__ seg_col0, int* __restrict__ seg_ncol) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg) return;
+  const long long a = lower_bound_u64(sc_key, n_sc, (unsigned long long)(unsigned)s << 32);
+  const long long b = lower_bound_u64(sc_key, n_sc, (unsigned long long)(unsigned)(s + 1) << 32);
+  seg_col0[s] = (int)a;
+  seg_ncol[s] = (int)(b - a);
+}
+
+__global__ void sc_gcol_kernel(long long n, const unsigned long long* __restrict__ sc_key, int* __restrict__ gcol) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) gcol[i] = (int)(sc_key[i] & 0xffffffffu);
+}
+
+// unique rows sorted by (seg, locus): one thread per run accumulates pisum0, count, sum log Q in row order
+__global__ void uniq_runs_kernel(int n, const unsigned long long* __restrict__ ukeys_sorted,
+                                 const int* __restrict__ uidx_sorted, const int* __restrict__ u_pos,
+                                 const uint16_t* __restrict__ score, const int* __restrict__ seg_smax,
+                                 const unsigned long long* __restrict__ sc_key, long long n_sc,
+                                 double* __restrict__ sc_pisum0, int* __restrict__ sc_nuniq,
+                                 double* __restrict__ sc_logq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = ukeys_sorted[i];
+  if (i > 0 && ukeys_sorted[i - 1] == key) return;      // not a run head
+  const int seg = (int)(key >> 32);
+  const double inv = 1.0 / (double)seg_smax[seg];
+  double ps = 0.0, lq = 0.0;
+  int cnt = 0;
+  for (int k = i; k < n && ukeys_sorted[k] == key; ++k) {
+    const double q = expm1(((double)score[u_pos[uidx_sorted[k]]] * inv) * 100.0);
+    ps += q;
+    lq += log(q);
+    ++cnt;
+  }
+  const long long slot = lower_bound_u64(sc_key, n_sc, key);
+  sc_pisum0[slot] = ps;
+  sc_nuniq[slot] = cnt;
+  sc_logq[slot] = lq;
+}
+
+// tile column -> segment column slot, copies of pisum0 / nuniq in tile order
+__global__ void tile_scol_kernel(const long long* __restrict__ hdr, const long long* __restrict__ ent_off,
+                                 const int* __restrict__ tmp_gcol, const int* __restrict__ seg_col0,
+                                 const int* __restrict__ seg_ncol, const int* __restrict__ sc_gcol,
+                                 const double* __restrict__ sc_pisum0, const int* __restrict__ sc_nuniq,
+                                 int8_t* __restrict__ sc_inamb, int* __restrict__ c_scol,
+                                 double* __restrict__ c_pisum0, int* __restrict__ c_nuniq) {
+  const int t = blockIdx.x;
+  const long long* h = hdr + (long long)HDR_WORDS * t;
+  const int ncol = (int)h[H_NCOL], seg = (int)h[H_SEG];
+  const long long co = h[H_COL_OFF], src = ent_off[t] + 8LL * t;
+  const int c0 = seg_col0[seg], nc = seg_ncol[seg];
+  for (int c = threadIdx.x; c < pad8(ncol + 1); c += blockDim.x) {
+    if (c < ncol) {
+      const int g = tmp_gcol[src + c];
+      int lo = 0, hi = nc;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sc_gcol[c0 + mid] < g) lo = mid + 1; else hi = mid;
+      }
+      const int slot = c0 + lo;
+      c_scol[co + c] = slot;
+      c_pisum0[co + c] = sc_pisum0[slot];
+      c_nuniq[co + c] = sc_nuniq[slot];
+      sc_inamb[slot] = 1;
+    } else {
+      c_scol[co + c] = 0;
+      c_pisum0[co + c] = 0.0;
+      c_nuniq[co + c] = 0;
+    }
+  }
+}
+
+// per segment totals: W_amb = sum of tile weight sums, W_uni = sum of pisum0, log Q of unique rows, w_max
+__global__ void seg_totals_kernel(int n_seg, const int* __restrict__ seg_tile0, const int* __restrict__ seg_ntiles,
+                                  const double* __restrict__ t_wsum, const int* __restrict__ seg_col0,
+                                  const int* __restrict__ seg_ncol, const double* __restrict__ sc_pisum0,
+                                  const double* __restrict__ sc_logq, const int* __restrict__ seg_smax,
+                                  double* __restrict__ seg_wamb, double* __restrict__ seg_wtot,
+                                  double* __restrict__ seg_logq, double* __restrict__ seg_wmax) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n_seg) return;
+  const int s = warp;
+  double wa = 0.0, wu = 0.0, lq = 0.0;
+  for (int t = lane; t < seg_ntiles[s]; t += 32) wa += t_wsum[seg_tile0[s] + t];
+  for (int j = lane; j < seg_ncol[s]; j += 32) {
+    wu += sc_pisum0[seg_col0[s] + j];
+    lq += sc_logq[seg_col0[s] + j];
+  }
+  wa = warp_sum(wa);
+  wu = warp_sum(wu);
+  lq = warp_sum(lq);
+  if (lane == 0) {
+    seg_wamb[s] = wa;
+    seg_wtot[s] = wa + wu;
+    seg_logq[s] = lq;
+    const int sm = seg_smax[s];
+    seg_wmax[s] = sm > 0 ? expm1(((double)sm * (1.0 / (double)sm)) * 100.0) : 0.0;   // model.py:189-190
+  }
+}
+
+__global__ void narrow_kernel(int n, const long long* __restrict__ in, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int)in[i];
+}
+__global__ void widen_int_kernel(int n, const int* __restrict__ in, long long* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+static size_t tile_build_smem() {
+  return (size_t)E_HARD * 8 * 2 + (size_t)(E_HARD * 4 + 2) * 4 + (size_t)(R_CAP * 3 + 2) * 4 +
+         (size_t)(BUILD_THREADS + 1) * 4 + 64;
+}
+
+inline unsigned grid_for(long long n, int b = 256) { return (unsigned)std::max<long long>(1, (n + b - 1) / b); }
+
+}  // namespace
+
+int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long long nnz, const int* row_ptr,
+                 const int* col_idx, const uint16_t* score, const int* row_segment, int n_segments) {
+  free_fit(h);
+  free_layout(h);
+  Layout& L = h->L;
+  auto& pool = h->layout_allocs;
+  TmpPool tmp;
+  const int N = n_rows, S = n_segments;
+  L.N = N; L.K = n_cols; L.S = S; L.A = nnz;
+  const size_t Sz = (size_t)std::max(S, 1);
+
+  // ---- step 1 ----
+  uint8_t *is_amb, *is_uni;
+  int* counters;
+  unsigned long long *segA_u, *segAamb_u;
+  SS_CUDA_CHECK(h, tmp.get(&is_amb, (size_t)N));
+  SS_CUDA_CHECK(h, tmp.get(&is_uni, (size_t)N));
+  SS_CUDA_CHECK(h, tmp.get(&counters, 8));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.seg_smax, Sz));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.seg_nobs, Sz));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.seg_namb, Sz));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.seg_nuniq, Sz));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.seg_A, Sz));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.seg_Aamb, Sz));
+  segA_u = reinterpret_cast<unsigned long long*>(L.seg_A);
+  segAamb_u = reinterpret_cast<unsigned long long*>(L.seg_Aamb);
+  SS_CUDA_CHECK(h, cudaMemsetAsync(counters, 0, 8 * sizeof(int), st));
+  SS_CUDA_CHECK(h, cudaMemsetAsync(L.seg_smax, 0, Sz * 4, st));
+  SS_CUDA_CHECK(h, cudaMemsetAsync(L.seg_nobs, 0, Sz * 4, st));
+  SS_CUDA_CHECK(h, cudaMemsetAsync(L.seg_namb, 0, Sz * 4, st));
+  SS_CUDA_CHECK(h, cudaMemsetAsync(L.seg_nuniq, 0, Sz * 4, st));
+  SS_CUDA_CHECK(h, cudaMemsetAsync(L.seg_A, 0, Sz * 8, st));
+  SS_CUDA_CHECK(h, cudaMemsetAsync(L.seg_Aamb, 0, Sz * 8, st));
+  if (N > 0) {
+    row_class_kernel<<<grid_for(N), 256, 0, st>>>(N, row_ptr, score, row_segment, S, is_amb, is_uni, L.seg_smax,
+                                                  L.seg_nobs, L.seg_namb, L.seg_nuniq, segA_u, segAamb_u, counters);
+    h->launches++;
+  }
+  // ---- step 2: ambiguous / unique row lists ----
+  int *iota, *ar_unsorted, *d_nsel;
+  SS_CUDA_CHECK(h, tmp.get(&iota, (size_t)N));
+  SS_CUDA_CHECK(h, tmp.get(&ar_unsorted, (size_t)N));
+  SS_CUDA_CHECK(h, tmp.get(&d_nsel, 2));
+  int* u_row_tmp;
+  SS_CUDA_CHECK(h, tmp.get(&u_row_tmp, (size_t)N));
+  int n_amb = 0, n_uniq = 0, maxlen = 0;
+  if (N > 0) {
+    iota_kernel<<<grid_for(N), 256, 0, st>>>(N, iota);
+    h->launches++;
+    CUB_CALL(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, iota, is_amb, ar_unsorted, d_nsel, N, st));
+    CUB_CALL(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, iota, is_uni, u_row_tmp, d_nsel + 1, N, st));
+    int hsel[2];
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(hsel, d_nsel, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(&maxlen, counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(h, cudaStreamSynchronize(st));
+    n_amb = hsel[0];
+    n_uniq = hsel[1];
+  }
+  if (maxlen > E_HARD / 2) {
+    h->set_error("a read has " + std::to_string(maxlen) + " alignments; the tile capacity is " +
+                 std::to_string(E_HARD / 2));
+    return SS_ERR_CAPACITY;
+  }
+  const int chunk = maxlen ? E_HARD - maxlen + 1 : E_HARD;
+  L.maxlen = maxlen;
+  L.chunk = chunk;
+  L.n_uniq = n_uniq;
+
+  // sort ambiguous rows by segment (stable: row order inside a segment)
+  int *aseg_in, *aseg, *ar;
+  SS_CUDA_CHECK(h, tmp.get(&aseg_in, (size_t)n_amb));
+  SS_CUDA_CHECK(h, tmp.get(&aseg, (size_t)n_amb));
+  SS_CUDA_CHECK(h, tmp.get(&ar, (size_t)n_amb));
+  long long *alen, *pre;
+  SS_CUDA_CHECK(h, tmp.get(&alen, (size_t)n_amb + 1));
+  SS_CUDA_CHECK(h, tmp.get(&pre, (size_t)n_amb + 1));
+  int n_tiles = 0;
+  long long *seg_row0, *seg_namb64, *seg_ntiles64, *seg_tile0_64, *seg_ent0;
+  SS_CUDA_CHECK(h, tmp.get(&seg_row0, Sz + 1));
+  SS_CUDA_CHECK(h, tmp.get(&seg_namb64, Sz + 1));
+  SS_CUDA_CHECK(h, tmp.get(&seg_ntiles64, Sz + 1));
+  SS_CUDA_CHECK(h, tmp.get(&seg_tile0_64, Sz + 1));
+  SS_CUDA_CHECK(h, tmp.get(&seg_ent0, Sz + 1));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.seg_tile0, Sz));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.seg_ntiles, Sz));
+  SS_CUDA_CHECK(h, cudaMemsetAsync(L.seg_tile0, 0, Sz * 4, st));
+  SS_CUDA_CHECK(h, cudaMemsetAsync(L.seg_ntiles, 0, Sz * 4, st));
+  SS_CUDA_CHECK(h, cudaMemsetAsync(alen, 0, ((size_t)n_amb + 1) * 8, st));
+  int* rtile = nullptr;
+  int* tile_row0 = nullptr;
+  if (n_amb > 0) {
+    gather_seg_len_kernel<<<grid_for(n_amb), 256, 0, st>>>(n_amb, ar_unsorted, row_segment, row_ptr, aseg_in, nullptr);
+    h->launches++;
+    int bits = 1;
+    while ((1LL << bits) < S) ++bits;
+    CUB_CALL(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, aseg_in, aseg, ar_unsorted, ar, n_amb, 0, bits, st));
+    gather_seg_len_kernel<<<grid_for(n_amb), 256, 0, st>>>(n_amb, ar, row_segment, row_ptr, nullptr, alen);
+    h->launches++;
+    CUB_CALL(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, alen, pre, n_amb + 1, st));
+    // ---- steps 3/4: tiles ----
+    widen_int_kernel<<<grid_for(S), 256, 0, st>>>(S, L.seg_namb, seg_namb64);
+    h->launches++;
+    CUB_CALL(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, seg_namb64, seg_row0, S, st));
+    seg_tiles_kernel<<<grid_for(S), 256, 0, st>>>(S, n_amb, seg_row0, L.seg_namb, pre, chunk, seg_ntiles64, seg_ent0);
+    h->launches++;
+    CUB_CALL(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, seg_ntiles64, seg_tile0_64, S, st));
+    narrow_kernel<<<grid_for(S), 256, 0, st>>>(S, seg_ntiles64, L.seg_ntiles);
+    narrow_kernel<<<grid_for(S), 256, 0, st>>>(S, seg_tile0_64, L.seg_tile0);
+    h->launches += 2;
+    long long last_t0 = 0, last_nt = 0;
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(&last_t0, seg_tile0_64 + (S - 1), 8, cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(&last_nt, seg_ntiles64 + (S - 1), 8, cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(h, cudaStreamSynchronize(st));
+    n_tiles = (int)(last_t0 + last_nt);
+    SS_CUDA_CHECK(h, tmp.get(&rtile, (size_t)n_amb));
+    SS_CUDA_CHECK(h, tmp.get(&tile_row0, (size_t)n_tiles + 1));
+    row_tile_kernel<<<grid_for(n_amb), 256, 0, st>>>(n_amb, aseg, pre, seg_ent0, seg_tile0_64, chunk, rtile);
+    tile_heads_kernel<<<grid_for(n_amb), 256, 0, st>>>(n_amb, n_tiles, rtile, tile_row0);
+    h->launches += 2;
+  }
+  L.n_tiles = n_tiles;
+  const size_t Tz = (size_t)std::max(n_tiles, 1);
+
+  // offsets of entry / row arrays
+  long long *pad_ent, *pad_row, *ent_off, *row_off, *pad_col, *pad_jds, *col_off, *jds_off, *key_cnt, *key_off;
+  SS_CUDA_CHECK(h, tmp.get(&pad_ent, Tz + 1));
+  SS_CUDA_CHECK(h, tmp.get(&pad_row, Tz + 1));
+  SS_CUDA_CHECK(h, tmp.get(&ent_off, Tz + 1));
+  SS_CUDA_CHECK(h, tmp.get(&row_off, Tz + 1));
+  SS_CUDA_CHECK(h, tmp.get(&pad_col, Tz + 1));
+  SS_CUDA_CHECK(h, tmp.get(&pad_jds, Tz + 1));
+  SS_CUDA_CHECK(h, tmp.get(&col_off, Tz + 1));
+  SS_CUDA_CHECK(h, tmp.get(&jds_off, Tz + 1));
+  SS_CUDA_CHECK(h, tmp.get(&key_cnt, Tz + 1));
+  SS_CUDA_CHECK(h, tmp.get(&key_off, Tz + 1));
+  int *t_ncol, *t_maxlen, *t_nlong, *t_seg, *t_nrows, *t_nent;
+  double* t_wsum;
+  SS_CUDA_CHECK(h, tmp.get(&t_ncol, Tz));
+  SS_CUDA_CHECK(h, tmp.get(&t_maxlen, Tz));
+  SS_CUDA_CHECK(h, tmp.get(&t_nlong, Tz));
+  SS_CUDA_CHECK(h, tmp.get(&t_seg, Tz));
+  SS_CUDA_CHECK(h, tmp.get(&t_nrows, Tz));
+  SS_CUDA_CHECK(h, tmp.get(&t_nent, Tz));
+  SS_CUDA_CHECK(h, tmp.get(&t_wsum, Tz));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.tile_hdr, Tz * HDR_WORDS));
+  long long tot[4] = {0, 0, 0, 0};
+  uint16_t* tmp_cptr = nullptr;
+  int* tmp_gcol = nullptr;
+  uint16_t* tmp_jptr = nullptr;
+  const int jds_stride = pad8(maxlen + 1);
+  long long n_tilekeys = 0;
+  if (n_tiles > 0) {
+    SS_CUDA_CHECK(h, cudaMemsetAsync(pad_ent + n_tiles, 0, 8, st));
+    SS_CUDA_CHECK(h, cudaMemsetAsync(pad_row + n_tiles, 0, 8, st));
+    tile_sizes_kernel<<<grid_for(n_tiles), 256, 0, st>>>(n_tiles, tile_row0, pre, pad_ent, pad_row);
+    h->launches++;
+    CUB_CALL(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, pad_ent, ent_off, n_tiles + 1, st));
+    CUB_CALL(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, pad_row, row_off, n_tiles + 1, st));
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(&tot[0], ent_off + n_tiles, 8, cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(&tot[1], row_off + n_tiles, 8, cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(h, cudaStreamSynchronize(st));
+  }
+  L.tot_ent = tot[0];
+  L.tot_row = tot[1];
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.e_lcol, (size_t)L.tot_ent));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.e_cpos, (size_t)L.tot_ent));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.e_q, (size_t)L.tot_ent));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.e_opos, (size_t)L.tot_ent));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.r_len, (size_t)L.tot_row));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.r_w, (size_t)L.tot_row));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.r_orow, (size_t)L.tot_row));
+  if (n_tiles > 0) {
+    const size_t tmpc = (size_t)L.tot_ent + 8 * (size_t)n_tiles + 8;
+    SS_CUDA_CHECK(h, tmp.get(&tmp_cptr, tmpc));
+    SS_CUDA_CHECK(h, tmp.get(&tmp_gcol, tmpc));
+    SS_CUDA_CHECK(h, tmp.get(&tmp_jptr, (size_t)jds_stride * n_tiles));
+    TileBuildArgs a;
+    a.row_ptr = row_ptr; a.col_idx = col_idx; a.score = score; a.ar = ar; a.aseg = aseg; a.tile_row0 = tile_row0;
+    a.pre = pre; a.ent_off = ent_off; a.row_off = row_off; a.seg_smax = L.seg_smax; a.n_tiles = n_tiles;
+    a.e_lcol = L.e_lcol; a.e_cpos = L.e_cpos; a.e_q = L.e_q; a.e_opos = L.e_opos;
+    a.r_len = L.r_len; a.r_w = L.r_w; a.r_orow = L.r_orow;
+    a.tmp_cptr = tmp_cptr; a.tmp_gcol = tmp_gcol; a.tmp_jptr = tmp_jptr; a.jds_stride = jds_stride;
+    a.t_ncol = t_ncol; a.t_maxlen = t_maxlen; a.t_nlong = t_nlong; a.t_seg = t_seg; a.t_nrows = t_nrows;
+    a.t_nent = t_nent; a.t_wsum = t_wsum;
+    const size_t smem = tile_build_smem();
+    SS_CUDA_CHECK(h, cudaFuncSetAttribute(tile_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tile_build_kernel<<<n_tiles, BUILD_THREADS, smem, st>>>(a);
+    h->launches++;
+    SS_CUDA_CHECK(h, cudaGetLastError());
+    SS_CUDA_CHECK(h, cudaMemsetAsync(pad_col + n_tiles, 0, 8, st));
+    SS_CUDA_CHECK(h, cudaMemsetAsync(pad_jds + n_tiles, 0, 8, st));
+    SS_CUDA_CHECK(h, cudaMemsetAsync(key_cnt + n_tiles, 0, 8, st));
+    tile_pad2_kernel<<<grid_for(n_tiles), 256, 0, st>>>(n_tiles, t_ncol, t_maxlen, pad_col, pad_jds);
+    widen_int_kernel<<<grid_for(n_tiles), 256, 0, st>>>(n_tiles, t_ncol, key_cnt);
+    h->launches += 2;
+    CUB_CALL(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, pad_col, col_off, n_tiles + 1, st));
+    CUB_CALL(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, pad_jds, jds_off, n_tiles + 1, st));
+    CUB_CALL(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, key_cnt, key_off, n_tiles + 1, st));
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(&tot[2], col_off + n_tiles, 8, cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(&tot[3], jds_off + n_tiles, 8, cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(&n_tilekeys, key_off + n_tiles, 8, cudaMemcpyDeviceToHost, st));
+    tile_hdr_kernel<<<grid_for(n_tiles), 256, 0, st>>>(n_tiles, t_seg, t_nrows, t_nent, t_ncol, t_maxlen, t_nlong,
+                                                       ent_off, row_off, col_off, jds_off, L.tile_hdr);
+    h->launches++;
+    h->hdr_host.resize((size_t)n_tiles * HDR_WORDS);
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(h->hdr_host.data(), L.tile_hdr, (size_t)n_tiles * HDR_WORDS * 8,
+                                     cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(h, cudaStreamSynchronize(st));
+  }
+  L.tot_col = tot[2];
+  L.tot_jds = tot[3];
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.c_ptr, (size_t)L.tot_col));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.c_scol, (size_t)L.tot_col));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.c_pisum0, (size_t)L.tot_col));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.c_nuniq, (size_t)L.tot_col));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.j_ptr, (size_t)L.tot_jds));
+
+  // ---- step 6: segment columns ----
+  const long long n_keys = n_tilekeys + n_uniq;
+  unsigned long long *keys_all, *keys_sorted, *sc_key;
+  SS_CUDA_CHECK(h, tmp.get(&keys_all, (size_t)n_keys));
+  SS_CUDA_CHECK(h, tmp.get(&keys_sorted, (size_t)n_keys));
+  SS_CUDA_CHECK(h, tmp.get(&sc_key, (size_t)n_keys));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.u_row, (size_t)n_uniq));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.u_pos, (size_t)n_uniq));
+  if (n_tiles > 0) {
+    tile_compact_kernel<<<n_tiles, 128, 0, st>>>(n_tiles, L.tile_hdr, tmp_cptr, tmp_gcol, tmp_jptr, jds_stride, ent_off,
+                                                 key_off, L.c_ptr, L.j_ptr, keys_all);
+    h->launches++;
+  }
+  if (n_uniq > 0) {
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(L.u_row, u_row_tmp, (size_t)n_uniq * 4, cudaMemcpyDeviceToDevice, st));
+    uniq_keys_kernel<<<grid_for(n_uniq), 256, 0, st>>>(n_uniq, L.u_row, row_ptr, col_idx, row_segment, L.u_pos,
+                                                       keys_all + n_tilekeys);
+    h->launches++;
+  }
+  long long n_sc = 0;
+  if (n_keys > 0) {
+    if (n_keys > 0x7fffffffLL) {
+      h->set_error("too many (segment, locus) pairs");
+      return SS_ERR_CAPACITY;
+    }
+    int kbits = 33;
+    while ((1LL << (kbits - 32)) < S && kbits < 64) ++kbits;
+    CUB_CALL(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, keys_all, keys_sorted, (int)n_keys, 0, kbits, st));
+    CUB_CALL(cub::DeviceSelect::Unique(d_tmp, tmp_bytes, keys_sorted, sc_key, d_nsel, (int)n_keys, st));
+    int nsel = 0;
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(&nsel, d_nsel, 4, cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(h, cudaStreamSynchronize(st));
+    n_sc = nsel;
+  }
+  L.n_segcols = n_sc;
+  const size_t NCz = (size_t)std::max<long long>(n_sc, 1);
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.seg_col0, Sz));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.seg_ncol, Sz));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.sc_gcol, NCz));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.sc_pisum0, NCz));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.sc_nuniq, NCz));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &h->sc_inamb, NCz));
+  double* sc_logq;
+  SS_CUDA_CHECK(h, tmp.get(&sc_logq, NCz));
+  SS_CUDA_CHECK(h, cudaMemsetAsync(L.sc_pisum0, 0, NCz * 8, st));
+  SS_CUDA_CHECK(h, cudaMemsetAsync(L.sc_nuniq, 0, NCz * 4, st));
+  SS_CUDA_CHECK(h, cudaMemsetAsync(h->sc_inamb, 0, NCz, st));
+  SS_CUDA_CHECK(h, cudaMemsetAsync(sc_logq, 0, NCz * 8, st));
+  if (S > 0) {
+    seg_cols_kernel<<<grid_for(S), 256, 0, st>>>(S, sc_key, n_sc, L.seg_col0, L.seg_ncol);
+    h->launches++;
+  }
+  if (n_sc > 0) {
+    sc_gcol_kernel<<<grid_for(n_sc), 256, 0, st>>>(n_sc, sc_key, L.sc_gcol);
+    h->launches++;
+  }
+  if (n_uniq > 0) {
+    unsigned long long* uk_sorted;
+    int *uidx, *uidx_sorted;
+    SS_CUDA_CHECK(h, tmp.get(&uk_sorted, (size_t)n_uniq));
+    SS_CUDA_CHECK(h, tmp.get(&uidx, (size_t)n_uniq));
+    SS_CUDA_CHECK(h, tmp.get(&uidx_sorted, (size_t)n_uniq));
+    iota_kernel<<<grid_for(n_uniq), 256, 0, st>>>(n_uniq, uidx);
+    h->launches++;
+    int kbits = 33;
+    while ((1LL << (kbits - 32)) < S && kbits < 64) ++kbits;
+    CUB_CALL(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, keys_all + n_tilekeys, uk_sorted, uidx, uidx_sorted,
+                                             n_uniq, 0, kbits, st));
+    uniq_runs_kernel<<<grid_for(n_uniq), 256, 0, st>>>(n_uniq, uk_sorted, uidx_sorted, L.u_pos, score, L.seg_smax,
+                                                       sc_key, n_sc, L.sc_pisum0, L.sc_nuniq, sc_logq);
+    h->launches++;
+  }
+  // ---- step 7: tile columns -> segment columns; segment totals ----
+  if (n_tiles > 0) {
+    tile_scol_kernel<<<n_tiles, 128, 0, st>>>(L.tile_hdr, ent_off, tmp_gcol, L.seg_col0, L.seg_ncol, L.sc_gcol,
+                                              L.sc_pisum0, L.sc_nuniq, h->sc_inamb, L.c_scol, L.c_pisum0, L.c_nuniq);
+    h->launches++;
+  }
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.seg_wmax, Sz));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.seg_wtot, Sz));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.seg_wamb, Sz));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.seg_logq_uniq, Sz));
+  if (S > 0) {
+    seg_totals_kernel<<<grid_for((long long)S * 32), 256, 0, st>>>(S, L.seg_tile0, L.seg_ntiles, t_wsum, L.seg_col0,
+                                                                    L.seg_ncol, L.sc_pisum0, sc_logq, L.seg_smax,
+                                                                    L.seg_wamb, L.seg_wtot, L.seg_logq_uniq,
+                                                                    L.seg_wmax);
+    h->launches++;
+  }
+  SS_CUDA_CHECK(h, cudaGetLastError());
+  // ---- launch plan ----
+  h->seg_ntiles_host.assign(Sz, 0);
+  h->seg_tile0_host.assign(Sz, 0);
+  std::vector<int> ncol_host(Sz, 0), col0_host(Sz, 0);
+  if (S > 0) {
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(h->seg_ntiles_host.data(), L.seg_ntiles, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(h->seg_tile0_host.data(), L.seg_tile0, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(ncol_host.data(), L.seg_ncol, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(col0_host.data(), L.seg_col0, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
+  }
+  SS_CUDA_CHECK(h, cudaStreamSynchronize(st));
+  int rc = layout_plan(h, st, ncol_host, col0_host);
+  if (rc != SS_OK) return rc;
+  h->has_layout = true;
+  return SS_OK;
+}
+
+}  // namespace ss

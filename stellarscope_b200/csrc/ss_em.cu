@@ -580,6 +580,8 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
   h->P = P;
   h->P.K = L.K;
 
+#define SS_MARK(i) if (h->timing) SS_CUDA_CHECK(h, cudaEventRecord(h->ev[i], st))
+  SS_MARK(0);
   if (L.S > 0) {
     const int warps_per_block = 8;
     fit_prepare_kernel<<<(L.S + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
@@ -596,6 +598,7 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
   const bool lnl = P.use_likelihood != 0;
 
   // streaming kernel first (long running, cooperative), then the resident classes
+  SS_MARK(1);
   if (h->n_stream_tiles > 0) {
     StreamArgs sa;
     sa.tiles = h->stream_tiles;
@@ -626,6 +629,7 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     h->launches++;
     SS_CUDA_CHECK(h, cudaGetLastError());
   }
+  SS_MARK(2);
   for (int c = SS_NUM_CLASSES - 1; c >= 0; --c) {
     a.tile_list = h->cls_tiles[c];
     a.n_list = h->cls_count[c];
@@ -639,7 +643,8 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     }
     SS_CUDA_CHECK(h, e);
   }
-  // final lnL of the streamed tiles (not needed in likelihood mode: the trace has it)
+  SS_MARK(3);
+  // final lnL of the streamed tiles
   if (h->n_stream_tiles > 0) {
     a.tile_list = h->stream_tiles;
     a.n_list = h->n_stream_tiles;
@@ -650,12 +655,15 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     h->launches++;
     SS_CUDA_CHECK(h, cudaGetLastError());
   }
+  SS_MARK(4);
   if (L.S > 0) {
     const int warps_per_block = 8;
     fit_finalize_kernel<<<(L.S + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(L, F, h->P);
     h->launches++;
     SS_CUDA_CHECK(h, cudaGetLastError());
   }
+  SS_MARK(5);
+  h->ev_valid = h->timing;
   h->has_fit = true;
   return SS_OK;
 }

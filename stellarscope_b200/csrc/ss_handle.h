@@ -45,6 +45,11 @@ struct ss_handle_s {
   std::vector<void*> fit_allocs;
   int* stream_ctl = nullptr;      // device control words of the streaming kernel
 
+  // measurement aid: events around the kernel groups of the last fit
+  bool timing = false;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid = false;
+
   // multi-GPU hook
   ss_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;

@@ -165,10 +165,4 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
   return SS_OK;
 }
 
-int layout_build(ss_handle_s* h, cudaStream_t, int, int, long long, const int*, const int*, const uint16_t*,
-                 const int*, int) {
-  h->set_error("ss_layout_build: device builder not compiled in yet");
-  return SS_ERR_STATE;
-}
-
 }  // namespace ss

@@ -87,6 +87,17 @@ class Engine:
     def launch_count(self):
         return int(self.lib.ss_launch_count(self.h))
 
+    def enable_timing(self, on=True):
+        self._check(self.lib.ss_set_timing(self.h, int(bool(on))))
+
+    def last_timings(self):
+        """Device time (ms) of the kernel groups of the last ss_em_fit (synchronises):
+        prepare, streaming kernel, resident kernels, emit, finalize."""
+        buf = (C.c_double * 8)()
+        self._check(self.lib.ss_get_timings(self.h, buf, 8))
+        names = ('prepare', 'stream', 'resident', 'emit', 'finalize')
+        return {n: float(buf[i]) for i, n in enumerate(names)}
+
     # -- layout --------------------------------------------------------------
     def set_matrix(self, indptr, indices, scores, K):
         """Upload the N x K uint16 CSR score matrix (host arrays) to the device."""
@@ -263,6 +274,8 @@ class Engine:
         """ss_count.  Returns COO (cell, col, val) numpy arrays sorted by (cell, col)."""
         dev = self.device
         k = self._keep
+        if self.A == 0:
+            return (np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.float64))
         with torch.cuda.device(dev):
             rc_t = row_cell if isinstance(row_cell, torch.Tensor) else self._to_dev(row_cell, np.int32)
             ru_t = None

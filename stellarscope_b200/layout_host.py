@@ -114,8 +114,9 @@ def build(indptr, indices, scores, row_seg, S, K, e_hard=E_HARD, long_col=64):
         inv = 1.0 / seg_smax.astype(np.float64)
     Q = np.zeros(A, dtype=np.float64)
     Q[ef] = np.expm1((scores[ef].astype(np.float64) * inv[eseg[ef]]) * 100.0)
-    seg_wmax = np.where(seg_smax > 0,
-                        np.expm1((seg_smax.astype(np.float64) * inv) * 100.0), 0.0)
+    with np.errstate(invalid='ignore'):
+        seg_wmax = np.where(seg_smax > 0,
+                            np.expm1((seg_smax.astype(np.float64) * inv) * 100.0), 0.0)
     # row weights w_i = max_j Q_ij (model.py:183)
     w = np.zeros(N, dtype=np.float64)
     nz = np.flatnonzero(lens > 0)

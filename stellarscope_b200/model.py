@@ -1,0 +1,438 @@
+"""Host-side mirror of the reference's model API for the EM path.
+
+Same names, argument meaning and error behaviour as
+``stellarscope/utils/model.py`` (``TelescopeLikelihood`` :87-507,
+``_fit_pooling_model`` :675-804, ``Stellarscope.reassign`` :1239-1256,
+``Stellarscope.output_report`` :1291-1420) -- but every model of a pooling
+mode lives in ONE device layout and is fitted by one call into
+libstellarscope_b200.so.  Nothing here evaluates the model on the CPU; without
+a CUDA device construction fails.
+"""
+from __future__ import annotations
+
+import logging as lg
+import sys
+import time
+from collections import OrderedDict
+from typing import Optional
+
+import numpy as np
+import scipy.sparse
+
+from .engine import Engine, ModelError
+from .sparse_plus import csr_matrix_plus
+from .statistics import FitInfo, PoolInfo, ReassignInfo, counter_from_hist
+
+TIE_TOL_DEFAULT = 1e-9
+
+
+class StellarscopeError(Exception):
+    """Stands in for ``stellarscope.StellarscopeError`` when the reference
+    package is not importable; ``install()`` rebinds it to the real class."""
+
+
+def _canonical_csr(m):
+    m = scipy.sparse.csr_matrix(m)
+    if not m.has_canonical_format:
+        m = m.copy()
+        m.sum_duplicates()
+    if (m.data == 0).any():
+        m = m.copy()
+        m.eliminate_zeros()                      # model.py:114
+    if not m.has_sorted_indices:
+        m.sort_indices()
+    return m
+
+
+class TelescopeLikelihood(object):
+    """Drop-in for the reference class of the same name.
+
+    ``row_segment`` / ``n_segments`` are an extension used by
+    ``_fit_pooling_model``: row i belongs to model ``row_segment[i]`` (-1: to
+    none).  Without them the object is one model over the whole matrix, exactly
+    like the reference's ``TelescopeLikelihood(score_matrix, opts)``.
+    """
+
+    REASSIGN_MODES = [          # model.py:92-100
+        'best_exclude', 'best_conf', 'best_random', 'best_average',
+        'initial_unique', 'initial_random', 'total_hits',
+    ]
+
+    def __init__(self, score_matrix, opts, row_segment=None, n_segments=None, device=None,
+                 tie_tol=TIE_TOL_DEFAULT):
+        self.opts = opts
+        self.epsilon = opts.em_epsilon
+        self.max_iter = opts.max_iter
+        self.pi_prior = opts.pi_prior
+        self.theta_prior = opts.theta_prior
+        self.tie_tol = tie_tol
+        self.raw_scores = csr_matrix_plus(_canonical_csr(score_matrix))
+        self.N, self.K = self.raw_scores.shape
+        self.max_score = int(self.raw_scores.data.max()) if self.raw_scores.nnz else 0
+        self.scale_factor = 100.
+        if self.raw_scores.nnz and int(self.raw_scores.data.max()) > 65535:
+            raise StellarscopeError('alignment scores above 65535 are not supported (uint16, model.py:964)')
+        if row_segment is None:
+            row_segment = np.zeros(self.N, dtype=np.int32)
+            n_segments = 1
+        self.row_segment = np.ascontiguousarray(row_segment, dtype=np.int32)
+        self.n_segments = int(n_segments)
+
+        self._engine = Engine(device)
+        self._engine.set_matrix(self.raw_scores.indptr, self.raw_scores.indices,
+                                self.raw_scores.data.astype(np.uint16, copy=False), self.K)
+        self._engine.build_layout(self.row_segment, self.n_segments)
+
+        self._z = None
+        self._z_dev = None
+        self.pi = csr_matrix_plus(np.repeat(1. / self.K, self.K))     # model.py:164
+        self.pi_init = None
+        self.theta = np.repeat(1. / self.K, self.K)                   # model.py:172
+        self.theta_init = None
+        self.lnl = float('inf')
+        self.fitinfo = FitInfo(epsilon=self.epsilon, max_iter=self.max_iter)
+        self.segment_fitinfo = None
+        self.fit_seconds = None
+
+    # -- lazily materialised views the reference exposes as attributes ----------
+    @property
+    def Q(self):
+        """model.py:129-130 for a single-model object (lazy, host; not used by the fit)."""
+        if self.n_segments != 1:
+            raise AttributeError('Q is per model; this object holds several models')
+        q = self.raw_scores.astype(np.float64)
+        if q.nnz:
+            q.data = np.expm1((q.data * (1.0 / self.max_score)) * self.scale_factor)
+        return csr_matrix_plus(q)
+
+    def _y(self, pred):
+        n = np.diff(self.raw_scores.indptr)
+        return csr_matrix_plus(np.asmatrix(pred(n)).T, dtype=np.ubyte)
+
+    @property
+    def Y_amb(self):
+        return self._y(lambda n: n > 1)           # model.py:141
+
+    @property
+    def Y_uni(self):
+        return self._y(lambda n: n == 1)
+
+    @property
+    def Y_0(self):
+        return self._y(lambda n: n == 0)
+
+    @property
+    def z(self):
+        """N x K CSR float64 posterior (model.py:356; summed over models, :790).
+        Copied from the device on first access."""
+        if self._z is None:
+            if self.segment_fitinfo is None:
+                return None
+            zd = self._z_device().cpu().numpy()
+            m = csr_matrix_plus((zd, self.raw_scores.indices.copy(), self.raw_scores.indptr.copy()),
+                                shape=self.raw_scores.shape)
+            self._z = m
+        return self._z
+
+    @z.setter
+    def z(self, value):
+        self._z = value
+
+    def _z_device(self):
+        if self._z_dev is None:
+            self._z_dev = self._engine.emit_z()
+        return self._z_dev
+
+    # -- fit -------------------------------------------------------------------
+    def fit_segments(self):
+        """Fit every model of the layout; returns the list of FitInfo in segment order."""
+        import torch
+        o = self.opts
+        eng = self._engine
+        t0 = time.perf_counter()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(torch.cuda.current_stream(eng.device))
+        eng.fit(self.epsilon, self.max_iter, self.pi_prior, self.theta_prior,
+                bool(getattr(o, 'use_likelihood', False)))
+        end.record(torch.cuda.current_stream(eng.device))
+        res = eng.results(traces=True)
+        self.fit_seconds = start.elapsed_time(end) / 1e3
+        self.fit_wall_seconds = time.perf_counter() - t0
+        if (res['flags'] & 4).any():
+            bad = int(np.flatnonzero(res['flags'] & 4)[0])
+            # 0/0 in the M-step: FloatingPointError -> StellarscopeError, model.py:267-272
+            raise StellarscopeError(('invalid value encountered in divide',
+                                     f'model {bad} has no alignments or a zero denominator'))
+        tot_it = max(1, int(res['iters'].sum()))
+        infos = []
+        for s in range(self.n_segments):
+            fi = FitInfo(nobs=int(res['nobs'][s]), nfeats=int(res['nfeats'][s]), epsilon=self.epsilon,
+                         max_iter=self.max_iter)
+            n = int(res['iters'][s])
+            fi.converged = bool(res['flags'][s] & 1)
+            fi.reached_max = bool(res['flags'][s] & 2)
+            itime = self.fit_seconds / tot_it
+            fi.iterations = [(i + 1, itime, float(res['diffs'][s, i])) for i in range(n)]
+            fi.final_lnl = float(res['lnl'][s])
+            infos.append(fi)
+        self.segment_fitinfo = infos
+        self._results = res
+        self._z = None
+        self._z_dev = None
+        return infos
+
+    def em(self, loglev=lg.DEBUG):
+        """model.py:325-373 for a single-model object."""
+        if self.n_segments != 1:
+            raise StellarscopeError('em() is for a single model; use fit_segments()')
+        fi = self.fit_segments()[0]
+        self.fitinfo = fi
+        pi, theta = self._engine.dense_params(0)
+        self.pi = csr_matrix_plus(pi)
+        self.theta = theta
+        self.lnl = fi.final_lnl
+        for inum, _t, diff in fi.iterations:
+            lg.log(loglev, 'Iteration {:d}, diff={:.5g}'.format(inum, diff))
+        if fi.converged:
+            lg.log(loglev, f'EM converged after {len(fi.iterations):d} iterations.')
+        elif fi.reached_max:
+            lg.log(loglev, f'EM terminated after {len(fi.iterations):d} iterations.')
+        lg.log(loglev, f'Final log-likelihood: {self.lnl:f}.')
+        return
+
+    def segment_params(self, seg):
+        """(pi, theta) dense K-vectors of one model of a pooled fit."""
+        return self._engine.dense_params(seg)
+
+    # -- reassign: model.py:375-507 --------------------------------------------
+    def reassign(self, mode: str, thresh: Optional[float] = None):
+        if mode not in self.REASSIGN_MODES:
+            msg = f'Argument "method" should be one of {self.REASSIGN_MODES}'
+            raise ValueError(msg)
+        if mode == 'best_conf' and (thresh is None or thresh <= 0.5):
+            raise StellarscopeError(f"Confidence threshold ({thresh}) must be > 0.5")
+        needs_z = mode in ('best_exclude', 'best_conf', 'best_random', 'best_average')
+        z = None
+        if needs_z:
+            if self.segment_fitinfo is None:
+                raise StellarscopeError('reassign_mat was not set.')     # model.py:504-505 (no z)
+            z = self._z_device()
+        flag, nbest, info = self._engine.reassign(mode, z, thresh if thresh is not None else 0.0, self.tie_tol)
+        flag = flag.cpu().numpy().astype(bool)
+        rinfo = ReassignInfo(mode)
+        rinfo.assigned, rinfo.ambiguous, rinfo.unaligned = int(info[0]), int(info[1]), int(info[2])
+        if mode in ('best_exclude', 'best_random', 'best_average', 'initial_random'):
+            rinfo.ambigous_dist = counter_from_hist(info[4:])
+        indptr, indices = self.raw_scores.indptr, self.raw_scores.indices
+        row = np.repeat(np.arange(self.N, dtype=np.int64), np.diff(indptr))
+        if mode in ('best_random', 'initial_random'):
+            flag = _replay_random_choice(flag, row, nbest.cpu().numpy(), self.opts.rng)
+        keep_rows = row[flag]
+        ptr = np.zeros(self.N + 1, dtype=indptr.dtype)
+        np.cumsum(np.bincount(keep_rows, minlength=self.N), out=ptr[1:])
+        if mode == 'best_average':
+            nb = nbest.cpu().numpy()
+            data = 1.0 / nb[keep_rows].astype(np.float64)
+        else:
+            data = np.ones(len(keep_rows), dtype=np.int8)
+        mat = csr_matrix_plus((data, indices[flag], ptr), shape=self.raw_scores.shape)
+        return mat, rinfo
+
+
+def _replay_random_choice(flag, row, nbest, rng):
+    """``choose_random(1, rng)`` (sparse_plus.py:231-240) on the tie sets the device
+    found: for every row with more than one tied-best alignment, in row order,
+    the reference draws ``rng.choice(range(start, end))``; numpy produces the
+    same stream for one vectorised ``rng.integers(0, n)`` call (checked in
+    tests/test_oracle.py), so the draws are replayed on the host and applied
+    as a mask."""
+    tied_rows = np.flatnonzero(nbest > 1)
+    if len(tied_rows) == 0:
+        return flag
+    picks = rng.integers(0, nbest[tied_rows])
+    pos = np.flatnonzero(flag)                 # tied-best alignments, CSR order
+    prow = row[pos]
+    start = np.zeros(len(nbest) + 1, dtype=np.int64)
+    np.cumsum(nbest, out=start[1:])            # start of each row inside `pos`
+    in_tied = nbest[prow] > 1
+    out = flag.copy()
+    out[pos[in_tied]] = False
+    out[pos[start[tied_rows] + picks]] = True
+    return out
+
+
+def _em_wrapper(tl: TelescopeLikelihood):
+    tl.em()
+    return tl.z, tl.fitinfo
+
+
+def pooling_row_segments(st, opts):
+    """Row -> model map of a pooling mode (model.py:701-743).  Returns
+    ``(row_segment int32[N], keys)`` where ``keys[i]`` is the key of model i in
+    ``PoolInfo.models_info`` (model.py:766, 791)."""
+    N = st.shape[0]
+    if opts.pooling_mode == 'pseudobulk':
+        return np.zeros(N, dtype=np.int32), ['pseudobulk']
+    seg = np.full(N, -1, dtype=np.int32)
+    i = 0
+    if opts.pooling_mode == 'individual':
+        for _bcode, rowset in st.bcode_ridx_map.items():
+            if not rowset:
+                lg.info(f'        ...not fitting "{_bcode}" -> no reads found')
+                continue
+            rows = np.fromiter(rowset, dtype=np.int64, count=len(rowset))
+            if (seg[rows] >= 0).any():
+                raise StellarscopeError('a read belongs to more than one barcode')
+            seg[rows] = i
+            i += 1
+    elif opts.pooling_mode == 'celltype':
+        for _ctype in st.celltypes:
+            rows = []
+            for _bcode in st.ctype_bcode_map[_ctype]:
+                if _bcode in st.bcode_ridx_map:
+                    rows.extend(st.bcode_ridx_map[_bcode])
+            if not rows:
+                lg.info(f'        ...not fitting "{_ctype}" -> no reads found')
+                continue
+            rows = np.unique(np.asarray(rows, dtype=np.int64))
+            if (seg[rows] >= 0).any():
+                raise StellarscopeError('a barcode belongs to more than one celltype (not supported)')
+            seg[rows] = i
+            i += 1
+    else:
+        raise StellarscopeError(f'unknown pooling mode {opts.pooling_mode}')
+    return seg, list(range(i))
+
+
+def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
+    """Fit model using different pooling modes (model.py:675-804).
+
+    ``processes`` / ``opts.nproc`` are ignored for the fit: all models run
+    concurrently on the GPU.  Returns ``(TelescopeLikelihood, PoolInfo)``."""
+    poolinfo = PoolInfo(opts.pooling_mode)
+    if opts.ignore_umi:                                     # model.py:749-758
+        if getattr(st, 'corrected', None) is not None:
+            lg.warning('Ignoring UMI corrected matrix')
+        fullmat = st.raw_scores
+    else:
+        if getattr(st, 'corrected', None) is None:
+            raise StellarscopeError("UMI corrected matrix not found")
+        if st.corrected.shape != st.shape:
+            raise StellarscopeError("UMI corrected matrix shape mismatch")
+        fullmat = st.corrected
+
+    row_segment, keys = pooling_row_segments(st, opts)
+    if opts.pooling_mode == 'pseudobulk':
+        lg.info('Models to fit: 1')
+        ret_model = TelescopeLikelihood(fullmat, opts)
+        poolinfo.nmodels = 1
+        ret_model.em()
+        poolinfo.models_info['pseudobulk'] = ret_model.fitinfo
+        return ret_model, poolinfo
+
+    poolinfo.nmodels = (len(st.bcode_ridx_map) if opts.pooling_mode == 'individual'
+                        else len(st.celltypes))             # model.py:772, 778
+    lg.info(f'Models to fit: {poolinfo.nmodels}')
+    ret_model = TelescopeLikelihood(fullmat, opts, row_segment=row_segment, n_segments=len(keys))
+    infos = ret_model.fit_segments()
+    for k, fi in zip(keys, infos):
+        poolinfo.models_info[k] = fi
+    lg.info(f'        ...{len(infos)} models fitted')
+    ret_model.lnl = poolinfo.total_lnl                      # model.py:803
+    return ret_model, poolinfo
+
+
+# ---------------------------------------------------------------------------
+# Stellarscope.reassign / output_report  (model.py:1239-1256, 1291-1420)
+# ---------------------------------------------------------------------------
+def reassign(st, tl: TelescopeLikelihood):
+    """``Stellarscope.reassign``: every mode of ``opts.reassign_mode`` in order
+    (the modes share ``opts.rng``)."""
+    if not hasattr(st, 'reassignments'):
+        st.reassignments = {}
+    rmode_info = {}
+    for _rmode in st.opts.reassign_mode:
+        _thresh = st.opts.conf_prob if _rmode == 'best_conf' else None
+        _rmat, _rinfo = tl.reassign(_rmode, _thresh)
+        st.reassignments[_rmode] = _rmat
+        rmode_info[_rmode] = _rinfo
+    return rmode_info
+
+
+def count_matrices(st, tl: TelescopeLikelihood):
+    """The aggregation half of ``output_report`` (agg_bc / agg_bc_umi,
+    model.py:1302-1345): ``{mode: (numft x numbc) scipy CSR}`` plus the barcode
+    and feature lists in output order (:1371-1378)."""
+    if getattr(st, 'filtlist', None):
+        bc_list = sorted(st.filtlist, key=st.filtlist.get)
+    else:
+        bc_list = sorted(st.bcode_ridx_map.keys())
+    ft_list = sorted(st.feat_index, key=st.feat_index.get)
+    numft, numbc = len(ft_list), len(bc_list)
+    bc_pos = {b: i for i, b in enumerate(bc_list)}
+    qnames = sorted(st.read_index, key=st.read_index.get)           # model.py:1389
+    row_cell = np.fromiter((bc_pos.get(st.read_bcode_map[q], -1) for q in qnames), dtype=np.int32,
+                           count=len(qnames))
+    row_umi = None
+    if st.opts.umi_counts:
+        umi_ids = {}
+        row_umi = np.fromiter((umi_ids.setdefault(st.read_umi_map[q], len(umi_ids)) for q in qnames),
+                              dtype=np.int32, count=len(qnames))
+    out = OrderedDict()
+    for _rmode in st.opts.reassign_mode:
+        remat = st.reassignments[_rmode]
+        out[_rmode] = remat.count_by_cell(row_cell, numbc, row_umi=row_umi, engine=tl._engine)
+        if out[_rmode].shape != (numft, numbc):
+            raise StellarscopeError(f'Incompatible shapes: {out[_rmode].shape} != {(numft, numbc)}')
+    return out, bc_list, ft_list
+
+
+def output_report(st, tl: TelescopeLikelihood):
+    """``Stellarscope.output_report``: barcodes.tsv, features.tsv, TE_counts[.mode].mtx."""
+    import scipy.io
+    counts, bc_list, ft_list = count_matrices(st, tl)
+    with open(st.opts.outfile_path('barcodes.tsv'), 'w') as outh:
+        print('\n'.join(bc_list), file=outh)
+    with open(st.opts.outfile_path('features.tsv'), 'w') as outh:
+        print('\n'.join(ft_list), file=outh)
+    for rmode_i, (_rmode, _counts) in enumerate(counts.items()):
+        if rmode_i == 0:
+            out_mtx = st.opts.outfile_path('TE_counts.mtx')
+        else:
+            out_mtx = st.opts.outfile_path(f'TE_counts.{_rmode}.mtx')
+        scipy.io.mmwrite(out_mtx, _counts, comment=_mtx_meta(st, _rmode))
+    return
+
+
+def _mtx_meta(st, reassign_mode):
+    """MTX comment block (model.py:1347-1368)."""
+    o = st.opts
+    meta = OrderedDict({'PN': 'stellarscope', 'VN': getattr(o, 'version', '')})
+    for k in ('samfile', 'checkpoint', 'gtffile', 'filtered_bc'):
+        if hasattr(o, k):
+            meta[k] = getattr(o, k)
+    meta['pooling_mode'] = o.pooling_mode
+    meta['reassign_mode'] = reassign_mode
+    if o.ignore_umi:
+        meta['ignore_umi'] = 'Yes'
+        meta['umi_counts'] = 'Yes' if o.umi_counts else 'No'
+    meta['command'] = ' '.join(sys.argv)
+    return '\n '.join(f'{k}: {v}' for k, v in meta.items())
+
+
+def install():
+    """Make ``stellarscope assign`` / ``resume`` use this implementation:
+    rebinds the hot-path names of the reference's ``stellarscope.utils.model``
+    (must be importable) -- see INTEGRATION.md."""
+    global StellarscopeError
+    import stellarscope
+    import stellarscope.utils.model as ref
+    StellarscopeError = stellarscope.StellarscopeError
+    from . import sparse_plus
+    sparse_plus.StellarscopeError = StellarscopeError
+    ref.TelescopeLikelihood = TelescopeLikelihood
+    ref._fit_pooling_model = _fit_pooling_model
+    ref._em_wrapper = _em_wrapper
+    ref.Stellarscope.reassign = lambda self, tl: reassign(self, tl)
+    ref.Stellarscope.output_report = lambda self, tl: output_report(self, tl)
+    return ref

@@ -1,0 +1,90 @@
+"""``csr_matrix_plus`` -- scipy CSR with the per-cell aggregation the report needs.
+
+Mirror of the part of the reference's ``stellarscope/utils/sparse_plus.py``
+class that the hot path's callers use on reassignment matrices
+(``groupby_sum`` :367-396 via ``output_report`` model.py:1311, 1336;
+``check_equal`` :242-245; ``save``/``load`` :398-405).  The aggregation runs on
+the device (``ss_count``); instances hold no device state, so they pickle like
+plain scipy matrices (``Stellarscope.save``, model.py:1259-1274).
+"""
+from __future__ import annotations
+
+from collections.abc import Mapping
+
+import numpy as np
+import scipy.sparse
+
+
+class StellarscopeError(Exception):
+    pass
+
+
+_engine_cache = {}
+
+
+def _default_engine():
+    from .engine import Engine
+    if 'e' not in _engine_cache:
+        _engine_cache['e'] = Engine()
+    return _engine_cache['e']
+
+
+class csr_matrix_plus(scipy.sparse.csr_matrix):
+
+    def check_equal(self, other):
+        if self.shape != other.shape:
+            return False
+        return (self != other).nnz == 0
+
+    def save(self, filename):
+        np.savez(filename, data=self.data, indices=self.indices, indptr=self.indptr, shape=self.shape)
+
+    @classmethod
+    def load(cls, filename):
+        loader = np.load(filename)
+        return cls((loader['data'], loader['indices'], loader['indptr']), shape=loader['shape'])
+
+    # -- device aggregation ----------------------------------------------------
+    def _device_coo(self, row_group, row_umi, engine):
+        """COO (group, col, value) of sum over rows of each group, on the device."""
+        import torch
+        eng = _default_engine()          # a separate handle: the model's engine keeps its score matrix
+        m = self
+        if not m.has_sorted_indices:
+            m = m.copy()
+            m.sort_indices()
+        eng.set_matrix(m.indptr, m.indices, np.zeros(m.nnz, dtype=np.uint16), m.shape[1])
+        flag = eng._to_dev((m.data != 0).astype(np.uint8) if m.nnz else np.zeros(1, np.uint8), np.uint8)
+        weight = None
+        if not np.issubdtype(m.dtype, np.integer) or (m.nnz and (m.data != 1).any()):
+            weight = eng._to_dev(m.data.astype(np.float64), np.float64)
+        return eng.count(flag, row_group, weight=weight, row_umi=row_umi)
+
+    def count_by_cell(self, row_cell, n_cells, row_umi=None, engine=None):
+        """(K x n_cells) matrix of per-cell column sums -- ``agg_bc`` /
+        ``agg_bc_umi`` (model.py:1302-1345).  ``row_cell[i]`` = output column
+        of row i (-1: dropped).  int32 for integer matrices, float64 otherwise
+        and always float64 in UMI mode (model.py:1341)."""
+        cell, col, val = self._device_coo(np.ascontiguousarray(row_cell, dtype=np.int32),
+                                          None if row_umi is None else np.ascontiguousarray(row_umi, np.int32),
+                                          engine)
+        integer = np.issubdtype(self.dtype, np.integer) and row_umi is None
+        dtype = np.int32 if integer else np.float64
+        out = scipy.sparse.csr_matrix((val.astype(dtype), (col, cell)), shape=(self.shape[1], n_cells))
+        return out
+
+    def groupby_sum(self, by, group_index: bool = True, dtype=np.float64, proc: int = 1):
+        """Reference signature (sparse_plus.py:367-396): ``by`` maps row index ->
+        group label; returns the (n_groups x K) matrix of column sums per group
+        and the labels in first-seen order.  ``proc`` is ignored."""
+        if not isinstance(by, Mapping):
+            raise NotImplementedError('only Mapping `by` (like the reference)')
+        labels = {}
+        row_group = np.full(self.shape[0], -1, dtype=np.int32)
+        for k, v in by.items():
+            row_group[k] = labels.setdefault(v, len(labels))
+        cell, col, val = self._device_coo(row_group, None, None)
+        mat = scipy.sparse.csr_matrix((val.astype(dtype), (cell, col)), shape=(len(labels), self.shape[1]))
+        if group_index:
+            return type(self)(mat), list(labels.keys())
+        return type(self)(mat)

@@ -1,0 +1,200 @@
+"""Result records of the hot path: FitInfo, PoolInfo, ReassignInfo.
+
+Same attribute / property names and derived quantities as the reference's
+``stellarscope/utils/statistics.py:269-495`` so that ``stages.py`` logging and
+``output_stats`` (statistics.py:628-644) keep working; the values are filled
+from device results instead of from a fitted scipy model.
+"""
+from __future__ import annotations
+
+import logging as lg
+from collections import Counter
+from typing import Optional
+
+import numpy as np
+
+
+def _property_names(obj):
+    cls = obj.__class__
+    return [p for p in dir(cls) if isinstance(getattr(cls, p), property)]
+
+
+class GenericInfo:
+    """statistics.py:21-44"""
+
+    def __init__(self):
+        self.infotype = self.__class__.__name__
+
+    def __str__(self):
+        return '\n'.join(f'{k}\t{v}' for k, v in vars(self).items())
+
+    def to_dataframe(self):
+        import pandas as pd
+        names = _property_names(self)
+        return pd.DataFrame({'stage': self.infotype, 'mode': '', 'var': names,
+                             'value': [getattr(self, v) for v in names]}, dtype=object)
+
+
+class FitInfo(GenericInfo):
+    """statistics.py:269-307.  ``iterations`` holds ``(inum, itime, diff_est)``
+    (model.py:359); ``itime`` is the device time of the whole fit divided by the
+    number of iterations (the reference measures each iteration on the host)."""
+
+    def __init__(self, nobs=None, nfeats=None, epsilon=None, max_iter=None):
+        super().__init__()
+        self.converged = False
+        self.reached_max = False
+        self.nparams = 2
+        self.nobs = nobs
+        self.nfeats = nfeats
+        self.epsilon = epsilon
+        self.max_iter = max_iter
+        self.iterations = []
+        self.final_lnl = None
+
+    @property
+    def fitted(self) -> bool:
+        return self.converged | self.reached_max
+
+
+class PoolInfo(GenericInfo):
+    """statistics.py:309-407."""
+
+    def __init__(self, pooling_mode: Optional[str] = None):
+        super().__init__()
+        self.pooling_mode = pooling_mode
+        self.nmodels = 0
+        self.models_info = {}
+        self._total_params = None
+        self._total_obs = None
+        self._total_lnl = None
+        self._AIC = None
+        self._BIC = None
+
+    @property
+    def fitted_models(self) -> int:
+        return len(self.models_info)
+
+    @property
+    def total_lnl(self):
+        if self._total_lnl is None:
+            tot = np.longdouble(0.0)               # float128 accumulation, statistics.py:340
+            for fi in self.models_info.values():
+                tot += fi.final_lnl
+            self._total_lnl = tot
+        return self._total_lnl
+
+    @property
+    def total_obs(self) -> int:
+        if self._total_obs is None:
+            self._total_obs = sum(fi.nobs for fi in self.models_info.values())
+        return self._total_obs
+
+    @property
+    def total_params(self) -> int:
+        if self._total_params is None:
+            self._total_params = sum(fi.nparams * fi.nfeats for fi in self.models_info.values())
+        return self._total_params
+
+    @property
+    def AIC(self):
+        if self._AIC is None:
+            self._AIC = 2 * self.total_params - (2 * self.total_lnl)
+        return self._AIC
+
+    @property
+    def BIC(self):
+        if self._BIC is None:
+            self._BIC = self.total_params * np.log(self.total_obs) - (2 * self.total_lnl)
+        return self._BIC
+
+    def log(self, loglev=lg.INFO):
+        lg.log(loglev, f'Complete data log-likelihood (lnL): {self.total_lnl}')
+        lg.log(loglev, f'  Number of models estimated: {self.fitted_models}')
+        lg.log(loglev, f'  Total observations: {self.total_obs}')
+        lg.log(loglev, f'  Total parameters estimated: {self.total_params}')
+        lg.log(loglev, f'    AIC: {self.AIC}')
+        lg.log(loglev, f'    BIC: {self.BIC}')
+
+    def to_dataframe(self):
+        ret = super().to_dataframe()
+        ret['mode'] = self.pooling_mode
+        return ret
+
+
+class ReassignInfo(GenericInfo):
+    """statistics.py:410-495 (the attribute is spelled ``ambigous_dist`` by the
+    code that fills it, model.py:440)."""
+
+    explanations = {
+        'best_exclude': 'remain ambiguous -> excluded',
+        'best_conf': 'are low confidence -> excluded',
+        'best_random': 'remain ambiguous -> randomly assigned',
+        'best_average': 'remain ambiguous -> divided evenly',
+        'initial_unique': 'were initially ambiguous -> discarded',
+        'initial_random': 'were initially ambiguous -> randomly assigned',
+        'total_hits': 'initially had multiple alignments',
+    }
+
+    def __init__(self, reassign_mode: str):
+        super().__init__()
+        self.reassign_mode = reassign_mode
+        self.explanation = self.explanations[reassign_mode]
+        self._assigned = 0
+        self._ambiguous = 0
+        self._unaligned = None
+        self.ambiguous_dist = None
+
+    @property
+    def assigned(self):
+        return self._assigned
+
+    @assigned.setter
+    def assigned(self, val):
+        self._assigned = val
+
+    @property
+    def ambiguous(self):
+        return self._ambiguous
+
+    @ambiguous.setter
+    def ambiguous(self, val):
+        self._ambiguous = val
+
+    @property
+    def unaligned(self):
+        return self._unaligned
+
+    @unaligned.setter
+    def unaligned(self, val):
+        self._unaligned = val
+
+    def format(self, include_mode=True, show_unaligned=False):
+        m = self.reassign_mode
+        prefix = f'{m} - ' if include_mode else ''
+        ret = []
+        if m == 'total_hits':
+            ret.append(f'{prefix}{self.assigned} total alignments.')
+        elif m == 'initial_unique':
+            ret.append(f'{prefix}{self.assigned} uniquely mapped.')
+        else:
+            ret.append(f'{prefix}{self.assigned} assigned.')
+        ret.append(f'{prefix}{self.ambiguous} reads {self.explanation}.')
+        if show_unaligned and self.unaligned is not None:
+            ret.append(f'{prefix}{self.unaligned} had no alignments.')
+        return ret
+
+    def log(self, loglev=lg.INFO):
+        lg.log(loglev, f'Reassignment using {self.reassign_mode}')
+        for line in self.format(False):
+            lg.log(loglev, f'  {line}')
+
+    def to_dataframe(self):
+        ret = super().to_dataframe()
+        ret['mode'] = self.reassign_mode
+        return ret
+
+
+def counter_from_hist(hist):
+    """Device histogram of min(nbest, 63) -> ``Counter(nbest)`` (model.py:440)."""
+    return Counter({int(k): int(v) for k, v in enumerate(hist) if v})

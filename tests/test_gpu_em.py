@@ -1,0 +1,146 @@
+"""CUDA EM path (through the C ABI) against the oracle on seeded inputs."""
+import numpy as np
+import pytest
+
+from oracle.em_oracle import OracleLikelihood, Opts, submatrix_rows
+from stellarscope_b200 import layout_host, synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+PI_RTOL = 1e-6        # north_star: final pi/theta within 1e-6 relative in fp64
+LNL_RTOL = 1e-10
+
+
+def _fit_and_compare(d, row_seg, seg_rows, opts, use_import=False):
+    from stellarscope_b200.engine import Engine
+    S = len(seg_rows)
+    eng = Engine()
+    eng.set_matrix(d.indptr, d.indices, d.scores, d.K)
+    if use_import:
+        eng.import_layout(layout_host.build(d.indptr, d.indices, d.scores, row_seg, S, d.K))
+    else:
+        eng.build_layout(row_seg, S)
+    eng.fit(opts.em_epsilon, opts.max_iter, opts.pi_prior, opts.theta_prior, opts.use_likelihood)
+    res = eng.results()
+    z = eng.emit_z().cpu().numpy()
+    ptr64, idx64 = d.indptr.astype(np.int64), d.indices.astype(np.int64)
+    for s, rows in enumerate(seg_rows):
+        ptr, idx, sc, take = submatrix_rows(ptr64, idx64, d.scores, rows)
+        om = OracleLikelihood(ptr, idx, sc, d.K, opts).em()
+        n_it = len(om.fitinfo.iterations)
+        assert res['iters'][s] == n_it, f'segment {s}'
+        assert bool(res['flags'][s] & 1) == om.fitinfo.converged
+        assert bool(res['flags'][s] & 2) == om.fitinfo.reached_max
+        assert res['nobs'][s] == om.fitinfo.nobs and res['nfeats'][s] == om.fitinfo.nfeats
+        pi, th = eng.dense_params(s)
+        r, ok = H.rel_err(pi, np.asarray(om.pi, dtype=np.float64))
+        assert r < PI_RTOL and ok, f'pi segment {s}: {r}'
+        r, ok = H.rel_err(th, np.asarray(om.theta, dtype=np.float64))
+        assert r < PI_RTOL, f'theta segment {s}: {r}'
+        lo = float(om.lnl)
+        assert abs(res['lnl'][s] - lo) <= LNL_RTOL * abs(lo), f'lnl segment {s}'
+        do = np.array([x[2] for x in om.fitinfo.iterations])
+        dg = res['diffs'][s, :n_it]
+        assert np.all(np.abs(dg - do) <= 1e-12 + 1e-6 * do), f'diff trace segment {s}'
+        if len(take):
+            assert np.max(np.abs(z[take] - np.asarray(om.z, dtype=np.float64))) < 1e-9
+    eng.close()
+    return res
+
+
+@pytest.mark.parametrize('use_import', [False, True])
+def test_individual_resident(use_import):
+    d = H.small_synth(seed=21)
+    _fit_and_compare(d, d.row_cell, d.cell_rows(), Opts(), use_import)
+
+
+@pytest.mark.parametrize('use_import', [False, True])
+def test_pseudobulk_streaming(use_import):
+    d = H.small_synth(seed=22, n_alignments=25000)
+    res = _fit_and_compare(d, np.zeros(d.N, dtype=np.int32), [np.arange(d.N)], Opts(), use_import)
+    assert res['iters'][0] > 1
+
+
+def test_celltype_mixed_sizes():
+    d = H.small_synth(seed=23, n_cells=40, n_alignments=40000, n_celltypes=5, n_loci=800)
+    _fit_and_compare(d, d.cell_type[d.row_cell].astype(np.int32), d.celltype_rows(), Opts())
+
+
+def test_use_likelihood_resident_and_streaming():
+    d = H.small_synth(seed=24, n_alignments=12000)
+    _fit_and_compare(d, d.row_cell, d.cell_rows(), Opts(use_likelihood=True))
+    _fit_and_compare(d, np.zeros(d.N, dtype=np.int32), [np.arange(d.N)], Opts(use_likelihood=True))
+
+
+def test_priors_and_max_iter():
+    d = H.small_synth(seed=25)
+    _fit_and_compare(d, d.row_cell, d.cell_rows(), Opts(pi_prior=2, theta_prior=1000, max_iter=9))
+    _fit_and_compare(d, d.row_cell, d.cell_rows(), Opts(theta_prior=0, pi_prior=0, em_epsilon=1e-4))
+
+
+def test_all_unique_cells_and_tiny_cells():
+    d = H.small_synth(seed=26, unique_frac=1.0, n_cells=6, n_alignments=200)
+    _fit_and_compare(d, d.row_cell, d.cell_rows(), Opts())
+    d = H.small_synth(seed=27, n_cells=60, n_alignments=200)
+    _fit_and_compare(d, d.row_cell, d.cell_rows(), Opts())
+
+
+def test_zero_denominator_is_model_error():
+    """theta_prior = 0 and no ambiguous row -> 0/0 -> StellarscopeError class (model.py:267-272)."""
+    from stellarscope_b200.engine import Engine
+    indptr = np.array([0, 1, 2, 3, 5], dtype=np.int32)          # rows 0-2 unique, row 3 ambiguous
+    indices = np.array([1, 2, 1, 0, 3], dtype=np.int32)
+    scores = np.array([200, 180, 150, 170, 190], dtype=np.uint16)
+    seg = np.array([0, 0, 1, 2], dtype=np.int32)
+    eng = Engine()
+    eng.set_matrix(indptr, indices, scores, 5)
+    eng.build_layout(seg, 3)
+    eng.fit(1e-7, 100, 0.0, 0.0, False)
+    flags = eng.results()['flags']
+    assert (flags[:2] & 4).all() and not (flags[2] & 4)
+    eng.close()
+
+
+def test_rows_outside_models_get_no_z():
+    from stellarscope_b200.engine import Engine
+    d = H.small_synth(seed=29)
+    seg = d.row_cell.copy()
+    seg[seg == 0] = -1
+    eng = Engine()
+    eng.set_matrix(d.indptr, d.indices, d.scores, d.K)
+    eng.build_layout(seg, d.n_cells)
+    eng.fit()
+    z = eng.emit_z().cpu().numpy()
+    rows = np.flatnonzero(d.row_cell == 0)
+    for r in rows:
+        assert np.all(z[d.indptr[r]:d.indptr[r + 1]] == 0)
+    # every fitted non-empty row is a probability vector
+    sums = np.add.reduceat(z, d.indptr[:-1].astype(np.int64))
+    fitted = (seg >= 0) & (np.diff(d.indptr) > 0)
+    assert np.allclose(sums[fitted], 1.0, atol=1e-12)
+    eng.close()
+
+
+def test_full_size_properties_config2_shape():
+    """Size-independent checks at a larger size (rows sum to 1, pi sums to 1, idempotent refit)."""
+    from stellarscope_b200.engine import Engine
+    d = synth.generate(n_cells=2000, n_alignments=1_000_000, n_loci=28000, seed=5)
+    eng = Engine()
+    eng.set_matrix(d.indptr, d.indices, d.scores, d.K)
+    eng.build_layout(d.row_cell, d.n_cells)
+    eng.fit()
+    r1 = eng.results()
+    z = eng.emit_z().cpu().numpy()
+    sums = np.add.reduceat(z, d.indptr[:-1].astype(np.int64))
+    assert np.allclose(sums, 1.0, atol=1e-12)
+    p = eng.params()
+    for s in (0, 7, 1999):
+        a, n = p['seg_col0'][s], p['seg_ncol'][s]
+        tot = p['pi'][a:a + n].sum() + (d.K - n) * p['pi_rest'][s]
+        assert abs(tot - 1.0) < 1e-9
+    eng.fit()
+    r2 = eng.results()
+    assert np.array_equal(r1['iters'], r2['iters'])
+    assert np.allclose(r1['lnl'], r2['lnl'], rtol=1e-12, atol=0)
+    eng.close()
