@@ -172,9 +172,10 @@ int ss_set_allreduce(ss_handle_t h, ss_allreduce_fn fn, void* user);
 int64_t ss_launch_count(ss_handle_t h);
 
 /* Measurement aid (bench.py): when enabled, ss_em_fit brackets its kernel groups with CUDA
- * events on the caller's stream; ss_get_timings synchronises on them and returns the device
- * time in ms of [0] prepare, [1] streaming kernel, [2] resident kernels, [3] emit, [4] finalize
- * of the last fit. */
+ * events; ss_get_timings synchronises on them and returns the device time in ms of the last
+ * fit: [0] prepare, [1] all EM kernels (they run concurrently), [2] unused, [3] emit,
+ * [4] finalize, [5..10] span of the resident kernel of size class 0..5 (32..1024 threads),
+ * [11] span of the streaming kernel.  n >= 12. */
 int ss_set_timing(ss_handle_t h, int32_t enabled);
 int ss_get_timings(ss_handle_t h, double* ms, int32_t n);
 

@@ -42,6 +42,15 @@ int ss_destroy(ss_handle_t h) {
   free_layout(h);
   for (int i = 0; i < 6; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int i = 0; i < SS_NUM_AUX_STREAMS; ++i) {
+    if (h->tev_s[i]) cudaEventDestroy(h->tev_s[i]);
+    if (h->tev_e[i]) cudaEventDestroy(h->tev_e[i]);
+  }
+  for (int i = 0; i < SS_NUM_AUX_STREAMS; ++i) {
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
+  }
   delete h;
   return SS_OK;
 }
@@ -260,14 +269,19 @@ int ss_set_timing(ss_handle_t h, int32_t enabled) {
   SS_REQUIRE_HANDLE(h);
   cudaSetDevice(h->device);
   h->timing = enabled != 0;
-  if (h->timing && !h->ev[0])
+  if (h->timing && !h->ev[0]) {
     for (int i = 0; i < 6; ++i) SS_CUDA_CHECK(h, cudaEventCreate(&h->ev[i]));
+    for (int i = 0; i < SS_NUM_AUX_STREAMS; ++i) {
+      SS_CUDA_CHECK(h, cudaEventCreate(&h->tev_s[i]));
+      SS_CUDA_CHECK(h, cudaEventCreate(&h->tev_e[i]));
+    }
+  }
   return SS_OK;
 }
 
 int ss_get_timings(ss_handle_t h, double* ms, int32_t n) {
   SS_REQUIRE_HANDLE(h);
-  if (!ms || n < 5 || !h->ev_valid) {
+  if (!ms || n < 5 + SS_NUM_AUX_STREAMS || !h->ev_valid) {
     h->set_error("ss_get_timings: timing not enabled / no fit / buffer too small");
     return SS_ERR_STATE;
   }
@@ -277,6 +291,12 @@ int ss_get_timings(ss_handle_t h, double* ms, int32_t n) {
     float t = 0.f;
     SS_CUDA_CHECK(h, cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]));
     ms[i] = t;
+  }
+  // spans of the concurrent EM kernels: size classes 0..5, then the streaming kernel
+  for (int i = 0; i < SS_NUM_AUX_STREAMS; ++i) {
+    float t = 0.f;
+    if (h->aux_used[i]) SS_CUDA_CHECK(h, cudaEventElapsedTime(&t, h->tev_s[i], h->tev_e[i]));
+    ms[5 + i] = t;
   }
   return SS_OK;
 }

@@ -95,18 +95,19 @@ __global__ void fit_prepare_kernel(Layout L, FitState F, FitParams P, const int8
 }
 
 // ---------------------------------------------------------------------------
-// resident kernel: one CTA per single-tile segment
+// resident kernel: one CTA per single-tile segment.  The tile is loaded once (TMA bulk
+// copies) and iterated to convergence out of shared memory: two barriers per iteration.
 // ---------------------------------------------------------------------------
 template <int THREADS, bool LNL>
 __global__ void __launch_bounds__(THREADS) em_resident_kernel(EmArgs a) {
   extern __shared__ __align__(128) unsigned char dsm[];
-  __shared__ double s_red[32];
+  __shared__ double s_red[64];
   __shared__ uint64_t s_bar;
   constexpr int NW = THREADS / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = a.tile_list[blockIdx.x];
   const TileView v = load_tile_view(a.L.tile_hdr, t);
-  TileSmem s = carve_tile(dsm, v, LNL);
+  TileSmem s = carve_tile(dsm, v);
   const int seg = v.seg;
 
   if (tid == 0) {
@@ -136,50 +137,43 @@ __global__ void __launch_bounds__(THREADS) em_resident_kernel(EmArgs a) {
   __syncthreads();
 
   double* pt_cur = s.pt;
-  double* pt_nxt = LNL ? s.pt2 : s.pt;
+  double* pt_nxt = s.pt2;
   double lnl_prev = INFINITY, lnl_amb = 0.0;
-  int it = 0;
+  int it = 0, par = 0;
   bool done = false, conv = false;
   while (!done) {
     ++it;
     tile_phase_a<THREADS>(v, s, pt_cur);
-    __syncthreads();
-    // ---- phase B: thetasum per tile column, new pi, |delta pi| ----
+    group_sync<THREADS>();
+    // ---- phase B: thetasum per tile column -> theta', pi', x' = pi' theta', |delta pi| ----
     double dsum = 0.0;
     for (int c = warp; c < v.nlong; c += NW) {
       const double asum = tile_col_sum_warp(s, c, lane);
       if (lane == 0) {
         const double T = pt_cur[c] * asum;
-        const double pn = (ps0[c] + T + pipw) * inv_pid;
+        const double th = (T + thpw) * inv_thd;               // model.py:240
+        const double pn = (ps0[c] + T + pipw) * inv_pid;      // model.py:243-244
         dsum += fabs(pn - s.aux[c]);
-        s.val[s.cptr[c]] = T;
+        s.aux[c] = pn;
+        pt_nxt[c] = pn * th;
+        s.val[s.cptr[c]] = th;                                // column's own slot: theta' for the epilogue
       }
     }
     for (int c = v.nlong + tid; c < v.ncol; c += THREADS) {
       const double T = pt_cur[c] * tile_col_sum_thread(s, c);
+      const double th = (T + thpw) * inv_thd;
       const double pn = (ps0[c] + T + pipw) * inv_pid;
       dsum += fabs(pn - s.aux[c]);
-      s.val[s.cptr[c]] = T;
+      s.aux[c] = pn;
+      pt_nxt[c] = pn * th;
+      s.val[s.cptr[c]] = th;
     }
-    double diff = block_sum<THREADS>(dsum, s_red);      // contains the barrier that publishes val[]
+    double diff = block_sum<THREADS>(dsum, s_red, par++);     // barrier: publishes pt_nxt / aux / val
     if (it == 1) diff += diff1_extra;
     const bool reached = it >= max_iter;
     if (!LNL) {
-      conv = diff < eps;                                 // model.py:351
-      done = conv || reached;
-    }
-    // ---- pass 2: commit pi, theta, x = pi*theta ----
-    if (LNL || !done) {
-      for (int c = tid; c < v.ncol; c += THREADS) {
-        const double T = s.val[s.cptr[c]];
-        const double th = (T + thpw) * inv_thd;
-        const double pn = (ps0[c] + T + pipw) * inv_pid;
-        s.aux[c] = pn;
-        pt_nxt[c] = pn * th;
-      }
-    }
-    if (LNL) {
-      __syncthreads();
+      conv = diff < eps;                                       // model.py:351
+    } else {
       // lnL with the E-step's z (old x) and the new parameters: model.py:344
       double l = tile_lnl_pass<THREADS>(v, s, pt_cur, pt_nxt, true, nullptr, nullptr);
       for (int c = tid; c < v.ncol; c += THREADS) {
@@ -187,56 +181,38 @@ __global__ void __launch_bounds__(THREADS) em_resident_kernel(EmArgs a) {
         const double pn = s.aux[c];
         if (nu > 0 && pn > 0.0) l += (double)nu * log(pn);
       }
-      lnl_amb = block_sum<THREADS>(l, s_red);
+      lnl_amb = block_sum<THREADS>(l, s_red, par++);
       const double lnl = lnl_amb + lnl_extra;
-      conv = fabs(lnl - lnl_prev) < eps;                 // model.py:345-347
+      conv = fabs(lnl - lnl_prev) < eps;                       // model.py:345-347
       lnl_prev = lnl;
-      done = conv || reached;
       if (tid == 0 && lnls) lnls[it - 1] = lnl;
     }
+    done = conv || reached;
     if (tid == 0) diffs[it - 1] = diff;
-    if (!done) {
-      if (LNL) { double* tmp = pt_cur; pt_cur = pt_nxt; pt_nxt = tmp; }
-      __syncthreads();
-    }
+    if (!done) { double* tmp = pt_cur; pt_cur = pt_nxt; pt_nxt = tmp; }
   }
-  // ---- converged / reached max: publish parameters, final lnL, z ----
-  // non-LNL: pt_cur still holds the x of the last E-step, val[cptr[c]] the last T.
-  double* ptfin = LNL ? pt_nxt : s.aux;
+  // ---- converged / reached max: publish parameters, final lnL ----
+  // pt_cur = x of the last E-step (tl.z belongs to it), pt_nxt = final x, aux = final pi.
   for (int c = tid; c < v.ncol; c += THREADS) {
     const int slot = scol[c];
-    double pn, th;
-    if (LNL) {
-      pn = s.aux[c];
-      const double T = s.val[s.cptr[c]];
-      th = (T + thpw) * inv_thd;
-    } else {
-      const double T = s.val[s.cptr[c]];
-      th = (T + thpw) * inv_thd;
-      pn = (ps0[c] + T + pipw) * inv_pid;
-      s.aux[c] = pn * th;
-    }
-    a.F.sc_pi[slot] = pn;
-    a.F.sc_theta[slot] = th;
+    a.F.sc_pi[slot] = s.aux[c];
+    a.F.sc_theta[slot] = s.val[s.cptr[c]];
     a.F.sc_ptprev[slot] = pt_cur[c];
-    a.F.sc_ptfin[slot] = pn * th;
+    a.F.sc_ptfin[slot] = pt_nxt[c];
   }
-  __syncthreads();
-  double l = 0.0;
-  if (!LNL || a.z_out) {
-    l = tile_lnl_pass<THREADS>(v, s, pt_cur, ptfin, !LNL, a.z_out, a.L.e_opos + v.eo);
-  }
+  double l;
   if (!LNL) {
-    l = block_sum<THREADS>(l, s_red);
+    l = tile_lnl_pass<THREADS>(v, s, pt_cur, pt_nxt, true, nullptr, nullptr);
+    l = block_sum<THREADS>(l, s_red, par++);
   } else {
     // tile_lnl holds the ambiguous-row part only; the unique-row part is added by finalize
     double lu = 0.0;
     for (int c = tid; c < v.ncol; c += THREADS) {
       const int nu = nuq[c];
-      const double pn = a.F.sc_pi[scol[c]];
+      const double pn = s.aux[c];
       if (nu > 0 && pn > 0.0) lu += (double)nu * log(pn);
     }
-    lu = block_sum<THREADS>(lu, s_red);
+    lu = block_sum<THREADS>(lu, s_red, par++);
     l = lnl_amb - lu;
   }
   if (tid == 0) {
@@ -252,7 +228,7 @@ __global__ void __launch_bounds__(THREADS) em_resident_kernel(EmArgs a) {
 template <int THREADS, bool LNL>
 __global__ void __launch_bounds__(THREADS) em_stream_kernel(EmArgs a, StreamArgs sa) {
   extern __shared__ __align__(128) unsigned char dsm[];
-  __shared__ double s_red[32];
+  __shared__ double s_red[64];
   __shared__ uint64_t s_bar;
   constexpr int NW = THREADS / 32;
   cg::grid_group grid = cg::this_grid();
@@ -276,7 +252,7 @@ __global__ void __launch_bounds__(THREADS) em_stream_kernel(EmArgs a, StreamArgs
       const int t = sa.tiles[i];
       const TileView v = load_tile_view(a.L.tile_hdr, t);
       if (a.F.seg_iters[v.seg] != 0) continue;           // segment already finished
-      TileSmem s = carve_tile(dsm, v, false);
+      TileSmem s = carve_tile(dsm, v);
       if (tid == 0) {
         fence_proxy_async();
         tile_issue_loads(a.L, v, s, &s_bar);
@@ -338,7 +314,7 @@ __global__ void __launch_bounds__(THREADS) em_stream_kernel(EmArgs a, StreamArgs
         const int t = sa.tiles[i];
         const TileView v = load_tile_view(a.L.tile_hdr, t);
         if (a.F.seg_iters[v.seg] != 0) continue;
-        TileSmem s = carve_tile(dsm, v, true);
+        TileSmem s = carve_tile(dsm, v);
         if (tid == 0) {
           fence_proxy_async();
           tile_issue_loads(a.L, v, s, &s_bar);
@@ -352,7 +328,7 @@ __global__ void __launch_bounds__(THREADS) em_stream_kernel(EmArgs a, StreamArgs
         phase ^= 1;
         __syncthreads();
         double l = tile_lnl_pass<THREADS>(v, s, s.pt, s.pt2, true, nullptr, nullptr);
-        l = block_sum<THREADS>(l, s_red);
+        l = block_sum<THREADS>(l, s_red, 0);
         if (tid == 0) atomicAdd(&a.F.seg_lnl[v.seg], l);
         __syncthreads();
       }
@@ -418,12 +394,12 @@ __global__ void stream_freeze_kernel(FitState F, StreamArgs sa) {
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) emit_tiles_kernel(EmArgs a, int want_lnl) {
   extern __shared__ __align__(128) unsigned char dsm[];
-  __shared__ double s_red[32];
+  __shared__ double s_red[64];
   __shared__ uint64_t s_bar;
   const int tid = threadIdx.x;
   const int t = a.tile_list[blockIdx.x];
   const TileView v = load_tile_view(a.L.tile_hdr, t);
-  TileSmem s = carve_tile(dsm, v, true);
+  TileSmem s = carve_tile(dsm, v);
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -439,7 +415,7 @@ __global__ void __launch_bounds__(THREADS) emit_tiles_kernel(EmArgs a, int want_
   __syncthreads();
   double l = tile_lnl_pass<THREADS>(v, s, s.pt, s.pt2, want_lnl != 0, a.z_out, a.L.e_opos + v.eo);
   if (want_lnl) {
-    l = block_sum<THREADS>(l, s_red);
+    l = block_sum<THREADS>(l, s_red, 0);
     if (tid == 0) a.F.tile_lnl[t] = l;
   }
 }
@@ -535,6 +511,19 @@ static cudaError_t launch_resident(ss_handle_s* h, cudaStream_t st, const EmArgs
   return cudaGetLastError();
 }
 
+static cudaError_t ensure_aux_streams(ss_handle_s* h) {
+  if (h->ev_fork) return cudaSuccess;
+  cudaError_t e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  if (e != cudaSuccess) return e;
+  for (int i = 0; i < SS_NUM_AUX_STREAMS; ++i) {
+    e = cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 constexpr int STREAM_THREADS = 512;
 
 int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
@@ -546,37 +535,44 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     h->set_error("ss_em_fit: max_iter must be >= 1 and em_epsilon a number");
     return SS_ERR_ARG;
   }
-  free_fit(h);
   Layout& L = h->L;
   FitState& F = h->F;
   const size_t S = (size_t)L.S, NC = (size_t)L.n_segcols, MI = (size_t)P.max_iter;
-  auto& pool = h->fit_allocs;
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_thpw, S));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_pipw, S));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_inv_thd, S));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_inv_pid, S));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_diff1_extra, S));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_lnl_extra, S));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_pi, NC));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_pt[0], NC));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_pt[1], NC));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_ptprev, NC));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_ptfin, NC));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_theta, NC));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_T, NC));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_iters, S));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_flags, S));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_lnl, S));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_diffs, S * MI));
-  SS_CUDA_CHECK(h, cudaMemsetAsync(F.seg_diffs, 0, S * MI * sizeof(double), st));
-  if (P.use_likelihood) {
-    SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_lnls, S * MI));
-    SS_CUDA_CHECK(h, cudaMemsetAsync(F.seg_lnls, 0, S * MI * sizeof(double), st));
+  // the fit state is allocated once per (layout, max_iter, likelihood mode) and reused by later fits
+  const bool reuse = h->fit_allocs.size() > 0 && h->fit_S == S && h->fit_NC == NC && h->fit_MI == MI &&
+                     h->fit_T == (size_t)L.n_tiles && h->fit_lnl == (P.use_likelihood != 0);
+  if (!reuse) {
+    free_fit(h);
+    auto& pool = h->fit_allocs;
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_thpw, S));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_pipw, S));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_inv_thd, S));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_inv_pid, S));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_diff1_extra, S));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_lnl_extra, S));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_pi, NC));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_pt[0], NC));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_pt[1], NC));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_ptprev, NC));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_ptfin, NC));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_theta, NC));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.sc_T, NC));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_iters, S));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_flags, S));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_lnl, S));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_diffs, S * MI));
+    if (P.use_likelihood) SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_lnls, S * MI));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_diffacc, S));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &F.tile_lnl, (size_t)L.n_tiles));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &h->stream_ctl, 4));
+    h->fit_S = S; h->fit_NC = NC; h->fit_MI = MI; h->fit_T = (size_t)L.n_tiles;
+    h->fit_lnl = P.use_likelihood != 0;
   }
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.seg_diffacc, S));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &F.tile_lnl, (size_t)L.n_tiles));
+  h->has_fit = false;
+  SS_CUDA_CHECK(h, cudaMemsetAsync(F.seg_diffs, 0, std::max<size_t>(1, S * MI) * sizeof(double), st));
+  if (P.use_likelihood)
+    SS_CUDA_CHECK(h, cudaMemsetAsync(F.seg_lnls, 0, std::max<size_t>(1, S * MI) * sizeof(double), st));
   SS_CUDA_CHECK(h, cudaMemsetAsync(F.tile_lnl, 0, (size_t)std::max(1, L.n_tiles) * sizeof(double), st));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &h->stream_ctl, 4));
   h->P = P;
   h->P.K = L.K;
 
@@ -597,9 +593,18 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
   a.z_out = nullptr;
   const bool lnl = P.use_likelihood != 0;
 
-  // streaming kernel first (long running, cooperative), then the resident classes
+  // All EM kernels of the fit run concurrently: the cooperative streaming kernel (segments
+  // spanning several tiles) and one resident kernel per size class, each on its own stream
+  // forked from / joined back into the caller's stream.
   SS_MARK(1);
+  SS_CUDA_CHECK(h, ensure_aux_streams(h));
+  SS_CUDA_CHECK(h, cudaEventRecord(h->ev_fork, st));
+  for (int i = 0; i < SS_NUM_AUX_STREAMS; ++i) h->aux_used[i] = false;
   if (h->n_stream_tiles > 0) {
+    cudaStream_t sx = h->aux[SS_NUM_CLASSES];
+    h->aux_used[SS_NUM_CLASSES] = true;
+    SS_CUDA_CHECK(h, cudaStreamWaitEvent(sx, h->ev_fork, 0));
+    if (h->timing) SS_CUDA_CHECK(h, cudaEventRecord(h->tev_s[SS_NUM_CLASSES], sx));
     StreamArgs sa;
     sa.tiles = h->stream_tiles;
     sa.n_tiles = h->n_stream_tiles;
@@ -609,8 +614,8 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     sa.col_slot = h->stream_col_slot;
     sa.n_cols = h->n_stream_cols;
     sa.ctl = h->stream_ctl;
-    SS_CUDA_CHECK(h, cudaMemsetAsync(h->stream_ctl, 0, 4 * sizeof(int), st));
-    const size_t smem = h->stream_smem[lnl ? 1 : 0];
+    SS_CUDA_CHECK(h, cudaMemsetAsync(h->stream_ctl, 0, 4 * sizeof(int), sx));
+    const size_t smem = h->stream_smem;
     void* fn = lnl ? (void*)em_stream_kernel<STREAM_THREADS, true> : (void*)em_stream_kernel<STREAM_THREADS, false>;
     SS_CUDA_CHECK(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -623,32 +628,45 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     a.tile_list = h->stream_tiles;
     a.n_list = h->n_stream_tiles;
     void* args[] = {(void*)&a, (void*)&sa};
-    SS_CUDA_CHECK(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(STREAM_THREADS), args, smem, st));
+    SS_CUDA_CHECK(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(STREAM_THREADS), args, smem, sx));
     h->launches++;
-    stream_freeze_kernel<<<(unsigned)((h->n_stream_cols + 255) / 256), 256, 0, st>>>(F, sa);
+    stream_freeze_kernel<<<(unsigned)((h->n_stream_cols + 255) / 256), 256, 0, sx>>>(F, sa);
     h->launches++;
     SS_CUDA_CHECK(h, cudaGetLastError());
+    if (h->timing) SS_CUDA_CHECK(h, cudaEventRecord(h->tev_e[SS_NUM_CLASSES], sx));
+    SS_CUDA_CHECK(h, cudaEventRecord(h->ev_join[SS_NUM_CLASSES], sx));
   }
-  SS_MARK(2);
   for (int c = SS_NUM_CLASSES - 1; c >= 0; --c) {
+    if (h->cls_count[c] == 0) continue;
+    cudaStream_t sx = h->aux[c];
+    h->aux_used[c] = true;
+    SS_CUDA_CHECK(h, cudaStreamWaitEvent(sx, h->ev_fork, 0));
+    if (h->timing) SS_CUDA_CHECK(h, cudaEventRecord(h->tev_s[c], sx));
     a.tile_list = h->cls_tiles[c];
     a.n_list = h->cls_count[c];
-    const size_t smem = h->cls_smem[c][lnl ? 1 : 0];
+    const size_t smem = h->cls_smem[c];
     cudaError_t e = cudaSuccess;
     switch (c) {
-      case 0: e = launch_resident<128>(h, st, a, h->cls_count[c], smem, lnl); break;
-      case 1: e = launch_resident<256>(h, st, a, h->cls_count[c], smem, lnl); break;
-      case 2: e = launch_resident<512>(h, st, a, h->cls_count[c], smem, lnl); break;
-      default: e = launch_resident<1024>(h, st, a, h->cls_count[c], smem, lnl); break;
+      case 0: e = launch_resident<32>(h, sx, a, h->cls_count[c], smem, lnl); break;
+      case 1: e = launch_resident<64>(h, sx, a, h->cls_count[c], smem, lnl); break;
+      case 2: e = launch_resident<128>(h, sx, a, h->cls_count[c], smem, lnl); break;
+      case 3: e = launch_resident<256>(h, sx, a, h->cls_count[c], smem, lnl); break;
+      case 4: e = launch_resident<512>(h, sx, a, h->cls_count[c], smem, lnl); break;
+      default: e = launch_resident<1024>(h, sx, a, h->cls_count[c], smem, lnl); break;
     }
     SS_CUDA_CHECK(h, e);
+    if (h->timing) SS_CUDA_CHECK(h, cudaEventRecord(h->tev_e[c], sx));
+    SS_CUDA_CHECK(h, cudaEventRecord(h->ev_join[c], sx));
   }
+  for (int i = 0; i < SS_NUM_AUX_STREAMS; ++i)
+    if (h->aux_used[i]) SS_CUDA_CHECK(h, cudaStreamWaitEvent(st, h->ev_join[i], 0));
+  SS_MARK(2);
   SS_MARK(3);
   // final lnL of the streamed tiles
   if (h->n_stream_tiles > 0) {
     a.tile_list = h->stream_tiles;
     a.n_list = h->n_stream_tiles;
-    const size_t smem = h->stream_smem[1];
+    const size_t smem = h->stream_smem;
     SS_CUDA_CHECK(h, cudaFuncSetAttribute(emit_tiles_kernel<STREAM_THREADS>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     emit_tiles_kernel<STREAM_THREADS><<<h->n_stream_tiles, STREAM_THREADS, smem, st>>>(a, 1);

@@ -48,7 +48,7 @@ struct TileSmem {
   double* w;       // pr  row weights
   double* pt;      // pc  x_j of the current E-step
   double* aux;     // pc  resident: pi_j ; streaming: unused
-  double* pt2;     // pc  (likelihood mode) x_j after the M-step
+  double* pt2;     // pc  x_j after the M-step (ping-pong partner of pt)
   uint16_t* lcol;  // pe  tile-local column of each alignment
   uint16_t* cpos;  // pe  column-major slot of each alignment
   uint16_t* rlen;  // pr
@@ -56,12 +56,12 @@ struct TileSmem {
   uint16_t* jptr;  // pj  JDS start of each in-row position (maxlen+1 used)
 };
 
-__host__ __device__ inline size_t tile_smem_bytes(int nent, int nrows, int ncol, int maxlen, bool lnl) {
+__host__ __device__ inline size_t tile_smem_bytes(int nent, int nrows, int ncol, int maxlen) {
   const size_t pe = pad8(nent), pr = pad8(nrows), pc = pad8(ncol + 1), pj = pad8(maxlen + 1);
-  return 8 * (2 * pe + pr + 2 * pc + (lnl ? pc : 0)) + 2 * (2 * pe + pr + pc + pj);
+  return 8 * (2 * pe + pr + 3 * pc) + 2 * (2 * pe + pr + pc + pj);
 }
 
-__device__ __forceinline__ TileSmem carve_tile(unsigned char* base, const TileView& v, bool lnl) {
+__device__ __forceinline__ TileSmem carve_tile(unsigned char* base, const TileView& v) {
   TileSmem s;
   double* d = reinterpret_cast<double*>(base);
   s.q = d;            d += v.pe;
@@ -69,7 +69,7 @@ __device__ __forceinline__ TileSmem carve_tile(unsigned char* base, const TileVi
   s.w = d;            d += v.pr;
   s.pt = d;           d += v.pc;
   s.aux = d;          d += v.pc;
-  s.pt2 = d;          if (lnl) d += v.pc;
+  s.pt2 = d;          d += v.pc;
   uint16_t* u = reinterpret_cast<uint16_t*>(d);
   s.lcol = u;         u += v.pe;
   s.cpos = u;         u += v.pe;
@@ -156,18 +156,29 @@ __device__ __forceinline__ double tile_lnl_pass(const TileView& v, const TileSme
   return l;
 }
 
-// deterministic block sum: every thread returns the same value
+// deterministic block sum: every thread returns the same value.  `red` holds 2 x 32 doubles;
+// callers alternate `par` between consecutive uses so one barrier per call is enough (the
+// barrier also publishes the caller's preceding shared-memory writes).
 template <int THREADS>
-__device__ __forceinline__ double block_sum(double v, double* red /* >= THREADS/32 doubles */) {
+__device__ __forceinline__ double block_sum(double v, double* red, int par) {
   constexpr int NW = THREADS / 32;
   v = warp_sum(v);
-  __syncthreads();  // protect `red` from the previous use
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  if (THREADS == 32) {
+    __syncwarp();
+    return v;
+  }
+  double* r = red + 32 * (par & 1);
+  if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
   __syncthreads();
   double t = 0.0;
 #pragma unroll
-  for (int i = 0; i < NW; ++i) t += red[i];
+  for (int i = 0; i < NW; ++i) t += r[i];
   return t;
+}
+
+template <int THREADS>
+__device__ __forceinline__ void group_sync() {
+  if (THREADS == 32) __syncwarp(); else __syncthreads();
 }
 
 }  // namespace ss

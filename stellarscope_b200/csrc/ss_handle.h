@@ -6,7 +6,8 @@
 #include "../../include/stellarscope_b200.h"
 #include "ss_common.cuh"
 
-constexpr int SS_NUM_CLASSES = 4;
+constexpr int SS_NUM_CLASSES = 6;
+constexpr int SS_NUM_AUX_STREAMS = SS_NUM_CLASSES + 1;
 
 struct ss_handle_s {
   int device = 0;
@@ -22,9 +23,9 @@ struct ss_handle_s {
   std::vector<long long> hdr_host;            // tile headers, HDR_WORDS per tile
   std::vector<int> seg_ntiles_host, seg_tile0_host;
   // launch plan
-  int* cls_tiles[SS_NUM_CLASSES] = {nullptr, nullptr, nullptr, nullptr};  // device tile lists (single-tile segments)
-  int cls_count[SS_NUM_CLASSES] = {0, 0, 0, 0};
-  size_t cls_smem[SS_NUM_CLASSES][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // [class][lnl]
+  int* cls_tiles[SS_NUM_CLASSES] = {};   // device tile lists (single-tile segments), by size class
+  int cls_count[SS_NUM_CLASSES] = {};
+  size_t cls_smem[SS_NUM_CLASSES] = {};  // dynamic shared memory of the class (largest tile)
   int* stream_tiles = nullptr;    // device: tiles of multi-tile segments
   int n_stream_tiles = 0;
   int* stream_segs = nullptr;     // device: multi-tile segment ids
@@ -32,7 +33,7 @@ struct ss_handle_s {
   int* stream_col_seg = nullptr;  // device: for every column of a multi-tile segment, index into stream_segs
   int* stream_col_slot = nullptr; // device: its absolute slot
   long long n_stream_cols = 0;
-  size_t stream_smem[2] = {0, 0};
+  size_t stream_smem = 0;
   int* all_tiles = nullptr;       // device: 0 .. n_tiles-1
   size_t all_smem = 0;            // smem of the largest tile (likelihood-mode carve)
   int8_t* sc_inamb = nullptr;     // device: segment column is touched by a tile
@@ -43,12 +44,19 @@ struct ss_handle_s {
   ss::FitState F;
   ss::FitParams P;
   std::vector<void*> fit_allocs;
+  size_t fit_S = 0, fit_NC = 0, fit_MI = 0, fit_T = 0;
+  bool fit_lnl = false;
   int* stream_ctl = nullptr;      // device control words of the streaming kernel
 
   // measurement aid: events around the kernel groups of the last fit
   bool timing = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
+  // the EM kernels of one fit run concurrently on internal streams forked from the caller's stream
+  cudaStream_t aux[SS_NUM_AUX_STREAMS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[SS_NUM_AUX_STREAMS] = {};
+  bool aux_used[SS_NUM_AUX_STREAMS] = {};
+  cudaEvent_t tev_s[SS_NUM_AUX_STREAMS] = {}, tev_e[SS_NUM_AUX_STREAMS] = {};  // timing (when enabled)
 
   // multi-GPU hook
   ss_allreduce_fn allreduce = nullptr;

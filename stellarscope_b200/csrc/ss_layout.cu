@@ -19,7 +19,7 @@ void free_layout(ss_handle_s* h) {
   for (int c = 0; c < SS_NUM_CLASSES; ++c) {
     h->cls_tiles[c] = nullptr;
     h->cls_count[c] = 0;
-    h->cls_smem[c][0] = h->cls_smem[c][1] = 0;
+    h->cls_smem[c] = 0;
   }
   h->stream_tiles = h->stream_segs = h->stream_col_seg = h->stream_col_slot = nullptr;
   h->n_stream_tiles = h->n_stream_segs = 0;
@@ -97,24 +97,24 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
   Layout& L = h->L;
   auto& pool = h->layout_allocs;
   const int T = L.n_tiles;
-  static const size_t CLS_LIMIT[SS_NUM_CLASSES] = {24 * 1024, 56 * 1024, 112 * 1024, (size_t)-1};
+  // CTAs per SM by class: 32, 16, 8, 4, 2, 1 (228 KB per SM, 1 KB reserved per CTA, ~0.6 KB static)
+  static const size_t CLS_LIMIT[SS_NUM_CLASSES] = {5632, 12800, 27136, 56320, 114688, (size_t)-1};
   std::vector<int> cls[SS_NUM_CLASSES], stream, all(T);
   std::iota(all.begin(), all.end(), 0);
   size_t all_smem = 0;
   h->nnz_amb = 0;
   h->rows_amb = 0;
-  for (int c = 0; c < SS_NUM_CLASSES; ++c) h->cls_smem[c][0] = h->cls_smem[c][1] = 0;
-  h->stream_smem[0] = h->stream_smem[1] = 0;
+  for (int c = 0; c < SS_NUM_CLASSES; ++c) h->cls_smem[c] = 0;
+  h->stream_smem = 0;
   for (int t = 0; t < T; ++t) {
     const long long* hd = &h->hdr_host[(size_t)t * HDR_WORDS];
     const int seg = (int)hd[H_SEG], nrows = (int)hd[H_NROWS], nent = (int)hd[H_NENT], ncol = (int)hd[H_NCOL],
               maxlen = (int)hd[H_MAXLEN];
     h->nnz_amb += nent;
     h->rows_amb += nrows;
-    const size_t b0 = tile_smem_bytes(nent, nrows, ncol, maxlen, false);
-    const size_t b1 = tile_smem_bytes(nent, nrows, ncol, maxlen, true);
-    all_smem = std::max(all_smem, b1);
-    if (b1 + 1024 > h->max_smem_optin) {
+    const size_t b0 = tile_smem_bytes(nent, nrows, ncol, maxlen);
+    all_smem = std::max(all_smem, b0);
+    if (b0 + 1024 > h->max_smem_optin) {
       h->set_error("tile exceeds the shared-memory capacity");
       return SS_ERR_CAPACITY;
     }
@@ -122,12 +122,10 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
       int c = 0;
       while (b0 > CLS_LIMIT[c]) ++c;
       cls[c].push_back(t);
-      h->cls_smem[c][0] = std::max(h->cls_smem[c][0], b0);
-      h->cls_smem[c][1] = std::max(h->cls_smem[c][1], b1);
+      h->cls_smem[c] = std::max(h->cls_smem[c], b0);
     } else {
       stream.push_back(t);
-      h->stream_smem[0] = std::max(h->stream_smem[0], b0);
-      h->stream_smem[1] = std::max(h->stream_smem[1], b1);
+      h->stream_smem = std::max(h->stream_smem, b0);
     }
   }
   h->all_smem = all_smem;
