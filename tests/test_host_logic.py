@@ -1,0 +1,128 @@
+"""Host-side logic that needs no GPU: layout specification invariants, pooling row maps,
+random tie replay, result records, synthetic generator."""
+import types
+
+import numpy as np
+import pytest
+
+from oracle import em_oracle as eo
+from stellarscope_b200 import layout_host, statistics, synth
+from tests import helpers as H
+
+
+def test_synth_is_deterministic_and_well_formed():
+    a = H.small_synth(seed=3)
+    b = H.small_synth(seed=3)
+    assert np.array_equal(a.indices, b.indices) and np.array_equal(a.scores, b.scores)
+    lens = np.diff(a.indptr)
+    assert lens.min() >= 1 and a.scores.min() >= 140 and a.scores.max() <= 260
+    for r in range(0, a.N, 97):                       # strictly ascending columns inside a row
+        c = a.indices[a.indptr[r]:a.indptr[r + 1]]
+        assert np.all(np.diff(c) > 0)
+    assert np.all(np.diff(a.row_cell) >= 0)           # rows of a cell are contiguous
+
+
+def test_layout_spec_roundtrip():
+    """The tiles hold every alignment of every ambiguous row exactly once, JDS and column-major
+    indices are consistent, unique rows are folded into pisum0."""
+    d = H.small_synth(seed=4, n_alignments=12000)
+    S = d.n_cells
+    hl = layout_host.build(d.indptr, d.indices, d.scores, d.row_cell, S, d.K)
+    lens = np.diff(d.indptr)
+    seen = np.zeros(d.A, dtype=int)
+    for t in range(hl.n_tiles):
+        seg, nrows, nent, ncol, maxlen, nlong, eo_, ro, co, jo = hl.tile_hdr[t]
+        assert nent <= layout_host.E_HARD
+        rl = hl.r_len[ro:ro + nrows].astype(int)
+        assert np.all(np.diff(rl) <= 0) and rl[0] == maxlen and rl.sum() == nent
+        jp = hl.j_ptr[jo:jo + maxlen + 1].astype(int)
+        cp = hl.c_ptr[co:co + ncol + 1].astype(int)
+        assert jp[0] == 0 and jp[-1] == nent and cp[0] == 0 and cp[-1] == nent
+        cnt = np.diff(cp)
+        assert np.all(np.diff(cnt) <= 0) and (cnt > 64).sum() == nlong
+        opos = hl.e_opos[eo_:eo_ + nent]
+        seen[opos] += 1
+        lcol = hl.e_lcol[eo_:eo_ + nent].astype(int)
+        cpos = hl.e_cpos[eo_:eo_ + nent].astype(int)
+        assert sorted(cpos.tolist()) == list(range(nent))
+        assert np.all((cpos >= cp[lcol]) & (cpos < cp[lcol + 1]))
+        scol = hl.c_scol[co:co + ncol]
+        assert np.array_equal(hl.sc_gcol[scol][lcol], d.indices[opos])
+        for r in range(nrows):
+            row = hl.r_orow[ro + r]
+            assert d.row_cell[row] == seg and lens[row] == rl[r]
+            for p in range(rl[r]):
+                assert opos[jp[p] + r] == d.indptr[row] + p
+    amb_e = np.repeat(lens > 1, lens)
+    assert np.array_equal(seen, amb_e.astype(int))
+    # unique rows
+    uni = np.flatnonzero(lens == 1)
+    assert np.array_equal(hl.u_row, uni) and hl.sc_nuniq.sum() == len(uni)
+    assert hl.seg_nobs.sum() == d.N and hl.seg_A.sum() == d.A
+
+
+def test_layout_spec_matches_oracle_constants():
+    d = H.small_synth(seed=5, n_cells=3, n_alignments=900)
+    hl = layout_host.build(d.indptr, d.indices, d.scores, np.zeros(d.N, dtype=np.int32), 1, d.K)
+    m = eo.OracleLikelihood(d.indptr, d.indices, d.scores, d.K, eo.Opts())
+    assert hl.seg_smax[0] == m.max_score
+    assert np.isclose(hl.seg_wtot[0], m.total_wt, rtol=1e-13) and np.isclose(hl.seg_wamb[0], m.ambig_wt, rtol=1e-13)
+    assert np.isclose(hl.seg_wmax[0], m.w.max(), rtol=0)
+    ps0 = np.zeros(d.K)
+    ps0[hl.sc_gcol] = hl.sc_pisum0
+    assert np.allclose(ps0, m.pisum0, rtol=1e-13)
+    assert hl.seg_nobs[0] == m.fitinfo.nobs and hl.seg_ncol[0] == m.fitinfo.nfeats
+
+
+def test_pooling_row_segments():
+    from stellarscope_b200.model import pooling_row_segments, StellarscopeError
+    st = types.SimpleNamespace(shape=(7, 3))
+    st.bcode_ridx_map = {'B': {4, 5}, 'A': {0, 2}, 'E': set(), 'C': {6}}
+    st.celltypes = ['t1', 't0', 't2']
+    st.ctype_bcode_map = {'t0': ['A', 'Z'], 't1': ['C', 'B'], 't2': ['E']}
+    o = types.SimpleNamespace(pooling_mode='pseudobulk')
+    seg, keys = pooling_row_segments(st, o)
+    assert seg.tolist() == [0] * 7 and keys == ['pseudobulk']
+    o.pooling_mode = 'individual'                     # dict order, empty barcodes skipped (model.py:734-740)
+    seg, keys = pooling_row_segments(st, o)
+    assert seg.tolist() == [1, -1, 1, -1, 0, 0, 2] and keys == [0, 1, 2]
+    o.pooling_mode = 'celltype'                       # st.celltypes order (model.py:710-720)
+    seg, keys = pooling_row_segments(st, o)
+    assert seg.tolist() == [1, -1, 1, -1, 0, 0, 0] and keys == [0, 1]
+    st.ctype_bcode_map['t2'] = ['A']
+    with pytest.raises(StellarscopeError):
+        pooling_row_segments(st, o)
+
+
+def test_random_replay_matches_oracle_choose_random():
+    from stellarscope_b200.model import _replay_random_choice
+    rng = np.random.default_rng(1)
+    nb = rng.integers(0, 4, 300)
+    lens = nb + rng.integers(0, 3, 300)
+    ptr = np.concatenate([[0], np.cumsum(lens)])
+    row = np.repeat(np.arange(300), lens)
+    flag = np.zeros(ptr[-1], dtype=bool)
+    for r in range(300):
+        flag[ptr[r] + rng.choice(lens[r], nb[r], replace=False)] = True if nb[r] else False
+    a = _replay_random_choice(flag, row, nb, np.random.default_rng(9))
+    b = eo._choose_random(flag, row, nb, np.random.default_rng(9))
+    assert np.array_equal(a, b)
+    assert np.array_equal(np.bincount(row[a], minlength=300), (nb > 0).astype(int))
+
+
+def test_info_records():
+    p = statistics.PoolInfo('individual')
+    for i, (lnl, nobs, nf) in enumerate([(10.5, 4, 3), (20.25, 6, 5)]):
+        f = statistics.FitInfo(nobs=nobs, nfeats=nf, epsilon=1e-7, max_iter=100)
+        f.final_lnl = lnl
+        p.models_info[i] = f
+    assert p.fitted_models == 2 and p.total_obs == 10 and p.total_params == 16
+    assert float(p.total_lnl) == 30.75
+    assert float(p.AIC) == 2 * 16 - 2 * 30.75
+    assert np.isclose(float(p.BIC), 16 * np.log(10) - 2 * 30.75)
+    assert set(p.to_dataframe()['var']) >= {'AIC', 'BIC', 'total_lnl', 'total_obs', 'total_params'}
+    r = statistics.ReassignInfo('total_hits')
+    r.assigned, r.ambiguous, r.unaligned = 7, 2, 1
+    assert r.format() == ['total_hits - 7 total alignments.',
+                          'total_hits - 2 reads initially had multiple alignments.']
+    assert statistics.counter_from_hist([3, 0, 5]) == {0: 3, 2: 5}
