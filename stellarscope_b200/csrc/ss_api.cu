@@ -9,6 +9,12 @@ using namespace ss;
 #define SS_REQUIRE_HANDLE(h) \
   if (!(h)) return SS_ERR_ARG
 
+// unpack one half of the packed index words (export for tests)
+__global__ void unpack_idx_kernel(long long n, const uint32_t* __restrict__ idx, int field, uint16_t* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint16_t)(field == 0 ? (idx[i] & 0xffffu) : (idx[i] >> 16));
+}
+
 extern "C" {
 
 int ss_abi_version(void) { return SS_ABI_VERSION; }
@@ -113,8 +119,9 @@ int ss_layout_export(ss_handle_t h, const char* name, void* dst, int64_t* bytes)
   const size_t T = (size_t)L.n_tiles, S = (size_t)L.S, NC = (size_t)L.n_segcols;
   const Ent table[] = {
       {"tile_hdr", L.tile_hdr, T * HDR_WORDS * 8},
-      {"e_lcol", L.e_lcol, (size_t)L.tot_ent * 2}, {"e_cpos", L.e_cpos, (size_t)L.tot_ent * 2},
+      {"e_lcol", nullptr, (size_t)L.tot_ent * 2}, {"e_cpos", nullptr, (size_t)L.tot_ent * 2},
       {"e_q", L.e_q, (size_t)L.tot_ent * 8}, {"e_opos", L.e_opos, (size_t)L.tot_ent * 4},
+      {"e_idx", L.e_idx, (size_t)L.tot_ent * 4},
       {"r_len", L.r_len, (size_t)L.tot_row * 2}, {"r_w", L.r_w, (size_t)L.tot_row * 8},
       {"r_orow", L.r_orow, (size_t)L.tot_row * 4},
       {"c_ptr", L.c_ptr, (size_t)L.tot_col * 2}, {"c_scol", L.c_scol, (size_t)L.tot_col * 4},
@@ -140,6 +147,17 @@ int ss_layout_export(ss_handle_t h, const char* name, void* dst, int64_t* bytes)
       }
       *bytes = (int64_t)e.b;
       cudaSetDevice(h->device);
+      if (e.b && !e.p) {
+        // one half of the packed index words
+        const int field = strcmp(name, "e_lcol") == 0 ? 0 : 1;
+        uint16_t* tmp = nullptr;
+        SS_CUDA_CHECK(h, cudaMalloc(&tmp, e.b));
+        unpack_idx_kernel<<<(unsigned)((L.tot_ent + 255) / 256), 256>>>(L.tot_ent, L.e_idx, field, tmp);
+        cudaError_t ce = cudaMemcpy(dst, tmp, e.b, cudaMemcpyDeviceToHost);
+        cudaFree(tmp);
+        SS_CUDA_CHECK(h, ce);
+        return SS_OK;
+      }
       if (e.b) SS_CUDA_CHECK(h, cudaMemcpy(dst, e.p, e.b, cudaMemcpyDeviceToHost));
       return SS_OK;
     }

@@ -228,8 +228,8 @@ struct TileBuildArgs {
   const int* seg_smax;
   int n_tiles;
   // outputs at their final offsets
-  uint16_t *e_lcol, *e_cpos;
   double* e_q;
+  uint32_t* e_idx;
   int* e_opos;
   uint16_t* r_len;
   double* r_w;
@@ -240,7 +240,7 @@ struct TileBuildArgs {
   uint16_t* tmp_jptr;
   int jds_stride;
   // per tile scalars
-  int *t_ncol, *t_maxlen, *t_nlong, *t_seg, *t_nrows, *t_nent;
+  int *t_ncol, *t_maxlen, *t_nlong, *t_seg, *t_nrows, *t_nent, *t_rfrag, *t_cfrag;
   double* t_wsum;
 };
 
@@ -303,8 +303,10 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
   // (c) entries
   const double inv = 1.0 / (double)a.seg_smax[seg];
   double wsum = 0.0;
+  int rfrag_local = 0;
   for (int r = tid; r < nrows; r += BUILD_THREADS) {
     const int row = rrow[r], len = rlen[r];
+    if (len <= FRAG * FRAG_MAXG_ROW) rfrag_local += frag_group(len);
     const int b = a.row_ptr[row];
     double w = 0.0;
     for (int p = 0; p < len; ++p) {
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
   for (int e = nent + tid; e < ep2; e += BUILD_THREADS) keys[e] = ~0ull;
   // zero the padding of the entry / row arrays
   for (int e = nent + tid; e < pad8(nent); e += BUILD_THREADS) {
-    a.e_q[eo + e] = 0.0; a.e_opos[eo + e] = 0; a.e_lcol[eo + e] = 0; a.e_cpos[eo + e] = 0;
+    a.e_q[eo + e] = 0.0; a.e_idx[eo + e] = 0u; a.e_opos[eo + e] = 0;
   }
   for (int r = nrows + tid; r < pad8(nrows); r += BUILD_THREADS) {
     a.r_len[ro + r] = 0; a.r_w[ro + r] = 0.0; a.r_orow[ro + r] = 0;
@@ -378,6 +380,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
     cptr[lc] = cnt;
     a.tmp_gcol[co_tmp + lc] = (int)((ckeys[lc] >> 16) & 0xffffffffu);
     nlong_local += cnt > LONG_COL;
+    if (cnt <= FRAG * FRAG_MAXG_COL) nlong_local += frag_group(cnt) << 16;   // packed: cfrag in the high half
   }
   if (tid == 0) cptr[ncol] = 0;
   __syncthreads();
@@ -386,13 +389,19 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
     const int ci = colidx[i];
     const int lc = rank_of[ci];
     const int e = (int)(keys[i] & 0xffffu);
-    a.e_lcol[eo + e] = (uint16_t)lc;
-    a.e_cpos[eo + e] = (uint16_t)(cptr[lc] + (i - colstart[ci]));
+    a.e_idx[eo + e] = pack_idx((unsigned)lc, (unsigned)(cptr[lc] + (i - colstart[ci])));
   }
   for (int lc = tid; lc <= ncol; lc += BUILD_THREADS) a.tmp_cptr[co_tmp + lc] = (uint16_t)cptr[lc];
   for (int p = tid; p <= lmax; p += BUILD_THREADS) a.tmp_jptr[(long long)a.jds_stride * t + p] = (uint16_t)jptr[p];
-  // number of long columns: block reduce
+  // number of long columns / column fragments / row fragments: block reduce
   {
+    int vr = rfrag_local;
+    for (int o = 16; o > 0; o >>= 1) vr += __shfl_xor_sync(0xffffffffu, vr, o);
+    __syncthreads();
+    if ((tid & 31) == 0) scratch[tid >> 5] = vr;
+    __syncthreads();
+    int rtot = 0;
+    for (int i = 0; i < BUILD_THREADS / 32; ++i) rtot += scratch[i];
     int v = nlong_local;
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
@@ -401,7 +410,9 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
     if (tid == 0) {
       int tot = 0;
       for (int i = 0; i < BUILD_THREADS / 32; ++i) tot += scratch[i];
-      a.t_nlong[t] = tot;
+      a.t_nlong[t] = tot & 0xffff;
+      a.t_cfrag[t] = tot >> 16;
+      a.t_rfrag[t] = rtot;
       a.t_ncol[t] = ncol;
       a.t_maxlen[t] = lmax;
       a.t_seg[t] = seg;
@@ -420,7 +431,8 @@ __global__ void tile_pad2_kernel(int n_tiles, const int* __restrict__ t_ncol, co
 }
 
 __global__ void tile_hdr_kernel(int n_tiles, const int* t_seg, const int* t_nrows, const int* t_nent, const int* t_ncol,
-                                const int* t_maxlen, const int* t_nlong, const long long* ent_off,
+                                const int* t_maxlen, const int* t_nlong, const int* t_rfrag, const int* t_cfrag,
+                                const long long* ent_off,
                                 const long long* row_off, const long long* col_off, const long long* jds_off,
                                 long long* __restrict__ hdr) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -429,6 +441,7 @@ __global__ void tile_hdr_kernel(int n_tiles, const int* t_seg, const int* t_nrow
   h[H_SEG] = t_seg[t]; h[H_NROWS] = t_nrows[t]; h[H_NENT] = t_nent[t]; h[H_NCOL] = t_ncol[t];
   h[H_MAXLEN] = t_maxlen[t]; h[H_NLONG] = t_nlong[t];
   h[H_ENT_OFF] = ent_off[t]; h[H_ROW_OFF] = row_off[t]; h[H_COL_OFF] = col_off[t]; h[H_JDS_OFF] = jds_off[t];
+  h[H_RFRAG] = t_rfrag[t]; h[H_CFRAG] = t_cfrag[t];
 }
 
 // copy cptr / jptr to their final offsets, emit (seg, locus) keys of the tile columns
@@ -726,8 +739,10 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
   SS_CUDA_CHECK(h, tmp.get(&jds_off, Tz + 1));
   SS_CUDA_CHECK(h, tmp.get(&key_cnt, Tz + 1));
   SS_CUDA_CHECK(h, tmp.get(&key_off, Tz + 1));
-  int *t_ncol, *t_maxlen, *t_nlong, *t_seg, *t_nrows, *t_nent;
+  int *t_ncol, *t_maxlen, *t_nlong, *t_seg, *t_nrows, *t_nent, *t_rfrag, *t_cfrag;
   double* t_wsum;
+  SS_CUDA_CHECK(h, tmp.get(&t_rfrag, Tz));
+  SS_CUDA_CHECK(h, tmp.get(&t_cfrag, Tz));
   SS_CUDA_CHECK(h, tmp.get(&t_ncol, Tz));
   SS_CUDA_CHECK(h, tmp.get(&t_maxlen, Tz));
   SS_CUDA_CHECK(h, tmp.get(&t_nlong, Tz));
@@ -755,9 +770,8 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
   }
   L.tot_ent = tot[0];
   L.tot_row = tot[1];
-  SS_CUDA_CHECK(h, dev_alloc(pool, &L.e_lcol, (size_t)L.tot_ent));
-  SS_CUDA_CHECK(h, dev_alloc(pool, &L.e_cpos, (size_t)L.tot_ent));
   SS_CUDA_CHECK(h, dev_alloc(pool, &L.e_q, (size_t)L.tot_ent));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &L.e_idx, (size_t)L.tot_ent));
   SS_CUDA_CHECK(h, dev_alloc(pool, &L.e_opos, (size_t)L.tot_ent));
   SS_CUDA_CHECK(h, dev_alloc(pool, &L.r_len, (size_t)L.tot_row));
   SS_CUDA_CHECK(h, dev_alloc(pool, &L.r_w, (size_t)L.tot_row));
@@ -770,11 +784,11 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
     TileBuildArgs a;
     a.row_ptr = row_ptr; a.col_idx = col_idx; a.score = score; a.ar = ar; a.aseg = aseg; a.tile_row0 = tile_row0;
     a.pre = pre; a.ent_off = ent_off; a.row_off = row_off; a.seg_smax = L.seg_smax; a.n_tiles = n_tiles;
-    a.e_lcol = L.e_lcol; a.e_cpos = L.e_cpos; a.e_q = L.e_q; a.e_opos = L.e_opos;
+    a.e_q = L.e_q; a.e_idx = L.e_idx; a.e_opos = L.e_opos;
     a.r_len = L.r_len; a.r_w = L.r_w; a.r_orow = L.r_orow;
     a.tmp_cptr = tmp_cptr; a.tmp_gcol = tmp_gcol; a.tmp_jptr = tmp_jptr; a.jds_stride = jds_stride;
     a.t_ncol = t_ncol; a.t_maxlen = t_maxlen; a.t_nlong = t_nlong; a.t_seg = t_seg; a.t_nrows = t_nrows;
-    a.t_nent = t_nent; a.t_wsum = t_wsum;
+    a.t_nent = t_nent; a.t_wsum = t_wsum; a.t_rfrag = t_rfrag; a.t_cfrag = t_cfrag;
     const size_t smem = tile_build_smem();
     SS_CUDA_CHECK(h, cudaFuncSetAttribute(tile_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tile_build_kernel<<<n_tiles, BUILD_THREADS, smem, st>>>(a);
@@ -793,7 +807,8 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
     SS_CUDA_CHECK(h, cudaMemcpyAsync(&tot[3], jds_off + n_tiles, 8, cudaMemcpyDeviceToHost, st));
     SS_CUDA_CHECK(h, cudaMemcpyAsync(&n_tilekeys, key_off + n_tiles, 8, cudaMemcpyDeviceToHost, st));
     tile_hdr_kernel<<<grid_for(n_tiles), 256, 0, st>>>(n_tiles, t_seg, t_nrows, t_nent, t_ncol, t_maxlen, t_nlong,
-                                                       ent_off, row_off, col_off, jds_off, L.tile_hdr);
+                                                       t_rfrag, t_cfrag, ent_off, row_off, col_off, jds_off,
+                                                       L.tile_hdr);
     h->launches++;
     h->hdr_host.resize((size_t)n_tiles * HDR_WORDS);
     SS_CUDA_CHECK(h, cudaMemcpyAsync(h->hdr_host.data(), L.tile_hdr, (size_t)n_tiles * HDR_WORDS * 8,

@@ -12,15 +12,33 @@
 
 namespace ss {
 
-constexpr int E_HARD = 4096;     // hard cap on alignments per tile
+constexpr int E_HARD = 4096;     // hard cap on alignments per tile (worst case fits 227 KB of shared memory)
 constexpr int ALIGN_ELEMS = 8;   // per-tile slices start at multiples of 8 elements (16 B for u16)
-constexpr int LONG_COL = 64;     // tile columns with more rows than this are reduced by a warp
-constexpr int HDR_WORDS = 10;    // int64 words per tile header
+constexpr int LONG_COL = 32;     // tile columns with more rows than this are reduced by a warp
+constexpr int HDR_WORDS = 12;    // int64 words per tile header
 
 // tile header word indices
-enum { H_SEG = 0, H_NROWS, H_NENT, H_NCOL, H_MAXLEN, H_NLONG, H_ENT_OFF, H_ROW_OFF, H_COL_OFF, H_JDS_OFF };
+enum { H_SEG = 0, H_NROWS, H_NENT, H_NCOL, H_MAXLEN, H_NLONG, H_ENT_OFF, H_ROW_OFF, H_COL_OFF, H_JDS_OFF,
+       H_RFRAG, H_CFRAG };
+
+// Fragments (resident kernel): a row / column is cut into pieces of FRAG entries handled by
+// one lane each; a row with f pieces occupies a lane group of size pow2ceil(f) (<= FRAG_MAXG_ROW),
+// a column one of size <= FRAG_MAXG_COL; longer ones take the generic path.
+constexpr int FRAG = 4;
+constexpr int FRAG_MAXG_ROW = 8;    // rows up to 32 alignments
+constexpr int FRAG_MAXG_COL = 32;   // columns up to 128 rows
+__host__ __device__ inline int frag_group(int len) {      // lanes a row/column of `len` entries occupies
+  const int f = (len + FRAG - 1) / FRAG;
+  int g = 1;
+  while (g < f) g <<= 1;
+  return g;
+}
 
 __host__ __device__ inline int pad8(int n) { return (n + 7) & ~7; }
+
+// per alignment of a tile: Q_ij (e_q) and a packed index word (e_idx) =
+// tile-local column | column-major slot << 16
+__host__ __device__ inline uint32_t pack_idx(uint32_t lcol, uint32_t cpos) { return lcol | (cpos << 16); }
 
 // Device-resident layout (all pointers are device pointers owned by the handle).
 struct Layout {
@@ -29,9 +47,8 @@ struct Layout {
   long long tot_ent = 0, tot_row = 0, tot_col = 0, tot_jds = 0;
   long long* tile_hdr = nullptr;
   // per alignment (tile order)
-  uint16_t* e_lcol = nullptr;
-  uint16_t* e_cpos = nullptr;
   double* e_q = nullptr;
+  uint32_t* e_idx = nullptr;
   int* e_opos = nullptr;
   // per ambiguous row (tile order)
   uint16_t* r_len = nullptr;

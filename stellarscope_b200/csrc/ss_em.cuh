@@ -10,6 +10,9 @@
 //       T_j  = x_j * sum_i val[i,j]                (= sum_i w_i z_ij = thetasum_j, model.py:239)
 // Every sum runs in a fixed order that depends only on the sparsity pattern, so two
 // loci that always co-occur with equal scores get bit-identical T.
+//
+// Per alignment the tile holds Q (f64) and one packed index word (tile-local column | slot in
+// the column-major scratch << 16).
 #pragma once
 #include "ss_common.cuh"
 
@@ -44,13 +47,12 @@ __device__ __forceinline__ TileView load_tile_view(const long long* __restrict__
 // shared-memory image of a tile
 struct TileSmem {
   double* q;       // pe  alignment weights Q_ij, JDS order
+  uint32_t* idx;   // pe  tile-local column | column-major slot << 16
   double* val;     // pe  scratch, column-major order
   double* w;       // pr  row weights
   double* pt;      // pc  x_j of the current E-step
   double* aux;     // pc  resident: pi_j ; streaming: unused
   double* pt2;     // pc  x_j after the M-step (ping-pong partner of pt)
-  uint16_t* lcol;  // pe  tile-local column of each alignment
-  uint16_t* cpos;  // pe  column-major slot of each alignment
   uint16_t* rlen;  // pr
   uint16_t* cptr;  // pc  column-major start of each tile column (ncol+1 used)
   uint16_t* jptr;  // pj  JDS start of each in-row position (maxlen+1 used)
@@ -58,7 +60,7 @@ struct TileSmem {
 
 __host__ __device__ inline size_t tile_smem_bytes(int nent, int nrows, int ncol, int maxlen) {
   const size_t pe = pad8(nent), pr = pad8(nrows), pc = pad8(ncol + 1), pj = pad8(maxlen + 1);
-  return 8 * (2 * pe + pr + 3 * pc) + 2 * (2 * pe + pr + pc + pj);
+  return 8 * (2 * pe + pr + 3 * pc) + 4 * pe + 2 * (pr + pc + pj);
 }
 
 __device__ __forceinline__ TileSmem carve_tile(unsigned char* base, const TileView& v) {
@@ -70,9 +72,8 @@ __device__ __forceinline__ TileSmem carve_tile(unsigned char* base, const TileVi
   s.pt = d;           d += v.pc;
   s.aux = d;          d += v.pc;
   s.pt2 = d;          d += v.pc;
-  uint16_t* u = reinterpret_cast<uint16_t*>(d);
-  s.lcol = u;         u += v.pe;
-  s.cpos = u;         u += v.pe;
+  s.idx = reinterpret_cast<uint32_t*>(d);
+  uint16_t* u = reinterpret_cast<uint16_t*>(s.idx + v.pe);
   s.rlen = u;         u += v.pr;
   s.cptr = u;         u += v.pc;
   s.jptr = u;
@@ -82,18 +83,17 @@ __device__ __forceinline__ TileSmem carve_tile(unsigned char* base, const TileVi
 // issue the TMA bulk copies of a tile's read-only arrays (one thread)
 __device__ __forceinline__ void tile_issue_loads(const Layout& L, const TileView& v, const TileSmem& s,
                                                  uint64_t* bar) {
-  const uint32_t bytes = 8u * v.pe + 8u * v.pr + 2u * (2u * v.pe + v.pr + v.pc + v.pj);
+  const uint32_t bytes = 12u * v.pe + 8u * v.pr + 2u * (v.pr + v.pc + v.pj);
   mbar_expect_tx(bar, bytes);
   bulk_g2s(s.q, L.e_q + v.eo, 8u * v.pe, bar);
+  bulk_g2s(s.idx, L.e_idx + v.eo, 4u * v.pe, bar);
   bulk_g2s(s.w, L.r_w + v.ro, 8u * v.pr, bar);
-  bulk_g2s(s.lcol, L.e_lcol + v.eo, 2u * v.pe, bar);
-  bulk_g2s(s.cpos, L.e_cpos + v.eo, 2u * v.pe, bar);
   bulk_g2s(s.rlen, L.r_len + v.ro, 2u * v.pr, bar);
   bulk_g2s(s.cptr, L.c_ptr + v.co, 2u * v.pc, bar);
   bulk_g2s(s.jptr, L.j_ptr + v.jo, 2u * v.pj, bar);
 }
 
-// phase A: row pass
+// phase A of a streamed tile: one thread per JDS row
 template <int THREADS>
 __device__ __forceinline__ void tile_phase_a(const TileView& v, const TileSmem& s, const double* __restrict__ pt) {
   for (int r = threadIdx.x; r < v.nrows; r += THREADS) {
@@ -101,27 +101,39 @@ __device__ __forceinline__ void tile_phase_a(const TileView& v, const TileSmem& 
     double acc = 0.0;
     for (int p = 0; p < len; ++p) {
       const int e = s.jptr[p] + r;
-      acc = fma(s.q[e], pt[s.lcol[e]], acc);
+      acc = fma(s.q[e], pt[s.idx[e] & 0xffffu], acc);
     }
     const double sc = acc > 0.0 ? s.w[r] * (1.0 / acc) : 0.0;
     for (int p = 0; p < len; ++p) {
       const int e = s.jptr[p] + r;
-      s.val[s.cpos[e]] = s.q[e] * sc;
+      s.val[s.idx[e] >> 16] = s.q[e] * sc;
     }
   }
 }
 
-// phase B helper: sum of the column-major slots of tile column c
-__device__ __forceinline__ double tile_col_sum_thread(const TileSmem& s, int c) {
-  const int b = s.cptr[c], e = s.cptr[c + 1];
-  double a = 0.0;
-  for (int k = b; k < e; ++k) a += s.val[k];
+// phase B helper: sum of the column-major slots [b, b+n) of a tile column, by one thread
+__device__ __forceinline__ double col_sum_thread(const double* __restrict__ val, int b, int n) {
+  const double* p = val + b;
+  double a;
+  switch (n) {
+    case 1: a = p[0]; break;
+    case 2: a = p[0] + p[1]; break;
+    case 3: a = (p[0] + p[1]) + p[2]; break;
+    case 4: a = ((p[0] + p[1]) + p[2]) + p[3]; break;
+    case 5: a = (((p[0] + p[1]) + p[2]) + p[3]) + p[4]; break;
+    case 6: a = ((((p[0] + p[1]) + p[2]) + p[3]) + p[4]) + p[5]; break;
+    case 7: a = (((((p[0] + p[1]) + p[2]) + p[3]) + p[4]) + p[5]) + p[6]; break;
+    case 8: a = ((((((p[0] + p[1]) + p[2]) + p[3]) + p[4]) + p[5]) + p[6]) + p[7]; break;
+    default:
+      a = 0.0;
+      for (int k = 0; k < n; ++k) a += p[k];
+      break;
+  }
   return a;
 }
-__device__ __forceinline__ double tile_col_sum_warp(const TileSmem& s, int c, int lane) {
-  const int b = s.cptr[c], e = s.cptr[c + 1];
+__device__ __forceinline__ double col_sum_warp(const double* __restrict__ val, int b, int n, int lane) {
   double a = 0.0;
-  for (int k = b + lane; k < e; k += 32) a += s.val[k];
+  for (int k = lane; k < n; k += 32) a += val[b + k];
   return warp_sum(a);
 }
 
@@ -138,12 +150,12 @@ __device__ __forceinline__ double tile_lnl_pass(const TileView& v, const TileSme
     double acc = 0.0;
     for (int p = 0; p < len; ++p) {
       const int e = s.jptr[p] + r;
-      acc = fma(s.q[e], ptold[s.lcol[e]], acc);
+      acc = fma(s.q[e], ptold[s.idx[e] & 0xffffu], acc);
     }
     const double inv = acc > 0.0 ? 1.0 / acc : 0.0;
     for (int p = 0; p < len; ++p) {
       const int e = s.jptr[p] + r;
-      const int c = s.lcol[e];
+      const int c = s.idx[e] & 0xffffu;
       const double q = s.q[e];
       const double z = (q * ptold[c]) * inv;
       if (want_lnl) {
@@ -168,12 +180,15 @@ __device__ __forceinline__ double block_sum(double v, double* red, int par) {
     return v;
   }
   double* r = red + 32 * (par & 1);
-  if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) r[threadIdx.x >> 5] = v;
   __syncthreads();
-  double t = 0.0;
+  // every warp reduces the NW partials the same way (one lane per partial, xor tree, broadcast):
+  // cheaper on the shared-memory data path than every lane reading all partials
+  double t = lane < NW ? r[lane] : 0.0;
 #pragma unroll
-  for (int i = 0; i < NW; ++i) t += r[i];
-  return t;
+  for (int o = NW / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return __shfl_sync(0xffffffffu, t, 0);
 }
 
 template <int THREADS>

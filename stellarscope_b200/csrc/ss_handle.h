@@ -8,6 +8,8 @@
 
 constexpr int SS_NUM_CLASSES = 6;
 constexpr int SS_NUM_AUX_STREAMS = SS_NUM_CLASSES + 1;
+constexpr int SS_FR = 2;   // row fragments held in registers per thread (resident kernel)
+constexpr int SS_FC = 2;   // column fragments per thread
 
 struct ss_handle_s {
   int device = 0;

@@ -9,6 +9,10 @@
 
 namespace ss {
 
+static size_t frag_smem_bytes_host(int nent, int ncol) {
+  return 8 * ((size_t)pad8(nent) + 3 * (size_t)pad8(ncol + 1));
+}
+
 void free_layout(ss_handle_s* h) {
   for (void* p : h->layout_allocs) cudaFree(p);
   h->layout_allocs.clear();
@@ -29,6 +33,12 @@ void free_layout(ss_handle_s* h) {
   h->has_layout = false;
 }
 
+__global__ void pack_idx_kernel(long long n, const uint16_t* __restrict__ lcol, const uint16_t* __restrict__ cpos,
+                                uint32_t* __restrict__ idx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) idx[i] = pack_idx(lcol[i], cpos[i]);
+}
+
 template <class T>
 static cudaError_t upload(std::vector<void*>& pool, T** dst, const T* src, size_t n, cudaStream_t st) {
   cudaError_t e = dev_alloc(pool, dst, n);
@@ -46,9 +56,20 @@ int layout_import(ss_handle_s* h, cudaStream_t st, const ss_host_layout* HL) {
   L.tot_ent = HL->tot_ent; L.tot_row = HL->tot_row; L.tot_col = HL->tot_col; L.tot_jds = HL->tot_jds;
   const size_t T = (size_t)L.n_tiles, S = (size_t)L.S, NC = (size_t)L.n_segcols;
   SS_CUDA_CHECK(h, upload(pool, &L.tile_hdr, (const long long*)HL->tile_hdr, T * HDR_WORDS, st));
-  SS_CUDA_CHECK(h, upload(pool, &L.e_lcol, HL->e_lcol, (size_t)L.tot_ent, st));
-  SS_CUDA_CHECK(h, upload(pool, &L.e_cpos, HL->e_cpos, (size_t)L.tot_ent, st));
-  SS_CUDA_CHECK(h, upload(pool, &L.e_q, HL->e_q, (size_t)L.tot_ent, st));
+  {
+    std::vector<void*> tmp;
+    uint16_t *d_lcol, *d_cpos;
+    SS_CUDA_CHECK(h, upload(tmp, &d_lcol, HL->e_lcol, (size_t)L.tot_ent, st));
+    SS_CUDA_CHECK(h, upload(tmp, &d_cpos, HL->e_cpos, (size_t)L.tot_ent, st));
+    SS_CUDA_CHECK(h, upload(pool, &L.e_q, HL->e_q, (size_t)L.tot_ent, st));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &L.e_idx, (size_t)L.tot_ent));
+    if (L.tot_ent > 0) {
+      pack_idx_kernel<<<(unsigned)((L.tot_ent + 255) / 256), 256, 0, st>>>(L.tot_ent, d_lcol, d_cpos, L.e_idx);
+      h->launches++;
+    }
+    SS_CUDA_CHECK(h, cudaStreamSynchronize(st));
+    for (void* q : tmp) cudaFree(q);
+  }
   SS_CUDA_CHECK(h, upload(pool, &L.e_opos, HL->e_opos, (size_t)L.tot_ent, st));
   SS_CUDA_CHECK(h, upload(pool, &L.r_len, HL->r_len, (size_t)L.tot_row, st));
   SS_CUDA_CHECK(h, upload(pool, &L.r_w, HL->r_w, (size_t)L.tot_row, st));
@@ -122,7 +143,8 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
       int c = 0;
       while (b0 > CLS_LIMIT[c]) ++c;
       cls[c].push_back(t);
-      h->cls_smem[c] = std::max(h->cls_smem[c], b0);
+      // the largest class runs the fragment kernel (tile data in registers, less shared memory)
+      h->cls_smem[c] = std::max(h->cls_smem[c], c == SS_NUM_CLASSES - 1 ? frag_smem_bytes_host(nent, ncol) : b0);
     } else {
       stream.push_back(t);
       h->stream_smem = std::max(h->stream_smem, b0);

@@ -34,6 +34,17 @@ E_HARD = 4096        # hard cap on alignments per tile (shared-memory budget, cs
 ALIGN = 8            # every per-tile slice starts at a multiple of 8 elements
 
 
+FRAG, FRAG_MAXG_ROW, FRAG_MAXG_COL = 4, 8, 32     # csrc/ss_common.cuh
+
+
+def frag_group(n):
+    f = (n + FRAG - 1) // FRAG
+    g = 1
+    while g < f:
+        g <<= 1
+    return g
+
+
 def _pad(n, a=ALIGN):
     return (n + a - 1) // a * a
 
@@ -48,7 +59,8 @@ class HostLayout:
     n_tiles: int
     chunk: int
     maxlen: int
-    # tile headers (int64 [n_tiles, 10]): seg, nrows, nent, ncol, maxlen, nlong, ent_off, row_off, col_off, jds_off
+    # tile headers (int64 [n_tiles, 12]): seg, nrows, nent, ncol, maxlen, nlong, ent_off, row_off, col_off, jds_off,
+    # rfrag, cfrag (lanes the rows / columns occupy in the fragment kernel; longer ones excluded)
     tile_hdr: np.ndarray
     # entry arrays
     e_lcol: np.ndarray   # u16
@@ -89,10 +101,10 @@ class HostLayout:
     u_row: np.ndarray       # i32 original row ids of unique rows of fitted segments
     u_pos: np.ndarray       # i32 CSR position of their single alignment
 
-    LONG_COL = 64
+    LONG_COL = 32
 
 
-def build(indptr, indices, scores, row_seg, S, K, e_hard=E_HARD, long_col=64):
+def build(indptr, indices, scores, row_seg, S, K, e_hard=E_HARD, long_col=32):
     indptr = np.asarray(indptr, dtype=np.int64)
     indices = np.asarray(indices, dtype=np.int64)
     scores = np.asarray(scores)
@@ -179,7 +191,7 @@ def build(indptr, indices, scores, row_seg, S, K, e_hard=E_HARD, long_col=64):
     n_tiles = int(seg_ntiles.sum())
     rtile = seg_tile0[aseg] + tin if len(ar) else np.zeros(0, dtype=np.int64)
 
-    hdr = np.zeros((n_tiles, 10), dtype=np.int64)
+    hdr = np.zeros((n_tiles, 12), dtype=np.int64)
     sc_inamb = np.zeros(len(ukey), dtype=np.int8)
     ent_off = row_off = col_off = jds_off = 0
     E_l, P_l, Q_l, O_l = [], [], [], []
@@ -222,7 +234,9 @@ def build(indptr, indices, scores, row_seg, S, K, e_hard=E_HARD, long_col=64):
                                              ug[corder])
         nlong = int((ccs > long_col).sum())
         sc_inamb[slot] = 1
-        hdr[t] = (s, nrows, nent, len(ug), ml, nlong, ent_off, row_off, col_off, jds_off)
+        rfrag = int(sum(frag_group(int(x)) for x in rl if x <= FRAG * FRAG_MAXG_ROW))
+        cfrag = int(sum(frag_group(int(x)) for x in ccs if x <= FRAG * FRAG_MAXG_COL))
+        hdr[t] = (s, nrows, nent, len(ug), ml, nlong, ent_off, row_off, col_off, jds_off, rfrag, cfrag)
 
         def padded(x, n, dtype):
             out = np.zeros(n, dtype=dtype); out[:len(x)] = x; return out
