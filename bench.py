@@ -125,6 +125,7 @@ class BenchOpts:
         self.reassign_mode = ['best_exclude']
         self.conf_prob = 0.9
         self.rng = np.random.default_rng(0)
+        self.shard_models = False      # weak scaling: every rank fits its own 10k cells
 
 
 # ---------------------------------------------------------------------------

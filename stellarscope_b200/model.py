@@ -333,13 +333,48 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
     poolinfo.nmodels = (len(st.bcode_ridx_map) if opts.pooling_mode == 'individual'
                         else len(st.celltypes))             # model.py:772, 778
     lg.info(f'Models to fit: {poolinfo.nmodels}')
-    ret_model = TelescopeLikelihood(fullmat, opts, row_segment=row_segment, n_segments=len(keys))
-    infos = ret_model.fit_segments()
+    world, rank = _dist_info()
+    if not getattr(opts, 'shard_models', True):
+        world = 1                    # every rank fits its own, independent data set
+    if world == 1:
+        ret_model = TelescopeLikelihood(fullmat, opts, row_segment=row_segment, n_segments=len(keys))
+        infos = ret_model.fit_segments()
+    else:
+        # models are independent: shard them over the ranks (one process per GPU), no collective on
+        # the data path; every rank keeps the global row numbering, rows of other ranks' models are
+        # simply not fitted here
+        from . import parallel
+        import torch.distributed as dist
+        m = _canonical_csr(fullmat)
+        shards, _ = parallel.shard_models(m.indptr, row_segment, len(keys), world)
+        mine = shards[rank]
+        remap = np.full(len(keys) + 1, -1, dtype=np.int32)
+        remap[mine] = np.arange(len(mine), dtype=np.int32)
+        local_seg = np.where(row_segment >= 0, remap[np.maximum(row_segment, 0)], -1).astype(np.int32)
+        ret_model = TelescopeLikelihood(m, opts, row_segment=local_seg, n_segments=len(mine))
+        ret_model.model_ids = mine
+        local_infos = ret_model.fit_segments()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (mine.tolist(), local_infos))
+        infos = [None] * len(keys)
+        for ids, recs in gathered:
+            for i, fi in zip(ids, recs):
+                infos[i] = fi
     for k, fi in zip(keys, infos):
         poolinfo.models_info[k] = fi
     lg.info(f'        ...{len(infos)} models fitted')
     ret_model.lnl = poolinfo.total_lnl                      # model.py:803
     return ret_model, poolinfo
+
+
+def _dist_info():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(), dist.get_rank()
+    except Exception:
+        pass
+    return 1, 0
 
 
 # ---------------------------------------------------------------------------
@@ -379,9 +414,26 @@ def count_matrices(st, tl: TelescopeLikelihood):
         row_umi = np.fromiter((umi_ids.setdefault(st.read_umi_map[q], len(umi_ids)) for q in qnames),
                               dtype=np.int32, count=len(qnames))
     out = OrderedDict()
+    world, rank = _dist_info()
+    if not getattr(st.opts, 'shard_models', True):
+        world = 1
     for _rmode in st.opts.reassign_mode:
         remat = st.reassignments[_rmode]
-        out[_rmode] = remat.count_by_cell(row_cell, numbc, row_umi=row_umi, engine=tl._engine)
+        cm = remat.count_by_cell(row_cell, numbc, row_umi=row_umi, engine=tl._engine)
+        if world > 1:
+            # every rank holds the counts of its own models' rows (disjoint): add them up.  The modes
+            # that do not use z (initial_*, total_hits) are identical on every rank.
+            import torch.distributed as dist
+            parts = [None] * world
+            dist.all_gather_object(parts, cm)
+            if _rmode in ('initial_unique', 'initial_random', 'total_hits'):
+                cm = parts[0]
+            else:
+                cm = parts[0]
+                for pm in parts[1:]:
+                    cm = cm + pm
+                cm = scipy.sparse.csr_matrix(cm)
+        out[_rmode] = cm
         if out[_rmode].shape != (numft, numbc):
             raise StellarscopeError(f'Incompatible shapes: {out[_rmode].shape} != {(numft, numbc)}')
     return out, bc_list, ft_list
