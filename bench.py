@@ -240,11 +240,11 @@ def run_ours(args):
         e.record()
         return s, e
 
+    sampler = ClockSampler(local)          # samples clocks / throttle reasons from the warm-up on
+    sampler.start()
     for _ in range(args.warmup):
         one_fit()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     l0 = eng.launch_count()
     evs = []
     t_wall0 = time.perf_counter()
@@ -346,7 +346,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     args = ap.parse_args()

@@ -37,6 +37,12 @@ int ss_create(int device, ss_handle_t* out) {
   h->num_sms = v > 0 ? v : 148;
   cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   h->max_smem_optin = (size_t)v;
+  // keep the stream-ordered pool's memory across synchronisations (temporaries of the builder)
+  cudaMemPool_t mp;
+  if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
   *out = h;
   return SS_OK;
 }

@@ -18,14 +18,22 @@ namespace ss {
 
 namespace {
 
+// temporaries come from the stream-ordered pool (cudaMallocAsync): no device-wide
+// synchronisation per allocation, memory is reused across builds
 struct TmpPool {
+  cudaStream_t st;
   std::vector<void*> p;
+  explicit TmpPool(cudaStream_t s) : st(s) {}
   ~TmpPool() {
-    for (void* q : p) cudaFree(q);
+    for (void* q : p) cudaFreeAsync(q, st);
   }
   template <class T>
   cudaError_t get(T** out, size_t n) {
-    return dev_alloc(p, out, n);
+    *out = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(out), n * sizeof(T), st);
+    if (e == cudaSuccess) p.push_back(*out);
+    return e;
   }
 };
 
@@ -610,7 +618,7 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
   free_layout(h);
   Layout& L = h->L;
   auto& pool = h->layout_allocs;
-  TmpPool tmp;
+  TmpPool tmp(st);
   const int N = n_rows, S = n_segments;
   L.N = N; L.K = n_cols; L.S = S; L.A = nnz;
   const size_t Sz = (size_t)std::max(S, 1);

@@ -66,7 +66,10 @@ class TelescopeLikelihood(object):
         self.pi_prior = opts.pi_prior
         self.theta_prior = opts.theta_prior
         self.tie_tol = tie_tol
-        self.raw_scores = csr_matrix_plus(_canonical_csr(score_matrix))
+        self.raw_scores = (score_matrix if isinstance(score_matrix, csr_matrix_plus) and
+                           getattr(score_matrix, '_ss_canonical', False)
+                           else csr_matrix_plus(_canonical_csr(score_matrix)))
+        self.raw_scores._ss_canonical = True
         self.N, self.K = self.raw_scores.shape
         self.max_score = int(self.raw_scores.data.max()) if self.raw_scores.nnz else 0
         self.scale_factor = 100.
@@ -164,16 +167,16 @@ class TelescopeLikelihood(object):
             raise StellarscopeError(('invalid value encountered in divide',
                                      f'model {bad} has no alignments or a zero denominator'))
         tot_it = max(1, int(res['iters'].sum()))
+        itime = self.fit_seconds / tot_it
+        iters, flags, lnl = res['iters'].tolist(), res['flags'].tolist(), res['lnl'].tolist()
+        nobs, nfeats, diffs = res['nobs'].tolist(), res['nfeats'].tolist(), res['diffs']
         infos = []
         for s in range(self.n_segments):
-            fi = FitInfo(nobs=int(res['nobs'][s]), nfeats=int(res['nfeats'][s]), epsilon=self.epsilon,
-                         max_iter=self.max_iter)
-            n = int(res['iters'][s])
-            fi.converged = bool(res['flags'][s] & 1)
-            fi.reached_max = bool(res['flags'][s] & 2)
-            itime = self.fit_seconds / tot_it
-            fi.iterations = [(i + 1, itime, float(res['diffs'][s, i])) for i in range(n)]
-            fi.final_lnl = float(res['lnl'][s])
+            fi = FitInfo(nobs=nobs[s], nfeats=nfeats[s], epsilon=self.epsilon, max_iter=self.max_iter)
+            fi.converged = bool(flags[s] & 1)
+            fi.reached_max = bool(flags[s] & 2)
+            fi.set_trace(iters[s], itime, diffs[s])
+            fi.final_lnl = lnl[s]
             infos.append(fi)
         self.segment_fitinfo = infos
         self._results = res
@@ -276,15 +279,20 @@ def pooling_row_segments(st, opts):
     seg = np.full(N, -1, dtype=np.int32)
     i = 0
     if opts.pooling_mode == 'individual':
+        import itertools
+        sets = []
         for _bcode, rowset in st.bcode_ridx_map.items():
             if not rowset:
                 lg.info(f'        ...not fitting "{_bcode}" -> no reads found')
                 continue
-            rows = np.fromiter(rowset, dtype=np.int64, count=len(rowset))
-            if (seg[rows] >= 0).any():
-                raise StellarscopeError('a read belongs to more than one barcode')
-            seg[rows] = i
-            i += 1
+            sets.append(rowset)
+        lens = np.fromiter((len(x) for x in sets), dtype=np.int64, count=len(sets))
+        rows = np.fromiter(itertools.chain.from_iterable(sets), dtype=np.int64, count=int(lens.sum()))
+        ids = np.repeat(np.arange(len(sets), dtype=np.int32), lens)
+        if len(rows) and np.bincount(rows, minlength=N).max() > 1:
+            raise StellarscopeError('a read belongs to more than one barcode')
+        seg[rows] = ids
+        i = len(sets)
     elif opts.pooling_mode == 'celltype':
         for _ctype in st.celltypes:
             rows = []

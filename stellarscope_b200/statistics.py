@@ -49,8 +49,31 @@ class FitInfo(GenericInfo):
         self.nfeats = nfeats
         self.epsilon = epsilon
         self.max_iter = max_iter
-        self.iterations = []
+        self._iterations = []
+        self._trace = None            # (n, itime, diffs ndarray): materialised on first access
         self.final_lnl = None
+
+    @property
+    def iterations(self):
+        """list of ``(inum, itime, diff_est)`` (model.py:359).  With thousands of models the
+        tuples are only built when somebody looks at them."""
+        if self._trace is not None:
+            n, itime, diffs = self._trace
+            self._iterations = [(i + 1, itime, float(diffs[i])) for i in range(n)]
+            self._trace = None
+        return self._iterations
+
+    @iterations.setter
+    def iterations(self, value):
+        self._trace = None
+        self._iterations = value
+
+    @property
+    def n_iterations(self) -> int:
+        return self._trace[0] if self._trace is not None else len(self._iterations)
+
+    def set_trace(self, n, itime, diffs):
+        self._trace = (int(n), float(itime), diffs)
 
     @property
     def fitted(self) -> bool:
