@@ -54,6 +54,7 @@ enum ss_reassign_mode {
 typedef struct ss_layout_info {
   int32_t n_rows, n_cols, n_segments, n_tiles, max_row_len, chunk;
   int32_t n_unique_rows, n_resident_tiles, n_stream_tiles, n_stream_segments;
+  int32_t n_cluster_tiles, n_cluster_segments;
   int64_t nnz, n_segcols, tot_ent, tot_row, tot_col, tot_jds;
   int64_t nnz_ambiguous, rows_ambiguous;
 } ss_layout_info;
@@ -175,7 +176,8 @@ int64_t ss_launch_count(ss_handle_t h);
  * events; ss_get_timings synchronises on them and returns the device time in ms of the last
  * fit: [0] prepare, [1] all EM kernels (they run concurrently), [2] unused, [3] emit,
  * [4] finalize, [5..10] span of the resident kernel of size class 0..5 (32..1024 threads),
- * [11] span of the streaming kernel.  n >= 12. */
+ * [11] span of the streaming kernel, [12..18] span of the cluster kernels for segments of
+ * 2..8 tiles.  n >= 12. */
 int ss_set_timing(ss_handle_t h, int32_t enabled);
 int ss_get_timings(ss_handle_t h, double* ms, int32_t n);
 

@@ -31,7 +31,8 @@ c_f64p = C.POINTER(C.c_double)
 class LayoutInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         'n_rows', 'n_cols', 'n_segments', 'n_tiles', 'max_row_len', 'chunk',
-        'n_unique_rows', 'n_resident_tiles', 'n_stream_tiles', 'n_stream_segments')] + \
+        'n_unique_rows', 'n_resident_tiles', 'n_stream_tiles', 'n_stream_segments',
+        'n_cluster_tiles', 'n_cluster_segments')] + \
         [(n, C.c_int64) for n in (
             'nnz', 'n_segcols', 'tot_ent', 'tot_row', 'tot_col', 'tot_jds',
             'nnz_ambiguous', 'rows_ambiguous')]

@@ -107,7 +107,8 @@ int ss_layout_get_info(ss_handle_t h, ss_layout_info* o) {
   o->n_rows = L.N; o->n_cols = L.K; o->n_segments = L.S; o->n_tiles = L.n_tiles;
   o->max_row_len = L.maxlen; o->chunk = L.chunk; o->n_unique_rows = L.n_uniq;
   o->n_stream_tiles = h->n_stream_tiles; o->n_stream_segments = h->n_stream_segs;
-  o->n_resident_tiles = L.n_tiles - h->n_stream_tiles;
+  o->n_resident_tiles = L.n_tiles - h->n_stream_tiles - h->n_cluster_tiles;
+  o->n_cluster_tiles = h->n_cluster_tiles; o->n_cluster_segments = h->n_cluster_segs;
   o->nnz = L.A; o->n_segcols = L.n_segcols;
   o->tot_ent = L.tot_ent; o->tot_row = L.tot_row; o->tot_col = L.tot_col; o->tot_jds = L.tot_jds;
   o->nnz_ambiguous = h->nnz_amb; o->rows_ambiguous = h->rows_amb;
@@ -305,7 +306,7 @@ int ss_set_timing(ss_handle_t h, int32_t enabled) {
 
 int ss_get_timings(ss_handle_t h, double* ms, int32_t n) {
   SS_REQUIRE_HANDLE(h);
-  if (!ms || n < 5 + SS_NUM_AUX_STREAMS || !h->ev_valid) {
+  if (!ms || n < 12 || !h->ev_valid) {
     h->set_error("ss_get_timings: timing not enabled / no fit / buffer too small");
     return SS_ERR_STATE;
   }
@@ -320,7 +321,7 @@ int ss_get_timings(ss_handle_t h, double* ms, int32_t n) {
   for (int i = 0; i < SS_NUM_AUX_STREAMS; ++i) {
     float t = 0.f;
     if (h->aux_used[i]) SS_CUDA_CHECK(h, cudaEventElapsedTime(&t, h->tev_s[i], h->tev_e[i]));
-    ms[5 + i] = t;
+    if (5 + i < n) ms[5 + i] = t;
   }
   return SS_OK;
 }

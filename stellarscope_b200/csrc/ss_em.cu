@@ -599,6 +599,221 @@ __global__ void __launch_bounds__(THREADS) em_fragment_kernel(EmArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// cluster kernel: one thread-block CLUSTER per segment of 2..8 tiles.  Every CTA keeps its
+// tile resident in shared memory (like the resident kernel); the columns of the segment are
+// owned round-robin by the CTAs (owner of segment column j = j mod nt).  Per iteration:
+//   phase A (local rows) | barrier | phase B (local partial column sums -> `part`)
+//   cluster.sync | owners pull the partial sums of their columns from every tile over DSMEM
+//   in fixed tile order (deterministic), compute theta', pi', x', |delta pi|
+//   cluster.sync | every CTA pulls x' of its tile columns from the owners and the nt partial
+//   |delta pi| sums, takes the (identical) convergence decision.
+// No global memory traffic and no atomics inside the loop.
+// ---------------------------------------------------------------------------
+struct ClusterArgs {
+  const int* segs;
+  const uint16_t* xref;
+  const long long* seg_xref_off;
+};
+
+template <int THREADS, bool LNL, int NT>
+__global__ void __launch_bounds__(THREADS) em_cluster_kernel(EmArgs a, ClusterArgs ca) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  __shared__ double s_red[64];
+  __shared__ double s_dsum[2];          // [0] |delta pi| of the owned columns, [1] lnL part
+  __shared__ uint64_t s_bar;
+  constexpr int NW = THREADS / 32;
+  constexpr int nt = NT;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = (int)cluster.block_rank();
+  const int seg = ca.segs[blockIdx.x / nt];
+  const int t = a.L.seg_tile0[seg] + rank;
+  const TileView v = load_tile_view(a.L.tile_hdr, t);
+  TileSmem s = carve_tile(dsm, v);
+  const int Kc = a.L.seg_ncol[seg], col0 = a.L.seg_col0[seg];
+  const int no_max = (Kc + nt - 1) / nt;                    // owned columns, upper bound (same on every rank)
+  const int no_pad = pad8(no_max + 1);
+  const int n_owned = rank < Kc ? (Kc - rank + nt - 1) / nt : 0;
+  // owner arrays live at the same offset in every CTA of the cluster (largest tile of the segment)
+  size_t tile_bytes = 0;
+  int aux_off[NT];                                           // offset (doubles) of `part` in every tile's image
+#pragma unroll
+  for (int k = 0; k < NT; ++k) {
+    const TileView vk = load_tile_view(a.L.tile_hdr, a.L.seg_tile0[seg] + k);
+    const size_t bts = tile_smem_bytes(vk.nent, vk.nrows, vk.ncol, vk.maxlen);
+    tile_bytes = bts > tile_bytes ? bts : tile_bytes;
+    aux_off[k] = 2 * vk.pe + vk.pr + vk.pc;                  // q, val, w, pt precede aux (carve_tile)
+  }
+  tile_bytes = (tile_bytes + 127) & ~(size_t)127;
+  double* own_x0 = reinterpret_cast<double*>(dsm + tile_bytes);
+  double* own_x1 = own_x0 + no_pad;
+  double* own_pi = own_x1 + no_pad;
+  double* own_ps0 = own_pi + no_pad;
+  uint16_t* own_xref = reinterpret_cast<uint16_t*>(own_ps0 + no_pad);   // [n_owned][NT]
+  double* part = s.aux;                                      // partial column sums of this tile
+
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) tile_issue_loads(a.L, v, s, &s_bar);
+  const double invK = 1.0 / (double)a.P.K;
+  const bool has_uniq = a.L.seg_nuniq[seg] > 0;
+  const uint16_t* __restrict__ xref = ca.xref + ca.seg_xref_off[seg];
+  for (int c = tid; c < v.ncol; c += THREADS) s.pt[c] = invK * invK;
+  for (int i = tid; i < n_owned; i += THREADS) {
+    const int j = rank + i * nt;
+    own_x0[i] = invK * invK;
+    own_pi[i] = invK;
+    own_ps0[i] = has_uniq ? a.L.sc_pisum0[col0 + j] : 0.0;
+#pragma unroll
+    for (int k = 0; k < NT; ++k) own_xref[i * NT + k] = xref[(long long)j * nt + k];
+  }
+  const double thpw = a.F.seg_thpw[seg], pipw = a.F.seg_pipw[seg];
+  const double inv_thd = a.F.seg_inv_thd[seg], inv_pid = a.F.seg_inv_pid[seg];
+  const double diff1_extra = a.F.seg_diff1_extra[seg];
+  const double eps = a.P.eps;
+  const int max_iter = a.P.max_iter;
+  const int* __restrict__ scol = a.L.c_scol + v.co;
+  double* diffs = a.F.seg_diffs + (long long)seg * max_iter;
+  double* lnls = a.F.seg_lnls ? a.F.seg_lnls + (long long)seg * max_iter : nullptr;
+  double* dsm_d = reinterpret_cast<double*>(dsm);
+  mbar_wait(&s_bar, 0);
+  __syncthreads();
+  cluster.sync();                                            // everybody's shared memory is initialised
+
+  double* pt_cur = s.pt;
+  double* pt_nxt = s.pt2;
+  int cur = 0;                                               // own_x buffer holding the current x
+  double lnl_prev = INFINITY;
+  int it = 0, par = 0;
+  bool done = false, conv = false;
+  while (!done) {
+    ++it;
+    tile_phase_a<THREADS>(v, s, pt_cur);
+    __syncthreads();
+    for (int c = warp; c < v.nlong; c += NW) {
+      const int b = s.cptr[c], n = (int)s.cptr[c + 1] - b;
+      const double asum = col_sum_warp(s.val, b, n, lane);
+      if (lane == 0) part[c] = asum;
+    }
+    for (int c = v.nlong + tid; c < v.ncol; c += THREADS) {
+      const int b = s.cptr[c], n = (int)s.cptr[c + 1] - b;
+      part[c] = col_sum_thread(s.val, b, n);
+    }
+    cluster.sync();
+    // ---- owners: thetasum of the owned segment columns, new parameters ----
+    double* ox_cur = cur ? own_x1 : own_x0;
+    double* ox_nxt = cur ? own_x0 : own_x1;
+    double dsum = 0.0;
+    for (int i = tid; i < n_owned; i += THREADS) {
+      double pk[NT];
+      bool in_tile = false;
+#pragma unroll
+      for (int k = 0; k < NT; ++k) {                         // all remote loads in flight together
+        const unsigned c = own_xref[i * NT + k];
+        pk[k] = 0.0;
+        if (c != 0xffffu) {
+          pk[k] = cluster.map_shared_rank(dsm_d + aux_off[k], k)[c];
+          in_tile = true;
+        }
+      }
+      if (!in_tile) continue;       // column of unique rows only: constant, handled by prepare / finalize
+      double asum = 0.0;
+#pragma unroll
+      for (int k = 0; k < NT; ++k) asum += pk[k];             // fixed tile order
+      const double T = ox_cur[i] * asum;
+      const double th = (T + thpw) * inv_thd;                           // model.py:240
+      const double pn = (own_ps0[i] + T + pipw) * inv_pid;              // model.py:243-244
+      dsum += fabs(pn - own_pi[i]);
+      own_pi[i] = pn;
+      ox_nxt[i] = pn * th;
+    }
+    dsum = block_sum<THREADS>(dsum, s_red, par++);
+    if (tid == 0) s_dsum[0] = dsum;
+    cluster.sync();
+    // ---- everybody: x' of the tile's columns, convergence ----
+    double diff = 0.0;
+#pragma unroll
+    for (int k = 0; k < NT; ++k) diff += cluster.map_shared_rank(s_dsum, k)[0];
+    if (it == 1) diff += diff1_extra;
+    {
+      const double* ox = cur ? own_x0 : own_x1;              // buffer written in this iteration
+      for (int c = tid; c < v.ncol; c += THREADS) {
+        const int j = scol[c] - col0;
+        pt_nxt[c] = cluster.map_shared_rank(ox, j % nt)[j / nt];
+      }
+    }
+    const bool reached = it >= max_iter;
+    if (!LNL) {
+      conv = diff < eps;
+      __syncthreads();
+    } else {
+      __syncthreads();
+      double l = tile_lnl_pass<THREADS>(v, s, pt_cur, pt_nxt, true, nullptr, nullptr);
+      if (has_uniq)
+        for (int i = tid; i < n_owned; i += THREADS) {
+          bool in_tile = false;
+#pragma unroll
+          for (int k = 0; k < NT; ++k) in_tile |= own_xref[i * NT + k] != 0xffffu;
+          const int nu = a.L.sc_nuniq[col0 + rank + i * nt];
+          if (in_tile && nu > 0 && own_pi[i] > 0.0) l += (double)nu * log(own_pi[i]);
+        }
+      l = block_sum<THREADS>(l, s_red, par++);
+      if (tid == 0) s_dsum[1] = l;
+      cluster.sync();
+      double lnl = a.F.seg_lnl_extra[seg];
+#pragma unroll
+      for (int k = 0; k < NT; ++k) lnl += cluster.map_shared_rank(s_dsum, k)[1];
+      conv = fabs(lnl - lnl_prev) < eps;
+      lnl_prev = lnl;
+      if (rank == 0 && tid == 0 && lnls) lnls[it - 1] = lnl;
+    }
+    done = conv || reached;
+    if (rank == 0 && tid == 0) diffs[it - 1] = diff;
+    if (!done) {
+      double* tmp = pt_cur; pt_cur = pt_nxt; pt_nxt = tmp;
+      cur ^= 1;
+    }
+  }
+  // ---- publish ----
+  {
+    const double* ox_cur = cur ? own_x1 : own_x0;
+    const double* ox_nxt = cur ? own_x0 : own_x1;
+    for (int i = tid; i < n_owned; i += THREADS) {
+      const int j = rank + i * nt;
+      bool in_tile = false;
+#pragma unroll
+      for (int k = 0; k < NT; ++k) in_tile |= own_xref[i * NT + k] != 0xffffu;
+      if (!in_tile) continue;
+      a.F.sc_pi[col0 + j] = own_pi[i];
+      a.F.sc_ptprev[col0 + j] = ox_cur[i];
+      a.F.sc_ptfin[col0 + j] = ox_nxt[i];
+      // theta' = x' / pi' would lose the last bit: recompute it like the iteration did
+      const double xo = ox_cur[i];
+      double asum = 0.0;
+#pragma unroll
+      for (int k = 0; k < NT; ++k) {
+        const unsigned c = own_xref[i * NT + k];
+        if (c != 0xffffu) asum += cluster.map_shared_rank(dsm_d + aux_off[k], k)[c];
+      }
+      a.F.sc_theta[col0 + j] = (xo * asum + thpw) * inv_thd;
+    }
+  }
+  double l = tile_lnl_pass<THREADS>(v, s, pt_cur, pt_nxt, true, nullptr, nullptr);
+  l = block_sum<THREADS>(l, s_red, par++);
+  if (tid == 0) {
+    a.F.tile_lnl[t] = l;
+    if (rank == 0) {
+      a.F.seg_iters[seg] = it;
+      a.F.seg_flags[seg] = (conv ? 1 : 0) | (it >= max_iter ? 2 : 0);
+    }
+  }
+  cluster.sync();                                            // nobody leaves while its shared memory may be read
+}
+
+// ---------------------------------------------------------------------------
 // streaming kernel: cooperative grid over the tiles of multi-tile segments
 // ---------------------------------------------------------------------------
 template <int THREADS, bool LNL>
@@ -925,6 +1140,7 @@ static cudaError_t ensure_aux_streams(ss_handle_s* h) {
 }
 
 constexpr int STREAM_THREADS = 512;
+constexpr int CLUSTER_THREADS = 512;
 
 int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
   if (!h->has_layout) {
@@ -1035,6 +1251,48 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     SS_CUDA_CHECK(h, cudaGetLastError());
     if (h->timing) SS_CUDA_CHECK(h, cudaEventRecord(h->tev_e[SS_NUM_CLASSES], sx));
     SS_CUDA_CHECK(h, cudaEventRecord(h->ev_join[SS_NUM_CLASSES], sx));
+  }
+  // clusters: segments of 2..8 tiles
+  for (int nt = ss_handle_s::MAX_CLUSTER; nt >= 2; --nt) {
+    if (h->clu_count[nt] == 0) continue;
+    const int si = SS_NUM_CLASSES + 1 + (nt - 2);
+    cudaStream_t sx = h->aux[si];
+    h->aux_used[si] = true;
+    SS_CUDA_CHECK(h, cudaStreamWaitEvent(sx, h->ev_fork, 0));
+    if (h->timing) SS_CUDA_CHECK(h, cudaEventRecord(h->tev_s[si], sx));
+    ClusterArgs ca;
+    ca.segs = h->clu_segs[nt];
+    ca.xref = h->clu_xref;
+    ca.seg_xref_off = h->seg_xref_off;
+    a.tile_list = nullptr;
+    a.n_list = 0;
+    void (*kfn)(EmArgs, ClusterArgs) = nullptr;
+    switch (nt) {
+#define SS_CLU_CASE(N)                                                                                  \
+  case N:                                                                                               \
+    kfn = lnl ? em_cluster_kernel<CLUSTER_THREADS, true, N> : em_cluster_kernel<CLUSTER_THREADS, false, N>; \
+    break;
+      SS_CLU_CASE(2) SS_CLU_CASE(3) SS_CLU_CASE(4) SS_CLU_CASE(5) SS_CLU_CASE(6) SS_CLU_CASE(7) SS_CLU_CASE(8)
+#undef SS_CLU_CASE
+    }
+    const size_t smem = h->clu_smem[nt] + 256;
+    SS_CUDA_CHECK(h, cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(h->clu_count[nt] * nt));
+    cfg.blockDim = dim3(CLUSTER_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = sx;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)nt;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SS_CUDA_CHECK(h, cudaLaunchKernelEx(&cfg, kfn, a, ca));
+    h->launches++;
+    if (h->timing) SS_CUDA_CHECK(h, cudaEventRecord(h->tev_e[si], sx));
+    SS_CUDA_CHECK(h, cudaEventRecord(h->ev_join[si], sx));
   }
   for (int c = SS_NUM_CLASSES - 1; c >= 0; --c) {
     if (h->cls_count[c] == 0) continue;

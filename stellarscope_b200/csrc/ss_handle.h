@@ -7,7 +7,7 @@
 #include "ss_common.cuh"
 
 constexpr int SS_NUM_CLASSES = 6;
-constexpr int SS_NUM_AUX_STREAMS = SS_NUM_CLASSES + 1;
+constexpr int SS_NUM_AUX_STREAMS = SS_NUM_CLASSES + 1 + 7;   // size classes, streaming kernel, cluster sizes 2..8
 constexpr int SS_FR = 2;   // row fragments held in registers per thread (resident kernel)
 constexpr int SS_FC = 2;   // column fragments per thread
 
@@ -36,6 +36,14 @@ struct ss_handle_s {
   int* stream_col_slot = nullptr; // device: its absolute slot
   long long n_stream_cols = 0;
   size_t stream_smem = 0;
+  // segments of 2..8 tiles: one thread-block cluster per segment (DSMEM exchange)
+  static constexpr int MAX_CLUSTER = 8;
+  int* clu_segs[MAX_CLUSTER + 1] = {};     // device: segment ids by number of tiles
+  int clu_count[MAX_CLUSTER + 1] = {};
+  size_t clu_smem[MAX_CLUSTER + 1] = {};
+  uint16_t* clu_xref = nullptr;            // device: [segment column][tile of the segment] -> tile column or 0xffff
+  long long* seg_xref_off = nullptr;       // device: offset of a segment's block in clu_xref (-1: none)
+  int n_cluster_tiles = 0, n_cluster_segs = 0;
   int* all_tiles = nullptr;       // device: 0 .. n_tiles-1
   size_t all_smem = 0;            // smem of the largest tile (likelihood-mode carve)
   int8_t* sc_inamb = nullptr;     // device: segment column is touched by a tile

@@ -30,6 +30,8 @@ void free_layout(ss_handle_s* h) {
   h->n_stream_cols = 0;
   h->all_tiles = nullptr;
   h->sc_inamb = nullptr;
+  for (int k = 0; k <= ss_handle_s::MAX_CLUSTER; ++k) { h->clu_segs[k] = nullptr; h->clu_count[k] = 0; h->clu_smem[k] = 0; }
+  h->clu_xref = nullptr; h->seg_xref_off = nullptr; h->n_cluster_tiles = h->n_cluster_segs = 0;
   h->has_layout = false;
 }
 
@@ -37,6 +39,20 @@ __global__ void pack_idx_kernel(long long n, const uint16_t* __restrict__ lcol, 
                                 uint32_t* __restrict__ idx) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) idx[i] = pack_idx(lcol[i], cpos[i]);
+}
+
+// cross reference of the cluster kernel: for every column of a clustered segment, its local
+// column index inside each tile of the segment
+__global__ void cluster_xref_kernel(const int* __restrict__ tiles, int n, Layout L, const long long* __restrict__ seg_xref_off,
+                                    uint16_t* __restrict__ xref) {
+  const int t = tiles[blockIdx.x];
+  const long long* h = L.tile_hdr + (long long)HDR_WORDS * t;
+  const int seg = (int)h[H_SEG], ncol = (int)h[H_NCOL];
+  const long long co = h[H_COL_OFF];
+  const int nt = L.seg_ntiles[seg], k = t - L.seg_tile0[seg], col0 = L.seg_col0[seg];
+  const long long off = seg_xref_off[seg];
+  for (int c = threadIdx.x; c < ncol; c += blockDim.x)
+    xref[off + (long long)(L.c_scol[co + c] - col0) * nt + k] = (uint16_t)c;
 }
 
 template <class T>
@@ -127,6 +143,32 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
   h->rows_amb = 0;
   for (int c = 0; c < SS_NUM_CLASSES; ++c) h->cls_smem[c] = 0;
   h->stream_smem = 0;
+  // segments of 2..8 tiles whose tiles (plus the owner arrays) fit shared memory run as clusters
+  const int MAXC = ss_handle_s::MAX_CLUSTER;
+  std::vector<char> seg_clustered((size_t)std::max(L.S, 1), 0);
+  std::vector<int> clu[ss_handle_s::MAX_CLUSTER + 1];
+  std::vector<long long> xoff((size_t)std::max(L.S, 1), -1);
+  long long xref_total = 0;
+  for (int k = 0; k <= MAXC; ++k) h->clu_smem[k] = 0;
+  for (int sgm = 0; sgm < L.S; ++sgm) {
+    const int nt = h->seg_ntiles_host[sgm];
+    if (nt < 2 || nt > MAXC) continue;
+    const size_t no_pad = (size_t)pad8((seg_ncol[sgm] + nt - 1) / nt + 1);
+    const size_t owner_bytes = 8 * 4 * no_pad + 2 * no_pad * nt;
+    size_t need = 0;
+    for (int k = 0; k < nt; ++k) {
+      const long long* hd = &h->hdr_host[(size_t)(h->seg_tile0_host[sgm] + k) * HDR_WORDS];
+      need = std::max(need, tile_smem_bytes((int)hd[H_NENT], (int)hd[H_NROWS], (int)hd[H_NCOL], (int)hd[H_MAXLEN]) +
+                                owner_bytes);
+    }
+    if (need + 2048 > h->max_smem_optin) continue;
+    seg_clustered[sgm] = 1;
+    clu[nt].push_back(sgm);
+    h->clu_smem[nt] = std::max(h->clu_smem[nt], need);
+    xoff[sgm] = xref_total;
+    xref_total += (long long)seg_ncol[sgm] * nt;
+  }
+  std::vector<int> cluster_tiles;
   for (int t = 0; t < T; ++t) {
     const long long* hd = &h->hdr_host[(size_t)t * HDR_WORDS];
     const int seg = (int)hd[H_SEG], nrows = (int)hd[H_NROWS], nent = (int)hd[H_NENT], ncol = (int)hd[H_NCOL],
@@ -145,6 +187,8 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
       cls[c].push_back(t);
       // the largest class runs the fragment kernel (tile data in registers, less shared memory)
       h->cls_smem[c] = std::max(h->cls_smem[c], c == SS_NUM_CLASSES - 1 ? frag_smem_bytes_host(nent, ncol) : b0);
+    } else if (seg_clustered[seg]) {
+      cluster_tiles.push_back(t);
     } else {
       stream.push_back(t);
       h->stream_smem = std::max(h->stream_smem, b0);
@@ -167,7 +211,7 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
   // multi-tile segments and their columns
   std::vector<int> segs, col_seg, col_slot;
   for (int s = 0; s < L.S; ++s) {
-    if (h->seg_ntiles_host[s] > 1) {
+    if (h->seg_ntiles_host[s] > 1 && !seg_clustered[s]) {
       const int si = (int)segs.size();
       segs.push_back(s);
       for (int j = 0; j < seg_ncol[s]; ++j) {
@@ -181,6 +225,31 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
   SS_CUDA_CHECK(h, upload(pool, &h->stream_segs, (const int*)segs.data(), segs.size(), st));
   SS_CUDA_CHECK(h, upload(pool, &h->stream_col_seg, (const int*)col_seg.data(), col_seg.size(), st));
   SS_CUDA_CHECK(h, upload(pool, &h->stream_col_slot, (const int*)col_slot.data(), col_slot.size(), st));
+  // cluster segments
+  h->n_cluster_tiles = (int)cluster_tiles.size();
+  h->n_cluster_segs = 0;
+  for (int k = 2; k <= MAXC; ++k) {
+    // big segments first
+    std::sort(clu[k].begin(), clu[k].end(), [&](int a, int b) {
+      const long long ea = h->hdr_host[(size_t)(h->seg_tile0_host[a] + k - 1) * HDR_WORDS + H_NENT];
+      const long long eb = h->hdr_host[(size_t)(h->seg_tile0_host[b] + k - 1) * HDR_WORDS + H_NENT];
+      return ea != eb ? ea > eb : a < b;
+    });
+    h->clu_count[k] = (int)clu[k].size();
+    h->n_cluster_segs += h->clu_count[k];
+    SS_CUDA_CHECK(h, upload(pool, &h->clu_segs[k], (const int*)clu[k].data(), clu[k].size(), st));
+  }
+  SS_CUDA_CHECK(h, upload(pool, &h->seg_xref_off, (const long long*)xoff.data(), xoff.size(), st));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &h->clu_xref, (size_t)std::max<long long>(xref_total, 1)));
+  if (xref_total > 0) {
+    int* d_ct;
+    SS_CUDA_CHECK(h, upload(pool, &d_ct, (const int*)cluster_tiles.data(), cluster_tiles.size(), st));
+    SS_CUDA_CHECK(h, cudaMemsetAsync(h->clu_xref, 0xff, (size_t)xref_total * sizeof(uint16_t), st));
+    cluster_xref_kernel<<<(unsigned)cluster_tiles.size(), 128, 0, st>>>(d_ct, (int)cluster_tiles.size(), L,
+                                                                         h->seg_xref_off, h->clu_xref);
+    h->launches++;
+    SS_CUDA_CHECK(h, cudaGetLastError());
+  }
   SS_CUDA_CHECK(h, cudaStreamSynchronize(st));  // host vectors go out of scope
   return SS_OK;
 }

@@ -93,12 +93,13 @@ class Engine:
     def last_timings(self):
         """Device time (ms) of the kernel groups of the last ss_em_fit (synchronises):
         prepare, streaming kernel, resident kernels, emit, finalize."""
-        buf = (C.c_double * 16)()
-        self._check(self.lib.ss_get_timings(self.h, buf, 16))
+        buf = (C.c_double * 24)()
+        self._check(self.lib.ss_get_timings(self.h, buf, 24))
         out = {'prepare': buf[0], 'em': buf[1], 'emit': buf[3], 'finalize': buf[4], 'stream': buf[11]}
         for i, t in enumerate((32, 64, 128, 256, 512, 1024)):
             out[f'resident{t}'] = buf[5 + i]
         out['resident'] = max(buf[5:11])
+        out['cluster'] = max(buf[12:19])
         return {k: float(v) for k, v in out.items()}
 
     # -- layout --------------------------------------------------------------

@@ -33,8 +33,8 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 
 def test_struct_layouts_match_header():
-    # ss_layout_info: 10 int32 + 8 int64; ss_host_layout: 7 int32 (+pad) + 6 int64 + 33 pointers
-    assert ctypes.sizeof(_lib.LayoutInfo) == 10 * 4 + 8 * 8
+    # ss_layout_info: 12 int32 + 8 int64; ss_host_layout: 7 int32 (+pad) + 6 int64 + 33 pointers
+    assert ctypes.sizeof(_lib.LayoutInfo) == 12 * 4 + 8 * 8
     assert ctypes.sizeof(_lib.HostLayoutC) == 8 * 4 + 6 * 8 + 33 * 8
 
 

@@ -62,6 +62,43 @@ def test_pseudobulk_streaming(use_import):
     assert res['iters'][0] > 1
 
 
+def test_pseudobulk_many_tiles_streaming_kernel():
+    # > 8 tiles: the cooperative streaming kernel (segments of 2..8 tiles run as clusters)
+    d = H.small_synth(seed=30, n_alignments=48000, n_loci=1500)
+    from stellarscope_b200.engine import Engine
+    _fit_and_compare(d, np.zeros(d.N, dtype=np.int32), [np.arange(d.N)], Opts())
+
+
+def test_cluster_segments_of_every_size():
+    # cells of 2..8 tiles next to single-tile cells
+    sizes = [3000, 6000, 9000, 13000, 17000, 21000, 25000, 29000, 500, 800]
+    parts = [H.small_synth(seed=40 + i, n_cells=1, n_alignments=a, n_loci=900, unique_frac=0.05) for i, a in enumerate(sizes)]
+    indptr = [np.zeros(1, dtype=np.int64)]
+    idx, sc, cell = [], [], []
+    off = 0
+    for c, p in enumerate(parts):
+        indptr.append(p.indptr[1:].astype(np.int64) + off)
+        off += p.A
+        idx.append(p.indices)
+        sc.append(p.scores)
+        cell.append(np.full(p.N, c, dtype=np.int32))
+    import types
+    d = types.SimpleNamespace(indptr=np.concatenate(indptr).astype(np.int32), indices=np.concatenate(idx),
+                              scores=np.concatenate(sc), K=parts[0].K, row_cell=np.concatenate(cell),
+                              n_cells=len(parts))
+    d.N = len(d.indptr) - 1
+    rows = [np.flatnonzero(d.row_cell == c) for c in range(d.n_cells)]
+    from stellarscope_b200.engine import Engine
+    eng = Engine()
+    eng.set_matrix(d.indptr, d.indices, d.scores, d.K)
+    eng.build_layout(d.row_cell, d.n_cells)
+    info = eng.layout_info()
+    assert info['n_cluster_segments'] >= 6 and info['n_cluster_tiles'] >= 20
+    eng.close()
+    _fit_and_compare(d, d.row_cell, rows, Opts())
+    _fit_and_compare(d, d.row_cell, rows, Opts(use_likelihood=True, max_iter=40))
+
+
 def test_celltype_mixed_sizes():
     d = H.small_synth(seed=23, n_cells=40, n_alignments=40000, n_celltypes=5, n_loci=800)
     _fit_and_compare(d, d.cell_type[d.row_cell].astype(np.int32), d.celltype_rows(), Opts())
