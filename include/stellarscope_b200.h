@@ -36,7 +36,10 @@ enum ss_status {
   SS_ERR_CUDA = 2,     /* CUDA runtime failure */
   SS_ERR_STATE = 3,    /* call order (no layout / no fit yet) */
   SS_ERR_MODEL = 4,    /* StellarscopeError class: empty model, zero denominator (model.py:267-272) */
-  SS_ERR_CAPACITY = 5  /* a read has more alignments than a tile can hold */
+  SS_ERR_CAPACITY = 5, /* a read has more alignments than a tile can hold */
+  SS_ERR_NOT_CANONICAL = 6 /* ss_layout_build: zero scores / unsorted or duplicate column indices; the
+                              reference canonicalises on construction (csr_matrix + eliminate_zeros,
+                              model.py:113-114) -- the caller does that on the host and retries */
 };
 
 /* reassignment modes, order of TelescopeLikelihood.REASSIGN_MODES (model.py:92-100) */
@@ -92,6 +95,7 @@ const char* ss_last_error(ss_handle_t h);
  *       the N x K uint16 CSR score matrix (st.corrected / st.raw_scores, model.py:749-758)
  *   row_segment[n_rows]: model index of each row (cell, celltype, 0 for
  *       pseudobulk), -1 = row belongs to no model.
+ * The matrix must be canonical (checked on the device in the same pass: SS_ERR_NOT_CANONICAL).
  * Synchronises the stream (sizes of the layout are data dependent). */
 int ss_layout_build(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, int64_t nnz,
                     const int32_t* row_ptr, const int32_t* col_idx, const uint16_t* score,

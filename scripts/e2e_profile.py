@@ -15,7 +15,6 @@ def T(label, fn, n=3):
         torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
     print(f'{label:28s} {1e3*min(ts):8.2f} ms'); return r
 T('pooling_row_segments', lambda: model.pooling_row_segments(st, opts))
-T('canonical_csr', lambda: model._canonical_csr(st.raw_scores))
 seg, keys = model.pooling_row_segments(st, opts)
 eng = Engine(0)
 T('set_matrix (pin+H2D)', lambda: eng.set_matrix(d.indptr, d.indices, d.scores, d.K))

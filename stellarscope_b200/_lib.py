@@ -12,7 +12,7 @@ from . import build as _build
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-SS_OK, SS_ERR_ARG, SS_ERR_CUDA, SS_ERR_STATE, SS_ERR_MODEL, SS_ERR_CAPACITY = range(6)
+SS_OK, SS_ERR_ARG, SS_ERR_CUDA, SS_ERR_STATE, SS_ERR_MODEL, SS_ERR_CAPACITY, SS_ERR_NOT_CANONICAL = range(7)
 ABI_VERSION = 1
 
 MODES = {  # order of TelescopeLikelihood.REASSIGN_MODES (reference model.py:92-100)

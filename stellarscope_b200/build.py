@@ -12,6 +12,8 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libstellarscope_b200.so')
 SOURCES = ['ss_api.cu', 'ss_layout.cu', 'ss_build.cu', 'ss_em.cu', 'ss_reassign.cu']
 HEADERS = ['ss_common.cuh', 'ss_em.cuh', 'ss_handle.h', os.path.join('..', '..', 'include', 'stellarscope_b200.h')]
+HOSTUTIL_SRC = os.path.join(CSRC, 'ss_hostutil.c')
+HOSTUTIL = os.path.join(HERE, '_ss_hostutil.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 
@@ -54,5 +56,22 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def hostutil_needs_build():
+    return (not os.path.exists(HOSTUTIL)) or os.path.getmtime(HOSTUTIL_SRC) > os.path.getmtime(HOSTUTIL)
+
+
+def build_hostutil(force=False):
+    """CPython helper of the Python boundary (plain C, gcc): row -> model map from the
+    reference's dict of row sets."""
+    if not force and not hostutil_needs_build():
+        return HOSTUTIL
+    import sysconfig
+    inc = sysconfig.get_paths()['include']
+    cmd = [os.environ.get('CC', 'gcc'), '-O2', '-fPIC', '-shared', '-I', inc, HOSTUTIL_SRC, '-o', HOSTUTIL]
+    subprocess.check_call(cmd)
+    return HOSTUTIL
+
+
 if __name__ == '__main__':
+    print(build_hostutil(force='--force' in sys.argv))
     print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -50,6 +50,7 @@ int ss_create(int device, ss_handle_t* out) {
 int ss_destroy(ss_handle_t h) {
   SS_REQUIRE_HANDLE(h);
   cudaSetDevice(h->device);
+  tl_alloc_stream = nullptr;
   free_fit(h);
   free_layout(h);
   for (int i = 0; i < 6; ++i)
@@ -82,6 +83,7 @@ int ss_layout_build(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols,
     return SS_ERR_ARG;
   }
   cudaSetDevice(h->device);
+  tl_alloc_stream = (cudaStream_t)stream;
   return layout_build(h, (cudaStream_t)stream, n_rows, n_cols, nnz, row_ptr, col_idx, score, row_segment,
                       n_segments);
 }
@@ -93,6 +95,7 @@ int ss_layout_import(ss_handle_t h, void* stream, const ss_host_layout* L) {
     return SS_ERR_ARG;
   }
   cudaSetDevice(h->device);
+  tl_alloc_stream = (cudaStream_t)stream;
   return layout_import(h, (cudaStream_t)stream, L);
 }
 
@@ -177,6 +180,7 @@ int ss_em_fit(ss_handle_t h, void* stream, double em_epsilon, int32_t max_iter, 
               int32_t use_likelihood) {
   SS_REQUIRE_HANDLE(h);
   cudaSetDevice(h->device);
+  tl_alloc_stream = (cudaStream_t)stream;
   FitParams P;
   P.eps = em_epsilon;
   P.max_iter = max_iter;

@@ -50,8 +50,10 @@ struct TmpPool {
   } while (0)
 
 // ---- step 1: classify rows, per-segment integer statistics --------------------
-// counters: [0] = max row length among ambiguous rows
-__global__ void row_class_kernel(int n_rows, const int* __restrict__ row_ptr, const uint16_t* __restrict__ score,
+// counters: [0] = max row length among ambiguous rows, [1] = 1 when the matrix is not canonical
+// (a zero score, column indices not strictly ascending inside a row, or outside [0, K))
+__global__ void row_class_kernel(int n_rows, int n_cols, const int* __restrict__ row_ptr,
+                                 const int* __restrict__ col_idx, const uint16_t* __restrict__ score,
                                  const int* __restrict__ row_seg, int n_seg, uint8_t* __restrict__ is_amb,
                                  uint8_t* __restrict__ is_uni, int* __restrict__ seg_smax, int* __restrict__ seg_nobs,
                                  int* __restrict__ seg_namb, int* __restrict__ seg_nuniq,
@@ -64,8 +66,15 @@ __global__ void row_class_kernel(int n_rows, const int* __restrict__ row_ptr, co
     if (seg >= n_seg) seg = -1;
     const int b = row_ptr[row], e = row_ptr[row + 1];
     len = e - b;
-    if (seg >= 0)
-      for (int k = b; k < e; ++k) rmax = max(rmax, (int)score[k]);
+    bool bad = len < 0;
+    int prev = -1;
+    for (int k = b; k < e; ++k) {
+      const int sc = (int)score[k], c = col_idx[k];
+      rmax = max(rmax, sc);
+      bad |= sc == 0 || c <= prev || c >= n_cols;
+      prev = c;
+    }
+    if (bad) counters[1] = 1;
     is_amb[row] = seg >= 0 && len > 1;
     is_uni[row] = seg >= 0 && len == 1;
   }
@@ -221,7 +230,6 @@ __device__ int block_excl_scan(int* data, int n, int* scratch) {
 }
 
 constexpr int BUILD_THREADS = 256;
-constexpr int R_CAP = E_HARD / 2;
 
 struct TileBuildArgs {
   const int* row_ptr;
@@ -253,23 +261,36 @@ struct TileBuildArgs {
 };
 
 // ---- step 5: one CTA per tile ---------------------------------------------------
+// Instantiated for three tile-size classes (ECAP = 256 / 1024 / E_HARD alignments) so that the
+// many small tiles of individual-mode cells do not pay for the shared memory of the largest
+// one; every instance is launched over all tiles and a CTA returns when the tile is not of its
+// class (ELOW < nent <= ECAP).
+template <int ECAP>
+constexpr size_t tile_build_smem() {
+  return (size_t)ECAP * 8 * 2 + (size_t)(ECAP * 4 + 2) * 4 + (size_t)(ECAP / 2 * 2 + ECAP + 2) * 4 +
+         (size_t)(BUILD_THREADS + 1) * 4 + 64;
+}
+
+template <int ECAP, int ELOW>
 __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs a) {
   extern __shared__ __align__(16) unsigned char dsm[];
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(dsm);   // E_HARD
-  unsigned long long* ckeys = keys + E_HARD;                                // E_HARD
-  int* colidx = reinterpret_cast<int*>(ckeys + E_HARD);                     // E_HARD: column (gcol order) of each sorted entry
-  int* colstart = colidx + E_HARD;                                          // E_HARD + 1
-  int* rank_of = colstart + E_HARD + 1;                                     // E_HARD
-  int* cptr = rank_of + E_HARD;                                             // E_HARD + 1
-  int* rrow = cptr + E_HARD + 1;                                            // R_CAP  original row of JDS row r
-  int* rlen = rrow + R_CAP;                                                 // R_CAP
-  int* jptr = rlen + R_CAP;                                                 // R_CAP + 2 (maxlen <= E_HARD/2)
-  int* scratch = jptr + R_CAP + 2;                                          // BUILD_THREADS + 1
-  __shared__ double s_red[32];
+  constexpr int RCAP = ECAP / 2;
   const int tid = threadIdx.x;
   const int t = blockIdx.x;
   const int row0 = a.tile_row0[t], nrows = a.tile_row0[t + 1] - row0;
   const int nent = (int)(a.pre[row0 + nrows] - a.pre[row0]);
+  if (nent <= ELOW || nent > ECAP) return;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(dsm);   // ECAP
+  unsigned long long* ckeys = keys + ECAP;                                  // ECAP
+  int* colidx = reinterpret_cast<int*>(ckeys + ECAP);                       // ECAP: column (gcol order) of each sorted entry
+  int* colstart = colidx + ECAP;                                            // ECAP + 1
+  int* rank_of = colstart + ECAP + 1;                                       // ECAP
+  int* cptr = rank_of + ECAP;                                               // ECAP + 1
+  int* rrow = cptr + ECAP + 1;                                              // RCAP  original row of JDS row r
+  int* rlen = rrow + RCAP;                                                  // RCAP
+  int* jptr = rlen + RCAP;                                                  // ECAP + 2 (a row may be as long as the tile)
+  int* scratch = jptr + ECAP + 2;                                           // BUILD_THREADS + 1
+  __shared__ double s_red[32];
   const int seg = a.aseg[row0];
   const long long eo = a.ent_off[t], ro = a.row_off[t];
 
@@ -603,11 +624,6 @@ __global__ void widen_int_kernel(int n, const int* __restrict__ in, long long* _
   if (i < n) out[i] = in[i];
 }
 
-static size_t tile_build_smem() {
-  return (size_t)E_HARD * 8 * 2 + (size_t)(E_HARD * 4 + 2) * 4 + (size_t)(R_CAP * 3 + 2) * 4 +
-         (size_t)(BUILD_THREADS + 1) * 4 + 64;
-}
-
 inline unsigned grid_for(long long n, int b = 256) { return (unsigned)std::max<long long>(1, (n + b - 1) / b); }
 
 }  // namespace
@@ -646,7 +662,7 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
   SS_CUDA_CHECK(h, cudaMemsetAsync(L.seg_A, 0, Sz * 8, st));
   SS_CUDA_CHECK(h, cudaMemsetAsync(L.seg_Aamb, 0, Sz * 8, st));
   if (N > 0) {
-    row_class_kernel<<<grid_for(N), 256, 0, st>>>(N, row_ptr, score, row_segment, S, is_amb, is_uni, L.seg_smax,
+    row_class_kernel<<<grid_for(N), 256, 0, st>>>(N, n_cols, row_ptr, col_idx, score, row_segment, S, is_amb, is_uni, L.seg_smax,
                                                   L.seg_nobs, L.seg_namb, L.seg_nuniq, segA_u, segAamb_u, counters);
     h->launches++;
   }
@@ -665,10 +681,17 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
     CUB_CALL(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, iota, is_uni, u_row_tmp, d_nsel + 1, N, st));
     int hsel[2];
     SS_CUDA_CHECK(h, cudaMemcpyAsync(hsel, d_nsel, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    SS_CUDA_CHECK(h, cudaMemcpyAsync(&maxlen, counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int hcnt[2] = {0, 0};
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(hcnt, counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     SS_CUDA_CHECK(h, cudaStreamSynchronize(st));
     n_amb = hsel[0];
     n_uniq = hsel[1];
+    maxlen = hcnt[0];
+    if (hcnt[1]) {
+      h->set_error("score matrix is not canonical CSR (needs non-zero scores and strictly ascending column "
+                   "indices in [0, K) inside every row)");
+      return SS_ERR_NOT_CANONICAL;
+    }
   }
   if (maxlen > E_HARD / 2) {
     h->set_error("a read has " + std::to_string(maxlen) + " alignments; the tile capacity is " +
@@ -797,11 +820,19 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
     a.tmp_cptr = tmp_cptr; a.tmp_gcol = tmp_gcol; a.tmp_jptr = tmp_jptr; a.jds_stride = jds_stride;
     a.t_ncol = t_ncol; a.t_maxlen = t_maxlen; a.t_nlong = t_nlong; a.t_seg = t_seg; a.t_nrows = t_nrows;
     a.t_nent = t_nent; a.t_wsum = t_wsum; a.t_rfrag = t_rfrag; a.t_cfrag = t_cfrag;
-    const size_t smem = tile_build_smem();
-    SS_CUDA_CHECK(h, cudaFuncSetAttribute(tile_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tile_build_kernel<<<n_tiles, BUILD_THREADS, smem, st>>>(a);
-    h->launches++;
-    SS_CUDA_CHECK(h, cudaGetLastError());
+#define SS_TILE_BUILD(ECAP, ELOW)                                                                         \
+  do {                                                                                                    \
+    constexpr size_t smem = tile_build_smem<ECAP>();                                                      \
+    SS_CUDA_CHECK(h, cudaFuncSetAttribute(tile_build_kernel<ECAP, ELOW>,                                  \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    tile_build_kernel<ECAP, ELOW><<<n_tiles, BUILD_THREADS, smem, st>>>(a);                               \
+    h->launches++;                                                                                        \
+    SS_CUDA_CHECK(h, cudaGetLastError());                                                                 \
+  } while (0)
+    SS_TILE_BUILD(E_HARD, 1024);      // largest tiles first: they take longest
+    SS_TILE_BUILD(1024, 256);
+    SS_TILE_BUILD(256, 0);
+#undef SS_TILE_BUILD
     SS_CUDA_CHECK(h, cudaMemsetAsync(pad_col + n_tiles, 0, 8, st));
     SS_CUDA_CHECK(h, cudaMemsetAsync(pad_jds + n_tiles, 0, 8, st));
     SS_CUDA_CHECK(h, cudaMemsetAsync(key_cnt + n_tiles, 0, 8, st));

@@ -1080,8 +1080,7 @@ __global__ void fit_finalize_kernel(Layout L, FitState F, FitParams P) {
 // host side
 // ---------------------------------------------------------------------------
 void free_fit(ss_handle_s* h) {
-  for (void* p : h->fit_allocs) cudaFree(p);
-  h->fit_allocs.clear();
+  dev_free_all(h->fit_allocs);
   h->F = FitState();
   h->stream_ctl = nullptr;
   h->has_fit = false;

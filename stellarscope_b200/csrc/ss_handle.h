@@ -93,12 +93,24 @@ int count(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, const int* ro
           const uint8_t* flag, const double* weight, const int* row_cell, const int* row_umi, long long cap,
           int* out_cell, int* out_col, double* out_val, long long* n_out);
 
+// Device memory of a handle comes from the device's stream-ordered pool (cudaMallocAsync; the
+// pool keeps its memory, ss_create): a layout build makes ~50 allocations and cudaMalloc would
+// cost more than the kernels.  Entry points set the stream the allocations are ordered on.
+extern thread_local cudaStream_t tl_alloc_stream;
 template <class T>
 inline cudaError_t dev_alloc(std::vector<void*>& pool, T** p, size_t n) {
   *p = nullptr;
   if (n == 0) n = 1;
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(p), n * sizeof(T), tl_alloc_stream);
   if (e == cudaSuccess) pool.push_back(*p);
   return e;
+}
+// free everything in `pool`; the device is synchronised first (kernels of internal streams may
+// still use the memory)
+inline void dev_free_all(std::vector<void*>& pool) {
+  if (pool.empty()) return;
+  cudaDeviceSynchronize();
+  for (void* p : pool) cudaFreeAsync(p, tl_alloc_stream);
+  pool.clear();
 }
 }  // namespace ss

@@ -1,0 +1,219 @@
+/* Host-side helper of the Python boundary (CPython C API, plain C).
+ *
+ * The reference hands the pooling driver its rows as Python containers:
+ * ``st.bcode_ridx_map`` = dict barcode -> set of row ids (model.py:875, 1053) and
+ * builds one N x 1 selector per model from them (row_identity_matrix,
+ * sparse_plus.py:408-441; model.py:722-723, 742-743).  The device layout wants
+ * the inverse map, row -> model id, as one int32 array.  Walking a million
+ * Python ints through the iterator protocol costs more than the whole fit on
+ * the GPU, so this module walks the sets' hash tables directly.
+ *
+ *   fill_row_segments(groups, ids, seg) -> number of rows assigned
+ *     groups  sequence of sets (any iterable of ints is accepted)
+ *     ids     int32 buffer, ids[i] = model id of groups[i]
+ *     seg     writable int32 buffer [N], pre-filled with -1
+ *   Raises ValueError when a row is claimed by two different models, IndexError
+ *   when a row id is outside [0, N).
+ */
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <time.h>
+#include <unistd.h>
+
+/* ---- threaded fast path ---------------------------------------------------------
+ * Exact sets of exact, compact (single-digit) ints -- what the reference's loader
+ * produces -- are walked by a few worker threads while the calling thread keeps the
+ * GIL: the workers only READ the set tables and the int objects (no reference
+ * counts, no allocation, no exceptions).  Anything else makes a worker bail out and
+ * the serial, fully checked path below redoes the job.  Rows are claimed with a
+ * compare-and-swap so that a row claimed by two models is detected whatever the
+ * interleaving. */
+typedef struct {
+  PyObject** items;
+  const int32_t* ids;
+  Py_ssize_t g0, g1, n;
+  int32_t* seg;
+  Py_ssize_t count;
+  int status; /* 0 ok, 1 unsupported object -> serial path, 2 conflict / range -> serial path reports it */
+} worker_t;
+
+static void* worker_main(void* arg) {
+  worker_t* w = (worker_t*)arg;
+  Py_ssize_t count = 0;
+  for (Py_ssize_t g = w->g0; g < w->g1; ++g) {
+    PyObject* s = w->items[g];
+    const int32_t id = w->ids[g];
+    Py_ssize_t pos = 0;
+    PyObject* key;
+    Py_hash_t hash;
+    while (_PySet_NextEntry(s, &pos, &key, &hash)) {
+      if (!PyLong_CheckExact(key) || !PyUnstable_Long_IsCompact((PyLongObject*)key)) {
+        w->status = 1;
+        return NULL;
+      }
+      const Py_ssize_t row = PyUnstable_Long_CompactValue((PyLongObject*)key);
+      if (row < 0 || row >= w->n) {
+        w->status = 2;
+        return NULL;
+      }
+      int32_t expect = -1;
+      if (__atomic_compare_exchange_n(&w->seg[row], &expect, id, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+        ++count;
+      } else if (expect != id) {
+        w->status = 2;
+        return NULL;
+      }
+    }
+  }
+  w->count = count;
+  return NULL;
+}
+
+/* returns the number of rows assigned, -1 when the serial path has to take over (seg is then
+ * partially written and must be reset by the caller) */
+static Py_ssize_t fill_threaded(PyObject** items, Py_ssize_t ng, const int32_t* ids, int32_t* seg, Py_ssize_t n) {
+  Py_ssize_t total = 0;
+  for (Py_ssize_t g = 0; g < ng; ++g) {
+    if (!PyAnySet_CheckExact(items[g])) return -1;
+    total += PySet_GET_SIZE(items[g]);
+  }
+  long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+  int nt = (int)(ncpu < 1 ? 1 : (ncpu > 8 ? 8 : ncpu));
+  { const char* e = getenv("SS_HOST_THREADS"); if (e) nt = atoi(e) < 1 ? 1 : (atoi(e) > 8 ? 8 : atoi(e)); }
+  if (total < 200000 || nt < 2) return -1;  /* small inputs: the serial path is as fast */
+  worker_t w[8];
+  pthread_t th[8];
+  Py_ssize_t g = 0, acc = 0;
+  for (int i = 0; i < nt; ++i) {
+    w[i].items = items; w[i].ids = ids; w[i].seg = seg; w[i].n = n; w[i].count = 0; w[i].status = 0;
+    w[i].g0 = g;
+    const Py_ssize_t target = total * (i + 1) / nt;
+    while (g < ng && (acc < target || i == nt - 1)) acc += PySet_GET_SIZE(items[g++]);
+    w[i].g1 = g;
+  }
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  int started = 0;
+  for (int i = 0; i < nt; ++i) {
+    if (pthread_create(&th[i], NULL, worker_main, &w[i]) != 0) break;
+    ++started;
+  }
+  for (int i = 0; i < started; ++i) pthread_join(th[i], NULL);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (getenv("SS_HOST_DEBUG")) fprintf(stderr, "threads: %.3f ms\n", 1e3 * ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec)));
+  if (getenv("SS_HOST_DEBUG")) for (int i = 0; i < nt; ++i) fprintf(stderr, "worker %d: groups %zd..%zd count %zd status %d\n", i, w[i].g0, w[i].g1, w[i].count, w[i].status);
+  if (started < nt) return -1;
+  Py_ssize_t count = 0;
+  for (int i = 0; i < nt; ++i) {
+    if (w[i].status != 0) return -1;
+    count += w[i].count;
+  }
+  return count;
+}
+
+static int assign_row(PyObject* key, int32_t id, int32_t* seg, Py_ssize_t n, Py_ssize_t* count) {
+  Py_ssize_t row = PyLong_AsSsize_t(key);
+  if (row == -1 && PyErr_Occurred()) {
+    PyErr_Clear();
+    /* numpy integer scalars etc. */
+    PyObject* ix = PyNumber_Index(key);
+    if (!ix) return -1;
+    row = PyLong_AsSsize_t(ix);
+    Py_DECREF(ix);
+    if (row == -1 && PyErr_Occurred()) return -1;
+  }
+  if (row < 0 || row >= n) {
+    PyErr_Format(PyExc_IndexError, "row id %zd outside [0, %zd)", row, n);
+    return -1;
+  }
+  if (seg[row] != -1 && seg[row] != id) {
+    PyErr_Format(PyExc_ValueError, "row %zd belongs to more than one model (%d and %d)", row, (int)seg[row], (int)id);
+    return -1;
+  }
+  if (seg[row] == -1) ++*count;
+  seg[row] = id;
+  return 0;
+}
+
+static PyObject* fill_row_segments(PyObject* self, PyObject* args) {
+  PyObject *groups, *ids_obj, *seg_obj;
+  if (!PyArg_ParseTuple(args, "OOO", &groups, &ids_obj, &seg_obj)) return NULL;
+  Py_buffer ids, seg;
+  if (PyObject_GetBuffer(ids_obj, &ids, PyBUF_C_CONTIGUOUS | PyBUF_FORMAT) < 0) return NULL;
+  if (PyObject_GetBuffer(seg_obj, &seg, PyBUF_C_CONTIGUOUS | PyBUF_WRITABLE | PyBUF_FORMAT) < 0) {
+    PyBuffer_Release(&ids);
+    return NULL;
+  }
+  PyObject* fast = NULL;
+  PyObject* result = NULL;
+  if (ids.itemsize != 4 || seg.itemsize != 4) {
+    PyErr_SetString(PyExc_TypeError, "ids and seg must be int32 buffers");
+    goto done;
+  }
+  fast = PySequence_Fast(groups, "groups must be a sequence");
+  if (!fast) goto done;
+  {
+    const Py_ssize_t ng = PySequence_Fast_GET_SIZE(fast);
+    const Py_ssize_t n = seg.len / 4;
+    int32_t* segp = (int32_t*)seg.buf;
+    const int32_t* idp = (const int32_t*)ids.buf;
+    Py_ssize_t count = 0;
+    if (ids.len / 4 < ng) {
+      PyErr_SetString(PyExc_ValueError, "ids is shorter than groups");
+      goto done;
+    }
+    {
+      const Py_ssize_t c = fill_threaded(PySequence_Fast_ITEMS(fast), ng, idp, segp, n);
+      if (c >= 0) {
+        result = PyLong_FromSsize_t(c);
+        goto done;
+      }
+      /* serial path: start again from a clean map (seg was pre-filled with -1 by contract) */
+      for (Py_ssize_t i = 0; i < n; ++i) segp[i] = -1;
+    }
+    for (Py_ssize_t g = 0; g < ng; ++g) {
+      PyObject* s = PySequence_Fast_GET_ITEM(fast, g);
+      const int32_t id = idp[g];
+      if (PyAnySet_Check(s)) {
+        Py_ssize_t pos = 0;
+        PyObject* key;
+        Py_hash_t hash;
+        while (_PySet_NextEntry(s, &pos, &key, &hash)) {
+          if (assign_row(key, id, segp, n, &count) < 0) goto done;
+        }
+      } else {
+        PyObject* it = PyObject_GetIter(s);
+        if (!it) goto done;
+        PyObject* key;
+        while ((key = PyIter_Next(it))) {
+          const int rc = assign_row(key, id, segp, n, &count);
+          Py_DECREF(key);
+          if (rc < 0) {
+            Py_DECREF(it);
+            goto done;
+          }
+        }
+        Py_DECREF(it);
+        if (PyErr_Occurred()) goto done;
+      }
+    }
+    result = PyLong_FromSsize_t(count);
+  }
+done:
+  Py_XDECREF(fast);
+  PyBuffer_Release(&ids);
+  PyBuffer_Release(&seg);
+  return result;
+}
+
+static PyMethodDef methods[] = {
+    {"fill_row_segments", fill_row_segments, METH_VARARGS,
+     "fill_row_segments(groups, ids, seg): seg[row] = ids[i] for every row of groups[i]"},
+    {NULL, NULL, 0, NULL}};
+
+static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_ss_hostutil", "host helpers of stellarscope_b200", -1, methods};
+
+PyMODINIT_FUNC PyInit__ss_hostutil(void) { return PyModule_Create(&moddef); }

@@ -9,13 +9,14 @@
 
 namespace ss {
 
+thread_local cudaStream_t tl_alloc_stream = nullptr;
+
 static size_t frag_smem_bytes_host(int nent, int ncol) {
   return 8 * ((size_t)pad8(nent) + 3 * (size_t)pad8(ncol + 1));
 }
 
 void free_layout(ss_handle_s* h) {
-  for (void* p : h->layout_allocs) cudaFree(p);
-  h->layout_allocs.clear();
+  dev_free_all(h->layout_allocs);
   h->L = Layout();
   h->hdr_host.clear();
   h->seg_ntiles_host.clear();
@@ -84,7 +85,7 @@ int layout_import(ss_handle_s* h, cudaStream_t st, const ss_host_layout* HL) {
       h->launches++;
     }
     SS_CUDA_CHECK(h, cudaStreamSynchronize(st));
-    for (void* q : tmp) cudaFree(q);
+    for (void* q : tmp) cudaFreeAsync(q, st);
   }
   SS_CUDA_CHECK(h, upload(pool, &L.e_opos, HL->e_opos, (size_t)L.tot_ent, st));
   SS_CUDA_CHECK(h, upload(pool, &L.r_len, HL->r_len, (size_t)L.tot_row, st));

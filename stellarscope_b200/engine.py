@@ -23,6 +23,12 @@ class EngineError(RuntimeError):
         self.status = status
 
 
+class NotCanonicalError(EngineError):
+    """SS_ERR_NOT_CANONICAL -- ss_layout_build found zero scores or unsorted / duplicate column
+    indices; the caller canonicalises the matrix on the host (what the reference does on
+    construction, model.py:113-114) and builds again."""
+
+
 class ModelError(EngineError):
     """SS_ERR_MODEL -- the class of failures the reference raises as
     ``StellarscopeError`` (model.py:267-272, 454-457)."""
@@ -71,7 +77,8 @@ class Engine:
     def _check(self, rc):
         if rc != 0:
             msg = self.lib.ss_last_error(self.h).decode()
-            raise (ModelError if rc == _lib.SS_ERR_MODEL else EngineError)(rc, msg)
+            cls = {_lib.SS_ERR_MODEL: ModelError, _lib.SS_ERR_NOT_CANONICAL: NotCanonicalError}.get(rc, EngineError)
+            raise cls(rc, msg)
 
     def _to_dev(self, arr, dtype, pinned=True):
         a = _np(arr, dtype)

@@ -1,0 +1,29 @@
+"""Loader of the CPython host helper ``_ss_hostutil`` (csrc/ss_hostutil.c).
+
+Built in-tree with gcc on first use; host-side container walking only -- no
+model arithmetic lives here.
+"""
+from __future__ import annotations
+
+import importlib.util
+
+from . import build as _build
+
+_mod = None
+
+
+def load():
+    global _mod
+    if _mod is None:
+        if _build.hostutil_needs_build():
+            _build.build_hostutil()
+        spec = importlib.util.spec_from_file_location('_ss_hostutil', _build.HOSTUTIL)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _mod = mod
+    return _mod
+
+
+def fill_row_segments(groups, ids, seg):
+    """seg[row] = ids[i] for every row of the i-th container of ``groups``."""
+    return load().fill_row_segments(groups, ids, seg)

@@ -19,9 +19,9 @@ from typing import Optional
 import numpy as np
 import scipy.sparse
 
-from .engine import Engine, ModelError
+from .engine import Engine, ModelError, NotCanonicalError
 from .sparse_plus import csr_matrix_plus
-from .statistics import FitInfo, PoolInfo, ReassignInfo, counter_from_hist
+from .statistics import FitInfo, PoolInfo, ReassignInfo, SegmentFitInfos, counter_from_hist
 
 TIE_TOL_DEFAULT = 1e-9
 
@@ -66,25 +66,35 @@ class TelescopeLikelihood(object):
         self.pi_prior = opts.pi_prior
         self.theta_prior = opts.theta_prior
         self.tie_tol = tie_tol
-        self.raw_scores = (score_matrix if isinstance(score_matrix, csr_matrix_plus) and
-                           getattr(score_matrix, '_ss_canonical', False)
-                           else csr_matrix_plus(_canonical_csr(score_matrix)))
-        self.raw_scores._ss_canonical = True
-        self.N, self.K = self.raw_scores.shape
-        self.max_score = int(self.raw_scores.data.max()) if self.raw_scores.nnz else 0
+        # The reference canonicalises on construction (csr_matrix(...), eliminate_zeros, model.py:113-114).
+        # Checking that on the host costs a pass over the matrix; ss_layout_build checks it on the device
+        # in the pass it makes anyway and the host only canonicalises when that check fails.
+        m = score_matrix if scipy.sparse.isspmatrix_csr(score_matrix) else scipy.sparse.csr_matrix(score_matrix)
+        self.N, self.K = m.shape
         self.scale_factor = 100.
-        if self.raw_scores.nnz and int(self.raw_scores.data.max()) > 65535:
-            raise StellarscopeError('alignment scores above 65535 are not supported (uint16, model.py:964)')
-        if row_segment is None:
-            row_segment = np.zeros(self.N, dtype=np.int32)
-            n_segments = 1
-        self.row_segment = np.ascontiguousarray(row_segment, dtype=np.int32)
-        self.n_segments = int(n_segments)
-
         self._engine = Engine(device)
-        self._engine.set_matrix(self.raw_scores.indptr, self.raw_scores.indices,
-                                self.raw_scores.data.astype(np.uint16, copy=False), self.K)
-        self._engine.build_layout(self.row_segment, self.n_segments)
+        for attempt in (0, 1):
+            self.max_score = int(m.data.max()) if m.nnz else 0
+            if self.max_score > 65535 or (m.nnz and m.data.min() < 0):
+                raise StellarscopeError('alignment scores outside [0, 65535] are not supported (uint16, model.py:964)')
+            self._engine.set_matrix(m.indptr, m.indices, m.data, self.K)        # H2D in flight ...
+            if attempt == 0:
+                if callable(row_segment):                                      # ... while the host walks the row sets
+                    row_segment, self.segment_keys = row_segment()
+                    n_segments = len(self.segment_keys)
+                elif row_segment is None:
+                    row_segment = np.zeros(self.N, dtype=np.int32)
+                    n_segments = 1
+                self.row_segment = np.ascontiguousarray(row_segment, dtype=np.int32)
+                self.n_segments = int(n_segments)
+            try:
+                self._engine.build_layout(self.row_segment, self.n_segments)
+                break
+            except NotCanonicalError:
+                if attempt == 1:
+                    raise
+                m = _canonical_csr(m)
+        self.raw_scores = m if isinstance(m, csr_matrix_plus) else csr_matrix_plus(m)
 
         self._z = None
         self._z_dev = None
@@ -168,16 +178,7 @@ class TelescopeLikelihood(object):
                                      f'model {bad} has no alignments or a zero denominator'))
         tot_it = max(1, int(res['iters'].sum()))
         itime = self.fit_seconds / tot_it
-        iters, flags, lnl = res['iters'].tolist(), res['flags'].tolist(), res['lnl'].tolist()
-        nobs, nfeats, diffs = res['nobs'].tolist(), res['nfeats'].tolist(), res['diffs']
-        infos = []
-        for s in range(self.n_segments):
-            fi = FitInfo(nobs=nobs[s], nfeats=nfeats[s], epsilon=self.epsilon, max_iter=self.max_iter)
-            fi.converged = bool(flags[s] & 1)
-            fi.reached_max = bool(flags[s] & 2)
-            fi.set_trace(iters[s], itime, diffs[s])
-            fi.final_lnl = lnl[s]
-            infos.append(fi)
+        infos = SegmentFitInfos(res, self.epsilon, self.max_iter, itime)
         self.segment_fitinfo = infos
         self._results = res
         self._z = None
@@ -272,43 +273,45 @@ def _em_wrapper(tl: TelescopeLikelihood):
 def pooling_row_segments(st, opts):
     """Row -> model map of a pooling mode (model.py:701-743).  Returns
     ``(row_segment int32[N], keys)`` where ``keys[i]`` is the key of model i in
-    ``PoolInfo.models_info`` (model.py:766, 791)."""
+    ``PoolInfo.models_info`` (model.py:766, 791).  The reference's containers
+    (``bcode_ridx_map``: barcode -> set of row ids) are walked by the C helper
+    ``csrc/ss_hostutil.c``."""
+    from . import hostutil
     N = st.shape[0]
     if opts.pooling_mode == 'pseudobulk':
         return np.zeros(N, dtype=np.int32), ['pseudobulk']
     seg = np.full(N, -1, dtype=np.int32)
+    groups, ids = [], []
     i = 0
     if opts.pooling_mode == 'individual':
-        import itertools
-        sets = []
         for _bcode, rowset in st.bcode_ridx_map.items():
             if not rowset:
                 lg.info(f'        ...not fitting "{_bcode}" -> no reads found')
                 continue
-            sets.append(rowset)
-        lens = np.fromiter((len(x) for x in sets), dtype=np.int64, count=len(sets))
-        rows = np.fromiter(itertools.chain.from_iterable(sets), dtype=np.int64, count=int(lens.sum()))
-        ids = np.repeat(np.arange(len(sets), dtype=np.int32), lens)
-        if len(rows) and np.bincount(rows, minlength=N).max() > 1:
-            raise StellarscopeError('a read belongs to more than one barcode')
-        seg[rows] = ids
-        i = len(sets)
+            groups.append(rowset)
+        i = len(groups)
+        ids = np.arange(i, dtype=np.int32)
+        what = 'a read belongs to more than one barcode'
     elif opts.pooling_mode == 'celltype':
         for _ctype in st.celltypes:
-            rows = []
+            n0 = len(groups)
             for _bcode in st.ctype_bcode_map[_ctype]:
-                if _bcode in st.bcode_ridx_map:
-                    rows.extend(st.bcode_ridx_map[_bcode])
-            if not rows:
+                rowset = st.bcode_ridx_map.get(_bcode)
+                if rowset:
+                    groups.append(rowset)
+            if len(groups) == n0:
                 lg.info(f'        ...not fitting "{_ctype}" -> no reads found')
                 continue
-            rows = np.unique(np.asarray(rows, dtype=np.int64))
-            if (seg[rows] >= 0).any():
-                raise StellarscopeError('a barcode belongs to more than one celltype (not supported)')
-            seg[rows] = i
+            ids.extend([i] * (len(groups) - n0))
             i += 1
+        ids = np.asarray(ids, dtype=np.int32)
+        what = 'a barcode belongs to more than one celltype (not supported)'
     else:
         raise StellarscopeError(f'unknown pooling mode {opts.pooling_mode}')
+    try:
+        hostutil.fill_row_segments(groups, ids, seg)
+    except ValueError as e:
+        raise StellarscopeError(f'{what}: {e}')
     return seg, list(range(i))
 
 
@@ -329,7 +332,6 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
             raise StellarscopeError("UMI corrected matrix shape mismatch")
         fullmat = st.corrected
 
-    row_segment, keys = pooling_row_segments(st, opts)
     if opts.pooling_mode == 'pseudobulk':
         lg.info('Models to fit: 1')
         ret_model = TelescopeLikelihood(fullmat, opts)
@@ -345,14 +347,17 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
     if not getattr(opts, 'shard_models', True):
         world = 1                    # every rank fits its own, independent data set
     if world == 1:
-        ret_model = TelescopeLikelihood(fullmat, opts, row_segment=row_segment, n_segments=len(keys))
-        infos = ret_model.fit_segments()
+        # the row -> model map is computed while the matrix is on its way to the device
+        ret_model = TelescopeLikelihood(fullmat, opts, row_segment=lambda: pooling_row_segments(st, opts))
+        keys = ret_model.segment_keys
+        infos = ret_model.fit_segments().keyed(keys)
     else:
         # models are independent: shard them over the ranks (one process per GPU), no collective on
         # the data path; every rank keeps the global row numbering, rows of other ranks' models are
         # simply not fitted here
         from . import parallel
         import torch.distributed as dist
+        row_segment, keys = pooling_row_segments(st, opts)
         m = _canonical_csr(fullmat)
         shards, _ = parallel.shard_models(m.indptr, row_segment, len(keys), world)
         mine = shards[rank]
@@ -361,15 +366,17 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
         local_seg = np.where(row_segment >= 0, remap[np.maximum(row_segment, 0)], -1).astype(np.int32)
         ret_model = TelescopeLikelihood(m, opts, row_segment=local_seg, n_segments=len(mine))
         ret_model.model_ids = mine
-        local_infos = ret_model.fit_segments()
+        local = ret_model.fit_segments()
         gathered = [None] * world
-        dist.all_gather_object(gathered, (mine.tolist(), local_infos))
-        infos = [None] * len(keys)
-        for ids, recs in gathered:
-            for i, fi in zip(ids, recs):
-                infos[i] = fi
-    for k, fi in zip(keys, infos):
-        poolinfo.models_info[k] = fi
+        dist.all_gather_object(gathered, (np.asarray(mine), local._res, local._itime))
+        # concatenate the per-rank result arrays; order[i] = row of model i in the concatenation
+        ids = np.concatenate([np.asarray(g[0], dtype=np.int64) for g in gathered])
+        res = {k: np.concatenate([g[1][k] for g in gathered]) for k in ('iters', 'flags', 'lnl', 'nobs', 'nfeats', 'diffs')}
+        order = np.empty(len(keys), dtype=np.int64)
+        order[ids] = np.arange(len(ids))
+        infos = SegmentFitInfos(res, ret_model.epsilon, ret_model.max_iter, max(g[2] for g in gathered),
+                                keys=keys, order=order)
+    poolinfo.models_info = infos
     lg.info(f'        ...{len(infos)} models fitted')
     ret_model.lnl = poolinfo.total_lnl                      # model.py:803
     return ret_model, poolinfo

@@ -80,6 +80,87 @@ class FitInfo(GenericInfo):
         return self.converged | self.reached_max
 
 
+class SegmentFitInfos:
+    """``FitInfo`` records of all models of one fit, backed by the arrays that came back from
+    the device.  Behaves like a read-only sequence (and, with ``keys``, like the dict
+    ``PoolInfo.models_info`` of the reference, model.py:766, 791): a record is only built when
+    somebody asks for it -- with 10^4..10^5 models, building them all costs more than the fit."""
+
+    def __init__(self, res, epsilon, max_iter, itime, keys=None, order=None):
+        self._res = res                      # dict of arrays: iters, flags, lnl, nobs, nfeats, diffs
+        self._eps, self._mi, self._itime = epsilon, max_iter, itime
+        self._keys = list(keys) if keys is not None else None
+        self._pos = None if self._keys is None else {k: i for i, k in enumerate(self._keys)}
+        self._order = order                  # optional: position -> row of the arrays
+        self._cache = {}
+
+    # -- sequence protocol --
+    def __len__(self):
+        return len(self._keys) if self._keys is not None else len(self._res['iters'])
+
+    def _make(self, i):
+        fi = self._cache.get(i)
+        if fi is None:
+            r = self._res
+            j = i if self._order is None else int(self._order[i])
+            fi = FitInfo(nobs=int(r['nobs'][j]), nfeats=int(r['nfeats'][j]), epsilon=self._eps, max_iter=self._mi)
+            fl = int(r['flags'][j])
+            fi.converged = bool(fl & 1)
+            fi.reached_max = bool(fl & 2)
+            fi.set_trace(int(r['iters'][j]), self._itime, r['diffs'][j])
+            fi.final_lnl = float(r['lnl'][j])
+            self._cache[i] = fi
+        return fi
+
+    def __getitem__(self, k):
+        if self._keys is not None:
+            return self._make(self._pos[k])
+        if isinstance(k, slice):
+            return [self._make(i) for i in range(*k.indices(len(self)))]
+        if k < 0:
+            k += len(self)
+        if not 0 <= k < len(self):
+            raise IndexError(k)
+        return self._make(k)
+
+    def __iter__(self):
+        if self._keys is not None:
+            return iter(self._keys)
+        return (self._make(i) for i in range(len(self)))
+
+    # -- mapping protocol (when keyed) --
+    def keys(self):
+        return list(self._keys)
+
+    def values(self):
+        return (self._make(i) for i in range(len(self)))
+
+    def items(self):
+        return ((k, self._make(i)) for i, k in enumerate(self._keys))
+
+    def __contains__(self, k):
+        return k in self._pos if self._pos is not None else False
+
+    def keyed(self, keys):
+        out = SegmentFitInfos(self._res, self._eps, self._mi, self._itime, keys=keys, order=self._order)
+        return out
+
+    # -- vectorised totals (PoolInfo) --
+    def _rows(self):
+        return slice(None) if self._order is None else np.asarray(self._order)
+
+    def total_lnl(self):
+        """float128 accumulation in model order (statistics.py:338-343)."""
+        v = np.asarray(self._res['lnl'])[self._rows()].astype(np.longdouble)
+        return np.cumsum(v)[-1] if len(v) else np.longdouble(0.0)
+
+    def total_obs(self):
+        return int(np.asarray(self._res['nobs'])[self._rows()].astype(np.int64).sum())
+
+    def total_params(self):
+        return int(2 * np.asarray(self._res['nfeats'])[self._rows()].astype(np.int64).sum())
+
+
 class PoolInfo(GenericInfo):
     """statistics.py:309-407."""
 
@@ -101,22 +182,31 @@ class PoolInfo(GenericInfo):
     @property
     def total_lnl(self):
         if self._total_lnl is None:
-            tot = np.longdouble(0.0)               # float128 accumulation, statistics.py:340
-            for fi in self.models_info.values():
-                tot += fi.final_lnl
-            self._total_lnl = tot
+            if isinstance(self.models_info, SegmentFitInfos):
+                self._total_lnl = self.models_info.total_lnl()
+            else:
+                tot = np.longdouble(0.0)               # float128 accumulation, statistics.py:340
+                for fi in self.models_info.values():
+                    tot += fi.final_lnl
+                self._total_lnl = tot
         return self._total_lnl
 
     @property
     def total_obs(self) -> int:
         if self._total_obs is None:
-            self._total_obs = sum(fi.nobs for fi in self.models_info.values())
+            if isinstance(self.models_info, SegmentFitInfos):
+                self._total_obs = self.models_info.total_obs()
+            else:
+                self._total_obs = sum(fi.nobs for fi in self.models_info.values())
         return self._total_obs
 
     @property
     def total_params(self) -> int:
         if self._total_params is None:
-            self._total_params = sum(fi.nparams * fi.nfeats for fi in self.models_info.values())
+            if isinstance(self.models_info, SegmentFitInfos):
+                self._total_params = self.models_info.total_params()
+            else:
+                self._total_params = sum(fi.nparams * fi.nfeats for fi in self.models_info.values())
         return self._total_params
 
     @property
