@@ -120,7 +120,8 @@ int ss_em_fit(ss_handle_t h, void* stream, double em_epsilon, int32_t max_iter, 
 
 /* Per-segment results of the last fit (any pointer may be NULL):
  *   iters[S]  number of iterations (len(FitInfo.iterations), statistics.py:280)
- *   flags[S]  bit0 converged, bit1 reached_max, bit2 model error (SS_ERR_MODEL class)
+ *   flags[S]  bit0 converged, bit1 reached_max, bit2 model error (SS_ERR_MODEL class),
+ *             bit3 a peer did not answer (row-sharded fit)
  *   lnl[S]    FitInfo.final_lnl (model.py:368-370)
  *   diffs[S*max_iter] diff_est trace (model.py:340, 359), unused slots = 0
  *   lnls[S*max_iter]  lnL trace (only with use_likelihood)
@@ -166,12 +167,29 @@ int ss_count(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, const 
              const int32_t* row_umi, int64_t cap, int32_t* out_cell, int32_t* out_col, double* out_val,
              int64_t* n_out);
 
-/* Pseudobulk over several GPUs: install a hook that all-reduces (SUM) a device
- * buffer of `count` doubles in place on `stream`; the fit calls it once per
- * iteration on the theta sums (model.py:239) and once at build time on the
- * segment totals.  NULL removes the hook. */
+/* ---- one model, rows sharded over the GPUs of a box (pooling_mode=pseudobulk) ----
+ * The reference fits the pseudobulk model single-threaded (model.py:762-767).  Here every rank
+ * (one process per GPU) holds a block of rows of the SAME model; ss_layout_build / ss_em_fit are
+ * called on every rank with n_segments = 1 and the library runs the exchange step of the path:
+ * the sum over ranks of the theta sums (model.py:239) once per iteration, plus build-time sums
+ * (s_max MAX, model.py:115; pisum0, weights, model.py:183-194).
+ *
+ * ss_set_allreduce: hook that all-reduces `count` doubles in place on `stream` (op 0 = sum,
+ *   1 = max) -- the caller's NCCL communicator.  Used for the build-time sums and, when no peer
+ *   buffers are installed, once per iteration from a host loop.  NULL removes the hook.
+ * ss_set_peers: rank / world of the sharded fit and (optionally) peer-mapped exchange buffers:
+ *   peer_bufs[r] = address, valid on THIS device, of rank r's buffer of `bytes` bytes
+ *   (>= ss_peer_buffer_bytes(K), zero-filled, e.g. torch symmetric memory over NVLink).  With
+ *   peer buffers the whole fit runs in one persistent kernel per rank that exchanges the partial
+ *   sums over peer memory itself; every rank adds them in rank order, so all ranks take the
+ *   identical convergence decision.  world = 1 with peer_bufs = NULL selects the same dense code
+ *   path on a single GPU.  The caller must keep the ranks in step (barrier) before each fit. */
 typedef int (*ss_allreduce_fn)(void* user, void* stream, double* buf, int64_t count, int32_t op /*0 sum, 1 max*/);
 int ss_set_allreduce(ss_handle_t h, ss_allreduce_fn fn, void* user);
+int64_t ss_peer_buffer_bytes(int32_t n_cols);
+int ss_set_peers(ss_handle_t h, int32_t rank, int32_t world, void* const* peer_bufs, int64_t bytes);
+/* pi / theta of the row-sharded model over all K loci (tl.pi, tl.theta, model.py:357) */
+int ss_em_get_dense_params(ss_handle_t h, void* stream, double* pi, double* theta);
 
 /* number of kernel launches issued by this handle since creation */
 int64_t ss_launch_count(ss_handle_t h);

@@ -52,6 +52,7 @@ int ss_destroy(ss_handle_t h) {
   cudaSetDevice(h->device);
   tl_alloc_stream = nullptr;
   free_fit(h);
+  free_dense(h);
   free_layout(h);
   for (int i = 0; i < 6; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -215,8 +216,14 @@ int ss_em_get_results(ss_handle_t h, void* stream, int32_t* iters, int32_t* flag
     }
     COPY_OUT(lnls, h->F.seg_lnls, S * h->P.max_iter, double);
   }
-  COPY_OUT(nobs, h->L.seg_nobs, S, int);
-  COPY_OUT(nfeats, h->L.seg_ncol, S, int);
+  if (h->dense_mode() && h->dn_ready) {
+    // rows sharded over ranks: observations / loci of the whole model, not of this rank's block
+    COPY_OUT(nobs, h->dn_counts, 1, int);
+    COPY_OUT(nfeats, h->dn_counts + 1, 1, int);
+  } else {
+    COPY_OUT(nobs, h->L.seg_nobs, S, int);
+    COPY_OUT(nfeats, h->L.seg_ncol, S, int);
+  }
   return SS_OK;
 }
 
@@ -289,6 +296,42 @@ int ss_set_allreduce(ss_handle_t h, ss_allreduce_fn fn, void* user) {
   SS_REQUIRE_HANDLE(h);
   h->allreduce = fn;
   h->allreduce_user = user;
+  return SS_OK;
+}
+
+int64_t ss_peer_buffer_bytes(int32_t n_cols) {
+  const int nchunks = (n_cols + SS_DN_TAIL + 64 + 511) / 512;
+  return (int64_t)(2 * (int64_t)nchunks * 512 + SS_DN_MAXW) * 8;
+}
+
+int ss_set_peers(ss_handle_t h, int32_t rank, int32_t world, void* const* peer_bufs, int64_t bytes) {
+  SS_REQUIRE_HANDLE(h);
+  if (world < 1 || world > SS_DN_MAXW || rank < 0 || rank >= world) {
+    h->set_error("ss_set_peers: need 0 <= rank < world <= 8");
+    return SS_ERR_ARG;
+  }
+  cudaSetDevice(h->device);
+  free_dense(h);
+  h->dn_world = world;
+  h->dn_rank = rank;
+  h->dn_epoch = 0;
+  h->dn_peers = peer_bufs != nullptr;
+  h->dn_force = true;
+  h->dn_peer_bytes = peer_bufs ? (size_t)bytes : 0;
+  for (int r = 0; r < SS_DN_MAXW; ++r) h->dn_peer_base[r] = (peer_bufs && r < world) ? peer_bufs[r] : nullptr;
+  return SS_OK;
+}
+
+int ss_em_get_dense_params(ss_handle_t h, void* stream, double* pi, double* theta) {
+  SS_REQUIRE_HANDLE(h);
+  if (!h->has_fit || !h->dense_mode() || !h->dn_ready) {
+    h->set_error("ss_em_get_dense_params: no row-sharded fit");
+    return SS_ERR_STATE;
+  }
+  cudaSetDevice(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  COPY_OUT(pi, h->dn_pi, h->L.K, double);
+  COPY_OUT(theta, h->dn_theta, h->L.K, double);
   return SS_OK;
 }
 

@@ -631,6 +631,7 @@ inline unsigned grid_for(long long n, int b = 256) { return (unsigned)std::max<l
 int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long long nnz, const int* row_ptr,
                  const int* col_idx, const uint16_t* score, const int* row_segment, int n_segments) {
   free_fit(h);
+  free_dense(h);
   free_layout(h);
   Layout& L = h->L;
   auto& pool = h->layout_allocs;
@@ -666,6 +667,8 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
                                                   L.seg_nobs, L.seg_namb, L.seg_nuniq, segA_u, segAamb_u, counters);
     h->launches++;
   }
+  // rows sharded over ranks: s_max is the maximum of the WHOLE matrix (model.py:115)
+  if (int rc = dense_allreduce_smax(h, st)) return rc;
   // ---- step 2: ambiguous / unique row lists ----
   int *iota, *ar_unsorted, *d_nsel;
   SS_CUDA_CHECK(h, tmp.get(&iota, (size_t)N));

@@ -18,15 +18,6 @@ namespace cg = cooperative_groups;
 
 namespace ss {
 
-struct EmArgs {
-  Layout L;
-  FitState F;
-  FitParams P;
-  const int* tile_list;
-  int n_list;
-  double* z_out;
-};
-
 struct StreamArgs {
   const int* tiles;
   int n_tiles;
@@ -1193,6 +1184,17 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
 
 #define SS_MARK(i) if (h->timing) SS_CUDA_CHECK(h, cudaEventRecord(h->ev[i], st))
   SS_MARK(0);
+  if (h->dense_mode()) {
+    // one model, rows sharded over ranks (or forced on one rank): dense K-long parameter vectors
+    for (int i = 0; i < SS_NUM_AUX_STREAMS; ++i) h->aux_used[i] = false;
+    const int rc = em_fit_dense(h, st, h->P);
+    if (rc != SS_OK) return rc;
+    if (h->timing) {
+      SS_MARK(3); SS_MARK(4); SS_MARK(5);
+      h->ev_valid = true;
+    }
+    return SS_OK;
+  }
   if (L.S > 0) {
     const int warps_per_block = 8;
     fit_prepare_kernel<<<(L.S + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(

@@ -18,6 +18,16 @@
 
 namespace ss {
 
+// kernel argument block shared by the EM kernels
+struct EmArgs {
+  Layout L;
+  FitState F;
+  FitParams P;
+  const int* tile_list;
+  int n_list;
+  double* z_out;
+};
+
 struct TileView {
   int seg, nrows, nent, ncol, maxlen, nlong;
   int pe, pr, pc, pj;

@@ -10,6 +10,8 @@ constexpr int SS_NUM_CLASSES = 6;
 constexpr int SS_NUM_AUX_STREAMS = SS_NUM_CLASSES + 1 + 7;   // size classes, streaming kernel, cluster sizes 2..8
 constexpr int SS_FR = 2;   // row fragments held in registers per thread (resident kernel)
 constexpr int SS_FC = 2;   // column fragments per thread
+constexpr int SS_DN_MAXW = 8;   // ranks of a row-sharded (dense) fit: the GPUs of one NVSwitch domain
+constexpr int SS_DN_TAIL = 8;   // scalar slots behind the K columns of an exchange buffer ([0] = lnL part)
 
 struct ss_handle_s {
   int device = 0;
@@ -72,6 +74,24 @@ struct ss_handle_s {
   ss_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
 
+  // ---- row-sharded single-model fit (ss_dense.cu) ----
+  bool dn_force = false;          // dense path on a single rank (tests)
+  bool dn_peers = false;          // exchange buffers in peer-mapped symmetric memory
+  int dn_world = 1, dn_rank = 0;
+  void* dn_peer_base[SS_DN_MAXW] = {};
+  size_t dn_peer_bytes = 0;
+  unsigned long long dn_epoch = 0;
+  bool dn_ready = false;
+  std::vector<void*> dense_allocs;
+  double* dn_stat = nullptr;      // [3K + tail]: pisum0 | nuniq | active | scalars, summed over ranks
+  double dn_tail_host[SS_DN_TAIL] = {};
+  int* dn_tgcol = nullptr;
+  double *dn_pi = nullptr, *dn_theta = nullptr, *dn_x[2] = {nullptr, nullptr}, *dn_T[2] = {nullptr, nullptr};
+  double *dn_part = nullptr, *dn_lnl = nullptr;
+  int *dn_ctl = nullptr, *dn_counts = nullptr;
+  int dn_nchunks = 0, dn_Kp = 0;
+  bool dense_mode() const { return dn_force || dn_peers || (allreduce != nullptr && dn_world > 1); }
+
   void set_error(const std::string& m) { err = m; }
 };
 
@@ -80,6 +100,10 @@ namespace ss {
 int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P);
 int em_emit_z(ss_handle_s* h, cudaStream_t st, double* z);
 void free_fit(ss_handle_s* h);
+// ss_dense.cu
+int em_fit_dense(ss_handle_s* h, cudaStream_t st, const FitParams& P);
+int dense_allreduce_smax(ss_handle_s* h, cudaStream_t st);
+void free_dense(ss_handle_s* h);
 // ss_layout.cu
 int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long long nnz, const int* row_ptr,
                  const int* col_idx, const uint16_t* score, const int* row_segment, int n_segments);

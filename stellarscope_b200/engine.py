@@ -34,6 +34,14 @@ class ModelError(EngineError):
     ``StellarscopeError`` (model.py:267-272, 454-457)."""
 
 
+class _null_ctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 def _np(x, dtype):
     return np.ascontiguousarray(np.asarray(x), dtype=dtype)
 
@@ -108,6 +116,88 @@ class Engine:
         out['resident'] = max(buf[5:11])
         out['cluster'] = max(buf[12:19])
         return {k: float(v) for k, v in out.items()}
+
+    # -- one model, rows sharded over ranks (pseudobulk; csrc/ss_dense.cu) ------------
+    def set_sharding(self, rank, world, group=None, peers=True, K=None):
+        """This handle fits a block of rows of ONE model shared with ``world - 1`` other ranks.
+
+        Installs the all-reduce hook (``torch.distributed`` / NCCL on the caller's process group) for
+        the build-time sums and -- with ``peers`` -- exchange buffers in NVLink-mapped symmetric
+        memory, so that the per-iteration exchange happens inside the persistent fit kernel.
+        ``world == 1`` selects the same dense code path on a single GPU.  Call before
+        ``build_layout``."""
+        rank, world = int(rank), int(world)
+        self.sharded = True
+        self.shard_rank, self.shard_world, self.shard_group = rank, world, group
+        self.peer_mode = False
+        ptr_arr = None
+        nbytes = 0
+        if world > 1:
+            import torch.distributed as dist
+            dev = self.device
+
+            class _DevBuf:                                  # zero-copy view of the library's device buffer
+                def __init__(self, ptr, n):
+                    self.__cuda_array_interface__ = {'shape': (n,), 'typestr': '<f8', 'data': (ptr, False),
+                                                     'version': 3, 'strides': None}
+
+            def hook(_user, stream, buf, count, op):
+                try:
+                    t = torch.as_tensor(_DevBuf(C.cast(buf, C.c_void_p).value, int(count)), device=dev)
+                    sptr = int(stream or 0)
+                    cur = torch.cuda.current_stream(dev)
+                    ctx = (torch.cuda.stream(torch.cuda.ExternalStream(sptr, device=dev))
+                           if sptr != cur.cuda_stream else _null_ctx())
+                    with torch.cuda.device(dev), ctx:
+                        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM, group=group)
+                    self.n_allreduce += 1
+                    return 0
+                except Exception:                           # never let an exception cross the C boundary
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            self.n_allreduce = 0
+            self._hook = _lib.ALLREDUCE_FN(hook)
+            self._check(self.lib.ss_set_allreduce(self.h, self._hook, None))
+            if peers:
+                if K is None:
+                    raise ValueError('set_sharding(peers=True) needs the number of loci K')
+                try:
+                    import torch.distributed._symmetric_memory as symm
+                    nbytes = int(self.lib.ss_peer_buffer_bytes(int(K)))
+                    with torch.cuda.device(dev):
+                        buf = symm.empty(nbytes // 8, dtype=torch.float64, device=dev)
+                        buf.zero_()
+                        g = group if group is not None else dist.group.WORLD
+                        hdl = symm.rendezvous(buf, g)
+                        ptrs = [int(p) for p in hdl.buffer_ptrs]
+                        torch.cuda.synchronize(dev)
+                        dist.barrier(group=group)           # every rank's buffer is zero before anybody signals
+                    self._keep['symm_buf'], self._keep['symm_hdl'] = buf, hdl
+                    ptr_arr = (C.c_void_p * world)(*ptrs)
+                    self.peer_mode = True
+                except Exception as e:                      # no peer access: per-iteration NCCL from the host loop
+                    import logging
+                    logging.getLogger(__name__).warning('symmetric memory unavailable (%s): using the NCCL hook '
+                                                        'for the per-iteration exchange', e)
+                    ptr_arr, nbytes = None, 0
+        self._check(self.lib.ss_set_peers(self.h, rank, world, ptr_arr, nbytes))
+
+    def sync_ranks(self):
+        """Keep the ranks of a sharded fit in step (the peers kernel spins on its peers)."""
+        if getattr(self, 'sharded', False) and self.shard_world > 1:
+            import torch.distributed as dist
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.shard_group)
+
+    def dense_params_sharded(self):
+        """pi, theta over all K loci of the row-sharded model (synchronises)."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            pi = torch.empty(self.K, dtype=torch.float64, device=dev)
+            th = torch.empty(self.K, dtype=torch.float64, device=dev)
+            self._check(self.lib.ss_em_get_dense_params(self.h, self._stream(), self._p(pi), self._p(th)))
+            return pi.cpu().numpy(), th.cpu().numpy()
 
     # -- layout --------------------------------------------------------------
     def set_matrix(self, indptr, indices, scores, K):
@@ -200,6 +290,8 @@ class Engine:
         """ss_em_fit: enqueue EM for every segment (asynchronous)."""
         self.max_iter = int(max_iter)
         self.use_likelihood = bool(use_likelihood)
+        self._params_cache = None
+        self.sync_ranks()
         with torch.cuda.device(self.device):
             rc = self.lib.ss_em_fit(self.h, self._stream(), float(em_epsilon), int(max_iter), float(pi_prior),
                                     float(theta_prior), int(bool(use_likelihood)))
@@ -221,6 +313,8 @@ class Engine:
             self._check(rc)
             out = dict(iters=iters.cpu().numpy(), flags=flags.cpu().numpy(), lnl=lnl.cpu().numpy(),
                        nobs=nobs.cpu().numpy(), nfeats=nfeats.cpu().numpy())
+            if (out['flags'] & 8).any():
+                raise EngineError(_lib.SS_ERR_CUDA, 'row-sharded fit: a peer rank did not answer (timeout)')
             if diffs is not None:
                 out['diffs'] = diffs.cpu().numpy().reshape(S, MI)
             if lnls is not None:
@@ -248,6 +342,8 @@ class Engine:
 
     def dense_params(self, seg):
         """Full-length (K) pi and theta of one segment, like ``tl.pi`` / ``tl.theta``."""
+        if getattr(self, 'sharded', False):
+            return self.dense_params_sharded()
         p = self._params_cache = getattr(self, '_params_cache', None) or self.params()
         a, n = int(p['seg_col0'][seg]), int(p['seg_ncol'][seg])
         pi = np.full(self.K, p['pi_rest'][seg])

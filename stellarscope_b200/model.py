@@ -59,7 +59,7 @@ class TelescopeLikelihood(object):
     ]
 
     def __init__(self, score_matrix, opts, row_segment=None, n_segments=None, device=None,
-                 tie_tol=TIE_TOL_DEFAULT):
+                 tie_tol=TIE_TOL_DEFAULT, shard=None):
         self.opts = opts
         self.epsilon = opts.em_epsilon
         self.max_iter = opts.max_iter
@@ -73,6 +73,10 @@ class TelescopeLikelihood(object):
         self.N, self.K = m.shape
         self.scale_factor = 100.
         self._engine = Engine(device)
+        if shard is not None:
+            # ONE model whose rows are spread over ranks: (rank, world, process group[, peers])
+            rank, world, group = shard[:3]
+            self._engine.set_sharding(rank, world, group, peers=(shard[3] if len(shard) > 3 else True), K=self.K)
         for attempt in (0, 1):
             self.max_score = int(m.data.max()) if m.nnz else 0
             if self.max_score > 65535 or (m.nnz and m.data.min() < 0):
@@ -334,7 +338,21 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
 
     if opts.pooling_mode == 'pseudobulk':
         lg.info('Models to fit: 1')
-        ret_model = TelescopeLikelihood(fullmat, opts)
+        world, rank = _dist_info()
+        if world > 1 and getattr(opts, 'shard_models', True):
+            # one model: shard its ROWS over the ranks (blocks of equal alignment count); the theta sums
+            # are exchanged once per iteration.  Rows of other ranks belong to no local
+            # model, so z -- and the counts derived from it -- are rank-local and add up over ranks.
+            from . import parallel
+            import torch.distributed as dist
+            m = _canonical_csr(fullmat)
+            r0, r1 = parallel.row_block(m.indptr, rank, world)
+            seg = np.full(m.shape[0], -1, dtype=np.int32)
+            seg[r0:r1] = 0
+            ret_model = TelescopeLikelihood(m, opts, row_segment=seg, n_segments=1,
+                                            shard=(rank, world, None, getattr(opts, 'peer_exchange', True)))
+        else:
+            ret_model = TelescopeLikelihood(fullmat, opts)
         poolinfo.nmodels = 1
         ret_model.em()
         poolinfo.models_info['pseudobulk'] = ret_model.fitinfo

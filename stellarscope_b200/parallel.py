@@ -104,3 +104,16 @@ def row_blocks(indptr, row_cell, world):
         bounds.append(max(bounds[-1], int(cand[j])))
     bounds.append(N)
     return np.array(bounds, dtype=np.int64)
+
+
+def row_block(indptr, rank, world):
+    """Row range [r0, r1) of ``rank`` when the rows of one model are cut into ``world`` contiguous
+    blocks of about equal alignment count (pseudobulk sharding without cell information: per-cell
+    counts of the rank-local rows are added up over the ranks afterwards)."""
+    N = len(indptr) - 1
+    A = int(indptr[-1])
+    targets = (A * np.arange(world + 1, dtype=np.int64)) // world
+    bounds = np.searchsorted(np.asarray(indptr, dtype=np.int64), targets, side='left')
+    bounds[0], bounds[-1] = 0, N
+    bounds = np.maximum.accumulate(np.minimum(bounds, N))
+    return int(bounds[rank]), int(bounds[rank + 1])

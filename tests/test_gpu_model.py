@@ -138,3 +138,30 @@ def test_binmax_known_answers_through_ss_reassign():
     flag, nbest, info = eng.reassign('best_exclude', z, tie_tol=0.0)
     assert flag.cpu().numpy().tolist() == [1, 0, 1, 0, 0, 1, 0, 0, 0]
     eng.close()
+
+
+@pytest.mark.parametrize('name', ['pseudobulk', 'pseudobulk_lnl', 'pseudobulk_priors'])
+@pytest.mark.parametrize('peers', [True, False])
+def test_row_sharded_dense_path_single_rank(name, peers):
+    """The row-sharded (dense K-vector) fit of csrc/ss_dense.cu on ONE rank -- persistent kernel
+    (peers=True) and host-loop variant (peers=False) -- against the golden pseudobulk fits of the
+    real reference.  The multi-rank exchange is covered by scripts/dist_check.py (2+ GPUs)."""
+    from stellarscope_b200 import model
+    g = H.load_golden(name)
+    opts = H.golden_opts(g, cls=H.StOpts)
+    st = H.make_st(g, opts)
+    tl = model.TelescopeLikelihood(st.raw_scores, opts, shard=(0, 1, None, peers))
+    tl.em()
+    fi = tl.fitinfo
+    assert len(fi.iterations) == g['iters'][0]
+    assert fi.converged == bool(g['converged'][0]) and fi.reached_max == bool(g['reached_max'][0])
+    assert fi.nobs == g['nobs'][0] and fi.nfeats == g['nfeats'][0]
+    assert abs(fi.final_lnl - g['lnl'][0]) <= 1e-10 * abs(g['lnl'][0])
+    d = np.array([x[2] for x in fi.iterations])
+    dg = g['diffs'][0, :len(d)]
+    assert np.all(np.abs(d - dg) <= 1e-12 + 1e-6 * dg)
+    r, ok = H.rel_err(np.asarray(tl.pi.toarray()).ravel(), g['pi'][0])
+    assert r < 1e-6 and ok
+    r, ok = H.rel_err(tl.theta, g['theta'][0])
+    assert r < 1e-6
+    assert np.max(np.abs(tl.z.data - g['z'])) < 1e-9
