@@ -53,6 +53,8 @@ CASES = {
                           dict(pooling_mode='pseudobulk', pi_prior=3, theta_prior=500, max_iter=30), False),
     'individual_maxiter': (dict(n_cells=6, n_alignments=1500, n_loci=100, seed=19, unique_frac=0.0),
                            dict(pooling_mode='individual', max_iter=7), False),
+    # BASELINE.json configs[0]: bundled BAM + GTF, pseudobulk, defaults (golden: data/telescope_report.tsv)
+    'config1': ('config1', dict(pooling_mode='pseudobulk'), False),
 }
 
 
@@ -86,8 +88,41 @@ def make_st(d, opts, corrected):
     return st, names
 
 
+def config1_dataset():
+    """BASELINE.json configs[0]: the BAM + GTF the reference bundles, through the loader restatement
+    (oracle/loader_oracle.py) with ``--barcode_tag RG --ignore_umi`` (the bundled BAM has no CB/UB tags,
+    SURVEY.md 0.5).  Returns the data set plus the golden columns of ``data/telescope_report.tsv``."""
+    from oracle.loader_oracle import load_alignment
+    data = os.path.join(refshim.REFERENCE_ROOT, 'stellarscope', 'data')
+    r = load_alignment(os.path.join(data, 'alignment.bam'), os.path.join(data, 'annotation.gtf'),
+                       barcode_tag='RG', ignore_umi=True)
+    m = r['matrix']
+    N, K = m.shape
+    d = types.SimpleNamespace(indptr=m.indptr.astype(np.int32), indices=m.indices.astype(np.int32),
+                              scores=m.data.astype(np.uint16), N=N, K=K, A=int(m.nnz), n_cells=1,
+                              row_cell=np.zeros(N, dtype=np.int32), cell_type=np.zeros(1, dtype=np.int32),
+                              n_celltypes=1, row_umi=np.arange(N, dtype=np.int32))
+    d.cell_rows = lambda: [np.arange(N)]
+    feats = sorted(r['feat_index'], key=r['feat_index'].get)
+    rep = {}
+    lines = open(os.path.join(data, 'telescope_report.tsv')).read().splitlines()
+    cols = lines[1].split('\t')
+    for ln in lines[2:]:
+        f = ln.split('\t')
+        rep[f[0]] = dict(zip(cols[1:], f[1:]))
+    extra = dict(feat_names=np.array(feats), minAS=r['minAS'], maxAS=r['maxAS'],
+                 report_names=np.array(list(rep.keys())))
+    for c in ('final_count', 'final_conf', 'final_prop', 'init_aligned', 'unique_count'):
+        extra['report_' + c] = np.array([float(rep[k][c]) for k in rep])
+    return d, extra
+
+
 def run_case(name, skw, okw, corrected, ref):
-    d = synth.generate(**skw)
+    extra = {}
+    if skw == 'config1':
+        d, extra = config1_dataset()
+    else:
+        d = synth.generate(**skw)
     tmpdir = tempfile.mkdtemp()
     opts = refshim.RefOpts(reassign_mode=MODES, rng=np.random.default_rng(2024), **okw)
     opts.outfile_path = lambda suffix: os.path.join(tmpdir, suffix)
@@ -169,6 +204,7 @@ def run_case(name, skw, okw, corrected, ref):
         fn = 'TE_counts.mtx' if mi == 0 else f'TE_counts.{mode}.mtx'
         out[f'c_{mode}'] = np.asarray(scipy.io.mmread(os.path.join(tmpdir, fn)).todense())
     out['barcodes'] = np.array(open(os.path.join(tmpdir, 'barcodes.tsv')).read().split())
+    out.update(extra)
     np.savez_compressed(os.path.join(GOLDEN, f'ref_{name}.npz'), **out)
     print(f'{name}: N={d.N} A={d.A} K={d.K} models={len(keys)} iters={out["iters"].tolist()[:6]} '
           f'lnl={out["total_lnl"]:.6f} promoted={bool(out["promoted"].any())}')
@@ -177,7 +213,10 @@ def run_case(name, skw, okw, corrected, ref):
 def main():
     ref = refshim.load()
     os.makedirs(GOLDEN, exist_ok=True)
+    only = sys.argv[1:]
     for name, (skw, okw, corrected) in CASES.items():
+        if only and name not in only:
+            continue
         run_case(name, skw, okw, corrected, ref)
 
 

@@ -165,3 +165,22 @@ def test_row_sharded_dense_path_single_rank(name, peers):
     r, ok = H.rel_err(tl.theta, g['theta'][0])
     assert r < 1e-6
     assert np.max(np.abs(tl.z.data - g['z'])) < 1e-9
+
+
+def test_config1_reproduces_telescope_report():
+    """BASELINE.json configs[0] through the CUDA path: pooling_mode=pseudobulk, reassign_mode=best_exclude
+    (+ best_conf / total_hits / initial_unique) on the matrix of the bundled BAM + GTF, against the
+    reference's own golden ``data/telescope_report.tsv`` (independent of the oracle)."""
+    from stellarscope_b200 import model
+    from tests.test_oracle import config1_report_check
+    g = H.load_golden('config1')
+    opts = H.golden_opts(g, cls=H.StOpts)
+    opts.reassign_mode = ['best_exclude', 'best_conf', 'total_hits', 'initial_unique']
+    st = H.make_st(g, opts)
+    tl, poolinfo = model._fit_pooling_model(st, opts)
+    assert len(poolinfo.models_info['pseudobulk'].iterations) == 16
+    assert abs(tl.lnl - 94724.99236416568) <= 1e-10 * 94724.99236416568       # SURVEY.md section 6 probe
+    model.reassign(st, tl)
+    counts, bc, ft = model.count_matrices(st, tl)
+    pi = np.asarray(tl.pi.toarray()).ravel()
+    config1_report_check(g, pi, {m: np.asarray(counts[m].todense())[:, 0] for m in opts.reassign_mode})

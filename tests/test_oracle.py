@@ -137,3 +137,59 @@ def test_empty_model_raises():
     with pytest.raises(eo.OracleError):
         eo.OracleLikelihood(np.array([0, 0, 0]), np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.uint16), 5,
                             eo.Opts()).em()
+
+
+# ---- config 1 (bundled BAM + GTF) against the reference's own golden report -------------------------
+def config1_report_check(g, pi, counts):
+    """``stellarscope/data/telescope_report.tsv`` (Telescope 1.0.2 on the bundled files) against a
+    fit of the config-1 matrix: final_prop <-> pi (3 printed digits), final_count <-> best_exclude,
+    final_conf <-> best_conf at 0.9, init_aligned <-> total_hits, unique_count <-> initial_unique
+    (SURVEY.md 8c).  ``counts[mode]`` = per-locus counts of the single cell."""
+    col = {n: j for j, n in enumerate(g['feat_names'].tolist())}
+    checked = 0
+    for i, name in enumerate(g['report_names'].tolist()):
+        j = col[name]
+        fp = float(g['report_final_prop'][i])
+        assert abs(pi[j] - fp) <= 0.006 * fp + 1e-300, (name, pi[j], fp)
+        assert counts['best_exclude'][j] == g['report_final_count'][i], name
+        assert counts['best_conf'][j] == g['report_final_conf'][i], name
+        assert counts['total_hits'][j] == g['report_init_aligned'][i], name
+        assert counts['initial_unique'][j] == g['report_unique_count'][i], name
+        checked += 1
+    assert checked == 59                                    # telescope_report.tsv:3-61
+    return checked
+
+
+def test_oracle_config1_reproduces_telescope_report():
+    g = H.load_golden('config1')
+    assert g['indptr'][-1] == 18471 and len(g['indptr']) - 1 == 1000 and int(g['K']) == 100   # SURVEY.md 0.5
+    assert int(g['minAS']) == 240 and int(g['maxAS']) == 300
+    opts = H.golden_opts(g)
+    ptr, idx, sc = H.golden_matrix(g)
+    K = int(g['K'])
+    m = eo.OracleLikelihood(ptr, idx, sc, K, opts).em()
+    assert len(m.fitinfo.iterations) == 16
+    names = ['sample_01']
+    counts = {}
+    for mode in ('best_exclude', 'best_conf', 'total_hits', 'initial_unique'):
+        rp, ri, rd, _ = m.reassign(mode, 0.9, rng=np.random.default_rng(0))
+        counts[mode] = eo.aggregate_counts(rp, ri, rd, K, ['sample_01'] * (len(ptr) - 1), names)[:, 0]
+    config1_report_check(g, np.asarray(m.pi, dtype=np.float64), counts)
+
+
+@pytest.mark.skipif(not refshim.available(), reason='reference checkout not present')
+def test_loader_restatement_reproduces_config1_fixture():
+    """oracle/loader_oracle.py on the bundled BAM + GTF gives the committed fixture matrix."""
+    import os
+    from oracle.loader_oracle import load_alignment
+    data = os.path.join(refshim.REFERENCE_ROOT, 'stellarscope', 'data')
+    r = load_alignment(os.path.join(data, 'alignment.bam'), os.path.join(data, 'annotation.gtf'),
+                       barcode_tag='RG', ignore_umi=True)
+    g = H.load_golden('config1')
+    m = r['matrix']
+    assert np.array_equal(m.indptr, g['indptr']) and np.array_equal(m.indices, g['indices'])
+    assert np.array_equal(m.data, g['scores'])
+    assert sorted(r['feat_index'], key=r['feat_index'].get) == g['feat_names'].tolist()
+    # with default tags every fragment is skipped as "Missing CB" (model.py:1099-1101): nothing to fit
+    r0 = load_alignment(os.path.join(data, 'alignment.bam'), os.path.join(data, 'annotation.gtf'))
+    assert r0['matrix'].shape[0] == 0
