@@ -257,6 +257,7 @@ struct TileBuildArgs {
   int jds_stride;
   // per tile scalars
   int *t_ncol, *t_maxlen, *t_nlong, *t_seg, *t_nrows, *t_nent, *t_rfrag, *t_cfrag;
+  int* t_gt;               // [n_tiles][10]: rows longer than 4/8/16/32, columns with more than 4..128 rows
   double* t_wsum;
 };
 
@@ -420,6 +421,18 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
     const int e = (int)(keys[i] & 0xffffu);
     a.e_idx[eo + e] = pack_idx((unsigned)lc, (unsigned)(cptr[lc] + (i - colstart[ci])));
   }
+  // lane-group boundaries: rows are sorted by length, columns by count (both descending), so
+  // "number of rows longer than x" is the first position whose length is <= x
+  if (tid < 10) {
+    const int x = tid < 4 ? (4 << tid) : (4 << (tid - 4));    // 4 8 16 32 | 4 8 16 32 64 128
+    int lo = 0, hi = tid < 4 ? nrows : ncol;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const int v = tid < 4 ? rlen[mid] : cptr[mid + 1] - cptr[mid];
+      if (v > x) lo = mid + 1; else hi = mid;
+    }
+    a.t_gt[10 * t + tid] = lo;
+  }
   for (int lc = tid; lc <= ncol; lc += BUILD_THREADS) a.tmp_cptr[co_tmp + lc] = (uint16_t)cptr[lc];
   for (int p = tid; p <= lmax; p += BUILD_THREADS) a.tmp_jptr[(long long)a.jds_stride * t + p] = (uint16_t)jptr[p];
   // number of long columns / column fragments / row fragments: block reduce
@@ -461,7 +474,7 @@ __global__ void tile_pad2_kernel(int n_tiles, const int* __restrict__ t_ncol, co
 
 __global__ void tile_hdr_kernel(int n_tiles, const int* t_seg, const int* t_nrows, const int* t_nent, const int* t_ncol,
                                 const int* t_maxlen, const int* t_nlong, const int* t_rfrag, const int* t_cfrag,
-                                const long long* ent_off,
+                                const int* t_gt, const long long* ent_off,
                                 const long long* row_off, const long long* col_off, const long long* jds_off,
                                 long long* __restrict__ hdr) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -471,6 +484,8 @@ __global__ void tile_hdr_kernel(int n_tiles, const int* t_seg, const int* t_nrow
   h[H_MAXLEN] = t_maxlen[t]; h[H_NLONG] = t_nlong[t];
   h[H_ENT_OFF] = ent_off[t]; h[H_ROW_OFF] = row_off[t]; h[H_COL_OFF] = col_off[t]; h[H_JDS_OFF] = jds_off[t];
   h[H_RFRAG] = t_rfrag[t]; h[H_CFRAG] = t_cfrag[t];
+  for (int i = 0; i < 10; ++i) h[H_RGT4 + i] = t_gt[10 * t + i];
+  h[H_CGT128 + 1] = 0; h[H_CGT128 + 2] = 0;
 }
 
 // copy cptr / jptr to their final offsets, emit (seg, locus) keys of the tile columns
@@ -784,6 +799,8 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
   SS_CUDA_CHECK(h, tmp.get(&t_nrows, Tz));
   SS_CUDA_CHECK(h, tmp.get(&t_nent, Tz));
   SS_CUDA_CHECK(h, tmp.get(&t_wsum, Tz));
+  int* t_gt;
+  SS_CUDA_CHECK(h, tmp.get(&t_gt, Tz * 10));
   SS_CUDA_CHECK(h, dev_alloc(pool, &L.tile_hdr, Tz * HDR_WORDS));
   long long tot[4] = {0, 0, 0, 0};
   uint16_t* tmp_cptr = nullptr;
@@ -822,7 +839,7 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
     a.r_len = L.r_len; a.r_w = L.r_w; a.r_orow = L.r_orow;
     a.tmp_cptr = tmp_cptr; a.tmp_gcol = tmp_gcol; a.tmp_jptr = tmp_jptr; a.jds_stride = jds_stride;
     a.t_ncol = t_ncol; a.t_maxlen = t_maxlen; a.t_nlong = t_nlong; a.t_seg = t_seg; a.t_nrows = t_nrows;
-    a.t_nent = t_nent; a.t_wsum = t_wsum; a.t_rfrag = t_rfrag; a.t_cfrag = t_cfrag;
+    a.t_nent = t_nent; a.t_wsum = t_wsum; a.t_rfrag = t_rfrag; a.t_cfrag = t_cfrag; a.t_gt = t_gt;
 #define SS_TILE_BUILD(ECAP, ELOW)                                                                         \
   do {                                                                                                    \
     constexpr size_t smem = tile_build_smem<ECAP>();                                                      \
@@ -849,7 +866,7 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
     SS_CUDA_CHECK(h, cudaMemcpyAsync(&tot[3], jds_off + n_tiles, 8, cudaMemcpyDeviceToHost, st));
     SS_CUDA_CHECK(h, cudaMemcpyAsync(&n_tilekeys, key_off + n_tiles, 8, cudaMemcpyDeviceToHost, st));
     tile_hdr_kernel<<<grid_for(n_tiles), 256, 0, st>>>(n_tiles, t_seg, t_nrows, t_nent, t_ncol, t_maxlen, t_nlong,
-                                                       t_rfrag, t_cfrag, ent_off, row_off, col_off, jds_off,
+                                                       t_rfrag, t_cfrag, t_gt, ent_off, row_off, col_off, jds_off,
                                                        L.tile_hdr);
     h->launches++;
     h->hdr_host.resize((size_t)n_tiles * HDR_WORDS);

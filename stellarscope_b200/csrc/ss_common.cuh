@@ -15,11 +15,13 @@ namespace ss {
 constexpr int E_HARD = 4096;     // hard cap on alignments per tile (worst case fits 227 KB of shared memory)
 constexpr int ALIGN_ELEMS = 8;   // per-tile slices start at multiples of 8 elements (16 B for u16)
 constexpr int LONG_COL = 32;     // tile columns with more rows than this are reduced by a warp
-constexpr int HDR_WORDS = 12;    // int64 words per tile header
+constexpr int HDR_WORDS = 24;    // int64 words per tile header
 
-// tile header word indices
+// tile header word indices.  H_RGT*: rows of the tile longer than 4/8/16/32 alignments, H_CGT*: tile
+// columns with more than 4..128 rows -- the lane-group boundaries of the lane kernel (rows are sorted
+// by length, columns by count, both descending).
 enum { H_SEG = 0, H_NROWS, H_NENT, H_NCOL, H_MAXLEN, H_NLONG, H_ENT_OFF, H_ROW_OFF, H_COL_OFF, H_JDS_OFF,
-       H_RFRAG, H_CFRAG };
+       H_RFRAG, H_CFRAG, H_RGT4, H_RGT8, H_RGT16, H_RGT32, H_CGT4, H_CGT8, H_CGT16, H_CGT32, H_CGT64, H_CGT128 };
 
 // Fragments (resident kernel): a row / column is cut into pieces of FRAG entries handled by
 // one lane each; a row with f pieces occupies a lane group of size pow2ceil(f) (<= FRAG_MAXG_ROW),

@@ -86,162 +86,35 @@ __global__ void fit_prepare_kernel(Layout L, FitState F, FitParams P, const int8
 }
 
 // ---------------------------------------------------------------------------
-// resident kernel: one CTA per single-tile segment.  The tile is loaded once (TMA bulk
-// copies) and iterated to convergence out of shared memory: two barriers per iteration.
-// ---------------------------------------------------------------------------
-template <int THREADS, bool LNL>
-__global__ void __launch_bounds__(THREADS) em_resident_kernel(EmArgs a) {
-  extern __shared__ __align__(128) unsigned char dsm[];
-  __shared__ double s_red[64];
-  __shared__ uint64_t s_bar;
-  constexpr int NW = THREADS / 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int t = a.tile_list[blockIdx.x];
-  const TileView v = load_tile_view(a.L.tile_hdr, t);
-  TileSmem s = carve_tile(dsm, v);
-  const int seg = v.seg;
-
-  if (tid == 0) {
-    mbar_init(&s_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid == 0) tile_issue_loads(a.L, v, s, &s_bar);
-
-  const double invK = 1.0 / (double)a.P.K;       // model.py:164,172
-  for (int c = tid; c < v.ncol; c += THREADS) {
-    s.aux[c] = invK;
-    s.pt[c] = invK * invK;
-  }
-  const double thpw = a.F.seg_thpw[seg], pipw = a.F.seg_pipw[seg];
-  const double inv_thd = a.F.seg_inv_thd[seg], inv_pid = a.F.seg_inv_pid[seg];
-  const double diff1_extra = a.F.seg_diff1_extra[seg];
-  const double lnl_extra = a.F.seg_lnl_extra[seg];
-  const double eps = a.P.eps;
-  const int max_iter = a.P.max_iter;
-  const double* __restrict__ ps0 = a.L.c_pisum0 + v.co;
-  const int* __restrict__ nuq = a.L.c_nuniq + v.co;
-  const int* __restrict__ scol = a.L.c_scol + v.co;
-  double* diffs = a.F.seg_diffs + (long long)seg * max_iter;
-  double* lnls = a.F.seg_lnls ? a.F.seg_lnls + (long long)seg * max_iter : nullptr;
-  mbar_wait(&s_bar, 0);
-  __syncthreads();
-
-  double* pt_cur = s.pt;
-  double* pt_nxt = s.pt2;
-  double lnl_prev = INFINITY, lnl_amb = 0.0;
-  int it = 0, par = 0;
-  bool done = false, conv = false;
-  while (!done) {
-    ++it;
-    tile_phase_a<THREADS>(v, s, pt_cur);
-    group_sync<THREADS>();
-    // ---- phase B: thetasum per tile column -> theta', pi', x' = pi' theta', |delta pi| ----
-    double dsum = 0.0;
-    for (int c = warp; c < v.nlong; c += NW) {
-      const double asum = col_sum_warp(s.val, s.cptr[c], (int)s.cptr[c + 1] - (int)s.cptr[c], lane);
-      if (lane == 0) {
-        const double T = pt_cur[c] * asum;
-        const double th = (T + thpw) * inv_thd;               // model.py:240
-        const double pn = (ps0[c] + T + pipw) * inv_pid;      // model.py:243-244
-        dsum += fabs(pn - s.aux[c]);
-        s.aux[c] = pn;
-        pt_nxt[c] = pn * th;
-        s.val[s.cptr[c]] = th;                                // column's own slot: theta' for the epilogue
-      }
-    }
-    for (int c = v.nlong + tid; c < v.ncol; c += THREADS) {
-      const double T = pt_cur[c] * col_sum_thread(s.val, s.cptr[c], (int)s.cptr[c + 1] - (int)s.cptr[c]);
-      const double th = (T + thpw) * inv_thd;
-      const double pn = (ps0[c] + T + pipw) * inv_pid;
-      dsum += fabs(pn - s.aux[c]);
-      s.aux[c] = pn;
-      pt_nxt[c] = pn * th;
-      s.val[s.cptr[c]] = th;
-    }
-    double diff = block_sum<THREADS>(dsum, s_red, par++);     // barrier: publishes pt_nxt / aux / val
-    if (it == 1) diff += diff1_extra;
-    const bool reached = it >= max_iter;
-    if (!LNL) {
-      conv = diff < eps;                                       // model.py:351
-    } else {
-      // lnL with the E-step's z (old x) and the new parameters: model.py:344
-      double l = tile_lnl_pass<THREADS>(v, s, pt_cur, pt_nxt, true, nullptr, nullptr);
-      for (int c = tid; c < v.ncol; c += THREADS) {
-        const int nu = nuq[c];
-        const double pn = s.aux[c];
-        if (nu > 0 && pn > 0.0) l += (double)nu * log(pn);
-      }
-      lnl_amb = block_sum<THREADS>(l, s_red, par++);
-      const double lnl = lnl_amb + lnl_extra;
-      conv = fabs(lnl - lnl_prev) < eps;                       // model.py:345-347
-      lnl_prev = lnl;
-      if (tid == 0 && lnls) lnls[it - 1] = lnl;
-    }
-    done = conv || reached;
-    if (tid == 0) diffs[it - 1] = diff;
-    if (!done) { double* tmp = pt_cur; pt_cur = pt_nxt; pt_nxt = tmp; }
-  }
-  // ---- converged / reached max: publish parameters, final lnL ----
-  // pt_cur = x of the last E-step (tl.z belongs to it), pt_nxt = final x, aux = final pi.
-  for (int c = tid; c < v.ncol; c += THREADS) {
-    const int slot = scol[c];
-    a.F.sc_pi[slot] = s.aux[c];
-    a.F.sc_theta[slot] = s.val[s.cptr[c]];
-    a.F.sc_ptprev[slot] = pt_cur[c];
-    a.F.sc_ptfin[slot] = pt_nxt[c];
-  }
-  double l;
-  if (!LNL) {
-    l = tile_lnl_pass<THREADS>(v, s, pt_cur, pt_nxt, true, nullptr, nullptr);
-    l = block_sum<THREADS>(l, s_red, par++);
-  } else {
-    // tile_lnl holds the ambiguous-row part only; the unique-row part is added by finalize
-    double lu = 0.0;
-    for (int c = tid; c < v.ncol; c += THREADS) {
-      const int nu = nuq[c];
-      const double pn = s.aux[c];
-      if (nu > 0 && pn > 0.0) lu += (double)nu * log(pn);
-    }
-    lu = block_sum<THREADS>(lu, s_red, par++);
-    l = lnl_amb - lu;
-  }
-  if (tid == 0) {
-    a.F.tile_lnl[t] = l;
-    a.F.seg_iters[seg] = it;
-    a.F.seg_flags[seg] = (conv ? 1 : 0) | (it >= max_iter ? 2 : 0);
-  }
-}
-
-// ---------------------------------------------------------------------------
-// fragment kernel (largest size class): one CTA per single-tile segment, iterated to convergence on chip.
+// lane kernel: one CTA per single-tile segment (a cell in individual mode), iterated to
+// convergence on chip.
 //
-// The tile's static data (Q, index words, row weights) lives in REGISTERS for the whole fit:
-// every lane owns up to FR row fragments and FC column fragments of <= FRAG entries.  A row
-// (column) with more than FRAG entries is spread over an aligned group of 2/4/8 (..32) lanes
-// whose partial sums are combined by xor shuffles, so every lane does the same small amount of
-// work whatever the row / column lengths are (no intra-CTA imbalance at the two barriers).
-// Shared memory holds only what rows and columns exchange: the column-major scratch `val`
-// (8 B / alignment) and the per-column vectors x (ping-pong) and pi.
+// The tile's static data (Q, index words, row weights, the per-column state pi / x) lives in
+// REGISTERS for the whole fit: every lane owns FR row fragments and FC column fragments of <= 4
+// entries.  A row (column) with more than 4 entries is spread over an aligned group of 2/4/8
+// (..32) lanes whose partial sums are combined by xor shuffles, so every lane does the same small
+// amount of work whatever the row / column lengths are (no intra-CTA imbalance at the barriers).
+// Shared memory only carries what rows and columns exchange: the column-major scratch `val`
+// (8 B per alignment) and the vector x = pi*theta (ping-pong).  Per alignment and iteration that
+// is one gather (x_j), one scatter (val) and one column read -- the shared-memory data path is the
+// binding resource of this kernel, so nothing else goes through it.
+//
+// Lane layout (from the tile header: rows are sorted by length, columns by count, descending):
+// virtual lane vl = tid + j * THREADS for fragment slot j; the 8-lane groups come first, then the
+// 4-, 2- and 1-lane ones, so that groups are aligned and the lanes of a warp have (almost always)
+// the same fragment length.  Per slot the warp-uniform maximum fragment length / group size is
+// computed once; inside the loop only uniform branches remain, lanes with fewer entries work on
+// padding (q = 0, a dummy column whose x is 0, a dummy scratch slot).
 // Rows longer than 32 / columns longer than 128 and whatever does not fit the FR*THREADS
 // (FC*THREADS) lanes take generic paths that read the tile from global memory.
 // ---------------------------------------------------------------------------
-struct FragSmem {
-  double* val;   // pe
-  double* pt;    // pc
-  double* pt2;   // pc
-  double* aux;   // pc   pi of the columns on the generic path; all columns after the fit
-};
-__host__ __device__ inline size_t frag_smem_bytes(int nent, int ncol) {
-  return 8 * ((size_t)pad8(nent) + 3 * (size_t)pad8(ncol + 1));
-}
-
-__device__ __forceinline__ double group_xor_sum(double a, int g, int maxg_in_warp) {
-  // butterfly inside aligned lane groups of size g (1,2,4,..,32); executed by all 32 lanes
+__device__ __forceinline__ double group_xor_sum(double a, int g, int gmax) {
+  // butterfly inside aligned lane groups of size g (1,2,4,..,32); executed by all 32 lanes, gmax is
+  // the largest group of the warp (warp-uniform)
   const unsigned full = 0xffffffffu;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    if (o < maxg_in_warp) {                      // warp-uniform
+    if (o < gmax) {
       const double t = __shfl_xor_sync(full, a, o);
       if (o < g) a += t;
     }
@@ -250,20 +123,20 @@ __device__ __forceinline__ double group_xor_sum(double a, int g, int maxg_in_war
 }
 
 template <int THREADS, bool LNL, int FR, int FC>
-__global__ void __launch_bounds__(THREADS) em_fragment_kernel(EmArgs a) {
+__global__ void __launch_bounds__(THREADS) em_lane_kernel(EmArgs a) {
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double s_red[64];
   constexpr int NW = THREADS / 32;
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = a.tile_list[blockIdx.x];
+  const long long* __restrict__ hd = a.L.tile_hdr + (long long)HDR_WORDS * t;
   const TileView v = load_tile_view(a.L.tile_hdr, t);
   const int seg = v.seg;
-  FragSmem s;
-  s.val = reinterpret_cast<double*>(dsm);
-  s.pt = s.val + v.pe;
-  s.pt2 = s.pt + v.pc;
-  s.aux = s.pt2 + v.pc;
+  double* val = reinterpret_cast<double*>(dsm);      // pe + 8 (slot pe: scratch of the padding entries)
+  double* pt = val + v.pe + 8;                       // pc  (slot ncol: x of the dummy column = 0)
+  double* pt2 = pt + v.pc;                           // pc
+  double* aux = pt2 + v.pc;                          // pc  pi of the columns on the generic path; all columns after the fit
   // global views of the tile
   const double* __restrict__ gq = a.L.e_q + v.eo;
   const uint32_t* __restrict__ gidx = a.L.e_idx + v.eo;
@@ -277,8 +150,12 @@ __global__ void __launch_bounds__(THREADS) em_fragment_kernel(EmArgs a) {
 
   const double invK = 1.0 / (double)a.P.K;       // model.py:164,172
   for (int c = tid; c < v.ncol; c += THREADS) {
-    s.aux[c] = invK;
-    s.pt[c] = invK * invK;
+    aux[c] = invK;
+    pt[c] = invK * invK;
+  }
+  if (tid == 0) {
+    pt[v.ncol] = 0.0;
+    pt2[v.ncol] = 0.0;
   }
   const double thpw = a.F.seg_thpw[seg], pipw = a.F.seg_pipw[seg];
   const double inv_thd = a.F.seg_inv_thd[seg], inv_pid = a.F.seg_inv_pid[seg];
@@ -291,11 +168,9 @@ __global__ void __launch_bounds__(THREADS) em_fragment_kernel(EmArgs a) {
   double* lnls = a.F.seg_lnls ? a.F.seg_lnls + (long long)seg * max_iter : nullptr;
 
   // ---- row fragments ----
-  // rows are sorted by length (desc): #rows longer than p = jptr[p+1] - jptr[p]
-  auto rows_gt = [&](int p) -> int { return p < v.maxlen ? (int)gjptr[p + 1] - (int)gjptr[p] : 0; };
-  const int n_huge = rows_gt(FRAG * FRAG_MAXG_ROW);            // generic path
-  const int n8 = rows_gt(16) - n_huge, n4 = rows_gt(8) - rows_gt(16), n2 = rows_gt(4) - rows_gt(8);
-  const int n1 = v.nrows - rows_gt(4);
+  const int rgt4 = (int)hd[H_RGT4], rgt8 = (int)hd[H_RGT8], rgt16 = (int)hd[H_RGT16], rgt32 = (int)hd[H_RGT32];
+  const int n_huge = rgt32;                                     // generic path
+  const int n8 = rgt16 - rgt32, n4 = rgt8 - rgt16, n2 = rgt4 - rgt8, n1 = v.nrows - rgt4;
   const int V8 = 8 * n8, V4 = V8 + 4 * n4, V2 = V4 + 2 * n2, V = V2 + n1;   // virtual lanes
   const int Vc = min(V, FR * THREADS);                          // lanes held in registers
   // first row that is NOT covered by the register fragments (group sizes divide 32)
@@ -305,16 +180,19 @@ __global__ void __launch_bounds__(THREADS) em_fragment_kernel(EmArgs a) {
   else if (Vc < V4) r_ovf = n_huge + n8 + (Vc - V8) / 4;
   else if (Vc < V2) r_ovf = n_huge + n8 + n4 + (Vc - V4) / 2;
   else r_ovf = n_huge + n8 + n4 + n2 + (Vc - V2);
+  const bool generic_rows = n_huge > 0 || r_ovf < v.nrows;
 
+  const uint32_t dummy_off = ((uint32_t)v.ncol << 3) | ((uint32_t)v.pe << 19);
   double fq[FR][FRAG], fw[FR];
-  uint32_t fi[FR][FRAG];
-  int fn[FR], fg[FR];
+  uint32_t fo[FR][FRAG];        // byte offset of x_j | byte offset of the scratch slot << 16
+  int fg[FR], nA[FR], gA[FR];
 #pragma unroll
   for (int j = 0; j < FR; ++j) {
     const int vl = tid + j * THREADS;
-    fn[j] = 0; fg[j] = 1; fw[j] = 0.0;
+    int n = 0;
+    fg[j] = 1; fw[j] = 0.0;
 #pragma unroll
-    for (int p = 0; p < FRAG; ++p) { fq[j][p] = 0.0; fi[j][p] = 0u; }
+    for (int p = 0; p < FRAG; ++p) { fq[j][p] = 0.0; fo[j][p] = dummy_off; }
     if (vl < Vc) {
       int r, k, g;
       if (vl < V8) { g = 8; r = n_huge + vl / 8; k = vl % 8; }
@@ -322,27 +200,24 @@ __global__ void __launch_bounds__(THREADS) em_fragment_kernel(EmArgs a) {
       else if (vl < V2) { g = 2; r = n_huge + n8 + n4 + (vl - V4) / 2; k = (vl - V4) % 2; }
       else { g = 1; r = n_huge + n8 + n4 + n2 + (vl - V2); k = 0; }
       const int len = grlen[r];
-      const int n = max(0, min(FRAG, len - FRAG * k));
-      fn[j] = n; fg[j] = g; fw[j] = gw[r];
+      n = max(0, min(FRAG, len - FRAG * k));
+      fg[j] = g; fw[j] = gw[r];
 #pragma unroll
       for (int p = 0; p < FRAG; ++p)
         if (p < n) {
           const int e = (int)gjptr[FRAG * k + p] + r;
+          const uint32_t ix = gidx[e];
           fq[j][p] = gq[e];
-          fi[j][p] = gidx[e];
+          fo[j][p] = ((ix & 0xffffu) << 3) | ((ix >> 16) << 19);
         }
     }
+    nA[j] = __reduce_max_sync(full, n);
+    gA[j] = __reduce_max_sync(full, fg[j]);
   }
   // ---- column fragments ----
-  // columns are sorted by count (desc); cols_gt(x) = #columns with more than x rows (bisection)
-  auto ccount = [&](int c) -> int { return (int)gcptr[c + 1] - (int)gcptr[c]; };
-  auto cols_gt = [&](int x) -> int {
-    int lo = 0, hi = v.ncol;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ccount(mid) > x) lo = mid + 1; else hi = mid; }
-    return lo;
-  };
-  const int b128 = cols_gt(FRAG * FRAG_MAXG_COL);               // generic (warp-strided) path
-  const int b64 = cols_gt(64), b32 = cols_gt(32), b16 = cols_gt(16), b8 = cols_gt(8), b4 = cols_gt(4);
+  const int b128 = (int)hd[H_CGT128];                           // generic (warp-strided) path
+  const int b64 = (int)hd[H_CGT64], b32 = (int)hd[H_CGT32], b16 = (int)hd[H_CGT16], b8 = (int)hd[H_CGT8],
+            b4 = (int)hd[H_CGT4];
   const int W32 = 32 * (b64 - b128), W16 = W32 + 16 * (b32 - b64), W8 = W16 + 8 * (b16 - b32);
   const int W4 = W8 + 4 * (b8 - b16), W2 = W4 + 2 * (b4 - b8), W = W2 + (v.ncol - b4);
   const int Wc = min(W, FC * THREADS);
@@ -354,14 +229,16 @@ __global__ void __launch_bounds__(THREADS) em_fragment_kernel(EmArgs a) {
   else if (Wc < W4) c_ovf = b16 + (Wc - W8) / 4;
   else if (Wc < W2) c_ovf = b8 + (Wc - W4) / 2;
   else c_ovf = b4 + (Wc - W2);
+  const bool generic_cols = b128 > 0 || c_ovf < v.ncol;
 
-  int cb[FC], cn[FC], cg[FC], cc[FC];       // first slot, #slots (<= FRAG), group size, column (-1: not leader)
-  double cpi[FC], cps0[FC], cx[FC], cth[FC];
+  int cb[FC], cn[FC], cg[FC], cc[FC];       // byte offset of the first slot, #slots (<= FRAG), group size, column (-1: not leader)
+  int nB[FC], gB[FC];
+  double cpi[FC], cps0[FC], cx[FC];
 #pragma unroll
   for (int j = 0; j < FC; ++j) {
     const int vl = tid + j * THREADS;
     cb[j] = 0; cn[j] = 0; cg[j] = 1; cc[j] = -1;
-    cpi[j] = invK; cps0[j] = 0.0; cx[j] = invK * invK; cth[j] = 0.0;
+    cpi[j] = invK; cps0[j] = 0.0; cx[j] = invK * invK;
     if (vl < Wc) {
       int c, k, g;
       if (vl < W32) { g = 32; c = b128 + vl / 32; k = vl % 32; }
@@ -371,52 +248,63 @@ __global__ void __launch_bounds__(THREADS) em_fragment_kernel(EmArgs a) {
       else if (vl < W2) { g = 2; c = b8 + (vl - W4) / 2; k = (vl - W4) % 2; }
       else { g = 1; c = b4 + (vl - W2); k = 0; }
       const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
-      cb[j] = b + FRAG * k;
+      cb[j] = 8 * (b + FRAG * k);
       cn[j] = max(0, min(FRAG, n - FRAG * k));
       cg[j] = g;
       cc[j] = k == 0 ? c : -1;
       cps0[j] = has_uniq ? ps0[c] : 0.0;
     }
+    nB[j] = __reduce_max_sync(full, cn[j]);
+    gB[j] = __reduce_max_sync(full, cg[j]);
   }
   __syncthreads();
 
-  double* pt_cur = s.pt;
-  double* pt_nxt = s.pt2;
+  double* pt_cur = pt;
+  double* pt_nxt = pt2;
+  unsigned char* const vb = reinterpret_cast<unsigned char*>(val);
   double lnl_prev = INFINITY, lnl_amb = 0.0;
   double finv[FR];                           // 1 / row sum of the last E-step (likelihood mode)
   int it = 0, par = 0;
   bool done = false, conv = false;
   while (!done) {
     ++it;
-    // ---- phase A: rows ----
+    // ---- phase A: rows.  r_i = sum_j Q_ij x_j ; val[i,j] = Q_ij w_i / r_i ----
+    const unsigned char* const xb = reinterpret_cast<const unsigned char*>(pt_cur);
 #pragma unroll
     for (int j = 0; j < FR; ++j) {
-      double acc = 0.0;
+      if (nA[j] > 0) {                                            // warp-uniform
+        double acc = 0.0;
 #pragma unroll
-      for (int p = 0; p < FRAG; ++p)
-        if (p < fn[j]) acc = fma(fq[j][p], pt_cur[fi[j][p] & 0xffffu], acc);
-      const int gmax = __reduce_max_sync(full, fg[j]);
-      acc = group_xor_sum(acc, fg[j], gmax);
-      const double inv = acc > 0.0 ? 1.0 / acc : 0.0;
-      if (LNL) finv[j] = inv;
-      const double sc = fw[j] * inv;
+        for (int p = 0; p < FRAG; ++p)
+          if (p < nA[j]) acc = fma(fq[j][p], *reinterpret_cast<const double*>(xb + (fo[j][p] & 0xffffu)), acc);
+        if (gA[j] > 1) acc = group_xor_sum(acc, fg[j], gA[j]);
+        const bool pos = acc > 0.0;
+        double inv = 1.0 / (pos ? acc : 1.0);                     // padding lanes: no 1/0 slow path
+        inv = pos ? inv : 0.0;
+        if (LNL) finv[j] = inv;
+        const double sc = fw[j] * inv;
 #pragma unroll
-      for (int p = 0; p < FRAG; ++p)
-        if (p < fn[j]) s.val[fi[j][p] >> 16] = fq[j][p] * sc;
-    }
-    for (int r = tid; r < v.nrows; r += THREADS) {               // generic rows (rare)
-      const int rr = r < n_huge ? r : r_ovf + (r - n_huge);
-      if (rr >= v.nrows) break;
-      const int len = grlen[rr];
-      double acc = 0.0;
-      for (int p = 0; p < len; ++p) {
-        const int e = (int)gjptr[p] + rr;
-        acc = fma(gq[e], pt_cur[gidx[e] & 0xffffu], acc);
+        for (int p = 0; p < FRAG; ++p)
+          if (p < nA[j]) *reinterpret_cast<double*>(vb + (fo[j][p] >> 16)) = fq[j][p] * sc;
+      } else if (LNL) {
+        finv[j] = 0.0;
       }
-      const double sc = acc > 0.0 ? gw[rr] * (1.0 / acc) : 0.0;
-      for (int p = 0; p < len; ++p) {
-        const int e = (int)gjptr[p] + rr;
-        s.val[gidx[e] >> 16] = gq[e] * sc;
+    }
+    if (generic_rows) {
+      for (int r = tid; r < v.nrows; r += THREADS) {               // rows outside the register lanes (rare)
+        const int rr = r < n_huge ? r : r_ovf + (r - n_huge);
+        if (rr >= v.nrows) break;
+        const int len = grlen[rr];
+        double acc = 0.0;
+        for (int p = 0; p < len; ++p) {
+          const int e = (int)gjptr[p] + rr;
+          acc = fma(gq[e], pt_cur[gidx[e] & 0xffffu], acc);
+        }
+        const double sc = acc > 0.0 ? gw[rr] * (1.0 / acc) : 0.0;
+        for (int p = 0; p < len; ++p) {
+          const int e = (int)gjptr[p] + rr;
+          val[gidx[e] >> 16] = gq[e] * sc;
+        }
       }
     }
     group_sync<THREADS>();
@@ -424,43 +312,49 @@ __global__ void __launch_bounds__(THREADS) em_fragment_kernel(EmArgs a) {
     double dsum = 0.0;
 #pragma unroll
     for (int j = 0; j < FC; ++j) {
-      double asum = 0.0;
+      if (nB[j] > 0) {                                            // warp-uniform
+        double asum = 0.0;
+        const unsigned char* const cp = vb + cb[j];
 #pragma unroll
-      for (int k = 0; k < FRAG; ++k)
-        if (k < cn[j]) asum += s.val[cb[j] + k];
-      const int gmax = __reduce_max_sync(full, cg[j]);
-      asum = group_xor_sum(asum, cg[j], gmax);
-      const double T = cx[j] * asum;
-      const double th = (T + thpw) * inv_thd;                 // model.py:240
-      const double pn = (cps0[j] + T + pipw) * inv_pid;       // model.py:243-244
-      if (cc[j] >= 0) {
-        dsum += fabs(pn - cpi[j]);
-        pt_nxt[cc[j]] = pn * th;
+        for (int k = 0; k < FRAG; ++k)
+          if (k < nB[j]) {
+            if (k < cn[j]) asum += *reinterpret_cast<const double*>(cp + 8 * k);
+          }
+        if (gB[j] > 1) asum = group_xor_sum(asum, cg[j], gB[j]);
+        const double T = cx[j] * asum;
+        const double th = (T + thpw) * inv_thd;                 // model.py:240
+        const double pn = (cps0[j] + T + pipw) * inv_pid;       // model.py:243-244
+        const double xn = pn * th;
+        if (cc[j] >= 0) {
+          dsum += fabs(pn - cpi[j]);
+          pt_nxt[cc[j]] = xn;
+        }
+        cpi[j] = pn;
+        cx[j] = xn;
       }
-      cpi[j] = pn;
-      cth[j] = th;
-      cx[j] = pn * th;
     }
-    for (int c = warp; c < b128; c += NW) {                     // very long columns: one warp each
-      const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
-      const double asum = col_sum_warp(s.val, b, n, lane);
-      if (lane == 0) {
-        const double T = pt_cur[c] * asum;
+    if (generic_cols) {
+      for (int c = warp; c < b128; c += NW) {                     // very long columns: one warp each
+        const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
+        const double asum = col_sum_warp(val, b, n, lane);
+        if (lane == 0) {
+          const double T = pt_cur[c] * asum;
+          const double th = (T + thpw) * inv_thd;
+          const double pn = ((has_uniq ? ps0[c] : 0.0) + T + pipw) * inv_pid;
+          dsum += fabs(pn - aux[c]);
+          aux[c] = pn;
+          pt_nxt[c] = pn * th;
+        }
+      }
+      for (int c = c_ovf + tid; c < v.ncol; c += THREADS) {       // columns beyond the register lanes
+        const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
+        const double T = pt_cur[c] * col_sum_thread(val, b, n);
         const double th = (T + thpw) * inv_thd;
         const double pn = ((has_uniq ? ps0[c] : 0.0) + T + pipw) * inv_pid;
-        dsum += fabs(pn - s.aux[c]);
-        s.aux[c] = pn;
+        dsum += fabs(pn - aux[c]);
+        aux[c] = pn;
         pt_nxt[c] = pn * th;
       }
-    }
-    for (int c = c_ovf + tid; c < v.ncol; c += THREADS) {       // columns beyond the register lanes
-      const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
-      const double T = pt_cur[c] * col_sum_thread(s.val, b, n);
-      const double th = (T + thpw) * inv_thd;
-      const double pn = ((has_uniq ? ps0[c] : 0.0) + T + pipw) * inv_pid;
-      dsum += fabs(pn - s.aux[c]);
-      s.aux[c] = pn;
-      pt_nxt[c] = pn * th;
     }
     double diff = block_sum<THREADS>(dsum, s_red, par++);     // barrier: publishes pt_nxt / aux
     if (it == 1) diff += diff1_extra;
@@ -474,28 +368,30 @@ __global__ void __launch_bounds__(THREADS) em_fragment_kernel(EmArgs a) {
       for (int j = 0; j < FR; ++j)
 #pragma unroll
         for (int p = 0; p < FRAG; ++p)
-          if (p < fn[j]) {
-            const int c = fi[j][p] & 0xffffu;
+          if (p < nA[j]) {
+            const int c = (fo[j][p] & 0xffffu) >> 3;
             const double z = (fq[j][p] * pt_cur[c]) * finv[j];
             const double pn = pt_nxt[c];
             if (z > 0.0 && pn > 0.0) l = fma(z, log(fq[j][p] * pn), l);
           }
-      for (int r = tid; r < v.nrows; r += THREADS) {
-        const int rr = r < n_huge ? r : r_ovf + (r - n_huge);
-        if (rr >= v.nrows) break;
-        const int len = grlen[rr];
-        double acc = 0.0;
-        for (int p = 0; p < len; ++p) {
-          const int e = (int)gjptr[p] + rr;
-          acc = fma(gq[e], pt_cur[gidx[e] & 0xffffu], acc);
-        }
-        const double inv = acc > 0.0 ? 1.0 / acc : 0.0;
-        for (int p = 0; p < len; ++p) {
-          const int e = (int)gjptr[p] + rr;
-          const int c = gidx[e] & 0xffffu;
-          const double z = (gq[e] * pt_cur[c]) * inv;
-          const double pn = pt_nxt[c];
-          if (z > 0.0 && pn > 0.0) l = fma(z, log(gq[e] * pn), l);
+      if (generic_rows) {
+        for (int r = tid; r < v.nrows; r += THREADS) {
+          const int rr = r < n_huge ? r : r_ovf + (r - n_huge);
+          if (rr >= v.nrows) break;
+          const int len = grlen[rr];
+          double acc = 0.0;
+          for (int p = 0; p < len; ++p) {
+            const int e = (int)gjptr[p] + rr;
+            acc = fma(gq[e], pt_cur[gidx[e] & 0xffffu], acc);
+          }
+          const double inv = acc > 0.0 ? 1.0 / acc : 0.0;
+          for (int p = 0; p < len; ++p) {
+            const int e = (int)gjptr[p] + rr;
+            const int c = gidx[e] & 0xffffu;
+            const double z = (gq[e] * pt_cur[c]) * inv;
+            const double pn = pt_nxt[c];
+            if (z > 0.0 && pn > 0.0) l = fma(z, log(gq[e] * pn), l);
+          }
         }
       }
       if (has_uniq) {
@@ -506,10 +402,10 @@ __global__ void __launch_bounds__(THREADS) em_fragment_kernel(EmArgs a) {
             if (nu > 0 && cpi[j] > 0.0) l += (double)nu * log(cpi[j]);
           }
         for (int c = warp; c < b128; c += NW)
-          if (lane == 0) { const int nu = nuq[c]; if (nu > 0 && s.aux[c] > 0.0) l += (double)nu * log(s.aux[c]); }
+          if (lane == 0) { const int nu = nuq[c]; if (nu > 0 && aux[c] > 0.0) l += (double)nu * log(aux[c]); }
         for (int c = c_ovf + tid; c < v.ncol; c += THREADS) {
           const int nu = nuq[c];
-          if (nu > 0 && s.aux[c] > 0.0) l += (double)nu * log(s.aux[c]);
+          if (nu > 0 && aux[c] > 0.0) l += (double)nu * log(aux[c]);
         }
       }
       lnl_amb = block_sum<THREADS>(l, s_red, par++);
@@ -523,27 +419,41 @@ __global__ void __launch_bounds__(THREADS) em_fragment_kernel(EmArgs a) {
     if (!done) { double* tmp = pt_cur; pt_cur = pt_nxt; pt_nxt = tmp; }
   }
   // ---- converged / reached max: publish parameters, final lnL ----
-  // pt_cur = x of the last E-step (tl.z belongs to it), pt_nxt = final x.
+  // pt_cur = x of the last E-step (tl.z belongs to it), pt_nxt = final x; `val` still holds the last E-step.
+  // theta' = x'/pi' would lose the last bit: redo the column sum exactly like the last iteration did
 #pragma unroll
-  for (int j = 0; j < FC; ++j)
-    if (cc[j] >= 0) {
-      const int slot = scol[cc[j]];
-      a.F.sc_pi[slot] = cpi[j];
-      a.F.sc_theta[slot] = cth[j];
-      s.aux[cc[j]] = cpi[j];
-    }
-  for (int c = warp; c < b128; c += NW) {
-    const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
-    const double asum = col_sum_warp(s.val, b, n, lane);      // same tree as the iteration
-    if (lane == 0) {
-      a.F.sc_pi[scol[c]] = s.aux[c];
-      a.F.sc_theta[scol[c]] = (pt_cur[c] * asum + thpw) * inv_thd;
+  for (int j = 0; j < FC; ++j) {
+    if (nB[j] > 0) {
+      double asum = 0.0;
+      const unsigned char* const cp = vb + cb[j];
+#pragma unroll
+      for (int k = 0; k < FRAG; ++k)
+        if (k < nB[j]) {
+          if (k < cn[j]) asum += *reinterpret_cast<const double*>(cp + 8 * k);
+        }
+      if (gB[j] > 1) asum = group_xor_sum(asum, cg[j], gB[j]);
+      if (cc[j] >= 0) {
+        const int slot = scol[cc[j]];
+        a.F.sc_pi[slot] = cpi[j];
+        a.F.sc_theta[slot] = (pt_cur[cc[j]] * asum + thpw) * inv_thd;
+        aux[cc[j]] = cpi[j];
+      }
     }
   }
-  for (int c = c_ovf + tid; c < v.ncol; c += THREADS) {
-    const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
-    a.F.sc_pi[scol[c]] = s.aux[c];
-    a.F.sc_theta[scol[c]] = (pt_cur[c] * col_sum_thread(s.val, b, n) + thpw) * inv_thd;
+  if (generic_cols) {
+    for (int c = warp; c < b128; c += NW) {
+      const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
+      const double asum = col_sum_warp(val, b, n, lane);      // same tree as the iteration
+      if (lane == 0) {
+        a.F.sc_pi[scol[c]] = aux[c];
+        a.F.sc_theta[scol[c]] = (pt_cur[c] * asum + thpw) * inv_thd;
+      }
+    }
+    for (int c = c_ovf + tid; c < v.ncol; c += THREADS) {
+      const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
+      a.F.sc_pi[scol[c]] = aux[c];
+      a.F.sc_theta[scol[c]] = (pt_cur[c] * col_sum_thread(val, b, n) + thpw) * inv_thd;
+    }
   }
   for (int c = tid; c < v.ncol; c += THREADS) {
     a.F.sc_ptprev[scol[c]] = pt_cur[c];
@@ -576,7 +486,7 @@ __global__ void __launch_bounds__(THREADS) em_fragment_kernel(EmArgs a) {
     if (has_uniq)
       for (int c = tid; c < v.ncol; c += THREADS) {
         const int nu = nuq[c];
-        const double pn = s.aux[c];
+        const double pn = aux[c];
         if (nu > 0 && pn > 0.0) lu += (double)nu * log(pn);
       }
     lu = block_sum<THREADS>(lu, s_red, par++);
@@ -1078,36 +988,17 @@ void free_fit(ss_handle_s* h) {
 }
 
 
-template <int THREADS>
-static cudaError_t launch_resident(ss_handle_s* h, cudaStream_t st, const EmArgs& a, int n, size_t smem, bool lnl) {
-  if (n == 0) return cudaSuccess;
-  cudaError_t e;
-  if (lnl) {
-    auto fn = em_resident_kernel<THREADS, true>;
-    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    fn<<<n, THREADS, smem, st>>>(a);
-  } else {
-    auto fn = em_resident_kernel<THREADS, false>;
-    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    fn<<<n, THREADS, smem, st>>>(a);
-  }
-  h->launches++;
-  return cudaGetLastError();
-}
-
 template <int THREADS, int FR, int FC>
-static cudaError_t launch_fragment(ss_handle_s* h, cudaStream_t st, const EmArgs& a, int n, size_t smem, bool lnl) {
+static cudaError_t launch_lane(ss_handle_s* h, cudaStream_t st, const EmArgs& a, int n, size_t smem, bool lnl) {
   if (n == 0) return cudaSuccess;
   cudaError_t e;
   if (lnl) {
-    auto fn = em_fragment_kernel<THREADS, true, FR, FC>;
+    auto fn = em_lane_kernel<THREADS, true, FR, FC>;
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     fn<<<n, THREADS, smem, st>>>(a);
   } else {
-    auto fn = em_fragment_kernel<THREADS, false, FR, FC>;
+    auto fn = em_lane_kernel<THREADS, false, FR, FC>;
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     fn<<<n, THREADS, smem, st>>>(a);
@@ -1306,12 +1197,12 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     const size_t smem = h->cls_smem[c];
     cudaError_t e = cudaSuccess;
     switch (c) {
-      case 0: e = launch_resident<32>(h, sx, a, h->cls_count[c], smem, lnl); break;
-      case 1: e = launch_resident<64>(h, sx, a, h->cls_count[c], smem, lnl); break;
-      case 2: e = launch_resident<128>(h, sx, a, h->cls_count[c], smem, lnl); break;
-      case 3: e = launch_resident<256>(h, sx, a, h->cls_count[c], smem, lnl); break;
-      case 4: e = launch_resident<512>(h, sx, a, h->cls_count[c], smem, lnl); break;
-      default: e = launch_fragment<1024, SS_FR, SS_FC>(h, sx, a, h->cls_count[c], smem, lnl); break;
+      case 0: e = launch_lane<32, SS_FR, SS_FC>(h, sx, a, h->cls_count[c], smem, lnl); break;
+      case 1: e = launch_lane<64, SS_FR, SS_FC>(h, sx, a, h->cls_count[c], smem, lnl); break;
+      case 2: e = launch_lane<128, SS_FR, SS_FC>(h, sx, a, h->cls_count[c], smem, lnl); break;
+      case 3: e = launch_lane<256, SS_FR, SS_FC>(h, sx, a, h->cls_count[c], smem, lnl); break;
+      case 4: e = launch_lane<512, SS_FR, SS_FC>(h, sx, a, h->cls_count[c], smem, lnl); break;
+      default: e = launch_lane<1024, SS_FR_BIG, SS_FC_BIG>(h, sx, a, h->cls_count[c], smem, lnl); break;
     }
     SS_CUDA_CHECK(h, e);
     if (h->timing) SS_CUDA_CHECK(h, cudaEventRecord(h->tev_e[c], sx));

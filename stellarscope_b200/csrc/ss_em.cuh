@@ -121,6 +121,11 @@ __device__ __forceinline__ void tile_phase_a(const TileView& v, const TileSmem& 
   }
 }
 
+// shared memory of the lane kernel: scratch (+ one padding line), x ping-pong, pi
+__host__ __device__ inline size_t lane_smem_bytes(int nent, int ncol) {
+  return 8 * ((size_t)pad8(nent) + 8 + 3 * (size_t)pad8(ncol + 1));
+}
+
 // phase B helper: sum of the column-major slots [b, b+n) of a tile column, by one thread
 __device__ __forceinline__ double col_sum_thread(const double* __restrict__ val, int b, int n) {
   const double* p = val + b;

@@ -8,8 +8,11 @@
 
 constexpr int SS_NUM_CLASSES = 6;
 constexpr int SS_NUM_AUX_STREAMS = SS_NUM_CLASSES + 1 + 7;   // size classes, streaming kernel, cluster sizes 2..8
-constexpr int SS_FR = 2;   // row fragments held in registers per thread (resident kernel)
-constexpr int SS_FC = 2;   // column fragments per thread
+// lane kernel: row / column fragments (of <= 4 alignments) held in registers per thread; the
+// 1024-thread class has half the registers per thread
+constexpr int SS_FR = 2, SS_FC = 4;
+constexpr int SS_FR_BIG = 2, SS_FC_BIG = 2;
+constexpr int SS_CLS_THREADS[SS_NUM_CLASSES] = {32, 64, 128, 256, 512, 1024};
 constexpr int SS_DN_MAXW = 8;   // ranks of a row-sharded (dense) fit: the GPUs of one NVSwitch domain
 constexpr int SS_DN_TAIL = 8;   // scalar slots behind the K columns of an exchange buffer ([0] = lnL part)
 

@@ -11,10 +11,6 @@ namespace ss {
 
 thread_local cudaStream_t tl_alloc_stream = nullptr;
 
-static size_t frag_smem_bytes_host(int nent, int ncol) {
-  return 8 * ((size_t)pad8(nent) + 3 * (size_t)pad8(ncol + 1));
-}
-
 void free_layout(ss_handle_s* h) {
   dev_free_all(h->layout_allocs);
   h->L = Layout();
@@ -135,8 +131,6 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
   Layout& L = h->L;
   auto& pool = h->layout_allocs;
   const int T = L.n_tiles;
-  // CTAs per SM by class: 32, 16, 8, 4, 2, 1 (228 KB per SM, 1 KB reserved per CTA, ~0.6 KB static)
-  static const size_t CLS_LIMIT[SS_NUM_CLASSES] = {5632, 12800, 27136, 56320, 114688, (size_t)-1};
   std::vector<int> cls[SS_NUM_CLASSES], stream, all(T);
   std::iota(all.begin(), all.end(), 0);
   size_t all_smem = 0;
@@ -183,11 +177,14 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
       return SS_ERR_CAPACITY;
     }
     if (h->seg_ntiles_host[seg] == 1) {
+      // lane kernel: the smallest CTA whose lanes hold all row / column fragments in registers
+      const long long rfrag = hd[H_RFRAG], cfrag = hd[H_CFRAG];
       int c = 0;
-      while (b0 > CLS_LIMIT[c]) ++c;
+      while (c < SS_NUM_CLASSES - 1 &&
+             (rfrag > (long long)SS_FR * SS_CLS_THREADS[c] || cfrag > (long long)SS_FC * SS_CLS_THREADS[c]))
+        ++c;
       cls[c].push_back(t);
-      // the largest class runs the fragment kernel (tile data in registers, less shared memory)
-      h->cls_smem[c] = std::max(h->cls_smem[c], c == SS_NUM_CLASSES - 1 ? frag_smem_bytes_host(nent, ncol) : b0);
+      h->cls_smem[c] = std::max(h->cls_smem[c], lane_smem_bytes(nent, ncol));
     } else if (seg_clustered[seg]) {
       cluster_tiles.push_back(t);
     } else {

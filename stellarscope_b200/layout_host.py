@@ -35,6 +35,7 @@ ALIGN = 8            # every per-tile slice starts at a multiple of 8 elements
 
 
 FRAG, FRAG_MAXG_ROW, FRAG_MAXG_COL = 4, 8, 32     # csrc/ss_common.cuh
+HDR_WORDS = 24       # int64 words per tile header (csrc/ss_common.cuh)
 
 
 def frag_group(n):
@@ -59,8 +60,9 @@ class HostLayout:
     n_tiles: int
     chunk: int
     maxlen: int
-    # tile headers (int64 [n_tiles, 12]): seg, nrows, nent, ncol, maxlen, nlong, ent_off, row_off, col_off, jds_off,
-    # rfrag, cfrag (lanes the rows / columns occupy in the fragment kernel; longer ones excluded)
+    # tile headers (int64 [n_tiles, 24]): seg, nrows, nent, ncol, maxlen, nlong, ent_off, row_off, col_off, jds_off,
+    # rfrag, cfrag (lanes the rows / columns occupy in the lane kernel; longer ones excluded),
+    # rows longer than 4/8/16/32, columns with more than 4/8/16/32/64/128 rows, 2 spare words
     tile_hdr: np.ndarray
     # entry arrays
     e_lcol: np.ndarray   # u16
@@ -191,7 +193,7 @@ def build(indptr, indices, scores, row_seg, S, K, e_hard=E_HARD, long_col=32):
     n_tiles = int(seg_ntiles.sum())
     rtile = seg_tile0[aseg] + tin if len(ar) else np.zeros(0, dtype=np.int64)
 
-    hdr = np.zeros((n_tiles, 12), dtype=np.int64)
+    hdr = np.zeros((n_tiles, HDR_WORDS), dtype=np.int64)
     sc_inamb = np.zeros(len(ukey), dtype=np.int8)
     ent_off = row_off = col_off = jds_off = 0
     E_l, P_l, Q_l, O_l = [], [], [], []
@@ -236,7 +238,13 @@ def build(indptr, indices, scores, row_seg, S, K, e_hard=E_HARD, long_col=32):
         sc_inamb[slot] = 1
         rfrag = int(sum(frag_group(int(x)) for x in rl if x <= FRAG * FRAG_MAXG_ROW))
         cfrag = int(sum(frag_group(int(x)) for x in ccs if x <= FRAG * FRAG_MAXG_COL))
-        hdr[t] = (s, nrows, nent, len(ug), ml, nlong, ent_off, row_off, col_off, jds_off, rfrag, cfrag)
+        # number of rows longer than 4/8/16/32 alignments, of columns with more than 4..128 rows
+        # (lane-group boundaries of the lane kernel, csrc/ss_em.cu)
+        rgt = [int((rl > x).sum()) for x in (4, 8, 16, 32)]
+        cgt = [int((ccs > x).sum()) for x in (4, 8, 16, 32, 64, 128)]
+        hdr[t, :12] = (s, nrows, nent, len(ug), ml, nlong, ent_off, row_off, col_off, jds_off, rfrag, cfrag)
+        hdr[t, 12:16] = rgt
+        hdr[t, 16:22] = cgt
 
         def padded(x, n, dtype):
             out = np.zeros(n, dtype=dtype); out[:len(x)] = x; return out

@@ -31,7 +31,8 @@ def test_layout_spec_roundtrip():
     lens = np.diff(d.indptr)
     seen = np.zeros(d.A, dtype=int)
     for t in range(hl.n_tiles):
-        seg, nrows, nent, ncol, maxlen, nlong, eo_, ro, co, jo, rfrag, cfrag = hl.tile_hdr[t]
+        seg, nrows, nent, ncol, maxlen, nlong, eo_, ro, co, jo, rfrag, cfrag = hl.tile_hdr[t][:12]
+        rgt, cgt = hl.tile_hdr[t][12:16], hl.tile_hdr[t][16:22]
         assert nent <= layout_host.E_HARD
         rl = hl.r_len[ro:ro + nrows].astype(int)
         assert np.all(np.diff(rl) <= 0) and rl[0] == maxlen and rl.sum() == nent
@@ -40,6 +41,8 @@ def test_layout_spec_roundtrip():
         assert jp[0] == 0 and jp[-1] == nent and cp[0] == 0 and cp[-1] == nent
         cnt = np.diff(cp)
         assert np.all(np.diff(cnt) <= 0) and (cnt > 32).sum() == nlong
+        assert rgt.tolist() == [(rl > x).sum() for x in (4, 8, 16, 32)]
+        assert cgt.tolist() == [(cnt > x).sum() for x in (4, 8, 16, 32, 64, 128)]
         opos = hl.e_opos[eo_:eo_ + nent]
         seen[opos] += 1
         lcol = hl.e_lcol[eo_:eo_ + nent].astype(int)
