@@ -38,6 +38,7 @@ sys.path.insert(0, ROOT)
 METRIC = 'alignments_x_em_iterations_per_sec'
 UNIT = 'aln*iter/s'
 WORKLOAD = dict(n_cells=10_000, n_alignments=5_000_000, n_loci=28_000)
+CPU_SAMPLE_CELLS = 4000      # cells of the workload the CPU baseline fits (about 10-20 s on 16 cores)
 OPTS = dict(em_epsilon=1e-7, max_iter=100, pi_prior=0, theta_prior=200000)   # stellarscope_assign.yaml:231-250
 
 
@@ -182,7 +183,7 @@ def run_reference(args):
         return 0
     cores = os.cpu_count() or 1
     d = make_workload(seed=0, scale=0.1)            # the sample is drawn from a 1/10 replica (same per-cell sizes)
-    n_sample = 64 * cores
+    n_sample = 1000
     for _ in range(args.warmup):
         cpu_sample_rate(d, cores, cores, seed=99)
     rates, tot_units, tot_dt = [], 0, 0.0
@@ -234,11 +235,13 @@ def run_ours(args):
     # ---- resident-input path: matrix in HBM, layout built on device, timed region = the fit ----
     eng = Engine(local)
     eng.set_matrix(d.indptr, d.indices, d.scores, d.K)
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    eng.build_layout(d.row_cell, d.n_cells)
-    torch.cuda.synchronize(dev)
-    build_ms = 1e3 * (time.perf_counter() - t0)
+    build_ms = None
+    for _ in range(2):                         # the first build pays for the memory pool; report the second
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        eng.build_layout(d.row_cell, d.n_cells)
+        torch.cuda.synchronize(dev)
+        build_ms = 1e3 * (time.perf_counter() - t0)
     info = eng.layout_info()
     eng.enable_timing(True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -322,7 +325,7 @@ def run_ours(args):
         em_ms = groups['em']                      # all fused E+M kernels of one fit (they run concurrently)
         achieved = alg_bytes_all / (em_ms / 1e3) / 1e9 if em_ms > 0 else 0.0
         cores = os.cpu_count() or 1
-        cpu_rate, cpu_units, cpu_dt, cpu_n = cpu_sample_rate(d, 64 * cores, cores, seed=1)
+        cpu_rate, cpu_units, cpu_dt, cpu_n = cpu_sample_rate(d, CPU_SAMPLE_CELLS, cores, seed=1)
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=tmax_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
@@ -340,8 +343,8 @@ def run_ours(args):
             gpu_launches=int(launches_all),
             roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
                           traffic=None,
-                          kernel='fused E+M kernels of one fit: em_resident_kernel (6 size classes) + '
-                                 'em_fragment_kernel + em_cluster_kernel, launched concurrently',
+                          kernel='fused E+M kernels of one fit: em_lane_kernel (one launch per CTA-size class) + '
+                                 'em_cluster_kernel (cells of 2..8 tiles), launched concurrently',
                           note='EFFECTIVE bandwidth: algorithmic bytes = iterations x (12 B/ambiguous alignment + '
                                '4 B/row + 16 B/active column), SURVEY.md 8d; every model is read from HBM once and '
                                'iterated out of shared memory / registers, so this is not DRAM traffic (see profiles/ '

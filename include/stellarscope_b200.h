@@ -197,9 +197,11 @@ int64_t ss_launch_count(ss_handle_t h);
 /* Measurement aid (bench.py): when enabled, ss_em_fit brackets its kernel groups with CUDA
  * events; ss_get_timings synchronises on them and returns the device time in ms of the last
  * fit: [0] prepare, [1] all EM kernels (they run concurrently), [2] unused, [3] emit,
- * [4] finalize, [5..10] span of the resident kernel of size class 0..5 (32..1024 threads),
- * [11] span of the streaming kernel, [12..18] span of the cluster kernels for segments of
- * 2..8 tiles.  n >= 12. */
+ * [4] finalize, then the span of each concurrent EM kernel: [5 .. 5+C-1] the lane kernel of
+ * size class 0..C-1 (C = ss_lane_classes), [5+C] the streaming kernel, [5+C+1 .. 5+C+7] the
+ * cluster kernels for segments of 2..8 tiles.  n >= 5 + C + 8.
+ * ss_lane_classes: CTA sizes (threads) of the lane-kernel size classes; returns C. */
+int ss_lane_classes(int32_t* threads, int32_t cap);
 int ss_set_timing(ss_handle_t h, int32_t enabled);
 int ss_get_timings(ss_handle_t h, double* ms, int32_t n);
 

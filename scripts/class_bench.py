@@ -24,7 +24,7 @@ for sz in sizes:
     res = eng.results(traces=False)
     segA = eng.export_layout_array('seg_A', np.int64)
     units = float((segA * res['iters']).sum())
-    cls = {k: round(v, 3) for k, v in best.items() if k.startswith('resident') and v > 0 or k == 'stream' and v > 0}
+    cls = {k: round(v, 3) for k, v in best.items() if k.startswith('lane') and v > 0 or k == 'stream' and v > 0}
     print(f'size {sz:5d} cells {n_cells:6d} tiles {info["n_tiles"]} stream_tiles {info["n_stream_tiles"]} '
           f'mean_iters {res["iters"].mean():.1f} em_ms {best["em"]:.3f} rate {units / best["em"] / 1e6:.1f} G/s  {cls}', flush=True)
     eng.close()

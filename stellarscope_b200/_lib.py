@@ -85,6 +85,7 @@ SIGNATURES = {
     'ss_set_peers': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int64]),
     'ss_em_get_dense_params': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'ss_launch_count': (C.c_int64, [C.c_void_p]),
+    'ss_lane_classes': (C.c_int, [c_i32p, C.c_int32]),
     'ss_set_timing': (C.c_int, [C.c_void_p, C.c_int32]),
     'ss_get_timings': (C.c_int, [C.c_void_p, c_f64p, C.c_int32]),
 }

@@ -337,6 +337,11 @@ int ss_em_get_dense_params(ss_handle_t h, void* stream, double* pi, double* thet
 
 int64_t ss_launch_count(ss_handle_t h) { return h ? h->launches : 0; }
 
+int ss_lane_classes(int32_t* threads, int32_t cap) {
+  for (int i = 0; i < SS_NUM_CLASSES && i < cap; ++i) threads[i] = SS_CLS_THREADS[i];
+  return SS_NUM_CLASSES;
+}
+
 int ss_set_timing(ss_handle_t h, int32_t enabled) {
   SS_REQUIRE_HANDLE(h);
   cudaSetDevice(h->device);
@@ -353,7 +358,7 @@ int ss_set_timing(ss_handle_t h, int32_t enabled) {
 
 int ss_get_timings(ss_handle_t h, double* ms, int32_t n) {
   SS_REQUIRE_HANDLE(h);
-  if (!ms || n < 12 || !h->ev_valid) {
+  if (!ms || n < 5 + SS_NUM_AUX_STREAMS || !h->ev_valid) {
     h->set_error("ss_get_timings: timing not enabled / no fit / buffer too small");
     return SS_ERR_STATE;
   }

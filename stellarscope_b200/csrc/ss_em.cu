@@ -122,11 +122,34 @@ __device__ __forceinline__ double group_xor_sum(double a, int g, int gmax) {
   return a;
 }
 
-template <int THREADS, bool LNL, int FR, int FC>
-__global__ void __launch_bounds__(THREADS) em_lane_kernel(EmArgs a) {
+// deterministic block sum for a run-time number of warps (every thread returns the same value;
+// one barrier, which also publishes the caller's preceding shared-memory writes).  `red` holds
+// 2 x 32 doubles; callers alternate `par`.
+__device__ __forceinline__ double lane_block_sum(double v, int nw, double* red, int par) {
+  v = warp_sum(v);
+  if (nw == 1) {
+    __syncwarp();
+    return v;
+  }
+  const int lane = threadIdx.x & 31;
+  double* r = red + 32 * (par & 1);
+  if (lane == 0) r[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = lane < nw ? r[lane] : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    if (o < nw) t += __shfl_xor_sync(0xffffffffu, t, o);        // nw is block-uniform; lanes >= nw hold 0
+  return __shfl_sync(0xffffffffu, t, 0);
+}
+
+// THREADS = blockDim.x (a multiple of 32, chosen per tile by the launch plan so that all warps
+// carry the same number of fragment slots)
+template <int TT, bool LNL, int FR, int FC, int MAXREG>
+__global__ void __maxnreg__(MAXREG) em_lane_kernel(EmArgs a) {
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double s_red[64];
-  constexpr int NW = THREADS / 32;
+  const int THREADS = TT ? TT : blockDim.x;
+  const int NW = THREADS >> 5;
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = a.tile_list[blockIdx.x];
@@ -307,7 +330,7 @@ __global__ void __launch_bounds__(THREADS) em_lane_kernel(EmArgs a) {
         }
       }
     }
-    group_sync<THREADS>();
+    if (NW == 1) __syncwarp(); else __syncthreads();
     // ---- phase B: thetasum per tile column -> theta', pi', x' = pi' theta', |delta pi| ----
     double dsum = 0.0;
 #pragma unroll
@@ -356,7 +379,7 @@ __global__ void __launch_bounds__(THREADS) em_lane_kernel(EmArgs a) {
         pt_nxt[c] = pn * th;
       }
     }
-    double diff = block_sum<THREADS>(dsum, s_red, par++);     // barrier: publishes pt_nxt / aux
+    double diff = lane_block_sum(dsum, NW, s_red, par++);     // barrier: publishes pt_nxt / aux
     if (it == 1) diff += diff1_extra;
     const bool reached = it >= max_iter;
     if (!LNL) {
@@ -408,7 +431,7 @@ __global__ void __launch_bounds__(THREADS) em_lane_kernel(EmArgs a) {
           if (nu > 0 && aux[c] > 0.0) l += (double)nu * log(aux[c]);
         }
       }
-      lnl_amb = block_sum<THREADS>(l, s_red, par++);
+      lnl_amb = lane_block_sum(l, NW, s_red, par++);
       const double lnl = lnl_amb + lnl_extra;
       conv = fabs(lnl - lnl_prev) < eps;                       // model.py:345-347
       lnl_prev = lnl;
@@ -478,10 +501,10 @@ __global__ void __launch_bounds__(THREADS) em_lane_kernel(EmArgs a) {
         if (z > 0.0 && pn > 0.0) l = fma(z, log(gq[e] * pn), l);
       }
     }
-    l = block_sum<THREADS>(l, s_red, par++);
+    l = lane_block_sum(l, NW, s_red, par++);
   } else {
     // tile_lnl holds the ambiguous-row part only; the unique-row part is added by finalize
-    group_sync<THREADS>();
+    if (NW == 1) __syncwarp(); else __syncthreads();
     double lu = 0.0;
     if (has_uniq)
       for (int c = tid; c < v.ncol; c += THREADS) {
@@ -489,7 +512,7 @@ __global__ void __launch_bounds__(THREADS) em_lane_kernel(EmArgs a) {
         const double pn = aux[c];
         if (nu > 0 && pn > 0.0) lu += (double)nu * log(pn);
       }
-    lu = block_sum<THREADS>(lu, s_red, par++);
+    lu = lane_block_sum(lu, NW, s_red, par++);
     l = lnl_amb - lu;
   }
   if (tid == 0) {
@@ -988,20 +1011,21 @@ void free_fit(ss_handle_s* h) {
 }
 
 
-template <int THREADS, int FR, int FC>
-static cudaError_t launch_lane(ss_handle_s* h, cudaStream_t st, const EmArgs& a, int n, size_t smem, bool lnl) {
+template <int TT, int FR, int FC, int MAXREG>
+static cudaError_t launch_lane(ss_handle_s* h, cudaStream_t st, const EmArgs& a, int n, int threads, size_t smem,
+                               bool lnl) {
   if (n == 0) return cudaSuccess;
   cudaError_t e;
   if (lnl) {
-    auto fn = em_lane_kernel<THREADS, true, FR, FC>;
+    auto fn = em_lane_kernel<TT, true, FR, FC, MAXREG>;
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fn<<<n, THREADS, smem, st>>>(a);
+    fn<<<n, threads, smem, st>>>(a);
   } else {
-    auto fn = em_lane_kernel<THREADS, false, FR, FC>;
+    auto fn = em_lane_kernel<TT, false, FR, FC, MAXREG>;
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fn<<<n, THREADS, smem, st>>>(a);
+    fn<<<n, threads, smem, st>>>(a);
   }
   h->launches++;
   return cudaGetLastError();
@@ -1011,8 +1035,12 @@ static cudaError_t ensure_aux_streams(ss_handle_s* h) {
   if (h->ev_fork) return cudaSuccess;
   cudaError_t e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   if (e != cudaSuccess) return e;
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   for (int i = 0; i < SS_NUM_AUX_STREAMS; ++i) {
-    e = cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
+    // the cluster / streaming kernels have few, long-running CTAs that each need a whole SM: the
+    // block scheduler must place them before the many short CTAs of the lane kernels
+    e = cudaStreamCreateWithPriority(&h->aux[i], cudaStreamNonBlocking, i >= SS_NUM_CLASSES ? prio_hi : prio_lo);
     if (e != cudaSuccess) return e;
     e = cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
     if (e != cudaSuccess) return e;
@@ -1196,14 +1224,22 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     a.n_list = h->cls_count[c];
     const size_t smem = h->cls_smem[c];
     cudaError_t e = cudaSuccess;
-    switch (c) {
-      case 0: e = launch_lane<32, SS_FR, SS_FC>(h, sx, a, h->cls_count[c], smem, lnl); break;
-      case 1: e = launch_lane<64, SS_FR, SS_FC>(h, sx, a, h->cls_count[c], smem, lnl); break;
-      case 2: e = launch_lane<128, SS_FR, SS_FC>(h, sx, a, h->cls_count[c], smem, lnl); break;
-      case 3: e = launch_lane<256, SS_FR, SS_FC>(h, sx, a, h->cls_count[c], smem, lnl); break;
-      case 4: e = launch_lane<512, SS_FR, SS_FC>(h, sx, a, h->cls_count[c], smem, lnl); break;
-      default: e = launch_lane<1024, SS_FR_BIG, SS_FC_BIG>(h, sx, a, h->cls_count[c], smem, lnl); break;
+    // one instantiation per CTA size: a compile-time thread count is worth ~7% (index arithmetic, reduction tree)
+#define SS_LANE_CASE(T)                                                                              \
+  case T:                                                                                            \
+    e = launch_lane<T, SS_FR, SS_FC, SS_MAXREG>(h, sx, a, h->cls_count[c], T, smem, lnl);             \
+    break;
+    if (c < SS_NUM_CLASSES - 1) {
+      switch (SS_CLS_THREADS[c]) {
+        SS_LANE_CASE(32) SS_LANE_CASE(64) SS_LANE_CASE(96) SS_LANE_CASE(128) SS_LANE_CASE(160) SS_LANE_CASE(192)
+        SS_LANE_CASE(224) SS_LANE_CASE(256) SS_LANE_CASE(320) SS_LANE_CASE(384) SS_LANE_CASE(448) SS_LANE_CASE(512)
+        default: e = cudaErrorInvalidValue; break;
+      }
+    } else {
+      e = launch_lane<SS_BIG_THREADS_V, SS_FR_BIG, SS_FC_BIG, SS_MAXREG_BIG>(h, sx, a, h->cls_count[c],
+                                                                              SS_BIG_THREADS_V, smem, lnl);
     }
+#undef SS_LANE_CASE
     SS_CUDA_CHECK(h, e);
     if (h->timing) SS_CUDA_CHECK(h, cudaEventRecord(h->tev_e[c], sx));
     SS_CUDA_CHECK(h, cudaEventRecord(h->ev_join[c], sx));

@@ -6,13 +6,38 @@
 #include "../../include/stellarscope_b200.h"
 #include "ss_common.cuh"
 
-constexpr int SS_NUM_CLASSES = 6;
+// lane kernel (csrc/ss_em.cu): row / column fragments (of <= 4 alignments) held in registers per
+// thread.  Single-tile segments are binned by the smallest CTA size whose lanes hold all their
+// fragments (launch plan, ss_layout.cu); the last class (1024 threads, half the registers per
+// thread) takes the tiles that need more lanes than 512 threads offer.  The -D knobs below exist
+// for tuning runs (measured on B200, configs[1]: 128 registers beat 96 / 80 / 64, FR=2 FC=4 beat
+// 1/2, 2/2 and 4/4; the class granularity is worth ~2%).
+#ifndef SS_FR_V
+#define SS_FR_V 2
+#define SS_FC_V 4
+#define SS_MAXREG_V 128
+#endif
+#ifndef SS_FR_BIG_V
+#define SS_FR_BIG_V 2
+#define SS_FC_BIG_V 2
+#define SS_MAXREG_BIG_V 64
+#define SS_BIG_THREADS_V 1024
+#endif
+#ifndef SS_CLS_SET
+#define SS_CLS_SET 0
+#endif
+#if SS_CLS_SET == 0
+#define SS_CLS_LIST 32, 64, 96, 128, 160, 192, 224, 256, 320, 384, 448, 512
+#elif SS_CLS_SET == 1
+#define SS_CLS_LIST 32, 64, 128, 256, 512
+#else
+#define SS_CLS_LIST 32, 64, 96, 128, 192, 256, 384, 512
+#endif
+constexpr int SS_FR = SS_FR_V, SS_FC = SS_FC_V, SS_MAXREG = SS_MAXREG_V;
+constexpr int SS_FR_BIG = SS_FR_BIG_V, SS_FC_BIG = SS_FC_BIG_V, SS_MAXREG_BIG = SS_MAXREG_BIG_V;
+constexpr int SS_CLS_THREADS[] = {SS_CLS_LIST, SS_BIG_THREADS_V};
+constexpr int SS_NUM_CLASSES = (int)(sizeof(SS_CLS_THREADS) / sizeof(int));
 constexpr int SS_NUM_AUX_STREAMS = SS_NUM_CLASSES + 1 + 7;   // size classes, streaming kernel, cluster sizes 2..8
-// lane kernel: row / column fragments (of <= 4 alignments) held in registers per thread; the
-// 1024-thread class has half the registers per thread
-constexpr int SS_FR = 2, SS_FC = 4;
-constexpr int SS_FR_BIG = 2, SS_FC_BIG = 2;
-constexpr int SS_CLS_THREADS[SS_NUM_CLASSES] = {32, 64, 128, 256, 512, 1024};
 constexpr int SS_DN_MAXW = 8;   // ranks of a row-sharded (dense) fit: the GPUs of one NVSwitch domain
 constexpr int SS_DN_TAIL = 8;   // scalar slots behind the K columns of an exchange buffer ([0] = lnL part)
 

@@ -7,6 +7,10 @@
 #include "ss_em.cuh"
 #include "ss_handle.h"
 
+#ifndef SS_PLAN_RULE
+#define SS_PLAN_RULE 1     // 1: smallest CTA that holds all fragments; 0: cost model (same speed on B200)
+#endif
+
 namespace ss {
 
 thread_local cudaStream_t tl_alloc_stream = nullptr;
@@ -177,12 +181,27 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
       return SS_ERR_CAPACITY;
     }
     if (h->seg_ntiles_host[seg] == 1) {
-      // lane kernel: the smallest CTA whose lanes hold all row / column fragments in registers
+      // lane kernel: among the CTA sizes whose lanes hold all row / column fragments in registers, the
+      // one with the smallest (warps x time per iteration): a warp's iteration costs about 50
+      // instructions per row slot, 36 per column slot and 55 of fixed overhead, and the CTA waits for
+      // its slowest warp at two barriers, so a partly filled extra slot is paid by every warp
       const long long rfrag = hd[H_RFRAG], cfrag = hd[H_CFRAG];
-      int c = 0;
-      while (c < SS_NUM_CLASSES - 1 &&
-             (rfrag > (long long)SS_FR * SS_CLS_THREADS[c] || cfrag > (long long)SS_FC * SS_CLS_THREADS[c]))
-        ++c;
+      const long long vr = (rfrag + 31) / 32, vc = (cfrag + 31) / 32;
+      int c = SS_NUM_CLASSES - 1;
+      long long best = -1;
+      for (int k = 0; k < SS_NUM_CLASSES - 1; ++k) {
+        const long long w = SS_CLS_THREADS[k] / 32;
+        const long long sr = (vr + w - 1) / w, sc = (vc + w - 1) / w;
+        if (sr > SS_FR || sc > SS_FC) continue;
+#if SS_PLAN_RULE == 0
+        const long long cost = w * (50 * sr + 36 * sc + 55);
+        if (best < 0 || cost < best) { best = cost; c = k; }
+#else
+        (void)best;
+        c = k;                       // smallest CTA whose lanes hold all fragments
+        break;
+#endif
+      }
       cls[c].push_back(t);
       h->cls_smem[c] = std::max(h->cls_smem[c], lane_smem_bytes(nent, ncol));
     } else if (seg_clustered[seg]) {

@@ -108,13 +108,16 @@ class Engine:
     def last_timings(self):
         """Device time (ms) of the kernel groups of the last ss_em_fit (synchronises):
         prepare, streaming kernel, resident kernels, emit, finalize."""
-        buf = (C.c_double * 24)()
-        self._check(self.lib.ss_get_timings(self.h, buf, 24))
-        out = {'prepare': buf[0], 'em': buf[1], 'emit': buf[3], 'finalize': buf[4], 'stream': buf[11]}
-        for i, t in enumerate((32, 64, 128, 256, 512, 1024)):
-            out[f'resident{t}'] = buf[5 + i]
-        out['resident'] = max(buf[5:11])
-        out['cluster'] = max(buf[12:19])
+        thr = (C.c_int32 * 32)()
+        nc = self.lib.ss_lane_classes(thr, 32)
+        n = 5 + nc + 8
+        buf = (C.c_double * n)()
+        self._check(self.lib.ss_get_timings(self.h, buf, n))
+        out = {'prepare': buf[0], 'em': buf[1], 'emit': buf[3], 'finalize': buf[4], 'stream': buf[5 + nc]}
+        for i in range(nc):
+            out[f'lane{i}_{thr[i]}'] = buf[5 + i]
+        out['resident'] = max(buf[5:5 + nc])
+        out['cluster'] = max(buf[5 + nc + 1:5 + nc + 8])
         return {k: float(v) for k, v in out.items()}
 
     # -- one model, rows sharded over ranks (pseudobulk; csrc/ss_dense.cu) ------------
