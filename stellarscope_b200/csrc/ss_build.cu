@@ -266,14 +266,14 @@ struct TileBuildArgs {
 // many small tiles of individual-mode cells do not pay for the shared memory of the largest
 // one; every instance is launched over all tiles and a CTA returns when the tile is not of its
 // class (ELOW < nent <= ECAP).
-template <int ECAP>
+template <int ECAP, int BT>
 constexpr size_t tile_build_smem() {
   return (size_t)ECAP * 8 * 2 + (size_t)(ECAP * 4 + 2) * 4 + (size_t)(ECAP / 2 * 2 + ECAP + 2) * 4 +
-         (size_t)(BUILD_THREADS + 1) * 4 + 64;
+         (size_t)(BT + 1) * 4 + 64;
 }
 
-template <int ECAP, int ELOW>
-__global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs a) {
+template <int ECAP, int ELOW, int BT>
+__global__ void __launch_bounds__(BT) tile_build_kernel(TileBuildArgs a) {
   extern __shared__ __align__(16) unsigned char dsm[];
   constexpr int RCAP = ECAP / 2;
   const int tid = threadIdx.x;
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
   int* rrow = cptr + ECAP + 1;                                              // RCAP  original row of JDS row r
   int* rlen = rrow + RCAP;                                                  // RCAP
   int* jptr = rlen + RCAP;                                                  // ECAP + 2 (a row may be as long as the tile)
-  int* scratch = jptr + ECAP + 2;                                           // BUILD_THREADS + 1
+  int* scratch = jptr + ECAP + 2;                                           // BT + 1
   __shared__ double s_red[32];
   const int seg = a.aseg[row0];
   const long long eo = a.ent_off[t], ro = a.row_off[t];
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
   // (a) JDS row order: (len desc, rank asc)
   const int np2 = next_pow2(nrows);
   int lmax = 0;
-  for (int r = tid; r < np2; r += BUILD_THREADS) {
+  for (int r = tid; r < np2; r += BT) {
     if (r < nrows) {
       const int row = a.ar[row0 + r];
       const int len = a.row_ptr[row + 1] - a.row_ptr[row];
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
   }
   __syncthreads();
   bitonic_sort(keys, np2);
-  for (int r = tid; r < nrows; r += BUILD_THREADS) {
+  for (int r = tid; r < nrows; r += BT) {
     const int rank = (int)(keys[r] & 0xffffffffu);
     const int len = E_HARD - (int)(keys[r] >> 32);
     rrow[r] = a.ar[row0 + rank];
@@ -318,9 +318,9 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
   __syncthreads();
   lmax = rlen[0];
   // (b) jptr[p] = sum_{p' < p} #(rows with len > p'); rows are sorted, so #(len > p) = first r with len <= p
-  for (int p = tid; p <= lmax; p += BUILD_THREADS) jptr[p] = 0;
+  for (int p = tid; p <= lmax; p += BT) jptr[p] = 0;
   __syncthreads();
-  for (int p = tid; p < lmax; p += BUILD_THREADS) {
+  for (int p = tid; p < lmax; p += BT) {
     int lo = 0, hi = nrows;                  // first r with rlen[r] <= p
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
   const double inv = 1.0 / (double)a.seg_smax[seg];
   double wsum = 0.0;
   int rfrag_local = 0;
-  for (int r = tid; r < nrows; r += BUILD_THREADS) {
+  for (int r = tid; r < nrows; r += BT) {
     const int row = rrow[r], len = rlen[r];
     if (len <= FRAG * FRAG_MAXG_ROW) rfrag_local += frag_group(len);
     const int b = a.row_ptr[row];
@@ -359,28 +359,28 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
     if ((tid & 31) == 0) s_red[tid >> 5] = v;
   }
   const int ep2 = next_pow2(nent);
-  for (int e = nent + tid; e < ep2; e += BUILD_THREADS) keys[e] = ~0ull;
+  for (int e = nent + tid; e < ep2; e += BT) keys[e] = ~0ull;
   // zero the padding of the entry / row arrays
-  for (int e = nent + tid; e < pad8(nent); e += BUILD_THREADS) {
+  for (int e = nent + tid; e < pad8(nent); e += BT) {
     a.e_q[eo + e] = 0.0; a.e_idx[eo + e] = 0u; a.e_opos[eo + e] = 0;
   }
-  for (int r = nrows + tid; r < pad8(nrows); r += BUILD_THREADS) {
+  for (int r = nrows + tid; r < pad8(nrows); r += BT) {
     a.r_len[ro + r] = 0; a.r_w[ro + r] = 0.0; a.r_orow[ro + r] = 0;
   }
   __syncthreads();
   if (tid == 0) {
     double tsum = 0.0;
-    for (int i = 0; i < BUILD_THREADS / 32; ++i) tsum += s_red[i];
+    for (int i = 0; i < BT / 32; ++i) tsum += s_red[i];
     a.t_wsum[t] = tsum;
   }
   // (d) tile columns: sort by (locus, JDS row)
   bitonic_sort(keys, ep2);
-  for (int i = tid; i < nent; i += BUILD_THREADS)
+  for (int i = tid; i < nent; i += BT)
     colidx[i] = (i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32)) ? 1 : 0;
   __syncthreads();
   const int ncol = block_excl_scan(colidx, nent, scratch);   // colidx[i] = (#heads before i); head i has the column index
   // the scan is exclusive: column of entry i = colidx[i] + head(i) - 1 -> recompute head
-  for (int i = tid; i < nent; i += BUILD_THREADS) {
+  for (int i = tid; i < nent; i += BT) {
     const bool head = (i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32));
     const int ci = colidx[i] + (head ? 1 : 0) - 1;
     colidx[i] = ci;
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
   __syncthreads();
   // order columns by (count desc, locus asc)
   const int cp2 = next_pow2(ncol);
-  for (int c = tid; c < cp2; c += BUILD_THREADS) {
+  for (int c = tid; c < cp2; c += BT) {
     if (c < ncol) {
       const int cnt = colstart[c + 1] - colstart[c];
       const unsigned long long g = keys[colstart[c]] >> 32;
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
   bitonic_sort(ckeys, cp2);
   int nlong_local = 0;
   const long long co_tmp = eo + 8LL * t;
-  for (int lc = tid; lc < ncol; lc += BUILD_THREADS) {
+  for (int lc = tid; lc < ncol; lc += BT) {
     const int c = (int)(ckeys[lc] & 0xffffu);
     const int cnt = E_HARD - (int)(ckeys[lc] >> 48);
     rank_of[c] = lc;
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
   if (tid == 0) cptr[ncol] = 0;
   __syncthreads();
   block_excl_scan(cptr, ncol + 1, scratch);     // cptr[ncol] = nent
-  for (int i = tid; i < nent; i += BUILD_THREADS) {
+  for (int i = tid; i < nent; i += BT) {
     const int ci = colidx[i];
     const int lc = rank_of[ci];
     const int e = (int)(keys[i] & 0xffffu);
@@ -433,8 +433,8 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
     }
     a.t_gt[10 * t + tid] = lo;
   }
-  for (int lc = tid; lc <= ncol; lc += BUILD_THREADS) a.tmp_cptr[co_tmp + lc] = (uint16_t)cptr[lc];
-  for (int p = tid; p <= lmax; p += BUILD_THREADS) a.tmp_jptr[(long long)a.jds_stride * t + p] = (uint16_t)jptr[p];
+  for (int lc = tid; lc <= ncol; lc += BT) a.tmp_cptr[co_tmp + lc] = (uint16_t)cptr[lc];
+  for (int p = tid; p <= lmax; p += BT) a.tmp_jptr[(long long)a.jds_stride * t + p] = (uint16_t)jptr[p];
   // number of long columns / column fragments / row fragments: block reduce
   {
     int vr = rfrag_local;
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
     if ((tid & 31) == 0) scratch[tid >> 5] = vr;
     __syncthreads();
     int rtot = 0;
-    for (int i = 0; i < BUILD_THREADS / 32; ++i) rtot += scratch[i];
+    for (int i = 0; i < BT / 32; ++i) rtot += scratch[i];
     int v = nlong_local;
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) tile_build_kernel(TileBuildArgs
     __syncthreads();
     if (tid == 0) {
       int tot = 0;
-      for (int i = 0; i < BUILD_THREADS / 32; ++i) tot += scratch[i];
+      for (int i = 0; i < BT / 32; ++i) tot += scratch[i];
       a.t_nlong[t] = tot & 0xffff;
       a.t_cfrag[t] = tot >> 16;
       a.t_rfrag[t] = rtot;
@@ -840,18 +840,18 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
     a.tmp_cptr = tmp_cptr; a.tmp_gcol = tmp_gcol; a.tmp_jptr = tmp_jptr; a.jds_stride = jds_stride;
     a.t_ncol = t_ncol; a.t_maxlen = t_maxlen; a.t_nlong = t_nlong; a.t_seg = t_seg; a.t_nrows = t_nrows;
     a.t_nent = t_nent; a.t_wsum = t_wsum; a.t_rfrag = t_rfrag; a.t_cfrag = t_cfrag; a.t_gt = t_gt;
-#define SS_TILE_BUILD(ECAP, ELOW)                                                                         \
+#define SS_TILE_BUILD(ECAP, ELOW, BT)                                                                     \
   do {                                                                                                    \
-    constexpr size_t smem = tile_build_smem<ECAP>();                                                      \
-    SS_CUDA_CHECK(h, cudaFuncSetAttribute(tile_build_kernel<ECAP, ELOW>,                                  \
+    constexpr size_t smem = tile_build_smem<ECAP, BT>();                                                  \
+    SS_CUDA_CHECK(h, cudaFuncSetAttribute(tile_build_kernel<ECAP, ELOW, BT>,                              \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    tile_build_kernel<ECAP, ELOW><<<n_tiles, BUILD_THREADS, smem, st>>>(a);                               \
+    tile_build_kernel<ECAP, ELOW, BT><<<n_tiles, BT, smem, st>>>(a);                                      \
     h->launches++;                                                                                        \
     SS_CUDA_CHECK(h, cudaGetLastError());                                                                 \
   } while (0)
-    SS_TILE_BUILD(E_HARD, 1024);      // largest tiles first: they take longest
-    SS_TILE_BUILD(1024, 256);
-    SS_TILE_BUILD(256, 0);
+    SS_TILE_BUILD(E_HARD, 1024, 1024);      // largest tiles first: they take longest (one CTA per SM)
+    SS_TILE_BUILD(1024, 256, 512);
+    SS_TILE_BUILD(256, 0, 128);
 #undef SS_TILE_BUILD
     SS_CUDA_CHECK(h, cudaMemsetAsync(pad_col + n_tiles, 0, 8, st));
     SS_CUDA_CHECK(h, cudaMemsetAsync(pad_jds + n_tiles, 0, 8, st));

@@ -209,7 +209,40 @@ done:
   return result;
 }
 
+/* number_groups(groups, ids) -> n: ids[i] = running index of groups[i] among the NON-EMPTY containers
+ * (-1 for an empty one: the reference skips barcodes without reads, model.py:735-739). */
+static PyObject* number_groups(PyObject* self, PyObject* args) {
+  PyObject *groups, *ids_obj;
+  if (!PyArg_ParseTuple(args, "OO", &groups, &ids_obj)) return NULL;
+  Py_buffer ids;
+  if (PyObject_GetBuffer(ids_obj, &ids, PyBUF_C_CONTIGUOUS | PyBUF_WRITABLE | PyBUF_FORMAT) < 0) return NULL;
+  PyObject* fast = PySequence_Fast(groups, "groups must be a sequence");
+  PyObject* result = NULL;
+  if (fast) {
+    const Py_ssize_t ng = PySequence_Fast_GET_SIZE(fast);
+    if (ids.itemsize != 4 || ids.len / 4 < ng) {
+      PyErr_SetString(PyExc_ValueError, "ids must be an int32 buffer as long as groups");
+    } else {
+      int32_t* idp = (int32_t*)ids.buf;
+      int32_t n = 0;
+      int ok = 1;
+      for (Py_ssize_t g = 0; g < ng && ok; ++g) {
+        PyObject* s = PySequence_Fast_GET_ITEM(fast, g);
+        Py_ssize_t len = PyAnySet_Check(s) ? PySet_GET_SIZE(s) : PyObject_Length(s);
+        if (len < 0) ok = 0;
+        else idp[g] = len > 0 ? n++ : -1;
+      }
+      if (ok) result = PyLong_FromLong(n);
+    }
+    Py_DECREF(fast);
+  }
+  PyBuffer_Release(&ids);
+  return result;
+}
+
 static PyMethodDef methods[] = {
+    {"number_groups", number_groups, METH_VARARGS,
+     "number_groups(groups, ids): ids[i] = index of groups[i] among the non-empty containers, -1 if empty"},
     {"fill_row_segments", fill_row_segments, METH_VARARGS,
      "fill_row_segments(groups, ids, seg): seg[row] = ids[i] for every row of groups[i]"},
     {NULL, NULL, 0, NULL}};

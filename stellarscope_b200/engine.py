@@ -34,6 +34,35 @@ class ModelError(EngineError):
     ``StellarscopeError`` (model.py:267-272, 454-457)."""
 
 
+class LazyTrace:
+    """(S, max_iter) trace that lives on the device (a private copy, so later fits do not change it)
+    until somebody indexes it; behaves like the numpy array afterwards."""
+
+    def __init__(self, dev_tensor, S, MI):
+        self._dev, self._shape, self._host = dev_tensor, (S, MI), None
+
+    def numpy(self):
+        if self._host is None:
+            self._host = self._dev.cpu().numpy().reshape(self._shape)
+            self._dev = None
+        return self._host
+
+    shape = property(lambda self: self._shape)
+
+    def __getitem__(self, k):
+        return self.numpy()[k]
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def __len__(self):
+        return self._shape[0]
+
+    def __getstate__(self):                   # picklable (multi-GPU gather of the per-model records)
+        return {'_dev': None, '_shape': self._shape, '_host': self.numpy()}
+
+
 class _null_ctx:
     def __enter__(self):
         return self
@@ -301,27 +330,28 @@ class Engine:
         self._check(rc)
 
     def results(self, traces=True):
-        """Per-segment results as numpy arrays (synchronises)."""
+        """Per-segment results as numpy arrays (synchronises).  The per-iteration traces (S x max_iter
+        doubles -- 8 MB for 10^4 models) stay on the device: ``out['diffs']`` / ``out['lnls']`` are
+        fetched on first access (``LazyTrace``)."""
         S, MI, dev = self.S, self.max_iter, self.device
         with torch.cuda.device(dev):
-            iters = torch.empty(S, dtype=torch.int32, device=dev)
-            flags = torch.empty(S, dtype=torch.int32, device=dev)
-            lnl = torch.empty(S, dtype=torch.float64, device=dev)
-            nobs = torch.empty(S, dtype=torch.int32, device=dev)
-            nfeats = torch.empty(S, dtype=torch.int32, device=dev)
+            i32 = torch.empty(4 * max(S, 1), dtype=torch.int32, device=dev)
+            lnl = torch.empty(max(S, 1), dtype=torch.float64, device=dev)
+            iters, flags, nobs, nfeats = (i32[k * S:(k + 1) * S] for k in range(4))
             diffs = torch.empty(S * MI, dtype=torch.float64, device=dev) if traces else None
             lnls = torch.empty(S * MI, dtype=torch.float64, device=dev) if traces and self.use_likelihood else None
             rc = self.lib.ss_em_get_results(self.h, self._stream(), self._p(iters), self._p(flags), self._p(lnl),
                                             self._p(diffs), self._p(lnls), self._p(nobs), self._p(nfeats))
             self._check(rc)
-            out = dict(iters=iters.cpu().numpy(), flags=flags.cpu().numpy(), lnl=lnl.cpu().numpy(),
-                       nobs=nobs.cpu().numpy(), nfeats=nfeats.cpu().numpy())
+            h32 = i32.cpu().numpy()
+            out = dict(iters=h32[0:S], flags=h32[S:2 * S], nobs=h32[2 * S:3 * S], nfeats=h32[3 * S:4 * S],
+                       lnl=lnl[:S].cpu().numpy())
             if (out['flags'] & 8).any():
                 raise EngineError(_lib.SS_ERR_CUDA, 'row-sharded fit: a peer rank did not answer (timeout)')
             if diffs is not None:
-                out['diffs'] = diffs.cpu().numpy().reshape(S, MI)
+                out['diffs'] = LazyTrace(diffs, S, MI)
             if lnls is not None:
-                out['lnls'] = lnls.cpu().numpy().reshape(S, MI)
+                out['lnls'] = LazyTrace(lnls, S, MI)
         return out
 
     def params(self):

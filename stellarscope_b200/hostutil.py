@@ -27,3 +27,8 @@ def load():
 def fill_row_segments(groups, ids, seg):
     """seg[row] = ids[i] for every row of the i-th container of ``groups``."""
     return load().fill_row_segments(groups, ids, seg)
+
+
+def number_groups(groups, ids):
+    """ids[i] = running index of groups[i] among the non-empty containers (-1: empty); returns their number."""
+    return load().number_groups(groups, ids)

@@ -78,8 +78,7 @@ class TelescopeLikelihood(object):
             rank, world, group = shard[:3]
             self._engine.set_sharding(rank, world, group, peers=(shard[3] if len(shard) > 3 else True), K=self.K)
         for attempt in (0, 1):
-            self.max_score = int(m.data.max()) if m.nnz else 0
-            if self.max_score > 65535 or (m.nnz and m.data.min() < 0):
+            if m.dtype != np.uint16 and m.nnz and (m.data.max() > 65535 or m.data.min() < 0):
                 raise StellarscopeError('alignment scores outside [0, 65535] are not supported (uint16, model.py:964)')
             self._engine.set_matrix(m.indptr, m.indices, m.data, self.K)        # H2D in flight ...
             if attempt == 0:
@@ -99,6 +98,7 @@ class TelescopeLikelihood(object):
                     raise
                 m = _canonical_csr(m)
         self.raw_scores = m if isinstance(m, csr_matrix_plus) else csr_matrix_plus(m)
+        self._max_score = None
 
         self._z = None
         self._z_dev = None
@@ -112,6 +112,13 @@ class TelescopeLikelihood(object):
         self.fit_seconds = None
 
     # -- lazily materialised views the reference exposes as attributes ----------
+    @property
+    def max_score(self):
+        """model.py:115 (the fit takes its per-model maxima on the device)."""
+        if self._max_score is None:
+            self._max_score = int(self.raw_scores.data.max()) if self.raw_scores.nnz else 0
+        return self._max_score
+
     @property
     def Q(self):
         """model.py:129-130 for a single-model object (lazy, host; not used by the fit)."""
@@ -288,13 +295,13 @@ def pooling_row_segments(st, opts):
     groups, ids = [], []
     i = 0
     if opts.pooling_mode == 'individual':
-        for _bcode, rowset in st.bcode_ridx_map.items():
-            if not rowset:
-                lg.info(f'        ...not fitting "{_bcode}" -> no reads found')
-                continue
-            groups.append(rowset)
-        i = len(groups)
-        ids = np.arange(i, dtype=np.int32)
+        groups = list(st.bcode_ridx_map.values())
+        ids = np.empty(len(groups), dtype=np.int32)
+        i = hostutil.number_groups(groups, ids)               # barcodes without reads get no model (model.py:735-739)
+        if i < len(groups):
+            for _bcode, rowset in st.bcode_ridx_map.items():
+                if not rowset:
+                    lg.info(f'        ...not fitting "{_bcode}" -> no reads found')
         what = 'a read belongs to more than one barcode'
     elif opts.pooling_mode == 'celltype':
         for _ctype in st.celltypes:

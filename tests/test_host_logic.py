@@ -129,3 +129,56 @@ def test_info_records():
     assert r.format() == ['total_hits - 7 total alignments.',
                           'total_hits - 2 reads initially had multiple alignments.']
     assert statistics.counter_from_hist([3, 0, 5]) == {0: 3, 2: 5}
+
+
+def test_pooling_row_segments_walks_the_reference_containers():
+    """row -> model map from ``bcode_ridx_map`` (dict of row sets) / celltype maps through the C helper
+    (csrc/ss_hostutil.c): model ids in dict order, barcodes without reads get no model
+    (reference model.py:735-739), a row claimed twice is an error."""
+    import types
+    from stellarscope_b200 import model
+    st = types.SimpleNamespace(shape=(10, 4))
+    st.bcode_ridx_map = {'B1': {0, 3}, 'EMPTY': set(), 'B2': {1, 2, 9}, 'B3': {5}}
+    o = types.SimpleNamespace(pooling_mode='individual')
+    seg, keys = model.pooling_row_segments(st, o)
+    assert keys == [0, 1, 2]
+    assert seg.tolist() == [0, 1, 1, 0, -1, 2, -1, -1, -1, 1]
+    st.celltypes = ['t0', 't1', 't2']
+    st.ctype_bcode_map = {'t0': ['B3', 'B1'], 't1': ['EMPTY', 'NOPE'], 't2': ['B2']}
+    o.pooling_mode = 'celltype'
+    seg, keys = model.pooling_row_segments(st, o)
+    assert keys == [0, 1]                                  # t1 has no reads: not fitted
+    assert seg.tolist() == [0, 1, 1, 0, -1, 0, -1, -1, -1, 1]
+    st.bcode_ridx_map['B4'] = {9}
+    o.pooling_mode = 'individual'
+    with pytest.raises(model.StellarscopeError):
+        model.pooling_row_segments(st, o)
+    o.pooling_mode = 'pseudobulk'
+    seg, keys = model.pooling_row_segments(st, o)
+    assert keys == ['pseudobulk'] and not seg.any()
+    # large input: the threaded walk gives the same map
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(300000)
+    cuts = np.sort(rng.choice(300000, 999, replace=False))
+    sets = [set(x.tolist()) for x in np.split(perm, cuts)]
+    st2 = types.SimpleNamespace(shape=(300000, 4), bcode_ridx_map={f'b{i}': s for i, s in enumerate(sets)})
+    seg, keys = model.pooling_row_segments(st2, o.__class__(pooling_mode='individual'))
+    exp = np.empty(300000, dtype=np.int32)
+    for i, x in enumerate(np.split(perm, cuts)):
+        exp[x] = i
+    assert np.array_equal(seg, exp) and len(keys) == 1000
+
+
+def test_segment_fit_infos_lazy_records():
+    from stellarscope_b200.statistics import SegmentFitInfos, PoolInfo
+    res = dict(iters=np.array([3, 5]), flags=np.array([1, 2]), lnl=np.array([1.5, 2.25]), nobs=np.array([10, 20]),
+               nfeats=np.array([4, 6]), diffs=np.arange(20, dtype=float).reshape(2, 10))
+    infos = SegmentFitInfos(res, 1e-7, 10, 0.5).keyed(['a', 'b'])
+    assert list(infos.keys()) == ['a', 'b'] and len(infos) == 2
+    fb = infos['b']
+    assert fb.reached_max and not fb.converged and fb.nobs == 20 and fb.nfeats == 6 and fb.final_lnl == 2.25
+    assert fb.iterations == [(i + 1, 0.5, 10.0 + i) for i in range(5)]
+    p = PoolInfo('individual')
+    p.models_info = infos
+    assert float(p.total_lnl) == 3.75 and p.total_obs == 30 and p.total_params == 20 and p.fitted_models == 2
+    assert abs(float(p.AIC) - (2 * 20 - 2 * 3.75)) < 1e-12
