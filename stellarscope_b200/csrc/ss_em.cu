@@ -523,7 +523,385 @@ __global__ void __maxnreg__(MAXREG) em_lane_kernel(EmArgs a) {
 }
 
 // ---------------------------------------------------------------------------
-// cluster kernel: one thread-block CLUSTER per segment of 2..8 tiles.  Every CTA keeps its
+// cluster lane kernel: one thread-block CLUSTER per segment of 2..16 tiles (a cell with more than
+// one tile of alignments).  Every CTA keeps the rows of its tile in registers like the lane kernel
+// (FR row fragments per lane); per iteration
+//   phase A   local rows: r_i = sum_j Q_ij x_j, scatter Q_ij w_i / r_i into the column-major scratch
+//   phase B1  local partial column sums (lane fragments, xor-shuffle groups) -> part[parity][c]
+//   cluster barrier                                   <- the ONE cluster-wide barrier of an iteration
+//   phase B2  every CTA adds, for each of ITS columns, the partial sums of all tiles that contain the
+//             column straight from its peers' shared memory (DSMEM loads, fixed tile order, so all
+//             CTAs that hold a column compute bit-identical theta', pi', x') -- no owner, no second
+//             exchange.  |delta pi| is summed over the columns a CTA is the first holder of and
+//             PUSHED into every peer's shared memory.
+// The cluster-wide |delta pi| of iteration k is therefore complete one barrier later: convergence of
+// iteration k is detected after the barrier of iteration k+1 (whose phase A / B1 ran speculatively
+// and is discarded); x of iterations k-1 and k are still in the ping-pong buffers, theta of
+// iteration k in `th`.  No global memory traffic and no atomics inside the loop.
+// (The likelihood-convergence mode keeps the three-barrier kernel below.)
+// ---------------------------------------------------------------------------
+struct ClusterArgs {
+  const int* segs;
+  const uint16_t* xref;
+  const long long* seg_xref_off;
+  double* part;                    // [2][part_total] partial column sums of the cluster tiles (global, L2)
+  const long long* tile_part_off;  // offset of a tile's columns in `part`
+  long long part_total;
+};
+
+#ifndef SS_CLANE_THREADS
+#define SS_CLANE_THREADS 512
+#define SS_CLANE_FR 4
+#define SS_CLANE_FC 6
+#define SS_CLANE_MAXREG 128
+#define SS_CLANE_UNROLL 4
+#endif
+constexpr int SS_MAX_CLUSTER_TILES = 8;
+constexpr int CLANE_THREADS = SS_CLANE_THREADS;
+constexpr int CLANE_FR = SS_CLANE_FR, CLANE_FC = SS_CLANE_FC, CLANE_UNROLL = SS_CLANE_UNROLL;
+
+__global__ void __maxnreg__(SS_CLANE_MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  __shared__ double s_red[64];
+  __shared__ double s_dall[2][16];        // [parity][rank]: |delta pi| partial of every CTA of the cluster (pushed)
+  constexpr int THREADS = CLANE_THREADS, FR = CLANE_FR, FC = CLANE_FC;
+  constexpr int NW = THREADS / 32;
+  const unsigned full = 0xffffffffu;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nt = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int seg = ca.segs[blockIdx.x / nt];
+  const int t0 = a.L.seg_tile0[seg];
+  const int t = t0 + rank;
+  const long long* __restrict__ hd = a.L.tile_hdr + (long long)HDR_WORDS * t;
+  const TileView v = load_tile_view(a.L.tile_hdr, t);
+  // the same carve in every CTA of the cluster: sizes of the segment's largest tile
+  int pemax = 0, pcmax = 0;
+  __shared__ long long part_off[SS_MAX_CLUSTER_TILES];
+  if (threadIdx.x < SS_MAX_CLUSTER_TILES) part_off[threadIdx.x] = (int)threadIdx.x < nt ? ca.tile_part_off[t0 + threadIdx.x] : 0;
+  for (int k = 0; k < nt; ++k) {
+    const long long* hk = a.L.tile_hdr + (long long)HDR_WORDS * (t0 + k);
+    pemax = max(pemax, pad8((int)hk[H_NENT]));
+    pcmax = max(pcmax, pad8((int)hk[H_NCOL] + 1));
+  }
+  double* pt = reinterpret_cast<double*>(dsm);         // x ping
+  double* pt2 = pt + pcmax;                            // x pong
+  double* spi = pt2 + pcmax;                           // pi
+  double* sth = spi + pcmax;                           // theta of the last update
+  double* val = sth + pcmax;                           // pemax + 8 (slot pe: scratch of the padding entries)
+  uint16_t* xr = reinterpret_cast<uint16_t*>(val + pemax + 8);   // [ncol][nt] local column of the same locus in tile k
+
+  const double* __restrict__ gq = a.L.e_q + v.eo;
+  const uint32_t* __restrict__ gidx = a.L.e_idx + v.eo;
+  const uint16_t* __restrict__ grlen = a.L.r_len + v.ro;
+  const double* __restrict__ gw = a.L.r_w + v.ro;
+  const uint16_t* __restrict__ gjptr = a.L.j_ptr + v.jo;
+  const uint16_t* __restrict__ gcptr = a.L.c_ptr + v.co;
+  const double* __restrict__ ps0 = a.L.c_pisum0 + v.co;
+  const int* __restrict__ scol = a.L.c_scol + v.co;
+  const int col0 = a.L.seg_col0[seg];
+  const uint16_t* __restrict__ gxref = ca.xref + ca.seg_xref_off[seg];
+
+  const double invK = 1.0 / (double)a.P.K;
+  for (int c = tid; c < v.ncol; c += THREADS) {
+    spi[c] = invK;
+    pt[c] = invK * invK;
+    const long long j = scol[c] - col0;
+    for (int k = 0; k < nt; ++k) xr[c * nt + k] = gxref[j * nt + k];
+  }
+  if (tid == 0) {
+    pt[v.ncol] = 0.0;
+    pt2[v.ncol] = 0.0;
+  }
+  if (tid < 32) { s_dall[0][tid & 15] = 0.0; s_dall[1][tid & 15] = 0.0; }
+  const double thpw = a.F.seg_thpw[seg], pipw = a.F.seg_pipw[seg];
+  const double inv_thd = a.F.seg_inv_thd[seg], inv_pid = a.F.seg_inv_pid[seg];
+  const double diff1_extra = a.F.seg_diff1_extra[seg];
+  const double eps = a.P.eps;
+  const int max_iter = a.P.max_iter;
+  const bool has_uniq = a.L.seg_nuniq[seg] > 0;
+  double* diffs = a.F.seg_diffs + (long long)seg * max_iter;
+
+  // ---- row fragments (as in the lane kernel) ----
+  const int rgt4 = (int)hd[H_RGT4], rgt8 = (int)hd[H_RGT8], rgt16 = (int)hd[H_RGT16], rgt32 = (int)hd[H_RGT32];
+  const int n_huge = rgt32;
+  const int n8 = rgt16 - rgt32, n4 = rgt8 - rgt16, n2 = rgt4 - rgt8, n1 = v.nrows - rgt4;
+  const int V8 = 8 * n8, V4 = V8 + 4 * n4, V2 = V4 + 2 * n2, V = V2 + n1;
+  const int Vc = min(V, FR * THREADS);
+  int r_ovf;
+  if (Vc >= V) r_ovf = v.nrows;
+  else if (Vc < V8) r_ovf = n_huge + Vc / 8;
+  else if (Vc < V4) r_ovf = n_huge + n8 + (Vc - V8) / 4;
+  else if (Vc < V2) r_ovf = n_huge + n8 + n4 + (Vc - V4) / 2;
+  else r_ovf = n_huge + n8 + n4 + n2 + (Vc - V2);
+  const bool generic_rows = n_huge > 0 || r_ovf < v.nrows;
+  const uint32_t dummy_off = ((uint32_t)v.ncol << 3) | ((uint32_t)v.pe << 19);
+  double fq[FR][FRAG], fw[FR];
+  uint32_t fo[FR][FRAG];
+  int fg[FR], nA[FR], gA[FR];
+#pragma unroll
+  for (int j = 0; j < FR; ++j) {
+    const int vl = tid + j * THREADS;
+    int n = 0;
+    fg[j] = 1; fw[j] = 0.0;
+#pragma unroll
+    for (int p = 0; p < FRAG; ++p) { fq[j][p] = 0.0; fo[j][p] = dummy_off; }
+    if (vl < Vc) {
+      int r, k, g;
+      if (vl < V8) { g = 8; r = n_huge + vl / 8; k = vl % 8; }
+      else if (vl < V4) { g = 4; r = n_huge + n8 + (vl - V8) / 4; k = (vl - V8) % 4; }
+      else if (vl < V2) { g = 2; r = n_huge + n8 + n4 + (vl - V4) / 2; k = (vl - V4) % 2; }
+      else { g = 1; r = n_huge + n8 + n4 + n2 + (vl - V2); k = 0; }
+      const int len = grlen[r];
+      n = max(0, min(FRAG, len - FRAG * k));
+      fg[j] = g; fw[j] = gw[r];
+#pragma unroll
+      for (int p = 0; p < FRAG; ++p)
+        if (p < n) {
+          const int e = (int)gjptr[FRAG * k + p] + r;
+          const uint32_t ix = gidx[e];
+          fq[j][p] = gq[e];
+          fo[j][p] = ((ix & 0xffffu) << 3) | ((ix >> 16) << 19);
+        }
+    }
+    nA[j] = __reduce_max_sync(full, n);
+    gA[j] = __reduce_max_sync(full, fg[j]);
+  }
+  // ---- column fragments: descriptors only (the column state lives in shared memory) ----
+  const int b128 = (int)hd[H_CGT128];
+  const int b64 = (int)hd[H_CGT64], b32 = (int)hd[H_CGT32], b16 = (int)hd[H_CGT16], b8 = (int)hd[H_CGT8],
+            b4 = (int)hd[H_CGT4];
+  const int W32 = 32 * (b64 - b128), W16 = W32 + 16 * (b32 - b64), W8 = W16 + 8 * (b16 - b32);
+  const int W4 = W8 + 4 * (b8 - b16), W2 = W4 + 2 * (b4 - b8), W = W2 + (v.ncol - b4);
+  const int Wc = min(W, FC * THREADS);
+  int c_ovf;
+  if (Wc >= W) c_ovf = v.ncol;
+  else if (Wc < W32) c_ovf = b128 + Wc / 32;
+  else if (Wc < W16) c_ovf = b64 + (Wc - W32) / 16;
+  else if (Wc < W8) c_ovf = b32 + (Wc - W16) / 8;
+  else if (Wc < W4) c_ovf = b16 + (Wc - W8) / 4;
+  else if (Wc < W2) c_ovf = b8 + (Wc - W4) / 2;
+  else c_ovf = b4 + (Wc - W2);
+  int cb[FC], cm[FC], nB[FC], gB[FC];     // byte offset of the first slot; #slots | group << 4 | (leader ? column + 1 : 0) << 12
+#pragma unroll
+  for (int j = 0; j < FC; ++j) {
+    const int vl = tid + j * THREADS;
+    int cnj = 0, cgj = 1, ccj = -1;
+    cb[j] = 0;
+    if (vl < Wc) {
+      int c, k, g;
+      if (vl < W32) { g = 32; c = b128 + vl / 32; k = vl % 32; }
+      else if (vl < W16) { g = 16; c = b64 + (vl - W32) / 16; k = (vl - W32) % 16; }
+      else if (vl < W8) { g = 8; c = b32 + (vl - W16) / 8; k = (vl - W16) % 8; }
+      else if (vl < W4) { g = 4; c = b16 + (vl - W8) / 4; k = (vl - W8) % 4; }
+      else if (vl < W2) { g = 2; c = b8 + (vl - W4) / 2; k = (vl - W4) % 2; }
+      else { g = 1; c = b4 + (vl - W2); k = 0; }
+      const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
+      cb[j] = 8 * (b + FRAG * k);
+      cnj = max(0, min(FRAG, n - FRAG * k));
+      cgj = g;
+      ccj = k == 0 ? c : -1;
+    }
+    cm[j] = cnj | (cgj << 4) | ((ccj + 1) << 12);
+    nB[j] = __reduce_max_sync(full, cnj);
+    gB[j] = __reduce_max_sync(full, cgj);
+  }
+  __syncthreads();
+  cluster.sync();                              // every CTA's shared memory is initialised
+
+  double* pt_cur = pt;
+  double* pt_nxt = pt2;
+  unsigned char* const vb = reinterpret_cast<unsigned char*>(val);
+  int it = 0, fin = 0, par = 0;
+  bool conv = false;
+#ifdef SS_CLANE_PROFILE
+  long long tA = 0, tB1 = 0, tS = 0, tB2 = 0, tR = 0, c0, c1;
+#define SS_TICK(acc) c1 = clock64(); acc += c1 - c0; c0 = c1;
+  c0 = clock64();
+#else
+#define SS_TICK(acc)
+#endif
+  while (true) {
+    ++it;
+    double* const gpart = ca.part + (long long)(it & 1) * ca.part_total;      // this iteration's exchange buffer
+    double* const mypart = gpart + ca.tile_part_off[t];
+    if (it <= max_iter) {
+      // ---- phase A ----
+      const unsigned char* const xb = reinterpret_cast<const unsigned char*>(pt_cur);
+#pragma unroll
+      for (int j = 0; j < FR; ++j) {
+        if (nA[j] > 0) {
+          double acc = 0.0;
+#pragma unroll
+          for (int p = 0; p < FRAG; ++p)
+            if (p < nA[j]) acc = fma(fq[j][p], *reinterpret_cast<const double*>(xb + (fo[j][p] & 0xffffu)), acc);
+          if (gA[j] > 1) acc = group_xor_sum(acc, fg[j], gA[j]);
+          const bool pos = acc > 0.0;
+          double inv = 1.0 / (pos ? acc : 1.0);
+          inv = pos ? inv : 0.0;
+          const double sc = fw[j] * inv;
+#pragma unroll
+          for (int p = 0; p < FRAG; ++p)
+            if (p < nA[j]) *reinterpret_cast<double*>(vb + (fo[j][p] >> 16)) = fq[j][p] * sc;
+        }
+      }
+      if (generic_rows) {
+        for (int r = tid; r < v.nrows; r += THREADS) {
+          const int rr = r < n_huge ? r : r_ovf + (r - n_huge);
+          if (rr >= v.nrows) break;
+          const int len = grlen[rr];
+          double acc = 0.0;
+          for (int p = 0; p < len; ++p) {
+            const int e = (int)gjptr[p] + rr;
+            acc = fma(gq[e], pt_cur[gidx[e] & 0xffffu], acc);
+          }
+          const double sc = acc > 0.0 ? gw[rr] * (1.0 / acc) : 0.0;
+          for (int p = 0; p < len; ++p) {
+            const int e = (int)gjptr[p] + rr;
+            val[gidx[e] >> 16] = gq[e] * sc;
+          }
+        }
+      }
+      __syncthreads();
+      SS_TICK(tA)
+      // ---- phase B1: local partial column sums ----
+#pragma unroll
+      for (int j = 0; j < FC; ++j) {
+        if (nB[j] > 0) {
+          double asum = 0.0;
+          const unsigned char* const cp = vb + cb[j];
+          const int cnj = cm[j] & 15;
+#pragma unroll
+          for (int k = 0; k < FRAG; ++k)
+            if (k < nB[j]) {
+              if (k < cnj) asum += *reinterpret_cast<const double*>(cp + 8 * k);
+            }
+          if (gB[j] > 1) asum = group_xor_sum(asum, (cm[j] >> 4) & 63, gB[j]);
+          const int c1 = cm[j] >> 12;
+          if (c1 > 0) mypart[c1 - 1] = asum;
+        }
+      }
+      for (int c = warp; c < b128; c += NW) {                     // very long columns: one warp each
+        const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
+        const double asum = col_sum_warp(val, b, n, lane);
+        if (lane == 0) mypart[c] = asum;
+      }
+      for (int c = c_ovf + tid; c < v.ncol; c += THREADS) {       // columns beyond the register lanes
+        const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
+        mypart[c] = col_sum_thread(val, b, n);
+      }
+    }
+    SS_TICK(tB1)
+    cluster.sync();                                               // barrier #it
+    SS_TICK(tS)
+    if (it > 1) {
+      // ---- decision for iteration it-1 (all CTAs add the pushed partials in rank order) ----
+      double diff = 0.0;
+      for (int r = 0; r < nt; ++r) diff += s_dall[(it - 1) & 1][r];
+      if (it - 1 == 1) diff += diff1_extra;
+      if (rank == 0 && tid == 0) diffs[it - 2] = diff;
+      conv = diff < eps;                                          // model.py:351
+      if (conv || it - 1 >= max_iter) {
+        fin = it - 1;
+        break;
+      }
+    }
+    // ---- phase B2: gather the partial sums of my columns from every tile, new parameters ----
+    double dsum = 0.0;
+    // U columns per thread at a time: their DSMEM loads are in flight together (a round trip costs
+    // ~1000 cycles), the additions stay in tile order
+    constexpr int U = CLANE_UNROLL;
+    for (int cbase = tid; cbase < v.ncol; cbase += U * THREADS) {
+      double tot[U];
+      bool first[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { tot[u] = 0.0; first[u] = true; }
+      for (int k = 0; k < nt; ++k) {                              // fixed tile order
+        const double* pk = gpart + part_off[k];
+        double vk[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int c = cbase + u * THREADS;
+          const unsigned ck = c < v.ncol ? (unsigned)xr[c * nt + k] : 0xffffu;
+          vk[u] = 0.0;
+          if (ck != 0xffffu) {
+#ifdef SS_CLANE_NOLOAD
+            vk[u] = 1.0 + (double)ck;
+#else
+            vk[u] = __ldcg(pk + ck);                             // written by a peer CTA: read from L2
+#endif
+            if (k < rank) first[u] = false;                       // an earlier tile holds this column too
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) tot[u] += vk[u];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int c = cbase + u * THREADS;
+        if (c < v.ncol) {
+          const double T = pt_cur[c] * tot[u];
+          const double th = (T + thpw) * inv_thd;                 // model.py:240
+          const double pn = ((has_uniq ? ps0[c] : 0.0) + T + pipw) * inv_pid;   // model.py:243-244
+          if (first[u]) dsum += fabs(pn - spi[c]);
+          spi[c] = pn;
+          sth[c] = th;
+          pt_nxt[c] = pn * th;
+        }
+      }
+    }
+    SS_TICK(tB2)
+    dsum = block_sum<THREADS>(dsum, s_red, par++);                // barrier: publishes pt_nxt
+    if (tid < nt) cluster.map_shared_rank(&s_dall[it & 1][rank], tid)[0] = dsum;   // push to every CTA
+    double* tmp = pt_cur; pt_cur = pt_nxt; pt_nxt = tmp;
+    SS_TICK(tR)
+  }
+#ifdef SS_CLANE_PROFILE
+  if (tid == 0 && blockIdx.x < 4)
+    printf("clane seg %d rank %d/%d nent %d ncol %d iters %d: cycles/iter A %lld B1 %lld sync %lld B2 %lld red %lld\n", seg, rank,
+           nt, v.nent, v.ncol, it, tA / it, tB1 / it, tS / it, tB2 / it, tR / it);
+#endif
+#undef SS_TICK
+  // ---- publish: iteration `fin` is final.  pt_cur = x_fin, pt_nxt = x_{fin-1} (the last E-step that counts) ----
+  for (int c = tid; c < v.ncol; c += THREADS) {
+    const int slot = scol[c];
+    a.F.sc_pi[slot] = spi[c];
+    a.F.sc_theta[slot] = sth[c];
+    a.F.sc_ptprev[slot] = pt_nxt[c];
+    a.F.sc_ptfin[slot] = pt_cur[c];
+  }
+  // final lnL: z of the last E-step (x_{fin-1}), final parameters (model.py:368-370)
+  double l = 0.0;
+  for (int r = tid; r < v.nrows; r += THREADS) {
+    const int len = grlen[r];
+    double acc = 0.0;
+    for (int p = 0; p < len; ++p) {
+      const int e = (int)gjptr[p] + r;
+      acc = fma(gq[e], pt_nxt[gidx[e] & 0xffffu], acc);
+    }
+    const double inv = acc > 0.0 ? 1.0 / acc : 0.0;
+    for (int p = 0; p < len; ++p) {
+      const int e = (int)gjptr[p] + r;
+      const int c = gidx[e] & 0xffffu;
+      const double z = (gq[e] * pt_nxt[c]) * inv;
+      const double pn = pt_cur[c];
+      if (z > 0.0 && pn > 0.0) l = fma(z, log(gq[e] * pn), l);
+    }
+  }
+  l = block_sum<THREADS>(l, s_red, par++);
+  if (tid == 0) {
+    a.F.tile_lnl[t] = l;
+    if (rank == 0) {
+      a.F.seg_iters[seg] = fin;
+      a.F.seg_flags[seg] = (conv ? 1 : 0) | (fin >= max_iter ? 2 : 0);
+    }
+  }
+  cluster.sync();                                                 // nobody leaves while its shared memory may be read
+}
+
+// ---------------------------------------------------------------------------
+// three-barrier cluster kernel (likelihood-convergence mode only): one thread-block CLUSTER per segment of 2..8 tiles.  Every CTA keeps its
 // tile resident in shared memory (like the resident kernel); the columns of the segment are
 // owned round-robin by the CTAs (owner of segment column j = j mod nt).  Per iteration:
 //   phase A (local rows) | barrier | phase B (local partial column sums -> `part`)
@@ -533,11 +911,6 @@ __global__ void __maxnreg__(MAXREG) em_lane_kernel(EmArgs a) {
 //   |delta pi| sums, takes the (identical) convergence decision.
 // No global memory traffic and no atomics inside the loop.
 // ---------------------------------------------------------------------------
-struct ClusterArgs {
-  const int* segs;
-  const uint16_t* xref;
-  const long long* seg_xref_off;
-};
 
 template <int THREADS, bool LNL, int NT>
 __global__ void __launch_bounds__(THREADS) em_cluster_kernel(EmArgs a, ClusterArgs ca) {
@@ -1184,22 +1557,33 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     ca.segs = h->clu_segs[nt];
     ca.xref = h->clu_xref;
     ca.seg_xref_off = h->seg_xref_off;
+    ca.part = h->clu_part;
+    ca.tile_part_off = h->tile_part_off;
+    ca.part_total = h->clu_part_total;
     a.tile_list = nullptr;
     a.n_list = 0;
     void (*kfn)(EmArgs, ClusterArgs) = nullptr;
-    switch (nt) {
-#define SS_CLU_CASE(N)                                                                                  \
-  case N:                                                                                               \
-    kfn = lnl ? em_cluster_kernel<CLUSTER_THREADS, true, N> : em_cluster_kernel<CLUSTER_THREADS, false, N>; \
+    size_t smem = 0;
+    int threads = CLUSTER_THREADS;
+    if (!lnl) {
+      kfn = em_clane_kernel;                       // one cluster barrier per iteration
+      smem = h->clu_smem_lane[nt] + 256;
+      threads = CLANE_THREADS;
+    } else {
+      switch (nt) {
+#define SS_CLU_CASE(N)                               \
+  case N:                                            \
+    kfn = em_cluster_kernel<CLUSTER_THREADS, true, N>; \
     break;
-      SS_CLU_CASE(2) SS_CLU_CASE(3) SS_CLU_CASE(4) SS_CLU_CASE(5) SS_CLU_CASE(6) SS_CLU_CASE(7) SS_CLU_CASE(8)
+        SS_CLU_CASE(2) SS_CLU_CASE(3) SS_CLU_CASE(4) SS_CLU_CASE(5) SS_CLU_CASE(6) SS_CLU_CASE(7) SS_CLU_CASE(8)
 #undef SS_CLU_CASE
+      }
+      smem = h->clu_smem[nt] + 256;
     }
-    const size_t smem = h->clu_smem[nt] + 256;
     SS_CUDA_CHECK(h, cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(h->clu_count[nt] * nt));
-    cfg.blockDim = dim3(CLUSTER_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = sx;
     cudaLaunchAttribute attr[1];

@@ -70,9 +70,13 @@ struct ss_handle_s {
   static constexpr int MAX_CLUSTER = 8;
   int* clu_segs[MAX_CLUSTER + 1] = {};     // device: segment ids by number of tiles
   int clu_count[MAX_CLUSTER + 1] = {};
-  size_t clu_smem[MAX_CLUSTER + 1] = {};
+  size_t clu_smem[MAX_CLUSTER + 1] = {};       // three-barrier kernel (likelihood mode)
+  size_t clu_smem_lane[MAX_CLUSTER + 1] = {};  // cluster lane kernel
   uint16_t* clu_xref = nullptr;            // device: [segment column][tile of the segment] -> tile column or 0xffff
   long long* seg_xref_off = nullptr;       // device: offset of a segment's block in clu_xref (-1: none)
+  double* clu_part = nullptr;              // device: [2][clu_part_total] partial column sums of the cluster tiles (L2-resident exchange)
+  long long* tile_part_off = nullptr;      // device: offset of a tile's columns in clu_part (-1: not a cluster tile)
+  long long clu_part_total = 0;
   int n_cluster_tiles = 0, n_cluster_segs = 0;
   int* all_tiles = nullptr;       // device: 0 .. n_tiles-1
   size_t all_smem = 0;            // smem of the largest tile (likelihood-mode carve)

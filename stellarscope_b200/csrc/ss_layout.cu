@@ -33,6 +33,7 @@ void free_layout(ss_handle_s* h) {
   h->sc_inamb = nullptr;
   for (int k = 0; k <= ss_handle_s::MAX_CLUSTER; ++k) { h->clu_segs[k] = nullptr; h->clu_count[k] = 0; h->clu_smem[k] = 0; }
   h->clu_xref = nullptr; h->seg_xref_off = nullptr; h->n_cluster_tiles = h->n_cluster_segs = 0;
+  h->clu_part = nullptr; h->tile_part_off = nullptr; h->clu_part_total = 0;
   h->has_layout = false;
 }
 
@@ -148,22 +149,27 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
   std::vector<int> clu[ss_handle_s::MAX_CLUSTER + 1];
   std::vector<long long> xoff((size_t)std::max(L.S, 1), -1);
   long long xref_total = 0;
-  for (int k = 0; k <= MAXC; ++k) h->clu_smem[k] = 0;
+  for (int k = 0; k <= MAXC; ++k) h->clu_smem[k] = h->clu_smem_lane[k] = 0;
   for (int sgm = 0; sgm < L.S; ++sgm) {
     const int nt = h->seg_ntiles_host[sgm];
     if (nt < 2 || nt > MAXC) continue;
     const size_t no_pad = (size_t)pad8((seg_ncol[sgm] + nt - 1) / nt + 1);
     const size_t owner_bytes = 8 * 4 * no_pad + 2 * no_pad * nt;
     size_t need = 0;
+    int pemax = 0, pcmax = 0;
     for (int k = 0; k < nt; ++k) {
       const long long* hd = &h->hdr_host[(size_t)(h->seg_tile0_host[sgm] + k) * HDR_WORDS];
       need = std::max(need, tile_smem_bytes((int)hd[H_NENT], (int)hd[H_NROWS], (int)hd[H_NCOL], (int)hd[H_MAXLEN]) +
                                 owner_bytes);
+      pemax = std::max(pemax, pad8((int)hd[H_NENT]));
+      pcmax = std::max(pcmax, pad8((int)hd[H_NCOL] + 1));
     }
-    if (need + 2048 > h->max_smem_optin) continue;
+    const size_t need_lane = clane_smem_bytes(pemax, pcmax, nt);
+    if (need + 2048 > h->max_smem_optin || need_lane + 2048 > h->max_smem_optin) continue;
     seg_clustered[sgm] = 1;
     clu[nt].push_back(sgm);
     h->clu_smem[nt] = std::max(h->clu_smem[nt], need);
+    h->clu_smem_lane[nt] = std::max(h->clu_smem_lane[nt], need_lane);
     xoff[sgm] = xref_total;
     xref_total += (long long)seg_ncol[sgm] * nt;
   }
@@ -255,6 +261,20 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
     h->clu_count[k] = (int)clu[k].size();
     h->n_cluster_segs += h->clu_count[k];
     SS_CUDA_CHECK(h, upload(pool, &h->clu_segs[k], (const int*)clu[k].data(), clu[k].size(), st));
+  }
+  // exchange buffers of the cluster lane kernel: the partial column sums of every cluster tile, twice
+  // (iteration parity); they live in global memory on purpose -- L2 feeds an SM several times faster
+  // than the SM-to-SM network (DSMEM: ~20 B/cycle), and the working set of the active clusters is a few MB
+  {
+    std::vector<long long> poff((size_t)std::max(T, 1), -1);
+    long long tot = 0;
+    for (int t : cluster_tiles) {
+      poff[t] = tot;
+      tot += pad8((int)h->hdr_host[(size_t)t * HDR_WORDS + H_NCOL] + 1);
+    }
+    h->clu_part_total = tot;
+    SS_CUDA_CHECK(h, upload(pool, &h->tile_part_off, (const long long*)poff.data(), poff.size(), st));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &h->clu_part, (size_t)std::max<long long>(2 * tot, 1)));
   }
   SS_CUDA_CHECK(h, upload(pool, &h->seg_xref_off, (const long long*)xoff.data(), xoff.size(), st));
   SS_CUDA_CHECK(h, dev_alloc(pool, &h->clu_xref, (size_t)std::max<long long>(xref_total, 1)));
