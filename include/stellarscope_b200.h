@@ -182,8 +182,8 @@ int ss_count(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, const 
  *   (>= ss_peer_buffer_bytes(K), zero-filled, e.g. torch symmetric memory over NVLink).  With
  *   peer buffers the whole fit runs in one persistent kernel per rank that exchanges the partial
  *   sums over peer memory itself; every rank adds them in rank order, so all ranks take the
- *   identical convergence decision.  world = 1 with peer_bufs = NULL selects the same dense code
- *   path on a single GPU.  The caller must keep the ranks in step (barrier) before each fit. */
+ *   identical convergence decision.  world = 1 with peer_bufs = NULL selects the same persistent
+ *   kernel on a single GPU (bytes < 0: the host-loop variant).  The caller must keep the ranks in step (barrier) before each fit. */
 typedef int (*ss_allreduce_fn)(void* user, void* stream, double* buf, int64_t count, int32_t op /*0 sum, 1 max*/);
 int ss_set_allreduce(ss_handle_t h, ss_allreduce_fn fn, void* user);
 int64_t ss_peer_buffer_bytes(int32_t n_cols);

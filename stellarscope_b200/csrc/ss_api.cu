@@ -300,8 +300,8 @@ int ss_set_allreduce(ss_handle_t h, ss_allreduce_fn fn, void* user) {
 }
 
 int64_t ss_peer_buffer_bytes(int32_t n_cols) {
-  const int nchunks = (n_cols + SS_DN_TAIL + 64 + 511) / 512;
-  return (int64_t)(2 * (int64_t)nchunks * 512 + SS_DN_MAXW) * 8;
+  const int nchunks = (n_cols + SS_DN_TAIL + 64 + SS_DN_THREADS - 1) / SS_DN_THREADS;
+  return (int64_t)(2 * (int64_t)nchunks * SS_DN_THREADS + SS_DN_MAXW) * 8;
 }
 
 int ss_set_peers(ss_handle_t h, int32_t rank, int32_t world, void* const* peer_bufs, int64_t bytes) {
@@ -316,6 +316,9 @@ int ss_set_peers(ss_handle_t h, int32_t rank, int32_t world, void* const* peer_b
   h->dn_rank = rank;
   h->dn_epoch = 0;
   h->dn_peers = peer_bufs != nullptr;
+  // a single rank has nothing to exchange: the persistent kernel runs on plain device buffers
+  // (bytes < 0 selects the host-loop variant, for tests)
+  h->dn_persistent = h->dn_peers || (world == 1 && bytes >= 0);
   h->dn_force = true;
   h->dn_peer_bytes = peer_bufs ? (size_t)bytes : 0;
   for (int r = 0; r < SS_DN_MAXW; ++r) h->dn_peer_base[r] = (peer_bufs && r < world) ? peer_bufs[r] : nullptr;

@@ -32,7 +32,8 @@ namespace cg = cooperative_groups;
 
 namespace ss {
 
-constexpr int DN_THREADS = 512;
+constexpr int DN_THREADS = SS_DN_THREADS;
+constexpr int SS_ST_FR = 2, SS_ST_FC = 3;      // fragments per lane of the streaming tile pass (1024 lanes)
 constexpr long long DN_SPIN_LIMIT = 20000000000LL;   // ~10 s of SM clocks: a lost peer must not hang the GPU
 
 struct DenseArgs {
@@ -51,6 +52,7 @@ struct DenseArgs {
   double* part;                         // [2 * nchunks]: |delta pi| and unique-row lnL partials per chunk
   const int* tgcol;                     // locus of every tile column
   double thpw, pipw, inv_thd, inv_pid, logq_uniq;
+  StreamGeom geom;                      // shared-memory geometry of the streaming tile pass
   int* ctl;                             // [0] iterations (0 = running), [1] flags, [2] communication error
   double* diffs;
   double* lnls;
@@ -72,38 +74,6 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsign
 }
 
 // ---- tile pass: partial thetasum of the local rows -> T (atomics; order-free, absorbed by the tie tolerance)
-template <int THREADS>
-__device__ __forceinline__ void dense_tile_pass(const EmArgs& a, const DenseArgs& d, const double* x, double* T,
-                                                unsigned char* dsm, uint64_t* bar, uint32_t& phase) {
-  constexpr int NW = THREADS / 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int t = blockIdx.x; t < d.n_tiles; t += gridDim.x) {
-    const TileView v = load_tile_view(a.L.tile_hdr, t);
-    TileSmem s = carve_tile(dsm, v);
-    if (tid == 0) {
-      fence_proxy_async();
-      tile_issue_loads(a.L, v, s, bar);
-    }
-    const int* __restrict__ gc = d.tgcol + v.co;
-    for (int c = tid; c < v.ncol; c += THREADS) s.pt[c] = __ldcg(x + gc[c]);
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    __syncthreads();
-    tile_phase_a<THREADS>(v, s, s.pt);
-    __syncthreads();
-    for (int c = warp; c < v.nlong; c += NW) {
-      const int b = s.cptr[c], n = (int)s.cptr[c + 1] - b;
-      const double asum = col_sum_warp(s.val, b, n, lane);
-      if (lane == 0) atomicAdd(&T[gc[c]], s.pt[c] * asum);
-    }
-    for (int c = v.nlong + tid; c < v.ncol; c += THREADS) {
-      const int b = s.cptr[c], n = (int)s.cptr[c + 1] - b;
-      atomicAdd(&T[gc[c]], s.pt[c] * col_sum_thread(s.val, b, n));
-    }
-    __syncthreads();   // shared memory is reused by the next tile
-  }
-}
-
 // ---- lnL of the local ambiguous rows: z from xold, parameters xnew (model.py:291-317) -> *acc
 template <int THREADS>
 __device__ __forceinline__ void dense_lnl_pass(const EmArgs& a, const DenseArgs& d, const double* xold,
@@ -175,9 +145,10 @@ __device__ __forceinline__ void dense_update(const DenseArgs& d, int cur, int it
 }
 
 __device__ __forceinline__ double dense_part_sum(const DenseArgs& d, int which) {
+  // lane-strided loads (in flight together) + xor tree: a fixed order, identical in every warp, CTA and rank
   double v = 0.0;
-  for (int c = 0; c < d.nchunks; ++c) v += __ldcg(d.part + which * d.nchunks + c);   // fixed order
-  return v;
+  for (int c = threadIdx.x & 31; c < d.nchunks; c += 32) v += __ldcg(d.part + which * d.nchunks + c);
+  return warp_sum(v);
 }
 
 // cross-rank barrier + visibility of the exchange buffers; called by every thread of the grid after a grid.sync
@@ -204,11 +175,15 @@ __global__ void __launch_bounds__(THREADS) em_dense_kernel(EmArgs a, DenseArgs d
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double s_red[64];
   __shared__ uint64_t s_bar;
+  __shared__ uint64_t s_bars[2];
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   uint32_t phase = 0;
+  uint32_t uses[2] = {0u, 0u};
   if (tid == 0) {
     mbar_init(&s_bar, 1);
+    mbar_init(&s_bars[0], 1);
+    mbar_init(&s_bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -216,15 +191,27 @@ __global__ void __launch_bounds__(THREADS) em_dense_kernel(EmArgs a, DenseArgs d
   double lnl_prev = INFINITY, lnl = 0.0;
   int it = 0;
   bool conv = false, comm_err = false;
+#ifdef SS_STREAM_PROFILE
+  long long k0_ = clock64(), kp[6] = {0, 0, 0, 0, 0, 0};
+#define K_TICK(i) { const long long k1_ = clock64(); kp[i] += k1_ - k0_; k0_ = k1_; }
+#else
+#define K_TICK(i)
+#endif
   while (true) {
     ++it;
     const int cur = (it - 1) & 1;
-    dense_tile_pass<THREADS>(a, d, d.x[cur], d.T[cur], dsm, &s_bar, phase);
+    lane_stream_pass<THREADS, SS_ST_FR, SS_ST_FC>(a.L, d.tgcol, nullptr, d.n_tiles, nullptr, d.x[cur], d.T[cur], d.geom,
+                                                    dsm, s_bars, uses);
+    K_TICK(0)
     grid.sync();
+    K_TICK(1)
     dense_exchange(d, ++epoch, grid);
     dense_update<THREADS>(d, cur, it, s_red);
+    K_TICK(2)
     grid.sync();
+    K_TICK(3)
     const double diff = dense_part_sum(d, 0);
+    K_TICK(4)
     if (LNL) {
       // lnL with the E-step's z (old x) and the new parameters: model.py:344
       dense_lnl_pass<THREADS>(a, d, d.x[cur], d.x[cur ^ 1], d.T[cur] + d.Kp, dsm, &s_bar, phase, s_red);
@@ -268,6 +255,14 @@ __global__ void __launch_bounds__(THREADS) em_dense_kernel(EmArgs a, DenseArgs d
     d.ctl[0] = it;
     d.ctl[1] = (conv ? 1 : 0) | (it >= d.max_iter ? 2 : 0) | (comm_err ? 8 : 0);
     *d.lnl_out = lnl;
+#ifdef SS_STREAM_PROFILE
+    const long long n = g_st_prof[7] ? g_st_prof[7] : 1;
+    printf("dense kernel, cycles per iteration (block 0): tile pass %lld  grid.sync %lld  update %lld  grid.sync %lld  part_sum %lld\n",
+           kp[0] / it, kp[1] / it, kp[2] / it, kp[3] / it, kp[4] / it);
+    printf("stream pass, cycles per tile (block 0, %lld tiles, nbuf %d): tma-wait %lld  gather-x %lld  phaseA %lld  phaseB+atomics %lld\n",
+           n, d.geom.nbuf, g_st_prof[0] / n, g_st_prof[1] / n, g_st_prof[2] / n, g_st_prof[3] / n);
+    for (int i = 0; i < 8; ++i) g_st_prof[i] = 0;
+#endif
   }
 }
 
@@ -277,17 +272,22 @@ __global__ void __launch_bounds__(THREADS) dense_pass_kernel(EmArgs a, DenseArgs
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double s_red[64];
   __shared__ uint64_t s_bar;
+  __shared__ uint64_t s_bars[2];
   if (*((volatile int*)d.ctl) != 0 && !lnl_pass) return;       // the fit has finished: no-op
   uint32_t phase = 0;
+  uint32_t uses[2] = {0u, 0u};
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
+    mbar_init(&s_bars[0], 1);
+    mbar_init(&s_bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (lnl_pass)
     dense_lnl_pass<THREADS>(a, d, d.x[cur], d.x[cur ^ 1], d.T[tail_buf] + d.Kp, dsm, &s_bar, phase, s_red);
   else
-    dense_tile_pass<THREADS>(a, d, d.x[cur], d.T[cur], dsm, &s_bar, phase);
+    lane_stream_pass<THREADS, SS_ST_FR, SS_ST_FC>(a.L, d.tgcol, nullptr, d.n_tiles, nullptr, d.x[cur], d.T[cur], d.geom,
+                                                    dsm, s_bars, uses);
 }
 
 template <int THREADS>
@@ -299,12 +299,14 @@ __global__ void __launch_bounds__(THREADS) dense_update_kernel(DenseArgs d, int 
 
 // one thread: convergence decision of iteration `it` (lnl_mode: T[tail_buf] tail holds the summed lnL part)
 __global__ void dense_decide_kernel(DenseArgs d, int it, int lnl_mode, int tail_buf, double* lnl_prev) {
+  // launched with one warp: the partial sums are reduced by all 32 lanes, lane 0 decides
+  const double diff = dense_part_sum(d, 0);
+  const double lu = dense_part_sum(d, 1);
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (d.ctl[0] != 0) return;
-  const double diff = dense_part_sum(d, 0);
   bool conv;
   if (lnl_mode) {
-    const double lnl = d.T[tail_buf][d.Kp] + dense_part_sum(d, 1) + d.logq_uniq;
+    const double lnl = d.T[tail_buf][d.Kp] + lu + d.logq_uniq;
     conv = fabs(lnl - *lnl_prev) < d.eps;
     *lnl_prev = lnl;
     d.lnls[it - 1] = lnl;
@@ -319,8 +321,9 @@ __global__ void dense_decide_kernel(DenseArgs d, int it, int lnl_mode, int tail_
   }
 }
 __global__ void dense_final_lnl_kernel(DenseArgs d, int tail_buf) {
+  const double lu = dense_part_sum(d, 1);
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  *d.lnl_out = d.T[tail_buf][d.Kp] + dense_part_sum(d, 1) + d.logq_uniq;
+  *d.lnl_out = d.T[tail_buf][d.Kp] + lu + d.logq_uniq;
 }
 
 // ---- preparation -------------------------------------------------------------------------------
@@ -515,7 +518,7 @@ int em_fit_dense(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
   memset(&d, 0, sizeof(d));
   d.K = K; d.Kp = h->dn_Kp; d.world = h->dn_world; d.rank = h->dn_rank; d.n_tiles = L.n_tiles;
   d.nchunks = h->dn_nchunks; d.max_iter = P.max_iter; d.eps = P.eps;
-  d.summed = h->dn_peers ? 0 : 1;
+  d.summed = h->dn_peers ? 0 : 1;       // no peer buffers: T already is the sum over ranks when the update reads it
   d.T[0] = h->dn_T[0]; d.T[1] = h->dn_T[1];
   for (int r = 0; r < SS_DN_MAXW; ++r) {
     if (h->dn_peers && r < h->dn_world) {
@@ -553,12 +556,13 @@ int em_fit_dense(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
   EmArgs a;
   a.L = L; a.F = F; a.P = h->P; a.z_out = nullptr; a.tile_list = nullptr; a.n_list = 0;
   const bool lnl = P.use_likelihood != 0;
-  const size_t smem = std::max<size_t>(h->all_smem, 1024);
+  d.geom = make_stream_geom(h->geom_all, h->max_smem_optin - 2048);
+  const size_t smem = std::max<size_t>(std::max(h->all_smem, stream_smem_bytes(d.geom)), 1024);
   const int nK = d.Kp + SS_DN_TAIL;
   dense_init_kernel<<<(nK + 255) / 256, 256, 0, st>>>(d);
   h->launches++;
   if (h->timing) SS_CUDA_CHECK(h, cudaEventRecord(h->ev[1], st));
-  if (h->dn_peers) {
+  if (h->dn_persistent) {
     // ---- one persistent cooperative kernel ----
     void* fn = lnl ? (void*)em_dense_kernel<DN_THREADS, true> : (void*)em_dense_kernel<DN_THREADS, false>;
     SS_CUDA_CHECK(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -578,7 +582,7 @@ int em_fit_dense(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     SS_CUDA_CHECK(h, cudaFuncSetAttribute(dense_pass_kernel<DN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
     const bool multi = h->allreduce && h->dn_world > 1;
-    const int grid_t = std::max(1, L.n_tiles);
+    const int grid_t = std::max(1, std::min(L.n_tiles, h->num_sms));   // persistent CTAs: the next tile is prefetched
     double* lnl_prev = h->dn_lnl + 1;
     const double inf = INFINITY;
     SS_CUDA_CHECK(h, cudaMemcpyAsync(lnl_prev, &inf, sizeof(double), cudaMemcpyHostToDevice, st));

@@ -27,6 +27,7 @@ struct StreamArgs {
   const int* col_slot;   // [n_cols] absolute slot
   long long n_cols;
   int* ctl;              // [0] = number of active segments, [1 + i] = segment i done (iters)
+  StreamGeom geom;       // shared-memory geometry of the streaming tile pass
 };
 
 // ---------------------------------------------------------------------------
@@ -1125,9 +1126,13 @@ __global__ void __launch_bounds__(THREADS) em_stream_kernel(EmArgs a, StreamArgs
   const long long gthreads = (long long)gridDim.x * THREADS;
   const int max_iter = a.P.max_iter;
   const double eps = a.P.eps;
+  __shared__ uint64_t s_bars[2];
   uint32_t phase = 0;
+  uint32_t uses[2] = {0u, 0u};
   if (tid == 0) {
     mbar_init(&s_bar, 1);
+    mbar_init(&s_bars[0], 1);
+    mbar_init(&s_bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -1135,34 +1140,9 @@ __global__ void __launch_bounds__(THREADS) em_stream_kernel(EmArgs a, StreamArgs
   for (int it = 1; it <= max_iter; ++it) {
     const int cur = (it - 1) & 1;
     const double* __restrict__ ptg = a.F.sc_pt[cur];
-    // ---- tile pass: phase A + B, partial thetasum -> global accumulators ----
-    for (int i = blockIdx.x; i < sa.n_tiles; i += gridDim.x) {
-      const int t = sa.tiles[i];
-      const TileView v = load_tile_view(a.L.tile_hdr, t);
-      if (a.F.seg_iters[v.seg] != 0) continue;           // segment already finished
-      TileSmem s = carve_tile(dsm, v);
-      if (tid == 0) {
-        fence_proxy_async();
-        tile_issue_loads(a.L, v, s, &s_bar);
-      }
-      const int* __restrict__ scol = a.L.c_scol + v.co;
-      for (int c = tid; c < v.ncol; c += THREADS) s.pt[c] = ptg[scol[c]];
-      mbar_wait(&s_bar, phase);
-      phase ^= 1;
-      __syncthreads();
-      tile_phase_a<THREADS>(v, s, s.pt);
-      __syncthreads();
-      for (int c = warp; c < v.nlong; c += NW) {
-        const int b = s.cptr[c], n = (int)s.cptr[c + 1] - b;
-        const double asum = col_sum_warp(s.val, b, n, lane);
-        if (lane == 0) atomicAdd(&a.F.sc_T[scol[c]], s.pt[c] * asum);
-      }
-      for (int c = v.nlong + tid; c < v.ncol; c += THREADS) {
-        const int b = s.cptr[c], n = (int)s.cptr[c + 1] - b;
-        atomicAdd(&a.F.sc_T[scol[c]], s.pt[c] * col_sum_thread(s.val, b, n));
-      }
-      __syncthreads();                                    // smem is reused by the next tile
-    }
+    // ---- tile pass: phase A + B, partial thetasum -> global accumulators (double-buffered TMA, lane fragments) ----
+    lane_stream_pass<THREADS, 2, 3>(a.L, a.L.c_scol, sa.tiles, sa.n_tiles, a.F.seg_iters, ptg, a.F.sc_T, sa.geom, dsm,
+                                    s_bars, uses);
     grid.sync();
     // ---- update pass over the columns of the active multi-tile segments ----
     double* __restrict__ ptn = a.F.sc_pt[cur ^ 1];
@@ -1421,7 +1401,7 @@ static cudaError_t ensure_aux_streams(ss_handle_s* h) {
   return cudaSuccess;
 }
 
-constexpr int STREAM_THREADS = 512;
+constexpr int STREAM_THREADS = 1024;
 constexpr int CLUSTER_THREADS = 512;
 
 int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
@@ -1523,8 +1503,9 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     sa.col_slot = h->stream_col_slot;
     sa.n_cols = h->n_stream_cols;
     sa.ctl = h->stream_ctl;
+    sa.geom = make_stream_geom(h->geom_stream, h->max_smem_optin - 2048);
     SS_CUDA_CHECK(h, cudaMemsetAsync(h->stream_ctl, 0, 4 * sizeof(int), sx));
-    const size_t smem = h->stream_smem;
+    const size_t smem = std::max(h->stream_smem, stream_smem_bytes(sa.geom));
     void* fn = lnl ? (void*)em_stream_kernel<STREAM_THREADS, true> : (void*)em_stream_kernel<STREAM_THREADS, false>;
     SS_CUDA_CHECK(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;

@@ -218,3 +218,286 @@ __device__ __forceinline__ void group_sync() {
 }
 
 }  // namespace ss
+
+namespace ss {
+
+// ---------------------------------------------------------------------------------------------------
+// Streaming tile pass with lane fragments (segments too large to stay on chip: celltype / pseudobulk
+// models and cells beyond the cluster size).  One E+M half-iteration over the tiles assigned to this
+// CTA: r_i = sum_j Q_ij x_j per row, partial thetasum per tile column -> fp64 RED into T[colmap[c]].
+//   * the tile arrays (Q, index words, row weights, lengths, column pointers, JDS pointers, column map)
+//     arrive by TMA bulk copies into one of TWO shared-memory buffers: the next tile is in flight while
+//     the current one is computed (HBM is the bound of this pass: 12 B per alignment + ~6 B of row /
+//     column metadata);
+//   * the compute is the lane kernel's: rows and columns are cut into fragments of <= 4 alignments,
+//     long rows / columns span aligned lane groups combined by xor shuffles, so that a tile costs the
+//     same few hundred cycles in every warp instead of "the longest row of warp 0".
+// ---------------------------------------------------------------------------------------------------
+struct StreamGeom {
+  int pe, pr, pc, pj;   // padded maxima over the streamed tiles
+  int nbuf;             // 2: double buffered, 1: the largest tile leaves no room for a second buffer
+};
+__host__ __device__ inline size_t stream_buf_bytes(const StreamGeom& g) {
+  return 12 * (size_t)g.pe + 10 * (size_t)g.pr + 6 * (size_t)g.pc + 2 * (size_t)g.pj;
+}
+__host__ __device__ inline size_t stream_smem_bytes(const StreamGeom& g) {
+  return (size_t)g.nbuf * stream_buf_bytes(g) + 8 * ((size_t)g.pe + 8) + 8 * (size_t)g.pc + 128;
+}
+
+// double buffered when two buffers + scratch fit `limit` bytes of shared memory
+inline StreamGeom make_stream_geom(const int* gm, size_t limit) {
+  StreamGeom g;
+  g.pe = gm[0]; g.pr = gm[1]; g.pc = gm[2]; g.pj = gm[3];
+  g.nbuf = 2;
+  if (stream_smem_bytes(g) > limit) g.nbuf = 1;
+  return g;
+}
+
+struct StreamBuf {
+  const double* q; const double* w; const uint32_t* idx; const int* gcol;
+  const uint16_t* rlen; const uint16_t* cptr; const uint16_t* jptr;
+};
+__device__ __forceinline__ StreamBuf carve_stream(unsigned char* base, const StreamGeom& g) {
+  StreamBuf b;
+  unsigned char* p = base;
+  b.q = reinterpret_cast<const double*>(p);       p += 8 * (size_t)g.pe;
+  b.w = reinterpret_cast<const double*>(p);       p += 8 * (size_t)g.pr;
+  b.idx = reinterpret_cast<const uint32_t*>(p);   p += 4 * (size_t)g.pe;
+  b.gcol = reinterpret_cast<const int*>(p);       p += 4 * (size_t)g.pc;
+  b.rlen = reinterpret_cast<const uint16_t*>(p);  p += 2 * (size_t)g.pr;
+  b.cptr = reinterpret_cast<const uint16_t*>(p);  p += 2 * (size_t)g.pc;
+  b.jptr = reinterpret_cast<const uint16_t*>(p);
+  return b;
+}
+__device__ __forceinline__ void stream_issue_loads(const Layout& L, const int* colmap, const TileView& v,
+                                                   const StreamBuf& b, uint64_t* bar) {
+  const uint32_t bytes = 12u * v.pe + 10u * v.pr + 6u * v.pc + 2u * v.pj;
+  mbar_expect_tx(bar, bytes);
+  bulk_g2s((void*)b.q, L.e_q + v.eo, 8u * v.pe, bar);
+  bulk_g2s((void*)b.idx, L.e_idx + v.eo, 4u * v.pe, bar);
+  bulk_g2s((void*)b.w, L.r_w + v.ro, 8u * v.pr, bar);
+  bulk_g2s((void*)b.rlen, L.r_len + v.ro, 2u * v.pr, bar);
+  bulk_g2s((void*)b.cptr, L.c_ptr + v.co, 2u * v.pc, bar);
+  bulk_g2s((void*)b.jptr, L.j_ptr + v.jo, 2u * v.pj, bar);
+  bulk_g2s((void*)b.gcol, colmap + v.co, 4u * v.pc, bar);
+}
+
+__device__ __forceinline__ double group_xor_sum_s(double a, int g, int gmax) {
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    if (o < gmax) {
+      const double t = __shfl_xor_sync(full, a, o);
+      if (o < g) a += t;
+    }
+  }
+  return a;
+}
+
+#ifdef SS_STREAM_PROFILE
+__device__ long long g_st_prof[8];
+#define ST_TICK(i) { const long long c1_ = clock64(); if (blockIdx.x == 0 && threadIdx.x == 0) g_st_prof[i] += c1_ - c0_; c0_ = c1_; }
+#define ST_T0 long long c0_ = clock64();
+#else
+#define ST_TICK(i)
+#define ST_T0
+#endif
+// compute of one tile whose arrays are in `b`; xs = tile-local x (ncol + 1 slots), val = scratch (pe + 8)
+template <int THREADS, int FR, int FC>
+__device__ __forceinline__ void lane_tile_compute(const long long* __restrict__ hd, const TileView& v, const StreamBuf& b,
+                                                  const double* __restrict__ x, double* __restrict__ T, double* xs,
+                                                  double* val) {
+  constexpr int NW = THREADS / 32;
+  const unsigned full = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  ST_T0
+  // ---- tile-local x ----
+  for (int c = tid; c < v.ncol; c += THREADS) xs[c] = __ldcg(x + b.gcol[c]);
+  if (tid == 0) xs[v.ncol] = 0.0;
+  __syncthreads();
+  ST_TICK(1)
+  // ---- phase A: row fragments ----
+  {
+    const int rgt4 = (int)hd[H_RGT4], rgt8 = (int)hd[H_RGT8], rgt16 = (int)hd[H_RGT16], rgt32 = (int)hd[H_RGT32];
+    const int n_huge = rgt32;
+    const int n8 = rgt16 - rgt32, n4 = rgt8 - rgt16, n2 = rgt4 - rgt8, n1 = v.nrows - rgt4;
+    const int V8 = 8 * n8, V4 = V8 + 4 * n4, V2 = V4 + 2 * n2, V = V2 + n1;
+    const int Vc = min(V, FR * THREADS);
+    int r_ovf;
+    if (Vc >= V) r_ovf = v.nrows;
+    else if (Vc < V8) r_ovf = n_huge + Vc / 8;
+    else if (Vc < V4) r_ovf = n_huge + n8 + (Vc - V8) / 4;
+    else if (Vc < V2) r_ovf = n_huge + n8 + n4 + (Vc - V4) / 2;
+    else r_ovf = n_huge + n8 + n4 + n2 + (Vc - V2);
+#pragma unroll
+    for (int j = 0; j < FR; ++j) {
+      const int vl = tid + j * THREADS;
+      if (j * THREADS >= Vc) break;                                  // block-uniform
+      int n = 0, g = 1, r = 0, k = 0;
+      if (vl < Vc) {
+        if (vl < V8) { g = 8; r = n_huge + vl / 8; k = vl % 8; }
+        else if (vl < V4) { g = 4; r = n_huge + n8 + (vl - V8) / 4; k = (vl - V8) % 4; }
+        else if (vl < V2) { g = 2; r = n_huge + n8 + n4 + (vl - V4) / 2; k = (vl - V4) % 2; }
+        else { g = 1; r = n_huge + n8 + n4 + n2 + (vl - V2); k = 0; }
+        n = max(0, min(FRAG, (int)b.rlen[r] - FRAG * k));
+      }
+      const int nmax = __reduce_max_sync(full, n);
+      if (nmax == 0) continue;                                        // warp-uniform
+      const int gmax = __reduce_max_sync(full, g);
+      double fq[FRAG];
+      uint32_t fi[FRAG];
+      double acc = 0.0;
+#pragma unroll
+      for (int p = 0; p < FRAG; ++p) {
+        fq[p] = 0.0;
+        fi[p] = 0u;
+        if (p < n) {
+          const int e = (int)b.jptr[FRAG * k + p] + r;
+          fi[p] = b.idx[e];
+          fq[p] = b.q[e];
+          acc = fma(fq[p], xs[fi[p] & 0xffffu], acc);
+        }
+      }
+      if (gmax > 1) acc = group_xor_sum_s(acc, g, gmax);
+      const bool pos = acc > 0.0;
+      double inv = 1.0 / (pos ? acc : 1.0);
+      inv = pos ? inv : 0.0;
+      const double sc = (n > 0 ? b.w[r] : 0.0) * inv;
+#pragma unroll
+      for (int p = 0; p < FRAG; ++p)
+        if (p < n) val[fi[p] >> 16] = fq[p] * sc;
+    }
+    if (n_huge > 0 || r_ovf < v.nrows) {
+      for (int r = tid; r < v.nrows; r += THREADS) {                 // rows outside the lanes (rare)
+        const int rr = r < n_huge ? r : r_ovf + (r - n_huge);
+        if (rr >= v.nrows) break;
+        const int len = b.rlen[rr];
+        double acc = 0.0;
+        for (int p = 0; p < len; ++p) {
+          const int e = (int)b.jptr[p] + rr;
+          acc = fma(b.q[e], xs[b.idx[e] & 0xffffu], acc);
+        }
+        const double sc = acc > 0.0 ? b.w[rr] * (1.0 / acc) : 0.0;
+        for (int p = 0; p < len; ++p) {
+          const int e = (int)b.jptr[p] + rr;
+          val[b.idx[e] >> 16] = b.q[e] * sc;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  ST_TICK(2)
+  // ---- phase B: column fragments -> RED into T ----
+  {
+    const int b128 = (int)hd[H_CGT128];
+    const int b64 = (int)hd[H_CGT64], b32 = (int)hd[H_CGT32], b16 = (int)hd[H_CGT16], b8 = (int)hd[H_CGT8],
+              b4 = (int)hd[H_CGT4];
+    const int W32 = 32 * (b64 - b128), W16 = W32 + 16 * (b32 - b64), W8 = W16 + 8 * (b16 - b32);
+    const int W4 = W8 + 4 * (b8 - b16), W2 = W4 + 2 * (b4 - b8), W = W2 + (v.ncol - b4);
+    const int Wc = min(W, FC * THREADS);
+    int c_ovf;
+    if (Wc >= W) c_ovf = v.ncol;
+    else if (Wc < W32) c_ovf = b128 + Wc / 32;
+    else if (Wc < W16) c_ovf = b64 + (Wc - W32) / 16;
+    else if (Wc < W8) c_ovf = b32 + (Wc - W16) / 8;
+    else if (Wc < W4) c_ovf = b16 + (Wc - W8) / 4;
+    else if (Wc < W2) c_ovf = b8 + (Wc - W4) / 2;
+    else c_ovf = b4 + (Wc - W2);
+#pragma unroll
+    for (int j = 0; j < FC; ++j) {
+      const int vl = tid + j * THREADS;
+      if (j * THREADS >= Wc) break;                                  // block-uniform
+      int n = 0, g = 1, c = 0, k = 0, base = 0;
+      if (vl < Wc) {
+        if (vl < W32) { g = 32; c = b128 + vl / 32; k = vl % 32; }
+        else if (vl < W16) { g = 16; c = b64 + (vl - W32) / 16; k = (vl - W32) % 16; }
+        else if (vl < W8) { g = 8; c = b32 + (vl - W16) / 8; k = (vl - W16) % 8; }
+        else if (vl < W4) { g = 4; c = b16 + (vl - W8) / 4; k = (vl - W8) % 4; }
+        else if (vl < W2) { g = 2; c = b8 + (vl - W4) / 2; k = (vl - W4) % 2; }
+        else { g = 1; c = b4 + (vl - W2); k = 0; }
+        const int cb = b.cptr[c];
+        base = cb + FRAG * k;
+        n = max(0, min(FRAG, (int)b.cptr[c + 1] - base));
+      }
+      const int gmax = __reduce_max_sync(full, g);
+      double asum = 0.0;
+#pragma unroll
+      for (int i = 0; i < FRAG; ++i)
+        if (i < n) asum += val[base + i];
+      if (gmax > 1) asum = group_xor_sum_s(asum, g, gmax);
+      if (vl < Wc && k == 0) atomicAdd(&T[b.gcol[c]], xs[c] * asum);
+    }
+    for (int c = warp; c < b128; c += NW) {                          // very long columns: one warp each
+      const int cb = b.cptr[c], n = (int)b.cptr[c + 1] - cb;
+      const double asum = col_sum_warp(val, cb, n, lane);
+      if (lane == 0) atomicAdd(&T[b.gcol[c]], xs[c] * asum);
+    }
+    for (int c = c_ovf + tid; c < v.ncol; c += THREADS) {            // columns beyond the lanes
+      const int cb = b.cptr[c], n = (int)b.cptr[c + 1] - cb;
+      atomicAdd(&T[b.gcol[c]], xs[c] * col_sum_thread(val, cb, n));
+    }
+  }
+  ST_TICK(3)
+}
+
+// the tiles tiles[i] (or i itself when tiles == nullptr), i = blockIdx.x, blockIdx.x + gridDim.x, ...;
+// tiles of segments with seg_done[seg] != 0 are skipped.  `uses[b]` counts the fills of buffer b (mbarrier parity).
+template <int THREADS, int FR, int FC>
+__device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __restrict__ colmap, const int* __restrict__ tiles,
+                                                 int n_items, const int* seg_done, const double* __restrict__ x,
+                                                 double* __restrict__ T, const StreamGeom& g, unsigned char* dsm,
+                                                 uint64_t* bars, uint32_t* uses) {
+  const int tid = threadIdx.x;
+  const size_t bb = stream_buf_bytes(g);
+  double* val = reinterpret_cast<double*>(dsm + (size_t)g.nbuf * bb);
+  double* xs = val + g.pe + 8;
+  auto next_item = [&](int i) {
+    while (i < n_items) {
+      const int t = tiles ? tiles[i] : i;
+      if (!seg_done || ((volatile const int*)seg_done)[(int)L.tile_hdr[(long long)HDR_WORDS * t + H_SEG]] == 0) break;
+      i += gridDim.x;
+    }
+    return i;
+  };
+  int cur = next_item(blockIdx.x);
+  int nb = 0;
+  if (cur < n_items && tid == 0) {
+    const int t = tiles ? tiles[cur] : cur;
+    fence_proxy_async();
+    stream_issue_loads(L, colmap, load_tile_view(L.tile_hdr, t), carve_stream(dsm, g), &bars[0]);
+  }
+  while (cur < n_items) {
+    const int b_cur = g.nbuf == 2 ? (nb & 1) : 0;
+    const int nxt = next_item(cur + gridDim.x);
+    if (g.nbuf == 2 && nxt < n_items && tid == 0) {
+      const int t = tiles ? tiles[nxt] : nxt;
+      fence_proxy_async();
+      stream_issue_loads(L, colmap, load_tile_view(L.tile_hdr, t), carve_stream(dsm + (size_t)(b_cur ^ 1) * bb, g),
+                         &bars[b_cur ^ 1]);
+    }
+    const int t = tiles ? tiles[cur] : cur;
+    const TileView v = load_tile_view(L.tile_hdr, t);
+    const StreamBuf b = carve_stream(dsm + (size_t)b_cur * bb, g);
+#ifdef SS_STREAM_PROFILE
+    long long c0_ = clock64();
+#endif
+    mbar_wait(&bars[b_cur], uses[b_cur] & 1);
+    uses[b_cur]++;
+    ST_TICK(0)
+    lane_tile_compute<THREADS, FR, FC>(L.tile_hdr + (long long)HDR_WORDS * t, v, b, x, T, xs, val);
+    __syncthreads();                                              // buffers, val and xs are free again
+#ifdef SS_STREAM_PROFILE
+    c0_ = clock64() - 0;   // (B tail + barrier counted with the next wait)
+    if (blockIdx.x == 0 && tid == 0) g_st_prof[7] += 1;
+#endif
+    if (g.nbuf == 1 && nxt < n_items && tid == 0) {
+      const int t2 = tiles ? tiles[nxt] : nxt;
+      fence_proxy_async();
+      stream_issue_loads(L, colmap, load_tile_view(L.tile_hdr, t2), carve_stream(dsm, g), &bars[0]);
+    }
+    cur = nxt;
+    ++nb;
+  }
+}
+
+}  // namespace ss

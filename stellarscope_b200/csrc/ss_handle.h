@@ -39,6 +39,7 @@ constexpr int SS_CLS_THREADS[] = {SS_CLS_LIST, SS_BIG_THREADS_V};
 constexpr int SS_NUM_CLASSES = (int)(sizeof(SS_CLS_THREADS) / sizeof(int));
 constexpr int SS_NUM_AUX_STREAMS = SS_NUM_CLASSES + 1 + 7;   // size classes, streaming kernel, cluster sizes 2..8
 constexpr int SS_DN_MAXW = 8;   // ranks of a row-sharded (dense) fit: the GPUs of one NVSwitch domain
+constexpr int SS_DN_THREADS = 1024;   // CTA size of the row-sharded kernels = columns per update chunk
 constexpr int SS_DN_TAIL = 8;   // scalar slots behind the K columns of an exchange buffer ([0] = lnL part)
 
 struct ss_handle_s {
@@ -80,6 +81,8 @@ struct ss_handle_s {
   int n_cluster_tiles = 0, n_cluster_segs = 0;
   int* all_tiles = nullptr;       // device: 0 .. n_tiles-1
   size_t all_smem = 0;            // smem of the largest tile (likelihood-mode carve)
+  int geom_all[4] = {8, 8, 8, 8};     // padded maxima (pe, pr, pc, pj) over all tiles / over the streamed tiles
+  int geom_stream[4] = {8, 8, 8, 8};
   int8_t* sc_inamb = nullptr;     // device: segment column is touched by a tile
   long long nnz_amb = 0, rows_amb = 0;
 
@@ -109,6 +112,7 @@ struct ss_handle_s {
   // ---- row-sharded single-model fit (ss_dense.cu) ----
   bool dn_force = false;          // dense path on a single rank (tests)
   bool dn_peers = false;          // exchange buffers in peer-mapped symmetric memory
+  bool dn_persistent = false;     // whole fit in one cooperative kernel (peers, or a single rank)
   int dn_world = 1, dn_rank = 0;
   void* dn_peer_base[SS_DN_MAXW] = {};
   size_t dn_peer_bytes = 0;

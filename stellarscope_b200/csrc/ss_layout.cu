@@ -143,6 +143,7 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
   h->rows_amb = 0;
   for (int c = 0; c < SS_NUM_CLASSES; ++c) h->cls_smem[c] = 0;
   h->stream_smem = 0;
+  for (int i = 0; i < 4; ++i) h->geom_all[i] = h->geom_stream[i] = 8;
   // segments of 2..8 tiles whose tiles (plus the owner arrays) fit shared memory run as clusters
   const int MAXC = ss_handle_s::MAX_CLUSTER;
   std::vector<char> seg_clustered((size_t)std::max(L.S, 1), 0);
@@ -182,6 +183,8 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
     h->rows_amb += nrows;
     const size_t b0 = tile_smem_bytes(nent, nrows, ncol, maxlen);
     all_smem = std::max(all_smem, b0);
+    const int gm[4] = {pad8(nent), pad8(nrows), pad8(ncol + 1), pad8(maxlen + 1)};
+    for (int i = 0; i < 4; ++i) h->geom_all[i] = std::max(h->geom_all[i], gm[i]);
     if (b0 + 1024 > h->max_smem_optin) {
       h->set_error("tile exceeds the shared-memory capacity");
       return SS_ERR_CAPACITY;
@@ -215,6 +218,7 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
     } else {
       stream.push_back(t);
       h->stream_smem = std::max(h->stream_smem, b0);
+      for (int i = 0; i < 4; ++i) h->geom_stream[i] = std::max(h->geom_stream[i], gm[i]);
     }
   }
   h->all_smem = all_smem;

@@ -213,6 +213,8 @@ class Engine:
                     logging.getLogger(__name__).warning('symmetric memory unavailable (%s): using the NCCL hook '
                                                         'for the per-iteration exchange', e)
                     ptr_arr, nbytes = None, 0
+        if world == 1 and not peers:
+            nbytes = -1                                     # single rank, host-loop variant (tests)
         self._check(self.lib.ss_set_peers(self.h, rank, world, ptr_arr, nbytes))
 
     def sync_ranks(self):
