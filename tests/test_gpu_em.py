@@ -181,3 +181,87 @@ def test_full_size_properties_config2_shape():
     assert np.array_equal(r1['iters'], r2['iters'])
     assert np.allclose(r1['lnl'], r2['lnl'], rtol=1e-12, atol=0)
     eng.close()
+
+
+def test_long_rows_take_the_generic_paths():
+    """Reads with up to 60 alignments (rows longer than 32 leave the lane groups) in small cells, one
+    multi-tile cell and the pseudobulk model -- lane, cluster and streaming kernels against the oracle."""
+    d = H.small_synth(seed=31, n_cells=8, n_alignments=30000, n_loci=400)
+    # every 37th read becomes a read with 33..60 alignments on random loci
+    rng = np.random.default_rng(31)
+    idx, sc, ptr = [], [], [0]
+    for i in range(d.N):
+        a, b = d.indptr[i], d.indptr[i + 1]
+        if i % 37 == 0:
+            k = int(rng.integers(33, 61))
+            cols = np.sort(rng.choice(np.arange(1, d.K), size=k, replace=False))
+            idx.append(cols.astype(np.int32))
+            sc.append((140 + rng.binomial(120, 0.65, k)).astype(np.uint16))
+        else:
+            idx.append(d.indices[a:b])
+            sc.append(d.scores[a:b])
+        ptr.append(ptr[-1] + len(idx[-1]))
+    d.indptr, d.indices, d.scores = np.array(ptr, dtype=np.int32), np.concatenate(idx), np.concatenate(sc)
+    assert np.diff(d.indptr).max() > 32
+    _fit_and_compare(d, d.row_cell, d.cell_rows(), Opts())
+    _fit_and_compare(d, np.zeros(d.N, dtype=np.int32), [np.arange(d.N)], Opts())
+
+
+def test_non_canonical_input_is_canonicalised_like_the_reference():
+    """Unsorted column indices, explicit zeros and duplicate entries: the device builder reports
+    SS_ERR_NOT_CANONICAL, the host canonicalises (csr_matrix + eliminate_zeros, model.py:113-114) and the
+    fit equals the fit of the canonical matrix."""
+    import scipy.sparse as sp
+    from stellarscope_b200 import model
+    from stellarscope_b200.engine import Engine, NotCanonicalError
+    d = H.small_synth(seed=32, n_cells=5, n_alignments=3000, n_loci=200)
+    m = sp.csr_matrix((d.scores.astype(np.int64), d.indices, d.indptr), shape=(d.N, d.K))
+    # scramble: reverse the order inside every row, add an explicit zero and split one entry in two
+    idx, dat, ptr = [], [], [0]
+    for i in range(d.N):
+        a, b = d.indptr[i], d.indptr[i + 1]
+        ci, cv = list(d.indices[a:b][::-1]), list(d.scores[a:b][::-1].astype(np.int64))
+        if i % 7 == 0 and b > a:
+            ci.append(ci[0]); cv.append(3); cv[0] -= 3          # duplicate column, same total
+        if i % 5 == 0:
+            free = [c for c in range(d.K) if c not in ci][:1]
+            ci += free; cv += [0] * len(free)                    # explicit zero
+        idx += ci; dat += cv; ptr.append(len(idx))
+    bad = sp.csr_matrix((np.array(dat), np.array(idx), np.array(ptr)), shape=(d.N, d.K))
+    assert not bad.has_sorted_indices
+    eng = Engine()
+    eng.set_matrix(bad.indptr, bad.indices, bad.data, d.K)
+    with pytest.raises(NotCanonicalError):
+        eng.build_layout(np.zeros(d.N, dtype=np.int32), 1)
+    eng.close()
+    o = H.StOpts()
+    t_bad = model.TelescopeLikelihood(bad, o)
+    t_ok = model.TelescopeLikelihood(m, o)
+    t_bad.em()
+    t_ok.em()
+    assert len(t_bad.fitinfo.iterations) == len(t_ok.fitinfo.iterations)
+    assert t_bad.lnl == t_ok.lnl
+    assert np.array_equal(t_bad.raw_scores.indices, t_ok.raw_scores.indices)
+    assert np.array_equal(np.asarray(t_bad.pi.todense()), np.asarray(t_ok.pi.todense()))
+    assert np.array_equal(t_bad.z.data, t_ok.z.data)
+
+
+def test_capacity_and_empty_inputs():
+    from stellarscope_b200 import model, _lib
+    from stellarscope_b200.engine import Engine, EngineError
+    import scipy.sparse as sp
+    # a read with more alignments than half a tile: explicit capacity error, not a wrong answer
+    K = 3000
+    indptr = np.array([0, 2500, 2502], dtype=np.int32)
+    indices = np.concatenate([np.arange(2500), [1, 2]]).astype(np.int32)
+    scores = np.full(2502, 150, dtype=np.uint16)
+    eng = Engine()
+    eng.set_matrix(indptr, indices, scores, K)
+    with pytest.raises(EngineError) as ei:
+        eng.build_layout(np.zeros(2, dtype=np.int32), 1)
+    assert ei.value.status == _lib.SS_ERR_CAPACITY
+    eng.close()
+    # no alignments at all: the reference's M-step divides by zero -> StellarscopeError (model.py:267-272)
+    empty = sp.csr_matrix((4, 10), dtype=np.uint16)
+    with pytest.raises(model.StellarscopeError):
+        model.TelescopeLikelihood(empty, H.StOpts()).em()
