@@ -306,7 +306,7 @@ def run_ours(args):
         h2d = tl._engine.h2d_bytes
         d2h = (4 * 4 + 8) * tl.n_segments      # iterations, flags, nobs, nfeats, lnL per model (the diff traces stay
                                                # on the device until a FitInfo.iterations is looked at)
-        tl._engine.close()
+        tl.close()
     e2e_dt = float(np.mean(e2e_times))
 
     # ---- reduce over ranks ----

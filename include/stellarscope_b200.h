@@ -85,6 +85,8 @@ int ss_abi_version(void);
 /* one handle per (process, GPU) */
 int ss_create(int device, ss_handle_t* out);
 int ss_destroy(ss_handle_t h);
+/* drop the layout, the fit state and their device memory; the handle (streams, events) stays usable */
+int ss_release(ss_handle_t h);
 const char* ss_last_error(ss_handle_t h);
 
 /* Build the tiled segment layout on the device.

@@ -8,10 +8,10 @@ d = bench.make_workload(0)
 opts = bench.BenchOpts()
 st = bench.make_st(d, opts)
 for _ in range(3):
-    tl, pi = model._fit_pooling_model(st, opts); torch.cuda.synchronize(); tl._engine.close()
+    tl, pi = model._fit_pooling_model(st, opts); torch.cuda.synchronize(); tl.close()
 pr = cProfile.Profile()
 pr.enable()
 for _ in range(5):
-    tl, pi = model._fit_pooling_model(st, opts); torch.cuda.synchronize(); tl._engine.close()
+    tl, pi = model._fit_pooling_model(st, opts); torch.cuda.synchronize(); tl.close()
 pr.disable()
 pstats.Stats(pr).sort_stats('cumulative').print_stats(28)

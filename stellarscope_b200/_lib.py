@@ -65,6 +65,7 @@ SIGNATURES = {
     'ss_abi_version': (C.c_int, []),
     'ss_create': (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     'ss_destroy': (C.c_int, [C.c_void_p]),
+    'ss_release': (C.c_int, [C.c_void_p]),
     'ss_last_error': (C.c_char_p, [C.c_void_p]),
     'ss_layout_build': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),

@@ -69,6 +69,15 @@ int ss_destroy(ss_handle_t h) {
   return SS_OK;
 }
 
+int ss_release(ss_handle_t h) {
+  SS_REQUIRE_HANDLE(h);
+  cudaSetDevice(h->device);
+  free_fit(h);
+  free_dense(h);
+  free_layout(h);
+  return SS_OK;
+}
+
 const char* ss_last_error(ss_handle_t h) { return h ? h->err.c_str() : "null handle"; }
 
 int ss_layout_build(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, int64_t nnz, const int32_t* row_ptr,

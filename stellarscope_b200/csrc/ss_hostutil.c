@@ -81,11 +81,11 @@ static Py_ssize_t fill_threaded(PyObject** items, Py_ssize_t ng, const int32_t* 
     total += PySet_GET_SIZE(items[g]);
   }
   long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
-  int nt = (int)(ncpu < 1 ? 1 : (ncpu > 8 ? 8 : ncpu));
-  { const char* e = getenv("SS_HOST_THREADS"); if (e) nt = atoi(e) < 1 ? 1 : (atoi(e) > 8 ? 8 : atoi(e)); }
+  int nt = (int)(ncpu < 1 ? 1 : (ncpu > 16 ? 16 : ncpu));
+  { const char* e = getenv("SS_HOST_THREADS"); if (e) nt = atoi(e) < 1 ? 1 : (atoi(e) > 16 ? 16 : atoi(e)); }
   if (total < 200000 || nt < 2) return -1;  /* small inputs: the serial path is as fast */
-  worker_t w[8];
-  pthread_t th[8];
+  worker_t w[16];
+  pthread_t th[16];
   Py_ssize_t g = 0, acc = 0;
   for (int i = 0; i < nt; ++i) {
     w[i].items = items; w[i].ids = ids; w[i].seg = seg; w[i].n = n; w[i].count = 0; w[i].status = 0;

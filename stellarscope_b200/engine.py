@@ -96,6 +96,32 @@ class Engine:
         self.max_iter = 0
 
     # -- plumbing ------------------------------------------------------------
+    _pool = {}          # device index -> idle engines (handle, internal streams and events are reused)
+
+    @classmethod
+    def acquire(cls, device=None):
+        """An idle pooled engine of the device, or a new one.  Creating a handle costs ~2 ms (streams,
+        events); a fit of 10^4 cells takes as long."""
+        if not torch.cuda.is_available():
+            raise RuntimeError('stellarscope_b200 needs a CUDA device (there is no CPU fallback)')
+        idx = torch.cuda.current_device() if device is None else torch.device('cuda', device).index
+        idle = cls._pool.get(idx)
+        if idle:
+            return idle.pop()
+        return cls(idx)
+
+    def release(self):
+        """Return the engine to the pool (its device buffers are dropped, the handle stays)."""
+        if getattr(self, 'h', None) is None:
+            return
+        if getattr(self, 'sharded', False):
+            self.close()                     # sharded handles carry peer buffers / hooks: do not reuse
+            return
+        self.lib.ss_release(self.h)
+        self._keep = {}
+        self._params_cache = None
+        Engine._pool.setdefault(self.device.index, []).append(self)
+
     def close(self):
         if getattr(self, 'h', None):
             self.lib.ss_destroy(self.h)

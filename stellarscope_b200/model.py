@@ -72,7 +72,7 @@ class TelescopeLikelihood(object):
         m = score_matrix if scipy.sparse.isspmatrix_csr(score_matrix) else scipy.sparse.csr_matrix(score_matrix)
         self.N, self.K = m.shape
         self.scale_factor = 100.
-        self._engine = Engine(device)
+        self._engine = Engine(device) if shard is not None else Engine.acquire(device)
         if shard is not None:
             # ONE model whose rows are spread over ranks: (rank, world, process group[, peers])
             rank, world, group = shard[:3]
@@ -110,6 +110,18 @@ class TelescopeLikelihood(object):
         self.fitinfo = FitInfo(epsilon=self.epsilon, max_iter=self.max_iter)
         self.segment_fitinfo = None
         self.fit_seconds = None
+
+    def close(self):
+        """Give the device resources back (the engine handle returns to a pool)."""
+        eng, self._engine = getattr(self, '_engine', None), None
+        if eng is not None:
+            eng.release()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     # -- lazily materialised views the reference exposes as attributes ----------
     @property
