@@ -38,6 +38,11 @@ sys.path.insert(0, ROOT)
 METRIC = 'alignments_x_em_iterations_per_sec'
 UNIT = 'aln*iter/s'
 WORKLOAD = dict(n_cells=10_000, n_alignments=5_000_000, n_loci=28_000)
+# dram__bytes_read.sum + dram__bytes_write.sum of the 16 fused E+M kernels of ONE fit of this workload, from the
+# ncu --set full capture profiles/r1c_em_full_ncu.csv (110.86 MB read + 0.23 MB written): every cell is read from
+# HBM once; the iterations run out of registers / shared memory
+NCU_DRAM_BYTES_PER_FIT = 111.1e6
+NCU_DRAM_SOURCE = 'profiles/r1c_em_full_ncu.csv (ncu --set full, one fit, sum over the 16 EM kernels)'
 CPU_SAMPLE_CELLS = 10000     # the CPU baseline fits every cell of the workload (about 10-15 s on 16 cores)
 OPTS = dict(em_epsilon=1e-7, max_iter=100, pi_prior=0, theta_prior=200000)   # stellarscope_assign.yaml:231-250
 
@@ -73,7 +78,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in line.split(',')])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.02)
 
     def stop(self):
         self._halt.set()
@@ -343,7 +348,8 @@ def run_ours(args):
                      seconds_per_step=e2e_max, api='stellarscope_b200.model._fit_pooling_model(st, opts)'),
             gpu_launches=int(launches_all),
             roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
-                          traffic=None,
+                          traffic=NCU_DRAM_BYTES_PER_FIT if world == 1 else None,
+                          traffic_source=NCU_DRAM_SOURCE,
                           kernel='fused E+M kernels of one fit: em_lane_kernel (one launch per CTA-size class) + '
                                  'em_cluster_kernel (cells of 2..8 tiles), launched concurrently',
                           note='EFFECTIVE bandwidth: algorithmic bytes = iterations x (12 B/ambiguous alignment + '
