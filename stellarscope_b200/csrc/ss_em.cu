@@ -1401,7 +1401,7 @@ static cudaError_t ensure_aux_streams(ss_handle_s* h) {
   return cudaSuccess;
 }
 
-constexpr int STREAM_THREADS = 1024;
+constexpr int STREAM_THREADS = 512;
 constexpr int CLUSTER_THREADS = 512;
 
 int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {

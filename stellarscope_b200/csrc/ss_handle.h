@@ -39,7 +39,7 @@ constexpr int SS_CLS_THREADS[] = {SS_CLS_LIST, SS_BIG_THREADS_V};
 constexpr int SS_NUM_CLASSES = (int)(sizeof(SS_CLS_THREADS) / sizeof(int));
 constexpr int SS_NUM_AUX_STREAMS = SS_NUM_CLASSES + 1 + 7;   // size classes, streaming kernel, cluster sizes 2..8
 constexpr int SS_DN_MAXW = 8;   // ranks of a row-sharded (dense) fit: the GPUs of one NVSwitch domain
-constexpr int SS_DN_THREADS = 1024;   // CTA size of the row-sharded kernels = columns per update chunk
+constexpr int SS_DN_THREADS = 512;    // CTA size of the row-sharded kernels = columns per update chunk
 constexpr int SS_DN_TAIL = 8;   // scalar slots behind the K columns of an exchange buffer ([0] = lnL part)
 
 struct ss_handle_s {

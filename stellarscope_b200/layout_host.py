@@ -31,6 +31,8 @@ from dataclasses import dataclass
 import numpy as np
 
 E_HARD = 4096        # hard cap on alignments per tile (shared-memory budget, csrc/ss_common.cuh)
+E_STREAM = 2048      # tile size of streamed segments (more than STREAM_SEG_TILES large tiles)
+STREAM_SEG_TILES = 8
 ALIGN = 8            # every per-tile slice starts at a multiple of 8 elements
 
 
@@ -184,7 +186,11 @@ def build(indptr, indices, scores, row_seg, S, K, e_hard=E_HARD, long_col=32):
     seg_row0 = np.searchsorted(aseg, np.arange(S))
     seg_ent0 = pre[np.minimum(seg_row0, len(ar))]
     o = pre[:-1] - seg_ent0[aseg] if len(ar) else np.zeros(0, dtype=np.int64)
-    tin = o // chunk
+    # segments that will be streamed are cut into smaller tiles (csrc/ss_build.cu seg_chunk)
+    chunk_small = E_STREAM - maxlen + 1 if (e_hard == E_HARD and maxlen <= E_STREAM // 2) else chunk
+    seg_aamb = np.bincount(aseg, weights=alen, minlength=S).astype(np.int64) if len(ar) else np.zeros(S, dtype=np.int64)
+    seg_chunk = np.where(seg_aamb > STREAM_SEG_TILES * chunk, chunk_small, chunk)
+    tin = o // seg_chunk[aseg] if len(ar) else o
     seg_ntiles = np.zeros(S, dtype=np.int32)
     if len(ar):
         np.maximum.at(seg_ntiles, aseg, (tin + 1).astype(np.int32))
