@@ -169,6 +169,20 @@ int ss_count(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, const 
              const int32_t* row_umi, int64_t cap, int32_t* out_cell, int32_t* out_col, double* out_val,
              int64_t* n_out);
 
+/* UMI de-duplication, the step before the path (Stellarscope.dedup_umi model.py:1148-1219,
+ * select_umi_representatives :561-668).  Works on the CSR score matrix (raw_scores).
+ *   row_group[n_rows]: id of the barcode+UMI pair of the row (0 .. n_groups-1), -1 = row takes no part
+ *   excluded[n_rows] out: 1 for the duplicate reads that are NOT the representative of their connected
+ *            component (reads of one pair that share a feature != column 0 are connected; the
+ *            representative has the largest (max/sum, -n_features, max, sum, row), model.py:578-601)
+ *   comp_root[n_rows] out: smallest row of the read's component, -1 for reads of single-read pairs
+ *   group_size[n_groups], group_ncomp[n_groups] out: reads / connected components of every pair
+ *            (UMIInfo.rpu_counter, UMIInfo.ncomps_umi, statistics.py:498-570)
+ * Synchronises the stream. */
+int ss_umi_dedup(ss_handle_t h, void* stream, int32_t n_rows, const int32_t* row_ptr, const int32_t* col_idx,
+                 const uint16_t* score, const int32_t* row_group, int32_t n_groups, uint8_t* excluded,
+                 int32_t* comp_root, int32_t* group_size, int32_t* group_ncomp);
+
 /* ---- one model, rows sharded over the GPUs of a box (pooling_mode=pseudobulk) ----
  * The reference fits the pseudobulk model single-threaded (model.py:762-767).  Here every rank
  * (one process per GPU) holds a block of rows of the SAME model; ss_layout_build / ss_em_fit are

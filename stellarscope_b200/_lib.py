@@ -81,6 +81,8 @@ SIGNATURES = {
     'ss_count': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                            c_i64p]),
+    'ss_umi_dedup': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'ss_set_allreduce': (C.c_int, [C.c_void_p, ALLREDUCE_FN, C.c_void_p]),
     'ss_peer_buffer_bytes': (C.c_int64, [C.c_int32]),
     'ss_set_peers': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int64]),

@@ -301,6 +301,19 @@ int ss_count(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, const 
   return rc;
 }
 
+int ss_umi_dedup(ss_handle_t h, void* stream, int32_t n_rows, const int32_t* row_ptr, const int32_t* col_idx,
+                 const uint16_t* score, const int32_t* row_group, int32_t n_groups, uint8_t* excluded, int32_t* comp_root,
+                 int32_t* group_size, int32_t* group_ncomp) {
+  SS_REQUIRE_HANDLE(h);
+  if (n_rows < 0 || n_groups < 0 || !row_ptr || !row_group || !excluded || !comp_root || !group_size || !group_ncomp) {
+    h->set_error("ss_umi_dedup: bad argument");
+    return SS_ERR_ARG;
+  }
+  cudaSetDevice(h->device);
+  return umi_dedup(h, (cudaStream_t)stream, n_rows, row_ptr, col_idx, score, row_group, n_groups, excluded, comp_root,
+                   group_size, group_ncomp);
+}
+
 int ss_set_allreduce(ss_handle_t h, ss_allreduce_fn fn, void* user) {
   SS_REQUIRE_HANDLE(h);
   h->allreduce = fn;

@@ -420,6 +420,27 @@ class Engine:
             self._check(self.lib.ss_em_emit_z(self.h, self._stream(), self._p(z)))
         return z[:self.A]
 
+    # -- UMI de-duplication (the step before the path) ---------------------------
+    def umi_dedup(self, row_group, n_groups):
+        """ss_umi_dedup on the uploaded matrix.  ``row_group[i]`` = id of the barcode+UMI pair of row i.
+        Returns numpy arrays: excluded bool[N], comp_root int32[N], group_size / group_ncomp int32[n_groups]."""
+        dev, k = self.device, self._keep
+        n_groups = int(n_groups)
+        with torch.cuda.device(dev):
+            rg = row_group if isinstance(row_group, torch.Tensor) else self._to_dev(row_group, np.int32)
+            ex = torch.empty(max(self.N, 1), dtype=torch.uint8, device=dev)
+            i32 = torch.empty(max(self.N, 1) + 2 * max(n_groups, 1), dtype=torch.int32, device=dev)
+            root, gs, gc = i32[:max(self.N, 1)], i32[max(self.N, 1):max(self.N, 1) + max(n_groups, 1)], \
+                i32[max(self.N, 1) + max(n_groups, 1):]
+            rc = self.lib.ss_umi_dedup(self.h, self._stream(), self.N, self._p(k['row_ptr']), self._p(k['col_idx']),
+                                       self._p(k['score']), self._p(rg), n_groups, self._p(ex), self._p(root),
+                                       self._p(gs), self._p(gc))
+            self._check(rc)
+            h = i32.cpu().numpy()
+            n1 = max(self.N, 1)
+            return dict(excluded=ex[:self.N].cpu().numpy().astype(bool), comp_root=h[:self.N],
+                        group_size=h[n1:n1 + n_groups], group_ncomp=h[n1 + max(n_groups, 1):n1 + max(n_groups, 1) + n_groups])
+
     # -- reassign / count ------------------------------------------------------
     def reassign(self, mode, z=None, conf_thresh=0.9, tie_tol=0.0):
         """ss_reassign.  Returns (flag uint8[A] device, nbest int32[N] device, info numpy int64[68])."""

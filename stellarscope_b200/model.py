@@ -539,4 +539,6 @@ def install():
     ref._em_wrapper = _em_wrapper
     ref.Stellarscope.reassign = lambda self, tl: reassign(self, tl)
     ref.Stellarscope.output_report = lambda self, tl: output_report(self, tl)
+    from . import umi
+    ref.Stellarscope.dedup_umi = lambda self, output_report=True, summary=True: umi.dedup_umi(self, output_report, summary)
     return ref

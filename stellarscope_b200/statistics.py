@@ -311,3 +311,83 @@ class ReassignInfo(GenericInfo):
 def counter_from_hist(hist):
     """Device histogram of min(nbest, 63) -> ``Counter(nbest)`` (model.py:440)."""
     return Counter({int(k): int(v) for k, v in enumerate(hist) if v})
+
+
+class UMIInfo(GenericInfo):
+    """statistics.py:498-626 -- filled from the per-pair read / component counts the device returns
+    instead of from the reference's dict of dicts."""
+
+    def __init__(self, group_sizes=None):
+        super().__init__()
+        self.rpu_counter = Counter()
+        self.rpu_bins = []
+        self.rpu_hist = None
+        if group_sizes is not None and len(group_sizes):
+            self.init_rpu(group_sizes)
+        self.ncomps_umi = Counter()
+        self._nexclude = 0
+
+    num_umi = property(lambda self: sum(self.rpu_counter.values()))
+    uni_umi = property(lambda self: self.rpu_counter[1])
+    dup_umi = property(lambda self: sum(f for n, f in self.rpu_counter.items() if n > 1))
+    max_rpu = property(lambda self: max(self.rpu_counter))
+    possible_dups = property(lambda self: sum((n - 1) * f for n, f in self.rpu_counter.items()))
+    max_comps = property(lambda self: max(self.ncomps_umi) if self.ncomps_umi else 0)
+
+    @property
+    def nexclude(self):
+        return self._nexclude
+
+    @nexclude.setter
+    def nexclude(self, val):
+        self._nexclude = val
+
+    def init_rpu(self, group_sizes):
+        """statistics.py:552-570 with the reads-per-pair counts as an array."""
+        rpu = np.asarray(group_sizes)
+        vals, freq = np.unique(rpu, return_counts=True)
+        self.rpu_counter = Counter({int(v): int(f) for v, f in zip(vals, freq)})
+        if self.max_rpu <= 5:
+            self.rpu_bins = list(range(1, self.max_rpu + 2))
+        else:
+            self.rpu_bins = [1, 2, 3, 4, 5, 6, 11, 21]
+            if self.max_rpu > 20:
+                self.rpu_bins.append(self.max_rpu + 1)
+        self.rpu_hist, _bins = np.histogram(rpu, self.rpu_bins)
+
+    def _bin_label(self, b_i):
+        bs, be = self.rpu_bins[b_i], self.rpu_bins[b_i + 1]
+        if be == self.rpu_bins[-1]:
+            return f'>{bs - 1}'
+        return f'{bs}' if be - bs == 1 else f'{bs}-{be - 1}'
+
+    def loginit(self, loglev=lg.INFO):
+        lg.log(loglev, f'Number of BC+UMI pairs: {self.num_umi}')
+        lg.log(loglev, f'  unique UMIs: {self.uni_umi}')
+        lg.log(loglev, f'  duplicated UMIs: {self.dup_umi}')
+        lg.log(loglev, f'  max reads per UMI: {self.max_rpu}')
+        for b_i, v in enumerate(self.rpu_hist):
+            lg.log(loglev, f'    UMIs with {self._bin_label(b_i)} reads: {v}')
+        lg.log(loglev, f'  Possible duplicate reads: {self.possible_dups}')
+        lg.log(loglev, 'Finding duplicates and selecting representatives...')
+
+    def log(self, loglev=lg.INFO):
+        lg.log(loglev, f'    UMIs with 1 component: {self.ncomps_umi[1]}')
+        lg.log(loglev, f'    UMIs with 2 components: {self.ncomps_umi[2]}')
+        lg.log(loglev, f'    UMIs with 3 components: {self.ncomps_umi[3]}')
+        _gt3 = sum(v for k, v in self.ncomps_umi.items() if k > 3)
+        if _gt3:
+            lg.log(loglev, f'    UMIs with >3 components: {_gt3}')
+        lg.log(loglev, f'Total UMI duplicate reads excluded: {self.nexclude}')
+
+    def to_dataframe(self, binned=True):
+        ret = super().to_dataframe()
+        if binned:
+            for b_i, v in enumerate(self.rpu_hist):
+                ret.loc[len(ret.index)] = ['UMIInfo', 'umidist', self._bin_label(b_i), v]
+        else:
+            for nread in range(1, self.max_rpu + 1):
+                ret.loc[len(ret.index)] = ['UMIInfo', 'umidist', nread, self.rpu_counter[nread]]
+        for ncomp in range(1, self.max_comps + 1):
+            ret.loc[len(ret.index)] = ['UMIInfo', 'compdist', ncomp, self.ncomps_umi[ncomp]]
+        return ret
