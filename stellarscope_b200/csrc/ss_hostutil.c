@@ -240,7 +240,69 @@ static PyObject* number_groups(PyObject* self, PyObject* args) {
   return result;
 }
 
+/* pair_ids(read_index, bcode_map, umi_map, row_group) -> list of (barcode, umi) pairs in first-seen order
+ * row_group[read_index[q]] = index of (bcode_map[q], umi_map[q]) in that list, for every read q in the
+ * iteration order of read_index -- the integer coding of the reference's bcumi_read dict
+ * (Stellarscope.dedup_umi, model.py:1161-1164). */
+static PyObject* pair_ids(PyObject* self, PyObject* args) {
+  PyObject *read_index, *bmap, *umap, *rg_obj;
+  if (!PyArg_ParseTuple(args, "O!O!O!O", &PyDict_Type, &read_index, &PyDict_Type, &bmap, &PyDict_Type, &umap, &rg_obj))
+    return NULL;
+  Py_buffer rg;
+  if (PyObject_GetBuffer(rg_obj, &rg, PyBUF_C_CONTIGUOUS | PyBUF_WRITABLE | PyBUF_FORMAT) < 0) return NULL;
+  PyObject* ids = NULL;
+  PyObject* result = NULL;
+  if (rg.itemsize != 4) {
+    PyErr_SetString(PyExc_TypeError, "row_group must be an int32 buffer");
+    goto done;
+  }
+  ids = PyDict_New();
+  if (!ids) goto done;
+  {
+    int32_t* out = (int32_t*)rg.buf;
+    const Py_ssize_t n = rg.len / 4;
+    Py_ssize_t pos = 0;
+    PyObject *qname, *rowobj;
+    while (PyDict_Next(read_index, &pos, &qname, &rowobj)) {
+      const Py_ssize_t row = PyLong_AsSsize_t(rowobj);
+      if (row == -1 && PyErr_Occurred()) goto done;
+      if (row < 0 || row >= n) {
+        PyErr_Format(PyExc_IndexError, "row id %zd outside [0, %zd)", row, n);
+        goto done;
+      }
+      PyObject* bc = PyDict_GetItemWithError(bmap, qname);
+      PyObject* um = bc ? PyDict_GetItemWithError(umap, qname) : NULL;
+      if (!bc || !um) {
+        if (!PyErr_Occurred()) PyErr_SetObject(PyExc_KeyError, qname);
+        goto done;
+      }
+      PyObject* key = PyTuple_Pack(2, bc, um);
+      if (!key) goto done;
+      PyObject* idobj = PyDict_GetItemWithError(ids, key);
+      Py_ssize_t id;
+      if (idobj) {
+        id = PyLong_AsSsize_t(idobj);
+      } else {
+        if (PyErr_Occurred()) { Py_DECREF(key); goto done; }
+        id = PyDict_GET_SIZE(ids);
+        PyObject* v = PyLong_FromSsize_t(id);
+        if (!v || PyDict_SetItem(ids, key, v) < 0) { Py_XDECREF(v); Py_DECREF(key); goto done; }
+        Py_DECREF(v);
+      }
+      Py_DECREF(key);
+      out[row] = (int32_t)id;
+    }
+    result = PyDict_Keys(ids);
+  }
+done:
+  Py_XDECREF(ids);
+  PyBuffer_Release(&rg);
+  return result;
+}
+
 static PyMethodDef methods[] = {
+    {"pair_ids", pair_ids, METH_VARARGS,
+     "pair_ids(read_index, bcode_map, umi_map, row_group): integer-code the (barcode, UMI) pair of every read"},
     {"number_groups", number_groups, METH_VARARGS,
      "number_groups(groups, ids): ids[i] = index of groups[i] among the non-empty containers, -1 if empty"},
     {"fill_row_segments", fill_row_segments, METH_VARARGS,

@@ -32,3 +32,8 @@ def fill_row_segments(groups, ids, seg):
 def number_groups(groups, ids):
     """ids[i] = running index of groups[i] among the non-empty containers (-1: empty); returns their number."""
     return load().number_groups(groups, ids)
+
+
+def pair_ids(read_index, bcode_map, umi_map, row_group):
+    """row_group[row] = index of the read's (barcode, UMI) pair in the returned first-seen list."""
+    return load().pair_ids(read_index, bcode_map, umi_map, row_group)

@@ -22,13 +22,18 @@ from .statistics import UMIInfo
 def _pair_ids(st):
     """Row -> id of its (barcode, UMI) pair, ids in first-seen order (the order of the reference's
     ``bcumi_read`` dict, model.py:1161-1164) and the pairs themselves."""
-    ids = {}
+    from . import hostutil
     N = st.shape[0]
     row_group = np.full(N, -1, dtype=np.int32)
-    bmap, umap = st.read_bcode_map, st.read_umi_map
-    for qname, row in st.read_index.items():
-        row_group[row] = ids.setdefault((bmap[qname], umap[qname]), len(ids))
-    return row_group, list(ids)
+    if all(type(m) is dict for m in (st.read_index, st.read_bcode_map, st.read_umi_map)):
+        pairs = hostutil.pair_ids(st.read_index, st.read_bcode_map, st.read_umi_map, row_group)   # C walk of the dicts
+    else:
+        ids = {}
+        bmap, umap = st.read_bcode_map, st.read_umi_map
+        for qname, row in st.read_index.items():
+            row_group[row] = ids.setdefault((bmap[qname], umap[qname]), len(ids))
+        pairs = list(ids)
+    return row_group, pairs
 
 
 def dedup_umi(st, output_report=True, summary=True):
