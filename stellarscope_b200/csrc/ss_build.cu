@@ -130,6 +130,27 @@ __global__ void gather_seg_len_kernel(int n, const int* __restrict__ rows, const
   if (len_out) len_out[i] = row_ptr[r + 1] - row_ptr[r];
 }
 
+// sort key of an ambiguous row: (segment, first locus).  Inside a segment the rows are ordered by the
+// first locus they align to (the second one when the first is column 0, __no_feature): reads multimap
+// inside a repeat family, so consecutive rows -- and therefore the tiles of a multi-tile segment -- touch
+// a narrow band of loci.  Tiles then share few columns: fewer partial sums to exchange between the CTAs
+// of a cluster, fewer RED operations and a smaller gather of x per streamed tile.
+__global__ void row_sortkey_kernel(int n, const int* __restrict__ rows, const int* __restrict__ row_seg,
+                                   const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                                   unsigned long long* __restrict__ key) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = rows[i];
+  const int b = row_ptr[r];
+  int c = col_idx[b];
+  if (c == 0) c = col_idx[b + 1];                 // ambiguous rows have at least two alignments
+  key[i] = ((unsigned long long)(unsigned)row_seg[r] << 32) | (unsigned)c;
+}
+__global__ void key_to_seg_kernel(int n, const unsigned long long* __restrict__ key, int* __restrict__ seg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) seg[i] = (int)(key[i] >> 32);
+}
+
 // rows of a segment are cut into tiles every `chunk` alignments; segments that will be streamed
 // (more than STREAM_SEG_TILES large tiles) use the small tile size
 __host__ __device__ inline int seg_chunk(long long a_amb, int chunk_big, int chunk_small) {
@@ -755,11 +776,17 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
   int* rtile = nullptr;
   int* tile_row0 = nullptr;
   if (n_amb > 0) {
-    gather_seg_len_kernel<<<grid_for(n_amb), 256, 0, st>>>(n_amb, ar_unsorted, row_segment, row_ptr, aseg_in, nullptr);
+    // stable sort by (segment, first locus): row order inside equal keys is kept
+    unsigned long long *rkey_in, *rkey;
+    SS_CUDA_CHECK(h, tmp.get(&rkey_in, (size_t)n_amb));
+    SS_CUDA_CHECK(h, tmp.get(&rkey, (size_t)n_amb));
+    row_sortkey_kernel<<<grid_for(n_amb), 256, 0, st>>>(n_amb, ar_unsorted, row_segment, row_ptr, col_idx, rkey_in);
     h->launches++;
-    int bits = 1;
-    while ((1LL << bits) < S) ++bits;
-    CUB_CALL(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, aseg_in, aseg, ar_unsorted, ar, n_amb, 0, bits, st));
+    int bits = 33;
+    while ((1LL << (bits - 32)) < S && bits < 64) ++bits;
+    CUB_CALL(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, rkey_in, rkey, ar_unsorted, ar, n_amb, 0, bits, st));
+    key_to_seg_kernel<<<grid_for(n_amb), 256, 0, st>>>(n_amb, rkey, aseg);
+    h->launches++;
     gather_seg_len_kernel<<<grid_for(n_amb), 256, 0, st>>>(n_amb, ar, row_segment, row_ptr, nullptr, alen);
     h->launches++;
     CUB_CALL(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, alen, pre, n_amb + 1, st));

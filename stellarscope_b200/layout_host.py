@@ -174,7 +174,12 @@ def build(indptr, indices, scores, row_seg, S, K, e_hard=E_HARD, long_col=32):
 
     # ---- tiles over ambiguous rows ----
     ar = np.flatnonzero(amb)
-    ar = ar[np.argsort(row_seg[ar], kind='stable')]          # (seg, row) order
+    # (segment, first locus, row) order: consecutive rows -- and the tiles of a multi-tile segment -- touch
+    # a narrow band of loci (csrc/ss_build.cu row_sortkey_kernel); column 0 does not count as first locus
+    first = indices[indptr[ar]].astype(np.int64)
+    second = indices[np.minimum(indptr[ar] + 1, len(indices) - 1)].astype(np.int64) if len(ar) else first
+    first = np.where(first == 0, second, first)
+    ar = ar[np.lexsort((first, row_seg[ar]))]                # lexsort is stable
     alen = lens[ar]
     maxlen = int(alen.max()) if len(ar) else 0
     if maxlen > e_hard // 2:
