@@ -590,8 +590,10 @@ __global__ void __maxnreg__(SS_CLANE_MAXREG) em_clane_kernel(EmArgs a, ClusterAr
   double* pt2 = pt + pcmax;                            // x pong
   double* spi = pt2 + pcmax;                           // pi
   double* sth = spi + pcmax;                           // theta of the last update
-  double* val = sth + pcmax;                           // pemax + 8 (slot pe: scratch of the padding entries)
+  double* spart = sth + pcmax;                         // this tile's partial column sums (the peers read the copy in L2)
+  double* val = spart + pcmax;                         // pemax + 8 (slot pe: scratch of the padding entries)
   uint16_t* xr = reinterpret_cast<uint16_t*>(val + pemax + 8);   // [ncol][nt] local column of the same locus in tile k
+  uint8_t* shr = reinterpret_cast<uint8_t*>(xr + (size_t)nt * pcmax);   // [ncol] another tile holds the column too
 
   const double* __restrict__ gq = a.L.e_q + v.eo;
   const uint32_t* __restrict__ gidx = a.L.e_idx + v.eo;
@@ -609,7 +611,13 @@ __global__ void __maxnreg__(SS_CLANE_MAXREG) em_clane_kernel(EmArgs a, ClusterAr
     spi[c] = invK;
     pt[c] = invK * invK;
     const long long j = scol[c] - col0;
-    for (int k = 0; k < nt; ++k) xr[c * nt + k] = gxref[j * nt + k];
+    bool sh = false;
+    for (int k = 0; k < nt; ++k) {
+      const uint16_t x = gxref[j * nt + k];
+      xr[c * nt + k] = x;
+      sh |= k != rank && x != 0xffffu;
+    }
+    shr[c] = sh ? 1 : 0;
   }
   if (tid == 0) {
     pt[v.ncol] = 0.0;
@@ -780,17 +788,25 @@ __global__ void __maxnreg__(SS_CLANE_MAXREG) em_clane_kernel(EmArgs a, ClusterAr
             }
           if (gB[j] > 1) asum = group_xor_sum(asum, (cm[j] >> 4) & 63, gB[j]);
           const int c1 = cm[j] >> 12;
-          if (c1 > 0) mypart[c1 - 1] = asum;
+          if (c1 > 0) {
+            spart[c1 - 1] = asum;
+            if (shr[c1 - 1]) mypart[c1 - 1] = asum;       // only shared columns travel through L2
+          }
         }
       }
       for (int c = warp; c < b128; c += NW) {                     // very long columns: one warp each
         const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
         const double asum = col_sum_warp(val, b, n, lane);
-        if (lane == 0) mypart[c] = asum;
+        if (lane == 0) {
+          spart[c] = asum;
+          if (shr[c]) mypart[c] = asum;
+        }
       }
       for (int c = c_ovf + tid; c < v.ncol; c += THREADS) {       // columns beyond the register lanes
         const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
-        mypart[c] = col_sum_thread(val, b, n);
+        const double asum = col_sum_thread(val, b, n);
+        spart[c] = asum;
+        if (shr[c]) mypart[c] = asum;
       }
     }
     SS_TICK(tB1)
@@ -827,11 +843,7 @@ __global__ void __maxnreg__(SS_CLANE_MAXREG) em_clane_kernel(EmArgs a, ClusterAr
           const unsigned ck = c < v.ncol ? (unsigned)xr[c * nt + k] : 0xffffu;
           vk[u] = 0.0;
           if (ck != 0xffffu) {
-#ifdef SS_CLANE_NOLOAD
-            vk[u] = 1.0 + (double)ck;
-#else
-            vk[u] = __ldcg(pk + ck);                             // written by a peer CTA: read from L2
-#endif
+            vk[u] = k == rank ? spart[ck] : __ldcg(pk + ck);      // a peer's partial sum: read from L2
             if (k < rank) first[u] = false;                       // an earlier tile holds this column too
           }
         }

@@ -126,10 +126,10 @@ __host__ __device__ inline size_t lane_smem_bytes(int nent, int ncol) {
   return 8 * ((size_t)pad8(nent) + 8 + 3 * (size_t)pad8(ncol + 1));
 }
 
-// shared memory of the cluster lane kernel (ss_em.cu): x ping-pong, pi, theta: 4 pcmax doubles;
-// scratch: pemax + 8 doubles; cross reference: nt * pcmax u16
+// shared memory of the cluster lane kernel (ss_em.cu): x ping-pong, pi, theta, partial sums: 5 pcmax
+// doubles; scratch: pemax + 8 doubles; cross reference: nt * pcmax u16; shared-column flags: pcmax bytes
 __host__ __device__ inline size_t clane_smem_bytes(int pemax, int pcmax, int nt) {
-  return 8 * (4 * (size_t)pcmax + (size_t)pemax + 8) + 2 * (size_t)nt * (size_t)pcmax + 64;
+  return 8 * (5 * (size_t)pcmax + (size_t)pemax + 8) + 2 * (size_t)nt * (size_t)pcmax + (size_t)pcmax + 64;
 }
 
 // phase B helper: sum of the column-major slots [b, b+n) of a tile column, by one thread
