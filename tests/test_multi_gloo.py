@@ -79,3 +79,96 @@ def test_fit_models_sharded_world2_gloo():
         assert recs == single                    # every rank sees every model's record, same as one process
         rows_all += rows
     assert sorted(rows_all) == list(range(d.N))   # rows are partitioned across the two ranks
+
+
+def test_row_block_equal_alignments():
+    d = H.small_synth(seed=10, n_cells=30, n_alignments=8000)
+    ptr = d.indptr.astype(np.int64)
+    for world in (1, 2, 3, 8):
+        blocks = [parallel.row_block(ptr, r, world) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == d.N
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+        per = np.array([ptr[b] - ptr[a] for a, b in blocks])
+        assert per.max() - per.min() <= 2 * np.diff(ptr).max()
+    assert [parallel.row_block(np.array([0, 3]), r, 4) for r in range(4)] == [(0, 0), (0, 1), (1, 1), (1, 1)]
+
+
+def _sharded_pseudobulk_worker(rank, world, port, q):
+    """The row-sharded pseudobulk protocol of csrc/ss_dense.cu restated in numpy over gloo: s_max by
+    all-reduce MAX, [pisum0, weights] by all-reduce SUM once, the K-vector of partial theta sums by
+    all-reduce SUM per iteration, identical update and decision on every rank."""
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    d = H.small_synth(seed=41, n_cells=8, n_alignments=4000, n_loci=120, unique_frac=0.1)
+    ptr = d.indptr.astype(np.int64)
+    r0, r1 = parallel.row_block(ptr, rank, world)
+    a, b = ptr[r0], ptr[r1]
+    lens = np.diff(ptr[r0:r1 + 1])
+    cols, sc = d.indices[a:b].astype(np.int64), d.scores[a:b].astype(np.float64)
+    K = d.K
+
+    def allreduce(x, op):
+        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+        dist.all_reduce(t, op=op)
+        return t.numpy()
+    smax = allreduce(np.array([sc.max() if len(sc) else 0.0]), dist.ReduceOp.MAX)[0]
+    Q = np.expm1((sc * (1.0 / smax)) * 100.0)
+    row = np.repeat(np.arange(r1 - r0), lens)
+    w = np.zeros(r1 - r0)
+    np.maximum.at(w, row, Q)
+    amb = lens > 1
+    stat = np.zeros(K + 2)
+    np.add.at(stat, cols[~amb[row]], Q[~amb[row]])                  # pisum0
+    stat[K], stat[K + 1] = w[amb].sum(), w.sum()
+    stat = allreduce(stat, dist.ReduceOp.SUM)
+    pisum0, wamb, wtot = stat[:K], stat[K], stat[K + 1]
+    wmax = np.expm1((smax * (1.0 / smax)) * 100.0)
+    thpw, pipw = 200000 * wmax, 0.0
+    thd, pid = wamb + thpw * K, wtot + pipw * K
+    pi = np.full(K, 1.0 / K)
+    th = np.full(K, 1.0 / K)
+    am = amb[row]
+    it = 0
+    while True:
+        it += 1
+        u = Q * pi[cols] * np.where(am, th[cols], 1.0)
+        rs = np.zeros(r1 - r0)
+        np.add.at(rs, row, u)
+        z = u / rs[row]
+        T = np.zeros(K)
+        np.add.at(T, cols[am], (z * w[row])[am])
+        T = allreduce(T, dist.ReduceOp.SUM)                         # the one exchange per iteration
+        th_n, pi_n = (T + thpw) / thd, (pisum0 + T + pipw) / pid
+        diff = np.abs(pi_n - pi).sum()
+        pi, th = pi_n, th_n
+        if diff < 1e-7 or it >= 100:
+            break
+    q.put((rank, it, pi.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_sharded_pseudobulk_protocol_world2_gloo():
+    from oracle.em_oracle import OracleLikelihood, Opts
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_pseudobulk_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    d = H.small_synth(seed=41, n_cells=8, n_alignments=4000, n_loci=120, unique_frac=0.1)
+    m = OracleLikelihood(d.indptr.astype(np.int64), d.indices.astype(np.int64), d.scores, d.K, Opts()).em()
+    po = np.asarray(m.pi, dtype=np.float64)
+    assert got[0][1] == got[1][1] == len(m.fitinfo.iterations)      # same decision on both ranks = the single-process one
+    assert got[0][2] == got[1][2]                                   # bit-identical parameters on both ranks
+    ok = po > 1e-290
+    assert np.max(np.abs(np.array(got[0][2])[ok] - po[ok]) / po[ok]) < 1e-9
