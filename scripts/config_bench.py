@@ -91,8 +91,10 @@ def main():
     assert np.all((res['flags'][fitted] & 3) != 0) and not np.any(res['flags'] & 4 & np.where(fitted, 4, 0))
     # sum of pi over the K loci of each model = 1
     col0, ncol = p['seg_col0'].astype(np.int64), p['seg_ncol'].astype(np.int64)
-    cs = np.concatenate([[0.0], np.cumsum(p['pi'])])
-    pisum = cs[col0 + ncol] - cs[col0] + (d.K - ncol) * p['pi_rest']
+    seg_sum = np.zeros(len(col0))
+    nz = ncol > 0
+    seg_sum[nz] = np.add.reduceat(p['pi'], col0[nz])          # per-model sums (a global prefix sum would lose 1e-9)
+    pisum = seg_sum + (d.K - ncol) * p['pi_rest']
     assert np.max(np.abs(pisum[fitted] - 1.0)) < 1e-9, np.max(np.abs(pisum[fitted] - 1.0))
     z = eng.emit_z()
     rowsum = torch.zeros(d.N, dtype=torch.float64, device=z.device)

@@ -826,43 +826,32 @@ __global__ void __maxnreg__(SS_CLANE_MAXREG) em_clane_kernel(EmArgs a, ClusterAr
     }
     // ---- phase B2: gather the partial sums of my columns from every tile, new parameters ----
     double dsum = 0.0;
-    // U columns per thread at a time: their DSMEM loads are in flight together (a round trip costs
-    // ~1000 cycles), the additions stay in tile order
-    constexpr int U = CLANE_UNROLL;
-    for (int cbase = tid; cbase < v.ncol; cbase += U * THREADS) {
-      double tot[U];
-      bool first[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) { tot[u] = 0.0; first[u] = true; }
-      for (int k = 0; k < nt; ++k) {                              // fixed tile order
-        const double* pk = gpart + part_off[k];
-        double vk[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int c = cbase + u * THREADS;
-          const unsigned ck = c < v.ncol ? (unsigned)xr[c * nt + k] : 0xffffu;
-          vk[u] = 0.0;
+    // a column held by this tile alone (the common case: the builder orders the rows by locus, so tiles
+    // overlap in few columns) needs nothing but its own partial sum; a shared column adds the partial
+    // sums of all its holders in tile order, read from L2
+    for (int c = tid; c < v.ncol; c += THREADS) {
+      double tot;
+      bool first = true;
+      if (!shr[c]) {
+        tot = spart[c];
+      } else {
+        tot = 0.0;
+        const uint16_t* xc = xr + c * nt;
+        for (int k = 0; k < nt; ++k) {                            // fixed tile order
+          const unsigned ck = xc[k];
           if (ck != 0xffffu) {
-            vk[u] = k == rank ? spart[ck] : __ldcg(pk + ck);      // a peer's partial sum: read from L2
-            if (k < rank) first[u] = false;                       // an earlier tile holds this column too
+            tot += k == rank ? spart[ck] : __ldcg(gpart + part_off[k] + ck);
+            if (k < rank) first = false;                          // an earlier tile holds this column too
           }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) tot[u] += vk[u];
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int c = cbase + u * THREADS;
-        if (c < v.ncol) {
-          const double T = pt_cur[c] * tot[u];
-          const double th = (T + thpw) * inv_thd;                 // model.py:240
-          const double pn = ((has_uniq ? ps0[c] : 0.0) + T + pipw) * inv_pid;   // model.py:243-244
-          if (first[u]) dsum += fabs(pn - spi[c]);
-          spi[c] = pn;
-          sth[c] = th;
-          pt_nxt[c] = pn * th;
-        }
-      }
+      const double T = pt_cur[c] * tot;
+      const double th = (T + thpw) * inv_thd;                     // model.py:240
+      const double pn = ((has_uniq ? ps0[c] : 0.0) + T + pipw) * inv_pid;   // model.py:243-244
+      if (first) dsum += fabs(pn - spi[c]);
+      spi[c] = pn;
+      sth[c] = th;
+      pt_nxt[c] = pn * th;
     }
     SS_TICK(tB2)
     dsum = block_sum<THREADS>(dsum, s_red, par++);                // barrier: publishes pt_nxt
