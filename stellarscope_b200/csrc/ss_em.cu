@@ -555,11 +555,10 @@ struct ClusterArgs {
 #define SS_CLANE_FR 4
 #define SS_CLANE_FC 6
 #define SS_CLANE_MAXREG 128
-#define SS_CLANE_UNROLL 4
 #endif
 constexpr int SS_MAX_CLUSTER_TILES = 8;
 constexpr int CLANE_THREADS = SS_CLANE_THREADS;
-constexpr int CLANE_FR = SS_CLANE_FR, CLANE_FC = SS_CLANE_FC, CLANE_UNROLL = SS_CLANE_UNROLL;
+constexpr int CLANE_FR = SS_CLANE_FR, CLANE_FC = SS_CLANE_FC;
 
 __global__ void __maxnreg__(SS_CLANE_MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
   extern __shared__ __align__(128) unsigned char dsm[];
@@ -835,15 +834,24 @@ __global__ void __maxnreg__(SS_CLANE_MAXREG) em_clane_kernel(EmArgs a, ClusterAr
       if (!shr[c]) {
         tot = spart[c];
       } else {
-        tot = 0.0;
+        // all peer loads of the column are issued together (one L2 round trip, ~900 cycles, instead of
+        // one per holder: the slowest thread sets the pace of the whole CTA); added in tile order
         const uint16_t* xc = xr + c * nt;
-        for (int k = 0; k < nt; ++k) {                            // fixed tile order
-          const unsigned ck = xc[k];
-          if (ck != 0xffffu) {
-            tot += k == rank ? spart[ck] : __ldcg(gpart + part_off[k] + ck);
-            if (k < rank) first = false;                          // an earlier tile holds this column too
+        double pk[SS_MAX_CLUSTER_TILES];
+#pragma unroll
+        for (int k = 0; k < SS_MAX_CLUSTER_TILES; ++k) {
+          pk[k] = 0.0;
+          if (k < nt) {
+            const unsigned ck = xc[k];
+            if (ck != 0xffffu) {
+              pk[k] = k == rank ? spart[ck] : __ldcg(gpart + part_off[k] + ck);
+              if (k < rank) first = false;                        // an earlier tile holds this column too
+            }
           }
         }
+        tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < SS_MAX_CLUSTER_TILES; ++k) tot += pk[k];     // fixed tile order
       }
       const double T = pt_cur[c] * tot;
       const double th = (T + thpw) * inv_thd;                     // model.py:240
