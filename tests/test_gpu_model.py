@@ -145,7 +145,7 @@ def test_binmax_known_answers_through_ss_reassign():
 def test_row_sharded_dense_path_single_rank(name, peers):
     """The row-sharded (dense K-vector) fit of csrc/ss_dense.cu on ONE rank -- persistent kernel
     (peers=True) and host-loop variant (peers=False) -- against the golden pseudobulk fits of the
-    real reference.  The multi-rank exchange is covered by scripts/dist_check.py (2+ GPUs)."""
+    real reference.  The multi-rank exchange is covered by tests/tools/dist_check.py (2+ GPUs)."""
     from stellarscope_b200 import model
     g = H.load_golden(name)
     opts = H.golden_opts(g, cls=H.StOpts)

@@ -1,6 +1,6 @@
 """Device-time measurement + validation of the BASELINE.json configurations on ONE GPU.
 
-    python scripts/config_bench.py cfg2|cfg3|cfg4|cfg5 [scale] [n_oracle_cells]
+    python tests/tools/config_bench.py cfg2|cfg3|cfg4|cfg5 [scale] [n_oracle_cells]
 
 cfg2: 10k cells, 5M alignments, individual          cfg3: 50k cells, 100M alignments, celltype(20), UMI dedup
 cfg4: one model, 500M alignments (pseudobulk)       cfg5: 100k cells, 500M alignments, individual, reassign sweep
@@ -17,7 +17,7 @@ import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 

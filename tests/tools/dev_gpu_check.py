@@ -1,6 +1,6 @@
 """Ad-hoc GPU parity check used during development (gpurun)."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from stellarscope_b200 import synth, layout_host
 from stellarscope_b200.engine import Engine

@@ -1,6 +1,6 @@
 """2+ GPU check (torchrun): model sharding of individual / celltype pooling against the golden fixtures."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch, torch.distributed as dist
 from tests import helpers as H

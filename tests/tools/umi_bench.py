@@ -1,6 +1,6 @@
 """UMI de-duplication: device path vs the CPU restatement of the reference.
 
-    python scripts/umi_bench.py [n_reads]
+    python tests/tools/umi_bench.py [n_reads]
 
 Synthetic 10x-style reads (config 3 shape: 15 % PCR duplicates inside a cell).  Reports the device time of
 ``ss_umi_dedup`` (CUDA events, matrix resident), the wall time of the drop-in ``umi.dedup_umi`` (host dict
@@ -8,7 +8,7 @@ walk + H2D + device + scipy outputs) and the oracle port (pure-Python restatemen
 model.py:561-668, 1148-1219) on a bounded sample of the same reads.
 """
 import os, sys, time, types
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import scipy.sparse as sp
 from oracle import umi_oracle as uo
