@@ -880,18 +880,25 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
     a.tmp_cptr = tmp_cptr; a.tmp_gcol = tmp_gcol; a.tmp_jptr = tmp_jptr; a.jds_stride = jds_stride;
     a.t_ncol = t_ncol; a.t_maxlen = t_maxlen; a.t_nlong = t_nlong; a.t_seg = t_seg; a.t_nrows = t_nrows;
     a.t_nent = t_nent; a.t_wsum = t_wsum; a.t_rfrag = t_rfrag; a.t_cfrag = t_cfrag; a.t_gt = t_gt;
-#define SS_TILE_BUILD(ECAP, ELOW, BT)                                                                     \
+    // the three size classes work on disjoint tiles: run them side by side on internal streams
+    SS_CUDA_CHECK(h, ensure_aux_streams(h));
+    SS_CUDA_CHECK(h, cudaEventRecord(h->ev_fork, st));
+#define SS_TILE_BUILD(ECAP, ELOW, BT, SIDX)                                                               \
   do {                                                                                                    \
     constexpr size_t smem = tile_build_smem<ECAP, BT>();                                                  \
+    cudaStream_t sx = h->aux[SIDX];                                                                       \
+    SS_CUDA_CHECK(h, cudaStreamWaitEvent(sx, h->ev_fork, 0));                                             \
     SS_CUDA_CHECK(h, cudaFuncSetAttribute(tile_build_kernel<ECAP, ELOW, BT>,                              \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    tile_build_kernel<ECAP, ELOW, BT><<<n_tiles, BT, smem, st>>>(a);                                      \
+    tile_build_kernel<ECAP, ELOW, BT><<<n_tiles, BT, smem, sx>>>(a);                                      \
     h->launches++;                                                                                        \
     SS_CUDA_CHECK(h, cudaGetLastError());                                                                 \
+    SS_CUDA_CHECK(h, cudaEventRecord(h->ev_join[SIDX], sx));                                              \
+    SS_CUDA_CHECK(h, cudaStreamWaitEvent(st, h->ev_join[SIDX], 0));                                       \
   } while (0)
-    SS_TILE_BUILD(E_HARD, 1024, 1024);      // largest tiles first: they take longest (one CTA per SM)
-    SS_TILE_BUILD(1024, 256, 512);
-    SS_TILE_BUILD(256, 0, 128);
+    SS_TILE_BUILD(E_HARD, 1024, 1024, 0);      // largest tiles: one CTA per SM
+    SS_TILE_BUILD(1024, 256, 256, 1);
+    SS_TILE_BUILD(256, 0, 128, 2);
 #undef SS_TILE_BUILD
     SS_CUDA_CHECK(h, cudaMemsetAsync(pad_col + n_tiles, 0, 8, st));
     SS_CUDA_CHECK(h, cudaMemsetAsync(pad_jds + n_tiles, 0, 8, st));

@@ -1393,7 +1393,7 @@ static cudaError_t launch_lane(ss_handle_s* h, cudaStream_t st, const EmArgs& a,
   return cudaGetLastError();
 }
 
-static cudaError_t ensure_aux_streams(ss_handle_s* h) {
+cudaError_t ensure_aux_streams(ss_handle_s* h) {
   if (h->ev_fork) return cudaSuccess;
   cudaError_t e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   if (e != cudaSuccess) return e;

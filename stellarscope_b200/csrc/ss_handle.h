@@ -136,6 +136,7 @@ namespace ss {
 int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P);
 int em_emit_z(ss_handle_s* h, cudaStream_t st, double* z);
 void free_fit(ss_handle_s* h);
+cudaError_t ensure_aux_streams(ss_handle_s* h);   // internal streams + fork / join events of the handle
 // ss_umi.cu
 int umi_dedup(ss_handle_s* h, cudaStream_t st, int n_rows, const int* row_ptr, const int* col_idx, const uint16_t* score,
               const int* row_group, int n_groups, uint8_t* excluded, int* comp_root, int* group_size, int* group_ncomp);
