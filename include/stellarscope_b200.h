@@ -183,6 +183,21 @@ int ss_umi_dedup(ss_handle_t h, void* stream, int32_t n_rows, const int32_t* row
                  const uint16_t* score, const int32_t* row_group, int32_t n_groups, uint8_t* excluded,
                  int32_t* comp_root, int32_t* group_size, int32_t* group_ncomp);
 
+/* Score-matrix construction, the producer of the path's input (mapping_to_matrix inside
+ * Stellarscope.load_alignment, model.py:958-978): one (read, feature, alnscore, alnlen) record per
+ * fragment x locus mapping (read = read_index[query_name], feat = feat_index[feat_name], both coded by
+ * the caller); stores  max over the records of one (read, feat) of  (alnscore - min_as + 1) + alnlen
+ * as uint16 and returns canonical CSR (columns ascending, no duplicates).
+ *   read/feat/alnscore/alnlen[n]: device arrays
+ *   row_ptr[n_reads + 1], col_idx[cap >= n], score[cap >= n] out: device arrays
+ *   info[4] out (HOST): stored elements, records whose value leaves (0, 65535], records with an index
+ *            outside the matrix, reads without a stored value in a feature column >= 1 (the reference
+ *            asserts there are none, model.py:971-974 -- the caller raises)
+ * SS_ERR_CAPACITY / SS_ERR_ARG (nothing written) when info[1] / info[2] is not 0.  Synchronises the stream. */
+int ss_scores_build(ss_handle_t h, void* stream, int64_t n, const int32_t* read, const int32_t* feat,
+                    const int32_t* alnscore, const int32_t* alnlen, int32_t min_as, int32_t n_reads, int32_t n_feats,
+                    int32_t* row_ptr, int32_t* col_idx, uint16_t* score, int64_t* info);
+
 /* ---- one model, rows sharded over the GPUs of a box (pooling_mode=pseudobulk) ----
  * The reference fits the pseudobulk model single-threaded (model.py:762-767).  Here every rank
  * (one process per GPU) holds a block of rows of the SAME model; ss_layout_build / ss_em_fit are

@@ -314,6 +314,19 @@ int ss_umi_dedup(ss_handle_t h, void* stream, int32_t n_rows, const int32_t* row
                    group_size, group_ncomp);
 }
 
+int ss_scores_build(ss_handle_t h, void* stream, int64_t n, const int32_t* read, const int32_t* feat,
+                    const int32_t* alnscore, const int32_t* alnlen, int32_t min_as, int32_t n_reads, int32_t n_feats,
+                    int32_t* row_ptr, int32_t* col_idx, uint16_t* score, int64_t* info) {
+  SS_REQUIRE_HANDLE(h);
+  if (!row_ptr || !info || (n > 0 && (!read || !feat || !alnscore || !alnlen || !col_idx || !score))) {
+    h->set_error("ss_scores_build: bad argument");
+    return SS_ERR_ARG;
+  }
+  cudaSetDevice(h->device);
+  return scores_build(h, (cudaStream_t)stream, n, read, feat, alnscore, alnlen, min_as, n_reads, n_feats, row_ptr, col_idx,
+                      score, reinterpret_cast<long long*>(info));
+}
+
 int ss_set_allreduce(ss_handle_t h, ss_allreduce_fn fn, void* user) {
   SS_REQUIRE_HANDLE(h);
   h->allreduce = fn;

@@ -140,6 +140,9 @@ cudaError_t ensure_aux_streams(ss_handle_s* h);   // internal streams + fork / j
 // ss_umi.cu
 int umi_dedup(ss_handle_s* h, cudaStream_t st, int n_rows, const int* row_ptr, const int* col_idx, const uint16_t* score,
               const int* row_group, int n_groups, uint8_t* excluded, int* comp_root, int* group_size, int* group_ncomp);
+int scores_build(ss_handle_s* h, cudaStream_t st, long long n, const int* read, const int* feat, const int* alnscore,
+                 const int* alnlen, int min_as, int n_reads, int n_feats, int* row_ptr, int* col_idx, uint16_t* score,
+                 long long* info_host);
 // ss_dense.cu
 int em_fit_dense(ss_handle_s* h, cudaStream_t st, const FitParams& P);
 int dense_allreduce_smax(ss_handle_s* h, cudaStream_t st);

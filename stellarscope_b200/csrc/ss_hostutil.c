@@ -300,7 +300,72 @@ done:
   return result;
 }
 
+/* code_mappings(mappings, read_index, feat_index, read, feat, alnscore, alnlen)
+ * mappings: list of (code, query_name, feat_name, alnscore, alnlen) tuples, the loader's output
+ * (Stellarscope._load_sequential, model.py:1131-1132).  Integer-codes them for ss_scores_build:
+ * read[i] = read_index[query_name], feat[i] = feat_index[feat_name] -- the two dict look-ups of
+ * mapping_to_matrix (model.py:967-968), KeyError like there. */
+static int get_i32_buffer(PyObject* obj, Py_buffer* b, Py_ssize_t n, const char* name) {
+  if (PyObject_GetBuffer(obj, b, PyBUF_C_CONTIGUOUS | PyBUF_WRITABLE) < 0) return -1;
+  if (b->itemsize != 4 || b->len / 4 < n) {
+    PyErr_Format(PyExc_TypeError, "%s must be an int32 buffer of at least %zd items", name, n);
+    PyBuffer_Release(b);
+    return -1;
+  }
+  return 0;
+}
+
+static PyObject* code_mappings(PyObject* self, PyObject* args) {
+  PyObject *maps, *read_index, *feat_index, *o_read, *o_feat, *o_as, *o_len;
+  if (!PyArg_ParseTuple(args, "O!O!O!OOOO", &PyList_Type, &maps, &PyDict_Type, &read_index, &PyDict_Type, &feat_index,
+                        &o_read, &o_feat, &o_as, &o_len))
+    return NULL;
+  const Py_ssize_t n = PyList_GET_SIZE(maps);
+  Py_buffer b_read, b_feat, b_as, b_len;
+  if (get_i32_buffer(o_read, &b_read, n, "read") < 0) return NULL;
+  if (get_i32_buffer(o_feat, &b_feat, n, "feat") < 0) { PyBuffer_Release(&b_read); return NULL; }
+  if (get_i32_buffer(o_as, &b_as, n, "alnscore") < 0) { PyBuffer_Release(&b_read); PyBuffer_Release(&b_feat); return NULL; }
+  if (get_i32_buffer(o_len, &b_len, n, "alnlen") < 0) {
+    PyBuffer_Release(&b_read); PyBuffer_Release(&b_feat); PyBuffer_Release(&b_as);
+    return NULL;
+  }
+  int32_t *rd = (int32_t*)b_read.buf, *ft = (int32_t*)b_feat.buf, *as = (int32_t*)b_as.buf, *ln = (int32_t*)b_len.buf;
+  PyObject* result = NULL;
+  for (Py_ssize_t i = 0; i < n; ++i) {
+    PyObject* m = PyList_GET_ITEM(maps, i);
+    if (!PyTuple_Check(m) || PyTuple_GET_SIZE(m) != 5) {
+      PyErr_SetString(PyExc_ValueError, "mapping must be a (code, query_name, feat_name, alnscore, alnlen) tuple");
+      goto done;
+    }
+    PyObject* r = PyDict_GetItemWithError(read_index, PyTuple_GET_ITEM(m, 1));
+    if (!r) { if (!PyErr_Occurred()) PyErr_SetObject(PyExc_KeyError, PyTuple_GET_ITEM(m, 1)); goto done; }
+    PyObject* f = PyDict_GetItemWithError(feat_index, PyTuple_GET_ITEM(m, 2));
+    if (!f) { if (!PyErr_Occurred()) PyErr_SetObject(PyExc_KeyError, PyTuple_GET_ITEM(m, 2)); goto done; }
+    const long rv = PyLong_AsLong(r), fv = PyLong_AsLong(f);
+    const long av = PyLong_AsLong(PyTuple_GET_ITEM(m, 3)), lv = PyLong_AsLong(PyTuple_GET_ITEM(m, 4));
+    if (PyErr_Occurred()) goto done;
+    if (rv < 0 || rv > INT32_MAX || fv < 0 || fv > INT32_MAX || av < INT32_MIN / 2 || av > INT32_MAX / 2 || lv < INT32_MIN / 2 ||
+        lv > INT32_MAX / 2) {
+      PyErr_SetString(PyExc_OverflowError, "mapping field does not fit in int32");
+      goto done;
+    }
+    rd[i] = (int32_t)rv;
+    ft[i] = (int32_t)fv;
+    as[i] = (int32_t)av;
+    ln[i] = (int32_t)lv;
+  }
+  result = PyLong_FromSsize_t(n);
+done:
+  PyBuffer_Release(&b_read);
+  PyBuffer_Release(&b_feat);
+  PyBuffer_Release(&b_as);
+  PyBuffer_Release(&b_len);
+  return result;
+}
+
 static PyMethodDef methods[] = {
+    {"code_mappings", code_mappings, METH_VARARGS,
+     "code_mappings(mappings, read_index, feat_index, read, feat, alnscore, alnlen): integer-code the loader's mapping tuples"},
     {"pair_ids", pair_ids, METH_VARARGS,
      "pair_ids(read_index, bcode_map, umi_map, row_group): integer-code the (barcode, UMI) pair of every read"},
     {"number_groups", number_groups, METH_VARARGS,

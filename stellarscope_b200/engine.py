@@ -441,6 +441,34 @@ class Engine:
             return dict(excluded=ex[:self.N].cpu().numpy().astype(bool), comp_root=h[:self.N],
                         group_size=h[n1:n1 + n_groups], group_ncomp=h[n1 + max(n_groups, 1):n1 + max(n_groups, 1) + n_groups])
 
+    def scores_build(self, read, feat, alnscore, alnlen, min_as, n_reads, n_feats, keep=True):
+        """ss_scores_build: integer-coded mapping records (host int32 arrays) -> canonical uint16 CSR.
+        Returns (indptr int32[N+1], indices int32[nnz], data uint16[nnz], info int64[4]) as numpy arrays; with
+        ``keep`` the device copy becomes the engine's matrix (``set_matrix_device``), ready for ``build_layout``."""
+        n = len(read)
+        n_reads, n_feats = int(n_reads), int(n_feats)
+        dev = self.device
+        with torch.cuda.device(dev):
+            rec = np.empty((4, max(n, 1)), dtype=np.int32)
+            rec[0, :n], rec[1, :n], rec[2, :n], rec[3, :n] = read, feat, alnscore, alnlen
+            d = self._to_dev(rec, np.int32)
+            self.h2d_bytes = rec.nbytes
+            row_ptr = torch.empty(n_reads + 1, dtype=torch.int32, device=dev)
+            col_idx = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            score = torch.empty(max(n, 1), dtype=torch.uint16, device=dev)
+            info = np.zeros(4, dtype=np.int64)
+            rc = self.lib.ss_scores_build(self.h, self._stream(), n, self._p(d[0]), self._p(d[1]), self._p(d[2]),
+                                          self._p(d[3]), int(min_as), n_reads, n_feats, self._p(row_ptr),
+                                          self._p(col_idx), self._p(score), info.ctypes.data_as(_lib.c_i64p))
+            if rc == _lib.SS_ERR_CAPACITY:
+                raise OverflowError(self.lib.ss_last_error(self.h).decode())
+            self._check(rc)
+            nnz = int(info[0])
+            col_idx, score = col_idx[:nnz], score[:nnz]
+            if keep:
+                self.set_matrix_device(row_ptr, col_idx, score, n_feats)
+            return row_ptr.cpu().numpy(), col_idx.cpu().numpy(), score.cpu().numpy(), info
+
     # -- reassign / count ------------------------------------------------------
     def reassign(self, mode, z=None, conf_thresh=0.9, tie_tol=0.0):
         """ss_reassign.  Returns (flag uint8[A] device, nbest int32[N] device, info numpy int64[68])."""

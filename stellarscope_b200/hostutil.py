@@ -37,3 +37,8 @@ def number_groups(groups, ids):
 def pair_ids(read_index, bcode_map, umi_map, row_group):
     """row_group[row] = index of the read's (barcode, UMI) pair in the returned first-seen list."""
     return load().pair_ids(read_index, bcode_map, umi_map, row_group)
+
+
+def code_mappings(mappings, read_index, feat_index, read, feat, alnscore, alnlen):
+    """Integer-code the loader's (code, query_name, feat_name, alnscore, alnlen) tuples into int32 arrays."""
+    return load().code_mappings(mappings, read_index, feat_index, read, feat, alnscore, alnlen)

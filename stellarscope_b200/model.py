@@ -541,4 +541,6 @@ def install():
     ref.Stellarscope.output_report = lambda self, tl: output_report(self, tl)
     from . import umi
     ref.Stellarscope.dedup_umi = lambda self, output_report=True, summary=True: umi.dedup_umi(self, output_report, summary)
+    from . import loader
+    ref.Stellarscope.load_alignment = lambda self, annotation: loader.load_alignment(self, annotation)
     return ref
