@@ -31,58 +31,124 @@ struct StreamArgs {
 };
 
 // ---------------------------------------------------------------------------
-// prepare: per segment constants (model.py:189-194) and default parameters of
-// the columns no tile touches.  One warp per segment.
+// prepare: per segment constants (model.py:189-194) and default parameters of the columns no tile
+// touches.  Two kernels: one warp per column chunk (SS_COL_CHUNK slots of one segment -- a segment
+// with many columns does not serialise on one warp), then one warp per segment that adds the
+// chunks' partial sums in chunk order.
 // ---------------------------------------------------------------------------
-__global__ void fit_prepare_kernel(Layout L, FitState F, FitParams P, const int8_t* __restrict__ sc_inamb) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= L.S) return;
-  const int s = warp;
+struct ColChunks {
+  int n;
+  const int* seg;        // [n] segment of the chunk
+  const int* j0;         // [n] first column of the chunk (segment-relative)
+  const int* seg_chunk0; // [S] first chunk of the segment
+  double* part;          // [2][n]
+};
+
+struct SegConst {
+  double invK, thpw, pipw, inv_thd, inv_pid;
+  bool bad;
+};
+__device__ __forceinline__ SegConst seg_constants(const Layout& L, const FitParams& P, int s) {
+  SegConst c;
   const double K = (double)P.K;
-  const double invK = 1.0 / K;
+  c.invK = 1.0 / K;
   const double wmax = L.seg_wmax[s];
-  const double thpw = P.theta_prior * wmax;
-  const double pipw = P.pi_prior * wmax;
-  const double thd = L.seg_wamb[s] + thpw * K;
-  const double pid = L.seg_wtot[s] + pipw * K;
-  const bool bad = !(thd > 0.0) || !(pid > 0.0);
-  const double inv_thd = bad ? 0.0 : 1.0 / thd;
-  const double inv_pid = bad ? 0.0 : 1.0 / pid;
+  c.thpw = P.theta_prior * wmax;
+  c.pipw = P.pi_prior * wmax;
+  const double thd = L.seg_wamb[s] + c.thpw * K;
+  const double pid = L.seg_wtot[s] + c.pipw * K;
+  c.bad = !(thd > 0.0) || !(pid > 0.0);
+  c.inv_thd = c.bad ? 0.0 : 1.0 / thd;
+  c.inv_pid = c.bad ? 0.0 : 1.0 / pid;
+  return c;
+}
+
+__global__ void fit_prepare_cols_kernel(Layout L, FitState F, FitParams P, const int8_t* __restrict__ sc_inamb, ColChunks cc) {
+  const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ch >= cc.n) return;
+  const int s = cc.seg[ch];
+  const SegConst k = seg_constants(L, P, s);
   const int c0 = L.seg_col0[s], nc = L.seg_ncol[s];
-  const double th_rest = thpw * inv_thd;
-  const double pi_rest = pipw * inv_pid;
+  const int jb = cc.j0[ch], je = min(nc, jb + SS_COL_CHUNK);
+  const double th_rest = k.thpw * k.inv_thd;
+  const double invK = k.invK;
   double d1 = 0.0, lx = 0.0;
-  for (int j = lane; j < nc; j += 32) {
-    const int slot = c0 + j;
-    const double p1 = (L.sc_pisum0[slot] + pipw) * inv_pid;
-    F.sc_pi[slot] = p1;
-    F.sc_theta[slot] = th_rest;
-    F.sc_ptprev[slot] = invK * invK;
-    F.sc_ptfin[slot] = p1 * th_rest;
-    F.sc_pt[0][slot] = invK * invK;
-    F.sc_pt[1][slot] = invK * invK;
-    F.sc_T[slot] = 0.0;
-    if (!sc_inamb[slot]) {
-      d1 += fabs(p1 - invK);
-      const int nu = L.sc_nuniq[slot];
-      if (nu > 0 && p1 > 0.0) lx += (double)nu * log(p1);
+  // Single-tile segments (lane kernel) keep their state on chip and publish pi / theta / x of the tile's columns
+  // themselves: only the columns no tile touches need their (constant) parameters here.  Multi-tile segments
+  // (cluster / streaming kernels) start from the per-slot state below.
+  const bool full = L.seg_ntiles[s] > 1;
+  for (int j0 = jb; j0 < je; j0 += 128) {
+    double ps0[4];
+    int nu[4];
+    bool out[4];                  // column outside the tiles
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 32 * u + lane;
+      const bool ok = j < je;
+      out[u] = ok && !sc_inamb[c0 + j];
+      ps0[u] = ok ? L.sc_pisum0[c0 + j] : 0.0;
+      nu[u] = out[u] ? L.sc_nuniq[c0 + j] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 32 * u + lane;
+      if (j >= je) continue;
+      const int slot = c0 + j;
+      const double p1 = (ps0[u] + k.pipw) * k.inv_pid;
+      if (full || out[u]) {
+        F.sc_pi[slot] = p1;
+        F.sc_theta[slot] = th_rest;
+      }
+      if (full) {
+        F.sc_ptprev[slot] = invK * invK;
+        F.sc_ptfin[slot] = p1 * th_rest;
+        F.sc_pt[0][slot] = invK * invK;
+        F.sc_pt[1][slot] = invK * invK;
+        F.sc_T[slot] = 0.0;
+      }
+      if (out[u]) {
+        d1 += fabs(p1 - invK);
+        if (nu[u] > 0 && p1 > 0.0) lx += (double)nu[u] * log(p1);
+      }
     }
   }
   d1 = warp_sum(d1);
   lx = warp_sum(lx);
   if (lane == 0) {
-    d1 += (K - (double)nc) * fabs(pi_rest - invK);
-    F.seg_thpw[s] = thpw;
-    F.seg_pipw[s] = pipw;
-    F.seg_inv_thd[s] = inv_thd;
-    F.seg_inv_pid[s] = inv_pid;
+    cc.part[ch] = d1;
+    cc.part[cc.n + ch] = lx;
+  }
+}
+
+__global__ void fit_prepare_kernel(Layout L, FitState F, FitParams P, ColChunks cc) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= L.S) return;
+  const int s = warp;
+  const SegConst k = seg_constants(L, P, s);
+  const int nc = L.seg_ncol[s];
+  const int ch0 = cc.seg_chunk0[s], nch = (nc + SS_COL_CHUNK - 1) / SS_COL_CHUNK;
+  double d1 = 0.0, lx = 0.0;
+  for (int i = lane; i < nch; i += 32) {
+    d1 += cc.part[ch0 + i];
+    lx += cc.part[cc.n + ch0 + i];
+  }
+  d1 = warp_sum(d1);
+  lx = warp_sum(lx);
+  if (lane == 0) {
+    const double pi_rest = k.pipw * k.inv_pid;
+    d1 += ((double)P.K - (double)nc) * fabs(pi_rest - k.invK);
+    F.seg_thpw[s] = k.thpw;
+    F.seg_pipw[s] = k.pipw;
+    F.seg_inv_thd[s] = k.inv_thd;
+    F.seg_inv_pid[s] = k.inv_pid;
     F.seg_diff1_extra[s] = d1;
     F.seg_lnl_extra[s] = lx + L.seg_logq_uniq[s];
     F.seg_diffacc[s] = 0.0;
     F.seg_lnl[s] = 0.0;
     F.seg_iters[s] = 0;
-    F.seg_flags[s] = bad ? 4 : 0;
+    F.seg_flags[s] = k.bad ? 4 : 0;
   }
 }
 
@@ -502,19 +568,25 @@ __global__ void __maxnreg__(MAXREG) em_lane_kernel(EmArgs a) {
         if (z > 0.0 && pn > 0.0) l = fma(z, log(gq[e] * pn), l);
       }
     }
+    // + the unique rows of the tile's columns, n_uniq_j * log(pi_j) (the columns no tile touches are in
+    // seg_lnl_extra): the tile of a single-tile segment carries the segment's whole ambiguous-column part
+    if (has_uniq) {
+#pragma unroll
+      for (int j = 0; j < FC; ++j)
+        if (cc[j] >= 0) {
+          const int nu = nuq[cc[j]];
+          if (nu > 0 && cpi[j] > 0.0) l += (double)nu * log(cpi[j]);
+        }
+      for (int c = warp; c < b128; c += NW)
+        if (lane == 0) { const int nu = nuq[c]; if (nu > 0 && aux[c] > 0.0) l += (double)nu * log(aux[c]); }
+      for (int c = c_ovf + tid; c < v.ncol; c += THREADS) {
+        const int nu = nuq[c];
+        if (nu > 0 && aux[c] > 0.0) l += (double)nu * log(aux[c]);
+      }
+    }
     l = lane_block_sum(l, NW, s_red, par++);
   } else {
-    // tile_lnl holds the ambiguous-row part only; the unique-row part is added by finalize
-    if (NW == 1) __syncwarp(); else __syncthreads();
-    double lu = 0.0;
-    if (has_uniq)
-      for (int c = tid; c < v.ncol; c += THREADS) {
-        const int nu = nuq[c];
-        const double pn = aux[c];
-        if (nu > 0 && pn > 0.0) lu += (double)nu * log(pn);
-      }
-    lu = lane_block_sum(lu, NW, s_red, par++);
-    l = lnl_amb - lu;
+    l = lnl_amb;                 // lnL of the last iteration: ambiguous rows + unique rows of the tile's columns
   }
   if (tid == 0) {
     a.F.tile_lnl[t] = l;
@@ -1307,28 +1379,54 @@ __global__ void emit_unique_kernel(Layout L, double* __restrict__ z_out) {
   z_out[L.u_pos[i]] = 1.0;
 }
 
+// unique rows on the tile columns of multi-tile segments: sum of n_uniq_j * log(pi_j), one warp per column
+// chunk (a single tile adds this part itself -- lane kernel; the columns no tile touches are in seg_lnl_extra)
+__global__ void fit_finalize_cols_kernel(Layout L, FitState F, const int8_t* __restrict__ sc_inamb, ColChunks cc) {
+  const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ch >= cc.n) return;
+  const int s = cc.seg[ch];
+  if (L.seg_ntiles[s] < 2) return;
+  const int c0 = L.seg_col0[s], nc = L.seg_ncol[s];
+  const int jb = cc.j0[ch], je = min(nc, jb + SS_COL_CHUNK);
+  double l = 0.0;
+  for (int j0 = jb; j0 < je; j0 += 128) {
+    int nu[4];
+    double p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 32 * u + lane;
+      nu[u] = j < je && sc_inamb[c0 + j] ? L.sc_nuniq[c0 + j] : 0;
+      p[u] = j < je ? F.sc_pi[c0 + j] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (nu[u] > 0 && p[u] > 0.0) l += (double)nu[u] * log(p[u]);
+  }
+  l = warp_sum(l);
+  if (lane == 0) cc.part[ch] = l;
+}
+
 // per segment: final lnL = sum of tile parts + unique-row part; segments without tiles
 // (no ambiguous rows) are solved in closed form.  One warp per segment.
-__global__ void fit_finalize_kernel(Layout L, FitState F, FitParams P) {
+__global__ void fit_finalize_kernel(Layout L, FitState F, FitParams P, ColChunks cc) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= L.S) return;
   const int s = warp;
   if (F.seg_flags[s] & 4) return;
   const int nt = L.seg_ntiles[s], t0 = L.seg_tile0[s];
-  const int c0 = L.seg_col0[s], nc = L.seg_ncol[s];
   double l = 0.0;
-  for (int j = lane; j < nc; j += 32) {
-    const int nu = L.sc_nuniq[c0 + j];
-    const double p = F.sc_pi[c0 + j];
-    if (nu > 0 && p > 0.0) l += (double)nu * log(p);
+  if (nt > 1) {
+    const int ch0 = cc.seg_chunk0[s], nch = (L.seg_ncol[s] + SS_COL_CHUNK - 1) / SS_COL_CHUNK;
+    for (int i = lane; i < nch; i += 32) l += cc.part[ch0 + i];
   }
   l = warp_sum(l);
   double lt = 0.0;
   for (int t = lane; t < nt; t += 32) lt += F.tile_lnl[t0 + t];
   lt = warp_sum(lt);
   if (lane == 0) {
-    F.seg_lnl[s] = lt + l + L.seg_logq_uniq[s];
+    F.seg_lnl[s] = lt + l + F.seg_lnl_extra[s];
     if (nt == 0) {
       // T = 0 in every iteration: pi is constant after iteration 1
       const double d1 = F.seg_diff1_extra[s];
@@ -1476,10 +1574,20 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     }
     return SS_OK;
   }
+  ColChunks chunks;
+  chunks.n = h->n_col_chunks;
+  chunks.seg = h->chunk_seg;
+  chunks.j0 = h->chunk_j0;
+  chunks.seg_chunk0 = h->seg_chunk0;
+  chunks.part = h->chunk_part;
   if (L.S > 0) {
     const int warps_per_block = 8;
-    fit_prepare_kernel<<<(L.S + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-        L, F, h->P, h->sc_inamb);
+    if (h->n_col_chunks > 0) {
+      fit_prepare_cols_kernel<<<(h->n_col_chunks + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+          L, F, h->P, h->sc_inamb, chunks);
+      h->launches++;
+    }
+    fit_prepare_kernel<<<(L.S + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(L, F, h->P, chunks);
     h->launches++;
     SS_CUDA_CHECK(h, cudaGetLastError());
   }
@@ -1636,7 +1744,12 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
   SS_MARK(4);
   if (L.S > 0) {
     const int warps_per_block = 8;
-    fit_finalize_kernel<<<(L.S + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(L, F, h->P);
+    if (h->n_col_chunks > 0 && h->n_stream_tiles + h->n_cluster_tiles > 0) {
+      fit_finalize_cols_kernel<<<(h->n_col_chunks + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+          L, F, h->sc_inamb, chunks);
+      h->launches++;
+    }
+    fit_finalize_kernel<<<(L.S + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(L, F, h->P, chunks);
     h->launches++;
     SS_CUDA_CHECK(h, cudaGetLastError());
   }

@@ -38,6 +38,7 @@ constexpr int SS_FR_BIG = SS_FR_BIG_V, SS_FC_BIG = SS_FC_BIG_V, SS_MAXREG_BIG = 
 constexpr int SS_CLS_THREADS[] = {SS_CLS_LIST, SS_BIG_THREADS_V};
 constexpr int SS_NUM_CLASSES = (int)(sizeof(SS_CLS_THREADS) / sizeof(int));
 constexpr int SS_NUM_AUX_STREAMS = SS_NUM_CLASSES + 1 + 7;   // size classes, streaming kernel, cluster sizes 2..8
+constexpr int SS_COL_CHUNK = 512;
 constexpr int SS_DN_MAXW = 8;   // ranks of a row-sharded (dense) fit: the GPUs of one NVSwitch domain
 constexpr int SS_DN_THREADS = 512;    // CTA size of the row-sharded kernels = columns per update chunk
 constexpr int SS_DN_TAIL = 8;   // scalar slots behind the K columns of an exchange buffer ([0] = lnL part)
@@ -66,6 +67,14 @@ struct ss_handle_s {
   int* stream_col_seg = nullptr;  // device: for every column of a multi-tile segment, index into stream_segs
   int* stream_col_slot = nullptr; // device: its absolute slot
   long long n_stream_cols = 0;
+  // column chunks (SS_COL_CHUNK slots of one segment each): the per-column work of prepare / finalize runs one
+  // warp per chunk, so a segment with many columns does not serialise on one warp; partial sums are combined
+  // per segment in chunk order (deterministic)
+  int n_col_chunks = 0;
+  int* chunk_seg = nullptr;       // device: segment of the chunk
+  int* chunk_j0 = nullptr;        // device: first column (segment-relative) of the chunk
+  int* seg_chunk0 = nullptr;      // device: first chunk of the segment
+  double* chunk_part = nullptr;   // device: [2][n_col_chunks] partial sums
   size_t stream_smem = 0;
   // segments of 2..8 tiles: one thread-block cluster per segment (DSMEM exchange)
   static constexpr int MAX_CLUSTER = 8;

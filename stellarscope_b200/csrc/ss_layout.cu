@@ -30,6 +30,9 @@ void free_layout(ss_handle_s* h) {
   h->n_stream_tiles = h->n_stream_segs = 0;
   h->n_stream_cols = 0;
   h->all_tiles = nullptr;
+  h->n_col_chunks = 0;
+  h->chunk_seg = h->chunk_j0 = h->seg_chunk0 = nullptr;
+  h->chunk_part = nullptr;
   h->sc_inamb = nullptr;
   for (int k = 0; k <= ss_handle_s::MAX_CLUSTER; ++k) { h->clu_segs[k] = nullptr; h->clu_count[k] = 0; h->clu_smem[k] = 0; }
   h->clu_xref = nullptr; h->seg_xref_off = nullptr; h->n_cluster_tiles = h->n_cluster_segs = 0;
@@ -235,6 +238,22 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
   h->n_stream_tiles = (int)stream.size();
   SS_CUDA_CHECK(h, upload(pool, &h->stream_tiles, (const int*)stream.data(), stream.size(), st));
   SS_CUDA_CHECK(h, upload(pool, &h->all_tiles, (const int*)all.data(), all.size(), st));
+  // column chunks of all segments (prepare / finalize)
+  {
+    std::vector<int> cseg, cj0, sc0((size_t)std::max(L.S, 1), 0);
+    for (int s = 0; s < L.S; ++s) {
+      sc0[s] = (int)cseg.size();
+      for (int j = 0; j < seg_ncol[s]; j += SS_COL_CHUNK) {
+        cseg.push_back(s);
+        cj0.push_back(j);
+      }
+    }
+    h->n_col_chunks = (int)cseg.size();
+    SS_CUDA_CHECK(h, upload(pool, &h->chunk_seg, (const int*)cseg.data(), cseg.size(), st));
+    SS_CUDA_CHECK(h, upload(pool, &h->chunk_j0, (const int*)cj0.data(), cj0.size(), st));
+    SS_CUDA_CHECK(h, upload(pool, &h->seg_chunk0, (const int*)sc0.data(), sc0.size(), st));
+    SS_CUDA_CHECK(h, dev_alloc(pool, &h->chunk_part, (size_t)std::max(2 * h->n_col_chunks, 1)));
+  }
   // multi-tile segments and their columns
   std::vector<int> segs, col_seg, col_slot;
   for (int s = 0; s < L.S; ++s) {
