@@ -16,6 +16,13 @@
 
 namespace cg = cooperative_groups;
 
+// streaming kernel: CTA size and fragment slots per lane (rows / columns) of the tile pass
+#ifndef SS_STREAM_THREADS
+#define SS_STREAM_THREADS 512
+#define SS_STREAM_FR 2
+#define SS_STREAM_FC 3
+#endif
+
 namespace ss {
 
 struct StreamArgs {
@@ -1222,7 +1229,7 @@ __global__ void __launch_bounds__(THREADS) em_stream_kernel(EmArgs a, StreamArgs
     const int cur = (it - 1) & 1;
     const double* __restrict__ ptg = a.F.sc_pt[cur];
     // ---- tile pass: phase A + B, partial thetasum -> global accumulators (double-buffered TMA, lane fragments) ----
-    lane_stream_pass<THREADS, 2, 3>(a.L, a.L.c_scol, sa.tiles, sa.n_tiles, a.F.seg_iters, ptg, a.F.sc_T, sa.geom, dsm,
+    lane_stream_pass<THREADS, SS_STREAM_FR, SS_STREAM_FC>(a.L, a.L.c_scol, sa.tiles, sa.n_tiles, a.F.seg_iters, ptg, a.F.sc_T, sa.geom, dsm,
                                     s_bars, uses);
     grid.sync();
     // ---- update pass over the columns of the active multi-tile segments ----
@@ -1508,7 +1515,7 @@ cudaError_t ensure_aux_streams(ss_handle_s* h) {
   return cudaSuccess;
 }
 
-constexpr int STREAM_THREADS = 512;
+constexpr int STREAM_THREADS = SS_STREAM_THREADS;
 constexpr int CLUSTER_THREADS = 512;
 
 int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
