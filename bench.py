@@ -39,10 +39,10 @@ METRIC = 'alignments_x_em_iterations_per_sec'
 UNIT = 'aln*iter/s'
 WORKLOAD = dict(n_cells=10_000, n_alignments=5_000_000, n_loci=28_000)
 # dram__bytes_read.sum + dram__bytes_write.sum of the 16 fused E+M kernels of ONE fit of this workload, from the
-# ncu --set full capture profiles/r1d_em_full_ncu.csv (110.8 MB read + 0.2 MB written): every cell is read from
+# ncu --set full capture profiles/r1e_em_full_ncu.csv (110.8 MB read + 0.2 MB written): every cell is read from
 # HBM once; the iterations run out of registers / shared memory
 NCU_DRAM_BYTES_PER_FIT = 111.0e6
-NCU_DRAM_SOURCE = 'profiles/r1d_em_full_ncu.csv (ncu --set full, one fit, sum over the 16 EM kernels)'
+NCU_DRAM_SOURCE = 'profiles/r1e_em_full_ncu.csv (ncu --set full, one fit, sum over the 16 EM kernels)'
 CPU_SAMPLE_CELLS = 10000     # the CPU baseline fits every cell of the workload (about 10-15 s on 16 cores)
 OPTS = dict(em_epsilon=1e-7, max_iter=100, pi_prior=0, theta_prior=200000)   # stellarscope_assign.yaml:231-250
 
