@@ -59,7 +59,7 @@ class TelescopeLikelihood(object):
     ]
 
     def __init__(self, score_matrix, opts, row_segment=None, n_segments=None, device=None,
-                 tie_tol=TIE_TOL_DEFAULT, shard=None):
+                 tie_tol=TIE_TOL_DEFAULT, shard=None, device_matrix=None):
         self.opts = opts
         self.epsilon = opts.em_epsilon
         self.max_iter = opts.max_iter
@@ -80,7 +80,10 @@ class TelescopeLikelihood(object):
         for attempt in (0, 1):
             if m.dtype != np.uint16 and m.nnz and (m.data.max() > 65535 or m.data.min() < 0):
                 raise StellarscopeError('alignment scores outside [0, 65535] are not supported (uint16, model.py:964)')
-            self._engine.set_matrix(m.indptr, m.indices, m.data, self.K)        # H2D in flight ...
+            if device_matrix is not None and attempt == 0:
+                self._engine.set_matrix_device(*device_matrix, self.K)         # canonical copy of another model object
+            else:
+                self._engine.set_matrix(m.indptr, m.indices, m.data, self.K)    # H2D in flight ...
             if attempt == 0:
                 if callable(row_segment):                                      # ... while the host walks the row sets
                     row_segment, self.segment_keys = row_segment()
@@ -338,6 +341,15 @@ def pooling_row_segments(st, opts):
     return seg, list(range(i))
 
 
+def _row_cells(st):
+    """Cell (running index of the barcode in ``bcode_ridx_map``) of every row, -1 for rows of no barcode."""
+    from . import hostutil
+    groups = list(st.bcode_ridx_map.values())
+    cell = np.full(st.shape[0], -1, dtype=np.int32)
+    hostutil.fill_row_segments(groups, np.arange(len(groups), dtype=np.int32), cell)
+    return cell
+
+
 def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
     """Fit model using different pooling modes (model.py:675-804).
 
@@ -365,9 +377,13 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
             from . import parallel
             import torch.distributed as dist
             m = _canonical_csr(fullmat)
-            r0, r1 = parallel.row_block(m.indptr, rank, world)
             seg = np.full(m.shape[0], -1, dtype=np.int32)
-            seg[r0:r1] = 0
+            if getattr(opts, 'umi_counts', False):
+                # distinct UMIs are counted per cell: all reads of a cell on one rank
+                seg[parallel.model_cell_block(np.diff(m.indptr), np.arange(m.shape[0]), _row_cells(st), rank, world)] = 0
+            else:
+                r0, r1 = parallel.row_block(m.indptr, rank, world)
+                seg[r0:r1] = 0
             ret_model = TelescopeLikelihood(m, opts, row_segment=seg, n_segments=1,
                                             shard=(rank, world, None, getattr(opts, 'peer_exchange', True)))
         else:
@@ -396,7 +412,11 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
         import torch.distributed as dist
         row_segment, keys = pooling_row_segments(st, opts)
         m = _canonical_csr(fullmat)
-        shards, _ = parallel.shard_models(m.indptr, row_segment, len(keys), world)
+        # a model larger than a rank's fair share (the biggest cell types on 8 GPUs) cannot be balanced by packing
+        # whole models: such WIDE models are fitted by all ranks together, rows cut into blocks like pseudobulk
+        wf = getattr(opts, 'wide_model_factor', 1.0)            # None: never split a model
+        shards, _, wide = parallel.shard_models(m.indptr, row_segment, len(keys), world,
+                                                wide_factor=float('inf') if wf is None else wf)
         mine = shards[rank]
         remap = np.full(len(keys) + 1, -1, dtype=np.int32)
         remap[mine] = np.arange(len(mine), dtype=np.int32)
@@ -406,13 +426,38 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
         local = ret_model.fit_segments()
         gathered = [None] * world
         dist.all_gather_object(gathered, (np.asarray(mine), local._res, local._itime))
+        fields = ('iters', 'flags', 'lnl', 'nobs', 'nfeats', 'diffs')
+        parts = [(np.asarray(g[0], dtype=np.int64), g[1]) for g in gathered]
+        itime = max(g[2] for g in gathered)
+        if len(wide):
+            lens = np.diff(m.indptr)
+            eng = ret_model._engine
+            dev_matrix = tuple(eng._keep[k] for k in ('row_ptr', 'col_idx', 'score'))
+            z_all = ret_model._z_device()
+            row_cell = _row_cells(st) if getattr(opts, 'umi_counts', False) else None
+            for w in wide:
+                rows_w = np.flatnonzero(row_segment == w)
+                if row_cell is None:
+                    rows_w = parallel.model_row_block(lens, rows_w, rank, world)
+                else:                                       # per (cell, UMI) counting: whole cells per rank
+                    rows_w = parallel.model_cell_block(lens, rows_w, row_cell, rank, world)
+                seg_w = np.full(m.shape[0], -1, dtype=np.int32)
+                seg_w[rows_w] = 0
+                tw = TelescopeLikelihood(m, opts, row_segment=seg_w, n_segments=1, device_matrix=dev_matrix,
+                                         shard=(rank, world, None, getattr(opts, 'peer_exchange', True)))
+                info_w = tw.fit_segments()                  # the same record on every rank
+                z_all += tw._z_device()                     # disjoint rows: the rank-local z of the wide model
+                parts.append((np.array([w], dtype=np.int64), info_w._res))
+                itime = max(itime, info_w._itime)
+                tw._engine.sync_ranks()
+                tw.close()
+            ret_model.wide_model_ids = wide
         # concatenate the per-rank result arrays; order[i] = row of model i in the concatenation
-        ids = np.concatenate([np.asarray(g[0], dtype=np.int64) for g in gathered])
-        res = {k: np.concatenate([g[1][k] for g in gathered]) for k in ('iters', 'flags', 'lnl', 'nobs', 'nfeats', 'diffs')}
+        ids = np.concatenate([p[0] for p in parts])
+        res = {k: np.concatenate([np.asarray(p[1][k]) for p in parts]) for k in fields}
         order = np.empty(len(keys), dtype=np.int64)
         order[ids] = np.arange(len(ids))
-        infos = SegmentFitInfos(res, ret_model.epsilon, ret_model.max_iter, max(g[2] for g in gathered),
-                                keys=keys, order=order)
+        infos = SegmentFitInfos(res, ret_model.epsilon, ret_model.max_iter, itime, keys=keys, order=order)
     poolinfo.models_info = infos
     lg.info(f'        ...{len(infos)} models fitted')
     ret_model.lnl = poolinfo.total_lnl                      # model.py:803

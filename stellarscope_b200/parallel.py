@@ -31,6 +31,22 @@ def lpt_shards(sizes, world):
     return [np.array(sorted(b), dtype=np.int64) for b in bins]
 
 
+def model_cell_block(lens, rows, row_cell, rank, world):
+    """Like ``model_row_block`` but whole CELLS go to a rank (``row_cell[i]`` = cell of row i; the rows of a cell
+    need not be contiguous): the cells of the model, in id order, are cut into ``world`` consecutive groups of
+    about equal alignment count.  Needed when the counting is per (cell, UMI) -- ``--umi_counts`` -- because the
+    distinct UMIs of a cell can only be counted where all its reads are ("keep a cell's rows
+    together so counts stay rank-local")."""
+    rows = np.asarray(rows, dtype=np.int64)
+    if len(rows) == 0:
+        return rows
+    cells, inv = np.unique(np.asarray(row_cell)[rows], return_inverse=True)
+    a_cell = np.bincount(inv, weights=np.asarray(lens, dtype=np.int64)[rows], minlength=len(cells))
+    mid = np.cumsum(a_cell) - 0.5 * a_cell                        # midpoint rule: monotone -> consecutive groups
+    cell_rank = np.minimum(world - 1, (mid * world / max(float(a_cell.sum()), 1.0)).astype(np.int64))
+    return rows[cell_rank[inv] == rank]
+
+
 def extract_rows(indptr, indices, data, rows):
     """Row-compacted CSR of ``rows`` (ascending)."""
     rows = np.asarray(rows, dtype=np.int64)
@@ -41,12 +57,41 @@ def extract_rows(indptr, indices, data, rows):
     return ptr, indices[take], data[take], take
 
 
-def shard_models(indptr, row_segment, n_segments, world):
-    """(per-rank model index arrays, alignments per model) for a row -> model map."""
+def shard_models(indptr, row_segment, n_segments, world, wide_factor=None):
+    """(per-rank model index arrays, alignments per model) for a row -> model map.
+
+    With ``wide_factor`` a third value is returned: the WIDE models, those with more than
+    ``wide_factor * A_total / world`` alignments (no packing of whole models can balance a model that is
+    larger than a rank's fair share, e.g. the largest of 20 cell types on 8 GPUs).  They are left out of the
+    per-rank lists: their ROWS are cut into ``world`` blocks and fitted by all ranks together like a
+    pseudobulk model (celltype row)."""
     lens = np.diff(indptr).astype(np.int64)
     fitted = row_segment >= 0
     seg_A = np.bincount(row_segment[fitted], weights=lens[fitted], minlength=n_segments).astype(np.int64)
-    return lpt_shards(seg_A, world), seg_A
+    if wide_factor is None:
+        return lpt_shards(seg_A, world), seg_A
+    wide = wide_models(seg_A, world, wide_factor)
+    narrow = np.setdiff1d(np.arange(n_segments, dtype=np.int64), wide)
+    shards = [narrow[b] for b in lpt_shards(seg_A[narrow], world)]
+    return shards, seg_A, wide
+
+
+def wide_models(seg_A, world, factor=1.0):
+    """Indices (ascending) of the models with more than ``factor * sum(seg_A) / world`` alignments."""
+    seg_A = np.asarray(seg_A, dtype=np.int64)
+    if world < 2 or factor is None or len(seg_A) == 0:
+        return np.zeros(0, dtype=np.int64)
+    return np.flatnonzero(seg_A > float(factor) * float(seg_A.sum()) / world).astype(np.int64)
+
+
+def model_row_block(lens, rows, rank, world):
+    """The block of ``rows`` (ascending row ids of ONE model) that ``rank`` fits when the model's rows are cut
+    into ``world`` consecutive blocks of about equal alignment count."""
+    rows = np.asarray(rows, dtype=np.int64)
+    ptr = np.zeros(len(rows) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(lens, dtype=np.int64)[rows], out=ptr[1:])
+    a, b = row_block(ptr, rank, world)
+    return rows[a:b]
 
 
 def local_problem(indptr, indices, data, row_segment, my_models):

@@ -172,3 +172,53 @@ def test_row_sharded_pseudobulk_protocol_world2_gloo():
     assert got[0][2] == got[1][2]                                   # bit-identical parameters on both ranks
     ok = po > 1e-290
     assert np.max(np.abs(np.array(got[0][2])[ok] - po[ok]) / po[ok]) < 1e-9
+
+
+def test_wide_models_are_split_by_rows_and_left_out_of_the_packing():
+    """Celltype sharding: a model larger than a rank's fair share is fitted by all ranks
+    (rows cut into blocks of equal alignment count), the others are packed whole (LPT)."""
+    from stellarscope_b200 import parallel
+    rng = np.random.default_rng(3)
+    n_rows, n_models, world = 4000, 6, 4
+    lens = rng.integers(2, 9, n_rows)
+    indptr = np.zeros(n_rows + 1, dtype=np.int64)
+    np.cumsum(lens, out=indptr[1:])
+    seg = rng.choice(n_models, size=n_rows, p=[0.55, 0.2, 0.1, 0.07, 0.05, 0.03]).astype(np.int32)
+    seg[rng.random(n_rows) < 0.02] = -1                                  # rows of no model
+    shards, seg_A, wide = parallel.shard_models(indptr, seg, n_models, world, wide_factor=1.0)
+    assert wide.tolist() == [0]                                          # 55 % > 1/4
+    assert sorted(np.concatenate(shards).tolist()) == [1, 2, 3, 4, 5]    # every narrow model on exactly one rank
+    assert int(seg_A.sum()) == int(lens[seg >= 0].sum())
+    # the wide model: the ranks' blocks partition its rows, in order, with balanced alignment counts
+    rows = np.flatnonzero(seg == 0)
+    blocks = [parallel.model_row_block(lens, rows, r, world) for r in range(world)]
+    assert np.array_equal(np.concatenate(blocks), rows)
+    loads = np.array([lens[b].sum() for b in blocks])
+    assert loads.max() - loads.min() <= 2 * lens.max()
+    # total load per rank (narrow models + its block of the wide one) is balanced much better than LPT alone
+    tot = np.array([seg_A[shards[r]].sum() + loads[r] for r in range(world)])
+    plain = np.array([seg_A[b].sum() for b in parallel.lpt_shards(seg_A, world)])
+    assert tot.max() < 0.65 * plain.max()
+    # switches: a huge factor (or world 1) splits nothing; the two-value form is unchanged
+    assert parallel.shard_models(indptr, seg, n_models, world, wide_factor=float('inf'))[2].size == 0
+    assert parallel.wide_models(seg_A, 1, 1.0).size == 0
+    assert len(parallel.shard_models(indptr, seg, n_models, world)) == 2
+    assert parallel.wide_models(seg_A, world, 0.7).tolist() == [0, 1]          # 20 % > 0.7 / 4
+
+
+def test_cell_blocks_keep_the_rows_of_a_cell_on_one_rank():
+    from stellarscope_b200 import parallel
+    rng = np.random.default_rng(4)
+    n_rows, n_cells, world = 6000, 150, 4
+    lens = rng.integers(2, 9, n_rows)
+    row_cell = rng.integers(0, n_cells, n_rows).astype(np.int32)         # rows of a cell are scattered (BAM order)
+    rows = np.flatnonzero(rng.random(n_rows) < 0.7)                      # the rows of one model
+    blocks = [parallel.model_cell_block(lens, rows, row_cell, r, world) for r in range(world)]
+    assert np.array_equal(np.sort(np.concatenate(blocks)), rows)         # a partition of the model's rows
+    owner = {}
+    for r, b in enumerate(blocks):
+        for c in np.unique(row_cell[b]):
+            assert owner.setdefault(int(c), r) == r                      # no cell on two ranks
+    loads = np.array([lens[b].sum() for b in blocks], dtype=float)
+    assert loads.max() / loads.mean() < 1.1
+    assert parallel.model_cell_block(lens, np.zeros(0, dtype=np.int64), row_cell, 0, world).size == 0
