@@ -412,11 +412,13 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
         import torch.distributed as dist
         row_segment, keys = pooling_row_segments(st, opts)
         m = _canonical_csr(fullmat)
-        # a model larger than a rank's fair share (the biggest cell types on 8 GPUs) cannot be balanced by packing
+        # a model much larger than a rank's fair share (a dominant cell type on 8 GPUs) cannot be balanced by packing
         # whole models: such WIDE models are fitted by all ranks together, rows cut into blocks like pseudobulk
-        wf = getattr(opts, 'wide_model_factor', 1.0)            # None: never split a model
+        # opts.wide_models: None (default: pack whole models), 'auto' (parallel.wide_models) or a list of model indices;
+        # opts.wide_model_cost: lockstep overhead of one wide model in alignments of single-GPU work
         shards, _, wide = parallel.shard_models(m.indptr, row_segment, len(keys), world,
-                                                wide_factor=float('inf') if wf is None else wf)
+                                                wide=getattr(opts, 'wide_models', None) or [],
+                                                wide_cost=getattr(opts, 'wide_model_cost', 2_000_000))
         mine = shards[rank]
         remap = np.full(len(keys) + 1, -1, dtype=np.int32)
         remap[mine] = np.arange(len(mine), dtype=np.int32)
@@ -449,6 +451,7 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
                 z_all += tw._z_device()                     # disjoint rows: the rank-local z of the wide model
                 parts.append((np.array([w], dtype=np.int64), info_w._res))
                 itime = max(itime, info_w._itime)
+                ret_model.fit_seconds_wide = getattr(ret_model, 'fit_seconds_wide', 0.0) + (tw.fit_seconds or 0.0)
                 tw._engine.sync_ranks()
                 tw.close()
             ret_model.wide_model_ids = wide

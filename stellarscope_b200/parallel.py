@@ -57,31 +57,58 @@ def extract_rows(indptr, indices, data, rows):
     return ptr, indices[take], data[take], take
 
 
-def shard_models(indptr, row_segment, n_segments, world, wide_factor=None):
+def shard_models(indptr, row_segment, n_segments, world, wide=None, wide_cost=2_000_000, wide_gain=0.03):
     """(per-rank model index arrays, alignments per model) for a row -> model map.
 
-    With ``wide_factor`` a third value is returned: the WIDE models, those with more than
-    ``wide_factor * A_total / world`` alignments (no packing of whole models can balance a model that is
-    larger than a rank's fair share, e.g. the largest of 20 cell types on 8 GPUs).  They are left out of the
-    per-rank lists: their ROWS are cut into ``world`` blocks and fitted by all ranks together like a
-    pseudobulk model (celltype row)."""
+    With ``wide`` a third value is returned, the WIDE models: ``'auto'`` chooses them (``wide_models``), a list
+    names them.  They are left out of the per-rank lists: their ROWS are cut into ``world`` blocks and fitted
+    by all ranks together like a pseudobulk model (celltype row)."""
     lens = np.diff(indptr).astype(np.int64)
     fitted = row_segment >= 0
     seg_A = np.bincount(row_segment[fitted], weights=lens[fitted], minlength=n_segments).astype(np.int64)
-    if wide_factor is None:
+    if wide is None:
         return lpt_shards(seg_A, world), seg_A
-    wide = wide_models(seg_A, world, wide_factor)
-    narrow = np.setdiff1d(np.arange(n_segments, dtype=np.int64), wide)
+    if isinstance(wide, str):
+        wide_ids = wide_models(seg_A, world, wide_cost, wide_gain)
+    else:
+        wide_ids = np.array(sorted(int(w) for w in wide), dtype=np.int64)
+        if world < 2:
+            wide_ids = wide_ids[:0]
+    narrow = np.setdiff1d(np.arange(n_segments, dtype=np.int64), wide_ids)
     shards = [narrow[b] for b in lpt_shards(seg_A[narrow], world)]
-    return shards, seg_A, wide
+    return shards, seg_A, wide_ids
 
 
-def wide_models(seg_A, world, factor=1.0):
-    """Indices (ascending) of the models with more than ``factor * sum(seg_A) / world`` alignments."""
+def makespan(seg_A, world, wide, cost):
+    """Load of the fullest rank in alignments: its packed models (LPT) plus, for every wide model, 1/world of
+    its alignments and ``cost`` -- the price of fitting in lockstep with the other ranks (one exchange and two
+    grid-wide barriers per iteration, ~20 us x ~80 iterations, expressed in alignments of single-GPU work)."""
     seg_A = np.asarray(seg_A, dtype=np.int64)
-    if world < 2 or factor is None or len(seg_A) == 0:
+    wide = np.asarray(wide, dtype=np.int64)
+    narrow = np.setdiff1d(np.arange(len(seg_A)), wide)
+    packed = max((float(seg_A[narrow[b]].sum()) for b in lpt_shards(seg_A[narrow], world)), default=0.0)
+    return packed + float(seg_A[wide].sum()) / world + float(cost) * len(wide)
+
+
+def wide_models(seg_A, world, cost=2_000_000, gain=0.03):
+    """Models that are fitted by all ranks together instead of being packed onto one rank (ascending indices).
+
+    Packing whole models (LPT) cannot balance a model that is much larger than a rank's fair share -- a
+    dominant cell type on 8 GPUs.  Greedy on ``makespan``: the largest packed model becomes wide as long as
+    that shortens the fullest rank's load by more than ``gain`` (relative).  ``cost=None`` never splits."""
+    seg_A = np.asarray(seg_A, dtype=np.int64)
+    if world < 2 or cost is None or len(seg_A) == 0:
         return np.zeros(0, dtype=np.int64)
-    return np.flatnonzero(seg_A > float(factor) * float(seg_A.sum()) / world).astype(np.int64)
+    order = np.lexsort((np.arange(len(seg_A)), -seg_A))           # candidates, largest first
+    wide = []
+    now = makespan(seg_A, world, wide, cost)
+    for cand in order:
+        new = makespan(seg_A, world, wide + [int(cand)], cost)
+        if not new < (1.0 - gain) * now:
+            break
+        wide.append(int(cand))
+        now = new
+    return np.array(sorted(wide), dtype=np.int64)
 
 
 def model_row_block(lens, rows, rank, world):

@@ -175,8 +175,8 @@ def test_row_sharded_pseudobulk_protocol_world2_gloo():
 
 
 def test_wide_models_are_split_by_rows_and_left_out_of_the_packing():
-    """Celltype sharding: a model larger than a rank's fair share is fitted by all ranks
-    (rows cut into blocks of equal alignment count), the others are packed whole (LPT)."""
+    """Celltype sharding: a model that whole-model packing (LPT) cannot balance is fitted by all
+    ranks (rows cut into blocks of equal alignment count), the others are packed whole."""
     from stellarscope_b200 import parallel
     rng = np.random.default_rng(3)
     n_rows, n_models, world = 4000, 6, 4
@@ -185,25 +185,35 @@ def test_wide_models_are_split_by_rows_and_left_out_of_the_packing():
     np.cumsum(lens, out=indptr[1:])
     seg = rng.choice(n_models, size=n_rows, p=[0.55, 0.2, 0.1, 0.07, 0.05, 0.03]).astype(np.int32)
     seg[rng.random(n_rows) < 0.02] = -1                                  # rows of no model
-    shards, seg_A, wide = parallel.shard_models(indptr, seg, n_models, world, wide_factor=1.0)
-    assert wide.tolist() == [0]                                          # 55 % > 1/4
-    assert sorted(np.concatenate(shards).tolist()) == [1, 2, 3, 4, 5]    # every narrow model on exactly one rank
+    shards, seg_A, wide = parallel.shard_models(indptr, seg, n_models, world, wide='auto', wide_cost=0, wide_gain=0.1)
+    assert wide.tolist() == [0, 1]                                       # 55 % and 20 % against a fair share of 25 %
+    assert sorted(np.concatenate(shards).tolist()) == [2, 3, 4, 5]       # every packed model on exactly one rank
     assert int(seg_A.sum()) == int(lens[seg >= 0].sum())
-    # the wide model: the ranks' blocks partition its rows, in order, with balanced alignment counts
+    # a wide model: the ranks' blocks partition its rows, in order, with balanced alignment counts
     rows = np.flatnonzero(seg == 0)
     blocks = [parallel.model_row_block(lens, rows, r, world) for r in range(world)]
     assert np.array_equal(np.concatenate(blocks), rows)
     loads = np.array([lens[b].sum() for b in blocks])
     assert loads.max() - loads.min() <= 2 * lens.max()
-    # total load per rank (narrow models + its block of the wide one) is balanced much better than LPT alone
-    tot = np.array([seg_A[shards[r]].sum() + loads[r] for r in range(world)])
-    plain = np.array([seg_A[b].sum() for b in parallel.lpt_shards(seg_A, world)])
-    assert tot.max() < 0.65 * plain.max()
-    # switches: a huge factor (or world 1) splits nothing; the two-value form is unchanged
-    assert parallel.shard_models(indptr, seg, n_models, world, wide_factor=float('inf'))[2].size == 0
-    assert parallel.wide_models(seg_A, 1, 1.0).size == 0
+    # the fullest rank carries much less than with packing alone
+    plain = parallel.makespan(seg_A, world, [], 0)
+    assert plain == max(seg_A[b].sum() for b in parallel.lpt_shards(seg_A, world))
+    assert parallel.makespan(seg_A, world, wide, 0) < 0.6 * plain
+    # the lockstep cost of a wide model decides: expensive exchange -> fewer / no wide models
+    assert parallel.wide_models(seg_A, world, cost=0.05 * seg_A.sum(), gain=0.03).tolist() == [0]
+    assert parallel.wide_models(seg_A, world, cost=seg_A.sum(), gain=0.03).size == 0
+    # BASELINE config 3 shape: 20 Dirichlet(0.5) cell types on 8 GPUs, largest 16.8 % (fair share 12.5 %) -- splitting
+    # would cost more than the 1.34 x imbalance; a dominant type of 40 % is split
+    c3 = (np.array([.168, .14, .13, .118, .08, .063, .048, .046, .045, .043, .033, .021, .019, .014, .012, .01, .005, .003,
+                    .002, .002]) * 100e6).astype(np.int64)
+    assert parallel.wide_models(c3, 8).size == 0
+    dom = np.concatenate([[int(0.4 * 100e6)], (c3[1:] * 0.6 / c3[1:].sum() * 100e6).astype(np.int64)])
+    assert parallel.wide_models(dom, 8).tolist() == [0]
+    # switches: None / one rank split nothing; an explicit list is taken as it is; the two-value form is unchanged
+    assert parallel.wide_models(seg_A, world, None).size == 0 and parallel.wide_models(seg_A, 1, 0).size == 0
+    assert parallel.shard_models(indptr, seg, n_models, world, wide=[5, 2])[2].tolist() == [2, 5]
+    assert parallel.shard_models(indptr, seg, n_models, world, wide=[])[2].size == 0
     assert len(parallel.shard_models(indptr, seg, n_models, world)) == 2
-    assert parallel.wide_models(seg_A, world, 0.7).tolist() == [0, 1]          # 20 % > 0.7 / 4
 
 
 def test_cell_blocks_keep_the_rows_of_a_cell_on_one_rank():

@@ -12,14 +12,15 @@ torch.cuda.set_device(local)
 dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 rank, world = dist.get_rank(), dist.get_world_size()
 ok = True
-# (golden, wide_model_factor): the largest cell type of the `celltype` fixture holds 74 % of the alignments, so
-# with the default factor it is fitted by all ranks together (rows in blocks); 0.3 makes two of the three
-# models wide (on 2 ranks one rank then has no model of its own); None never splits a model
-for name, wide_factor in (('individual', 1.0), ('celltype', 1.0), ('celltype', 0.3), ('celltype', None), ('celltype_umidedup', 1.0),
-                          ('individual_umicounts', 1.0)):
+# (golden, wide models): the largest cell type of the `celltype` fixture holds 74 % of the alignments: 'auto' (with the
+# lockstep cost set to 0 for these tiny fixtures) fits it with all ranks together (rows in blocks); [1, 2] makes two
+# of the three models wide (on 2 ranks one rank then has no model of its own), [0, 1, 2] all three (no rank has a
+# model of its own); None never splits a model
+for name, wide in (('individual', 'auto'), ('celltype', 'auto'), ('celltype', [1, 2]), ('celltype', [0, 1, 2]), ('celltype', None),
+                   ('celltype_umidedup', 'auto'), ('individual_umicounts', 'auto')):
     g = H.load_golden(name)
     opts = H.golden_opts(g, cls=H.StOpts)
-    opts.wide_model_factor = wide_factor
+    opts.wide_models, opts.wide_model_cost = wide, 0
     opts.reassign_mode = ['best_exclude', 'best_average', 'total_hits']
     st = H.make_st(g, opts)
     tl, pool = model._fit_pooling_model(st, opts)
@@ -32,7 +33,7 @@ for name, wide_factor in (('individual', 1.0), ('celltype', 1.0), ('celltype', 0
     for m in opts.reassign_mode:
         good &= bool(np.allclose(np.asarray(counts[m].todense()), g[f'c_{m}'], rtol=1e-12, atol=0))
     pi_ok = True
-    print(f'rank {rank}/{world} {name} wide_factor={wide_factor}: local models {tl.n_segments} of {len(keys)}, wide '
+    print(f'rank {rank}/{world} {name} wide={wide}: local models {tl.n_segments} of {len(keys)}, wide '
           f'{list(getattr(tl, "wide_model_ids", []))} -> {"OK" if good else "MISMATCH"}', flush=True)
     ok &= good
 # pseudobulk: ONE model, rows sharded over the ranks; exchange over peer memory (persistent kernel)
@@ -66,13 +67,13 @@ for name in ('pseudobulk', 'pseudobulk_lnl', 'pseudobulk_priors'):
         ok &= good
 # --umi_counts with models / rows split over the ranks: the distinct UMIs of a cell are counted where all its reads
 # are (whole cells per rank); checked against the same call without sharding (every rank alone, all rows)
-for name, wide_factor in (('celltype', 0.3), ('pseudobulk', None), ('individual_umicounts', 1.0)):
+for name, wide in (('celltype', [1, 2]), ('pseudobulk', None), ('individual_umicounts', 'auto')):
     g = H.load_golden(name)
     res = []
     for shard in (True, False):
         opts = H.golden_opts(g, cls=H.StOpts)
         opts.umi_counts, opts.ignore_umi = True, True
-        opts.wide_model_factor = wide_factor
+        opts.wide_models, opts.wide_model_cost = wide, 0
         opts.shard_models = shard
         opts.reassign_mode = ['best_exclude', 'best_average', 'total_hits']
         st = H.make_st(g, opts)
