@@ -351,7 +351,7 @@ def run_ours(args):
                           traffic=NCU_DRAM_BYTES_PER_FIT if world == 1 else None,
                           traffic_source=NCU_DRAM_SOURCE,
                           kernel='fused E+M kernels of one fit: em_lane_kernel (one launch per CTA-size class) + '
-                                 'em_cluster_kernel (cells of 2..8 tiles), launched concurrently',
+                                 'em_clane_kernel (thread-block clusters: cells of 2..8 tiles), launched concurrently',
                           note='EFFECTIVE bandwidth: algorithmic bytes = iterations x (12 B/ambiguous alignment + '
                                '4 B/row + 16 B/active column), SURVEY.md 8d; every model is read from HBM once and '
                                'iterated out of shared memory / registers, so this is not DRAM traffic (see profiles/ '
