@@ -19,7 +19,7 @@ from typing import Optional
 import numpy as np
 import scipy.sparse
 
-from .engine import Engine, ModelError, NotCanonicalError
+from .engine import Engine, ModelError, NotCanonicalError, to_host
 from .sparse_plus import csr_matrix_plus
 from .statistics import FitInfo, PoolInfo, ReassignInfo, SegmentFitInfos, counter_from_hist
 
@@ -167,7 +167,7 @@ class TelescopeLikelihood(object):
         if self._z is None:
             if self.segment_fitinfo is None:
                 return None
-            zd = self._z_device().cpu().numpy()
+            zd = to_host(self._z_device())
             m = csr_matrix_plus((zd, self.raw_scores.indices.copy(), self.raw_scores.indptr.copy()),
                                 shape=self.raw_scores.shape)
             self._z = m
@@ -248,7 +248,7 @@ class TelescopeLikelihood(object):
                 raise StellarscopeError('reassign_mat was not set.')     # model.py:504-505 (no z)
             z = self._z_device()
         flag, nbest, info = self._engine.reassign(mode, z, thresh if thresh is not None else 0.0, self.tie_tol)
-        flag = flag.cpu().numpy().astype(bool)
+        flag = to_host(flag).view(np.bool_)                     # 0 / 1 bytes
         rinfo = ReassignInfo(mode)
         rinfo.assigned, rinfo.ambiguous, rinfo.unaligned = int(info[0]), int(info[1]), int(info[2])
         if mode in ('best_exclude', 'best_random', 'best_average', 'initial_random'):
@@ -256,12 +256,12 @@ class TelescopeLikelihood(object):
         indptr, indices = self.raw_scores.indptr, self.raw_scores.indices
         row = np.repeat(np.arange(self.N, dtype=np.int64), np.diff(indptr))
         if mode in ('best_random', 'initial_random'):
-            flag = _replay_random_choice(flag, row, nbest.cpu().numpy(), self.opts.rng)
+            flag = _replay_random_choice(flag, row, to_host(nbest), self.opts.rng)
         keep_rows = row[flag]
         ptr = np.zeros(self.N + 1, dtype=indptr.dtype)
         np.cumsum(np.bincount(keep_rows, minlength=self.N), out=ptr[1:])
         if mode == 'best_average':
-            nb = nbest.cpu().numpy()
+            nb = to_host(nbest)
             data = 1.0 / nb[keep_rows].astype(np.float64)
         else:
             data = np.ones(len(keep_rows), dtype=np.int8)
