@@ -1,0 +1,26 @@
+"""Device -> host transfer of large results (engine.to_host: pinned ring + threaded copy-out) is a plain copy."""
+import numpy as np
+import pytest
+
+
+@pytest.mark.gpu
+def test_to_host_equals_plain_copy_for_all_result_dtypes_and_sizes():
+    import torch
+    from stellarscope_b200 import engine
+    g = torch.Generator(device='cuda').manual_seed(1)
+    chunk = engine._HostStager.CHUNK
+    for dtype, n in ((torch.uint8, 3 * chunk + 17), (torch.int32, chunk // 4 * 9 + 3), (torch.float64, chunk // 8 * 11 + 1),
+                     (torch.uint16, chunk + 5), (torch.int32, 1000), (torch.float64, engine._HostStager.MIN_BYTES // 8)):
+        if dtype.is_floating_point:
+            t = torch.rand(n, generator=g, device='cuda', dtype=dtype)
+        else:
+            t = torch.randint(0, 200, (n,), generator=g, device='cuda', dtype=torch.int32).to(dtype)
+        for rep in range(2):                                       # ring slots are reused across calls
+            h = engine.to_host(t)
+            ref = t.cpu().numpy()
+            assert h.dtype == ref.dtype and h.shape == ref.shape and np.array_equal(h, ref)
+    # a strided view and a 2-d result
+    t2 = torch.arange(6 * (chunk // 8), device='cuda', dtype=torch.float64).reshape(6, -1)
+    assert np.array_equal(engine.to_host(t2), t2.cpu().numpy())
+    assert np.array_equal(engine.to_host(t2[:, ::2]), t2[:, ::2].cpu().numpy())
+    assert engine.to_host(torch.zeros(0, device='cuda')).shape == (0,)
