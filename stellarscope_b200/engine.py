@@ -126,10 +126,48 @@ class _HostStager:
             return out
 
 
+    def push(self, a, device):
+        """Host array -> new device tensor through the ring (the mirror image of ``fetch``): worker threads copy
+        chunks into the pinned slots while earlier slots are on their way.  For uploads too large to pin as a
+        whole -- pinning a multi-GB matrix costs more than the transfer and the pinned block would stay cached."""
+        a = np.ascontiguousarray(a)
+        n = a.nbytes
+        with self.lock, torch.cuda.device(device):
+            self._ensure()
+            t = torch.empty(tuple(a.shape), dtype=_NP_TORCH[a.dtype.type], device=device)
+            dst = t.reshape(-1).view(torch.uint8)
+            src = a.reshape(-1).view(np.uint8)
+            stream = torch.cuda.current_stream(device)
+            C_ = self.CHUNK
+            offs = list(range(0, n, C_))
+
+            def fill(slot, off, m, ev):
+                if ev is not None:
+                    ev.synchronize()                             # the slot's previous chunk has left
+                self.ring_np[slot * C_:slot * C_ + m] = src[off:off + m]
+
+            fills = [None] * self.SLOTS
+            for i in range(min(self.SLOTS, len(offs))):
+                fills[i] = self.pool.submit(fill, i, offs[i], min(C_, n - offs[i]), None)
+            for i, off in enumerate(offs):
+                slot = i % self.SLOTS
+                m = min(C_, n - off)
+                fills[slot].result()
+                dst[off:off + m].copy_(self.ring[slot * C_:slot * C_ + m], non_blocking=True)
+                self.events[slot].record(stream)
+                j = i + self.SLOTS
+                if j < len(offs):
+                    fills[slot] = self.pool.submit(fill, slot, offs[j], min(C_, n - offs[j]), self.events[slot])
+            stream.synchronize()                                 # the ring is free for the next call
+            return t
+
+
 _TORCH_NP = {torch.uint8: np.uint8, torch.int8: np.int8, torch.int16: np.int16, torch.uint16: np.uint16,
              torch.int32: np.int32, torch.int64: np.int64, torch.float32: np.float32, torch.float64: np.float64,
              torch.bool: np.bool_}
+_NP_TORCH = {v: k for k, v in _TORCH_NP.items()}
 _stager = _HostStager()
+PINNED_UPLOAD_LIMIT = 256 << 20      # larger uploads go through the staging ring instead of a pinned copy
 
 
 def to_host(t):
@@ -213,6 +251,8 @@ class Engine:
 
     def _to_dev(self, arr, dtype, pinned=True):
         a = _np(arr, dtype)
+        if a.nbytes > PINNED_UPLOAD_LIMIT and a.dtype.type in _NP_TORCH:
+            return _stager.push(a, self.device)
         t = torch.from_numpy(a)
         if pinned and a.nbytes:
             t = t.pin_memory()

@@ -24,3 +24,22 @@ def test_to_host_equals_plain_copy_for_all_result_dtypes_and_sizes():
     assert np.array_equal(engine.to_host(t2), t2.cpu().numpy())
     assert np.array_equal(engine.to_host(t2[:, ::2]), t2[:, ::2].cpu().numpy())
     assert engine.to_host(torch.zeros(0, device='cuda')).shape == (0,)
+
+
+@pytest.mark.gpu
+def test_push_through_the_ring_is_a_plain_upload(monkeypatch):
+    import torch
+    from stellarscope_b200 import engine
+    rng = np.random.default_rng(2)
+    chunk = engine._HostStager.CHUNK
+    for dtype, n in ((np.int32, chunk // 4 * 10 + 7), (np.uint16, chunk // 2 * 3 + 1), (np.float64, chunk // 8 + 3), (np.uint8, 5)):
+        a = rng.integers(0, 60000, n).astype(dtype)
+        for rep in range(2):
+            t = engine._stager.push(a, torch.device('cuda', 0))
+            assert t.dtype == torch.from_numpy(a[:1]).dtype and np.array_equal(t.cpu().numpy(), a)
+    # Engine._to_dev takes this route above the limit
+    monkeypatch.setattr(engine, 'PINNED_UPLOAD_LIMIT', 1 << 20)
+    eng = engine.Engine(0)
+    a = rng.integers(0, 1000, 3_000_000).astype(np.int32)
+    assert np.array_equal(eng._to_dev(a, np.int32).cpu().numpy(), a)
+    eng.close()
