@@ -157,6 +157,16 @@ int ss_reassign(ss_handle_t h, void* stream, int32_t mode, double conf_thresh, d
                 int32_t n_rows, const int32_t* row_ptr, const uint16_t* score, const double* z,
                 uint8_t* flag, int32_t* nbest, int64_t* info);
 
+/* The reassignment matrix itself as CSR (the first return value of TelescopeLikelihood.reassign,
+ * model.py:375-507; stored in Stellarscope.reassignments[mode] :1254): compaction of the flagged alignments.
+ *   flag[nnz], nbest[n_rows]: outputs of ss_reassign (nbest may be NULL)
+ *   out_ptr[n_rows + 1] (int64), out_idx[cap]: row pointers / column of every selected alignment, row order kept
+ *   out_val[cap] or NULL: 1 / nbest of the row (the fractions of best_average, model.py:448)
+ * *n_out = number of selected alignments (host value; SS_ERR_CAPACITY if it exceeds cap).  Synchronises. */
+int ss_reassign_csr(ss_handle_t h, void* stream, int32_t n_rows, const int32_t* row_ptr, const int32_t* col_idx,
+                    const uint8_t* flag, const int32_t* nbest, int64_t cap, int64_t* out_ptr, int32_t* out_idx,
+                    double* out_val, int64_t* n_out);
+
 /* Count aggregation (Stellarscope.output_report agg_bc / agg_bc_umi,
  * model.py:1302-1345; groupby_sum sparse_plus.py:367-396).
  *   flag/weight: the reassignment matrix in CSR order (weight NULL = 1 per flagged alignment)

@@ -301,6 +301,22 @@ int ss_count(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, const 
   return rc;
 }
 
+int ss_reassign_csr(ss_handle_t h, void* stream, int32_t n_rows, const int32_t* row_ptr, const int32_t* col_idx,
+                    const uint8_t* flag, const int32_t* nbest, int64_t cap, int64_t* out_ptr, int32_t* out_idx,
+                    double* out_val, int64_t* n_out) {
+  SS_REQUIRE_HANDLE(h);
+  if (!n_out) {
+    h->set_error("ss_reassign_csr: bad argument");
+    return SS_ERR_ARG;
+  }
+  cudaSetDevice(h->device);
+  long long n = 0;
+  const int rc = reassign_csr(h, (cudaStream_t)stream, n_rows, row_ptr, col_idx, flag, nbest, cap,
+                              reinterpret_cast<long long*>(out_ptr), out_idx, out_val, &n);
+  *n_out = n;
+  return rc;
+}
+
 int ss_umi_dedup(ss_handle_t h, void* stream, int32_t n_rows, const int32_t* row_ptr, const int32_t* col_idx,
                  const uint16_t* score, const int32_t* row_group, int32_t n_groups, uint8_t* excluded, int32_t* comp_root,
                  int32_t* group_size, int32_t* group_ncomp) {

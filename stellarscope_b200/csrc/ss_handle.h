@@ -147,6 +147,8 @@ int em_emit_z(ss_handle_s* h, cudaStream_t st, double* z);
 void free_fit(ss_handle_s* h);
 cudaError_t ensure_aux_streams(ss_handle_s* h);   // internal streams + fork / join events of the handle
 // ss_umi.cu
+int reassign_csr(ss_handle_s* h, cudaStream_t st, int n_rows, const int* row_ptr, const int* col_idx, const uint8_t* flag,
+                 const int* nbest, long long cap, long long* out_ptr, int* out_idx, double* out_val, long long* n_out);
 int umi_dedup(ss_handle_s* h, cudaStream_t st, int n_rows, const int* row_ptr, const int* col_idx, const uint16_t* score,
               const int* row_group, int n_groups, uint8_t* excluded, int* comp_root, int* group_size, int* group_ncomp);
 int scores_build(ss_handle_s* h, cudaStream_t st, long long n, const int* read, const int* feat, const int* alnscore,

@@ -363,7 +363,99 @@ done:
   return result;
 }
 
+/* row_labels(read_index, label_of_read, position_of_label, out, ids_or_None)
+ * out[read_index[q]] = position_of_label.get(label_of_read[q], -1) for every read q -- the row -> output column
+ * map of output_report (model.py:1389-1394: rows in read_index order, barcodes looked up per read name).
+ * With `ids` (a dict, filled here) the labels are numbered in the order of the rows instead (label -> running id;
+ * position_of_label is ignored): the UMI ids of agg_bc_umi.  KeyError like the reference when a read has no label. */
+static PyObject* row_labels(PyObject* self, PyObject* args) {
+  PyObject *read_index, *label_of, *pos_of, *out_obj, *ids;
+  if (!PyArg_ParseTuple(args, "O!O!OOO", &PyDict_Type, &read_index, &PyDict_Type, &label_of, &pos_of, &out_obj, &ids))
+    return NULL;
+  if (ids != Py_None && !PyDict_Check(ids)) {
+    PyErr_SetString(PyExc_TypeError, "ids must be a dict or None");
+    return NULL;
+  }
+  if (ids == Py_None && !PyDict_Check(pos_of)) {
+    PyErr_SetString(PyExc_TypeError, "position_of_label must be a dict");
+    return NULL;
+  }
+  Py_buffer ob;
+  if (PyObject_GetBuffer(out_obj, &ob, PyBUF_C_CONTIGUOUS | PyBUF_WRITABLE) < 0) return NULL;
+  PyObject* result = NULL;
+  if (ob.itemsize != 4) {
+    PyErr_SetString(PyExc_TypeError, "out must be an int32 buffer");
+    goto done;
+  }
+  {
+    int32_t* out = (int32_t*)ob.buf;
+    const Py_ssize_t n = ob.len / 4;
+    const Py_ssize_t n_reads = PyDict_GET_SIZE(read_index);
+    /* by row: the running ids of the UMI variant follow the row order, not the dict order */
+    PyObject** by_row = NULL;
+    if (ids != Py_None) {
+      by_row = (PyObject**)calloc((size_t)(n > 0 ? n : 1), sizeof(PyObject*));
+      if (!by_row) { PyErr_NoMemory(); goto done; }
+    }
+    Py_ssize_t pos = 0;
+    PyObject *qname, *rowobj;
+    int ok = 1;
+    while (PyDict_Next(read_index, &pos, &qname, &rowobj)) {
+      const Py_ssize_t row = PyLong_AsSsize_t(rowobj);
+      if (row == -1 && PyErr_Occurred()) { ok = 0; break; }
+      if (row < 0 || row >= n) {
+        PyErr_Format(PyExc_IndexError, "row id %zd outside [0, %zd)", row, n);
+        ok = 0;
+        break;
+      }
+      PyObject* lab = PyDict_GetItemWithError(label_of, qname);
+      if (!lab) {
+        if (!PyErr_Occurred()) PyErr_SetObject(PyExc_KeyError, qname);
+        ok = 0;
+        break;
+      }
+      if (by_row) {
+        by_row[row] = lab;                       /* borrowed; label_of keeps it alive */
+      } else {
+        PyObject* p = PyDict_GetItemWithError(pos_of, lab);
+        if (!p && PyErr_Occurred()) { ok = 0; break; }
+        long v = -1;
+        if (p) {
+          v = PyLong_AsLong(p);
+          if (v == -1 && PyErr_Occurred()) { ok = 0; break; }
+        }
+        out[row] = (int32_t)v;
+      }
+    }
+    if (ok && by_row) {
+      for (Py_ssize_t r = 0; r < n && ok; ++r) {
+        PyObject* lab = by_row[r];
+        if (!lab) { out[r] = -1; continue; }
+        PyObject* idobj = PyDict_GetItemWithError(ids, lab);
+        Py_ssize_t id;
+        if (idobj) {
+          id = PyLong_AsSsize_t(idobj);
+        } else {
+          if (PyErr_Occurred()) { ok = 0; break; }
+          id = PyDict_GET_SIZE(ids);
+          PyObject* v = PyLong_FromSsize_t(id);
+          if (!v || PyDict_SetItem(ids, lab, v) < 0) { Py_XDECREF(v); ok = 0; break; }
+          Py_DECREF(v);
+        }
+        out[r] = (int32_t)id;
+      }
+    }
+    free(by_row);
+    if (ok) result = PyLong_FromSsize_t(n_reads);
+  }
+done:
+  PyBuffer_Release(&ob);
+  return result;
+}
+
 static PyMethodDef methods[] = {
+    {"row_labels", row_labels, METH_VARARGS,
+     "row_labels(read_index, label_of_read, position_of_label, out, ids): out[row] = position (or running id) of the read's label"},
     {"code_mappings", code_mappings, METH_VARARGS,
      "code_mappings(mappings, read_index, feat_index, read, feat, alnscore, alnlen): integer-code the loader's mapping tuples"},
     {"pair_ids", pair_ids, METH_VARARGS,

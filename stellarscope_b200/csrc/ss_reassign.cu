@@ -319,4 +319,64 @@ int count(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, const int* ro
   return SS_OK;
 }
 
+// ---------------------------------------------------------------------------
+// the reassignment matrix as CSR: compaction of the flagged alignments
+// ---------------------------------------------------------------------------
+__global__ void select_count_kernel(int n_rows, const int* __restrict__ row_ptr, const uint8_t* __restrict__ flag,
+                                    long long* __restrict__ per_row) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row > n_rows) return;
+  int c = 0;
+  if (row < n_rows)
+    for (int k = row_ptr[row]; k < row_ptr[row + 1]; ++k) c += flag[k] != 0;
+  per_row[row] = c;                                  // per_row[n_rows] = 0: the scan's last element is the total
+}
+
+__global__ void select_fill_kernel(int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                                   const uint8_t* __restrict__ flag, const int* __restrict__ nbest,
+                                   const long long* __restrict__ out_ptr, int* __restrict__ out_idx,
+                                   double* __restrict__ out_val) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  long long o = out_ptr[row];
+  const double v = (out_val && nbest && nbest[row] > 0) ? 1.0 / (double)nbest[row] : 1.0;   // best / nbest, model.py:448
+  for (int k = row_ptr[row]; k < row_ptr[row + 1]; ++k) {
+    if (!flag[k]) continue;
+    out_idx[o] = col_idx[k];
+    if (out_val) out_val[o] = v;
+    ++o;
+  }
+}
+
+int reassign_csr(ss_handle_s* h, cudaStream_t st, int n_rows, const int* row_ptr, const int* col_idx, const uint8_t* flag,
+                 const int* nbest, long long cap, long long* out_ptr, int* out_idx, double* out_val, long long* n_out) {
+  *n_out = 0;
+  if (n_rows < 0 || !row_ptr || !col_idx || !flag || !out_ptr || (cap > 0 && !out_idx)) {
+    h->set_error("ss_reassign_csr: bad argument");
+    return SS_ERR_ARG;
+  }
+  TmpPool tmp;
+  const int B = 256;
+  long long* per_row;
+  SS_CUDA_CHECK(h, tmp.get(&per_row, (size_t)n_rows + 1));
+  select_count_kernel<<<(n_rows + 1 + B - 1) / B, B, 0, st>>>(n_rows, row_ptr, flag, per_row);
+  h->launches++;
+  CUB_CALL(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, per_row, out_ptr, n_rows + 1, st));
+  long long total = 0;
+  SS_CUDA_CHECK(h, cudaMemcpyAsync(&total, out_ptr + n_rows, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  SS_CUDA_CHECK(h, cudaStreamSynchronize(st));
+  *n_out = total;
+  if (total > cap) {
+    h->set_error("ss_reassign_csr: output capacity too small");
+    return SS_ERR_CAPACITY;
+  }
+  if (total > 0 && n_rows > 0) {
+    select_fill_kernel<<<(n_rows + B - 1) / B, B, 0, st>>>(n_rows, row_ptr, col_idx, flag, nbest, out_ptr, out_idx, out_val);
+    h->launches++;
+    SS_CUDA_CHECK(h, cudaGetLastError());
+  }
+  SS_CUDA_CHECK(h, cudaStreamSynchronize(st));      // temporaries are freed on return
+  return SS_OK;
+}
+
 }  // namespace ss

@@ -595,6 +595,22 @@ class Engine:
             self._check(rc)
             return flag[:self.A], nbest[:self.N], info.cpu().numpy()
 
+    def reassign_csr(self, flag, nbest=None, fractions=False):
+        """ss_reassign_csr: the flagged alignments as CSR.  Returns numpy (indptr int64[N+1], indices int32[n],
+        values float64[n] or None); ``fractions``: 1 / nbest per selected alignment (best_average)."""
+        dev, k = self.device, self._keep
+        with torch.cuda.device(dev):
+            out_ptr = torch.empty(self.N + 1, dtype=torch.int64, device=dev)
+            out_idx = torch.empty(max(self.A, 1), dtype=torch.int32, device=dev)
+            out_val = torch.empty(max(self.A, 1), dtype=torch.float64, device=dev) if fractions else None
+            n = C.c_int64(0)
+            rc = self.lib.ss_reassign_csr(self.h, self._stream(), self.N, self._p(k['row_ptr']), self._p(k['col_idx']),
+                                          self._p(flag), self._p(nbest if fractions else None), max(self.A, 1),
+                                          self._p(out_ptr), self._p(out_idx), self._p(out_val), C.byref(n))
+            self._check(rc)
+            m = n.value
+            return to_host(out_ptr), to_host(out_idx[:m]), (to_host(out_val[:m]) if fractions else None)
+
     def count(self, flag, row_cell, weight=None, row_umi=None, cap=None):
         """ss_count.  Returns COO (cell, col, val) numpy arrays sorted by (cell, col)."""
         dev = self.device

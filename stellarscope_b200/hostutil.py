@@ -42,3 +42,8 @@ def pair_ids(read_index, bcode_map, umi_map, row_group):
 def code_mappings(mappings, read_index, feat_index, read, feat, alnscore, alnlen):
     """Integer-code the loader's (code, query_name, feat_name, alnscore, alnlen) tuples into int32 arrays."""
     return load().code_mappings(mappings, read_index, feat_index, read, feat, alnscore, alnlen)
+
+
+def row_labels(read_index, label_of_read, position_of_label, out, ids=None):
+    """out[read_index[q]] = position_of_label.get(label_of_read[q], -1); with ``ids`` (a dict) running ids in row order."""
+    return load().row_labels(read_index, label_of_read, position_of_label, out, ids)

@@ -248,23 +248,28 @@ class TelescopeLikelihood(object):
                 raise StellarscopeError('reassign_mat was not set.')     # model.py:504-505 (no z)
             z = self._z_device()
         flag, nbest, info = self._engine.reassign(mode, z, thresh if thresh is not None else 0.0, self.tie_tol)
-        flag = to_host(flag).view(np.bool_)                     # 0 / 1 bytes
         rinfo = ReassignInfo(mode)
         rinfo.assigned, rinfo.ambiguous, rinfo.unaligned = int(info[0]), int(info[1]), int(info[2])
         if mode in ('best_exclude', 'best_random', 'best_average', 'initial_random'):
             rinfo.ambigous_dist = counter_from_hist(info[4:])
+        if mode not in ('best_random', 'initial_random'):
+            # the selection comes back as CSR straight from the device (no pass over all alignments on the host)
+            ptr, idx, frac = self._engine.reassign_csr(flag, nbest, fractions=(mode == 'best_average'))
+            data = frac if mode == 'best_average' else np.ones(len(idx), dtype=np.int8)
+            mat = csr_matrix_plus((data, idx, ptr.astype(self.raw_scores.indptr.dtype, copy=False)),
+                                  shape=self.raw_scores.shape)
+            if mode != 'best_average':
+                # lets count_by_cell aggregate without uploading the matrix again (while the engine still holds this matrix)
+                mat._ss_dev = (self._engine, flag, self._engine._keep.get('row_ptr'))
+            return mat, rinfo
+        flag = to_host(flag).view(np.bool_)                     # 0 / 1 bytes
         indptr, indices = self.raw_scores.indptr, self.raw_scores.indices
         row = np.repeat(np.arange(self.N, dtype=np.int64), np.diff(indptr))
-        if mode in ('best_random', 'initial_random'):
-            flag = _replay_random_choice(flag, row, to_host(nbest), self.opts.rng)
+        flag = _replay_random_choice(flag, row, to_host(nbest), self.opts.rng)
         keep_rows = row[flag]
         ptr = np.zeros(self.N + 1, dtype=indptr.dtype)
         np.cumsum(np.bincount(keep_rows, minlength=self.N), out=ptr[1:])
-        if mode == 'best_average':
-            nb = to_host(nbest)
-            data = 1.0 / nb[keep_rows].astype(np.float64)
-        else:
-            data = np.ones(len(keep_rows), dtype=np.int8)
+        data = np.ones(len(keep_rows), dtype=np.int8)
         mat = csr_matrix_plus((data, indices[flag], ptr), shape=self.raw_scores.shape)
         return mat, rinfo
 
@@ -494,9 +499,49 @@ def reassign(st, tl: TelescopeLikelihood):
     return rmode_info
 
 
+def _row_outputs(st, bc_pos):
+    """Output column (barcode position, -1: dropped) and -- with ``--umi_counts`` -- UMI id of every row, from the
+    reference's per-read dicts (model.py:1389-1394: rows in ``read_index`` order).  The dicts are walked by the C
+    helper; other mapping types take the Python route."""
+    N = len(st.read_index)
+    want_umi = bool(st.opts.umi_counts)
+    if type(st.read_index) is dict and type(st.read_bcode_map) is dict and (not want_umi or type(st.read_umi_map) is dict):
+        from . import hostutil
+        row_cell = None
+        groups = getattr(st, 'bcode_ridx_map', None)
+        if type(groups) is dict and groups:
+            # barcode -> row set is filled together with read -> barcode (store_read_info, model.py:1044-1053): walking
+            # the ~10^4 sets is 100 x cheaper than one dict look-up per read; used when the sets cover every row once
+            cand = np.full(N, -2, dtype=np.int32)
+            ids = np.fromiter((bc_pos.get(b, -1) for b in groups), dtype=np.int32, count=len(groups))
+            try:
+                hostutil.fill_row_segments(list(groups.values()), ids, cand)
+                if not (cand == -2).any():
+                    row_cell = cand
+            except (ValueError, IndexError):
+                row_cell = None
+        if row_cell is None:
+            row_cell = np.full(N, -1, dtype=np.int32)
+            hostutil.row_labels(st.read_index, st.read_bcode_map, bc_pos, row_cell)
+        row_umi = None
+        if want_umi:
+            row_umi = np.full(N, -1, dtype=np.int32)
+            hostutil.row_labels(st.read_index, st.read_umi_map, None, row_umi, {})
+        return row_cell, row_umi
+    qnames = sorted(st.read_index, key=st.read_index.get)           # model.py:1389
+    row_cell = np.fromiter((bc_pos.get(st.read_bcode_map[q], -1) for q in qnames), dtype=np.int32,
+                           count=len(qnames))
+    row_umi = None
+    if want_umi:
+        umi_ids = {}
+        row_umi = np.fromiter((umi_ids.setdefault(st.read_umi_map[q], len(umi_ids)) for q in qnames),
+                              dtype=np.int32, count=len(qnames))
+    return row_cell, row_umi
+
+
 def count_matrices(st, tl: TelescopeLikelihood):
     """The aggregation half of ``output_report`` (agg_bc / agg_bc_umi,
-    model.py:1302-1345): ``{mode: (numft x numbc) scipy CSR}`` plus the barcode
+    model.py:1302-1345): ``{mode: (numft x numbc) scipy sparse matrix}`` plus the barcode
     and feature lists in output order (:1371-1378)."""
     if getattr(st, 'filtlist', None):
         bc_list = sorted(st.filtlist, key=st.filtlist.get)
@@ -505,14 +550,7 @@ def count_matrices(st, tl: TelescopeLikelihood):
     ft_list = sorted(st.feat_index, key=st.feat_index.get)
     numft, numbc = len(ft_list), len(bc_list)
     bc_pos = {b: i for i, b in enumerate(bc_list)}
-    qnames = sorted(st.read_index, key=st.read_index.get)           # model.py:1389
-    row_cell = np.fromiter((bc_pos.get(st.read_bcode_map[q], -1) for q in qnames), dtype=np.int32,
-                           count=len(qnames))
-    row_umi = None
-    if st.opts.umi_counts:
-        umi_ids = {}
-        row_umi = np.fromiter((umi_ids.setdefault(st.read_umi_map[q], len(umi_ids)) for q in qnames),
-                              dtype=np.int32, count=len(qnames))
+    row_cell, row_umi = _row_outputs(st, bc_pos)
     out = OrderedDict()
     world, rank = _dist_info()
     if not getattr(st.opts, 'shard_models', True):

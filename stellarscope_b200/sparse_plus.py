@@ -4,8 +4,10 @@ Mirror of the part of the reference's ``stellarscope/utils/sparse_plus.py``
 class that the hot path's callers use on reassignment matrices
 (``groupby_sum`` :367-396 via ``output_report`` model.py:1311, 1336;
 ``check_equal`` :242-245; ``save``/``load`` :398-405).  The aggregation runs on
-the device (``ss_count``); instances hold no device state, so they pickle like
-plain scipy matrices (``Stellarscope.save``, model.py:1259-1274).
+the device (``ss_count``).  A matrix that ``TelescopeLikelihood.reassign`` just produced remembers the device
+flags it was compacted from (``_ss_dev``), so that the aggregation that follows does not upload it again; the
+attribute is dropped on pickling and is not inherited by derived matrices, so instances still pickle like plain
+scipy matrices (``Stellarscope.save``, model.py:1259-1274).
 """
 from __future__ import annotations
 
@@ -29,7 +31,19 @@ def _default_engine():
     return _engine_cache['e']
 
 
+def _rebuild(cls, data, indices, indptr, shape):
+    return cls((data, indices, indptr), shape=shape)
+
+
 class csr_matrix_plus(scipy.sparse.csr_matrix):
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop('_ss_dev', None)               # (engine, device flags): never pickled
+        return state
+
+    def __reduce_ex__(self, protocol):
+        return (_rebuild, (type(self), self.data, self.indices, self.indptr, self.shape))
 
     def check_equal(self, other):
         if self.shape != other.shape:
@@ -47,7 +61,11 @@ class csr_matrix_plus(scipy.sparse.csr_matrix):
     # -- device aggregation ----------------------------------------------------
     def _device_coo(self, row_group, row_umi, engine):
         """COO (group, col, value) of sum over rows of each group, on the device."""
-        import torch
+        dev = getattr(self, '_ss_dev', None)
+        if (dev is not None and engine is not None and dev[0] is engine and getattr(engine, 'h', None)
+                and engine._keep.get('row_ptr') is dev[2] and dev[1].numel() == engine.A):
+            # produced by this engine's ss_reassign a moment ago: its flags are still on the device
+            return engine.count(dev[1], row_group, row_umi=row_umi)
         eng = _default_engine()          # a separate handle: the model's engine keeps its score matrix
         m = self
         if not m.has_sorted_indices:
@@ -70,8 +88,11 @@ class csr_matrix_plus(scipy.sparse.csr_matrix):
                                           engine)
         integer = np.issubdtype(self.dtype, np.integer) and row_umi is None
         dtype = np.int32 if integer else np.float64
-        out = scipy.sparse.csr_matrix((val.astype(dtype), (col, cell)), shape=(self.shape[1], n_cells))
-        return out
+        # the device returns the triples sorted by (cell, locus) without duplicates: that is the CSC form of the
+        # (K x n_cells) matrix -- no host sort
+        indptr = np.zeros(n_cells + 1, dtype=np.int64)
+        np.cumsum(np.bincount(cell, minlength=n_cells), out=indptr[1:])
+        return scipy.sparse.csc_matrix((val.astype(dtype), col, indptr), shape=(self.shape[1], n_cells))
 
     def groupby_sum(self, by, group_index: bool = True, dtype=np.float64, proc: int = 1):
         """Reference signature (sparse_plus.py:367-396): ``by`` maps row index ->
@@ -84,7 +105,9 @@ class csr_matrix_plus(scipy.sparse.csr_matrix):
         for k, v in by.items():
             row_group[k] = labels.setdefault(v, len(labels))
         cell, col, val = self._device_coo(row_group, None, None)
-        mat = scipy.sparse.csr_matrix((val.astype(dtype), (cell, col)), shape=(len(labels), self.shape[1]))
+        indptr = np.zeros(len(labels) + 1, dtype=np.int64)                  # sorted by (group, column): already CSR
+        np.cumsum(np.bincount(cell, minlength=len(labels)), out=indptr[1:])
+        mat = scipy.sparse.csr_matrix((val.astype(dtype), col, indptr), shape=(len(labels), self.shape[1]))
         if group_index:
             return type(self)(mat), list(labels.keys())
         return type(self)(mat)

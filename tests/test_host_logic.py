@@ -182,3 +182,34 @@ def test_segment_fit_infos_lazy_records():
     p.models_info = infos
     assert float(p.total_lnl) == 3.75 and p.total_obs == 30 and p.total_params == 20 and p.fitted_models == 2
     assert abs(float(p.AIC) - (2 * 20 - 2 * 3.75)) < 1e-12
+
+
+def test_row_outputs_c_walk_equals_the_python_route():
+    """Row -> output column / UMI id maps of output_report (model.py:1389-1394): the C walk of the reference's dicts
+    gives what the generator expressions over ``sorted(read_index)`` give."""
+    import types
+    from collections import OrderedDict
+    from stellarscope_b200 import model
+    rng = np.random.default_rng(8)
+    N = 5000
+    order = rng.permutation(N)                                   # dict order != row order
+    read_index = {f'q{r:05d}': int(r) for r in order}
+    bcs = [f'BC{c:03d}' for c in range(40)]
+    read_bcode_map = {q: bcs[int(rng.integers(0, 40))] for q in read_index}
+    read_umi_map = {q: f'U{int(rng.integers(0, 300)):04d}' for q in read_index}
+    bc_pos = {b: i for i, b in enumerate(sorted(bcs[:35]))}      # 5 barcodes are filtered out -> -1
+    for umi_counts in (False, True):
+        st = types.SimpleNamespace(read_index=read_index, read_bcode_map=read_bcode_map, read_umi_map=read_umi_map,
+                                   opts=types.SimpleNamespace(umi_counts=umi_counts))
+        fast = model._row_outputs(st, bc_pos)
+        st2 = types.SimpleNamespace(read_index=OrderedDict(read_index), read_bcode_map=read_bcode_map, read_umi_map=read_umi_map,
+                                    opts=st.opts)                # not a plain dict -> Python route
+        slow = model._row_outputs(st2, bc_pos)
+        assert np.array_equal(fast[0], slow[0]) and (fast[0] == -1).sum() > 0
+        if umi_counts:
+            assert np.array_equal(fast[1], slow[1])
+        else:
+            assert fast[1] is None and slow[1] is None
+    bad = types.SimpleNamespace(read_index={'nobody': 0}, read_bcode_map={}, read_umi_map={}, opts=types.SimpleNamespace(umi_counts=False))
+    with pytest.raises(KeyError):
+        model._row_outputs(bad, bc_pos)
