@@ -43,3 +43,33 @@ def test_push_through_the_ring_is_a_plain_upload(monkeypatch):
     a = rng.integers(0, 1000, 3_000_000).astype(np.int32)
     assert np.array_equal(eng._to_dev(a, np.int32).cpu().numpy(), a)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_reassign_csr_is_the_compaction_of_the_flags():
+    """ss_reassign_csr against numpy: row pointers, kept columns in row order, 1/nbest fractions; no selection at all."""
+    import torch
+    from stellarscope_b200.engine import Engine
+    rng = np.random.default_rng(6)
+    N, K = 20_000, 300
+    lens = rng.integers(0, 7, N)                                  # empty rows included
+    indptr = np.zeros(N + 1, dtype=np.int32)
+    np.cumsum(lens, out=indptr[1:])
+    A = int(indptr[-1])
+    indices = np.concatenate([np.sort(rng.choice(K, size=l, replace=False)) for l in lens if l]).astype(np.int32)
+    eng = Engine(0)
+    eng.set_matrix(indptr, indices, rng.integers(1, 200, A).astype(np.uint16), K)
+    flag = (rng.random(A) < 0.4).astype(np.uint8)
+    nbest = rng.integers(0, 5, N).astype(np.int32)
+    row = np.repeat(np.arange(N), lens)
+    for fl in (flag, np.zeros(A, dtype=np.uint8), np.ones(A, dtype=np.uint8)):
+        ptr, idx, val = eng.reassign_csr(torch.from_numpy(fl).cuda(), torch.from_numpy(nbest).cuda(), fractions=True)
+        keep = fl.astype(bool)
+        exp_ptr = np.zeros(N + 1, dtype=np.int64)
+        np.cumsum(np.bincount(row[keep], minlength=N), out=exp_ptr[1:])
+        assert np.array_equal(ptr, exp_ptr) and np.array_equal(idx, indices[keep])
+        nb = nbest[row[keep]]
+        assert np.array_equal(val, np.where(nb > 0, 1.0 / np.maximum(nb, 1), 1.0))
+        ptr2, idx2, val2 = eng.reassign_csr(torch.from_numpy(fl).cuda())
+        assert val2 is None and np.array_equal(ptr2, exp_ptr) and np.array_equal(idx2, indices[keep])
+    eng.close()
