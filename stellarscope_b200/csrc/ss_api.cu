@@ -294,6 +294,7 @@ int ss_count(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, const 
              int64_t* n_out) {
   SS_REQUIRE_HANDLE(h);
   cudaSetDevice(h->device);
+  tl_alloc_stream = (cudaStream_t)stream;          // temporaries are allocated and freed in this stream's order
   long long n = 0;
   int rc = count(h, (cudaStream_t)stream, n_rows, n_cols, row_ptr, col_idx, flag, weight, row_cell, row_umi, cap,
                  out_cell, out_col, out_val, &n);
@@ -310,6 +311,7 @@ int ss_reassign_csr(ss_handle_t h, void* stream, int32_t n_rows, const int32_t* 
     return SS_ERR_ARG;
   }
   cudaSetDevice(h->device);
+  tl_alloc_stream = (cudaStream_t)stream;
   long long n = 0;
   const int rc = reassign_csr(h, (cudaStream_t)stream, n_rows, row_ptr, col_idx, flag, nbest, cap,
                               reinterpret_cast<long long*>(out_ptr), out_idx, out_val, &n);

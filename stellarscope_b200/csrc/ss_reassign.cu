@@ -184,10 +184,10 @@ __global__ void unpack_kernel(long long n, const unsigned long long* __restrict_
   out_val[i] = sums ? sums[i] : (double)cnt[i];
 }
 
-struct TmpPool {
+struct TmpPool {       // temporaries of one call: allocated (dev_alloc) and released in the order of the call's stream
   std::vector<void*> p;
   ~TmpPool() {
-    for (void* q : p) cudaFree(q);
+    for (void* q : p) cudaFreeAsync(q, tl_alloc_stream);
   }
   template <class T>
   cudaError_t get(T** out, size_t n) {
