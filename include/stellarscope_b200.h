@@ -208,6 +208,24 @@ int ss_scores_build(ss_handle_t h, void* stream, int64_t n, const int32_t* read,
                     const int32_t* alnscore, const int32_t* alnlen, int32_t min_as, int32_t n_reads, int32_t n_feats,
                     int32_t* row_ptr, int32_t* col_idx, uint16_t* score, int64_t* info);
 
+/* MatrixMarket body of a count matrix: the text scipy.io.mmwrite writes for the
+ * (features x barcodes) matrices at the end of Stellarscope.output_report (model.py:1418, header and
+ * metadata comment :1347-1368 stay with the caller): one line "row+1 col+1 value\n" per entry, in the
+ * order of the arrays.
+ *   row/col[n] (int32), val[n] (double): COO triples, device arrays (the order is kept)
+ *   integer != 0: values are printed as integers ("coordinate integer", int32 count matrices);
+ *            0: as the correctly rounded 17-significant-digit decimal without trailing zeros ("coordinate
+ *            real": best_average and --umi_counts), which parses back to the same double
+ *   off[n + 1] (int64, device, caller-owned): ss_mtx_measure fills it with the byte offset of every line
+ *            (off[n] = total) and returns the total in *n_bytes (HOST; synchronises the stream);
+ *   out[*n_bytes] (device, 16-byte aligned): ss_mtx_write writes the text there (asynchronous).
+ * SS_ERR_ARG (nothing written) for a negative index, a non-integer value with integer != 0, or a real
+ * value outside 0 / 2^-64 <= |x| < 2^63 (count matrices hold integers and sums of 1/nbest). */
+int ss_mtx_measure(ss_handle_t h, void* stream, int64_t n, const int32_t* row, const int32_t* col, const double* val,
+                   int32_t integer, int64_t* off, int64_t* n_bytes);
+int ss_mtx_write(ss_handle_t h, void* stream, int64_t n, const int32_t* row, const int32_t* col, const double* val,
+                 int32_t integer, const int64_t* off, uint8_t* out);
+
 /* ---- one model, rows sharded over the GPUs of a box (pooling_mode=pseudobulk) ----
  * The reference fits the pseudobulk model single-threaded (model.py:762-767).  Here every rank
  * (one process per GPU) holds a block of rows of the SAME model; ss_layout_build / ss_em_fit are

@@ -87,6 +87,10 @@ SIGNATURES = {
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'ss_scores_build': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                  C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, c_i64p]),
+    'ss_mtx_measure': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                c_i64p]),
+    'ss_mtx_write': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                              C.c_void_p]),
     'ss_set_allreduce': (C.c_int, [C.c_void_p, ALLREDUCE_FN, C.c_void_p]),
     'ss_peer_buffer_bytes': (C.c_int64, [C.c_int32]),
     'ss_set_peers': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int64]),

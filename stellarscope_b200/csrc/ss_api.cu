@@ -72,6 +72,7 @@ int ss_destroy(ss_handle_t h) {
 int ss_release(ss_handle_t h) {
   SS_REQUIRE_HANDLE(h);
   cudaSetDevice(h->device);
+  tl_alloc_stream = nullptr;          // the stream of the last call may be gone
   free_fit(h);
   free_dense(h);
   free_layout(h);
@@ -345,6 +346,28 @@ int ss_scores_build(ss_handle_t h, void* stream, int64_t n, const int32_t* read,
                       score, reinterpret_cast<long long*>(info));
 }
 
+int ss_mtx_measure(ss_handle_t h, void* stream, int64_t n, const int32_t* row, const int32_t* col, const double* val,
+                   int32_t integer, int64_t* off, int64_t* n_bytes) {
+  SS_REQUIRE_HANDLE(h);
+  if (!n_bytes) {
+    h->set_error("ss_mtx_measure: bad argument");
+    return SS_ERR_ARG;
+  }
+  cudaSetDevice(h->device);
+  tl_alloc_stream = (cudaStream_t)stream;
+  long long nb = 0;
+  const int rc = mtx_measure(h, (cudaStream_t)stream, n, row, col, val, integer, reinterpret_cast<long long*>(off), &nb);
+  *n_bytes = nb;
+  return rc;
+}
+
+int ss_mtx_write(ss_handle_t h, void* stream, int64_t n, const int32_t* row, const int32_t* col, const double* val,
+                 int32_t integer, const int64_t* off, uint8_t* out) {
+  SS_REQUIRE_HANDLE(h);
+  cudaSetDevice(h->device);
+  return mtx_write(h, (cudaStream_t)stream, n, row, col, val, integer, reinterpret_cast<const long long*>(off), out);
+}
+
 int ss_set_allreduce(ss_handle_t h, ss_allreduce_fn fn, void* user) {
   SS_REQUIRE_HANDLE(h);
   h->allreduce = fn;
@@ -394,6 +417,7 @@ int ss_em_get_dense_params(ss_handle_t h, void* stream, double* pi, double* thet
 int64_t ss_launch_count(ss_handle_t h) { return h ? h->launches : 0; }
 
 int ss_lane_classes(int32_t* threads, int32_t cap) {
+  if (!threads) return SS_NUM_CLASSES;
   for (int i = 0; i < SS_NUM_CLASSES && i < cap; ++i) threads[i] = SS_CLS_THREADS[i];
   return SS_NUM_CLASSES;
 }

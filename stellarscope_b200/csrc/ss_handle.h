@@ -154,6 +154,11 @@ int umi_dedup(ss_handle_s* h, cudaStream_t st, int n_rows, const int* row_ptr, c
 int scores_build(ss_handle_s* h, cudaStream_t st, long long n, const int* read, const int* feat, const int* alnscore,
                  const int* alnlen, int min_as, int n_reads, int n_feats, int* row_ptr, int* col_idx, uint16_t* score,
                  long long* info_host);
+// ss_mtx.cu
+int mtx_measure(ss_handle_s* h, cudaStream_t st, long long n, const int* row, const int* col, const double* val,
+                int integer, long long* off, long long* n_bytes);
+int mtx_write(ss_handle_s* h, cudaStream_t st, long long n, const int* row, const int* col, const double* val,
+              int integer, const long long* off, unsigned char* out);
 // ss_dense.cu
 int em_fit_dense(ss_handle_s* h, cudaStream_t st, const FitParams& P);
 int dense_allreduce_smax(ss_handle_s* h, cudaStream_t st);

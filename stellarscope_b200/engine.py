@@ -126,6 +126,36 @@ class _HostStager:
             return out
 
 
+    def drain_to_file(self, t, fh):
+        """Device bytes -> open binary file, in order, through the pinned ring: up to SLOTS chunk copies are in
+        flight while the oldest one is written (no host copy of the whole text is ever made)."""
+        src = t.contiguous().reshape(-1).view(torch.uint8)
+        n = src.numel()
+        if n == 0:
+            return 0
+        with self.lock, torch.cuda.device(t.device):
+            self._ensure()
+            stream = torch.cuda.current_stream(t.device)
+            C_ = self.CHUNK
+            offs = list(range(0, n, C_))
+
+            def issue(i):
+                slot, off = i % self.SLOTS, offs[i]
+                m = min(C_, n - off)
+                self.ring[slot * C_:slot * C_ + m].copy_(src[off:off + m], non_blocking=True)
+                self.events[slot].record(stream)
+
+            for i in range(min(self.SLOTS, len(offs))):
+                issue(i)
+            for i, off in enumerate(offs):
+                slot = i % self.SLOTS
+                m = min(C_, n - off)
+                self.events[slot].synchronize()
+                fh.write(memoryview(self.ring_np[slot * C_:slot * C_ + m]))
+                if i + self.SLOTS < len(offs):
+                    issue(i + self.SLOTS)                    # the slot is free again
+        return n
+
     def push(self, a, device):
         """Host array -> new device tensor through the ring (the mirror image of ``fetch``): worker threads copy
         chunks into the pinned slots while earlier slots are on their way.  For uploads too large to pin as a
@@ -168,6 +198,11 @@ _TORCH_NP = {torch.uint8: np.uint8, torch.int8: np.int8, torch.int16: np.int16, 
 _NP_TORCH = {v: k for k, v in _TORCH_NP.items()}
 _stager = _HostStager()
 PINNED_UPLOAD_LIMIT = 256 << 20      # larger uploads go through the staging ring instead of a pinned copy
+
+
+def drain_to_file(t, fh):
+    """Write the bytes of a device tensor to an open binary file (chunked through the pinned ring)."""
+    return _stager.drain_to_file(t, fh)
 
 
 def to_host(t):
@@ -610,6 +645,36 @@ class Engine:
             self._check(rc)
             m = n.value
             return to_host(out_ptr), to_host(out_idx[:m]), (to_host(out_val[:m]) if fractions else None)
+
+    def mtx_text(self, row, col, val, integer):
+        """ss_mtx_measure + ss_mtx_write: MatrixMarket body ("row+1 col+1 value\\n" per entry, order kept) of the COO
+        triples as a uint8 device tensor.  ``row`` / ``col`` / ``val``: host arrays or device tensors."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            def dev_arr(a, np_dtype, t_dtype):
+                if isinstance(a, torch.Tensor):
+                    return a.to(device=dev, dtype=t_dtype).contiguous()
+                return self._to_dev(a, np_dtype)
+            r = dev_arr(row, np.int32, torch.int32)
+            c = dev_arr(col, np.int32, torch.int32)
+            if isinstance(val, torch.Tensor) or np.asarray(val).dtype == np.float64:
+                v = dev_arr(val, np.float64, torch.float64)
+            else:
+                v = self._to_dev(val, np.asarray(val).dtype.type).to(torch.float64)   # widen on the device
+            n = int(r.numel())
+            if int(c.numel()) != n or int(v.numel()) != n:
+                raise ValueError('row, col and val must have the same length')
+            off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+            nbytes = C.c_int64(0)
+            rc = self.lib.ss_mtx_measure(self.h, self._stream(), n, self._p(r), self._p(c), self._p(v),
+                                         1 if integer else 0, self._p(off), C.byref(nbytes))
+            self._check(rc)
+            out = torch.empty(max(int(nbytes.value), 1), dtype=torch.uint8, device=dev)
+            rc = self.lib.ss_mtx_write(self.h, self._stream(), n, self._p(r), self._p(c), self._p(v),
+                                       1 if integer else 0, self._p(off), self._p(out))
+            self._check(rc)
+            torch.cuda.current_stream(dev).synchronize()          # r / c / v / off may go
+            return out[:int(nbytes.value)]
 
     def count(self, flag, row_cell, weight=None, row_umi=None, cap=None):
         """ss_count.  Returns COO (cell, col, val) numpy arrays sorted by (cell, col)."""

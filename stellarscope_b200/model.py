@@ -579,7 +579,7 @@ def count_matrices(st, tl: TelescopeLikelihood):
 
 def output_report(st, tl: TelescopeLikelihood):
     """``Stellarscope.output_report``: barcodes.tsv, features.tsv, TE_counts[.mode].mtx."""
-    import scipy.io
+    from . import mtx
     counts, bc_list, ft_list = count_matrices(st, tl)
     with open(st.opts.outfile_path('barcodes.tsv'), 'w') as outh:
         print('\n'.join(bc_list), file=outh)
@@ -590,7 +590,7 @@ def output_report(st, tl: TelescopeLikelihood):
             out_mtx = st.opts.outfile_path('TE_counts.mtx')
         else:
             out_mtx = st.opts.outfile_path(f'TE_counts.{_rmode}.mtx')
-        scipy.io.mmwrite(out_mtx, _counts, comment=_mtx_meta(st, _rmode))
+        mtx.mmwrite(out_mtx, _counts, comment=_mtx_meta(st, _rmode), engine=tl._engine)    # model.py:1418
     return
 
 
