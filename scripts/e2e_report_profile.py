@@ -23,6 +23,30 @@ for rep in range(2):
     counts, bc, ft = model.count_matrices(st, tl)
     torch.cuda.synchronize(); t2 = time.perf_counter()
     print(f'reassign (5 modes) {1e3 * (t1 - t0):.1f} ms, count_matrices {1e3 * (t2 - t1):.1f} ms', flush=True)
+# the file output: device formatter of output_report against scipy.io.mmwrite on the same matrices
+import tempfile, scipy.io
+from stellarscope_b200 import mtx
+tmpd = tempfile.mkdtemp(prefix='ss_report_')
+opts.outfile_path = lambda suffix: os.path.join(tmpd, suffix)
+opts.version = 'bench'
+for rep in range(2):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for i, (mode, cm) in enumerate(counts.items()):
+        mtx.mmwrite(os.path.join(tmpd, f'dev_{mode}.mtx'), cm, comment=model._mtx_meta(st, mode), engine=tl._engine,
+                    device_coo=getattr(cm, '_ss_dev_coo', None))
+    t1 = time.perf_counter()
+    for i, (mode, cm) in enumerate(counts.items()):
+        scipy.io.mmwrite(os.path.join(tmpd, f'ref_{mode}.mtx'), cm, comment=model._mtx_meta(st, mode))
+    t2 = time.perf_counter()
+    nent = sum(cm.nnz for cm in counts.values())
+    print(f'MTX files of 5 modes ({nent} entries): device formatter {1e3 * (t1 - t0):.1f} ms, scipy.io.mmwrite {1e3 * (t2 - t1):.1f} ms',
+          flush=True)
+for mode, cm in counts.items():
+    a, b = (open(os.path.join(tmpd, f'{k}_{mode}.mtx'), 'rb').read() for k in ('ref', 'dev'))
+    same = a == b if np.issubdtype(cm.dtype, np.integer) else (scipy.io.mmread(os.path.join(tmpd, f'dev_{mode}.mtx')).tocsc() != cm).nnz == 0
+    print(f'  {mode}: {"identical bytes" if a == b else ("equal matrices" if same else "MISMATCH")}')
+if '--no-cprofile' in sys.argv:
+    sys.exit(0)
 pr = cProfile.Profile(); pr.enable()
 model.reassign(st, tl); counts, bc, ft = model.count_matrices(st, tl)
 pr.disable()

@@ -676,12 +676,15 @@ class Engine:
             torch.cuda.current_stream(dev).synchronize()          # r / c / v / off may go
             return out[:int(nbytes.value)]
 
-    def count(self, flag, row_cell, weight=None, row_umi=None, cap=None):
-        """ss_count.  Returns COO (cell, col, val) numpy arrays sorted by (cell, col)."""
+    def count(self, flag, row_cell, weight=None, row_umi=None, cap=None, keep_device=False):
+        """ss_count.  Returns COO (cell, col, val) numpy arrays sorted by (cell, col); with ``keep_device`` a
+        fourth element: compact device copies of the three arrays (for the MTX writer), or None when they
+        would take more than an eighth of the free device memory."""
         dev = self.device
         k = self._keep
         if self.A == 0:
-            return (np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.float64))
+            empty = (np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.float64))
+            return empty + (None,) if keep_device else empty
         with torch.cuda.device(dev):
             rc_t = row_cell if isinstance(row_cell, torch.Tensor) else self._to_dev(row_cell, np.int32)
             ru_t = None
@@ -697,4 +700,10 @@ class Engine:
                                    self._p(ru_t), cap, self._p(oc), self._p(ol), self._p(ov), C.byref(n))
             self._check(rc)
             m = n.value
-            return to_host(oc[:m]), to_host(ol[:m]), to_host(ov[:m])
+            host = (to_host(oc[:m]), to_host(ol[:m]), to_host(ov[:m]))
+            if not keep_device:
+                return host
+            kept = None
+            if 16 * m <= torch.cuda.mem_get_info(dev)[0] // 8:
+                kept = (oc[:m].clone(), ol[:m].clone(), ov[:m].clone())      # the cap-sized buffers go
+            return host + (kept,)

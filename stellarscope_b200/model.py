@@ -559,6 +559,7 @@ def count_matrices(st, tl: TelescopeLikelihood):
         remat = st.reassignments[_rmode]
         cm = remat.count_by_cell(row_cell, numbc, row_umi=row_umi, engine=tl._engine)
         if world > 1:
+            cm.__dict__.pop('_ss_dev_coo', None)        # device triples of this rank's part only: not to be pickled
             # every rank holds the counts of its own models' rows (disjoint): add them up.  The modes
             # that do not use z (initial_*, total_hits) are identical on every rank.
             import torch.distributed as dist
@@ -590,7 +591,8 @@ def output_report(st, tl: TelescopeLikelihood):
             out_mtx = st.opts.outfile_path('TE_counts.mtx')
         else:
             out_mtx = st.opts.outfile_path(f'TE_counts.{_rmode}.mtx')
-        mtx.mmwrite(out_mtx, _counts, comment=_mtx_meta(st, _rmode), engine=tl._engine)    # model.py:1418
+        mtx.mmwrite(out_mtx, _counts, comment=_mtx_meta(st, _rmode), engine=tl._engine,
+                    device_coo=getattr(_counts, '_ss_dev_coo', None))                      # model.py:1418
     return
 
 

@@ -39,11 +39,13 @@ def header(n_rows, n_cols, nnz, field, comment=''):
     return ('\n'.join(lines) + '\n').encode()
 
 
-def mmwrite(target, a, comment='', engine=None):
+def mmwrite(target, a, comment='', engine=None, device_coo=None):
     """``scipy.io.mmwrite(target, a, comment=comment)`` for a sparse count matrix.  ``target``: path (``.mtx``
     is appended when the name has no extension, like scipy) or an open binary file.  ``a``: scipy sparse matrix,
     integer (-> ``integer``) or floating (-> ``real``).  Entries are written in the storage order of
-    ``a.tocoo()`` -- column-major for the CSC matrices of ``output_report``."""
+    ``a.tocoo()`` -- column-major for the CSC matrices of ``output_report``.  ``device_coo``: (row, col, value)
+    device tensors holding the entries of ``a`` in that order already (what ``count_by_cell`` leaves on the
+    matrix as ``_ss_dev_coo``); without it the triples are uploaded."""
     if not scipy.sparse.issparse(a):
         raise TypeError('mmwrite: a scipy sparse matrix is expected (the count matrices of output_report)')
     if np.issubdtype(a.dtype, np.integer) or a.dtype == np.bool_:
@@ -52,18 +54,23 @@ def mmwrite(target, a, comment='', engine=None):
         integer, field = False, 'real'
     else:
         raise TypeError(f'mmwrite: unsupported dtype {a.dtype}')
-    coo = a.tocoo()
     eng = engine if engine is not None and getattr(engine, 'h', None) else _default_engine()
+    nnz = int(a.nnz)
     # the body is complete on the device before the file is touched: an unsupported value leaves no partial file
-    text = eng.mtx_text(coo.row, coo.col, coo.data, integer)
+    if device_coo is not None and all(int(t.numel()) == nnz for t in device_coo):
+        text = eng.mtx_text(device_coo[0], device_coo[1], device_coo[2], integer)
+    else:
+        coo = a.tocoo()
+        nnz = int(coo.nnz)
+        text = eng.mtx_text(coo.row, coo.col, coo.data, integer)
     from .engine import drain_to_file
     if hasattr(target, 'write'):
-        target.write(header(a.shape[0], a.shape[1], coo.nnz, field, comment))
+        target.write(header(a.shape[0], a.shape[1], nnz, field, comment))
         drain_to_file(text, target)
         return
     path = os.fspath(target)
     if not os.path.splitext(path)[1]:
         path += '.mtx'
     with open(path, 'wb', buffering=0) as fh:
-        fh.write(header(a.shape[0], a.shape[1], coo.nnz, field, comment))
+        fh.write(header(a.shape[0], a.shape[1], nnz, field, comment))
         drain_to_file(text, fh)

@@ -59,13 +59,13 @@ class csr_matrix_plus(scipy.sparse.csr_matrix):
         return cls((loader['data'], loader['indices'], loader['indptr']), shape=loader['shape'])
 
     # -- device aggregation ----------------------------------------------------
-    def _device_coo(self, row_group, row_umi, engine):
+    def _device_coo(self, row_group, row_umi, engine, keep_device=False):
         """COO (group, col, value) of sum over rows of each group, on the device."""
         dev = getattr(self, '_ss_dev', None)
         if (dev is not None and engine is not None and dev[0] is engine and getattr(engine, 'h', None)
                 and engine._keep.get('row_ptr') is dev[2] and dev[1].numel() == engine.A):
             # produced by this engine's ss_reassign a moment ago: its flags are still on the device
-            return engine.count(dev[1], row_group, row_umi=row_umi)
+            return engine.count(dev[1], row_group, row_umi=row_umi, keep_device=keep_device)
         eng = _default_engine()          # a separate handle: the model's engine keeps its score matrix
         m = self
         if not m.has_sorted_indices:
@@ -76,23 +76,28 @@ class csr_matrix_plus(scipy.sparse.csr_matrix):
         weight = None
         if not np.issubdtype(m.dtype, np.integer) or (m.nnz and (m.data != 1).any()):
             weight = eng._to_dev(m.data.astype(np.float64), np.float64)
-        return eng.count(flag, row_group, weight=weight, row_umi=row_umi)
+        return eng.count(flag, row_group, weight=weight, row_umi=row_umi, keep_device=keep_device)
 
     def count_by_cell(self, row_cell, n_cells, row_umi=None, engine=None):
         """(K x n_cells) matrix of per-cell column sums -- ``agg_bc`` /
         ``agg_bc_umi`` (model.py:1302-1345).  ``row_cell[i]`` = output column
         of row i (-1: dropped).  int32 for integer matrices, float64 otherwise
         and always float64 in UMI mode (model.py:1341)."""
-        cell, col, val = self._device_coo(np.ascontiguousarray(row_cell, dtype=np.int32),
-                                          None if row_umi is None else np.ascontiguousarray(row_umi, np.int32),
-                                          engine)
+        cell, col, val, kept = self._device_coo(np.ascontiguousarray(row_cell, dtype=np.int32),
+                                                None if row_umi is None else np.ascontiguousarray(row_umi, np.int32),
+                                                engine, keep_device=True)
         integer = np.issubdtype(self.dtype, np.integer) and row_umi is None
         dtype = np.int32 if integer else np.float64
         # the device returns the triples sorted by (cell, locus) without duplicates: that is the CSC form of the
         # (K x n_cells) matrix -- no host sort
         indptr = np.zeros(n_cells + 1, dtype=np.int64)
         np.cumsum(np.bincount(cell, minlength=n_cells), out=indptr[1:])
-        return scipy.sparse.csc_matrix((val.astype(dtype), col, indptr), shape=(self.shape[1], n_cells))
+        out = scipy.sparse.csc_matrix((val.astype(dtype), col, indptr), shape=(self.shape[1], n_cells))
+        if kept is not None:
+            # the same triples, still on the device, in the storage order of `out` (cell-major): mtx.mmwrite formats
+            # them without a second upload (MTX row = locus, MTX column = cell)
+            out._ss_dev_coo = (kept[1], kept[0], kept[2])
+        return out
 
     def groupby_sum(self, by, group_index: bool = True, dtype=np.float64, proc: int = 1):
         """Reference signature (sparse_plus.py:367-396): ``by`` maps row index ->
