@@ -48,8 +48,7 @@ __global__ void mtx_len_kernel(long long n, const int* __restrict__ row, const i
     len[i] = 0;
     return;
   }
-  char tmp[ssmtx::MAX_LINE_CHARS];
-  len[i] = ssmtx::put_line(tmp, r, c, v, integer != 0);
+  len[i] = ssmtx::line_len(r, c, v, integer != 0);
 }
 
 __global__ void __launch_bounds__(MTX_B) mtx_write_kernel(long long n, const int* __restrict__ row,

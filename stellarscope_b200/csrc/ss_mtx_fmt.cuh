@@ -26,7 +26,14 @@ constexpr int MAX_INT_CHARS = 20;      // sign + 19 digits
 constexpr int MAX_REAL_CHARS = 64;     // sign + 19 integer digits + '.' + (19 leading zeros + 17 digits), rounded up
 constexpr int MAX_LINE_CHARS = 11 + 1 + 11 + 1 + MAX_REAL_CHARS + 1;
 
+// indices and counts fit 32 bits: comparisons and 32-bit multiply-high divisions instead of 64-bit division loops
+SS_HD int ndigits_u32(uint32_t v) {
+  return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6
+       : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+}
+
 SS_HD int ndigits_u64(uint64_t v) {
+  if ((v >> 32) == 0) return ndigits_u32((uint32_t)v);
   int n = 1;
   while (v >= 10) { v /= 10; ++n; }
   return n;
@@ -35,7 +42,10 @@ SS_HD int ndigits_u64(uint64_t v) {
 // decimal digits of v at p (no terminator); returns the number of characters
 SS_HD int put_u64(char* p, uint64_t v) {
   const int n = ndigits_u64(v);
-  for (int i = n - 1; i >= 0; --i) { p[i] = (char)('0' + (int)(v % 10)); v /= 10; }
+  int i = n - 1;
+  while ((v >> 32) != 0) { p[i--] = (char)('0' + (int)(v % 10)); v /= 10; }
+  uint32_t w = (uint32_t)v;
+  for (; i >= 0; --i) { const uint32_t q = w / 10u; p[i] = (char)('0' + (int)(w - 10u * q)); w = q; }
   return n;
 }
 
@@ -100,6 +110,17 @@ SS_HD int put_real(char* p, double x) {
     for (int i = 0; i < nf; ++i) p[n++] = fd[i];
   }
   return n;
+}
+
+// length of the line put_line writes
+SS_HD int line_len(int row, int col, double v, bool integer) {
+  int n = ndigits_u64((uint64_t)((long long)row + 1)) + ndigits_u64((uint64_t)((long long)col + 1)) + 3;
+  if (integer) {
+    const long long iv = (long long)v;
+    return n + (iv < 0 ? 1 + ndigits_u64((uint64_t)(-(iv + 1)) + 1u) : ndigits_u64((uint64_t)iv));
+  }
+  char tmp[MAX_REAL_CHARS];
+  return n + put_real(tmp, v);
 }
 
 // one line: "<row+1> <col+1> <value>\n" (MatrixMarket indices are 1-based)

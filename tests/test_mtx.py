@@ -27,6 +27,7 @@ def fmt():
     lib.ssmtx_put_real.argtypes = [C.c_double, C.c_char_p]
     lib.ssmtx_real_supported.argtypes = [C.c_double]
     lib.ssmtx_put_line.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_char_p]
+    lib.ssmtx_line_len.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int]
     return lib
 
 
@@ -98,6 +99,16 @@ def test_lines(fmt):
                                    (5, 7, 0.5, 0, '6 8 0.5\n'), (5, 7, 3.0, 0, '6 8 3\n')]:
         n = fmt.ssmtx_put_line(r, c, v, integer, buf)
         assert buf.raw[:n].decode() == want
+        assert fmt.ssmtx_line_len(r, c, v, integer) == len(want)
+    rng = np.random.default_rng(9)
+    for _ in range(3000):                                   # integers across all digit counts, both signs
+        r, c = (int(x) for x in rng.integers(0, 2 ** 31 - 1, 2) >> rng.integers(0, 31, 2))
+        v = float(int(rng.integers(-2 ** 52, 2 ** 52)) >> int(rng.integers(0, 52)))
+        n = fmt.ssmtx_put_line(r, c, v, 1, buf)
+        assert buf.raw[:n].decode() == f'{r + 1} {c + 1} {int(v)}\n'
+        assert fmt.ssmtx_line_len(r, c, v, 1) == n
+        x = float(rng.integers(1, 50) / rng.integers(1, 33))
+        assert fmt.ssmtx_line_len(r, c, x, 0) == fmt.ssmtx_put_line(r, c, x, 0, buf)
     assert fmt.ssmtx_max_line() >= 11 + 1 + 11 + 1 + 58 + 1
 
 

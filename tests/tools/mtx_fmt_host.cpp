@@ -10,5 +10,6 @@ int ssmtx_put_real(double x, char* out) { return ssmtx::put_real(out, x); }
 int ssmtx_put_line(int row, int col, double v, int integer, char* out) {
   return ssmtx::put_line(out, row, col, v, integer != 0);
 }
+int ssmtx_line_len(int row, int col, double v, int integer) { return ssmtx::line_len(row, col, v, integer != 0); }
 int ssmtx_max_line(void) { return ssmtx::MAX_LINE_CHARS; }
 }
