@@ -580,8 +580,24 @@ def count_matrices(st, tl: TelescopeLikelihood):
 
 def output_report(st, tl: TelescopeLikelihood):
     """``Stellarscope.output_report``: barcodes.tsv, features.tsv, TE_counts[.mode].mtx."""
-    from . import mtx
     counts, bc_list, ft_list = count_matrices(st, tl)
+    world, rank = _dist_info()
+    if world > 1 and getattr(st.opts, 'shard_models', True):
+        # the ranks of a sharded run hold the same (summed) matrices and the same output paths: one of them writes
+        import torch.distributed as dist
+        try:
+            if rank == 0:
+                _write_report(st, tl, counts, bc_list, ft_list)
+        finally:
+            dist.barrier()                       # the files exist when any rank returns
+        return
+    _write_report(st, tl, counts, bc_list, ft_list)
+    return
+
+
+def _write_report(st, tl, counts, bc_list, ft_list):
+    """barcodes.tsv, features.tsv (model.py:1380-1384) and one MTX file per reassignment mode (:1411-1418)."""
+    from . import mtx
     with open(st.opts.outfile_path('barcodes.tsv'), 'w') as outh:
         print('\n'.join(bc_list), file=outh)
     with open(st.opts.outfile_path('features.tsv'), 'w') as outh:

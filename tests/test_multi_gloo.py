@@ -232,3 +232,44 @@ def test_cell_blocks_keep_the_rows_of_a_cell_on_one_rank():
     loads = np.array([lens[b].sum() for b in blocks], dtype=float)
     assert loads.max() / loads.mean() < 1.1
     assert parallel.model_cell_block(lens, np.zeros(0, dtype=np.int64), row_cell, 0, world).size == 0
+
+
+def _report_worker(rank, world, port, q, tmpdir):
+    """output_report under model sharding: rank 0 alone writes, every rank returns after the files exist."""
+    import types
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from stellarscope_b200 import model
+    calls = []
+    model.count_matrices = lambda st, tl: ({'best_exclude': None}, ['BC0'], ['__no_feature'])
+
+    def fake_write(st, tl, counts, bc, ft):
+        import time
+        time.sleep(0.5)                              # the other rank must wait for this
+        calls.append(rank)
+        open(os.path.join(tmpdir, 'TE_counts.mtx'), 'w').write('x')
+    model._write_report = fake_write
+    st = types.SimpleNamespace(opts=types.SimpleNamespace(shard_models=True))
+    model.output_report(st, None)
+    q.put((rank, calls, os.path.exists(os.path.join(tmpdir, 'TE_counts.mtx'))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_output_report_single_writer_world2_gloo(tmp_path):
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_report_worker, args=(r, 2, port, q, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0] == (0, [0], True)                  # rank 0 wrote
+    assert got[1] == (1, [], True)                   # rank 1 did not write and returned after the file existed
