@@ -400,6 +400,11 @@ static PyObject* row_labels(PyObject* self, PyObject* args) {
     Py_ssize_t pos = 0;
     PyObject *qname, *rowobj;
     int ok = 1;
+    /* store_read_info (model.py:1045-1056) inserts a new read into both dicts at the same moment, with the same
+     * key object: as long as the two dicts yield identical key objects side by side, the label is taken from the
+     * parallel walk and no string is hashed; the first difference switches to look-ups for the rest */
+    Py_ssize_t pos2 = 0;
+    int parallel = 1;
     while (PyDict_Next(read_index, &pos, &qname, &rowobj)) {
       const Py_ssize_t row = PyLong_AsSsize_t(rowobj);
       if (row == -1 && PyErr_Occurred()) { ok = 0; break; }
@@ -408,7 +413,13 @@ static PyObject* row_labels(PyObject* self, PyObject* args) {
         ok = 0;
         break;
       }
-      PyObject* lab = PyDict_GetItemWithError(label_of, qname);
+      PyObject* lab = NULL;
+      if (parallel) {
+        PyObject *k2, *v2;
+        if (PyDict_Next(label_of, &pos2, &k2, &v2) && k2 == qname) lab = v2;
+        else parallel = 0;
+      }
+      if (!lab) lab = PyDict_GetItemWithError(label_of, qname);
       if (!lab) {
         if (!PyErr_Occurred()) PyErr_SetObject(PyExc_KeyError, qname);
         ok = 0;

@@ -311,6 +311,11 @@ def pooling_row_segments(st, opts):
     N = st.shape[0]
     if opts.pooling_mode == 'pseudobulk':
         return np.zeros(N, dtype=np.int32), ['pseudobulk']
+    if opts.pooling_mode in ('individual', 'celltype'):
+        from . import checkpoint
+        table = checkpoint.row_table(st)
+        if table is not None:
+            return _row_segments_from_table(st, opts, table)
     seg = np.full(N, -1, dtype=np.int32)
     groups, ids = [], []
     i = 0
@@ -346,9 +351,47 @@ def pooling_row_segments(st, opts):
     return seg, list(range(i))
 
 
+def _row_segments_from_table(st, opts, table):
+    """``pooling_row_segments`` for an object loaded from a side-car checkpoint (``checkpoint.RowTable``): the
+    barcode code of every row is already an array, no container is walked."""
+    code = table.row_bcode
+    nb = len(table.bcodes)
+    counts = np.bincount(code[code >= 0], minlength=nb)
+    if opts.pooling_mode == 'individual':
+        has = counts > 0
+        model_of = np.where(has, np.cumsum(has) - 1, -1).astype(np.int32)   # barcodes without reads get no model
+        for b in np.flatnonzero(~has):
+            lg.info(f'        ...not fitting "{table.bcodes[b]}" -> no reads found')
+        n_models = int(has.sum())
+    else:
+        code_of = {b: i for i, b in enumerate(table.bcodes)}
+        model_of = np.full(nb, -1, dtype=np.int32)
+        n_models = 0
+        for _ctype in st.celltypes:
+            found = False
+            for _bcode in st.ctype_bcode_map[_ctype]:
+                c = code_of.get(_bcode)
+                if c is None or counts[c] == 0:
+                    continue
+                if model_of[c] not in (-1, n_models):
+                    raise StellarscopeError('a barcode belongs to more than one celltype (not supported): '
+                                            f'{_bcode}')
+                model_of[c] = n_models
+                found = True
+            if not found:
+                lg.info(f'        ...not fitting "{_ctype}" -> no reads found')
+                continue
+            n_models += 1
+    seg = np.where(code >= 0, model_of[np.maximum(code, 0)], -1).astype(np.int32)
+    return seg, list(range(n_models))
+
+
 def _row_cells(st):
     """Cell (running index of the barcode in ``bcode_ridx_map``) of every row, -1 for rows of no barcode."""
-    from . import hostutil
+    from . import checkpoint, hostutil
+    table = checkpoint.row_table(st)
+    if table is not None:
+        return table.row_bcode.copy()
     groups = list(st.bcode_ridx_map.values())
     cell = np.full(st.shape[0], -1, dtype=np.int32)
     hostutil.fill_row_segments(groups, np.arange(len(groups), dtype=np.int32), cell)
@@ -505,6 +548,14 @@ def _row_outputs(st, bc_pos):
     helper; other mapping types take the Python route."""
     N = len(st.read_index)
     want_umi = bool(st.opts.umi_counts)
+    from . import checkpoint
+    table = checkpoint.row_table(st)
+    if table is not None and (not want_umi or table.row_umi is not None):
+        # loaded from a side-car checkpoint: barcode / UMI codes per row are arrays already
+        pos = np.fromiter((bc_pos.get(b, -1) for b in table.bcodes), dtype=np.int32, count=len(table.bcodes))
+        code = table.row_bcode
+        row_cell = np.where(code >= 0, pos[np.maximum(code, 0)] if len(pos) else -1, -1).astype(np.int32)
+        return row_cell, (table.row_umi.copy() if want_umi else None)
     if type(st.read_index) is dict and type(st.read_bcode_map) is dict and (not want_umi or type(st.read_umi_map) is dict):
         from . import hostutil
         row_cell = None
@@ -546,7 +597,9 @@ def count_matrices(st, tl: TelescopeLikelihood):
     if getattr(st, 'filtlist', None):
         bc_list = sorted(st.filtlist, key=st.filtlist.get)
     else:
-        bc_list = sorted(st.bcode_ridx_map.keys())
+        from . import checkpoint
+        table = checkpoint.row_table(st)
+        bc_list = sorted(table.bcodes) if table is not None else sorted(st.bcode_ridx_map.keys())
     ft_list = sorted(st.feat_index, key=st.feat_index.get)
     numft, numbc = len(ft_list), len(bc_list)
     bc_pos = {b: i for i, b in enumerate(bc_list)}
@@ -647,4 +700,7 @@ def install():
     ref.Stellarscope.dedup_umi = lambda self, output_report=True, summary=True: umi.dedup_umi(self, output_report, summary)
     from . import loader
     ref.Stellarscope.load_alignment = lambda self, annotation: loader.load_alignment(self, annotation)
+    from . import checkpoint
+    ref.Stellarscope.save = lambda self, filename: checkpoint.save(self, filename)
+    ref.Stellarscope.load = classmethod(lambda cls, filename: checkpoint.load(filename))
     return ref

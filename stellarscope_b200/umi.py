@@ -22,8 +22,19 @@ from .statistics import UMIInfo
 def _pair_ids(st):
     """Row -> id of its (barcode, UMI) pair, ids in first-seen order (the order of the reference's
     ``bcumi_read`` dict, model.py:1161-1164) and the pairs themselves."""
-    from . import hostutil
+    from . import checkpoint, hostutil
     N = st.shape[0]
+    table = checkpoint.row_table(st)
+    if table is not None and table.row_umi is not None and N == table.N:
+        # loaded from a side-car checkpoint: (barcode code, UMI code) per row -> pair ids in first-row order
+        nu = max(len(table.umis), 1)
+        key = table.row_bcode.astype(np.int64) * nu + table.row_umi
+        uniq, first, inv = np.unique(key, return_index=True, return_inverse=True)
+        order = np.argsort(first, kind='stable')
+        rank = np.empty(len(uniq), dtype=np.int32)
+        rank[order] = np.arange(len(uniq), dtype=np.int32)
+        pairs = [(table.bcodes[k // nu], table.umis[k % nu]) for k in uniq[order].tolist()]
+        return rank[inv.reshape(-1)].astype(np.int32), pairs
     row_group = np.full(N, -1, dtype=np.int32)
     if all(type(m) is dict for m in (st.read_index, st.read_bcode_map, st.read_umi_map)):
         pairs = hostutil.pair_ids(st.read_index, st.read_bcode_map, st.read_umi_map, row_group)   # C walk of the dicts
@@ -76,9 +87,14 @@ def dedup_umi(st, output_report=True, summary=True):
 def _write_tracking(st, raw, row_group, pairs, out):
     """``umi_tracking.txt`` (model.py:1157-1158, 1200-1206): for every duplicated pair its reads with the
     component label (scipy numbers components by their first read), EX / REP and the feature -> score dict."""
-    qnames = [None] * raw.shape[0]
-    for q, r in st.read_index.items():
-        qnames[r] = q
+    from . import checkpoint
+    table = checkpoint.row_table(st)
+    if table is not None and table.N == raw.shape[0]:
+        qnames = table.names()
+    else:
+        qnames = [None] * raw.shape[0]
+        for q, r in st.read_index.items():
+            qnames[r] = q
     order = np.argsort(row_group, kind='stable')                 # reads of a pair in row order
     bounds = np.searchsorted(row_group[order], np.arange(len(pairs) + 1))
     root, excluded = out['comp_root'], out['excluded']
