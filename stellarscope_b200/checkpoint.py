@@ -171,7 +171,8 @@ class LazyMap(MutableMapping):
 def row_table(st):
     """The row table of an object loaded from a side-car checkpoint, or None when the object's containers are
     (or may have become) something else."""
-    t = getattr(st, '_ss_rows', None)
+    m = getattr(st, 'read_index', None)
+    t = m._table if isinstance(m, LazyMap) else None       # the object carries no attribute the reference's does not
     if t is None or t.dirty:
         return None
     for k in ROW_MAPS[:4]:
@@ -284,7 +285,6 @@ def save(st, filename):
     for k in ROW_MAPS:
         if hasattr(st, k):
             setattr(light, k, None)
-    light.__dict__.pop('_ss_rows', None)
     for k in MATRICES:
         m = getattr(st, k, None)
         if m is not None and scipy.sparse.issparse(m):
@@ -354,5 +354,4 @@ def load(filename):
                 st.reassignments[key[2:]] = m
     for k in head['maps']:
         setattr(st, k, LazyMap(t, k))
-    st._ss_rows = t
     return st

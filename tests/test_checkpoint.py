@@ -62,10 +62,8 @@ def make_st(seed=3, n_cells=25, n_alignments=6000, umi=True, empty_barcode=False
 
 
 def assert_same_object(a, b):
-    assert set(a.__dict__) - {'_ss_rows'} == set(b.__dict__) - {'_ss_rows'}
+    assert list(a.__dict__) == list(b.__dict__)                # same attributes, nothing added
     for k, va in a.__dict__.items():
-        if k == '_ss_rows':
-            continue
         vb = getattr(b, k)
         if sp.issparse(va):
             assert type(va) is type(vb) and va.shape == vb.shape and va.dtype == vb.dtype, k
@@ -168,7 +166,7 @@ def test_reference_pickles_and_odd_objects(tmp_path):
     with open(f, 'wb') as fh:
         pickle.dump(st, fh)                                    # what the reference's save writes
     ld = checkpoint.load(f)
-    assert type(ld.read_index) is dict and not hasattr(ld, '_ss_rows')
+    assert type(ld.read_index) is dict and checkpoint.row_table(ld) is None
     assert_same_object(ld, st)
     # containers of another shape (rows not numbered in insertion order): saved as a plain pickle, nothing lost
     odd = make_st(seed=6, umi=False)
@@ -202,3 +200,25 @@ def test_real_reference_save_load(tmp_path):
     ours = checkpoint.load(b)
     assert type(ours) is type(theirs)
     assert_same_object(ours, theirs)
+
+
+def test_lazy_map_behaves_like_the_dict(tmp_path):
+    st = make_st(seed=4, umi=True)
+    f = str(tmp_path / 'c.pickle')
+    checkpoint.save(st, f)
+    ld = checkpoint.load(f)
+    ri, ref = ld.read_index, st.read_index
+    q = next(iter(ref))
+    assert len(ri) == len(ref) and not ri.materialised          # len needs no dict
+    assert q in ri and ri[q] == ref[q] and ri.get('nope') is None and ri.get(q) == ref[q]
+    assert sorted(ri, key=ri.get) == sorted(ref, key=ref.get)   # the idiom of output_report (model.py:1389)
+    assert list(ri.items()) == list(ref.items()) and list(ri.values()) == list(ref.values())
+    assert ri == ref and dict(ri) == ref
+    assert ri.setdefault(q, -5) == ref[q]
+    with pytest.raises(KeyError):
+        ri['nope']
+    import copy
+    assert copy.deepcopy(ld.read_bcode_map) == st.read_bcode_map
+    assert ld.read_umi_map.pop(q) == st.read_umi_map[q] and q not in ld.read_umi_map
+    assert checkpoint.row_table(ld) is None                     # that was a write
+    assert 'read_index' in repr(ri)
