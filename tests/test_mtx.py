@@ -131,6 +131,16 @@ def test_header_comment_edge_cases_match_scipy():
         assert mtx.header(7, 5, 1, 'integer', comment) + b'3 5 3\n' == f.getvalue(), repr(comment)
 
 
+def test_mmwrite_rejects_what_it_does_not_write():
+    """Argument errors come before any device work (no GPU needed)."""
+    from stellarscope_b200 import mtx
+    with pytest.raises(TypeError):
+        mtx.mmwrite('x.mtx', np.ones((2, 2)))                          # dense: not a count matrix of output_report
+    with pytest.raises(TypeError):
+        mtx.mmwrite('x.mtx', sp.csc_matrix(np.ones((2, 2), dtype=np.complex128)))
+    assert not os.path.exists('x.mtx')
+
+
 def test_golden_files_are_scipy():
     """The committed goldens are what scipy.io.mmwrite (the reference's writer) produces for the committed
     triples (tests/tools/make_golden_mtx.py)."""
