@@ -180,6 +180,13 @@ def test_reference_pickles_and_odd_objects(tmp_path):
     checkpoint.save(odd, g)
     assert not os.path.exists(checkpoint.sidecar_path(g))
     assert_same_object(checkpoint.load(g), odd)
+    # a side-car of another save is refused
+    h1, h2 = str(tmp_path / 'h1.pickle'), str(tmp_path / 'h2.pickle')
+    checkpoint.save(st, h1)
+    checkpoint.save(st, h2)
+    os.replace(checkpoint.sidecar_path(h2), checkpoint.sidecar_path(h1))
+    with pytest.raises(ValueError):
+        checkpoint.load(h1)
     # a side-car that went missing is an error, not an empty object
     h = str(tmp_path / 'h.pickle')
     checkpoint.save(st, h)
