@@ -141,6 +141,32 @@ def test_mmwrite_rejects_what_it_does_not_write():
     assert not os.path.exists('x.mtx')
 
 
+def test_write_all_handles_short_writes():
+    from stellarscope_b200.engine import write_all
+
+    class Short:                                    # an unbuffered sink that takes at most 5 bytes per call
+        def __init__(self):
+            self.got = bytearray()
+
+        def write(self, mv):
+            k = min(5, len(mv))
+            self.got += bytes(mv[:k])
+            return k
+    sink = Short()
+    data = bytes(range(256)) * 3
+    write_all(sink, memoryview(data))
+    assert bytes(sink.got) == data
+    buf = io.BytesIO()
+    write_all(buf, memoryview(data))
+    assert buf.getvalue() == data
+
+    class Stuck:
+        def write(self, mv):
+            return 0
+    with pytest.raises(OSError):
+        write_all(Stuck(), memoryview(b'abc'))
+
+
 def test_golden_files_are_scipy():
     """The committed goldens are what scipy.io.mmwrite (the reference's writer) produces for the committed
     triples (tests/tools/make_golden_mtx.py)."""
