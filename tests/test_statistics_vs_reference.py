@@ -112,3 +112,22 @@ def test_output_stats_accepts_our_records(theirs, tmp_path):
     text = open(out).read()
     assert text.startswith('stage\tvar') or 'PoolInfo' in text
     assert 'total_lnl' in text and 'ReassignInfo' in text
+
+
+def test_sparse_plus_file_format_and_equality(theirs, tmp_path):
+    """csr_matrix_plus.save / load / check_equal: files written by either implementation are read by the other
+    (reference sparse_plus.py:242-245, 398-405)."""
+    import scipy.sparse as sp
+    import stellarscope.utils.sparse_plus as ref_sp
+    from stellarscope_b200 import sparse_plus as our_sp
+    rng = np.random.default_rng(0)
+    m = sp.random(40, 30, density=0.1, random_state=1, format='csr', dtype=np.float64)
+    a, b = our_sp.csr_matrix_plus(m), ref_sp.csr_matrix_plus(m)
+    fa, fb = str(tmp_path / 'a.npz'), str(tmp_path / 'b.npz')
+    a.save(fa)
+    b.save(fb)
+    assert ref_sp.csr_matrix_plus.load(fa).check_equal(b)
+    assert our_sp.csr_matrix_plus.load(fb).check_equal(a)
+    assert a.check_equal(b) and b.check_equal(a)
+    c = our_sp.csr_matrix_plus(m * 2)
+    assert not a.check_equal(c) and not a.check_equal(our_sp.csr_matrix_plus(m[:, :29]))
