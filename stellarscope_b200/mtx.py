@@ -7,6 +7,13 @@ reassignment mode) that is 10-25 s per mode, more than the EM fit, the reassignm
 together.  Here the text is produced on the device (``ss_mtx_measure`` / ``ss_mtx_write``,
 ``csrc/ss_mtx.cu``) and streamed into the file through the pinned staging ring.
 
+The writer itself is third-party code outside the reference checkout: ``scipy.io.mmwrite`` (the reference asks for
+``scipy>=1.2.1``, setup.py:48, unpinned; 1.18.1 in this image, whose writer is the C++ ``fast_matrix_market`` since
+1.12).  Its format is the published MatrixMarket coordinate format: banner ``%%MatrixMarket matrix coordinate
+<field> general``, ``%`` comment lines, a ``rows cols entries`` line, one ``row col value`` line (1-based) per stored
+entry.  Parity is anchored on the reference's call site (tests/test_mtx.py: files of the real ``output_report``,
+scipy's own output, goldens written by scipy).
+
 The file has the same header, comment block, size line, entry order and -- for integer matrices -- the same
 bytes as scipy's.  Real values (best_average, ``--umi_counts``) are written as the correctly rounded
 17-significant-digit decimal (parses back to the same double) where scipy prints the shortest round-trip
