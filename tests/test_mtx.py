@@ -167,6 +167,33 @@ def test_write_all_handles_short_writes():
         write_all(Stuck(), memoryview(b'abc'))
 
 
+def test_oracle_restatement(fmt):
+    """oracle/mtx_oracle.py: byte-identical to scipy for integer matrices (incl. the golden), equal to the formatter
+    shared with the device for real values, and its real files parse back bit-exactly."""
+    from oracle import mtx_oracle
+    rng = np.random.default_rng(7)
+    comment = 'PN: stellarscope\n VN: 1.5\n reassign_mode: best_exclude'
+    mi = _random_counts(rng, 300, 41, 2500, real=False)
+    f = io.BytesIO()
+    scipy.io.mmwrite(f, mi, comment=comment)
+    assert mtx_oracle.mtx_bytes(mi, comment) == f.getvalue()
+    mr = _random_counts(rng, 300, 41, 2500, real=True)
+    text = mtx_oracle.mtx_bytes(mr, comment)
+    back = scipy.io.mmread(io.BytesIO(text)).tocsc()
+    back.sort_indices()
+    assert (back.indices == mr.indices).all() and (back.data == mr.data).all()
+    buf = C.create_string_buffer(128)
+    body = text.split(b'\n')[5:-1]
+    coo = mr.tocoo()
+    for ln, r, c, v in zip(body[:400], coo.row, coo.col, coo.data):
+        n = fmt.ssmtx_put_line(int(r), int(c), float(v), 0, buf)
+        assert buf.raw[:n] == ln + b'\n'
+    z = np.load(os.path.join(GOLDEN, 'mtx_cases.npz'))
+    g = sp.csc_matrix((z['int_data'].astype(np.int32), z['int_indices'], z['int_indptr']), shape=tuple(z['shape']))
+    with open(os.path.join(GOLDEN, 'mtx_int.mtx'), 'rb') as fh:
+        assert mtx_oracle.mtx_bytes(g, str(z['comment'])) == fh.read()
+
+
 def test_golden_files_are_scipy():
     """The committed goldens are what scipy.io.mmwrite (the reference's writer) produces for the committed
     triples (tests/tools/make_golden_mtx.py)."""
