@@ -53,6 +53,19 @@ CASES = {
                           dict(pooling_mode='pseudobulk', pi_prior=3, theta_prior=500, max_iter=30), False),
     'individual_maxiter': (dict(n_cells=6, n_alignments=1500, n_loci=100, seed=19, unique_frac=0.0),
                            dict(pooling_mode='individual', max_iter=7), False),
+    # second batch: aggregation by UMI under celltype pooling, priors and tiny / mostly-unique cells under individual
+    # pooling (cells without ambiguous rows), a single iteration, another confidence threshold
+    'celltype_umicounts': (dict(n_cells=14, n_alignments=2600, n_loci=140, seed=21, unique_frac=0.1, n_celltypes=3,
+                                umi_dup_rate=0.2),
+                           dict(pooling_mode='celltype', umi_counts=True), False),
+    'individual_priors': (dict(n_cells=9, n_alignments=1800, n_loci=110, seed=22, unique_frac=0.15),
+                          dict(pooling_mode='individual', pi_prior=2, theta_prior=1000), False),
+    'individual_sparsecells': (dict(n_cells=24, n_alignments=700, n_loci=90, seed=23, unique_frac=0.85),
+                               dict(pooling_mode='individual'), False),
+    'pseudobulk_maxiter1': (dict(n_cells=5, n_alignments=1200, n_loci=100, seed=24, unique_frac=0.1),
+                            dict(pooling_mode='pseudobulk', max_iter=1), False),
+    'individual_conf06': (dict(n_cells=8, n_alignments=1600, n_loci=100, seed=25, unique_frac=0.1),
+                          dict(pooling_mode='individual', conf_prob=0.6), False),
     # BASELINE.json configs[0]: bundled BAM + GTF, pseudobulk, defaults (golden: data/telescope_report.tsv)
     'config1': ('config1', dict(pooling_mode='pseudobulk'), False),
 }

@@ -84,14 +84,14 @@ class RowTable:
             lab = np.array(self.umis + [None], dtype=object)[self.row_umi].tolist()
             return dict(zip(self.names(), lab))
         if kind == 'bcode_ridx_map':
-            out = defaultdict(set)
+            out = defaultdict(set) if self.default_maps.get(kind, True) else {}
             order = np.argsort(self.row_bcode, kind='stable')
             bounds = np.searchsorted(self.row_bcode[order], np.arange(len(self.bcodes) + 1))
             for i, b in enumerate(self.bcodes):
                 out[b] = set(order[bounds[i]:bounds[i + 1]].tolist())
             return out
         if kind == 'bcode_umi_map':
-            out = defaultdict(list)
+            out = defaultdict(list) if self.default_maps.get(kind, True) else {}
             if self.bu_ptr is not None:
                 u = np.array(self.umis + [None], dtype=object)
                 for i, b in enumerate(self.bcodes):
@@ -102,6 +102,7 @@ class RowTable:
         raise KeyError(kind)
 
     bu_keys = None          # barcodes that are keys of bcode_umi_map (None: all with entries)
+    default_maps = {}       # container kind -> it was a defaultdict (the reference's are, model.py:875-876)
 
     def n_keys(self, kind):
         if kind in ('read_index', 'read_bcode_map'):
@@ -247,6 +248,11 @@ def _table_from_dicts(st):
     t = RowTable(N, blob, bcodes, row_bcode, umis, row_umi, bu_ptr, bu_code)
     t.bu_keys = bu_keys
     t._names = names
+    t.default_maps = {k: isinstance(getattr(st, k, None), defaultdict) for k in ('bcode_ridx_map', 'bcode_umi_map')}
+    for k, factory in (('bcode_ridx_map', set), ('bcode_umi_map', list)):
+        m = getattr(st, k, None)
+        if isinstance(m, defaultdict) and m.default_factory is not factory:
+            return None                                    # not the reference's container
     return t
 
 
@@ -305,7 +311,7 @@ def save(st, filename):
         arrays['bu_ptr'], arrays['bu_code'] = t.bu_ptr, t.bu_code
     head = {'magic': MAGIC, 'n_rows': t.N, 'n_bcodes': len(t.bcodes), 'n_umis': None if t.umis is None else len(t.umis),
             'matrices': meta, 'maps': [k for k in ROW_MAPS if hasattr(st, k)],
-            'bu_keys': None if t.bu_keys is None else sorted(t.bu_keys)}
+            'bu_keys': None if t.bu_keys is None else sorted(t.bu_keys), 'default_maps': dict(t.default_maps)}
     side = sidecar_path(filename)
     tmp = side + '.tmp'
     with open(tmp, 'wb') as fh:
@@ -346,6 +352,7 @@ def load(filename):
                      z['row_umi'] if 'row_umi' in z.files else None,
                      z['bu_ptr'] if 'bu_ptr' in z.files else None, z['bu_code'] if 'bu_code' in z.files else None)
         t.bu_keys = None if head.get('bu_keys') is None else set(head['bu_keys'])
+        t.default_maps = dict(head.get('default_maps') or {})
         for key in head['matrices']:
             m = _mat_from(key, z, head['matrices'])
             if key.startswith('m.'):

@@ -75,6 +75,10 @@ def assert_same_object(a, b):
         elif k == 'opts':
             assert va.__dict__ == vb.__dict__
         elif k in ROW_MAPS:
+            da = va._mat() if isinstance(va, checkpoint.LazyMap) else va
+            db = vb._mat() if isinstance(vb, checkpoint.LazyMap) else vb
+            assert type(da) is type(db), k
+            assert getattr(da, 'default_factory', None) is getattr(db, 'default_factory', None), k
             assert dict(va) == dict(vb), k
             assert list(va) == list(vb), k                     # same key order
         else:
@@ -222,3 +226,15 @@ def test_lazy_map_behaves_like_the_dict(tmp_path):
     assert ld.read_umi_map.pop(q) == st.read_umi_map[q] and q not in ld.read_umi_map
     assert checkpoint.row_table(ld) is None                     # that was a write
     assert 'read_index' in repr(ri)
+
+
+def test_plain_dict_containers_keep_their_type(tmp_path):
+    st = make_st(seed=2, umi=True)
+    st.bcode_ridx_map = dict(st.bcode_ridx_map)                # e.g. an object somebody rebuilt by hand
+    st.bcode_umi_map = dict(st.bcode_umi_map)
+    f = str(tmp_path / 'c.pickle')
+    checkpoint.save(st, f)
+    ld = checkpoint.load(f)
+    assert_same_object(ld, pickle.loads(pickle.dumps(st)))
+    with pytest.raises(KeyError):
+        ld.bcode_ridx_map['never seen']

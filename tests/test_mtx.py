@@ -122,6 +122,15 @@ def test_header_matches_scipy():
         assert mtx.header(7, 5, 1, field, comment) + b'3 5 3\n' == f.getvalue()
 
 
+def test_header_comment_edge_cases_match_scipy():
+    from stellarscope_b200 import mtx
+    m = sp.csc_matrix((np.array([3], dtype=np.int32), (np.array([2]), np.array([4]))), shape=(7, 5))
+    for comment in ('', 'one', 'a\nb', 'a\n\nb', 'trailing\n'):
+        f = io.BytesIO()
+        scipy.io.mmwrite(f, m, comment=comment)
+        assert mtx.header(7, 5, 1, 'integer', comment) + b'3 5 3\n' == f.getvalue(), repr(comment)
+
+
 def test_golden_files_are_scipy():
     """The committed goldens are what scipy.io.mmwrite (the reference's writer) produces for the committed
     triples (tests/tools/make_golden_mtx.py)."""
