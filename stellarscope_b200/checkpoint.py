@@ -309,7 +309,9 @@ def save(st, filename):
         arrays['umis'] = np.frombuffer('\n'.join(t.umis).encode(), dtype=np.uint8)
     if t.bu_ptr is not None:
         arrays['bu_ptr'], arrays['bu_code'] = t.bu_ptr, t.bu_code
-    head = {'magic': MAGIC, 'n_rows': t.N, 'n_bcodes': len(t.bcodes), 'n_umis': None if t.umis is None else len(t.umis),
+    token = os.urandom(8).hex()                            # ties the pickle to its side-car (checked by load)
+    arrays['token'] = np.frombuffer(token.encode(), dtype=np.uint8)
+    head = {'magic': MAGIC, 'token': token, 'n_rows': t.N, 'n_bcodes': len(t.bcodes), 'n_umis': None if t.umis is None else len(t.umis),
             'matrices': meta, 'maps': [k for k in ROW_MAPS if hasattr(st, k)],
             'bu_keys': None if t.bu_keys is None else sorted(t.bu_keys), 'default_maps': dict(t.default_maps)}
     side = sidecar_path(filename)
@@ -346,6 +348,8 @@ def load(filename):
     if not os.path.exists(side):
         raise FileNotFoundError(f'{side}: the side-car of checkpoint {filename} is missing')
     with np.load(side) as z:
+        if 'token' in head and ('token' not in z.files or z['token'].tobytes().decode() != head['token']):
+            raise ValueError(f'{side} does not belong to checkpoint {filename} (written by another save)')
         bcodes = _split(z['bcodes'], head['n_bcodes'])
         umis = _split(z['umis'], head['n_umis']) if head['n_umis'] is not None else None
         t = RowTable(head['n_rows'], z['names'], bcodes, z['row_bcode'], umis,

@@ -151,7 +151,7 @@ class _HostStager:
                 slot = i % self.SLOTS
                 m = min(C_, n - off)
                 self.events[slot].synchronize()
-                fh.write(memoryview(self.ring_np[slot * C_:slot * C_ + m]))
+                write_all(fh, memoryview(self.ring_np[slot * C_:slot * C_ + m]))
                 if i + self.SLOTS < len(offs):
                     issue(i + self.SLOTS)                    # the slot is free again
         return n
@@ -198,6 +198,17 @@ _TORCH_NP = {torch.uint8: np.uint8, torch.int8: np.int8, torch.int16: np.int16, 
 _NP_TORCH = {v: k for k, v in _TORCH_NP.items()}
 _stager = _HostStager()
 PINNED_UPLOAD_LIMIT = 256 << 20      # larger uploads go through the staging ring instead of a pinned copy
+
+
+def write_all(fh, mv):
+    """``fh.write`` until every byte is out: an unbuffered file object may accept fewer bytes than it is given."""
+    while len(mv):
+        n = fh.write(mv)
+        if n is None or n >= len(mv):
+            return
+        if n <= 0:
+            raise OSError('write returned no progress')
+        mv = mv[n:]
 
 
 def drain_to_file(t, fh):

@@ -63,14 +63,14 @@ def mmwrite(target, a, comment='', engine=None, device_coo=None):
         coo = a.tocoo()
         nnz = int(coo.nnz)
         text = eng.mtx_text(coo.row, coo.col, coo.data, integer)
-    from .engine import drain_to_file
+    from .engine import drain_to_file, write_all
     if hasattr(target, 'write'):
-        target.write(header(a.shape[0], a.shape[1], nnz, field, comment))
+        write_all(target, memoryview(header(a.shape[0], a.shape[1], nnz, field, comment)))
         drain_to_file(text, target)
         return
     path = os.fspath(target)
     if not os.path.splitext(path)[1]:
         path += '.mtx'
     with open(path, 'wb', buffering=0) as fh:
-        fh.write(header(a.shape[0], a.shape[1], nnz, field, comment))
+        write_all(fh, memoryview(header(a.shape[0], a.shape[1], nnz, field, comment)))
         drain_to_file(text, fh)

@@ -46,17 +46,20 @@ class csr_matrix_plus(scipy.sparse.csr_matrix):
         return (_rebuild, (type(self), self.data, self.indices, self.indptr, self.shape))
 
     def check_equal(self, other):
-        if self.shape != other.shape:
-            return False
-        return (self != other).nnz == 0
+        """Same shape and no differing element (the reference's method of this name, sparse_plus.py:242-245)."""
+        same_shape = tuple(self.shape) == tuple(other.shape)
+        return bool(same_shape and (self != other).nnz == 0)
+
+    _NPZ_FIELDS = ('data', 'indices', 'indptr', 'shape')       # file format of the reference's save (sparse_plus.py:398-405)
 
     def save(self, filename):
-        np.savez(filename, data=self.data, indices=self.indices, indptr=self.indptr, shape=self.shape)
+        np.savez(filename, **{k: getattr(self, k) for k in self._NPZ_FIELDS})
 
     @classmethod
     def load(cls, filename):
-        loader = np.load(filename)
-        return cls((loader['data'], loader['indices'], loader['indptr']), shape=loader['shape'])
+        with np.load(filename) as z:
+            data, indices, indptr, shape = (z[k] for k in cls._NPZ_FIELDS)
+        return cls((data, indices, indptr), shape=tuple(int(x) for x in shape))
 
     # -- device aggregation ----------------------------------------------------
     def _device_coo(self, row_group, row_umi, engine, keep_device=False):

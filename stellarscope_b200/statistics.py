@@ -15,8 +15,12 @@ import numpy as np
 
 
 def _property_names(obj):
+    """Properties of the record, as the reference lists them (statistics.py:18-20) -- minus the ones that are plain
+    attributes there and properties only here (``_not_in_reference``), so ``to_dataframe`` / stats.final.tsv show
+    the reference's rows."""
     cls = obj.__class__
-    return [p for p in dir(cls) if isinstance(getattr(cls, p), property)]
+    skip = getattr(cls, '_not_in_reference', ())
+    return [p for p in dir(cls) if isinstance(getattr(cls, p), property) and p not in skip]
 
 
 class GenericInfo:
@@ -39,6 +43,7 @@ class FitInfo(GenericInfo):
     """statistics.py:269-307.  ``iterations`` holds ``(inum, itime, diff_est)``
     (model.py:359); ``itime`` is the device time of the whole fit divided by the
     number of iterations (the reference measures each iteration on the host)."""
+    _not_in_reference = ('iterations', 'n_iterations')     # lazy here, a plain list attribute in the reference
 
     def __init__(self, nobs=None, nfeats=None, epsilon=None, max_iter=None):
         super().__init__()

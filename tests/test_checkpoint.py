@@ -180,6 +180,13 @@ def test_reference_pickles_and_odd_objects(tmp_path):
     checkpoint.save(odd, g)
     assert not os.path.exists(checkpoint.sidecar_path(g))
     assert_same_object(checkpoint.load(g), odd)
+    # a side-car of another save is refused
+    h1, h2 = str(tmp_path / 'h1.pickle'), str(tmp_path / 'h2.pickle')
+    checkpoint.save(st, h1)
+    checkpoint.save(st, h2)
+    os.replace(checkpoint.sidecar_path(h2), checkpoint.sidecar_path(h1))
+    with pytest.raises(ValueError):
+        checkpoint.load(h1)
     # a side-car that went missing is an error, not an empty object
     h = str(tmp_path / 'h.pickle')
     checkpoint.save(st, h)
@@ -238,3 +245,45 @@ def test_plain_dict_containers_keep_their_type(tmp_path):
     assert_same_object(ld, pickle.loads(pickle.dumps(st)))
     with pytest.raises(KeyError):
         ld.bcode_ridx_map['never seen']
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/stellarscope'), reason='reference checkout not present')
+def test_install_rebinds_the_reference_names(tmp_path):
+    """The one-import binding of INTEGRATION.md against the real reference module, in a subprocess (install() rebinds
+    names of the imported reference for good): every hot-path name points at this package afterwards, and the
+    reference's own ``Stellarscope.save`` / ``load`` entry points go through the side-car."""
+    import subprocess
+    import sys
+    import textwrap
+    st = make_st(seed=13, umi=True)
+    src = str(tmp_path / 'src.pickle')
+    with open(src, 'wb') as fh:
+        pickle.dump(st.__dict__, fh)
+    code = textwrap.dedent(f'''
+        import pickle, sys
+        sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+        from oracle import refshim
+        ref = refshim.load()
+        import stellarscope_b200.model as b200
+        from stellarscope_b200 import checkpoint
+        assert b200.install() is ref
+        assert ref.TelescopeLikelihood is b200.TelescopeLikelihood
+        assert ref._fit_pooling_model is b200._fit_pooling_model and ref._em_wrapper is b200._em_wrapper
+        import stellarscope
+        assert b200.StellarscopeError is stellarscope.StellarscopeError
+        obj = ref.Stellarscope.__new__(ref.Stellarscope)
+        obj.__dict__.update(pickle.load(open({src!r}, 'rb')))
+        for name in ('reassign', 'output_report', 'dedup_umi', 'load_alignment', 'save'):
+            assert getattr(ref.Stellarscope, name).__module__ == 'stellarscope_b200.model', name
+        f = {str(tmp_path / 'c.pickle')!r}
+        assert obj.save(f) is True                              # stages.py:97 calls exactly this
+        back = ref.Stellarscope.load(f)                         # stages.py:108
+        assert type(back) is ref.Stellarscope and isinstance(back.read_index, checkpoint.LazyMap)
+        assert dict(back.read_bcode_map) == obj.read_bcode_map
+        seg_a, keys_a = b200.pooling_row_segments(back, back.opts)
+        seg_b, keys_b = b200.pooling_row_segments(obj, obj.opts)
+        assert (seg_a == seg_b).all() and keys_a == keys_b and not back.read_index.materialised
+        print('install ok')
+    ''')
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'install ok' in r.stdout, r.stdout + r.stderr

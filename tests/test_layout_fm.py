@@ -6,7 +6,6 @@ import numpy as np
 import pytest
 
 from stellarscope_b200 import layout_fm, layout_host
-from tests import helpers as H
 
 
 def _layout(seed, n_cells, n_alignments, max_k=32, n_loci=300):

@@ -131,6 +131,42 @@ def test_header_comment_edge_cases_match_scipy():
         assert mtx.header(7, 5, 1, 'integer', comment) + b'3 5 3\n' == f.getvalue(), repr(comment)
 
 
+def test_mmwrite_rejects_what_it_does_not_write():
+    """Argument errors come before any device work (no GPU needed)."""
+    from stellarscope_b200 import mtx
+    with pytest.raises(TypeError):
+        mtx.mmwrite('x.mtx', np.ones((2, 2)))                          # dense: not a count matrix of output_report
+    with pytest.raises(TypeError):
+        mtx.mmwrite('x.mtx', sp.csc_matrix(np.ones((2, 2), dtype=np.complex128)))
+    assert not os.path.exists('x.mtx')
+
+
+def test_write_all_handles_short_writes():
+    from stellarscope_b200.engine import write_all
+
+    class Short:                                    # an unbuffered sink that takes at most 5 bytes per call
+        def __init__(self):
+            self.got = bytearray()
+
+        def write(self, mv):
+            k = min(5, len(mv))
+            self.got += bytes(mv[:k])
+            return k
+    sink = Short()
+    data = bytes(range(256)) * 3
+    write_all(sink, memoryview(data))
+    assert bytes(sink.got) == data
+    buf = io.BytesIO()
+    write_all(buf, memoryview(data))
+    assert buf.getvalue() == data
+
+    class Stuck:
+        def write(self, mv):
+            return 0
+    with pytest.raises(OSError):
+        write_all(Stuck(), memoryview(b'abc'))
+
+
 def test_golden_files_are_scipy():
     """The committed goldens are what scipy.io.mmwrite (the reference's writer) produces for the committed
     triples (tests/tools/make_golden_mtx.py)."""
@@ -232,3 +268,34 @@ def test_gpu_mtx_csr_and_large_staging(tmp_path):
     mtx.mmwrite(b, m, comment='c')
     with open(a, 'rb') as fa, open(b, 'rb') as fb:
         assert fa.read() == fb.read()
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/stellarscope'), reason='reference checkout not present')
+def test_header_and_metadata_equal_the_real_output_report(tmp_path, monkeypatch):
+    """The real ``Stellarscope.output_report`` (unmodified reference, CPU) writes TE_counts*.mtx; banner, metadata
+    comment (mtx_meta, model.py:1347-1368) and size line of this package's writer must be the same bytes."""
+    import sys
+    from oracle import make_golden, refshim
+    from stellarscope_b200 import model, mtx, synth
+    ref = refshim.load()
+    monkeypatch.setattr(sys, 'argv', ['stellarscope', 'assign', '--pooling_mode', 'individual', 'aln.bam', 'te.gtf'])
+    d = synth.generate(n_cells=5, n_alignments=900, n_loci=60, seed=31, unique_frac=0.1)
+    for extra in (dict(), dict(ignore_umi=True, umi_counts=True), dict(samfile='aln.bam', gtffile='te.gtf')):
+        opts = refshim.RefOpts(reassign_mode=['best_exclude', 'best_average'], pooling_mode='individual',
+                               version='1.4.2', **extra)
+        opts.outfile_path = lambda suffix: str(tmp_path / suffix)
+        st, names = make_golden.make_st(d, opts, False)
+        with refshim.cli_fp_policy():
+            tl, poolinfo = ref._fit_pooling_model(st, opts)
+            ref.Stellarscope.reassign(st, tl)
+            ref.Stellarscope.output_report(st, tl)
+        for i, mode in enumerate(opts.reassign_mode):
+            fn = tmp_path / ('TE_counts.mtx' if i == 0 else f'TE_counts.{mode}.mtx')
+            raw = fn.read_bytes()
+            lines = raw.split(b'\n')
+            n_head = next(k for k, ln in enumerate(lines) if not ln.startswith(b'%')) + 1
+            real_head = b'\n'.join(lines[:n_head]) + b'\n'
+            K, C, nnz = (int(x) for x in lines[n_head - 1].split())
+            field = lines[0].split()[3].decode()
+            assert field == ('real' if (mode == 'best_average' or opts.umi_counts) else 'integer')
+            assert mtx.header(K, C, nnz, field, model._mtx_meta(st, mode)) == real_head, (extra, mode)
