@@ -1,4 +1,5 @@
 // extern "C" boundary (include/stellarscope_b200.h).
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -42,6 +43,14 @@ int ss_create(int device, ss_handle_t* out) {
   if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
     unsigned long long thr = ~0ull;
     cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  if (const char* e = getenv("SS_SMALL_TILE_THR")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= STREAM_SEG_TILES) h->small_tile_thr = v;
+  }
+  if (const char* e = getenv("SS_CLANE_THREADS")) {
+    const int v = atoi(e);
+    if (v == 256 || v == 512) h->clane_threads = v;
   }
   *out = h;
   return SS_OK;

@@ -639,11 +639,15 @@ constexpr int SS_MAX_CLUSTER_TILES = 8;
 constexpr int CLANE_THREADS = SS_CLANE_THREADS;
 constexpr int CLANE_FR = SS_CLANE_FR, CLANE_FC = SS_CLANE_FC;
 
+// THREADS: 512 (one CTA per SM, tiles of up to E_HARD alignments) or 256 (experiment: with SS_SMALL_TILE_THR=1 the
+// cluster segments are cut into E_STREAM tiles, two CTAs of different clusters share an SM and one cluster's barrier
+// / L2 exchange overlaps the other's phase A / B)
+template <int THREADS>
 __global__ void __maxnreg__(SS_CLANE_MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double s_red[64];
   __shared__ double s_dall[2][16];        // [parity][rank]: |delta pi| partial of every CTA of the cluster (pushed)
-  constexpr int THREADS = CLANE_THREADS, FR = CLANE_FR, FC = CLANE_FC;
+  constexpr int FR = CLANE_FR, FC = CLANE_FC;
   constexpr int NW = THREADS / 32;
   const unsigned full = 0xffffffffu;
   cg::cluster_group cluster = cg::this_cluster();
@@ -1671,9 +1675,9 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     size_t smem = 0;
     int threads = CLUSTER_THREADS;
     if (!lnl) {
-      kfn = em_clane_kernel;                       // one cluster barrier per iteration
+      threads = h->clane_threads == 256 ? 256 : CLANE_THREADS;
+      kfn = threads == 256 ? em_clane_kernel<256> : em_clane_kernel<CLANE_THREADS>;   // one cluster barrier per iteration
       smem = h->clu_smem_lane[nt] + 256;
-      threads = CLANE_THREADS;
     } else {
       switch (nt) {
 #define SS_CLU_CASE(N)                               \

@@ -237,11 +237,13 @@ struct StreamGeom {
   int pe, pr, pc, pj;   // padded maxima over the streamed tiles
   int nbuf;             // 2: double buffered, 1: the largest tile leaves no room for a second buffer
 };
+constexpr int STREAM_HDR_BYTES = 256;   // the tile header (HDR_WORDS * 8 = 192 B) travels with the tile
+constexpr int STREAM_DC_INTS = 32;      // class boundaries derived once per tile (lane_tile_compute)
 __host__ __device__ inline size_t stream_buf_bytes(const StreamGeom& g) {
-  return 12 * (size_t)g.pe + 10 * (size_t)g.pr + 6 * (size_t)g.pc + 2 * (size_t)g.pj;
+  return STREAM_HDR_BYTES + 12 * (size_t)g.pe + 10 * (size_t)g.pr + 6 * (size_t)g.pc + 2 * (size_t)g.pj;
 }
 __host__ __device__ inline size_t stream_smem_bytes(const StreamGeom& g) {
-  return (size_t)g.nbuf * stream_buf_bytes(g) + 8 * ((size_t)g.pe + 8) + 8 * (size_t)g.pc + 128;
+  return (size_t)g.nbuf * stream_buf_bytes(g) + 8 * ((size_t)g.pe + 8) + 8 * (size_t)g.pc + 4 * STREAM_DC_INTS + 128;
 }
 
 // double buffered when two buffers + scratch fit `limit` bytes of shared memory
@@ -254,12 +256,14 @@ inline StreamGeom make_stream_geom(const int* gm, size_t limit) {
 }
 
 struct StreamBuf {
+  const long long* hdr;
   const double* q; const double* w; const uint32_t* idx; const int* gcol;
   const uint16_t* rlen; const uint16_t* cptr; const uint16_t* jptr;
 };
 __device__ __forceinline__ StreamBuf carve_stream(unsigned char* base, const StreamGeom& g) {
   StreamBuf b;
   unsigned char* p = base;
+  b.hdr = reinterpret_cast<const long long*>(p);  p += STREAM_HDR_BYTES;
   b.q = reinterpret_cast<const double*>(p);       p += 8 * (size_t)g.pe;
   b.w = reinterpret_cast<const double*>(p);       p += 8 * (size_t)g.pr;
   b.idx = reinterpret_cast<const uint32_t*>(p);   p += 4 * (size_t)g.pe;
@@ -269,10 +273,11 @@ __device__ __forceinline__ StreamBuf carve_stream(unsigned char* base, const Str
   b.jptr = reinterpret_cast<const uint16_t*>(p);
   return b;
 }
-__device__ __forceinline__ void stream_issue_loads(const Layout& L, const int* colmap, const TileView& v,
+__device__ __forceinline__ void stream_issue_loads(const Layout& L, const int* colmap, int t, const TileView& v,
                                                    const StreamBuf& b, uint64_t* bar) {
-  const uint32_t bytes = 12u * v.pe + 10u * v.pr + 6u * v.pc + 2u * v.pj;
+  const uint32_t bytes = 8u * HDR_WORDS + 12u * v.pe + 10u * v.pr + 6u * v.pc + 2u * v.pj;
   mbar_expect_tx(bar, bytes);
+  bulk_g2s((void*)b.hdr, L.tile_hdr + (long long)HDR_WORDS * t, 8u * HDR_WORDS, bar);
   bulk_g2s((void*)b.q, L.e_q + v.eo, 8u * v.pe, bar);
   bulk_g2s((void*)b.idx, L.e_idx + v.eo, 4u * v.pe, bar);
   bulk_g2s((void*)b.w, L.r_w + v.ro, 8u * v.pr, bar);
@@ -306,7 +311,7 @@ __device__ long long g_st_prof[8];
 template <int THREADS, int FR, int FC>
 __device__ __forceinline__ void lane_tile_compute(const long long* __restrict__ hd, const TileView& v, const StreamBuf& b,
                                                   const double* __restrict__ x, double* __restrict__ T, double* xs,
-                                                  double* val) {
+                                                  double* val, int* dc) {
   constexpr int NW = THREADS / 32;
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -314,10 +319,8 @@ __device__ __forceinline__ void lane_tile_compute(const long long* __restrict__ 
   // ---- tile-local x ----
   for (int c = tid; c < v.ncol; c += THREADS) xs[c] = __ldcg(x + b.gcol[c]);
   if (tid == 0) xs[v.ncol] = 0.0;
-  __syncthreads();
-  ST_TICK(1)
-  // ---- phase A: row fragments ----
-  {
+  // ---- lane-group boundaries of the tile: derived once (one thread), read by everybody after the barrier ----
+  if (tid == THREADS - 1) {
     const int rgt4 = (int)hd[H_RGT4], rgt8 = (int)hd[H_RGT8], rgt16 = (int)hd[H_RGT16], rgt32 = (int)hd[H_RGT32];
     const int n_huge = rgt32;
     const int n8 = rgt16 - rgt32, n4 = rgt8 - rgt16, n2 = rgt4 - rgt8, n1 = v.nrows - rgt4;
@@ -329,6 +332,30 @@ __device__ __forceinline__ void lane_tile_compute(const long long* __restrict__ 
     else if (Vc < V4) r_ovf = n_huge + n8 + (Vc - V8) / 4;
     else if (Vc < V2) r_ovf = n_huge + n8 + n4 + (Vc - V4) / 2;
     else r_ovf = n_huge + n8 + n4 + n2 + (Vc - V2);
+    dc[0] = n_huge; dc[1] = n8; dc[2] = n4; dc[3] = n2; dc[4] = V8; dc[5] = V4; dc[6] = V2; dc[7] = Vc; dc[8] = r_ovf;
+    const int b128 = (int)hd[H_CGT128];
+    const int b64 = (int)hd[H_CGT64], b32 = (int)hd[H_CGT32], b16 = (int)hd[H_CGT16], b8 = (int)hd[H_CGT8],
+              b4 = (int)hd[H_CGT4];
+    const int W32 = 32 * (b64 - b128), W16 = W32 + 16 * (b32 - b64), W8 = W16 + 8 * (b16 - b32);
+    const int W4 = W8 + 4 * (b8 - b16), W2 = W4 + 2 * (b4 - b8), W = W2 + (v.ncol - b4);
+    const int Wc = min(W, FC * THREADS);
+    int c_ovf;
+    if (Wc >= W) c_ovf = v.ncol;
+    else if (Wc < W32) c_ovf = b128 + Wc / 32;
+    else if (Wc < W16) c_ovf = b64 + (Wc - W32) / 16;
+    else if (Wc < W8) c_ovf = b32 + (Wc - W16) / 8;
+    else if (Wc < W4) c_ovf = b16 + (Wc - W8) / 4;
+    else if (Wc < W2) c_ovf = b8 + (Wc - W4) / 2;
+    else c_ovf = b4 + (Wc - W2);
+    dc[9] = b128; dc[10] = b64; dc[11] = b32; dc[12] = b16; dc[13] = b8; dc[14] = b4;
+    dc[15] = W32; dc[16] = W16; dc[17] = W8; dc[18] = W4; dc[19] = W2; dc[20] = Wc; dc[21] = c_ovf;
+  }
+  __syncthreads();
+  ST_TICK(1)
+  // ---- phase A: row fragments ----
+  {
+    const int n_huge = dc[0], n8 = dc[1], n4 = dc[2], n2 = dc[3];
+    const int V8 = dc[4], V4 = dc[5], V2 = dc[6], Vc = dc[7], r_ovf = dc[8];
 #pragma unroll
     for (int j = 0; j < FR; ++j) {
       const int vl = tid + j * THREADS;
@@ -389,20 +416,8 @@ __device__ __forceinline__ void lane_tile_compute(const long long* __restrict__ 
   ST_TICK(2)
   // ---- phase B: column fragments -> RED into T ----
   {
-    const int b128 = (int)hd[H_CGT128];
-    const int b64 = (int)hd[H_CGT64], b32 = (int)hd[H_CGT32], b16 = (int)hd[H_CGT16], b8 = (int)hd[H_CGT8],
-              b4 = (int)hd[H_CGT4];
-    const int W32 = 32 * (b64 - b128), W16 = W32 + 16 * (b32 - b64), W8 = W16 + 8 * (b16 - b32);
-    const int W4 = W8 + 4 * (b8 - b16), W2 = W4 + 2 * (b4 - b8), W = W2 + (v.ncol - b4);
-    const int Wc = min(W, FC * THREADS);
-    int c_ovf;
-    if (Wc >= W) c_ovf = v.ncol;
-    else if (Wc < W32) c_ovf = b128 + Wc / 32;
-    else if (Wc < W16) c_ovf = b64 + (Wc - W32) / 16;
-    else if (Wc < W8) c_ovf = b32 + (Wc - W16) / 8;
-    else if (Wc < W4) c_ovf = b16 + (Wc - W8) / 4;
-    else if (Wc < W2) c_ovf = b8 + (Wc - W4) / 2;
-    else c_ovf = b4 + (Wc - W2);
+    const int b128 = dc[9], b64 = dc[10], b32 = dc[11], b16 = dc[12], b8 = dc[13], b4 = dc[14];
+    const int W32 = dc[15], W16 = dc[16], W8 = dc[17], W4 = dc[18], W2 = dc[19], Wc = dc[20], c_ovf = dc[21];
 #pragma unroll
     for (int j = 0; j < FC; ++j) {
       const int vl = tid + j * THREADS;
@@ -451,6 +466,7 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
   const size_t bb = stream_buf_bytes(g);
   double* val = reinterpret_cast<double*>(dsm + (size_t)g.nbuf * bb);
   double* xs = val + g.pe + 8;
+  int* dc = reinterpret_cast<int*>(xs + g.pc);
   auto next_item = [&](int i) {
     while (i < n_items) {
       const int t = tiles ? tiles[i] : i;
@@ -464,7 +480,7 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
   if (cur < n_items && tid == 0) {
     const int t = tiles ? tiles[cur] : cur;
     fence_proxy_async();
-    stream_issue_loads(L, colmap, load_tile_view(L.tile_hdr, t), carve_stream(dsm, g), &bars[0]);
+    stream_issue_loads(L, colmap, t, load_tile_view(L.tile_hdr, t), carve_stream(dsm, g), &bars[0]);
   }
   while (cur < n_items) {
     const int b_cur = g.nbuf == 2 ? (nb & 1) : 0;
@@ -472,11 +488,9 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
     if (g.nbuf == 2 && nxt < n_items && tid == 0) {
       const int t = tiles ? tiles[nxt] : nxt;
       fence_proxy_async();
-      stream_issue_loads(L, colmap, load_tile_view(L.tile_hdr, t), carve_stream(dsm + (size_t)(b_cur ^ 1) * bb, g),
+      stream_issue_loads(L, colmap, t, load_tile_view(L.tile_hdr, t), carve_stream(dsm + (size_t)(b_cur ^ 1) * bb, g),
                          &bars[b_cur ^ 1]);
     }
-    const int t = tiles ? tiles[cur] : cur;
-    const TileView v = load_tile_view(L.tile_hdr, t);
     const StreamBuf b = carve_stream(dsm + (size_t)b_cur * bb, g);
 #ifdef SS_STREAM_PROFILE
     long long c0_ = clock64();
@@ -484,7 +498,8 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
     mbar_wait(&bars[b_cur], uses[b_cur] & 1);
     uses[b_cur]++;
     ST_TICK(0)
-    lane_tile_compute<THREADS, FR, FC>(L.tile_hdr + (long long)HDR_WORDS * t, v, b, x, T, xs, val);
+    const TileView v = load_tile_view(b.hdr, 0);                  // the header arrived with the tile (shared memory)
+    lane_tile_compute<THREADS, FR, FC>(b.hdr, v, b, x, T, xs, val, dc);
     __syncthreads();                                              // buffers, val and xs are free again
 #ifdef SS_STREAM_PROFILE
     c0_ = clock64() - 0;   // (B tail + barrier counted with the next wait)
@@ -493,7 +508,7 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
     if (g.nbuf == 1 && nxt < n_items && tid == 0) {
       const int t2 = tiles ? tiles[nxt] : nxt;
       fence_proxy_async();
-      stream_issue_loads(L, colmap, load_tile_view(L.tile_hdr, t2), carve_stream(dsm, g), &bars[0]);
+      stream_issue_loads(L, colmap, t2, load_tile_view(L.tile_hdr, t2), carve_stream(dsm, g), &bars[0]);
     }
     cur = nxt;
     ++nb;

@@ -49,6 +49,11 @@ struct ss_handle_s {
   size_t max_smem_optin = 0;
   std::string err;
   long long launches = 0;
+  // experiment knobs (environment, read by ss_create): SS_SMALL_TILE_THR = segments with more than this many
+  // E_HARD tiles are cut into E_STREAM tiles (default STREAM_SEG_TILES: only the streamed ones; 1: every multi-tile
+  // segment); SS_CLANE_THREADS = CTA size of the cluster lane kernel (512 | 256)
+  int small_tile_thr = ss::STREAM_SEG_TILES;
+  int clane_threads = 512;
 
   // ---- layout ----
   bool has_layout = false;

@@ -28,6 +28,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import os
+
 import numpy as np
 
 E_HARD = 4096        # hard cap on alignments per tile (shared-memory budget, csrc/ss_common.cuh)
@@ -194,7 +196,8 @@ def build(indptr, indices, scores, row_seg, S, K, e_hard=E_HARD, long_col=32):
     # segments that will be streamed are cut into smaller tiles (csrc/ss_build.cu seg_chunk)
     chunk_small = E_STREAM - maxlen + 1 if (e_hard == E_HARD and maxlen <= E_STREAM // 2) else chunk
     seg_aamb = np.bincount(aseg, weights=alen, minlength=S).astype(np.int64) if len(ar) else np.zeros(S, dtype=np.int64)
-    seg_chunk = np.where(seg_aamb > STREAM_SEG_TILES * chunk, chunk_small, chunk)
+    small_thr = int(os.environ.get('SS_SMALL_TILE_THR', STREAM_SEG_TILES))      # experiment knob, like the device builder
+    seg_chunk = np.where(seg_aamb > small_thr * chunk, chunk_small, chunk)
     tin = o // seg_chunk[aseg] if len(ar) else o
     seg_ntiles = np.zeros(S, dtype=np.int32)
     if len(ar):
