@@ -20,6 +20,7 @@
 #include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -464,7 +465,125 @@ done:
   return result;
 }
 
+/* ---- gather_rows: row-compacted copy of a CSR matrix ---------------------------------------------
+ * A rank of a sharded run fits only the rows of its own models: it cuts them out of the
+ * host matrix before the upload.  numpy would need an index array as long as the result; here every row
+ * (run of consecutive rows) is one memcpy, spread over a few threads without the GIL.
+ *   row_extents(indptr, rows, out_ptr) -> total      out_ptr int64[n+1] = prefix sums of the rows' lengths
+ *   gather_rows(indptr, indices, data, rows, out_ptr, out_idx, out_dat)
+ * indptr / indices: int32 or int64 buffers; data: any item size; rows: int64, any order. */
+static inline int64_t ld_ix(const char* p, Py_ssize_t size, int64_t i) {
+  return size == 4 ? (int64_t)((const int32_t*)p)[i] : ((const int64_t*)p)[i];
+}
+typedef struct {
+  const char *ip, *idx, *dat;
+  Py_ssize_t ip_size, idx_size, dat_size;
+  const int64_t *rows, *optr;
+  char *oidx, *odat;
+  Py_ssize_t r0, r1;
+} gather_t;
+static void* gather_main(void* arg) {
+  gather_t* g = (gather_t*)arg;
+  Py_ssize_t r = g->r0;
+  while (r < g->r1) {
+    Py_ssize_t e = r + 1;
+    while (e < g->r1 && g->rows[e] == g->rows[e - 1] + 1) ++e;      /* run of consecutive rows: one copy */
+    const int64_t a = ld_ix(g->ip, g->ip_size, g->rows[r]), b = ld_ix(g->ip, g->ip_size, g->rows[e - 1] + 1);
+    const int64_t o = g->optr[r];
+    memcpy(g->oidx + o * g->idx_size, g->idx + a * g->idx_size, (size_t)((b - a) * g->idx_size));
+    memcpy(g->odat + o * g->dat_size, g->dat + a * g->dat_size, (size_t)((b - a) * g->dat_size));
+    r = e;
+  }
+  return NULL;
+}
+static int host_threads(void) {
+  long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+  int nt = (int)(ncpu < 1 ? 1 : (ncpu > 16 ? 16 : ncpu));
+  const char* e = getenv("SS_HOST_THREADS");
+  if (e) nt = atoi(e) < 1 ? 1 : (atoi(e) > 16 ? 16 : atoi(e));
+  return nt;
+}
+static PyObject* row_extents(PyObject* self, PyObject* args) {
+  Py_buffer ip, rows, optr;
+  if (!PyArg_ParseTuple(args, "y*y*w*", &ip, &rows, &optr)) return NULL;
+  PyObject* result = NULL;
+  const Py_ssize_t n = rows.len / 8, nrow = ip.len / ip.itemsize - 1;
+  if ((ip.itemsize != 4 && ip.itemsize != 8) || rows.itemsize != 8 || optr.itemsize != 8 || optr.len / 8 != n + 1) {
+    PyErr_SetString(PyExc_TypeError, "row_extents: indptr int32/int64, rows int64[n], out_ptr int64[n+1]");
+    goto done;
+  }
+  {
+    const int64_t* rw = (const int64_t*)rows.buf;
+    int64_t* o = (int64_t*)optr.buf;
+    int64_t acc = 0;
+    for (Py_ssize_t i = 0; i < n; ++i) {
+      if (rw[i] < 0 || rw[i] >= nrow) {
+        PyErr_Format(PyExc_IndexError, "row id %lld outside [0, %zd)", (long long)rw[i], nrow);
+        goto done;
+      }
+      o[i] = acc;
+      acc += ld_ix((const char*)ip.buf, ip.itemsize, rw[i] + 1) - ld_ix((const char*)ip.buf, ip.itemsize, rw[i]);
+    }
+    o[n] = acc;
+    result = PyLong_FromLongLong(acc);
+  }
+done:
+  PyBuffer_Release(&ip); PyBuffer_Release(&rows); PyBuffer_Release(&optr);
+  return result;
+}
+static PyObject* gather_rows(PyObject* self, PyObject* args) {
+  Py_buffer ip, idx, dat, rows, optr, oidx, odat;
+  if (!PyArg_ParseTuple(args, "y*y*y*y*y*w*w*", &ip, &idx, &dat, &rows, &optr, &oidx, &odat)) return NULL;
+  PyObject* result = NULL;
+  const Py_ssize_t n = rows.len / 8;
+  if ((ip.itemsize != 4 && ip.itemsize != 8) || rows.itemsize != 8 || optr.itemsize != 8 || optr.len / 8 != n + 1 ||
+      oidx.itemsize != idx.itemsize || odat.itemsize != dat.itemsize) {
+    PyErr_SetString(PyExc_TypeError, "gather_rows: mismatching buffers");
+    goto done;
+  }
+  {
+    const int64_t total = ((const int64_t*)optr.buf)[n];
+    if (oidx.len / oidx.itemsize < total || odat.len / odat.itemsize < total) {
+      PyErr_SetString(PyExc_ValueError, "gather_rows: output buffers too small");
+      goto done;
+    }
+    int nt = host_threads();
+    if (total < 1000000) nt = 1;
+    gather_t g[16];
+    pthread_t th[16];
+    const int64_t* op = (const int64_t*)optr.buf;
+    Py_ssize_t r = 0;
+    for (int i = 0; i < nt; ++i) {
+      g[i].ip = (const char*)ip.buf; g[i].idx = (const char*)idx.buf; g[i].dat = (const char*)dat.buf;
+      g[i].ip_size = ip.itemsize; g[i].idx_size = idx.itemsize; g[i].dat_size = dat.itemsize;
+      g[i].rows = (const int64_t*)rows.buf; g[i].optr = op; g[i].oidx = (char*)oidx.buf; g[i].odat = (char*)odat.buf;
+      g[i].r0 = r;
+      const int64_t target = total / nt * (i + 1);
+      while (r < n && (i == nt - 1 || op[r] < target)) ++r;
+      g[i].r1 = r;
+    }
+    Py_BEGIN_ALLOW_THREADS
+    int started = 0;
+    for (int i = 1; i < nt; ++i) {
+      if (pthread_create(&th[i], NULL, gather_main, &g[i]) != 0) break;
+      ++started;
+    }
+    gather_main(&g[0]);
+    for (int i = 1; i <= started; ++i) pthread_join(th[i], NULL);
+    for (int i = started + 1; i < nt; ++i) gather_main(&g[i]);      /* threads that could not be started */
+    Py_END_ALLOW_THREADS
+    result = PyLong_FromLongLong(total);
+  }
+done:
+  PyBuffer_Release(&ip); PyBuffer_Release(&idx); PyBuffer_Release(&dat); PyBuffer_Release(&rows);
+  PyBuffer_Release(&optr); PyBuffer_Release(&oidx); PyBuffer_Release(&odat);
+  return result;
+}
+
 static PyMethodDef methods[] = {
+    {"row_extents", row_extents, METH_VARARGS, "row_extents(indptr, rows, out_ptr): prefix sums of the lengths of the given rows"},
+    {"gather_rows", gather_rows, METH_VARARGS,
+     "gather_rows(indptr, indices, data, rows, out_ptr, out_idx, out_dat): row-compacted copy of a CSR matrix"},
     {"row_labels", row_labels, METH_VARARGS,
      "row_labels(read_index, label_of_read, position_of_label, out, ids): out[row] = position (or running id) of the read's label"},
     {"code_mappings", code_mappings, METH_VARARGS,

@@ -47,3 +47,17 @@ def code_mappings(mappings, read_index, feat_index, read, feat, alnscore, alnlen
 def row_labels(read_index, label_of_read, position_of_label, out, ids=None):
     """out[read_index[q]] = position_of_label.get(label_of_read[q], -1); with ``ids`` (a dict) running ids in row order."""
     return load().row_labels(read_index, label_of_read, position_of_label, out, ids)
+
+
+def gather_rows(indptr, indices, data, rows):
+    """Row-compacted CSR ``(ptr int64[n+1], idx, dat)`` of the given rows (any order) of a host CSR matrix:
+    one memcpy per run of consecutive rows, a few threads, no index array."""
+    import numpy as np
+    indptr, indices, data = (np.ascontiguousarray(a) for a in (indptr, indices, data))
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    ptr = np.empty(len(rows) + 1, dtype=np.int64)
+    total = load().row_extents(indptr, rows, ptr)
+    idx = np.empty(total, dtype=indices.dtype)
+    dat = np.empty(total, dtype=data.dtype)
+    load().gather_rows(indptr, indices, data, rows, ptr, idx, dat)
+    return ptr, idx, dat

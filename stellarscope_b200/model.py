@@ -59,7 +59,7 @@ class TelescopeLikelihood(object):
     ]
 
     def __init__(self, score_matrix, opts, row_segment=None, n_segments=None, device=None,
-                 tie_tol=TIE_TOL_DEFAULT, shard=None, device_matrix=None):
+                 tie_tol=TIE_TOL_DEFAULT, shard=None, device_matrix=None, row_ids=None, group=None):
         self.opts = opts
         self.epsilon = opts.em_epsilon
         self.max_iter = opts.max_iter
@@ -72,6 +72,13 @@ class TelescopeLikelihood(object):
         m = score_matrix if scipy.sparse.isspmatrix_csr(score_matrix) else scipy.sparse.csr_matrix(score_matrix)
         self.N, self.K = m.shape
         self.scale_factor = 100.
+        # ``row_ids`` (sharded runs): ascending global ids of the rows THIS rank holds.  The object
+        # keeps the reference's global shape (N, K, raw_scores); the device only ever sees the rank's rows --
+        # they are cut out of the host matrix before the upload and ``row_segment`` is indexed by local row.
+        self._row_ids = None if row_ids is None else np.ascontiguousarray(row_ids, dtype=np.int64)
+        self._group = group
+        if m.nnz > 2 ** 31 - 1:
+            raise OverflowError(f'{m.nnz} alignments: the device layout uses int32 row pointers (at most 2^31 - 1)')
         self._engine = Engine(device) if shard is not None else Engine.acquire(device)
         if shard is not None:
             # ONE model whose rows are spread over ranks: (rank, world, process group[, peers])
@@ -82,6 +89,9 @@ class TelescopeLikelihood(object):
                 raise StellarscopeError('alignment scores outside [0, 65535] are not supported (uint16, model.py:964)')
             if device_matrix is not None and attempt == 0:
                 self._engine.set_matrix_device(*device_matrix, self.K)         # canonical copy of another model object
+            elif self._row_ids is not None:
+                from . import hostutil
+                self._engine.set_matrix(*hostutil.gather_rows(m.indptr, m.indices, m.data, self._row_ids), self.K)
             else:
                 self._engine.set_matrix(m.indptr, m.indices, m.data, self.K)    # H2D in flight ...
             if attempt == 0:
@@ -89,7 +99,7 @@ class TelescopeLikelihood(object):
                     row_segment, self.segment_keys = row_segment()
                     n_segments = len(self.segment_keys)
                 elif row_segment is None:
-                    row_segment = np.zeros(self.N, dtype=np.int32)
+                    row_segment = np.zeros(self._engine.N, dtype=np.int32)
                     n_segments = 1
                 self.row_segment = np.ascontiguousarray(row_segment, dtype=np.int32)
                 self.n_segments = int(n_segments)
@@ -168,6 +178,9 @@ class TelescopeLikelihood(object):
             if self.segment_fitinfo is None:
                 return None
             zd = to_host(self._z_device())
+            if self._row_ids is not None:
+                # this rank's rows only (the other ranks' rows are zero here, like the rows of no model)
+                zd = self._scatter_entries(zd)
             m = csr_matrix_plus((zd, self.raw_scores.indices.copy(), self.raw_scores.indptr.copy()),
                                 shape=self.raw_scores.shape)
             self._z = m
@@ -176,6 +189,34 @@ class TelescopeLikelihood(object):
     @z.setter
     def z(self, value):
         self._z = value
+
+    def _scatter_entries(self, local_vals):
+        """Per-alignment values of the local rows -> array over all alignments of the global matrix (0 elsewhere)."""
+        indptr = self.raw_scores.indptr
+        rows = self._row_ids
+        lens = (indptr[rows + 1] - indptr[rows]).astype(np.int64)
+        lptr = np.zeros(len(rows) + 1, dtype=np.int64)
+        np.cumsum(lens, out=lptr[1:])
+        pos = np.repeat(indptr[rows].astype(np.int64) - lptr[:-1], lens) + np.arange(lptr[-1])
+        out = np.zeros(self.raw_scores.nnz, dtype=local_vals.dtype)
+        out[pos] = local_vals[:lptr[-1]]
+        return out
+
+    def _global_indptr(self, local_ptr, dtype):
+        """Row pointers over all N rows from the row pointers over this rank's rows (the other rows are empty)."""
+        if self._row_ids is None:
+            return local_ptr.astype(dtype, copy=False)
+        lens = np.zeros(self.N, dtype=np.int64)
+        lens[self._row_ids] = np.diff(local_ptr)
+        out = np.zeros(self.N + 1, dtype=np.int64)
+        np.cumsum(lens, out=out[1:])
+        return out.astype(dtype, copy=False)
+
+    def _sharded(self):
+        if self._row_ids is None:
+            return False
+        world, _ = _dist_info()
+        return world > 1
 
     def _z_device(self):
         if self._z_dev is None:
@@ -248,43 +289,64 @@ class TelescopeLikelihood(object):
                 raise StellarscopeError('reassign_mat was not set.')     # model.py:504-505 (no z)
             z = self._z_device()
         flag, nbest, info = self._engine.reassign(mode, z, thresh if thresh is not None else 0.0, self.tie_tol)
+        if self._sharded():
+            # every row lives on exactly one rank (parallel.plan_local_rows): the counters and the tie histogram of
+            # the whole matrix are the sums over the ranks
+            from . import parallel
+            info = parallel.allreduce_sum_host(np.asarray(info, dtype=np.int64), self._group)
         rinfo = ReassignInfo(mode)
         rinfo.assigned, rinfo.ambiguous, rinfo.unaligned = int(info[0]), int(info[1]), int(info[2])
         if mode in ('best_exclude', 'best_random', 'best_average', 'initial_random'):
             rinfo.ambigous_dist = counter_from_hist(info[4:])
+        indptr_dtype = self.raw_scores.indptr.dtype
         if mode not in ('best_random', 'initial_random'):
             # the selection comes back as CSR straight from the device (no pass over all alignments on the host)
             ptr, idx, frac = self._engine.reassign_csr(flag, nbest, fractions=(mode == 'best_average'))
             data = frac if mode == 'best_average' else np.ones(len(idx), dtype=np.int8)
-            mat = csr_matrix_plus((data, idx, ptr.astype(self.raw_scores.indptr.dtype, copy=False)),
-                                  shape=self.raw_scores.shape)
+            mat = csr_matrix_plus((data, idx, self._global_indptr(ptr, indptr_dtype)), shape=self.raw_scores.shape)
             if mode != 'best_average':
                 # lets count_by_cell aggregate without uploading the matrix again (while the engine still holds this matrix)
-                mat._ss_dev = (self._engine, flag, self._engine._keep.get('row_ptr'))
+                mat._ss_dev = (self._engine, flag, self._engine._keep.get('row_ptr'), self._row_ids)
             return mat, rinfo
         flag = to_host(flag).view(np.bool_)                     # 0 / 1 bytes
-        indptr, indices = self.raw_scores.indptr, self.raw_scores.indices
-        row = np.repeat(np.arange(self.N, dtype=np.int64), np.diff(indptr))
-        flag = _replay_random_choice(flag, row, to_host(nbest), self.opts.rng)
+        nbest = to_host(nbest)
+        if self._row_ids is None:
+            lptr, lidx = self.raw_scores.indptr.astype(np.int64), self.raw_scores.indices
+        else:
+            lptr = to_host(self._engine._keep['row_ptr']).astype(np.int64)
+            lidx = to_host(self._engine._keep['col_idx'])
+        n_local = len(lptr) - 1
+        row = np.repeat(np.arange(n_local, dtype=np.int64), np.diff(lptr))
+        tied_rows = np.flatnonzero(nbest > 1)
+        if self._sharded():
+            # one stream of draws for the whole matrix, in global row order, on every rank (the reference draws
+            # row by row, sparse_plus.py:233-238): gather the tie sets, draw them all, keep the own rows' picks
+            from . import parallel
+            g = parallel.gather_concat({'row': self._row_ids[tied_rows], 'n': nbest[tied_rows].astype(np.int64)},
+                                       self._group)
+            order = np.argsort(g['row'], kind='stable')
+            picks_all = self.opts.rng.integers(0, g['n'][order]) if len(order) else np.zeros(0, dtype=np.int64)
+            picks = picks_all[np.searchsorted(g['row'][order], self._row_ids[tied_rows])]
+        else:
+            picks = self.opts.rng.integers(0, nbest[tied_rows]) if len(tied_rows) else np.zeros(0, dtype=np.int64)
+        flag = _apply_random_choice(flag, row, nbest, tied_rows, picks)
         keep_rows = row[flag]
-        ptr = np.zeros(self.N + 1, dtype=indptr.dtype)
-        np.cumsum(np.bincount(keep_rows, minlength=self.N), out=ptr[1:])
+        ptr = np.zeros(n_local + 1, dtype=np.int64)
+        np.cumsum(np.bincount(keep_rows, minlength=n_local), out=ptr[1:])
         data = np.ones(len(keep_rows), dtype=np.int8)
-        mat = csr_matrix_plus((data, indices[flag], ptr), shape=self.raw_scores.shape)
+        mat = csr_matrix_plus((data, lidx[flag], self._global_indptr(ptr, indptr_dtype)), shape=self.raw_scores.shape)
         return mat, rinfo
 
 
-def _replay_random_choice(flag, row, nbest, rng):
+def _apply_random_choice(flag, row, nbest, tied_rows, picks):
     """``choose_random(1, rng)`` (sparse_plus.py:231-240) on the tie sets the device
     found: for every row with more than one tied-best alignment, in row order,
     the reference draws ``rng.choice(range(start, end))``; numpy produces the
     same stream for one vectorised ``rng.integers(0, n)`` call (checked in
-    tests/test_oracle.py), so the draws are replayed on the host and applied
-    as a mask."""
-    tied_rows = np.flatnonzero(nbest > 1)
+    tests/test_oracle.py), so the draws (``picks``, one per row of ``tied_rows``) are made on the host and
+    applied as a mask."""
     if len(tied_rows) == 0:
         return flag
-    picks = rng.integers(0, nbest[tied_rows])
     pos = np.flatnonzero(flag)                 # tied-best alignments, CSR order
     prow = row[pos]
     start = np.zeros(len(nbest) + 1, dtype=np.int64)
@@ -294,6 +356,14 @@ def _replay_random_choice(flag, row, nbest, rng):
     out[pos[in_tied]] = False
     out[pos[start[tied_rows] + picks]] = True
     return out
+
+
+def _replay_random_choice(flag, row, nbest, rng):
+    """Single-process form: draws and applies (kept for the tests of the draw order)."""
+    tied_rows = np.flatnonzero(nbest > 1)
+    if len(tied_rows) == 0:
+        return flag
+    return _apply_random_choice(flag, row, nbest, tied_rows, rng.integers(0, nbest[tied_rows]))
 
 
 def _em_wrapper(tl: TelescopeLikelihood):
@@ -423,16 +493,16 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
             # are exchanged once per iteration.  Rows of other ranks belong to no local
             # model, so z -- and the counts derived from it -- are rank-local and add up over ranks.
             from . import parallel
-            import torch.distributed as dist
             m = _canonical_csr(fullmat)
-            seg = np.full(m.shape[0], -1, dtype=np.int32)
             if getattr(opts, 'umi_counts', False):
                 # distinct UMIs are counted per cell: all reads of a cell on one rank
-                seg[parallel.model_cell_block(np.diff(m.indptr), np.arange(m.shape[0]), _row_cells(st), rank, world)] = 0
+                rows = parallel.model_cell_block(np.diff(m.indptr), np.arange(m.shape[0]), _row_cells(st), rank, world)
             else:
                 r0, r1 = parallel.row_block(m.indptr, rank, world)
-                seg[r0:r1] = 0
-            ret_model = TelescopeLikelihood(m, opts, row_segment=seg, n_segments=1,
+                rows = np.arange(r0, r1, dtype=np.int64)
+            # the rank uploads ITS block of rows only
+            ret_model = TelescopeLikelihood(m, opts, row_segment=np.zeros(len(rows), dtype=np.int32), n_segments=1,
+                                            row_ids=rows,
                                             shard=(rank, world, None, getattr(opts, 'peer_exchange', True)))
         else:
             ret_model = TelescopeLikelihood(fullmat, opts)
@@ -457,55 +527,68 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
         # the data path; every rank keeps the global row numbering, rows of other ranks' models are
         # simply not fitted here
         from . import parallel
-        import torch.distributed as dist
         row_segment, keys = pooling_row_segments(st, opts)
         m = _canonical_csr(fullmat)
         # a model much larger than a rank's fair share (a dominant cell type on 8 GPUs) cannot be balanced by packing
         # whole models: such WIDE models are fitted by all ranks together, rows cut into blocks like pseudobulk
         # opts.wide_models: None (default: pack whole models), 'auto' (parallel.wide_models) or a list of model indices;
         # opts.wide_model_cost: lockstep overhead of one wide model in alignments of single-GPU work
-        shards, _, wide = parallel.shard_models(m.indptr, row_segment, len(keys), world,
-                                                wide=getattr(opts, 'wide_models', None) or [],
-                                                wide_cost=getattr(opts, 'wide_model_cost', 2_000_000))
-        mine = shards[rank]
-        remap = np.full(len(keys) + 1, -1, dtype=np.int32)
-        remap[mine] = np.arange(len(mine), dtype=np.int32)
-        local_seg = np.where(row_segment >= 0, remap[np.maximum(row_segment, 0)], -1).astype(np.int32)
-        ret_model = TelescopeLikelihood(m, opts, row_segment=local_seg, n_segments=len(mine))
+        umi_counts = bool(getattr(opts, 'umi_counts', False))
+        loose = bool((row_segment < 0).any())
+        row_cell = _row_cells(st) if (loose or (umi_counts and getattr(opts, 'wide_models', None))) else None
+        plan = parallel.plan_local_rows(m.indptr, row_segment, len(keys), world, rank,
+                                        wide=getattr(opts, 'wide_models', None) or [],
+                                        wide_cost=getattr(opts, 'wide_model_cost', 2_000_000),
+                                        row_cell=row_cell, cells_whole=umi_counts)
+        mine, wide, rows = plan['mine'], plan['wide'], plan['rows']
+        # every rank cuts ITS rows out of the host matrix and uploads only them (1/world of the H2D traffic)
+        ret_model = TelescopeLikelihood(m, opts, row_segment=plan['local_seg'], n_segments=len(mine), row_ids=rows)
         ret_model.model_ids = mine
         local = ret_model.fit_segments()
-        gathered = [None] * world
-        dist.all_gather_object(gathered, (np.asarray(mine), local._res, local._itime))
-        fields = ('iters', 'flags', 'lnl', 'nobs', 'nfeats', 'diffs')
-        parts = [(np.asarray(g[0], dtype=np.int64), g[1]) for g in gathered]
-        itime = max(g[2] for g in gathered)
+        # per-model records of all ranks: fixed-width arrays through all_gather_into_tensor (no pickling; the
+        # per-iteration traces stay on the rank that fitted the model unless opts.gather_traces is set)
+        lr = local._res
+        rec = np.stack([np.asarray(mine, dtype=np.float64)] +
+                       [np.asarray(lr[k], dtype=np.float64) for k in ('iters', 'flags', 'nobs', 'nfeats', 'lnl')], axis=1) \
+            if len(mine) else np.zeros((0, 6))
+        payload = {'rec': rec}
+        want_traces = bool(getattr(opts, 'gather_traces', False))
+        if want_traces:
+            payload['diffs'] = (np.asarray(lr['diffs']).reshape(len(mine), -1) if len(mine)
+                                else np.zeros((0, ret_model.max_iter)))
+        g = parallel.gather_concat(payload)
+        ids = g['rec'][:, 0].astype(np.int64)
+        res = dict(iters=g['rec'][:, 1].astype(np.int32), flags=g['rec'][:, 2].astype(np.int32),
+                   nobs=g['rec'][:, 3].astype(np.int32), nfeats=g['rec'][:, 4].astype(np.int32), lnl=g['rec'][:, 5])
+        my0 = int(g['counts'][:rank].sum())
+        res['diffs'] = g['diffs'] if want_traces else _ShardedTrace(lr.get('diffs'), my0, len(mine), len(ids),
+                                                                   ret_model.max_iter)
+        itime = float(parallel.allreduce_sum_host(np.array([local._itime]))[0]) / world
+        parts_ids, parts_res = [ids], [res]
         if len(wide):
-            lens = np.diff(m.indptr)
             eng = ret_model._engine
             dev_matrix = tuple(eng._keep[k] for k in ('row_ptr', 'col_idx', 'score'))
             z_all = ret_model._z_device()
-            row_cell = _row_cells(st) if getattr(opts, 'umi_counts', False) else None
-            for w in wide:
-                rows_w = np.flatnonzero(row_segment == w)
-                if row_cell is None:
-                    rows_w = parallel.model_row_block(lens, rows_w, rank, world)
-                else:                                       # per (cell, UMI) counting: whole cells per rank
-                    rows_w = parallel.model_cell_block(lens, rows_w, row_cell, rank, world)
-                seg_w = np.full(m.shape[0], -1, dtype=np.int32)
-                seg_w[rows_w] = 0
+            for w, mask in zip(wide, plan['wide_local']):
+                seg_w = np.where(mask, 0, -1).astype(np.int32)
                 tw = TelescopeLikelihood(m, opts, row_segment=seg_w, n_segments=1, device_matrix=dev_matrix,
-                                         shard=(rank, world, None, getattr(opts, 'peer_exchange', True)))
+                                         row_ids=rows, shard=(rank, world, None, getattr(opts, 'peer_exchange', True)))
                 info_w = tw.fit_segments()                  # the same record on every rank
                 z_all += tw._z_device()                     # disjoint rows: the rank-local z of the wide model
-                parts.append((np.array([w], dtype=np.int64), info_w._res))
+                rw = dict(info_w._res)
+                rw['diffs'] = np.asarray(rw['diffs']).reshape(1, -1)
+                parts_ids.append(np.array([w], dtype=np.int64))
+                parts_res.append(rw)
                 itime = max(itime, info_w._itime)
                 ret_model.fit_seconds_wide = getattr(ret_model, 'fit_seconds_wide', 0.0) + (tw.fit_seconds or 0.0)
                 tw._engine.sync_ranks()
                 tw.close()
             ret_model.wide_model_ids = wide
         # concatenate the per-rank result arrays; order[i] = row of model i in the concatenation
-        ids = np.concatenate([p[0] for p in parts])
-        res = {k: np.concatenate([np.asarray(p[1][k]) for p in parts]) for k in fields}
+        ids = np.concatenate(parts_ids)
+        fields = ('iters', 'flags', 'lnl', 'nobs', 'nfeats')
+        res = {k: np.concatenate([np.asarray(p[k]) for p in parts_res]) for k in fields}
+        res['diffs'] = parts_res[0]['diffs'] if len(parts_res) == 1 else _StackedTrace([p['diffs'] for p in parts_res])
         order = np.empty(len(keys), dtype=np.int64)
         order[ids] = np.arange(len(ids))
         infos = SegmentFitInfos(res, ret_model.epsilon, ret_model.max_iter, itime, keys=keys, order=order)
@@ -513,6 +596,39 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
     lg.info(f'        ...{len(infos)} models fitted')
     ret_model.lnl = poolinfo.total_lnl                      # model.py:803
     return ret_model, poolinfo
+
+
+class _ShardedTrace:
+    """Row j of the gathered per-model traces: the |delta pi| trace of a model fitted on THIS rank (rows
+    ``my0 .. my0 + n_mine`` of the gathered order, read lazily from the device), NaN for the models of other
+    ranks (their traces stay where they were computed; ``opts.gather_traces = True`` ships them)."""
+
+    def __init__(self, local, my0, n_mine, n_all, max_iter):
+        self._local, self._my0, self._n, self._all, self._mi = local, my0, n_mine, n_all, max_iter
+
+    def __len__(self):
+        return self._all
+
+    def __getitem__(self, j):
+        j = int(j)
+        if self._my0 <= j < self._my0 + self._n and self._local is not None:
+            return self._local[j - self._my0]
+        return np.full(self._mi, np.nan)
+
+
+class _StackedTrace:
+    """Row-wise concatenation of trace blocks (each indexable by row)."""
+
+    def __init__(self, blocks):
+        self._blocks = blocks
+        self._starts = np.cumsum([0] + [len(b) for b in blocks])
+
+    def __len__(self):
+        return int(self._starts[-1])
+
+    def __getitem__(self, j):
+        b = int(np.searchsorted(self._starts, int(j), side='right')) - 1
+        return self._blocks[b][int(j) - int(self._starts[b])]
 
 
 def _dist_info():
@@ -612,19 +728,16 @@ def count_matrices(st, tl: TelescopeLikelihood):
         remat = st.reassignments[_rmode]
         cm = remat.count_by_cell(row_cell, numbc, row_umi=row_umi, engine=tl._engine)
         if world > 1:
-            cm.__dict__.pop('_ss_dev_coo', None)        # device triples of this rank's part only: not to be pickled
-            # every rank holds the counts of its own models' rows (disjoint): add them up.  The modes
-            # that do not use z (initial_*, total_hits) are identical on every rank.
-            import torch.distributed as dist
-            parts = [None] * world
-            dist.all_gather_object(parts, cm)
-            if _rmode in ('initial_unique', 'initial_random', 'total_hits'):
-                cm = parts[0]
-            else:
-                cm = parts[0]
-                for pm in parts[1:]:
-                    cm = cm + pm
-                cm = scipy.sparse.csr_matrix(cm)
+            cm.__dict__.pop('_ss_dev_coo', None)        # device triples of this rank's part only
+            # every rank holds the counts of its own rows (a partition of all rows, parallel.plan_local_rows): the
+            # COO triples of all ranks are concatenated -- tensors through all_gather_into_tensor, no pickled
+            # matrices -- and entries of the same (locus, cell) add up (a cell cut across ranks: pseudobulk blocks)
+            from . import parallel
+            coo = cm.tocoo()
+            g = parallel.gather_concat({'r': coo.row.astype(np.int32), 'c': coo.col.astype(np.int32),
+                                        'v': coo.data.astype(np.float64)})
+            merged = scipy.sparse.coo_matrix((g['v'], (g['r'], g['c'])), shape=cm.shape).tocsc()    # sums duplicates
+            cm = merged.astype(cm.dtype)
         out[_rmode] = cm
         if out[_rmode].shape != (numft, numbc):
             raise StellarscopeError(f'Incompatible shapes: {out[_rmode].shape} != {(numft, numbc)}')

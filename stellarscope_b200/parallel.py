@@ -189,3 +189,122 @@ def row_block(indptr, rank, world):
     bounds[0], bounds[-1] = 0, N
     bounds = np.maximum.accumulate(np.minimum(bounds, N))
     return int(bounds[rank]), int(bounds[rank + 1])
+
+
+# ---------------------------------------------------------------------------
+# Rank-local rows of a sharded run and the gathers of its results
+# ---------------------------------------------------------------------------
+def plan_local_rows(indptr, row_segment, n_segments, world, rank, wide=None, wide_cost=2_000_000, row_cell=None,
+                    cells_whole=False):
+    """Which rows this rank holds when the models of a pooling mode are sharded over ``world`` ranks.
+
+    Every row of the matrix goes to exactly ONE rank, so that whatever is computed per row (z, the reassignment
+    matrices, the per-cell counts, the ``ReassignInfo`` counters) adds up over the ranks to the single-GPU result:
+
+    * rows of a packed model -> the rank the model was packed onto (LPT, ``shard_models``);
+    * rows of a WIDE model -> cut into ``world`` blocks of about equal alignment count (whole cells per block
+      with ``cells_whole``, i.e. ``--umi_counts``);
+    * rows of no model (barcodes without a cell type, UMI-dropped rows: never fitted, but still counted by the
+      modes that do not use z -- model.py:468-502) -> spread by cell (``row_cell``) or, without it, in
+      ``world`` contiguous blocks.
+
+    Returns a dict: ``rows`` (ascending global row ids of this rank, int64), ``local_seg`` (int32 per local row:
+    index into ``mine`` or -1), ``mine`` (global ids of the models packed onto this rank), ``wide`` (global ids of
+    the wide models), ``wide_local`` (per wide model: bool mask over the LOCAL rows = this rank's block),
+    ``seg_A`` (alignments per model)."""
+    indptr = np.asarray(indptr)
+    row_segment = np.asarray(row_segment)
+    N = len(row_segment)
+    shards, seg_A, wide_ids = shard_models(indptr, row_segment, n_segments, world,
+                                           wide=wide if wide is not None else [], wide_cost=wide_cost)
+    mine = np.asarray(shards[rank], dtype=np.int64)
+    model_rank = np.full(n_segments + 1, -1, dtype=np.int32)
+    for r, b in enumerate(shards):
+        model_rank[b] = r
+    owner = model_rank[np.where(row_segment >= 0, row_segment, n_segments)]      # -1: wide model or no model
+    lens = None
+    wide_rows = []
+    for w in wide_ids:
+        rows_w = np.flatnonzero(row_segment == w)
+        if lens is None:
+            lens = np.diff(indptr).astype(np.int64)
+        if cells_whole and row_cell is not None:
+            blk = model_cell_block(lens, rows_w, row_cell, rank, world)
+        else:
+            blk = model_row_block(lens, rows_w, rank, world)
+        wide_rows.append(blk)
+        owner[rows_w] = -2                                   # not "no model"
+        owner[blk] = rank
+    loose = np.flatnonzero(owner == -1)
+    if len(loose):
+        if row_cell is not None:
+            c = np.asarray(row_cell)[loose]
+            owner[loose] = np.where(c >= 0, c % world, 0).astype(np.int32)
+        else:
+            owner[loose] = np.minimum(world - 1, (np.arange(len(loose), dtype=np.int64) * world) // len(loose))
+    rows = np.flatnonzero(owner == rank).astype(np.int64)
+    remap = np.full(n_segments + 1, -1, dtype=np.int32)
+    remap[mine] = np.arange(len(mine), dtype=np.int32)
+    seg_rows = row_segment[rows]
+    local_seg = remap[np.where(seg_rows >= 0, seg_rows, n_segments)].astype(np.int32)
+    wide_local = []
+    for blk in wide_rows:
+        m = np.zeros(len(rows), dtype=bool)
+        m[np.searchsorted(rows, blk)] = True
+        wide_local.append(m)
+    return dict(rows=rows, local_seg=local_seg, mine=mine, wide=np.asarray(wide_ids, dtype=np.int64),
+                wide_local=wide_local, seg_A=seg_A)
+
+
+def _comm_device(group=None):
+    """Device the collectives of ``group`` take their tensors on (NCCL: the current CUDA device; gloo: the host)."""
+    import torch
+    import torch.distributed as dist
+    if dist.get_backend(group) == 'nccl':
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device('cpu')
+
+
+def gather_concat(arrays, group=None):
+    """All-gather of variable-length 1-D (or row-wise 2-D) numpy arrays: every rank gets, per name, the
+    concatenation over the ranks in rank order, plus ``counts`` (rows contributed by every rank).  All arrays of
+    one call have the same number of rows on a rank.  The payload travels as tensors (``all_gather_into_tensor``
+    of buffers padded to the largest contribution) -- no pickling (results of 10^5 models / 10^8 count entries)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    names = list(arrays)
+    n = len(arrays[names[0]]) if names else 0
+    dev = _comm_device(group)
+    cnt = torch.zeros(world, dtype=torch.int64, device=dev)
+    mine = torch.tensor([n], dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(cnt, mine, group=group)
+    counts = cnt.cpu().numpy()
+    nmax = int(counts.max()) if world else 0
+    out = {}
+    for k in names:
+        a = np.ascontiguousarray(arrays[k])
+        if len(a) != n:
+            raise ValueError('gather_concat: arrays of one call must have the same length')
+        tail = tuple(a.shape[1:])
+        width = int(np.prod(tail, dtype=np.int64)) * a.dtype.itemsize       # bytes per row: travels as uint8
+        buf = torch.zeros(max(nmax * width, 1), dtype=torch.uint8, device=dev)
+        if n:
+            buf[:n * width].copy_(torch.from_numpy(a.reshape(-1).view(np.uint8)))
+        allb = torch.empty(world * max(nmax * width, 1), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allb, buf, group=group)
+        h = allb.cpu().numpy().reshape(world, max(nmax * width, 1))
+        parts = [h[r, :int(counts[r]) * width] for r in range(world)]
+        out[k] = np.concatenate(parts).view(a.dtype).reshape((-1,) + tail)
+    out['counts'] = counts
+    return out
+
+
+def allreduce_sum_host(a, group=None):
+    """Sum of a small host array over the ranks (int64 / float64), returned as numpy."""
+    import torch
+    import torch.distributed as dist
+    a = np.ascontiguousarray(a)
+    t = torch.from_numpy(a.copy()).to(_comm_device(group))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()

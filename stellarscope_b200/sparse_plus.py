@@ -68,6 +68,10 @@ class csr_matrix_plus(scipy.sparse.csr_matrix):
         if (dev is not None and engine is not None and dev[0] is engine and getattr(engine, 'h', None)
                 and engine._keep.get('row_ptr') is dev[2] and dev[1].numel() == engine.A):
             # produced by this engine's ss_reassign a moment ago: its flags are still on the device
+            rows = dev[3] if len(dev) > 3 else None
+            if rows is not None:                 # sharded run: the engine holds this rank's rows only
+                row_group = np.ascontiguousarray(row_group[rows])
+                row_umi = None if row_umi is None else np.ascontiguousarray(row_umi[rows])
             return engine.count(dev[1], row_group, row_umi=row_umi, keep_device=keep_device)
         eng = _default_engine()          # a separate handle: the model's engine keeps its score matrix
         m = self

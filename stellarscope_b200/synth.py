@@ -193,3 +193,116 @@ def apply_row_mask(data: SynthData, keep):
                      scores=data.scores[ek], K=data.K, row_cell=data.row_cell,
                      n_cells=data.n_cells, cell_type=data.cell_type,
                      n_celltypes=data.n_celltypes, row_umi=data.row_umi)
+
+
+def generate_device(n_cells=100, n_alignments=50_000, n_loci=28_000, seed=0, unique_frac=0.0, tie_frac=0.05,
+                    nofeat_frac=0.03, n_celltypes=1, umi_dup_rate=0.0, sigma=1.0, max_k=32, device=None,
+                    keep_device=False):
+    """``generate`` for the large configurations (BASELINE.json configs[2..4]: 10^8 .. 5x10^8 alignments), with
+    the per-row / per-alignment draws made by torch on the GPU: numpy needs ~3 minutes for 5x10^8 alignments, the
+    device a few seconds.  Same model of the data, same small host-side draws (families, popularity, cell sizes,
+    celltypes -- from ``numpy.random.default_rng(seed)``); the large draws come from a ``torch.Generator`` seeded
+    with ``seed``, so the matrix is a different sample of the same distribution than ``generate`` gives, and it is
+    reproducible on the same GPU model (all ranks of a bench run generate identical data; ``bench.py`` checks a
+    checksum).  Benchmark input only: nothing of the product depends on it.
+
+    Returns a ``SynthData`` of host arrays; with ``keep_device`` also ``.dev = (indptr, indices, scores)`` device
+    tensors (int32, int32, uint16)."""
+    import torch
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    rng = np.random.default_rng(seed)
+    K = n_loci + 1
+    fstart, fsize = make_families(n_loci, rng)
+    F = len(fsize)
+    has_mirror = fsize >= 6
+    draw_size = np.where(has_mirror, fsize - 1, fsize)
+    pop = 1.0 / np.arange(1, F + 1) ** 1.1
+    pop = pop[rng.permutation(F)]
+    pop /= pop.sum()
+    mean_k = (1 - unique_frac) * 3.5 + unique_frac * 1.0 + nofeat_frac + 0.08
+    N = max(n_cells, int(round(n_alignments / mean_k)))
+    wts = rng.lognormal(0.0, sigma, n_cells)
+    rows_per_cell = np.maximum(1, np.floor(wts / wts.sum() * N).astype(np.int64))
+    N = int(rows_per_cell.sum())
+    if n_celltypes > 1:
+        props = rng.dirichlet(np.full(n_celltypes, 0.5))
+        props = np.maximum(props, 1.0 / (10 * n_cells))
+        cell_type = rng.choice(n_celltypes, size=n_cells, p=props / props.sum()).astype(np.int32)
+        cell_type[:min(n_celltypes, n_cells)] = np.arange(min(n_celltypes, n_cells))
+    else:
+        cell_type = np.zeros(n_cells, dtype=np.int32)
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed) + 0x5eed)
+    i64 = torch.int64
+    import contextlib
+    with (torch.cuda.device(dev) if dev.type == 'cuda' else contextlib.nullcontext()):
+        t_fstart = torch.from_numpy(fstart).to(dev)
+        t_fsize = torch.from_numpy(fsize).to(dev)
+        t_mirror = torch.from_numpy(has_mirror).to(dev)
+        t_draw = torch.from_numpy(draw_size).to(dev)
+        cdf = torch.from_numpy(np.cumsum(pop)).to(dev)
+        fam = torch.searchsorted(cdf, torch.rand(N, generator=g, device=dev, dtype=torch.float64)).clamp_(max=F - 1)
+        m = t_draw[fam]
+        k = 2 + torch.poisson(torch.full((N,), 1.5, device=dev), generator=g).to(i64)
+        k = torch.minimum(k.clamp_(max=max_k), m)
+        if unique_frac > 0:
+            k = torch.where(torch.rand(N, generator=g, device=dev) < unique_frac, torch.ones_like(k), k)
+        start = torch.randint(0, 1 << 30, (N,), generator=g, device=dev) % m
+        stride = torch.from_numpy(_PRIMES).to(dev)[torch.randint(0, len(_PRIMES), (N,), generator=g, device=dev)]
+        forced = t_mirror[fam] & (torch.rand(N, generator=g, device=dev) < tie_frac)
+        start = torch.where(forced, torch.zeros_like(start), start)
+        ptr = torch.zeros(N + 1, dtype=i64, device=dev)
+        torch.cumsum(k, 0, out=ptr[1:])
+        A0 = int(ptr[-1])
+        erow = torch.repeat_interleave(torch.arange(N, device=dev), k, output_size=A0)
+        t = torch.arange(A0, device=dev) - ptr[erow]
+        member = (start[erow] + t * stride[erow]) % m[erow]
+        efam = fam[erow]
+        col = t_fstart[efam] + member
+        p = torch.where(t == 0, 0.75, 0.65).to(torch.float32)
+        del t
+        score = 140 + torch.binomial(torch.full((A0,), 120.0, device=dev), p, generator=g).to(i64)
+        del p
+        # one sortable key per alignment: row | column | score (51 bits)
+        keys = [(erow << 23) | (col << 8) | (score - 140)]
+        mir = (member == 0) & t_mirror[efam]
+        mr = erow[mir]
+        mf = efam[mir]
+        keys.append((mr << 23) | ((t_fstart[mf] + t_fsize[mf] - 1) << 8) | (score[mir] - 140))
+        del member, efam, col, mir, mr, mf, erow, score
+        nf = torch.nonzero(torch.rand(N, generator=g, device=dev) < nofeat_frac).reshape(-1)
+        nfs = torch.binomial(torch.full((len(nf),), 120.0, device=dev), torch.full((len(nf),), 0.65, device=dev),
+                             generator=g).to(i64)
+        keys.append((nf << 23) | nfs)
+        key = torch.cat(keys)
+        del keys
+        key, _ = torch.sort(key)
+        rows = key >> 23
+        indices = ((key >> 8) & 0x7fff).to(torch.int32)
+        scores = ((key & 0xff) + 140).to(torch.int32)
+        del key
+        indptr = torch.zeros(N + 1, dtype=i64, device=dev)
+        torch.cumsum(torch.bincount(rows, minlength=N), 0, out=indptr[1:])
+        del rows
+        if int(indptr[-1]) >= 2 ** 31:
+            raise OverflowError('more than 2^31 - 1 alignments: the score matrix uses int32 row pointers')
+        indptr = indptr.to(torch.int32)
+        row_cell_t = torch.repeat_interleave(torch.arange(n_cells, device=dev, dtype=torch.int32),
+                                             torch.from_numpy(rows_per_cell).to(dev), output_size=N)
+        umi = torch.arange(N, dtype=torch.int32, device=dev)
+        if umi_dup_rate > 0:
+            dup = torch.rand(N, generator=g, device=dev) < umi_dup_rate
+            dup[0] = False
+            dup[1:] &= row_cell_t[1:] == row_cell_t[:-1]
+            idx = torch.where(dup, torch.zeros_like(umi), umi)
+            umi = torch.cummax(idx, 0).values.to(torch.int32)
+        scores16 = scores.to(torch.uint16)
+        del scores
+        out = SynthData(indptr=indptr.cpu().numpy(), indices=indices.cpu().numpy(), scores=scores16.cpu().numpy(),
+                        K=K, row_cell=row_cell_t.cpu().numpy(), n_cells=n_cells, cell_type=cell_type,
+                        n_celltypes=max(1, n_celltypes), row_umi=umi.cpu().numpy())
+        if keep_device:
+            out.dev = (indptr, indices, scores16)
+            out.dev_row_cell = row_cell_t
+    return out

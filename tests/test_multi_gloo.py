@@ -273,3 +273,69 @@ def test_output_report_single_writer_world2_gloo(tmp_path):
         assert p.exitcode == 0
     assert got[0] == (0, [0], True)                  # rank 0 wrote
     assert got[1] == (1, [], True)                   # rank 1 did not write and returned after the file existed
+
+
+def test_plan_local_rows_partitions_every_row():
+    """Packed models, a wide model cut into blocks and rows of no model: every row on exactly one rank."""
+    d = H.small_synth(seed=12, n_cells=40, n_alignments=9000, n_loci=200)
+    seg = (d.row_cell % 5).astype(np.int32)
+    seg[d.row_cell % 11 == 0] = -1                                # cells without a model
+    for world in (1, 2, 3, 8):
+        for wide in ([], [2], [0, 1, 2, 3, 4]):
+            got = []
+            for rank in range(world):
+                p = parallel.plan_local_rows(d.indptr, seg, 5, world, rank, wide=wide, row_cell=d.row_cell)
+                rows = p['rows']
+                assert np.all(np.diff(rows) > 0)
+                assert len(p['local_seg']) == len(rows)
+                # local model ids index `mine`; rows of wide / no model carry -1
+                fitted = p['local_seg'] >= 0
+                assert np.array_equal(p['mine'][p['local_seg'][fitted]], seg[rows][fitted])
+                for w, m in zip(p['wide'], p['wide_local']):
+                    assert np.all(seg[rows][m] == w)
+                got.append(rows)
+            allr = np.concatenate(got)
+            assert np.array_equal(np.sort(allr), np.arange(d.N)), (world, wide)
+            if world > 1 and wide:
+                # a wide model's rows are spread over the ranks
+                w = wide[0]
+                per_rank = [int((seg[r] == w).sum()) for r in got]
+                assert min(per_rank) > 0
+
+
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    n = 3 + 2 * rank                                           # ragged contributions; rank 0 of the second call: none
+    g = parallel.gather_concat({'a': np.arange(n, dtype=np.int32) + 100 * rank,
+                                'b': np.full((n, 2), rank + 0.5),
+                                'c': (np.arange(n) + rank).astype(np.uint16)})
+    g2 = parallel.gather_concat({'x': np.arange(0 if rank == 0 else 4, dtype=np.int64)})
+    s = parallel.allreduce_sum_host(np.array([rank + 1, 10], dtype=np.int64))
+    q.put((rank, {k: v.tolist() for k, v in g.items()}, g2['x'].tolist(), g2['counts'].tolist(), s.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_concat_world2_gloo():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, g, x, xc, s in got:
+        assert g['a'] == [0, 1, 2, 100, 101, 102, 103, 104]
+        assert g['b'] == [[0.5, 0.5]] * 3 + [[1.5, 1.5]] * 5
+        assert g['c'] == [0, 1, 2, 1, 2, 3, 4, 5]
+        assert g['counts'] == [3, 5]
+        assert x == [0, 1, 2, 3] and xc == [0, 4]
+        assert s == [3, 20]
