@@ -1,8 +1,11 @@
-"""Timing of the REAL reference's fit in the build container ("the reference exactly as written
-on a <=200-cell subsample to document its O(cells x N_total) behaviour").  Build container only -- the reference
-is pure Python + scipy and does not travel to the GPU box; the numbers go to profiles/ and DESIGN.md section 6.
+"""Timing of the REAL reference's fit ("the reference exactly as written on a <=200-cell
+subsample to document its O(cells x N_total) behaviour").  TEST / BENCH INFRASTRUCTURE.
 
-    python -m oracle.time_reference [n_cells ...]
+    python -m oracle.time_reference [n_cells ...]                       # build container: /root/reference
+    python oracle/time_reference.py --npz sample.npz --ref baseline/_ref --nproc 16 --json
+                                                                        # bench.py's cpu_baseline.reference_as_written leg:
+                                                                        # the unmodified package under baseline/_ref (it
+                                                                        # travels to the GPU box) on a sample bench.py wrote
 
 Workload: the first n cells of BASELINE.json configs[1] (synthetic 10x, seed 0, ~500 alignments per cell),
 ``_fit_pooling_model`` in individual mode, serial (``nproc=1``) and with ``nproc = os.cpu_count()``; the unit is
@@ -19,6 +22,8 @@ import scipy.sparse as sp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+if '--ref' in sys.argv:                                    # before oracle.refshim reads the location
+    os.environ['STELLARSCOPE_REFERENCE'] = os.path.abspath(sys.argv[sys.argv.index('--ref') + 1])
 from oracle import em_oracle, refshim  # noqa: E402
 from oracle.make_golden import make_st  # noqa: E402
 from stellarscope_b200 import synth  # noqa: E402
@@ -35,7 +40,39 @@ def subsample(d, n_cells):
     return s
 
 
+def main_sample():
+    """One timed call of the reference's ``_fit_pooling_model`` (individual mode, ``nproc`` workers) on the sample
+    bench.py wrote; prints one JSON line."""
+    import json
+    a = sys.argv
+    z = np.load(a[a.index('--npz') + 1])
+    nproc = int(a[a.index('--nproc') + 1]) if '--nproc' in a else (os.cpu_count() or 1)
+    n = int(z['n_cells'])
+    d = types.SimpleNamespace(indptr=z['indptr'], indices=z['indices'], scores=z['scores'], N=len(z['indptr']) - 1,
+                              K=int(z['K']), A=int(z['indptr'][-1]), n_cells=n, row_cell=z['row_cell'],
+                              cell_type=np.zeros(n, dtype=np.int32), n_celltypes=1,
+                              row_umi=np.arange(len(z['indptr']) - 1, dtype=np.int32))
+    d.cell_rows = lambda: [np.flatnonzero(d.row_cell == c) for c in range(n)]
+    ref = refshim.load()
+    opts = refshim.RefOpts(pooling_mode='individual', nproc=nproc)
+    st, _ = make_st(d, opts, False)
+    a_cell = np.bincount(d.row_cell, weights=np.diff(d.indptr), minlength=n)
+    with refshim.cli_fp_policy():
+        t0 = time.perf_counter()
+        tl, pool = ref._fit_pooling_model(st, opts, processes=nproc)
+        dt = time.perf_counter() - t0
+    iters = np.array([len(pool.models_info[k].iterations) for k in pool.models_info])
+    units = float((a_cell * iters).sum())
+    print(json.dumps(dict(value=units / dt, unit='aln*iter/s', cores=nproc, kind='_ref', seconds=dt, cells=n,
+                          alignments=d.A, rows=d.N, mean_iters=float(iters.mean()),
+                          what='unmodified reference package (baseline/_ref), stellarscope.utils.model.'
+                               '_fit_pooling_model(st, opts) individual mode as written (one full-height masked '
+                               'matrix per cell, multiprocessing.Pool(nproc))')))
+
+
 def main():
+    if '--npz' in sys.argv:
+        return main_sample()
     sizes = [int(a) for a in sys.argv[1:]] or [50, 100, 200]
     ref = refshim.load()
     full = synth.generate(n_cells=10_000, n_alignments=5_000_000, n_loci=28_000, seed=0)

@@ -1,27 +1,48 @@
-"""Where does the e2e time go?  (host prep / H2D / build / fit / results)"""
-import os, sys, time
+"""Where the time of one reference-facing call goes (host side): cProfile of model._fit_pooling_model on a bench workload.
+
+    python scripts/e2e_profile.py [cfg5] [scale] [--report]     (--report: + Stellarscope.reassign sweep and count matrices)
+"""
+import cProfile, os, pstats, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import numpy as np
+import torch
 import bench
 from stellarscope_b200 import model
-from stellarscope_b200.engine import Engine
 
-d = bench.make_workload(0)
-opts = bench.BenchOpts()
+cfg = sys.argv[1] if len(sys.argv) > 1 else 'cfg5'
+scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+d = bench.make_workload(cfg, scale)
+opts = bench.BenchOpts(bench.CONFIGS[cfg]['mode'])
 st = bench.make_st(d, opts)
-def T(label, fn, n=3):
-    ts = []
-    for _ in range(n):
-        torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
-    print(f'{label:28s} {1e3*min(ts):8.2f} ms'); return r
-T('pooling_row_segments', lambda: model.pooling_row_segments(st, opts))
-seg, keys = model.pooling_row_segments(st, opts)
-eng = Engine(0)
-T('set_matrix (pin+H2D)', lambda: eng.set_matrix(d.indptr, d.indices, d.scores, d.K))
-T('build_layout', lambda: eng.build_layout(seg, len(keys)))
-T('fit', lambda: eng.fit())
-T('results(traces)', lambda: eng.results(traces=True))
-tl = model.TelescopeLikelihood(st.raw_scores, opts, row_segment=seg, n_segments=len(keys))
-T('fit_segments (FitInfo objs)', lambda: tl.fit_segments())
-T('TelescopeLikelihood ctor', lambda: model.TelescopeLikelihood(st.raw_scores, opts, row_segment=seg, n_segments=len(keys)), n=2)
-T('_fit_pooling_model', lambda: model._fit_pooling_model(st, opts), n=2)
+for i in range(2):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tl, pool = model._fit_pooling_model(st, opts)
+    torch.cuda.synchronize()
+    print(f'call {i}: {time.perf_counter() - t0:.3f} s (device fit {tl.fit_seconds:.3f} s)', flush=True)
+    tl.close()
+pr = cProfile.Profile()
+pr.enable()
+tl, pool = model._fit_pooling_model(st, opts)
+torch.cuda.synchronize()
+pr.disable()
+pstats.Stats(pr).sort_stats('cumulative').print_stats(28)
+if '--report' in sys.argv:
+    opts.reassign_mode = ['best_exclude', 'best_conf', 'best_random', 'best_average', 'total_hits']
+    st.opts = opts
+    for i in range(2):
+        t0 = time.perf_counter()
+        model.reassign(st, tl)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        counts, bc, ft = model.count_matrices(st, tl)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        print(f'pass {i}: reassign x5 {t1 - t0:.3f} s, count_matrices {t2 - t1:.3f} s', flush=True)
+    pr = cProfile.Profile()
+    pr.enable()
+    model.reassign(st, tl)
+    counts, bc, ft = model.count_matrices(st, tl)
+    torch.cuda.synchronize()
+    pr.disable()
+    pstats.Stats(pr).sort_stats('cumulative').print_stats(30)

@@ -169,6 +169,15 @@ class LazyMap(MutableMapping):
         return (dict, (d,))
 
 
+def attach_row_table(st, table, kinds=None):
+    """Give ``st`` the per-read containers of ``table`` as lazy mappings -- what ``load`` does for a side-car
+    checkpoint.  For callers that hold the row arrays already (``stellarscope resume`` from a side-car, synthetic
+    benchmark input): the hot path then reads the arrays and never builds a dict of 10^8 Python objects."""
+    for k in (kinds or ROW_MAPS):
+        setattr(st, k, LazyMap(table, k))
+    return st
+
+
 def row_table(st):
     """The row table of an object loaded from a side-car checkpoint, or None when the object's containers are
     (or may have become) something else."""

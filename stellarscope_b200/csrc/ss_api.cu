@@ -102,6 +102,12 @@ int ss_layout_build(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols,
     h->set_error("ss_layout_build: more than 1M loci not supported");
     return SS_ERR_ARG;
   }
+  if (nnz > 2147483647LL) {
+    // row_ptr is int32: a matrix with 2^31 or more alignments cannot be described (scipy switches to int64
+    // index arrays there); the caller shards the rows over more GPUs
+    h->set_error("ss_layout_build: more than 2^31 - 1 alignments (int32 row pointers)");
+    return SS_ERR_CAPACITY;
+  }
   cudaSetDevice(h->device);
   tl_alloc_stream = (cudaStream_t)stream;
   return layout_build(h, (cudaStream_t)stream, n_rows, n_cols, nnz, row_ptr, col_idx, score, row_segment,

@@ -175,15 +175,14 @@ __global__ void __launch_bounds__(THREADS) em_dense_kernel(EmArgs a, DenseArgs d
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double s_red[64];
   __shared__ uint64_t s_bar;
-  __shared__ uint64_t s_bars[2];
+  __shared__ StreamPipe s_pipe;
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   uint32_t phase = 0;
-  uint32_t uses[2] = {0u, 0u};
+  uint32_t n_use = 0u;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
-    mbar_init(&s_bars[0], 1);
-    mbar_init(&s_bars[1], 1);
+    stream_pipe_init(&s_pipe);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -191,17 +190,12 @@ __global__ void __launch_bounds__(THREADS) em_dense_kernel(EmArgs a, DenseArgs d
   double lnl_prev = INFINITY, lnl = 0.0;
   int it = 0;
   bool conv = false, comm_err = false;
-#ifdef SS_STREAM_PROFILE
-  long long k0_ = clock64(), kp[6] = {0, 0, 0, 0, 0, 0};
-#define K_TICK(i) { const long long k1_ = clock64(); kp[i] += k1_ - k0_; k0_ = k1_; }
-#else
 #define K_TICK(i)
-#endif
   while (true) {
     ++it;
     const int cur = (it - 1) & 1;
     lane_stream_pass<THREADS, SS_ST_FR, SS_ST_FC>(a.L, d.tgcol, nullptr, d.n_tiles, nullptr, d.x[cur], d.T[cur], d.geom,
-                                                    dsm, s_bars, uses);
+                                                    dsm, &s_pipe, n_use);
     K_TICK(0)
     grid.sync();
     K_TICK(1)
@@ -255,14 +249,6 @@ __global__ void __launch_bounds__(THREADS) em_dense_kernel(EmArgs a, DenseArgs d
     d.ctl[0] = it;
     d.ctl[1] = (conv ? 1 : 0) | (it >= d.max_iter ? 2 : 0) | (comm_err ? 8 : 0);
     *d.lnl_out = lnl;
-#ifdef SS_STREAM_PROFILE
-    const long long n = g_st_prof[7] ? g_st_prof[7] : 1;
-    printf("dense kernel, cycles per iteration (block 0): tile pass %lld  grid.sync %lld  update %lld  grid.sync %lld  part_sum %lld\n",
-           kp[0] / it, kp[1] / it, kp[2] / it, kp[3] / it, kp[4] / it);
-    printf("stream pass, cycles per tile (block 0, %lld tiles, nbuf %d): tma-wait %lld  gather-x %lld  phaseA %lld  phaseB+atomics %lld\n",
-           n, d.geom.nbuf, g_st_prof[0] / n, g_st_prof[1] / n, g_st_prof[2] / n, g_st_prof[3] / n);
-    for (int i = 0; i < 8; ++i) g_st_prof[i] = 0;
-#endif
   }
 }
 
@@ -272,14 +258,13 @@ __global__ void __launch_bounds__(THREADS) dense_pass_kernel(EmArgs a, DenseArgs
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double s_red[64];
   __shared__ uint64_t s_bar;
-  __shared__ uint64_t s_bars[2];
+  __shared__ StreamPipe s_pipe;
   if (*((volatile int*)d.ctl) != 0 && !lnl_pass) return;       // the fit has finished: no-op
   uint32_t phase = 0;
-  uint32_t uses[2] = {0u, 0u};
+  uint32_t n_use = 0u;
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
-    mbar_init(&s_bars[0], 1);
-    mbar_init(&s_bars[1], 1);
+    stream_pipe_init(&s_pipe);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -287,7 +272,7 @@ __global__ void __launch_bounds__(THREADS) dense_pass_kernel(EmArgs a, DenseArgs
     dense_lnl_pass<THREADS>(a, d, d.x[cur], d.x[cur ^ 1], d.T[tail_buf] + d.Kp, dsm, &s_bar, phase, s_red);
   else
     lane_stream_pass<THREADS, SS_ST_FR, SS_ST_FC>(a.L, d.tgcol, nullptr, d.n_tiles, nullptr, d.x[cur], d.T[cur], d.geom,
-                                                    dsm, s_bars, uses);
+                                                    dsm, &s_pipe, n_use);
 }
 
 template <int THREADS>

@@ -1218,13 +1218,12 @@ __global__ void __launch_bounds__(THREADS) em_stream_kernel(EmArgs a, StreamArgs
   const long long gthreads = (long long)gridDim.x * THREADS;
   const int max_iter = a.P.max_iter;
   const double eps = a.P.eps;
-  __shared__ uint64_t s_bars[2];
+  __shared__ StreamPipe s_pipe;
   uint32_t phase = 0;
-  uint32_t uses[2] = {0u, 0u};
+  uint32_t n_use = 0u;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
-    mbar_init(&s_bars[0], 1);
-    mbar_init(&s_bars[1], 1);
+    stream_pipe_init(&s_pipe);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -1234,7 +1233,7 @@ __global__ void __launch_bounds__(THREADS) em_stream_kernel(EmArgs a, StreamArgs
     const double* __restrict__ ptg = a.F.sc_pt[cur];
     // ---- tile pass: phase A + B, partial thetasum -> global accumulators (double-buffered TMA, lane fragments) ----
     lane_stream_pass<THREADS, SS_STREAM_FR, SS_STREAM_FC>(a.L, a.L.c_scol, sa.tiles, sa.n_tiles, a.F.seg_iters, ptg, a.F.sc_T, sa.geom, dsm,
-                                    s_bars, uses);
+                                    &s_pipe, n_use);
     grid.sync();
     // ---- update pass over the columns of the active multi-tile segments ----
     double* __restrict__ ptn = a.F.sc_pt[cur ^ 1];

@@ -225,25 +225,32 @@ namespace ss {
 // Streaming tile pass with lane fragments (segments too large to stay on chip: celltype / pseudobulk
 // models and cells beyond the cluster size).  One E+M half-iteration over the tiles assigned to this
 // CTA: r_i = sum_j Q_ij x_j per row, partial thetasum per tile column -> fp64 RED into T[colmap[c]].
-//   * the tile arrays (Q, index words, row weights, lengths, column pointers, JDS pointers, column map)
-//     arrive by TMA bulk copies into one of TWO shared-memory buffers: the next tile is in flight while
-//     the current one is computed (HBM is the bound of this pass: 12 B per alignment + ~6 B of row /
-//     column metadata);
-//   * the compute is the lane kernel's: rows and columns are cut into fragments of <= 4 alignments,
-//     long rows / columns span aligned lane groups combined by xor shuffles, so that a tile costs the
-//     same few hundred cycles in every warp instead of "the longest row of warp 0".
+//
+// The CTA is WARP-SPECIALISED (round 2: ncu showed the pass waiting, not computing -- every tile paid an L2
+// round trip for its x values, two dependent global loads for "is this segment still active", and a
+// one-thread derivation of the lane boundaries, all in front of a CTA barrier):
+//   * the last warp is the PRODUCER: it picks the next active tile of this CTA, issues the TMA bulk copies
+//     of the tile arrays (Q, index words, row weights, lengths, column pointers, JDS pointers, column map,
+//     tile header) into one of two shared-memory buffers, gathers the tile-local x values from global
+//     memory (many loads in flight per lane), derives the lane-group boundaries, and hands the buffer over
+//     through an mbarrier -- one tile ahead of the consumers, so none of that latency is on their path;
+//   * the other warps are CONSUMERS: wait for a complete buffer, phase A (row fragments), one barrier,
+//     phase B (column fragments -> RED), one barrier, release the buffer.
+// The compute is the lane kernel's: rows and columns are cut into fragments of <= 4 alignments, long rows
+// / columns span aligned lane groups combined by xor shuffles.
 // ---------------------------------------------------------------------------------------------------
 struct StreamGeom {
   int pe, pr, pc, pj;   // padded maxima over the streamed tiles
   int nbuf;             // 2: double buffered, 1: the largest tile leaves no room for a second buffer
 };
 constexpr int STREAM_HDR_BYTES = 256;   // the tile header (HDR_WORDS * 8 = 192 B) travels with the tile
-constexpr int STREAM_DC_INTS = 32;      // class boundaries derived once per tile (lane_tile_compute)
+constexpr int STREAM_DC_INTS = 24;      // lane-group boundaries of a tile (derived by the producer)
 __host__ __device__ inline size_t stream_buf_bytes(const StreamGeom& g) {
   return STREAM_HDR_BYTES + 12 * (size_t)g.pe + 10 * (size_t)g.pr + 6 * (size_t)g.pc + 2 * (size_t)g.pj;
 }
+// per buffer: tile arrays + tile-local x; shared by both: the column-major scratch
 __host__ __device__ inline size_t stream_smem_bytes(const StreamGeom& g) {
-  return (size_t)g.nbuf * stream_buf_bytes(g) + 8 * ((size_t)g.pe + 8) + 8 * (size_t)g.pc + 4 * STREAM_DC_INTS + 128;
+  return (size_t)g.nbuf * (stream_buf_bytes(g) + 8 * (size_t)g.pc) + 8 * ((size_t)g.pe + 8) + 128;
 }
 
 // double buffered when two buffers + scratch fit `limit` bytes of shared memory
@@ -299,67 +306,80 @@ __device__ __forceinline__ double group_xor_sum_s(double a, int g, int gmax) {
   return a;
 }
 
-#ifdef SS_STREAM_PROFILE
-__device__ long long g_st_prof[8];
-#define ST_TICK(i) { const long long c1_ = clock64(); if (blockIdx.x == 0 && threadIdx.x == 0) g_st_prof[i] += c1_ - c0_; c0_ = c1_; }
-#define ST_T0 long long c0_ = clock64();
-#else
-#define ST_TICK(i)
-#define ST_T0
-#endif
-// compute of one tile whose arrays are in `b`; xs = tile-local x (ncol + 1 slots), val = scratch (pe + 8)
-template <int THREADS, int FR, int FC>
-__device__ __forceinline__ void lane_tile_compute(const long long* __restrict__ hd, const TileView& v, const StreamBuf& b,
-                                                  const double* __restrict__ x, double* __restrict__ T, double* xs,
-                                                  double* val, int* dc) {
-  constexpr int NW = THREADS / 32;
+// control block of the pipeline (static shared memory of the kernel that runs the pass)
+struct StreamPipe {
+  uint64_t full[2];     // the TMA bytes of buffer b have landed
+  uint64_t ready[2];    // buffer b is complete: tile arrays, tile-local x, boundaries (producer -> consumers)
+  uint64_t empty[2];    // the consumers are done with buffer b (consumers -> producer)
+  int tile[2];          // tile in buffer b, -1: end of the pass
+  int dc[2][STREAM_DC_INTS];
+};
+__device__ __forceinline__ void stream_pipe_init(StreamPipe* p) {   // one thread, before a CTA barrier
+  for (int b = 0; b < 2; ++b) {
+    mbar_init(&p->full[b], 1);
+    mbar_init(&p->ready[b], 1);
+    mbar_init(&p->empty[b], 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int COUNT>
+__device__ __forceinline__ void consumer_bar() {      // named barrier 1: the consumer warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(COUNT) : "memory");
+}
+
+// lane-group boundaries of a tile from its header, for a pass with FR * CONS row lanes / FC * CONS column lanes
+__device__ __forceinline__ void stream_boundaries(const long long* hd, int nrows, int ncol, int row_lanes, int col_lanes,
+                                                  int* dc) {
+  const int rgt4 = (int)hd[H_RGT4], rgt8 = (int)hd[H_RGT8], rgt16 = (int)hd[H_RGT16], rgt32 = (int)hd[H_RGT32];
+  const int n_huge = rgt32;
+  const int n8 = rgt16 - rgt32, n4 = rgt8 - rgt16, n2 = rgt4 - rgt8, n1 = nrows - rgt4;
+  const int V8 = 8 * n8, V4 = V8 + 4 * n4, V2 = V4 + 2 * n2, V = V2 + n1;
+  const int Vc = min(V, row_lanes);
+  int r_ovf;
+  if (Vc >= V) r_ovf = nrows;
+  else if (Vc < V8) r_ovf = n_huge + Vc / 8;
+  else if (Vc < V4) r_ovf = n_huge + n8 + (Vc - V8) / 4;
+  else if (Vc < V2) r_ovf = n_huge + n8 + n4 + (Vc - V4) / 2;
+  else r_ovf = n_huge + n8 + n4 + n2 + (Vc - V2);
+  dc[0] = n_huge; dc[1] = n8; dc[2] = n4; dc[3] = n2; dc[4] = V8; dc[5] = V4; dc[6] = V2; dc[7] = Vc; dc[8] = r_ovf;
+  const int b128 = (int)hd[H_CGT128];
+  const int b64 = (int)hd[H_CGT64], b32 = (int)hd[H_CGT32], b16 = (int)hd[H_CGT16], b8 = (int)hd[H_CGT8],
+            b4 = (int)hd[H_CGT4];
+  const int W32 = 32 * (b64 - b128), W16 = W32 + 16 * (b32 - b64), W8 = W16 + 8 * (b16 - b32);
+  const int W4 = W8 + 4 * (b8 - b16), W2 = W4 + 2 * (b4 - b8), W = W2 + (ncol - b4);
+  const int Wc = min(W, col_lanes);
+  int c_ovf;
+  if (Wc >= W) c_ovf = ncol;
+  else if (Wc < W32) c_ovf = b128 + Wc / 32;
+  else if (Wc < W16) c_ovf = b64 + (Wc - W32) / 16;
+  else if (Wc < W8) c_ovf = b32 + (Wc - W16) / 8;
+  else if (Wc < W4) c_ovf = b16 + (Wc - W8) / 4;
+  else if (Wc < W2) c_ovf = b8 + (Wc - W4) / 2;
+  else c_ovf = b4 + (Wc - W2);
+  dc[9] = b128; dc[10] = b64; dc[11] = b32; dc[12] = b16; dc[13] = b8; dc[14] = b4;
+  dc[15] = W32; dc[16] = W16; dc[17] = W8; dc[18] = W4; dc[19] = W2; dc[20] = Wc; dc[21] = c_ovf;
+}
+
+// compute of one tile whose arrays are in `b` (consumer warps: CONS threads, tid < CONS);
+// xs = tile-local x (ncol + 1 slots, filled by the producer), val = scratch (pe + 8)
+template <int CONS, int FR, int FC>
+__device__ __forceinline__ void lane_tile_compute(const TileView& v, const StreamBuf& b, double* __restrict__ T,
+                                                  const double* __restrict__ xs, double* __restrict__ val,
+                                                  const int* __restrict__ dc) {
+  constexpr int NW = CONS / 32;
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  ST_T0
-  // ---- tile-local x ----
-  for (int c = tid; c < v.ncol; c += THREADS) xs[c] = __ldcg(x + b.gcol[c]);
-  if (tid == 0) xs[v.ncol] = 0.0;
-  // ---- lane-group boundaries of the tile: derived once (one thread), read by everybody after the barrier ----
-  if (tid == THREADS - 1) {
-    const int rgt4 = (int)hd[H_RGT4], rgt8 = (int)hd[H_RGT8], rgt16 = (int)hd[H_RGT16], rgt32 = (int)hd[H_RGT32];
-    const int n_huge = rgt32;
-    const int n8 = rgt16 - rgt32, n4 = rgt8 - rgt16, n2 = rgt4 - rgt8, n1 = v.nrows - rgt4;
-    const int V8 = 8 * n8, V4 = V8 + 4 * n4, V2 = V4 + 2 * n2, V = V2 + n1;
-    const int Vc = min(V, FR * THREADS);
-    int r_ovf;
-    if (Vc >= V) r_ovf = v.nrows;
-    else if (Vc < V8) r_ovf = n_huge + Vc / 8;
-    else if (Vc < V4) r_ovf = n_huge + n8 + (Vc - V8) / 4;
-    else if (Vc < V2) r_ovf = n_huge + n8 + n4 + (Vc - V4) / 2;
-    else r_ovf = n_huge + n8 + n4 + n2 + (Vc - V2);
-    dc[0] = n_huge; dc[1] = n8; dc[2] = n4; dc[3] = n2; dc[4] = V8; dc[5] = V4; dc[6] = V2; dc[7] = Vc; dc[8] = r_ovf;
-    const int b128 = (int)hd[H_CGT128];
-    const int b64 = (int)hd[H_CGT64], b32 = (int)hd[H_CGT32], b16 = (int)hd[H_CGT16], b8 = (int)hd[H_CGT8],
-              b4 = (int)hd[H_CGT4];
-    const int W32 = 32 * (b64 - b128), W16 = W32 + 16 * (b32 - b64), W8 = W16 + 8 * (b16 - b32);
-    const int W4 = W8 + 4 * (b8 - b16), W2 = W4 + 2 * (b4 - b8), W = W2 + (v.ncol - b4);
-    const int Wc = min(W, FC * THREADS);
-    int c_ovf;
-    if (Wc >= W) c_ovf = v.ncol;
-    else if (Wc < W32) c_ovf = b128 + Wc / 32;
-    else if (Wc < W16) c_ovf = b64 + (Wc - W32) / 16;
-    else if (Wc < W8) c_ovf = b32 + (Wc - W16) / 8;
-    else if (Wc < W4) c_ovf = b16 + (Wc - W8) / 4;
-    else if (Wc < W2) c_ovf = b8 + (Wc - W4) / 2;
-    else c_ovf = b4 + (Wc - W2);
-    dc[9] = b128; dc[10] = b64; dc[11] = b32; dc[12] = b16; dc[13] = b8; dc[14] = b4;
-    dc[15] = W32; dc[16] = W16; dc[17] = W8; dc[18] = W4; dc[19] = W2; dc[20] = Wc; dc[21] = c_ovf;
-  }
-  __syncthreads();
-  ST_TICK(1)
   // ---- phase A: row fragments ----
   {
     const int n_huge = dc[0], n8 = dc[1], n4 = dc[2], n2 = dc[3];
     const int V8 = dc[4], V4 = dc[5], V2 = dc[6], Vc = dc[7], r_ovf = dc[8];
 #pragma unroll
     for (int j = 0; j < FR; ++j) {
-      const int vl = tid + j * THREADS;
-      if (j * THREADS >= Vc) break;                                  // block-uniform
+      const int vl = tid + j * CONS;
+      if (j * CONS >= Vc) break;                                     // block-uniform
       int n = 0, g = 1, r = 0, k = 0;
       if (vl < Vc) {
         if (vl < V8) { g = 8; r = n_huge + vl / 8; k = vl % 8; }
@@ -395,7 +415,7 @@ __device__ __forceinline__ void lane_tile_compute(const long long* __restrict__ 
         if (p < n) val[fi[p] >> 16] = fq[p] * sc;
     }
     if (n_huge > 0 || r_ovf < v.nrows) {
-      for (int r = tid; r < v.nrows; r += THREADS) {                 // rows outside the lanes (rare)
+      for (int r = tid; r < v.nrows; r += CONS) {                    // rows outside the lanes (rare)
         const int rr = r < n_huge ? r : r_ovf + (r - n_huge);
         if (rr >= v.nrows) break;
         const int len = b.rlen[rr];
@@ -412,16 +432,15 @@ __device__ __forceinline__ void lane_tile_compute(const long long* __restrict__ 
       }
     }
   }
-  __syncthreads();
-  ST_TICK(2)
+  consumer_bar<CONS>();
   // ---- phase B: column fragments -> RED into T ----
   {
     const int b128 = dc[9], b64 = dc[10], b32 = dc[11], b16 = dc[12], b8 = dc[13], b4 = dc[14];
     const int W32 = dc[15], W16 = dc[16], W8 = dc[17], W4 = dc[18], W2 = dc[19], Wc = dc[20], c_ovf = dc[21];
 #pragma unroll
     for (int j = 0; j < FC; ++j) {
-      const int vl = tid + j * THREADS;
-      if (j * THREADS >= Wc) break;                                  // block-uniform
+      const int vl = tid + j * CONS;
+      if (j * CONS >= Wc) break;                                     // block-uniform
       int n = 0, g = 1, c = 0, k = 0, base = 0;
       if (vl < Wc) {
         if (vl < W32) { g = 32; c = b128 + vl / 32; k = vl % 32; }
@@ -447,72 +466,110 @@ __device__ __forceinline__ void lane_tile_compute(const long long* __restrict__ 
       const double asum = col_sum_warp(val, cb, n, lane);
       if (lane == 0) atomicAdd(&T[b.gcol[c]], xs[c] * asum);
     }
-    for (int c = c_ovf + tid; c < v.ncol; c += THREADS) {            // columns beyond the lanes
+    for (int c = c_ovf + tid; c < v.ncol; c += CONS) {               // columns beyond the lanes
       const int cb = b.cptr[c], n = (int)b.cptr[c + 1] - cb;
       atomicAdd(&T[b.gcol[c]], xs[c] * col_sum_thread(val, cb, n));
     }
   }
-  ST_TICK(3)
 }
 
-// the tiles tiles[i] (or i itself when tiles == nullptr), i = blockIdx.x, blockIdx.x + gridDim.x, ...;
-// tiles of segments with seg_done[seg] != 0 are skipped.  `uses[b]` counts the fills of buffer b (mbarrier parity).
+// The tiles tiles[i] (or i itself when tiles == nullptr), i = blockIdx.x, blockIdx.x + gridDim.x, ...; tiles of
+// segments with seg_done[seg] != 0 are skipped.  `n_use` counts the buffer fills of this CTA over the life of the
+// kernel (mbarrier parities); every thread carries the same value.  Called by all THREADS threads of the CTA; ends
+// with a CTA barrier.
 template <int THREADS, int FR, int FC>
 __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __restrict__ colmap, const int* __restrict__ tiles,
                                                  int n_items, const int* seg_done, const double* __restrict__ x,
                                                  double* __restrict__ T, const StreamGeom& g, unsigned char* dsm,
-                                                 uint64_t* bars, uint32_t* uses) {
-  const int tid = threadIdx.x;
+                                                 StreamPipe* pipe, uint32_t& n_use) {
+  constexpr int CONS = THREADS - 32;                     // consumer threads; the last warp produces
+  const int tid = threadIdx.x, lane = tid & 31;
   const size_t bb = stream_buf_bytes(g);
-  double* val = reinterpret_cast<double*>(dsm + (size_t)g.nbuf * bb);
-  double* xs = val + g.pe + 8;
-  int* dc = reinterpret_cast<int*>(xs + g.pc);
-  auto next_item = [&](int i) {
-    while (i < n_items) {
+  const int nbuf = g.nbuf;
+  double* val = reinterpret_cast<double*>(dsm + (size_t)nbuf * bb);
+  double* xs0 = val + g.pe + 8;
+  uint32_t n = n_use;
+  if (tid >= CONS) {
+    // ------------------------------ producer warp ------------------------------
+    auto next_item = [&](int i) {
+      while (i < n_items) {
+        const int t = tiles ? tiles[i] : i;
+        if (!seg_done || ((volatile const int*)seg_done)[(int)L.tile_hdr[(long long)HDR_WORDS * t + H_SEG]] == 0) break;
+        i += gridDim.x;
+      }
+      return i;
+    };
+    int i = next_item(blockIdx.x);
+    while (true) {
+      const int slot = nbuf == 2 ? (int)(n & 1u) : 0;
+      const uint32_t k = nbuf == 2 ? (n >> 1) : n;
+      if (k >= 1) mbar_wait(&pipe->empty[slot], (k - 1) & 1u);       // the consumers have released this buffer
+      if (i >= n_items) {
+        if (lane == 0) {
+          pipe->tile[slot] = -1;
+          mbar_arrive(&pipe->full[slot]);
+          mbar_arrive(&pipe->ready[slot]);
+        }
+        ++n;
+        break;
+      }
       const int t = tiles ? tiles[i] : i;
-      if (!seg_done || ((volatile const int*)seg_done)[(int)L.tile_hdr[(long long)HDR_WORDS * t + H_SEG]] == 0) break;
-      i += gridDim.x;
+      const TileView v = load_tile_view(L.tile_hdr, t);
+      const StreamBuf b = carve_stream(dsm + (size_t)slot * bb, g);
+      if (lane == 0) {
+        fence_proxy_async();
+        stream_issue_loads(L, colmap, t, v, b, &pipe->full[slot]);
+      }
+      const int i_next = next_item(i + gridDim.x);                   // overlaps the flight of the copies
+      mbar_wait(&pipe->full[slot], k & 1u);
+      // tile-local x: 8 loads in flight per lane
+      double* xs = xs0 + (size_t)slot * g.pc;
+      for (int c0 = 0; c0 < v.ncol; c0 += 256) {
+        double xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c = c0 + 32 * u + lane;
+          xv[u] = c < v.ncol ? __ldcg(x + b.gcol[c]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c = c0 + 32 * u + lane;
+          if (c < v.ncol) xs[c] = xv[u];
+        }
+      }
+      if (lane == 0) {
+        xs[v.ncol] = 0.0;
+        stream_boundaries(b.hdr, v.nrows, v.ncol, FR * CONS, FC * CONS, pipe->dc[slot]);
+        pipe->tile[slot] = t;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pipe->ready[slot]);                // release: x, boundaries, tile id
+      ++n;
+      i = i_next;
     }
-    return i;
-  };
-  int cur = next_item(blockIdx.x);
-  int nb = 0;
-  if (cur < n_items && tid == 0) {
-    const int t = tiles ? tiles[cur] : cur;
-    fence_proxy_async();
-    stream_issue_loads(L, colmap, t, load_tile_view(L.tile_hdr, t), carve_stream(dsm, g), &bars[0]);
+  } else {
+    // ------------------------------ consumer warps ------------------------------
+    while (true) {
+      const int slot = nbuf == 2 ? (int)(n & 1u) : 0;
+      const uint32_t k = nbuf == 2 ? (n >> 1) : n;
+      mbar_wait(&pipe->ready[slot], k & 1u);
+      const int t = pipe->tile[slot];
+      mbar_wait(&pipe->full[slot], k & 1u);                          // complete already; orders the reads after the copies
+      ++n;
+      if (t < 0) {
+        consumer_bar<CONS>();                                        // everybody has read the marker
+        if (tid == 0) mbar_arrive(&pipe->empty[slot]);
+        break;
+      }
+      const StreamBuf b = carve_stream(dsm + (size_t)slot * bb, g);
+      const TileView v = load_tile_view(b.hdr, 0);                   // the header arrived with the tile
+      lane_tile_compute<CONS, FR, FC>(v, b, T, xs0 + (size_t)slot * g.pc, val, pipe->dc[slot]);
+      consumer_bar<CONS>();                                          // buffer, x and scratch are free again
+      if (tid == 0) mbar_arrive(&pipe->empty[slot]);
+    }
   }
-  while (cur < n_items) {
-    const int b_cur = g.nbuf == 2 ? (nb & 1) : 0;
-    const int nxt = next_item(cur + gridDim.x);
-    if (g.nbuf == 2 && nxt < n_items && tid == 0) {
-      const int t = tiles ? tiles[nxt] : nxt;
-      fence_proxy_async();
-      stream_issue_loads(L, colmap, t, load_tile_view(L.tile_hdr, t), carve_stream(dsm + (size_t)(b_cur ^ 1) * bb, g),
-                         &bars[b_cur ^ 1]);
-    }
-    const StreamBuf b = carve_stream(dsm + (size_t)b_cur * bb, g);
-#ifdef SS_STREAM_PROFILE
-    long long c0_ = clock64();
-#endif
-    mbar_wait(&bars[b_cur], uses[b_cur] & 1);
-    uses[b_cur]++;
-    ST_TICK(0)
-    const TileView v = load_tile_view(b.hdr, 0);                  // the header arrived with the tile (shared memory)
-    lane_tile_compute<THREADS, FR, FC>(b.hdr, v, b, x, T, xs, val, dc);
-    __syncthreads();                                              // buffers, val and xs are free again
-#ifdef SS_STREAM_PROFILE
-    c0_ = clock64() - 0;   // (B tail + barrier counted with the next wait)
-    if (blockIdx.x == 0 && tid == 0) g_st_prof[7] += 1;
-#endif
-    if (g.nbuf == 1 && nxt < n_items && tid == 0) {
-      const int t2 = tiles ? tiles[nxt] : nxt;
-      fence_proxy_async();
-      stream_issue_loads(L, colmap, t2, load_tile_view(L.tile_hdr, t2), carve_stream(dsm, g), &bars[0]);
-    }
-    cur = nxt;
-    ++nb;
-  }
+  n_use = n;
+  __syncthreads();
 }
 
 }  // namespace ss

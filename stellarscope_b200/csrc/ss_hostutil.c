@@ -580,7 +580,211 @@ done:
   return result;
 }
 
+/* ---- sharding plan of a pooling mode: alignments per model, LPT packing, the rows of one rank -------------
+ * parallel.plan_local_rows in numpy makes ~10 passes over per-row arrays (1.4x10^8 rows at atlas scale: seconds
+ * on every rank, more than the fit).  Three helpers, the per-row ones threaded and without the GIL:
+ *   segment_alignments(indptr, row_segment, seg_A)        seg_A[s] = alignments of the rows of model s
+ *   lpt_assign(seg_A, world, model_rank)                  longest-processing-time packing, ties by index
+ *                                                         (the same assignment as parallel.lpt_shards)
+ *   count_rows(row_segment, model_rank, rank, counts)     rows of `rank` per chunk of rows (counts int64[NCH])
+ *   fill_rows(row_segment, model_rank, local_id, rank, offsets, rows, local_seg)
+ * Rows with row_segment < 0 or model_rank < 0 (wide models) are never selected here (numpy path of the caller). */
+#define SS_NCH 64
+typedef struct {
+  const char* ip; Py_ssize_t ip_size;
+  const int32_t* seg; Py_ssize_t n, S;
+  int64_t* part;                 /* [S] private partial sums */
+  const int32_t *model_rank, *local_id;
+  int rank;
+  int64_t *counts, *rows; const int64_t* offsets; int32_t* lseg;
+  Py_ssize_t c0, c1;             /* chunk range of this thread */
+  int mode;
+} plan_t;
+static inline void chunk_bounds(Py_ssize_t n, int c, Py_ssize_t* a, Py_ssize_t* b) {
+  *a = (Py_ssize_t)((__int128)n * c / SS_NCH);
+  *b = (Py_ssize_t)((__int128)n * (c + 1) / SS_NCH);
+}
+static void* plan_main(void* arg) {
+  plan_t* w = (plan_t*)arg;
+  for (Py_ssize_t c = w->c0; c < w->c1; ++c) {
+    Py_ssize_t a, b;
+    chunk_bounds(w->n, (int)c, &a, &b);
+    if (w->mode == 0) {
+      for (Py_ssize_t r = a; r < b; ++r) {
+        const int32_t s = w->seg[r];
+        if (s >= 0 && s < w->S) w->part[s] += ld_ix(w->ip, w->ip_size, r + 1) - ld_ix(w->ip, w->ip_size, r);
+      }
+    } else if (w->mode == 1) {
+      int64_t k = 0;
+      for (Py_ssize_t r = a; r < b; ++r) {
+        const int32_t s = w->seg[r];
+        k += (s >= 0 && s < w->S && w->model_rank[s] == w->rank);
+      }
+      w->counts[c] = k;
+    } else {
+      int64_t o = w->offsets[c];
+      for (Py_ssize_t r = a; r < b; ++r) {
+        const int32_t s = w->seg[r];
+        if (s >= 0 && s < w->S && w->model_rank[s] == w->rank) {
+          w->rows[o] = r;
+          w->lseg[o] = w->local_id[s];
+          ++o;
+        }
+      }
+    }
+  }
+  return NULL;
+}
+static void plan_run(plan_t* proto, int nt) {
+  plan_t w[16];
+  pthread_t th[16];
+  if (nt > 16) nt = 16;
+  if (nt < 1) nt = 1;
+  for (int i = 0; i < nt; ++i) {
+    w[i] = *proto;
+    w[i].c0 = (Py_ssize_t)SS_NCH * i / nt;
+    w[i].c1 = (Py_ssize_t)SS_NCH * (i + 1) / nt;
+  }
+  int started = 0;
+  for (int i = 1; i < nt; ++i) {
+    if (pthread_create(&th[i], NULL, plan_main, &w[i]) != 0) break;
+    ++started;
+  }
+  plan_main(&w[0]);
+  for (int i = 1; i <= started; ++i) pthread_join(th[i], NULL);
+  for (int i = started + 1; i < nt; ++i) plan_main(&w[i]);
+}
+static PyObject* segment_alignments(PyObject* self, PyObject* args) {
+  Py_buffer ip, seg, out;
+  if (!PyArg_ParseTuple(args, "y*y*w*", &ip, &seg, &out)) return NULL;
+  PyObject* result = NULL;
+  const Py_ssize_t n = seg.len / 4, S = out.len / 8;
+  if ((ip.itemsize != 4 && ip.itemsize != 8) || seg.itemsize != 4 || out.itemsize != 8 || ip.len / ip.itemsize != n + 1) {
+    PyErr_SetString(PyExc_TypeError, "segment_alignments: indptr int32/int64 [N+1], row_segment int32 [N], out int64 [S]");
+    goto done;
+  }
+  {
+    int nt = host_threads();
+    if (n < 2000000) nt = 1;
+    int64_t* parts = (int64_t*)calloc((size_t)nt * (size_t)(S > 0 ? S : 1), sizeof(int64_t));
+    if (!parts) { PyErr_NoMemory(); goto done; }
+    /* one private accumulator array per thread: chunk ranges are split evenly over nt threads by plan_run, so
+       thread i is identified by its first chunk */
+    plan_t w[16];
+    pthread_t th[16];
+    Py_BEGIN_ALLOW_THREADS
+    for (int i = 0; i < nt; ++i) {
+      memset(&w[i], 0, sizeof(plan_t));
+      w[i].ip = (const char*)ip.buf; w[i].ip_size = ip.itemsize; w[i].seg = (const int32_t*)seg.buf;
+      w[i].n = n; w[i].S = S; w[i].part = parts + (size_t)i * (size_t)(S > 0 ? S : 1); w[i].mode = 0;
+      w[i].c0 = (Py_ssize_t)SS_NCH * i / nt; w[i].c1 = (Py_ssize_t)SS_NCH * (i + 1) / nt;
+    }
+    int started = 0;
+    for (int i = 1; i < nt; ++i) {
+      if (pthread_create(&th[i], NULL, plan_main, &w[i]) != 0) break;
+      ++started;
+    }
+    plan_main(&w[0]);
+    for (int i = 1; i <= started; ++i) pthread_join(th[i], NULL);
+    for (int i = started + 1; i < nt; ++i) plan_main(&w[i]);
+    int64_t* o = (int64_t*)out.buf;
+    for (Py_ssize_t s = 0; s < S; ++s) {
+      int64_t a = 0;
+      for (int i = 0; i < nt; ++i) a += parts[(size_t)i * (size_t)S + s];
+      o[s] = a;
+    }
+    Py_END_ALLOW_THREADS
+    free(parts);
+    result = PyLong_FromSsize_t(S);
+  }
+done:
+  PyBuffer_Release(&ip); PyBuffer_Release(&seg); PyBuffer_Release(&out);
+  return result;
+}
+typedef struct { int64_t size; int32_t idx; } lpt_item;
+static int lpt_cmp(const void* a, const void* b) {
+  const lpt_item *x = (const lpt_item*)a, *y = (const lpt_item*)b;
+  if (x->size != y->size) return x->size > y->size ? -1 : 1;       /* larger first */
+  return x->idx < y->idx ? -1 : (x->idx > y->idx);                 /* ties by index */
+}
+static PyObject* lpt_assign(PyObject* self, PyObject* args) {
+  Py_buffer sizes, out;
+  int world;
+  if (!PyArg_ParseTuple(args, "y*iw*", &sizes, &world, &out)) return NULL;
+  PyObject* result = NULL;
+  const Py_ssize_t S = sizes.len / 8;
+  if (sizes.itemsize != 8 || out.itemsize != 4 || out.len / 4 != S || world < 1 || world > 4096) {
+    PyErr_SetString(PyExc_TypeError, "lpt_assign: sizes int64 [S], world, model_rank int32 [S]");
+    goto done;
+  }
+  {
+    lpt_item* it = (lpt_item*)malloc((size_t)(S > 0 ? S : 1) * sizeof(lpt_item));
+    int64_t* load = (int64_t*)calloc((size_t)world, sizeof(int64_t));
+    if (!it || !load) { free(it); free(load); PyErr_NoMemory(); goto done; }
+    const int64_t* sz = (const int64_t*)sizes.buf;
+    int32_t* mr = (int32_t*)out.buf;
+    for (Py_ssize_t s = 0; s < S; ++s) { it[s].size = sz[s]; it[s].idx = (int32_t)s; }
+    qsort(it, (size_t)S, sizeof(lpt_item), lpt_cmp);
+    for (Py_ssize_t k = 0; k < S; ++k) {
+      int best = 0;
+      for (int r = 1; r < world; ++r)
+        if (load[r] < load[best]) best = r;                          /* smallest load, ties by rank */
+      mr[it[k].idx] = best;
+      load[best] += it[k].size;
+    }
+    free(it); free(load);
+    result = PyLong_FromSsize_t(S);
+  }
+done:
+  PyBuffer_Release(&sizes); PyBuffer_Release(&out);
+  return result;
+}
+static PyObject* select_rows_impl(PyObject* args, int fill) {
+  Py_buffer seg, mr, lid, cnt, rows, lseg;
+  int rank;
+  memset(&lid, 0, sizeof(lid)); memset(&rows, 0, sizeof(rows)); memset(&lseg, 0, sizeof(lseg));
+  if (!fill) {
+    if (!PyArg_ParseTuple(args, "y*y*iw*", &seg, &mr, &rank, &cnt)) return NULL;
+  } else {
+    if (!PyArg_ParseTuple(args, "y*y*y*iy*w*w*", &seg, &mr, &lid, &rank, &cnt, &rows, &lseg)) return NULL;
+  }
+  PyObject* result = NULL;
+  const Py_ssize_t n = seg.len / 4, S = mr.len / 4;
+  if (seg.itemsize != 4 || mr.itemsize != 4 || cnt.itemsize != 8 || cnt.len / 8 != SS_NCH ||
+      (fill && (lid.itemsize != 4 || lid.len / 4 != S || rows.itemsize != 8 || lseg.itemsize != 4))) {
+    PyErr_SetString(PyExc_TypeError, "count_rows / fill_rows: mismatching buffers");
+    goto done;
+  }
+  {
+    plan_t w;
+    memset(&w, 0, sizeof(w));
+    w.seg = (const int32_t*)seg.buf; w.n = n; w.S = S; w.model_rank = (const int32_t*)mr.buf; w.rank = rank;
+    if (!fill) {
+      w.mode = 1; w.counts = (int64_t*)cnt.buf;
+    } else {
+      const int64_t* off = (const int64_t*)cnt.buf;
+      w.mode = 2; w.offsets = off; w.local_id = (const int32_t*)lid.buf; w.rows = (int64_t*)rows.buf; w.lseg = (int32_t*)lseg.buf;
+    }
+    int nt = host_threads();
+    if (n < 2000000) nt = 1;
+    Py_BEGIN_ALLOW_THREADS
+    plan_run(&w, nt);
+    Py_END_ALLOW_THREADS
+    result = PyLong_FromSsize_t(n);
+  }
+done:
+  PyBuffer_Release(&seg); PyBuffer_Release(&mr); PyBuffer_Release(&cnt);
+  if (fill) { PyBuffer_Release(&lid); PyBuffer_Release(&rows); PyBuffer_Release(&lseg); }
+  return result;
+}
+static PyObject* count_rows(PyObject* self, PyObject* args) { return select_rows_impl(args, 0); }
+static PyObject* fill_rows(PyObject* self, PyObject* args) { return select_rows_impl(args, 1); }
+
 static PyMethodDef methods[] = {
+    {"segment_alignments", segment_alignments, METH_VARARGS, "segment_alignments(indptr, row_segment, seg_A): alignments per model"},
+    {"lpt_assign", lpt_assign, METH_VARARGS, "lpt_assign(seg_A, world, model_rank): longest-processing-time packing"},
+    {"count_rows", count_rows, METH_VARARGS, "count_rows(row_segment, model_rank, rank, counts): rows of a rank per row chunk"},
+    {"fill_rows", fill_rows, METH_VARARGS, "fill_rows(row_segment, model_rank, local_id, rank, offsets, rows, local_seg)"},
     {"row_extents", row_extents, METH_VARARGS, "row_extents(indptr, rows, out_ptr): prefix sums of the lengths of the given rows"},
     {"gather_rows", gather_rows, METH_VARARGS,
      "gather_rows(indptr, indices, data, rows, out_ptr, out_idx, out_dat): row-compacted copy of a CSR matrix"},

@@ -419,6 +419,10 @@ class Engine:
         self.N = len(indptr) - 1
         self.K = int(K)
         self.A = int(indptr[-1])
+        if self.A > 2 ** 31 - 1 or self.N > 2 ** 31 - 2:
+            # scipy switches to int64 index arrays at 2^31 entries; the device layout keeps int32 row pointers
+            raise OverflowError(f'{self.A} alignments / {self.N} rows: the device layout uses int32 row pointers '
+                                f'(at most 2^31 - 1 alignments); shard the rows over more GPUs')
         with torch.cuda.device(self.device):
             self._keep['row_ptr'] = self._to_dev(indptr, np.int32)
             self._keep['col_idx'] = self._to_dev(indices, np.int32)
@@ -536,24 +540,31 @@ class Engine:
                 out['lnls'] = LazyTrace(lnls, S, MI)
         return out
 
-    def params(self):
-        """Per segment-column parameters (synchronises)."""
+    def params_device(self):
+        """Per segment-column parameters as DEVICE tensors (pi / theta / gcol over all segment columns) plus the
+        small per-segment arrays on the host; callers that need a few models slice before copying."""
         S, dev = self.S, self.device
         nc = self.layout_info()['n_segcols']
         with torch.cuda.device(dev):
-            col0 = torch.empty(S, dtype=torch.int32, device=dev)
-            ncol = torch.empty(S, dtype=torch.int32, device=dev)
-            gcol = torch.empty(nc, dtype=torch.int32, device=dev)
-            pi = torch.empty(nc, dtype=torch.float64, device=dev)
-            theta = torch.empty(nc, dtype=torch.float64, device=dev)
-            pi_rest = torch.empty(S, dtype=torch.float64, device=dev)
-            th_rest = torch.empty(S, dtype=torch.float64, device=dev)
+            col0 = torch.empty(max(S, 1), dtype=torch.int32, device=dev)
+            ncol = torch.empty(max(S, 1), dtype=torch.int32, device=dev)
+            gcol = torch.empty(max(nc, 1), dtype=torch.int32, device=dev)
+            pi = torch.empty(max(nc, 1), dtype=torch.float64, device=dev)
+            theta = torch.empty(max(nc, 1), dtype=torch.float64, device=dev)
+            pi_rest = torch.empty(max(S, 1), dtype=torch.float64, device=dev)
+            th_rest = torch.empty(max(S, 1), dtype=torch.float64, device=dev)
             rc = self.lib.ss_em_get_params(self.h, self._stream(), self._p(col0), self._p(ncol), self._p(gcol),
                                            self._p(pi), self._p(theta), self._p(pi_rest), self._p(th_rest))
             self._check(rc)
-            return dict(seg_col0=col0.cpu().numpy(), seg_ncol=ncol.cpu().numpy(), gcol=gcol.cpu().numpy(),
-                        pi=pi.cpu().numpy(), theta=theta.cpu().numpy(), pi_rest=pi_rest.cpu().numpy(),
-                        theta_rest=th_rest.cpu().numpy())
+            return dict(seg_col0=col0[:S].cpu().numpy(), seg_ncol=ncol[:S].cpu().numpy(), gcol=gcol[:nc], pi=pi[:nc],
+                        theta=theta[:nc], pi_rest=pi_rest[:S].cpu().numpy(), theta_rest=th_rest[:S].cpu().numpy())
+
+    def params(self):
+        """Per segment-column parameters (synchronises)."""
+        p = self.params_device()
+        for k in ('gcol', 'pi', 'theta'):
+            p[k] = to_host(p[k])
+        return p
 
     def dense_params(self, seg):
         """Full-length (K) pi and theta of one segment, like ``tl.pi`` / ``tl.theta``."""

@@ -61,3 +61,39 @@ def gather_rows(indptr, indices, data, rows):
     dat = np.empty(total, dtype=data.dtype)
     load().gather_rows(indptr, indices, data, rows, ptr, idx, dat)
     return ptr, idx, dat
+
+
+def segment_alignments(indptr, row_segment, n_segments):
+    """int64[n_segments]: alignments of the rows of every model (rows with a negative model id count nowhere)."""
+    import numpy as np
+    out = np.zeros(int(n_segments), dtype=np.int64)
+    load().segment_alignments(np.ascontiguousarray(indptr), np.ascontiguousarray(row_segment, dtype=np.int32), out)
+    return out
+
+
+def lpt_assign(seg_A, world):
+    """int32[S]: rank of every model under longest-processing-time packing (larger first, ties by index; the
+    least loaded rank, ties by rank) -- the assignment ``parallel.lpt_shards`` makes."""
+    import numpy as np
+    seg_A = np.ascontiguousarray(seg_A, dtype=np.int64)
+    out = np.empty(len(seg_A), dtype=np.int32)
+    load().lpt_assign(seg_A, int(world), out)
+    return out
+
+
+def rows_of_rank(row_segment, model_rank, local_id, rank):
+    """(rows int64[n], local_seg int32[n]): the rows whose model is packed onto ``rank`` (ascending) and the
+    local id of their model."""
+    import numpy as np
+    row_segment = np.ascontiguousarray(row_segment, dtype=np.int32)
+    model_rank = np.ascontiguousarray(model_rank, dtype=np.int32)
+    local_id = np.ascontiguousarray(local_id, dtype=np.int32)
+    counts = np.zeros(64, dtype=np.int64)
+    load().count_rows(row_segment, model_rank, int(rank), counts)
+    off = np.zeros(64, dtype=np.int64)
+    np.cumsum(counts[:-1], out=off[1:])
+    n = int(counts.sum())
+    rows = np.empty(n, dtype=np.int64)
+    lseg = np.empty(n, dtype=np.int32)
+    load().fill_rows(row_segment, model_rank, local_id, int(rank), off, rows, lseg)
+    return rows, lseg

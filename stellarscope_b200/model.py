@@ -426,9 +426,12 @@ def _row_segments_from_table(st, opts, table):
     barcode code of every row is already an array, no container is walked."""
     code = table.row_bcode
     nb = len(table.bcodes)
-    counts = np.bincount(code[code >= 0], minlength=nb)
+    all_coded = len(code) == 0 or int(code.min()) >= 0            # every row belongs to a barcode (the usual case)
+    counts = np.bincount(code if all_coded else code[code >= 0], minlength=nb)
     if opts.pooling_mode == 'individual':
         has = counts > 0
+        if all_coded and has.all():
+            return code, list(range(nb))                          # model of a row = its barcode code: no pass at all
         model_of = np.where(has, np.cumsum(has) - 1, -1).astype(np.int32)   # barcodes without reads get no model
         for b in np.flatnonzero(~has):
             lg.info(f'        ...not fitting "{table.bcodes[b]}" -> no reads found')
@@ -452,7 +455,10 @@ def _row_segments_from_table(st, opts, table):
                 lg.info(f'        ...not fitting "{_ctype}" -> no reads found')
                 continue
             n_models += 1
-    seg = np.where(code >= 0, model_of[np.maximum(code, 0)], -1).astype(np.int32)
+    if all_coded:
+        seg = model_of[code]
+    else:
+        seg = np.where(code >= 0, model_of[np.maximum(code, 0)], -1).astype(np.int32)
     return seg, list(range(n_models))
 
 

@@ -215,6 +215,19 @@ def plan_local_rows(indptr, row_segment, n_segments, world, rank, wide=None, wid
     indptr = np.asarray(indptr)
     row_segment = np.asarray(row_segment)
     N = len(row_segment)
+    no_wide = wide is None or (not isinstance(wide, str) and len(wide) == 0)
+    if no_wide and row_segment.dtype == np.int32 and (N == 0 or int(row_segment.min()) >= 0):
+        # the common case -- every row belongs to a packed model: three threaded passes in C instead of ~10 numpy
+        # passes over per-row arrays (1.4x10^8 rows at atlas scale)
+        from . import hostutil
+        seg_A = hostutil.segment_alignments(indptr, row_segment, n_segments)
+        model_rank = hostutil.lpt_assign(seg_A, world)
+        mine = np.flatnonzero(model_rank == rank).astype(np.int64)
+        local_id = np.full(n_segments, -1, dtype=np.int32)
+        local_id[mine] = np.arange(len(mine), dtype=np.int32)
+        rows, local_seg = hostutil.rows_of_rank(row_segment, model_rank, local_id, rank)
+        return dict(rows=rows, local_seg=local_seg, mine=mine, wide=np.zeros(0, dtype=np.int64), wide_local=[],
+                    seg_A=seg_A)
     shards, seg_A, wide_ids = shard_models(indptr, row_segment, n_segments, world,
                                            wide=wide if wide is not None else [], wide_cost=wide_cost)
     mine = np.asarray(shards[rank], dtype=np.int64)

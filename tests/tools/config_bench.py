@@ -42,7 +42,7 @@ def main():
     c['n_cells'] = max(1, int(c['n_cells'] * scale))
     c['n_alignments'] = int(c['n_alignments'] * scale)
     t0 = time.perf_counter()
-    d = synth.generate(n_loci=28_000, seed=0, **c)
+    d = (synth.generate_device if torch.cuda.is_available() else synth.generate)(n_loci=28_000, seed=0, **c)
     if c.get('umi_dup_rate'):
         d = synth.apply_row_mask(d, synth.umi_dedup_mask(d))          # rows zeroed like model.py:1216
     print(f'{name} x{scale}: {d.n_cells} cells, {d.N} rows, {d.A} alignments, mode {mode} '
