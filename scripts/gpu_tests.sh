@@ -1,6 +1,4 @@
 #!/bin/bash
-# run on the GPU box: full gpu test suite, output to gpurun_out/
+# the -m gpu suite on a GPU box:  gpurun -- 'bash scripts/gpu_tests.sh'
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
-echo "exit=$?" >> gpurun_out/pytest_gpu.log
-tail -45 gpurun_out/pytest_gpu.log
+timeout 1500 python -W ignore -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/gpu_tests.log

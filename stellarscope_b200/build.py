@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.environ.get('STELLARSCOPE_B200_LIB') or os.path.join(HERE, 'libstellarscope_b200.so')
-SOURCES = ['ss_api.cu', 'ss_layout.cu', 'ss_build.cu', 'ss_em.cu', 'ss_dense.cu', 'ss_reassign.cu', 'ss_umi.cu', 'ss_scores.cu', 'ss_mtx.cu']
+SOURCES = ['ss_api.cu', 'ss_layout.cu', 'ss_build.cu', 'ss_em.cu', 'ss_dense.cu', 'ss_reassign.cu', 'ss_count.cu', 'ss_umi.cu', 'ss_scores.cu', 'ss_mtx.cu']
 HEADERS = ['ss_common.cuh', 'ss_em.cuh', 'ss_handle.h', 'ss_mtx_fmt.cuh', os.path.join('..', '..', 'include', 'stellarscope_b200.h')]
 HOSTUTIL_SRC = os.path.join(CSRC, 'ss_hostutil.c')
 HOSTUTIL = os.path.join(HERE, '_ss_hostutil.so')

@@ -318,6 +318,19 @@ int ss_count(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, const 
   return rc;
 }
 
+int ss_count_cells(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, int32_t n_cells, const int32_t* row_ptr,
+                   const int32_t* col_idx, const uint8_t* flag, const int32_t* row_cell, int64_t cap, int64_t* out_ptr,
+                   int32_t* out_col, int32_t* out_cnt, int64_t* n_out) {
+  SS_REQUIRE_HANDLE(h);
+  cudaSetDevice(h->device);
+  tl_alloc_stream = (cudaStream_t)stream;
+  long long n = 0;
+  int rc = count_cells(h, (cudaStream_t)stream, n_rows, n_cols, n_cells, row_ptr, col_idx, flag, row_cell, cap,
+                       reinterpret_cast<long long*>(out_ptr), out_col, out_cnt, &n);
+  if (n_out) *n_out = n;
+  return rc;
+}
+
 int ss_reassign_csr(ss_handle_t h, void* stream, int32_t n_rows, const int32_t* row_ptr, const int32_t* col_idx,
                     const uint8_t* flag, const int32_t* nbest, int64_t cap, int64_t* out_ptr, int32_t* out_idx,
                     double* out_val, int64_t* n_out) {

@@ -93,7 +93,12 @@ class _HostStager:
             self.ring = torch.empty(self.SLOTS * self.CHUNK, dtype=torch.uint8, pin_memory=True)
             self.ring_np = self.ring.numpy()
             self.events = [torch.cuda.Event() for _ in range(self.SLOTS)]
-            self.pool = ThreadPoolExecutor(max_workers=self.SLOTS, thread_name_prefix='ss_d2h')
+            import os
+            try:
+                nthr = int(os.environ.get('SS_HOST_THREADS', self.SLOTS))
+            except ValueError:
+                nthr = self.SLOTS
+            self.pool = ThreadPoolExecutor(max_workers=max(2, min(self.SLOTS, nthr)), thread_name_prefix='ss_d2h')
 
     def fetch(self, t):
         n = t.numel() * t.element_size()
@@ -697,6 +702,37 @@ class Engine:
             self._check(rc)
             torch.cuda.current_stream(dev).synchronize()          # r / c / v / off may go
             return out[:int(nbytes.value)]
+
+    def count_cells(self, flag, row_cell, n_cells, keep_device=False):
+        """ss_count_cells: integer counts per (cell, locus) without a sort, as the CSC form of the (loci x cells)
+        matrix: numpy ``(indptr int64[n_cells+1], loci int32[nnz], counts int32[nnz])``; with ``keep_device`` a
+        fourth element, the three device tensors (for the MTX writer).  Returns None when the loci do not fit the
+        kernel's shared-memory bins (the caller takes ``count``)."""
+        dev, k = self.device, self._keep
+        n_cells = int(n_cells)
+        with torch.cuda.device(dev):
+            rc_t = row_cell if isinstance(row_cell, torch.Tensor) else self._to_dev(row_cell, np.int32)
+            out_ptr = torch.empty(n_cells + 1, dtype=torch.int64, device=dev)
+            # upper bound of the result: selected alignments (flag bytes are 0 / 1)
+            cap = int(flag.sum(dtype=torch.int64)) if self.A else 0
+            cap = max(1, min(cap, n_cells * self.K))
+            oc = torch.empty(cap, dtype=torch.int32, device=dev)
+            ov = torch.empty(cap, dtype=torch.int32, device=dev)
+            n = C.c_int64(0)
+            rc = self.lib.ss_count_cells(self.h, self._stream(), self.N, self.K, n_cells, self._p(k['row_ptr']),
+                                         self._p(k['col_idx']), self._p(flag), self._p(rc_t), cap, self._p(out_ptr),
+                                         self._p(oc), self._p(ov), C.byref(n))
+            if rc == _lib.SS_ERR_CAPACITY:
+                return None
+            self._check(rc)
+            m = n.value
+            host = (to_host(out_ptr), to_host(oc[:m]), to_host(ov[:m]))
+            if not keep_device:
+                return host
+            kept = None
+            if 8 * m <= torch.cuda.mem_get_info(dev)[0] // 8:
+                kept = (out_ptr, oc[:m].clone(), ov[:m].clone())
+            return host + (kept,)
 
     def count(self, flag, row_cell, weight=None, row_umi=None, cap=None, keep_device=False):
         """ss_count.  Returns COO (cell, col, val) numpy arrays sorted by (cell, col); with ``keep_device`` a

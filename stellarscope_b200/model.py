@@ -735,6 +735,7 @@ def count_matrices(st, tl: TelescopeLikelihood):
         cm = remat.count_by_cell(row_cell, numbc, row_umi=row_umi, engine=tl._engine)
         if world > 1:
             cm.__dict__.pop('_ss_dev_coo', None)        # device triples of this rank's part only
+            cm.__dict__.pop('_ss_dev_csc', None)
             # every rank holds the counts of its own rows (a partition of all rows, parallel.plan_local_rows): the
             # COO triples of all ranks are concatenated -- tensors through all_gather_into_tensor, no pickled
             # matrices -- and entries of the same (locus, cell) add up (a cell cut across ranks: pseudobulk blocks)

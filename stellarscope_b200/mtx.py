@@ -64,6 +64,14 @@ def mmwrite(target, a, comment='', engine=None, device_coo=None):
     eng = engine if engine is not None and getattr(engine, 'h', None) else _default_engine()
     nnz = int(a.nnz)
     # the body is complete on the device before the file is touched: an unsupported value leaves no partial file
+    csc = getattr(a, '_ss_dev_csc', None)
+    if device_coo is None and csc is not None and int(csc[1].numel()) == nnz and integer:
+        # CSC arrays left on the device by ss_count_cells: expand the column pointers into one cell index per entry
+        import torch
+        ptr, loci, cnt = csc
+        cells = torch.repeat_interleave(torch.arange(ptr.numel() - 1, device=ptr.device, dtype=torch.int32),
+                                        (ptr[1:] - ptr[:-1]), output_size=nnz)
+        device_coo = (loci, cells, cnt.to(torch.float64))
     if device_coo is not None and all(int(t.numel()) == nnz for t in device_coo):
         text = eng.mtx_text(device_coo[0], device_coo[1], device_coo[2], integer)
     else:

@@ -85,15 +85,39 @@ class csr_matrix_plus(scipy.sparse.csr_matrix):
             weight = eng._to_dev(m.data.astype(np.float64), np.float64)
         return eng.count(flag, row_group, weight=weight, row_umi=row_umi, keep_device=keep_device)
 
+    def _count_cells_fast(self, row_cell, n_cells, engine):
+        """Integer counts of a matrix whose selection flags are still on the engine's device (``_ss_dev``): the
+        sort-free per-cell kernel (``ss_count_cells``) hands back the CSC arrays of the (K x n_cells) matrix
+        directly -- int32 counts, no (cell, locus) key per entry to sort or to bring home."""
+        dev = getattr(self, '_ss_dev', None)
+        if not (dev is not None and engine is not None and dev[0] is engine and getattr(engine, 'h', None)
+                and engine._keep.get('row_ptr') is dev[2] and dev[1].numel() == engine.A and engine.A > 0):
+            return None
+        rows = dev[3] if len(dev) > 3 else None
+        if rows is not None:
+            row_cell = np.ascontiguousarray(row_cell[rows])
+        res = engine.count_cells(dev[1], row_cell, n_cells, keep_device=True)
+        if res is None:
+            return None
+        indptr, col, cnt, kept = res
+        out = scipy.sparse.csc_matrix((cnt, col, indptr), shape=(self.shape[1], n_cells))
+        if kept is not None:
+            out._ss_dev_csc = kept           # (column pointers, loci, counts) on the device: mtx.mmwrite expands them
+        return out
+
     def count_by_cell(self, row_cell, n_cells, row_umi=None, engine=None):
         """(K x n_cells) matrix of per-cell column sums -- ``agg_bc`` /
         ``agg_bc_umi`` (model.py:1302-1345).  ``row_cell[i]`` = output column
         of row i (-1: dropped).  int32 for integer matrices, float64 otherwise
         and always float64 in UMI mode (model.py:1341)."""
+        integer = np.issubdtype(self.dtype, np.integer) and row_umi is None
+        if integer:
+            out = self._count_cells_fast(np.ascontiguousarray(row_cell, dtype=np.int32), n_cells, engine)
+            if out is not None:
+                return out
         cell, col, val, kept = self._device_coo(np.ascontiguousarray(row_cell, dtype=np.int32),
                                                 None if row_umi is None else np.ascontiguousarray(row_umi, np.int32),
                                                 engine, keep_device=True)
-        integer = np.issubdtype(self.dtype, np.integer) and row_umi is None
         dtype = np.int32 if integer else np.float64
         # the device returns the triples sorted by (cell, locus) without duplicates: that is the CSC form of the
         # (K x n_cells) matrix -- no host sort
