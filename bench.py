@@ -609,11 +609,45 @@ def run_ours(args):
         d2h = (4 * 4 + 8) * tl.n_segments      # iterations, flags, nobs, nfeats, lnL per model (the diff traces stay
                                                # on the device until a FitInfo.iterations is looked at)
         nmod = len(poolinfo.models_info)
-        tl.close()
+        if i < n_e2e:
+            tl.close()
     e2e_dt = float(np.mean(e2e_times))
 
+    # ---- the whole drop-in flow once: fit (above) + Stellarscope.reassign over the mode sweep + per-cell count
+    #      matrices + the MatrixMarket files (BASELINE.json configs[4]: reassign_mode sweep) ----
+    full = None
+    if args.full_flow:
+        import shutil
+        import tempfile
+        sweep = ['best_exclude', 'best_conf', 'best_random', 'best_average', 'total_hits']
+        opts.reassign_mode = sweep
+        st.opts = opts
+        tmpdir = tempfile.mkdtemp(prefix='ss_bench_')
+        opts.outfile_path = lambda suffix: os.path.join(tmpdir, suffix)
+        try:
+            barrier()
+            t0 = time.perf_counter()
+            model.reassign(st, tl)
+            barrier()
+            t1 = time.perf_counter()
+            write = shutil.disk_usage(tmpdir).free > 40 * d.A           # ~14 bytes of text per count entry, 5 files
+            if write:
+                model.output_report(st, tl)
+            else:
+                model.count_matrices(st, tl)
+            barrier()
+            t2 = time.perf_counter()
+            mtx_bytes = sum(os.path.getsize(os.path.join(tmpdir, f)) for f in os.listdir(tmpdir)) if rank == 0 else 0
+            full = dict(reassign_s=t1 - t0, report_s=t2 - t1, mtx_written=bool(write), mtx_bytes=int(mtx_bytes),
+                        modes=sweep)
+        finally:
+            shutil.rmtree(tmpdir, ignore_errors=True)
+            st.reassignments = {}
+    tl.close()
+
     # ---- reduce over ranks ----
-    tvec = torch.tensor([total_ms, e2e_dt, em_ms, build_ms], dtype=torch.float64, device=dev)
+    tvec = torch.tensor([total_ms, e2e_dt, em_ms, build_ms, full['reassign_s'] if full else 0.0,
+                         full['report_s'] if full else 0.0], dtype=torch.float64, device=dev)
     pv = [1.0, 1.0, 1.0, 1.0, 0.0, 0.0] if par is None else [
         float(par['counts_equal']), float(par['iters_equal']), float(par['lnl_ok']), float(par['max_rel_pi'] < 1e-6),
         float(par['max_rel_pi']), float(par['cells'])]
@@ -628,7 +662,7 @@ def run_ours(args):
         dist.all_reduce(uvec, op=dist.ReduceOp.SUM)
         dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
         dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
-    tmax_ms, e2e_max, em_max, build_max = tvec.tolist()
+    tmax_ms, e2e_max, em_max, build_max, reassign_max, report_max = tvec.tolist()
     (units_all, e2e_units_all, launches_all, h2d_all, d2h_all, alg_all, lane_all, clu_all, str_all, tiles_all,
      ctiles_all, stiles_all, par_cells, models_all) = uvec.tolist()
     if mode == 'pseudobulk':
@@ -668,6 +702,12 @@ def run_ours(args):
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d_all), d2h_bytes_per_step=int(d2h_all),
                      seconds_per_step=e2e_max, models_returned=int(nmod),
                      api='stellarscope_b200.model._fit_pooling_model(st, opts), st from host scipy CSR + row table'),
+            e2e_full=(dict(seconds=e2e_max + reassign_max + report_max, fit_s=e2e_max, reassign_s=reassign_max,
+                           count_and_mtx_s=report_max, value=e2e_units_all / (e2e_max + reassign_max + report_max),
+                           unit=UNIT, modes=full['modes'], mtx_written=full['mtx_written'], mtx_bytes=full['mtx_bytes'],
+                           what='_fit_pooling_model + Stellarscope.reassign over the five modes + output_report '
+                                '(per-cell count matrices, barcodes / features, one MatrixMarket file per mode), '
+                                'host matrices in, files out; max over ranks per stage') if full else None),
             gpu_launches=int(launches_all),
             roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
                           traffic=traffic, traffic_source=traffic_src,
@@ -717,6 +757,8 @@ def main():
     ap.add_argument('--cpu-budget-aln', dest='cpu_budget_aln', type=float, default=4e6,
                     help='alignments per CPU-baseline sample (about 10-30 s of CPU work)')
     ap.add_argument('--no-ref-as-written', dest='ref_as_written', action='store_false')
+    ap.add_argument('--no-full-flow', dest='full_flow', action='store_false',
+                    help='skip the one pass of reassign sweep + count matrices + MatrixMarket files (e2e_full)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':

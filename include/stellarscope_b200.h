@@ -179,6 +179,13 @@ int ss_count(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, const 
              const int32_t* row_umi, int64_t cap, int32_t* out_cell, int32_t* out_col, double* out_val,
              int64_t* n_out);
 
+/* The random modes (best_random model.py:446, initial_random :482-491; csr_matrix_plus.choose_random
+ * sparse_plus.py:199-240): in row tied_rows[i] -- a row in which ss_reassign flagged several tied-best alignments --
+ * keep only the picks[i]-th flagged alignment (0-based, in CSR order).  The picks are drawn by the caller (the
+ * reference's numpy generator, in row order); flag is updated in place.  Asynchronous. */
+int ss_reassign_pick(ss_handle_t h, void* stream, int32_t n_tied, const int32_t* tied_rows, const int32_t* picks,
+                     const int32_t* row_ptr, uint8_t* flag);
+
 /* Per-cell integer counts without a sort (agg_bc, model.py:1302-1320, for the integer reassignment modes without
  * --umi_counts): the (loci x cells) count matrix in CSC form.  One CTA per cell accumulates the cell's selected
  * alignments in shared-memory bins over the loci.

@@ -4,7 +4,8 @@ wavefront per distinct 8-byte word that shares a bank pair.  Baseline order vs a
 alignments over the four slots.   python scripts/bank_conflict_sim.py"""
 import numpy as np, itertools, sys
 sys.path.insert(0,'.')
-from stellarscope_b200 import layout_fm, layout_host, synth
+import layout_fm
+from stellarscope_b200 import layout_host, synth
 d = synth.generate(n_cells=60, n_alignments=30000, n_loci=28000, seed=1)
 L = layout_host.build(d.indptr, d.indices, d.scores, d.row_cell, d.n_cells, d.K)
 def waves(words):   # words: list of 8-byte word indices of the active lanes of a half warp

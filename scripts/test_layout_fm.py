@@ -5,7 +5,10 @@ columns that overflow the lane budget, and the records account for every alignme
 import numpy as np
 import pytest
 
-from stellarscope_b200 import layout_fm, layout_host
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import layout_fm
+from stellarscope_b200 import layout_host
 
 
 def _layout(seed, n_cells, n_alignments, max_k=32, n_loci=300):

@@ -215,7 +215,7 @@ def _table_from_dicts(st):
     row_bcode = np.full(N, -1, dtype=np.int32)
     try:
         hostutil.row_labels(ri, rb, code, row_bcode)
-        by_set = np.full(N, -2, dtype=np.int32)
+        by_set = np.full(N, -1, dtype=np.int32)
         hostutil.fill_row_segments(list(groups.values()), np.arange(len(bcodes), dtype=np.int32), by_set)
     except (KeyError, ValueError, IndexError, TypeError):
         return None
@@ -324,12 +324,21 @@ def save(st, filename):
             'matrices': meta, 'maps': [k for k in ROW_MAPS if hasattr(st, k)],
             'bu_keys': None if t.bu_keys is None else sorted(t.bu_keys), 'default_maps': dict(t.default_maps)}
     side = sidecar_path(filename)
-    tmp = side + '.tmp'
-    with open(tmp, 'wb') as fh:
-        np.savez(fh, **arrays)                             # stored, not deflated: the arrays go out at disk speed
-    os.replace(tmp, side)
-    with open(filename, 'wb') as fh:
-        pickle.dump((MAGIC, head, light), fh)
+    # both files are written completely under temporary names first (a full disk or a crash while writing leaves
+    # the previous checkpoint pair untouched), then put in place by two renames back to back
+    tmp_side, tmp_pkl = side + '.tmp', str(filename) + '.tmp'
+    try:
+        with open(tmp_side, 'wb') as fh:
+            np.savez(fh, **arrays)                         # stored, not deflated: the arrays go out at disk speed
+        with open(tmp_pkl, 'wb') as fh:
+            pickle.dump((MAGIC, head, light), fh)
+    except BaseException:
+        for f in (tmp_side, tmp_pkl):
+            if os.path.exists(f):
+                os.remove(f)
+        raise
+    os.replace(tmp_side, side)
+    os.replace(tmp_pkl, filename)
     return True
 
 

@@ -318,6 +318,13 @@ int ss_count(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, const 
   return rc;
 }
 
+int ss_reassign_pick(ss_handle_t h, void* stream, int32_t n_tied, const int32_t* tied_rows, const int32_t* picks,
+                     const int32_t* row_ptr, uint8_t* flag) {
+  SS_REQUIRE_HANDLE(h);
+  cudaSetDevice(h->device);
+  return reassign_pick(h, (cudaStream_t)stream, n_tied, tied_rows, picks, row_ptr, flag);
+}
+
 int ss_count_cells(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, int32_t n_cells, const int32_t* row_ptr,
                    const int32_t* col_idx, const uint8_t* flag, const int32_t* row_cell, int64_t cap, int64_t* out_ptr,
                    int32_t* out_col, int32_t* out_cnt, int64_t* n_out) {

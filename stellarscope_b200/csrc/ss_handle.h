@@ -181,6 +181,8 @@ int count(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, const int* ro
           const uint8_t* flag, const double* weight, const int* row_cell, const int* row_umi, long long cap,
           int* out_cell, int* out_col, double* out_val, long long* n_out);
 
+int reassign_pick(ss_handle_s* h, cudaStream_t st, int n_tied, const int* tied_rows, const int* picks, const int* row_ptr,
+                  uint8_t* flag);
 // ss_count.cu
 int count_cells(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, int n_cells, const int* row_ptr, const int* col_idx,
                 const uint8_t* flag, const int* row_cell, long long cap, long long* out_ptr, int* out_col, int* out_cnt,

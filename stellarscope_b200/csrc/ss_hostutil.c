@@ -614,6 +614,11 @@ static void* plan_main(void* arg) {
         const int32_t s = w->seg[r];
         if (s >= 0 && s < w->S) w->part[s] += ld_ix(w->ip, w->ip_size, r + 1) - ld_ix(w->ip, w->ip_size, r);
       }
+    } else if (w->mode == 3) {
+      for (Py_ssize_t r = a; r < b; ++r) {
+        const int32_t s = w->seg[r];
+        if (s >= 0 && s < w->S) w->part[s] += 1;
+      }
     } else if (w->mode == 1) {
       int64_t k = 0;
       for (Py_ssize_t r = a; r < b; ++r) {
@@ -659,7 +664,10 @@ static PyObject* segment_alignments(PyObject* self, PyObject* args) {
   if (!PyArg_ParseTuple(args, "y*y*w*", &ip, &seg, &out)) return NULL;
   PyObject* result = NULL;
   const Py_ssize_t n = seg.len / 4, S = out.len / 8;
-  if ((ip.itemsize != 4 && ip.itemsize != 8) || seg.itemsize != 4 || out.itemsize != 8 || ip.len / ip.itemsize != n + 1) {
+  /* indptr of length 0: count ROWS per model instead of alignments (group_sizes) */
+  const int rows_only = ip.len == 0;
+  if ((!rows_only && ((ip.itemsize != 4 && ip.itemsize != 8) || ip.len / ip.itemsize != n + 1)) || seg.itemsize != 4 ||
+      out.itemsize != 8) {
     PyErr_SetString(PyExc_TypeError, "segment_alignments: indptr int32/int64 [N+1], row_segment int32 [N], out int64 [S]");
     goto done;
   }
@@ -676,7 +684,7 @@ static PyObject* segment_alignments(PyObject* self, PyObject* args) {
     for (int i = 0; i < nt; ++i) {
       memset(&w[i], 0, sizeof(plan_t));
       w[i].ip = (const char*)ip.buf; w[i].ip_size = ip.itemsize; w[i].seg = (const int32_t*)seg.buf;
-      w[i].n = n; w[i].S = S; w[i].part = parts + (size_t)i * (size_t)(S > 0 ? S : 1); w[i].mode = 0;
+      w[i].n = n; w[i].S = S; w[i].part = parts + (size_t)i * (size_t)(S > 0 ? S : 1); w[i].mode = rows_only ? 3 : 0;
       w[i].c0 = (Py_ssize_t)SS_NCH * i / nt; w[i].c1 = (Py_ssize_t)SS_NCH * (i + 1) / nt;
     }
     int started = 0;

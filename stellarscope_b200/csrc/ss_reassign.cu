@@ -320,6 +320,38 @@ int count(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, const int* ro
 }
 
 // ---------------------------------------------------------------------------
+// choose_random(1, rng) (sparse_plus.py:199-240): in every row with several tied-best alignments keep the one the
+// host drew.  The draws stay on the host (numpy's PCG64 stream, in row order -- INTEGRATION.md section 3); only the
+// tied rows and their picks travel.  One thread per tied row.
+// ---------------------------------------------------------------------------
+__global__ void pick_kernel(int n_tied, const int* __restrict__ tied_rows, const int* __restrict__ picks,
+                            const int* __restrict__ row_ptr, uint8_t* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_tied) return;
+  const int row = tied_rows[i], want = picks[i];
+  int seen = 0;
+  for (int k = row_ptr[row]; k < row_ptr[row + 1]; ++k) {
+    if (!flag[k]) continue;
+    if (seen != want) flag[k] = 0;
+    ++seen;
+  }
+}
+
+int reassign_pick(ss_handle_s* h, cudaStream_t st, int n_tied, const int* tied_rows, const int* picks, const int* row_ptr,
+                  uint8_t* flag) {
+  if (n_tied < 0 || (n_tied > 0 && (!tied_rows || !picks || !row_ptr || !flag))) {
+    h->set_error("ss_reassign_pick: bad argument");
+    return SS_ERR_ARG;
+  }
+  if (n_tied > 0) {
+    pick_kernel<<<(n_tied + 255) / 256, 256, 0, st>>>(n_tied, tied_rows, picks, row_ptr, flag);
+    h->launches++;
+    SS_CUDA_CHECK(h, cudaGetLastError());
+  }
+  return SS_OK;
+}
+
+// ---------------------------------------------------------------------------
 // the reassignment matrix as CSR: compaction of the flagged alignments
 // ---------------------------------------------------------------------------
 __global__ void select_count_kernel(int n_rows, const int* __restrict__ row_ptr, const uint8_t* __restrict__ flag,

@@ -657,8 +657,27 @@ class Engine:
             self._check(rc)
             return flag[:self.A], nbest[:self.N], info.cpu().numpy()
 
+    def tied_rows(self, nbest):
+        """Rows with more than one tied-best alignment (ascending) and their tie-set sizes, as host arrays -- all
+        the host needs to draw the picks of the random modes."""
+        with torch.cuda.device(self.device):
+            rows = torch.nonzero(nbest > 1).reshape(-1).to(torch.int32)
+            return to_host(rows), to_host(nbest[rows.long()])
+
+    def reassign_pick(self, flag, tied_rows, picks):
+        """ss_reassign_pick: keep the drawn alignment in every tied row (``flag`` is updated in place)."""
+        n = len(tied_rows)
+        if n == 0:
+            return
+        with torch.cuda.device(self.device):
+            tr = self._to_dev(tied_rows, np.int32)
+            pk = self._to_dev(picks, np.int32)
+            self._check(self.lib.ss_reassign_pick(self.h, self._stream(), n, self._p(tr), self._p(pk),
+                                                  self._p(self._keep['row_ptr']), self._p(flag)))
+            torch.cuda.current_stream(self.device).synchronize()      # tr / pk may go
+
     def reassign_csr(self, flag, nbest=None, fractions=False):
-        """ss_reassign_csr: the flagged alignments as CSR.  Returns numpy (indptr int64[N+1], indices int32[n],
+        """ss_reassign_csr: the flagged alignments as CSR.  Returns numpy (indptr int32 / int64 [N+1], indices int32[n],
         values float64[n] or None); ``fractions``: 1 / nbest per selected alignment (best_average)."""
         dev, k = self.device, self._keep
         with torch.cuda.device(dev):
@@ -671,6 +690,8 @@ class Engine:
                                           self._p(out_ptr), self._p(out_idx), self._p(out_val), C.byref(n))
             self._check(rc)
             m = n.value
+            if m < 2 ** 31:
+                out_ptr = out_ptr.to(torch.int32)         # half the bytes to bring home; scipy's index dtype anyway
             return to_host(out_ptr), to_host(out_idx[:m]), (to_host(out_val[:m]) if fractions else None)
 
     def mtx_text(self, row, col, val, integer):
@@ -729,9 +750,9 @@ class Engine:
             host = (to_host(out_ptr), to_host(oc[:m]), to_host(ov[:m]))
             if not keep_device:
                 return host
-            kept = None
-            if 8 * m <= torch.cuda.mem_get_info(dev)[0] // 8:
-                kept = (out_ptr, oc[:m].clone(), ov[:m].clone())
+            # compact device copies for the MTX writer (the cap-sized buffers go); cudaMemGetInfo costs ~20 ms a call,
+            # so the size is checked against a fixed bound instead (2^28 entries = 2 GB)
+            kept = (out_ptr, oc[:m].clone(), ov[:m].clone()) if m <= (1 << 28) else None
             return host + (kept,)
 
     def count(self, flag, row_cell, weight=None, row_umi=None, cap=None, keep_device=False):
@@ -761,7 +782,5 @@ class Engine:
             host = (to_host(oc[:m]), to_host(ol[:m]), to_host(ov[:m]))
             if not keep_device:
                 return host
-            kept = None
-            if 16 * m <= torch.cuda.mem_get_info(dev)[0] // 8:
-                kept = (oc[:m].clone(), ol[:m].clone(), ov[:m].clone())      # the cap-sized buffers go
+            kept = (oc[:m].clone(), ol[:m].clone(), ov[:m].clone()) if m <= (1 << 28) else None   # the cap-sized buffers go
             return host + (kept,)

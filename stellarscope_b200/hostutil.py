@@ -97,3 +97,12 @@ def rows_of_rank(row_segment, model_rank, local_id, rank):
     lseg = np.empty(n, dtype=np.int32)
     load().fill_rows(row_segment, model_rank, local_id, int(rank), off, rows, lseg)
     return rows, lseg
+
+
+def group_sizes(codes, n_groups):
+    """int64[n_groups]: number of rows with every code (negative codes count nowhere) -- ``np.bincount`` without
+    the int64 copy of 10^8 codes, on a few threads."""
+    import numpy as np
+    out = np.zeros(int(n_groups), dtype=np.int64)
+    load().segment_alignments(np.zeros(0, dtype=np.int32), np.ascontiguousarray(codes, dtype=np.int32), out)
+    return out

@@ -127,6 +127,7 @@ class TelescopeLikelihood(object):
     def close(self):
         """Give the device resources back (the engine handle returns to a pool)."""
         eng, self._engine = getattr(self, '_engine', None), None
+        self._steps_obj = None
         if eng is not None:
             eng.release()
 
@@ -256,6 +257,12 @@ class TelescopeLikelihood(object):
         """model.py:325-373 for a single-model object."""
         if self.n_segments != 1:
             raise StellarscopeError('em() is for a single model; use fit_segments()')
+        # pi_init / theta_init: the parameters after the FIRST M-step (model.py:336-337) = the result of a
+        # one-iteration fit; it costs one iteration of ~50 and keeps the attribute contract of the reference
+        eng = self._engine
+        eng.fit(self.epsilon, 1, self.pi_prior, self.theta_prior, False)
+        pi1, theta1 = eng.dense_params(0)
+        self.pi_init, self.theta_init = csr_matrix_plus(pi1), theta1
         fi = self.fit_segments()[0]
         self.fitinfo = fi
         pi, theta = self._engine.dense_params(0)
@@ -270,6 +277,28 @@ class TelescopeLikelihood(object):
             lg.log(loglev, f'EM terminated after {len(fi.iterations):d} iterations.')
         lg.log(loglev, f'Final log-likelihood: {self.lnl:f}.')
         return
+
+    # -- single steps (model.py:202-323): for callers that drive the iteration themselves; em() does not use them --
+    def _steps(self):
+        if getattr(self, '_steps_obj', None) is None:
+            from .steps import ModelSteps
+            self._steps_obj = ModelSteps(self)
+        return self._steps_obj
+
+    def estep(self, pi, theta):
+        """E(z[i,j]) for the given parameters: N x K CSR (model.py:202-226)."""
+        return self._steps().estep(pi, theta)
+
+    def mstep(self, z):
+        """MAP estimates ``(pi 1 x K sparse, theta K array)`` from z (model.py:229-272)."""
+        try:
+            return self._steps().mstep(z)
+        except FloatingPointError as e:
+            raise StellarscopeError(e.args)                    # model.py:267-272
+
+    def calculate_lnl(self, z, pi, theta):
+        """sum_ij z_ij log(Q_ij pi_j theta_j^Y_i) (model.py:276-323)."""
+        return self._steps().calculate_lnl(z, pi, theta)
 
     def segment_params(self, seg):
         """(pi, theta) dense K-vectors of one model of a pooled fit."""
@@ -308,33 +337,25 @@ class TelescopeLikelihood(object):
                 # lets count_by_cell aggregate without uploading the matrix again (while the engine still holds this matrix)
                 mat._ss_dev = (self._engine, flag, self._engine._keep.get('row_ptr'), self._row_ids)
             return mat, rinfo
-        flag = to_host(flag).view(np.bool_)                     # 0 / 1 bytes
-        nbest = to_host(nbest)
-        if self._row_ids is None:
-            lptr, lidx = self.raw_scores.indptr.astype(np.int64), self.raw_scores.indices
-        else:
-            lptr = to_host(self._engine._keep['row_ptr']).astype(np.int64)
-            lidx = to_host(self._engine._keep['col_idx'])
-        n_local = len(lptr) - 1
-        row = np.repeat(np.arange(n_local, dtype=np.int64), np.diff(lptr))
-        tied_rows = np.flatnonzero(nbest > 1)
+        # random modes: the tie sets come from the device, the draws from the reference's numpy generator in row
+        # order (one vectorised rng.integers call gives the stream of the reference's per-row rng.choice calls,
+        # tests/test_oracle.py), the picked alignment is kept on the device and the matrix compacted there
+        tied_rows, nb_tied = self._engine.tied_rows(nbest)
         if self._sharded():
             # one stream of draws for the whole matrix, in global row order, on every rank (the reference draws
             # row by row, sparse_plus.py:233-238): gather the tie sets, draw them all, keep the own rows' picks
             from . import parallel
-            g = parallel.gather_concat({'row': self._row_ids[tied_rows], 'n': nbest[tied_rows].astype(np.int64)},
-                                       self._group)
+            g = parallel.gather_concat({'row': self._row_ids[tied_rows], 'n': nb_tied.astype(np.int64)}, self._group)
             order = np.argsort(g['row'], kind='stable')
             picks_all = self.opts.rng.integers(0, g['n'][order]) if len(order) else np.zeros(0, dtype=np.int64)
             picks = picks_all[np.searchsorted(g['row'][order], self._row_ids[tied_rows])]
         else:
-            picks = self.opts.rng.integers(0, nbest[tied_rows]) if len(tied_rows) else np.zeros(0, dtype=np.int64)
-        flag = _apply_random_choice(flag, row, nbest, tied_rows, picks)
-        keep_rows = row[flag]
-        ptr = np.zeros(n_local + 1, dtype=np.int64)
-        np.cumsum(np.bincount(keep_rows, minlength=n_local), out=ptr[1:])
-        data = np.ones(len(keep_rows), dtype=np.int8)
-        mat = csr_matrix_plus((data, lidx[flag], self._global_indptr(ptr, indptr_dtype)), shape=self.raw_scores.shape)
+            picks = self.opts.rng.integers(0, nb_tied) if len(tied_rows) else np.zeros(0, dtype=np.int64)
+        self._engine.reassign_pick(flag, tied_rows, picks)
+        ptr, idx, _ = self._engine.reassign_csr(flag)
+        mat = csr_matrix_plus((np.ones(len(idx), dtype=np.int8), idx, self._global_indptr(ptr, indptr_dtype)),
+                              shape=self.raw_scores.shape)
+        mat._ss_dev = (self._engine, flag, self._engine._keep.get('row_ptr'), self._row_ids)
         return mat, rinfo
 
 
@@ -427,7 +448,8 @@ def _row_segments_from_table(st, opts, table):
     code = table.row_bcode
     nb = len(table.bcodes)
     all_coded = len(code) == 0 or int(code.min()) >= 0            # every row belongs to a barcode (the usual case)
-    counts = np.bincount(code if all_coded else code[code >= 0], minlength=nb)
+    from . import hostutil
+    counts = hostutil.group_sizes(code, nb)
     if opts.pooling_mode == 'individual':
         has = counts > 0
         if all_coded and has.all():
@@ -676,7 +698,12 @@ def _row_outputs(st, bc_pos):
         # loaded from a side-car checkpoint: barcode / UMI codes per row are arrays already
         pos = np.fromiter((bc_pos.get(b, -1) for b in table.bcodes), dtype=np.int32, count=len(table.bcodes))
         code = table.row_bcode
-        row_cell = np.where(code >= 0, pos[np.maximum(code, 0)] if len(pos) else -1, -1).astype(np.int32)
+        if len(code) and int(code.min()) >= 0 and np.array_equal(pos, np.arange(len(pos), dtype=np.int32)):
+            row_cell = code                       # barcodes are in output order already and every row has one
+        elif len(code) and int(code.min()) >= 0:
+            row_cell = pos[code]
+        else:
+            row_cell = np.where(code >= 0, pos[np.maximum(code, 0)] if len(pos) else -1, -1).astype(np.int32)
         return row_cell, (table.row_umi.copy() if want_umi else None)
     if type(st.read_index) is dict and type(st.read_bcode_map) is dict and (not want_umi or type(st.read_umi_map) is dict):
         from . import hostutil
@@ -685,11 +712,12 @@ def _row_outputs(st, bc_pos):
         if type(groups) is dict and groups:
             # barcode -> row set is filled together with read -> barcode (store_read_info, model.py:1044-1053): walking
             # the ~10^4 sets is 100 x cheaper than one dict look-up per read; used when the sets cover every row once
-            cand = np.full(N, -2, dtype=np.int32)
+            cand = np.full(N, -1, dtype=np.int32)            # the helper's own "unclaimed" value (threaded path)
             ids = np.fromiter((bc_pos.get(b, -1) for b in groups), dtype=np.int32, count=len(groups))
             try:
-                hostutil.fill_row_segments(list(groups.values()), ids, cand)
-                if not (cand == -2).any():
+                # number of rows the sets claimed: equal to N only when they cover every row (each exactly once --
+                # a row claimed by two barcodes raises); otherwise read_bcode_map decides, like the reference
+                if hostutil.fill_row_segments(list(groups.values()), ids, cand) == N:
                     row_cell = cand
             except (ValueError, IndexError):
                 row_cell = None
@@ -730,9 +758,10 @@ def count_matrices(st, tl: TelescopeLikelihood):
     world, rank = _dist_info()
     if not getattr(st.opts, 'shard_models', True):
         world = 1
+    dev_cache = {}                       # the row -> output column map goes to the device once for all modes
     for _rmode in st.opts.reassign_mode:
         remat = st.reassignments[_rmode]
-        cm = remat.count_by_cell(row_cell, numbc, row_umi=row_umi, engine=tl._engine)
+        cm = remat.count_by_cell(row_cell, numbc, row_umi=row_umi, engine=tl._engine, cache=dev_cache)
         if world > 1:
             cm.__dict__.pop('_ss_dev_coo', None)        # device triples of this rank's part only
             cm.__dict__.pop('_ss_dev_csc', None)
@@ -805,10 +834,14 @@ def install():
     """Make ``stellarscope assign`` / ``resume`` use this implementation:
     rebinds the hot-path names of the reference's ``stellarscope.utils.model``
     (must be importable) -- see INTEGRATION.md."""
-    global StellarscopeError
+    global StellarscopeError, PoolInfo, ReassignInfo
     import stellarscope
     import stellarscope.utils.model as ref
+    import stellarscope.utils.statistics as ref_stats
+    from . import statistics
     StellarscopeError = stellarscope.StellarscopeError
+    # the result records are the reference's own classes from here on (PoolInfo only adds vectorised totals)
+    PoolInfo, ReassignInfo = statistics.bind_reference_records(ref_stats)
     from . import sparse_plus
     sparse_plus.StellarscopeError = StellarscopeError
     ref.TelescopeLikelihood = TelescopeLikelihood

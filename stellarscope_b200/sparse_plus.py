@@ -85,7 +85,7 @@ class csr_matrix_plus(scipy.sparse.csr_matrix):
             weight = eng._to_dev(m.data.astype(np.float64), np.float64)
         return eng.count(flag, row_group, weight=weight, row_umi=row_umi, keep_device=keep_device)
 
-    def _count_cells_fast(self, row_cell, n_cells, engine):
+    def _count_cells_fast(self, row_cell, n_cells, engine, cache=None):
         """Integer counts of a matrix whose selection flags are still on the engine's device (``_ss_dev``): the
         sort-free per-cell kernel (``ss_count_cells``) hands back the CSC arrays of the (K x n_cells) matrix
         directly -- int32 counts, no (cell, locus) key per entry to sort or to bring home."""
@@ -94,9 +94,14 @@ class csr_matrix_plus(scipy.sparse.csr_matrix):
                 and engine._keep.get('row_ptr') is dev[2] and dev[1].numel() == engine.A and engine.A > 0):
             return None
         rows = dev[3] if len(dev) > 3 else None
-        if rows is not None:
-            row_cell = np.ascontiguousarray(row_cell[rows])
-        res = engine.count_cells(dev[1], row_cell, n_cells, keep_device=True)
+        rc = cache.get('row_cell_dev') if cache is not None else None
+        if rc is None:
+            if rows is not None:
+                row_cell = np.ascontiguousarray(row_cell[rows])
+            rc = engine._to_dev(row_cell, np.int32)
+            if cache is not None:
+                cache['row_cell_dev'] = rc
+        res = engine.count_cells(dev[1], rc, n_cells, keep_device=True)
         if res is None:
             return None
         indptr, col, cnt, kept = res
@@ -105,14 +110,14 @@ class csr_matrix_plus(scipy.sparse.csr_matrix):
             out._ss_dev_csc = kept           # (column pointers, loci, counts) on the device: mtx.mmwrite expands them
         return out
 
-    def count_by_cell(self, row_cell, n_cells, row_umi=None, engine=None):
+    def count_by_cell(self, row_cell, n_cells, row_umi=None, engine=None, cache=None):
         """(K x n_cells) matrix of per-cell column sums -- ``agg_bc`` /
         ``agg_bc_umi`` (model.py:1302-1345).  ``row_cell[i]`` = output column
         of row i (-1: dropped).  int32 for integer matrices, float64 otherwise
         and always float64 in UMI mode (model.py:1341)."""
         integer = np.issubdtype(self.dtype, np.integer) and row_umi is None
         if integer:
-            out = self._count_cells_fast(np.ascontiguousarray(row_cell, dtype=np.int32), n_cells, engine)
+            out = self._count_cells_fast(np.ascontiguousarray(row_cell, dtype=np.int32), n_cells, engine, cache)
             if out is not None:
                 return out
         cell, col, val, kept = self._device_coo(np.ascontiguousarray(row_cell, dtype=np.int32),

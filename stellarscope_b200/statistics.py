@@ -396,3 +396,38 @@ class UMIInfo(GenericInfo):
         for ncomp in range(1, self.max_comps + 1):
             ret.loc[len(ret.index)] = ['UMIInfo', 'compdist', ncomp, self.ncomps_umi[ncomp]]
         return ret
+
+
+def bind_reference_records(ref_stats):
+    """``model.install()``: use the reference's OWN record classes where the reference package is importable
+    (``stellarscope.utils.statistics``): ``ReassignInfo`` as it is, ``PoolInfo`` subclassed only to keep the
+    vectorised totals over the device result arrays (its loop over ``models_info.items()`` would build 10^5
+    ``FitInfo`` objects).  The classes above remain for the reference-less GPU box; tests compare the two
+    (tests/test_statistics_vs_reference.py).  Returns ``(PoolInfo, ReassignInfo)``."""
+    class PoolInfo(ref_stats.PoolInfo):
+        __doc__ = ref_stats.PoolInfo.__doc__
+
+        def __init__(self, pooling_mode=None):
+            super().__init__(pooling_mode)
+            self.infotype = 'PoolInfo'
+
+        @property
+        def total_lnl(self):
+            if self._total_lnl is None and isinstance(self.models_info, SegmentFitInfos):
+                self._total_lnl = self.models_info.total_lnl()
+            return ref_stats.PoolInfo.total_lnl.fget(self)
+
+        @property
+        def total_obs(self):
+            if self._total_obs is None and isinstance(self.models_info, SegmentFitInfos):
+                self._total_obs = self.models_info.total_obs()
+            return ref_stats.PoolInfo.total_obs.fget(self)
+
+        @property
+        def total_params(self):
+            if self._total_params is None and isinstance(self.models_info, SegmentFitInfos):
+                self._total_params = self.models_info.total_params()
+            return ref_stats.PoolInfo.total_params.fget(self)
+
+    PoolInfo.__name__ = PoolInfo.__qualname__ = 'PoolInfo'
+    return PoolInfo, ref_stats.ReassignInfo

@@ -271,6 +271,18 @@ def test_install_rebinds_the_reference_names(tmp_path):
         assert ref._fit_pooling_model is b200._fit_pooling_model and ref._em_wrapper is b200._em_wrapper
         import stellarscope
         assert b200.StellarscopeError is stellarscope.StellarscopeError
+        import stellarscope.utils.statistics as ref_stats
+        assert b200.ReassignInfo is ref_stats.ReassignInfo         # the reference's own record classes
+        assert issubclass(b200.PoolInfo, ref_stats.PoolInfo) and b200.PoolInfo.log is ref_stats.PoolInfo.log
+        import numpy as np
+        from stellarscope_b200.statistics import SegmentFitInfos, PoolInfo as LocalPool
+        res = dict(iters=np.array([3, 5]), flags=np.array([1, 2]), lnl=np.array([10.5, -2.25]), nobs=np.array([7, 9]),
+                   nfeats=np.array([4, 6]), diffs=np.zeros((2, 5)))
+        a, b = b200.PoolInfo('individual'), LocalPool('individual')
+        a.models_info = SegmentFitInfos(res, 1e-7, 5, 0.0).keyed([0, 1])
+        b.models_info = SegmentFitInfos(res, 1e-7, 5, 0.0).keyed([0, 1])
+        assert (a.total_lnl, a.total_obs, a.total_params, a.AIC, a.BIC) == (b.total_lnl, b.total_obs, b.total_params, b.AIC, b.BIC)
+        assert a.to_dataframe().equals(b.to_dataframe())
         obj = ref.Stellarscope.__new__(ref.Stellarscope)
         obj.__dict__.update(pickle.load(open({src!r}, 'rb')))
         for name in ('reassign', 'output_report', 'dedup_umi', 'load_alignment', 'save'):

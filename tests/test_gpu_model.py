@@ -184,3 +184,64 @@ def test_config1_reproduces_telescope_report():
     counts, bc, ft = model.count_matrices(st, tl)
     pi = np.asarray(tl.pi.toarray()).ravel()
     config1_report_check(g, pi, {m: np.asarray(counts[m].todense())[:, 0] for m in opts.reassign_mode})
+
+
+def test_tie_rule_inside_and_outside_the_tolerance():
+    """The device calls two alignments tied when z >= max * (1 - tie_tol) (relative, 1e-9 by default; the
+    reference compares for exact equality, sparse_plus.py:171-174, and produces exact ties only from bit-identical
+    parameters -- SURVEY.md 0.10).  A row whose runner-up lies INSIDE the margin without being equal is a tie here
+    (ambiguous, dropped by best_exclude, split by best_average); just outside the margin it is assigned; with
+    tie_tol = 0 the rule is the reference's."""
+    import torch
+    from stellarscope_b200.engine import Engine
+    eng = Engine()
+    rows = [[0.5, 0.5 * (1 - 1e-12), 1e-3],          # inside the tolerance, not equal
+            [0.5, 0.5 * (1 - 1e-6), 1e-3],           # outside
+            [0.4, 0.4, 0.2],                          # exact tie
+            [0.7, 0.2, 0.1]]
+    m = sp.csr_matrix(np.array(rows))
+    eng.set_matrix(m.indptr, m.indices, np.ones(m.nnz, dtype=np.uint16), 3)
+    z = torch.from_numpy(m.data.copy()).to(eng.device)
+    flag, nbest, info = eng.reassign('best_exclude', z, tie_tol=1e-9)
+    assert nbest.cpu().numpy().tolist() == [2, 1, 2, 1]
+    assert flag.cpu().numpy().reshape(4, 3).tolist() == [[0, 0, 0], [1, 0, 0], [0, 0, 0], [1, 0, 0]]
+    assert (int(info[0]), int(info[1]), int(info[2])) == (2, 2, 0)
+    flag, nbest, info = eng.reassign('best_average', z, tie_tol=1e-9)
+    assert flag.cpu().numpy().reshape(4, 3).tolist() == [[1, 1, 0], [1, 0, 0], [1, 1, 0], [1, 0, 0]]
+    flag, nbest, info = eng.reassign('best_exclude', z, tie_tol=0.0)       # the reference's exact rule
+    assert nbest.cpu().numpy().tolist() == [1, 1, 2, 1]
+    assert (int(info[0]), int(info[1])) == (3, 1)
+    eng.close()
+
+
+def test_single_steps_and_init_parameters_match_the_oracle():
+    """estep / mstep / calculate_lnl (reference model.py:202-323) and pi_init / theta_init (:336-337) of the drop-in
+    class against the oracle's, on a model with unique and ambiguous rows; one hand-driven EM iteration equals the
+    first iteration of em()."""
+    from oracle.em_oracle import OracleLikelihood, Opts
+    from stellarscope_b200 import model
+    d = H.small_synth(seed=21, n_cells=6, n_alignments=4000, n_loci=150, unique_frac=0.15)
+    opts = H.StOpts()
+    m = sp.csr_matrix((d.scores, d.indices, d.indptr), shape=(d.N, d.K))
+    tl = model.TelescopeLikelihood(m, opts)
+    om = OracleLikelihood(d.indptr.astype(np.int64), d.indices.astype(np.int64), d.scores, d.K, Opts())
+    pi0, th0 = np.repeat(1.0 / d.K, d.K), np.repeat(1.0 / d.K, d.K)
+    z = tl.estep(sp.csr_matrix(pi0), th0)
+    zo = np.asarray(om.estep(pi0, th0), dtype=np.float64)
+    assert z.shape == (d.N, d.K) and np.max(np.abs(z.data - zo)) < 1e-12
+    pi1, th1 = tl.mstep(z)
+    pio, tho = om.mstep(zo)
+    pio, tho = np.asarray(pio, dtype=np.float64).ravel(), np.asarray(tho, dtype=np.float64).ravel()
+    assert sp.issparse(pi1) and pi1.shape == (1, d.K) and th1.shape == (d.K,)
+    assert np.allclose(np.asarray(pi1.todense()).ravel(), pio, rtol=1e-12, atol=0)
+    assert np.allclose(th1, tho, rtol=1e-12, atol=0)
+    lnl = tl.calculate_lnl(z, pi1, th1)
+    lo = float(om.calculate_lnl(zo, pio, tho))
+    assert abs(lnl - lo) <= 1e-10 * abs(lo)
+    tl.em()
+    om.em()
+    assert np.allclose(np.asarray(tl.pi_init.todense()).ravel(), np.asarray(om.pi_init, dtype=np.float64).ravel(), rtol=1e-9, atol=0)
+    assert np.allclose(tl.theta_init, np.asarray(om.theta_init, dtype=np.float64).ravel(), rtol=1e-9, atol=0)
+    assert np.allclose(np.asarray(tl.pi_init.todense()).ravel(), pio, rtol=1e-9, atol=0)     # the hand-driven iteration
+    assert len(tl.fitinfo.iterations) == len(om.fitinfo.iterations)
+    tl.close()
