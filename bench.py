@@ -609,6 +609,7 @@ def run_ours(args):
         d2h = (4 * 4 + 8) * tl.n_segments      # iterations, flags, nobs, nfeats, lnL per model (the diff traces stay
                                                # on the device until a FitInfo.iterations is looked at)
         nmod = len(poolinfo.models_info)
+        host_t = getattr(tl, 'host_timings', None)
         if i < n_e2e:
             tl.close()
     e2e_dt = float(np.mean(e2e_times))
@@ -616,7 +617,7 @@ def run_ours(args):
     # ---- the whole drop-in flow once: fit (above) + Stellarscope.reassign over the mode sweep + per-cell count
     #      matrices + the MatrixMarket files (BASELINE.json configs[4]: reassign_mode sweep) ----
     full = None
-    if args.full_flow:
+    if args.full_flow and (world == 1 or args.full_flow_multi):
         import shutil
         import tempfile
         sweep = ['best_exclude', 'best_conf', 'best_random', 'best_average', 'total_hits']
@@ -688,7 +689,8 @@ def run_ours(args):
             dtype='f64', data='synthetic',
             config=dict(workload=CONFIGS[cfg]['label'], config=cfg, scale=args.scale,
                         l2='inputs larger than L2 for cfg3-cfg5; 256 MB written between timed steps as well',
-                        n_cells=d.n_cells, alignments=d.A, rows=d.N, K=d.K, models=int(models_all), **OPTS,
+                        n_cells=d.n_cells, alignments=d.A, rows=d.N, K=d.K,
+                        models=1 if mode == 'pseudobulk' else int(models_all), **OPTS,
                         mean_iters=float(iters[fitted].mean()) if fitted.any() else 0.0,
                         units_per_step=int(units_all),
                         per_model_fit_us=1e3 * (tmax_ms / args.steps) / max(1.0, models_all),
@@ -700,7 +702,7 @@ def run_ours(args):
                                      f'models packed onto {world} GPU(s) by LPT on alignment counts, no data-path '
                                      f'collective; per-model records gathered as tensors')),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d_all), d2h_bytes_per_step=int(d2h_all),
-                     seconds_per_step=e2e_max, models_returned=int(nmod),
+                     seconds_per_step=e2e_max, models_returned=int(nmod), host_breakdown_rank0_s=host_t,
                      api='stellarscope_b200.model._fit_pooling_model(st, opts), st from host scipy CSR + row table'),
             e2e_full=(dict(seconds=e2e_max + reassign_max + report_max, fit_s=e2e_max, reassign_s=reassign_max,
                            count_and_mtx_s=report_max, value=e2e_units_all / (e2e_max + reassign_max + report_max),
@@ -757,6 +759,8 @@ def main():
     ap.add_argument('--cpu-budget-aln', dest='cpu_budget_aln', type=float, default=4e6,
                     help='alignments per CPU-baseline sample (about 10-30 s of CPU work)')
     ap.add_argument('--no-ref-as-written', dest='ref_as_written', action='store_false')
+    ap.add_argument('--full-flow-multi', dest='full_flow_multi', action='store_true',
+                    help='run the e2e_full pass under torchrun as well (default: single GPU only)')
     ap.add_argument('--no-full-flow', dest='full_flow', action='store_false',
                     help='skip the one pass of reassign sweep + count matrices + MatrixMarket files (e2e_full)')
     args = ap.parse_args()

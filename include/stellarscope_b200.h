@@ -186,16 +186,19 @@ int ss_count(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, const 
 int ss_reassign_pick(ss_handle_t h, void* stream, int32_t n_tied, const int32_t* tied_rows, const int32_t* picks,
                      const int32_t* row_ptr, uint8_t* flag);
 
-/* Per-cell integer counts without a sort (agg_bc, model.py:1302-1320, for the integer reassignment modes without
- * --umi_counts): the (loci x cells) count matrix in CSC form.  One CTA per cell accumulates the cell's selected
- * alignments in shared-memory bins over the loci.
+/* Per-cell counts without a sort (agg_bc, model.py:1302-1320, for every reassignment mode without --umi_counts):
+ * the (loci x cells) count matrix in CSC form.  One CTA per cell accumulates the cell's selected alignments in
+ * shared-memory bins over the loci.
  *   row_cell[n_rows]: output column of the row (0 .. n_cells-1; anything else: row dropped)
- *   out_ptr[n_cells + 1] out: column pointers; out_col / out_cnt[cap] out: loci (ascending per cell) and counts
+ *   out_ptr[n_cells + 1] out: column pointers; out_col[cap] out: loci, ascending per cell
+ *   integer modes: out_cnt[cap] (int32 counts), out_val = NULL, nbest ignored
+ *   best_average:  out_val[cap] (double), out_cnt = NULL, nbest[n_rows] from ss_reassign: every selected alignment
+ *                  of row r adds 1 / nbest[r] (model.py:448)
  *   *n_out: entries produced (host value, call synchronises).  SS_ERR_CAPACITY: cap too small (*n_out = needed)
  *   or n_cols too large for the shared-memory bins (use ss_count). */
 int ss_count_cells(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, int32_t n_cells, const int32_t* row_ptr,
-                   const int32_t* col_idx, const uint8_t* flag, const int32_t* row_cell, int64_t cap, int64_t* out_ptr,
-                   int32_t* out_col, int32_t* out_cnt, int64_t* n_out);
+                   const int32_t* col_idx, const uint8_t* flag, const int32_t* nbest, const int32_t* row_cell, int64_t cap,
+                   int64_t* out_ptr, int32_t* out_col, int32_t* out_cnt, double* out_val, int64_t* n_out);
 
 /* UMI de-duplication, the step before the path (Stellarscope.dedup_umi model.py:1148-1219,
  * select_umi_representatives :561-668).  Works on the CSR score matrix (raw_scores).

@@ -326,14 +326,14 @@ int ss_reassign_pick(ss_handle_t h, void* stream, int32_t n_tied, const int32_t*
 }
 
 int ss_count_cells(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, int32_t n_cells, const int32_t* row_ptr,
-                   const int32_t* col_idx, const uint8_t* flag, const int32_t* row_cell, int64_t cap, int64_t* out_ptr,
-                   int32_t* out_col, int32_t* out_cnt, int64_t* n_out) {
+                   const int32_t* col_idx, const uint8_t* flag, const int32_t* nbest, const int32_t* row_cell, int64_t cap,
+                   int64_t* out_ptr, int32_t* out_col, int32_t* out_cnt, double* out_val, int64_t* n_out) {
   SS_REQUIRE_HANDLE(h);
   cudaSetDevice(h->device);
   tl_alloc_stream = (cudaStream_t)stream;
   long long n = 0;
-  int rc = count_cells(h, (cudaStream_t)stream, n_rows, n_cols, n_cells, row_ptr, col_idx, flag, row_cell, cap,
-                       reinterpret_cast<long long*>(out_ptr), out_col, out_cnt, &n);
+  int rc = count_cells(h, (cudaStream_t)stream, n_rows, n_cols, n_cells, row_ptr, col_idx, flag, nbest, row_cell, cap,
+                       reinterpret_cast<long long*>(out_ptr), out_col, out_cnt, out_val, &n);
   if (n_out) *n_out = n;
   return rc;
 }

@@ -13,7 +13,10 @@
 namespace ss {
 
 constexpr int E_HARD = 4096;     // hard cap on alignments per tile (worst case fits 227 KB of shared memory)
-constexpr int E_STREAM = 2048;   // tile size of segments that are streamed (more than STREAM_SEG_TILES large tiles):
+#ifndef SS_E_STREAM
+#define SS_E_STREAM 2048
+#endif
+constexpr int E_STREAM = SS_E_STREAM;   // tile size of segments that are streamed (more than STREAM_SEG_TILES large tiles):
                                  // small tiles let 2-3 CTAs share an SM, so one CTA's loads / atomics overlap another's compute
 constexpr int STREAM_SEG_TILES = 8;
 constexpr int ALIGN_ELEMS = 8;   // per-tile slices start at multiples of 8 elements (16 B for u16)

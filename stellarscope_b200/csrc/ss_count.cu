@@ -21,6 +21,7 @@ namespace {
 
 constexpr int CC_THREADS = 1024;
 constexpr int CC_LIST = 8192;          // touched-bin list kept in shared memory; beyond it the bins are scanned
+constexpr int CC_LIST_FRAC = 1024;     // ... of the fractional variant (its bins are doubles: 224 KB for 28k loci)
 
 // rows and selected alignments per cell; sortedness of row_cell
 __global__ void cc_hist_kernel(int n_rows, int n_cells, const int* __restrict__ row_ptr, const uint8_t* __restrict__ flag,
@@ -82,20 +83,25 @@ __global__ void cc_group_rows_kernel(int n_rows, int n_cells, const int* __restr
   rows_by_cell[cell_row0[c] + atomicAdd(&cursor[c], 1)] = row;
 }
 
-// one CTA per cell (persistent: cells are handed out through an atomic counter, the largest first if `order`)
+// one CTA per cell (persistent: cells are handed out through an atomic counter).  VT = unsigned int: integer counts;
+// VT = double: every selected alignment of row r adds 1 / nbest[r] (best_average, model.py:448) -- the bins are
+// twice as wide, the touched-bin list shorter (LIST entries), the additions are floating-point atomics (their order,
+// and with it the last bit of a sum, is not fixed)
+template <class VT, int LIST>
 __global__ void __launch_bounds__(CC_THREADS) cc_count_kernel(
     int n_cells, int n_cols, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
-    const uint8_t* __restrict__ flag, const long long* __restrict__ cell_row0, const int* __restrict__ rows_by_cell,
-    const int* __restrict__ first_row, const unsigned long long* __restrict__ cell_sel, const long long* __restrict__ ub_off,
-    int* __restrict__ next_cell, unsigned int* __restrict__ tmp_col, unsigned int* __restrict__ tmp_cnt,
-    long long* __restrict__ cell_nnz) {
+    const uint8_t* __restrict__ flag, const int* __restrict__ nbest, const long long* __restrict__ cell_row0,
+    const int* __restrict__ rows_by_cell, const int* __restrict__ first_row, const unsigned long long* __restrict__ cell_sel,
+    const long long* __restrict__ ub_off, int* __restrict__ next_cell, unsigned int* __restrict__ tmp_col,
+    VT* __restrict__ tmp_cnt, long long* __restrict__ cell_nnz) {
+  constexpr int CC_LIST = LIST;
   extern __shared__ __align__(16) unsigned char dsm[];
-  unsigned int* bins = reinterpret_cast<unsigned int*>(dsm);            // n_cols
-  unsigned int* list = bins + ((n_cols + 3) & ~3);                      // CC_LIST
+  VT* bins = reinterpret_cast<VT*>(dsm);                                // n_cols
+  unsigned int* list = reinterpret_cast<unsigned int*>(bins + ((n_cols + 3) & ~3));   // CC_LIST
   __shared__ int s_cell, s_nlist;
   __shared__ unsigned int s_scan[CC_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < n_cols; i += CC_THREADS) bins[i] = 0u;
+  for (int i = tid; i < n_cols; i += CC_THREADS) bins[i] = VT(0);
   __syncthreads();
   while (true) {
     if (tid == 0) {
@@ -115,11 +121,13 @@ __global__ void __launch_bounds__(CC_THREADS) cc_count_kernel(
     for (long long i = r0 + tid; i < r1; i += CC_THREADS) {
       const int row = rows_by_cell ? rows_by_cell[i] : (int)(base_row + (i - r0));
       const int b = row_ptr[row], e = row_ptr[row + 1];
+      VT one = VT(1);
+      if (sizeof(VT) == 8 && nbest) one = VT(1.0 / (double)max(1, nbest[row]));
       for (int k = b; k < e; ++k) {
         if (!flag[k]) continue;
         const unsigned col = (unsigned)col_idx[k];
         if (col >= (unsigned)n_cols) continue;
-        if (atomicAdd(&bins[col], 1u) == 0u) {
+        if (atomicAdd(&bins[col], one) == VT(0)) {
           const int p = atomicAdd(&s_nlist, 1);
           if (p < CC_LIST) list[p] = col;
         }
@@ -151,14 +159,14 @@ __global__ void __launch_bounds__(CC_THREADS) cc_count_kernel(
         const unsigned col = list[i];
         tmp_col[o + i] = col;
         tmp_cnt[o + i] = bins[col];
-        bins[col] = 0u;
+        bins[col] = VT(0);
       }
     } else {
       // many distinct loci: scan all bins in locus order (every thread owns a contiguous chunk)
       const int chunk = (n_cols + CC_THREADS - 1) / CC_THREADS;
       const int b0 = min(n_cols, tid * chunk), b1 = min(n_cols, b0 + chunk);
       unsigned int mine = 0;
-      for (int i = b0; i < b1; ++i) mine += bins[i] != 0u;
+      for (int i = b0; i < b1; ++i) mine += bins[i] != VT(0);
       unsigned int incl = mine;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -179,12 +187,12 @@ __global__ void __launch_bounds__(CC_THREADS) cc_count_kernel(
       __syncthreads();
       long long w = o + (long long)(incl - mine) + (warp > 0 ? s_scan[warp - 1] : 0u);
       for (int i = b0; i < b1; ++i) {
-        const unsigned int v = bins[i];
-        if (v != 0u) {
+        const VT v = bins[i];
+        if (v != VT(0)) {
           tmp_col[w] = (unsigned)i;
           tmp_cnt[w] = v;
           ++w;
-          bins[i] = 0u;
+          bins[i] = VT(0);
         }
       }
     }
@@ -204,9 +212,10 @@ __global__ void cc_first_row_kernel(int n_rows, int n_cells, const int* __restri
 }
 
 // tmp (upper-bound offsets) -> output (exact offsets): one warp per cell
+template <class VT, class OT>
 __global__ void cc_compact_kernel(int n_cells, const long long* __restrict__ ub_off, const long long* __restrict__ out_ptr,
-                                  const unsigned int* __restrict__ tmp_col, const unsigned int* __restrict__ tmp_cnt,
-                                  int* __restrict__ out_col, int* __restrict__ out_cnt) {
+                                  const unsigned int* __restrict__ tmp_col, const VT* __restrict__ tmp_cnt,
+                                  int* __restrict__ out_col, OT* __restrict__ out_cnt) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= n_cells) return;
@@ -214,7 +223,7 @@ __global__ void cc_compact_kernel(int n_cells, const long long* __restrict__ ub_
   const long long n = out_ptr[c + 1] - dst;
   for (long long i = lane; i < n; i += 32) {
     out_col[dst + i] = (int)tmp_col[src + i];
-    out_cnt[dst + i] = (int)tmp_cnt[src + i];
+    out_cnt[dst + i] = (OT)tmp_cnt[src + i];
   }
 }
 
@@ -245,14 +254,16 @@ struct TmpPool {
 
 // returns SS_OK, or SS_ERR_CAPACITY with *n_out = required entries when cap is too small / the loci do not fit the bins
 int count_cells(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, int n_cells, const int* row_ptr, const int* col_idx,
-                const uint8_t* flag, const int* row_cell, long long cap, long long* out_ptr, int* out_col, int* out_cnt,
-                long long* n_out) {
-  if (!row_ptr || !col_idx || !flag || !row_cell || !out_ptr || !n_out || n_cells < 0 || n_cols <= 0) {
+                const uint8_t* flag, const int* nbest, const int* row_cell, long long cap, long long* out_ptr, int* out_col,
+                int* out_cnt, double* out_val, long long* n_out) {
+  if (!row_ptr || !col_idx || !flag || !row_cell || !out_ptr || !n_out || n_cells < 0 || n_cols <= 0 ||
+      (out_val && out_cnt)) {
     h->set_error("ss_count_cells: bad argument");
     return SS_ERR_ARG;
   }
   *n_out = 0;
-  const size_t smem = 4 * (size_t)((n_cols + 3) & ~3) + 4 * (size_t)CC_LIST;
+  const bool frac = out_val != nullptr;            // fractional counts: 1 / nbest per selected alignment
+  const size_t smem = (frac ? 8 : 4) * (size_t)((n_cols + 3) & ~3) + 4 * (size_t)(frac ? CC_LIST_FRAC : CC_LIST);
   if (smem + 1024 > h->max_smem_optin) {
     h->set_error("ss_count_cells: the loci do not fit the shared-memory bins (use ss_count)");
     return SS_ERR_CAPACITY;
@@ -303,15 +314,24 @@ int count_cells(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, int n_c
     cc_first_row_kernel<<<GR, B, 0, st>>>(n_rows, n_cells, row_cell, first_row);
   }
   h->launches++;
-  unsigned int *tmp_col, *tmp_cnt;
+  unsigned int *tmp_col, *tmp_cnt = nullptr;
+  double* tmp_val = nullptr;
   SS_CUDA_CHECK(h, tmp.get(&tmp_col, (size_t)ub_total));
-  SS_CUDA_CHECK(h, tmp.get(&tmp_cnt, (size_t)ub_total));
-  SS_CUDA_CHECK(h, cudaFuncSetAttribute(cc_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (frac) SS_CUDA_CHECK(h, tmp.get(&tmp_val, (size_t)ub_total));
+  else SS_CUDA_CHECK(h, tmp.get(&tmp_cnt, (size_t)ub_total));
+  const void* kfn = frac ? (const void*)cc_count_kernel<double, CC_LIST_FRAC> : (const void*)cc_count_kernel<unsigned int, CC_LIST>;
+  SS_CUDA_CHECK(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  SS_CUDA_CHECK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cc_count_kernel, CC_THREADS, smem));
+  SS_CUDA_CHECK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, CC_THREADS, smem));
   const int grid = std::min(n_cells, std::max(1, occ) * h->num_sms);
-  cc_count_kernel<<<grid, CC_THREADS, smem, st>>>(n_cells, n_cols, row_ptr, col_idx, flag, cell_row0, rows_by_cell, first_row,
-                                                  cell_sel, ub_off, next_cell, tmp_col, tmp_cnt, cell_nnz);
+  if (frac)
+    cc_count_kernel<double, CC_LIST_FRAC><<<grid, CC_THREADS, smem, st>>>(n_cells, n_cols, row_ptr, col_idx, flag, nbest, cell_row0,
+                                                                       rows_by_cell, first_row, cell_sel, ub_off, next_cell,
+                                                                       tmp_col, tmp_val, cell_nnz);
+  else
+    cc_count_kernel<unsigned int, CC_LIST><<<grid, CC_THREADS, smem, st>>>(n_cells, n_cols, row_ptr, col_idx, flag, nullptr, cell_row0,
+                                                                        rows_by_cell, first_row, cell_sel, ub_off, next_cell,
+                                                                        tmp_col, tmp_cnt, cell_nnz);
   h->launches++;
   SS_CUDA_CHECK(h, cudaGetLastError());
   CUB_CALL(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, cell_nnz, out_ptr, n_cells + 1, st));
@@ -324,8 +344,9 @@ int count_cells(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, int n_c
     return SS_ERR_CAPACITY;
   }
   if (total > 0) {
-    cc_compact_kernel<<<(unsigned)(((long long)n_cells * 32 + B - 1) / B), B, 0, st>>>(n_cells, ub_off, out_ptr, tmp_col, tmp_cnt,
-                                                                                    out_col, out_cnt);
+    const unsigned gcmp = (unsigned)(((long long)n_cells * 32 + B - 1) / B);
+    if (frac) cc_compact_kernel<double, double><<<gcmp, B, 0, st>>>(n_cells, ub_off, out_ptr, tmp_col, tmp_val, out_col, out_val);
+    else cc_compact_kernel<unsigned int, int><<<gcmp, B, 0, st>>>(n_cells, ub_off, out_ptr, tmp_col, tmp_cnt, out_col, out_cnt);
     h->launches++;
     SS_CUDA_CHECK(h, cudaGetLastError());
   }

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(THREADS) em_dense_kernel(EmArgs a, DenseArgs d
   uint32_t n_use = 0u;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
-    stream_pipe_init(&s_pipe);
+    stream_pipe_init(&s_pipe, THREADS / 32 - 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(THREADS) dense_pass_kernel(EmArgs a, DenseArgs
   uint32_t n_use = 0u;
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
-    stream_pipe_init(&s_pipe);
+    stream_pipe_init(&s_pipe, THREADS / 32 - 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();

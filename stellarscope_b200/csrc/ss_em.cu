@@ -1223,7 +1223,7 @@ __global__ void __launch_bounds__(THREADS) em_stream_kernel(EmArgs a, StreamArgs
   uint32_t n_use = 0u;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
-    stream_pipe_init(&s_pipe);
+    stream_pipe_init(&s_pipe, THREADS / 32 - 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();

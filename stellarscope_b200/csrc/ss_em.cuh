@@ -248,9 +248,10 @@ constexpr int STREAM_DC_INTS = 24;      // lane-group boundaries of a tile (deri
 __host__ __device__ inline size_t stream_buf_bytes(const StreamGeom& g) {
   return STREAM_HDR_BYTES + 12 * (size_t)g.pe + 10 * (size_t)g.pr + 6 * (size_t)g.pc + 2 * (size_t)g.pj;
 }
-// per buffer: tile arrays + tile-local x; shared by both: the column-major scratch
+// per buffer: tile arrays + tile-local x + the column-major scratch (a scratch per buffer lets a warp start the next
+// tile's row phase while slower warps are still in this tile's column phase: ONE consumer barrier per tile)
 __host__ __device__ inline size_t stream_smem_bytes(const StreamGeom& g) {
-  return (size_t)g.nbuf * (stream_buf_bytes(g) + 8 * (size_t)g.pc) + 8 * ((size_t)g.pe + 8) + 128;
+  return (size_t)g.nbuf * (stream_buf_bytes(g) + 8 * (size_t)g.pc + 8 * ((size_t)g.pe + 8)) + 128;
 }
 
 // double buffered when two buffers + scratch fit `limit` bytes of shared memory
@@ -293,6 +294,22 @@ __device__ __forceinline__ void stream_issue_loads(const Layout& L, const int* c
   bulk_g2s((void*)b.jptr, L.j_ptr + v.jo, 2u * v.pj, bar);
   bulk_g2s((void*)b.gcol, colmap + v.co, 4u * v.pc, bar);
 }
+// the same with the column map on a barrier of its own (issued first: it is small and the producer needs it
+// before anything else -- the gather of the tile-local x then overlaps the flight of the big arrays)
+__device__ __forceinline__ void stream_issue_loads2(const Layout& L, const int* colmap, int t, const TileView& v,
+                                                    const StreamBuf& b, uint64_t* bar, uint64_t* bar_map) {
+  mbar_expect_tx(bar_map, 4u * v.pc);
+  bulk_g2s((void*)b.gcol, colmap + v.co, 4u * v.pc, bar_map);
+  const uint32_t bytes = 8u * HDR_WORDS + 12u * v.pe + 10u * v.pr + 2u * v.pc + 2u * v.pj;
+  mbar_expect_tx(bar, bytes);
+  bulk_g2s((void*)b.hdr, L.tile_hdr + (long long)HDR_WORDS * t, 8u * HDR_WORDS, bar);
+  bulk_g2s((void*)b.q, L.e_q + v.eo, 8u * v.pe, bar);
+  bulk_g2s((void*)b.idx, L.e_idx + v.eo, 4u * v.pe, bar);
+  bulk_g2s((void*)b.w, L.r_w + v.ro, 8u * v.pr, bar);
+  bulk_g2s((void*)b.rlen, L.r_len + v.ro, 2u * v.pr, bar);
+  bulk_g2s((void*)b.cptr, L.c_ptr + v.co, 2u * v.pc, bar);
+  bulk_g2s((void*)b.jptr, L.j_ptr + v.jo, 2u * v.pj, bar);
+}
 
 __device__ __forceinline__ double group_xor_sum_s(double a, int g, int gmax) {
   const unsigned full = 0xffffffffu;
@@ -309,16 +326,18 @@ __device__ __forceinline__ double group_xor_sum_s(double a, int g, int gmax) {
 // control block of the pipeline (static shared memory of the kernel that runs the pass)
 struct StreamPipe {
   uint64_t full[2];     // the TMA bytes of buffer b have landed
+  uint64_t mapf[2];     // ... its column map has (a barrier of its own: the producer gathers x from it first)
   uint64_t ready[2];    // buffer b is complete: tile arrays, tile-local x, boundaries (producer -> consumers)
   uint64_t empty[2];    // the consumers are done with buffer b (consumers -> producer)
   int tile[2];          // tile in buffer b, -1: end of the pass
   int dc[2][STREAM_DC_INTS];
 };
-__device__ __forceinline__ void stream_pipe_init(StreamPipe* p) {   // one thread, before a CTA barrier
+__device__ __forceinline__ void stream_pipe_init(StreamPipe* p, int consumer_warps) {   // one thread, before a CTA barrier
   for (int b = 0; b < 2; ++b) {
     mbar_init(&p->full[b], 1);
+    mbar_init(&p->mapf[b], 1);
     mbar_init(&p->ready[b], 1);
-    mbar_init(&p->empty[b], 1);
+    mbar_init(&p->empty[b], consumer_warps);
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -486,8 +505,8 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
   const int tid = threadIdx.x, lane = tid & 31;
   const size_t bb = stream_buf_bytes(g);
   const int nbuf = g.nbuf;
-  double* val = reinterpret_cast<double*>(dsm + (size_t)nbuf * bb);
-  double* xs0 = val + g.pe + 8;
+  double* val0 = reinterpret_cast<double*>(dsm + (size_t)nbuf * bb);           // nbuf scratch arrays of pe + 8
+  double* xs0 = val0 + (size_t)nbuf * (g.pe + 8);                              // nbuf tile-local x arrays of pc
   uint32_t n = n_use;
   if (tid >= CONS) {
     // ------------------------------ producer warp ------------------------------
@@ -508,6 +527,7 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
         if (lane == 0) {
           pipe->tile[slot] = -1;
           mbar_arrive(&pipe->full[slot]);
+          mbar_arrive(&pipe->mapf[slot]);
           mbar_arrive(&pipe->ready[slot]);
         }
         ++n;
@@ -518,10 +538,10 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
       const StreamBuf b = carve_stream(dsm + (size_t)slot * bb, g);
       if (lane == 0) {
         fence_proxy_async();
-        stream_issue_loads(L, colmap, t, v, b, &pipe->full[slot]);
+        stream_issue_loads2(L, colmap, t, v, b, &pipe->full[slot], &pipe->mapf[slot]);
       }
       const int i_next = next_item(i + gridDim.x);                   // overlaps the flight of the copies
-      mbar_wait(&pipe->full[slot], k & 1u);
+      mbar_wait(&pipe->mapf[slot], k & 1u);                          // the column map is in; the big arrays still fly
       // tile-local x: 8 loads in flight per lane
       double* xs = xs0 + (size_t)slot * g.pc;
       for (int c0 = 0; c0 < v.ncol; c0 += 256) {
@@ -537,6 +557,7 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
           if (c < v.ncol) xs[c] = xv[u];
         }
       }
+      mbar_wait(&pipe->full[slot], k & 1u);
       if (lane == 0) {
         xs[v.ncol] = 0.0;
         stream_boundaries(b.hdr, v.nrows, v.ncol, FR * CONS, FC * CONS, pipe->dc[slot]);
@@ -557,15 +578,18 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
       mbar_wait(&pipe->full[slot], k & 1u);                          // complete already; orders the reads after the copies
       ++n;
       if (t < 0) {
-        consumer_bar<CONS>();                                        // everybody has read the marker
-        if (tid == 0) mbar_arrive(&pipe->empty[slot]);
+        __syncwarp();                                                // the warp has read the marker
+        if (lane == 0) mbar_arrive(&pipe->empty[slot]);
         break;
       }
       const StreamBuf b = carve_stream(dsm + (size_t)slot * bb, g);
       const TileView v = load_tile_view(b.hdr, 0);                   // the header arrived with the tile
-      lane_tile_compute<CONS, FR, FC>(v, b, T, xs0 + (size_t)slot * g.pc, val, pipe->dc[slot]);
-      consumer_bar<CONS>();                                          // buffer, x and scratch are free again
-      if (tid == 0) mbar_arrive(&pipe->empty[slot]);
+      lane_tile_compute<CONS, FR, FC>(v, b, T, xs0 + (size_t)slot * g.pc, val0 + (size_t)slot * (g.pe + 8), pipe->dc[slot]);
+      // this warp is done with the buffer (tile arrays, x, scratch); the producer refills it when all warps are.
+      // No CTA-wide barrier here: the row phase of the next tile writes the OTHER scratch, and nobody reaches the
+      // tile after that before everybody has passed the next tile's row | column barrier, i.e. left this column phase
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pipe->empty[slot]);
     }
   }
   n_use = n;

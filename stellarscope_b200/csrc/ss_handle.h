@@ -185,8 +185,8 @@ int reassign_pick(ss_handle_s* h, cudaStream_t st, int n_tied, const int* tied_r
                   uint8_t* flag);
 // ss_count.cu
 int count_cells(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, int n_cells, const int* row_ptr, const int* col_idx,
-                const uint8_t* flag, const int* row_cell, long long cap, long long* out_ptr, int* out_col, int* out_cnt,
-                long long* n_out);
+                const uint8_t* flag, const int* nbest, const int* row_cell, long long cap, long long* out_ptr, int* out_col,
+                int* out_cnt, double* out_val, long long* n_out);
 
 // Device memory of a handle comes from the device's stream-ordered pool (cudaMallocAsync; the
 // pool keeps its memory, ss_create): a layout build makes ~50 allocations and cudaMalloc would

@@ -24,6 +24,16 @@
 #include <time.h>
 #include <unistd.h>
 
+/* The fast paths below read the hash tables of exact sets (_PySet_NextEntry) and the single digit of compact ints
+ * (PyUnstable_Long_IsCompact / CompactValue).  Both exist in CPython 3.12 (the interpreter of this image); 3.13
+ * no longer declares the first in its public headers, earlier versions lack the second.  On any other version the
+ * module still builds: the set walks go through the iterator protocol and PyLong_AsSsize_t (slower, same results). */
+#if PY_VERSION_HEX >= 0x030C0000 && PY_VERSION_HEX < 0x030D0000
+#define SS_FAST_SETS 1
+#else
+#define SS_FAST_SETS 0
+#endif
+
 /* ---- threaded fast path ---------------------------------------------------------
  * Exact sets of exact, compact (single-digit) ints -- what the reference's loader
  * produces -- are walked by a few worker threads while the calling thread keeps the
@@ -43,6 +53,10 @@ typedef struct {
 
 static void* worker_main(void* arg) {
   worker_t* w = (worker_t*)arg;
+#if !SS_FAST_SETS
+  w->status = 1;                 /* no public way to walk a set without the GIL: the serial path does the job */
+  return NULL;
+#else
   Py_ssize_t count = 0;
   for (Py_ssize_t g = w->g0; g < w->g1; ++g) {
     PyObject* s = w->items[g];
@@ -71,11 +85,15 @@ static void* worker_main(void* arg) {
   }
   w->count = count;
   return NULL;
+#endif
 }
 
 /* returns the number of rows assigned, -1 when the serial path has to take over (seg is then
  * partially written and must be reset by the caller) */
 static Py_ssize_t fill_threaded(PyObject** items, Py_ssize_t ng, const int32_t* ids, int32_t* seg, Py_ssize_t n) {
+#if !SS_FAST_SETS
+  return -1;
+#endif
   Py_ssize_t total = 0;
   for (Py_ssize_t g = 0; g < ng; ++g) {
     if (!PyAnySet_CheckExact(items[g])) return -1;
@@ -178,6 +196,7 @@ static PyObject* fill_row_segments(PyObject* self, PyObject* args) {
     for (Py_ssize_t g = 0; g < ng; ++g) {
       PyObject* s = PySequence_Fast_GET_ITEM(fast, g);
       const int32_t id = idp[g];
+#if SS_FAST_SETS
       if (PyAnySet_Check(s)) {
         Py_ssize_t pos = 0;
         PyObject* key;
@@ -185,7 +204,9 @@ static PyObject* fill_row_segments(PyObject* self, PyObject* args) {
         while (_PySet_NextEntry(s, &pos, &key, &hash)) {
           if (assign_row(key, id, segp, n, &count) < 0) goto done;
         }
-      } else {
+      } else
+#endif
+      {
         PyObject* it = PyObject_GetIter(s);
         if (!it) goto done;
         PyObject* key;

@@ -724,11 +724,12 @@ class Engine:
             torch.cuda.current_stream(dev).synchronize()          # r / c / v / off may go
             return out[:int(nbytes.value)]
 
-    def count_cells(self, flag, row_cell, n_cells, keep_device=False):
+    def count_cells(self, flag, row_cell, n_cells, keep_device=False, nbest=None):
         """ss_count_cells: integer counts per (cell, locus) without a sort, as the CSC form of the (loci x cells)
         matrix: numpy ``(indptr int64[n_cells+1], loci int32[nnz], counts int32[nnz])``; with ``keep_device`` a
         fourth element, the three device tensors (for the MTX writer).  Returns None when the loci do not fit the
-        kernel's shared-memory bins (the caller takes ``count``)."""
+        kernel's shared-memory bins (the caller takes ``count``).  With ``nbest`` (device, from ``reassign``) the
+        counts are fractional -- 1 / nbest of the row per selected alignment (best_average) -- and float64."""
         dev, k = self.device, self._keep
         n_cells = int(n_cells)
         with torch.cuda.device(dev):
@@ -738,11 +739,12 @@ class Engine:
             cap = int(flag.sum(dtype=torch.int64)) if self.A else 0
             cap = max(1, min(cap, n_cells * self.K))
             oc = torch.empty(cap, dtype=torch.int32, device=dev)
-            ov = torch.empty(cap, dtype=torch.int32, device=dev)
+            ov = torch.empty(cap, dtype=torch.float64 if nbest is not None else torch.int32, device=dev)
             n = C.c_int64(0)
             rc = self.lib.ss_count_cells(self.h, self._stream(), self.N, self.K, n_cells, self._p(k['row_ptr']),
-                                         self._p(k['col_idx']), self._p(flag), self._p(rc_t), cap, self._p(out_ptr),
-                                         self._p(oc), self._p(ov), C.byref(n))
+                                         self._p(k['col_idx']), self._p(flag), self._p(nbest), self._p(rc_t), cap,
+                                         self._p(out_ptr), self._p(oc), self._p(None if nbest is not None else ov),
+                                         self._p(ov if nbest is not None else None), C.byref(n))
             if rc == _lib.SS_ERR_CAPACITY:
                 return None
             self._check(rc)

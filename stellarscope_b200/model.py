@@ -333,9 +333,10 @@ class TelescopeLikelihood(object):
             ptr, idx, frac = self._engine.reassign_csr(flag, nbest, fractions=(mode == 'best_average'))
             data = frac if mode == 'best_average' else np.ones(len(idx), dtype=np.int8)
             mat = csr_matrix_plus((data, idx, self._global_indptr(ptr, indptr_dtype)), shape=self.raw_scores.shape)
-            if mode != 'best_average':
-                # lets count_by_cell aggregate without uploading the matrix again (while the engine still holds this matrix)
-                mat._ss_dev = (self._engine, flag, self._engine._keep.get('row_ptr'), self._row_ids)
+            # lets count_by_cell aggregate without uploading the matrix again (while the engine still holds this
+            # matrix); best_average also needs the tie-set sizes (its entries are 1 / nbest)
+            mat._ss_dev = (self._engine, flag, self._engine._keep.get('row_ptr'), self._row_ids) + \
+                ((nbest,) if mode == 'best_average' else ())
             return mat, rinfo
         # random modes: the tie sets come from the device, the draws from the reference's numpy generator in row
         # order (one vectorised rng.integers call gives the stream of the reference's per-row rng.choice calls,
@@ -521,7 +522,9 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
             # are exchanged once per iteration.  Rows of other ranks belong to no local
             # model, so z -- and the counts derived from it -- are rank-local and add up over ranks.
             from . import parallel
-            m = _canonical_csr(fullmat)
+            # no canonicalising pass over the whole matrix on the host: the device checks the rank's rows while it
+            # builds the layout and only a failed check makes this rank canonicalise (TelescopeLikelihood.__init__)
+            m = fullmat if scipy.sparse.isspmatrix_csr(fullmat) else scipy.sparse.csr_matrix(fullmat)
             if getattr(opts, 'umi_counts', False):
                 # distinct UMIs are counted per cell: all reads of a cell on one rank
                 rows = parallel.model_cell_block(np.diff(m.indptr), np.arange(m.shape[0]), _row_cells(st), rank, world)
@@ -555,24 +558,29 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
         # the data path; every rank keeps the global row numbering, rows of other ranks' models are
         # simply not fitted here
         from . import parallel
+        _t = [time.perf_counter()]
         row_segment, keys = pooling_row_segments(st, opts)
-        m = _canonical_csr(fullmat)
+        _t.append(time.perf_counter())
+        m = fullmat if scipy.sparse.isspmatrix_csr(fullmat) else scipy.sparse.csr_matrix(fullmat)
         # a model much larger than a rank's fair share (a dominant cell type on 8 GPUs) cannot be balanced by packing
         # whole models: such WIDE models are fitted by all ranks together, rows cut into blocks like pseudobulk
         # opts.wide_models: None (default: pack whole models), 'auto' (parallel.wide_models) or a list of model indices;
         # opts.wide_model_cost: lockstep overhead of one wide model in alignments of single-GPU work
         umi_counts = bool(getattr(opts, 'umi_counts', False))
-        loose = bool((row_segment < 0).any())
+        loose = len(row_segment) > 0 and int(row_segment.min()) < 0
         row_cell = _row_cells(st) if (loose or (umi_counts and getattr(opts, 'wide_models', None))) else None
         plan = parallel.plan_local_rows(m.indptr, row_segment, len(keys), world, rank,
                                         wide=getattr(opts, 'wide_models', None) or [],
                                         wide_cost=getattr(opts, 'wide_model_cost', 2_000_000),
-                                        row_cell=row_cell, cells_whole=umi_counts)
+                                        row_cell=row_cell, cells_whole=umi_counts, all_assigned=not loose)
         mine, wide, rows = plan['mine'], plan['wide'], plan['rows']
+        _t.append(time.perf_counter())
         # every rank cuts ITS rows out of the host matrix and uploads only them (1/world of the H2D traffic)
         ret_model = TelescopeLikelihood(m, opts, row_segment=plan['local_seg'], n_segments=len(mine), row_ids=rows)
         ret_model.model_ids = mine
+        _t.append(time.perf_counter())
         local = ret_model.fit_segments()
+        _t.append(time.perf_counter())
         # per-model records of all ranks: fixed-width arrays through all_gather_into_tensor (no pickling; the
         # per-iteration traces stay on the rank that fitted the model unless opts.gather_traces is set)
         lr = local._res
@@ -592,6 +600,11 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
         res['diffs'] = g['diffs'] if want_traces else _ShardedTrace(lr.get('diffs'), my0, len(mine), len(ids),
                                                                    ret_model.max_iter)
         itime = float(parallel.allreduce_sum_host(np.array([local._itime]))[0]) / world
+        _t.append(time.perf_counter())
+        # where this rank's wall time went (seconds): row -> model map, packing plan + row selection, cutting the rows
+        # out + upload + layout build, fit (incl. the wait for the device), gather of the records
+        ret_model.host_timings = dict(zip(('row_segments', 'plan', 'cut_upload_build', 'fit', 'gather_records'),
+                                          np.diff(_t).tolist()))
         parts_ids, parts_res = [ids], [res]
         if len(wide):
             eng = ret_model._engine
@@ -599,7 +612,7 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
             z_all = ret_model._z_device()
             for w, mask in zip(wide, plan['wide_local']):
                 seg_w = np.where(mask, 0, -1).astype(np.int32)
-                tw = TelescopeLikelihood(m, opts, row_segment=seg_w, n_segments=1, device_matrix=dev_matrix,
+                tw = TelescopeLikelihood(ret_model.raw_scores, opts, row_segment=seg_w, n_segments=1, device_matrix=dev_matrix,
                                          row_ids=rows, shard=(rank, world, None, getattr(opts, 'peer_exchange', True)))
                 info_w = tw.fit_segments()                  # the same record on every rank
                 z_all += tw._z_device()                     # disjoint rows: the rank-local z of the wide model
@@ -769,15 +782,44 @@ def count_matrices(st, tl: TelescopeLikelihood):
             # COO triples of all ranks are concatenated -- tensors through all_gather_into_tensor, no pickled
             # matrices -- and entries of the same (locus, cell) add up (a cell cut across ranks: pseudobulk blocks)
             from . import parallel
-            coo = cm.tocoo()
-            g = parallel.gather_concat({'r': coo.row.astype(np.int32), 'c': coo.col.astype(np.int32),
-                                        'v': coo.data.astype(np.float64)})
-            merged = scipy.sparse.coo_matrix((g['v'], (g['r'], g['c'])), shape=cm.shape).tocsc()    # sums duplicates
-            cm = merged.astype(cm.dtype)
+            cm = _merge_rank_counts(cm, world, parallel)
         out[_rmode] = cm
         if out[_rmode].shape != (numft, numbc):
             raise StellarscopeError(f'Incompatible shapes: {out[_rmode].shape} != {(numft, numbc)}')
     return out, bc_list, ft_list
+
+
+def _merge_rank_counts(cm, world, parallel):
+    """The count matrix of the whole run from the ranks' parts (each rank counted its own rows).  The parts travel as
+    arrays (``parallel.gather_concat``).  Usually no cell is cut across ranks (models are packed whole; wide /
+    pseudobulk models with ``--umi_counts`` keep cells whole): the columns of the result are then the ranks' columns
+    side by side and are put in place with one scatter per rank -- no sort, no sum.  Otherwise (a cell's rows on
+    several ranks) the triples are concatenated and entries of the same (locus, cell) add up."""
+    cm = scipy.sparse.csc_matrix(cm)
+    n_cells = cm.shape[1]
+    lens = np.diff(cm.indptr).astype(np.int64)
+    L = parallel.gather_concat({'lens': lens})['lens'].reshape(world, n_cells)
+    g = parallel.gather_concat({'c': cm.indices.astype(np.int32), 'v': np.ascontiguousarray(cm.data)})
+    if ((L > 0).sum(axis=0) > 1).any():
+        cells = np.concatenate([np.repeat(np.arange(n_cells, dtype=np.int32), L[r]) for r in range(world)])
+        merged = scipy.sparse.coo_matrix((g['v'], (g['c'], cells)), shape=cm.shape).tocsc()    # sums duplicates
+        return merged.astype(cm.dtype)
+    tot = L.sum(axis=0)
+    indptr = np.zeros(n_cells + 1, dtype=np.int64)
+    np.cumsum(tot, out=indptr[1:])
+    out_idx = np.empty(int(indptr[-1]), dtype=np.int32)
+    out_val = np.empty(int(indptr[-1]), dtype=cm.dtype)
+    off = 0
+    for r in range(world):
+        lr = L[r]
+        nr = int(lr.sum())
+        if nr:
+            src0 = np.cumsum(lr) - lr                                   # first entry of the cell in rank r's block
+            dest = np.repeat(indptr[:-1] - src0, lr) + np.arange(nr, dtype=np.int64)
+            out_idx[dest] = g['c'][off:off + nr]
+            out_val[dest] = g['v'][off:off + nr]
+        off += nr
+    return scipy.sparse.csc_matrix((out_val, out_idx, indptr), shape=cm.shape)
 
 
 def output_report(st, tl: TelescopeLikelihood):

@@ -65,7 +65,7 @@ def mmwrite(target, a, comment='', engine=None, device_coo=None):
     nnz = int(a.nnz)
     # the body is complete on the device before the file is touched: an unsupported value leaves no partial file
     csc = getattr(a, '_ss_dev_csc', None)
-    if device_coo is None and csc is not None and int(csc[1].numel()) == nnz and integer:
+    if device_coo is None and csc is not None and int(csc[1].numel()) == nnz:
         # CSC arrays left on the device by ss_count_cells: expand the column pointers into one cell index per entry
         import torch
         ptr, loci, cnt = csc

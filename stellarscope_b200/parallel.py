@@ -195,7 +195,7 @@ def row_block(indptr, rank, world):
 # Rank-local rows of a sharded run and the gathers of its results
 # ---------------------------------------------------------------------------
 def plan_local_rows(indptr, row_segment, n_segments, world, rank, wide=None, wide_cost=2_000_000, row_cell=None,
-                    cells_whole=False):
+                    cells_whole=False, all_assigned=None):
     """Which rows this rank holds when the models of a pooling mode are sharded over ``world`` ranks.
 
     Every row of the matrix goes to exactly ONE rank, so that whatever is computed per row (z, the reassignment
@@ -216,7 +216,9 @@ def plan_local_rows(indptr, row_segment, n_segments, world, rank, wide=None, wid
     row_segment = np.asarray(row_segment)
     N = len(row_segment)
     no_wide = wide is None or (not isinstance(wide, str) and len(wide) == 0)
-    if no_wide and row_segment.dtype == np.int32 and (N == 0 or int(row_segment.min()) >= 0):
+    if all_assigned is None:
+        all_assigned = N == 0 or int(row_segment.min()) >= 0
+    if no_wide and row_segment.dtype == np.int32 and all_assigned:
         # the common case -- every row belongs to a packed model: three threaded passes in C instead of ~10 numpy
         # passes over per-row arrays (1.4x10^8 rows at atlas scale)
         from . import hostutil

@@ -101,7 +101,10 @@ class csr_matrix_plus(scipy.sparse.csr_matrix):
             rc = engine._to_dev(row_cell, np.int32)
             if cache is not None:
                 cache['row_cell_dev'] = rc
-        res = engine.count_cells(dev[1], rc, n_cells, keep_device=True)
+        nbest = dev[4] if len(dev) > 4 else None          # best_average: fractions 1 / nbest
+        if nbest is None and not np.issubdtype(self.dtype, np.integer):
+            return None
+        res = engine.count_cells(dev[1], rc, n_cells, keep_device=True, nbest=nbest)
         if res is None:
             return None
         indptr, col, cnt, kept = res
@@ -116,7 +119,7 @@ class csr_matrix_plus(scipy.sparse.csr_matrix):
         of row i (-1: dropped).  int32 for integer matrices, float64 otherwise
         and always float64 in UMI mode (model.py:1341)."""
         integer = np.issubdtype(self.dtype, np.integer) and row_umi is None
-        if integer:
+        if row_umi is None:
             out = self._count_cells_fast(np.ascontiguousarray(row_cell, dtype=np.int32), n_cells, engine, cache)
             if out is not None:
                 return out
