@@ -78,9 +78,10 @@ class ClockSampler(threading.Thread):
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, interval=0.25):
         super().__init__(daemon=True)
         self.gpu = gpu_index
+        self.interval = interval
         self.rows = []
         self._halt = threading.Event()
 
@@ -93,7 +94,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in line.split(',')])
             except Exception:
                 pass
-            self._halt.wait(0.02)
+            self._halt.wait(self.interval)
 
     def stop(self):
         self._halt.set()
@@ -547,7 +548,7 @@ def run_ours(args):
         e.record()
         return s, e
 
-    sampler = ClockSampler(local)          # samples clocks / throttle reasons from the warm-up on
+    sampler = ClockSampler(local, args.clock_interval)          # samples clocks / throttle reasons from the warm-up on
     sampler.start()
     for _ in range(args.warmup):
         one_fit()
@@ -758,6 +759,8 @@ def main():
     ap.add_argument('--parity', type=int, default=120, help='models re-fitted by the CPU oracle (0: skip)')
     ap.add_argument('--cpu-budget-aln', dest='cpu_budget_aln', type=float, default=4e6,
                     help='alignments per CPU-baseline sample (about 10-30 s of CPU work)')
+    ap.add_argument('--clock-interval', dest='clock_interval', type=float, default=0.25,
+                    help='seconds between nvidia-smi clock samples during the timed region')
     ap.add_argument('--no-ref-as-written', dest='ref_as_written', action='store_false')
     ap.add_argument('--full-flow-multi', dest='full_flow_multi', action='store_true',
                     help='run the e2e_full pass under torchrun as well (default: single GPU only)')

@@ -642,12 +642,12 @@ constexpr int CLANE_FR = SS_CLANE_FR, CLANE_FC = SS_CLANE_FC;
 // THREADS: 512 (one CTA per SM, tiles of up to E_HARD alignments) or 256 (experiment: with SS_SMALL_TILE_THR=1 the
 // cluster segments are cut into E_STREAM tiles, two CTAs of different clusters share an SM and one cluster's barrier
 // / L2 exchange overlaps the other's phase A / B)
-template <int THREADS>
-__global__ void __maxnreg__(SS_CLANE_MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
+template <int THREADS, int FR_, int FC_, int MAXREG>
+__global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double s_red[64];
   __shared__ double s_dall[2][16];        // [parity][rank]: |delta pi| partial of every CTA of the cluster (pushed)
-  constexpr int FR = CLANE_FR, FC = CLANE_FC;
+  constexpr int FR = FR_, FC = FC_;
   constexpr int NW = THREADS / 32;
   const unsigned full = 0xffffffffu;
   cg::cluster_group cluster = cg::this_cluster();
@@ -1674,8 +1674,13 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     size_t smem = 0;
     int threads = CLUSTER_THREADS;
     if (!lnl) {
+      // one cluster barrier per iteration.  512 threads x 128 registers (4 row / 6 column fragment slots per lane);
+      // SS_CLANE_THREADS=256 goes with 2048-alignment tiles (SS_SMALL_TILE_THR=1: two CTAs per SM).  Measured and
+      // dropped: 1024 threads x 64 registers with half the slots (32 warps per SM) -- 53.2 ms against 52.3 ms on
+      // config 5 x0.1, the spills cost what the occupancy gains
       threads = h->clane_threads == 256 ? 256 : CLANE_THREADS;
-      kfn = threads == 256 ? em_clane_kernel<256> : em_clane_kernel<CLANE_THREADS>;   // one cluster barrier per iteration
+      if (threads == 256) kfn = em_clane_kernel<256, CLANE_FR, CLANE_FC, SS_CLANE_MAXREG>;
+      else kfn = em_clane_kernel<CLANE_THREADS, CLANE_FR, CLANE_FC, SS_CLANE_MAXREG>;
       smem = h->clu_smem_lane[nt] + 256;
     } else {
       switch (nt) {

@@ -242,16 +242,19 @@ namespace ss {
 struct StreamGeom {
   int pe, pr, pc, pj;   // padded maxima over the streamed tiles
   int nbuf;             // 2: double buffered, 1: the largest tile leaves no room for a second buffer
+  int nval;             // column-major scratch arrays: one per buffer when two CTAs still share an SM with that
+                        // (no end-of-tile barrier among the consumers), else one (and the barrier)
 };
 constexpr int STREAM_HDR_BYTES = 256;   // the tile header (HDR_WORDS * 8 = 192 B) travels with the tile
 constexpr int STREAM_DC_INTS = 24;      // lane-group boundaries of a tile (derived by the producer)
+constexpr int STREAM_MAX_ITEMS = 512;   // items of a CTA that the per-pass compaction handles (more: checked one by one)
 __host__ __device__ inline size_t stream_buf_bytes(const StreamGeom& g) {
   return STREAM_HDR_BYTES + 12 * (size_t)g.pe + 10 * (size_t)g.pr + 6 * (size_t)g.pc + 2 * (size_t)g.pj;
 }
 // per buffer: tile arrays + tile-local x + the column-major scratch (a scratch per buffer lets a warp start the next
 // tile's row phase while slower warps are still in this tile's column phase: ONE consumer barrier per tile)
 __host__ __device__ inline size_t stream_smem_bytes(const StreamGeom& g) {
-  return (size_t)g.nbuf * (stream_buf_bytes(g) + 8 * (size_t)g.pc + 8 * ((size_t)g.pe + 8)) + 128;
+  return (size_t)g.nbuf * (stream_buf_bytes(g) + 8 * (size_t)g.pc) + (size_t)g.nval * 8 * ((size_t)g.pe + 8) + 128;
 }
 
 // double buffered when two buffers + scratch fit `limit` bytes of shared memory
@@ -259,6 +262,10 @@ inline StreamGeom make_stream_geom(const int* gm, size_t limit) {
   StreamGeom g;
   g.pe = gm[0]; g.pr = gm[1]; g.pc = gm[2]; g.pj = gm[3];
   g.nbuf = 2;
+  g.nval = 2;
+  // two CTAs per SM (228 KB, 1 KB reserved per CTA, ~4 KB of static shared memory each) is worth more than the
+  // barrier the second scratch saves
+  if (stream_smem_bytes(g) > (size_t)109 * 1024) g.nval = 1;
   if (stream_smem_bytes(g) > limit) g.nbuf = 1;
   return g;
 }
@@ -331,6 +338,12 @@ struct StreamPipe {
   uint64_t empty[2];    // the consumers are done with buffer b (consumers -> producer)
   int tile[2];          // tile in buffer b, -1: end of the pass
   int dc[2][STREAM_DC_INTS];
+  // this CTA's ACTIVE items of the current pass (segments that have converged are left out), compacted once per
+  // pass by all threads: the producer then walks a list instead of chasing tile -> segment -> done flag through
+  // global memory for every item it skips (late iterations of a celltype fit skip most of them)
+  int n_active;
+  int warp_cnt[32];
+  int items[STREAM_MAX_ITEMS];
 };
 __device__ __forceinline__ void stream_pipe_init(StreamPipe* p, int consumer_warps) {   // one thread, before a CTA barrier
   for (int b = 0; b < 2; ++b) {
@@ -505,12 +518,44 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
   const int tid = threadIdx.x, lane = tid & 31;
   const size_t bb = stream_buf_bytes(g);
   const int nbuf = g.nbuf;
-  double* val0 = reinterpret_cast<double*>(dsm + (size_t)nbuf * bb);           // nbuf scratch arrays of pe + 8
-  double* xs0 = val0 + (size_t)nbuf * (g.pe + 8);                              // nbuf tile-local x arrays of pc
+  const int nval = g.nbuf == 2 ? g.nval : 1;
+  double* val0 = reinterpret_cast<double*>(dsm + (size_t)nbuf * bb);           // nval scratch arrays of pe + 8
+  double* xs0 = val0 + (size_t)g.nval * (g.pe + 8);                            // nbuf tile-local x arrays of pc
   uint32_t n = n_use;
+  // ---- active items of this CTA (all threads) ----
+  const int n_mine = (int)blockIdx.x < n_items ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const bool compact = seg_done != nullptr && n_mine <= STREAM_MAX_ITEMS;
+  if (compact) {
+    for (int j0 = 0; j0 < n_mine; j0 += THREADS) {                   // one round for up to THREADS items
+      const int j = j0 + tid;
+      bool act = false;
+      if (j < n_mine) {
+        const int i = (int)blockIdx.x + j * (int)gridDim.x;
+        const int t = tiles ? tiles[i] : i;
+        act = ((volatile const int*)seg_done)[(int)L.tile_hdr[(long long)HDR_WORDS * t + H_SEG]] == 0;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, act);
+      if (lane == 0) pipe->warp_cnt[tid >> 5] = __popc(m);
+      if (j0 == 0 && tid == 0) pipe->n_active = 0;
+      __syncthreads();
+      int before = pipe->n_active;
+      for (int w = 0; w < (tid >> 5); ++w) before += pipe->warp_cnt[w];
+      if (act) pipe->items[before + __popc(m & ((1u << lane) - 1u))] = (int)blockIdx.x + j * (int)gridDim.x;
+      __syncthreads();
+      if (tid == 0) {
+        int tot = pipe->n_active;
+        for (int w = 0; w < THREADS / 32; ++w) tot += pipe->warp_cnt[w];
+        pipe->n_active = tot;
+      }
+      __syncthreads();
+    }
+  }
   if (tid >= CONS) {
     // ------------------------------ producer warp ------------------------------
+    const int n_list = compact ? pipe->n_active : 0;
+    int li = 0;                                                       // position in the compacted list
     auto next_item = [&](int i) {
+      if (compact) return li < n_list ? pipe->items[li++] : n_items;
       while (i < n_items) {
         const int t = tiles ? tiles[i] : i;
         if (!seg_done || ((volatile const int*)seg_done)[(int)L.tile_hdr[(long long)HDR_WORDS * t + H_SEG]] == 0) break;
@@ -584,7 +629,9 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
       }
       const StreamBuf b = carve_stream(dsm + (size_t)slot * bb, g);
       const TileView v = load_tile_view(b.hdr, 0);                   // the header arrived with the tile
-      lane_tile_compute<CONS, FR, FC>(v, b, T, xs0 + (size_t)slot * g.pc, val0 + (size_t)slot * (g.pe + 8), pipe->dc[slot]);
+      lane_tile_compute<CONS, FR, FC>(v, b, T, xs0 + (size_t)slot * g.pc, val0 + (size_t)(nval == 2 ? slot : 0) * (g.pe + 8),
+                                      pipe->dc[slot]);
+      if (nval != 2) consumer_bar<CONS>();                           // one scratch: everybody has left the column phase
       // this warp is done with the buffer (tile arrays, x, scratch); the producer refills it when all warps are.
       // No CTA-wide barrier here: the row phase of the next tile writes the OTHER scratch, and nobody reaches the
       // tile after that before everybody has passed the next tile's row | column barrier, i.e. left this column phase
