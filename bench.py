@@ -520,7 +520,7 @@ def run_ours(args):
         local_seg = np.zeros(len(rows), dtype=np.int32)
         mine = np.array([0])
     else:
-        plan = parallel.plan_local_rows(d.indptr, row_seg, S, world, rank)
+        plan = parallel.plan_local_rows(d.indptr, row_seg, S, world, rank, collective=world > 1)
         rows, local_seg, mine = plan['rows'], plan['local_seg'], plan['mine']
     eng = Engine(local)
     if mode == 'pseudobulk' and world > 1:

@@ -524,6 +524,25 @@ static int host_threads(void) {
   if (e) nt = atoi(e) < 1 ? 1 : (atoi(e) > 16 ? 16 : atoi(e));
   return nt;
 }
+typedef struct {
+  const char* ip; Py_ssize_t ip_size, nrow;
+  const int64_t* rows; int64_t* optr;
+  Py_ssize_t r0, r1;
+  int64_t total, base;
+  int pass, bad;
+} ext_t;
+static void* ext_main(void* arg) {
+  ext_t* w = (ext_t*)arg;
+  int64_t acc = w->pass ? w->base : 0;
+  for (Py_ssize_t i = w->r0; i < w->r1; ++i) {
+    const int64_t r = w->rows[i];
+    if (r < 0 || r >= w->nrow) { w->bad = 1; return NULL; }
+    if (w->pass) w->optr[i] = acc;
+    acc += ld_ix(w->ip, w->ip_size, r + 1) - ld_ix(w->ip, w->ip_size, r);
+  }
+  w->total = acc - (w->pass ? w->base : 0);
+  return NULL;
+}
 static PyObject* row_extents(PyObject* self, PyObject* args) {
   Py_buffer ip, rows, optr;
   if (!PyArg_ParseTuple(args, "y*y*w*", &ip, &rows, &optr)) return NULL;
@@ -534,22 +553,96 @@ static PyObject* row_extents(PyObject* self, PyObject* args) {
     goto done;
   }
   {
-    const int64_t* rw = (const int64_t*)rows.buf;
-    int64_t* o = (int64_t*)optr.buf;
+    /* two passes over the rows on a few threads: chunk totals, then the prefix sums from the chunk bases */
+    int nt = host_threads();
+    if (n < 1000000) nt = 1;
+    ext_t w[16];
+    pthread_t th[16];
+    int bad = 0;
     int64_t acc = 0;
-    for (Py_ssize_t i = 0; i < n; ++i) {
-      if (rw[i] < 0 || rw[i] >= nrow) {
-        PyErr_Format(PyExc_IndexError, "row id %lld outside [0, %zd)", (long long)rw[i], nrow);
-        goto done;
+    Py_BEGIN_ALLOW_THREADS
+    for (int pass = 0; pass < 2; ++pass) {
+      int64_t base = 0;
+      for (int i = 0; i < nt; ++i) {
+        if (pass == 0) {
+          w[i].ip = (const char*)ip.buf; w[i].ip_size = ip.itemsize; w[i].nrow = nrow;
+          w[i].rows = (const int64_t*)rows.buf; w[i].optr = (int64_t*)optr.buf;
+          w[i].r0 = n * i / nt; w[i].r1 = n * (i + 1) / nt; w[i].bad = 0; w[i].total = 0;
+        } else {
+          w[i].base = base;
+          base += w[i].total;
+        }
+        w[i].pass = pass;
       }
-      o[i] = acc;
-      acc += ld_ix((const char*)ip.buf, ip.itemsize, rw[i] + 1) - ld_ix((const char*)ip.buf, ip.itemsize, rw[i]);
+      int started = 0;
+      for (int i = 1; i < nt; ++i) {
+        if (pthread_create(&th[i], NULL, ext_main, &w[i]) != 0) break;
+        ++started;
+      }
+      ext_main(&w[0]);
+      for (int i = 1; i <= started; ++i) pthread_join(th[i], NULL);
+      for (int i = started + 1; i < nt; ++i) ext_main(&w[i]);
+      for (int i = 0; i < nt; ++i) bad |= w[i].bad;
+      if (bad) break;
+      if (pass == 1) acc = base;
     }
-    o[n] = acc;
+    Py_END_ALLOW_THREADS
+    if (bad) {
+      PyErr_Format(PyExc_IndexError, "row id outside [0, %zd)", nrow);
+      goto done;
+    }
+    ((int64_t*)optr.buf)[n] = acc;
     result = PyLong_FromLongLong(acc);
   }
 done:
   PyBuffer_Release(&ip); PyBuffer_Release(&rows); PyBuffer_Release(&optr);
+  return result;
+}
+/* gather_chunk(indptr, src, rows, out_ptr, e0, e1, dst): elements [e0, e1) of the row-compacted copy of `src`
+ * (what gather_rows would produce) written to dst[0 .. e1-e0) -- the staging ring of the upload is filled straight
+ * from the host matrix, the compacted copy never exists on the host.  Called from several Python threads at once
+ * (the GIL is released). */
+static PyObject* gather_chunk(PyObject* self, PyObject* args) {
+  Py_buffer ip, src, rows, optr, dst;
+  long long e0, e1;
+  if (!PyArg_ParseTuple(args, "y*y*y*y*LLw*", &ip, &src, &rows, &optr, &e0, &e1, &dst)) return NULL;
+  PyObject* result = NULL;
+  const Py_ssize_t n = rows.len / 8, isz = src.itemsize;
+  if ((ip.itemsize != 4 && ip.itemsize != 8) || rows.itemsize != 8 || optr.itemsize != 8 || optr.len / 8 != n + 1 ||
+      e0 < 0 || e1 < e0 || (e1 - e0) * isz > dst.len) {
+    PyErr_SetString(PyExc_TypeError, "gather_chunk: mismatching buffers");
+    goto done;
+  }
+  {
+    const int64_t* op = (const int64_t*)optr.buf;
+    const int64_t* rw = (const int64_t*)rows.buf;
+    if (e1 > op[n]) { PyErr_SetString(PyExc_ValueError, "gather_chunk: range beyond the last row"); goto done; }
+    Py_BEGIN_ALLOW_THREADS
+    /* first row that holds element e0: largest r with op[r] <= e0 and op[r+1] > e0 */
+    Py_ssize_t lo = 0, hi = n;
+    while (lo < hi) {
+      const Py_ssize_t mid = (lo + hi) / 2;
+      if (op[mid + 1] <= e0) lo = mid + 1; else hi = mid;
+    }
+    Py_ssize_t r = lo;
+    int64_t e = e0;
+    char* d = (char*)dst.buf;
+    while (e < e1 && r < n) {
+      /* run of consecutive rows starting at r */
+      Py_ssize_t re = r + 1;
+      while (re < n && rw[re] == rw[re - 1] + 1 && op[re] < e1) ++re;
+      const int64_t src0 = ld_ix((const char*)ip.buf, ip.itemsize, rw[r]) + (e - op[r]);
+      const int64_t run_end = op[re] < e1 ? op[re] : e1;
+      memcpy(d, (const char*)src.buf + src0 * isz, (size_t)((run_end - e) * isz));
+      d += (run_end - e) * isz;
+      e = run_end;
+      r = re;
+    }
+    Py_END_ALLOW_THREADS
+    result = PyLong_FromLongLong(e1 - e0);
+  }
+done:
+  PyBuffer_Release(&ip); PyBuffer_Release(&src); PyBuffer_Release(&rows); PyBuffer_Release(&optr); PyBuffer_Release(&dst);
   return result;
 }
 static PyObject* gather_rows(PyObject* self, PyObject* args) {
@@ -814,6 +907,8 @@ static PyMethodDef methods[] = {
     {"lpt_assign", lpt_assign, METH_VARARGS, "lpt_assign(seg_A, world, model_rank): longest-processing-time packing"},
     {"count_rows", count_rows, METH_VARARGS, "count_rows(row_segment, model_rank, rank, counts): rows of a rank per row chunk"},
     {"fill_rows", fill_rows, METH_VARARGS, "fill_rows(row_segment, model_rank, local_id, rank, offsets, rows, local_seg)"},
+    {"gather_chunk", gather_chunk, METH_VARARGS,
+     "gather_chunk(indptr, src, rows, out_ptr, e0, e1, dst): a range of the row-compacted copy of src, written to dst"},
     {"row_extents", row_extents, METH_VARARGS, "row_extents(indptr, rows, out_ptr): prefix sums of the lengths of the given rows"},
     {"gather_rows", gather_rows, METH_VARARGS,
      "gather_rows(indptr, indices, data, rows, out_ptr, out_idx, out_dat): row-compacted copy of a CSR matrix"},

@@ -161,17 +161,23 @@ class _HostStager:
                     issue(i + self.SLOTS)                    # the slot is free again
         return n
 
-    def push(self, a, device):
+    def push(self, a, device, filler=None, shape=None, dtype=None):
         """Host array -> new device tensor through the ring (the mirror image of ``fetch``): worker threads copy
         chunks into the pinned slots while earlier slots are on their way.  For uploads too large to pin as a
-        whole -- pinning a multi-GB matrix costs more than the transfer and the pinned block would stay cached."""
-        a = np.ascontiguousarray(a)
-        n = a.nbytes
+        whole -- pinning a multi-GB matrix costs more than the transfer and the pinned block would stay cached.
+        With ``filler(dst_bytes, byte_offset, n_bytes)`` the chunks are PRODUCED into the slots instead of copied
+        from ``a`` (``shape`` / ``dtype`` of the result given): the rows a rank cuts out of the host matrix go
+        straight into the staging ring, the compacted copy never exists on the host."""
+        if filler is None:
+            a = np.ascontiguousarray(a)
+            shape, dtype = tuple(a.shape), a.dtype
+            src = a.reshape(-1).view(np.uint8)
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
         with self.lock, torch.cuda.device(device):
             self._ensure()
-            t = torch.empty(tuple(a.shape), dtype=_NP_TORCH[a.dtype.type], device=device)
+            t = torch.empty(tuple(shape), dtype=_NP_TORCH[dtype.type], device=device)
             dst = t.reshape(-1).view(torch.uint8)
-            src = a.reshape(-1).view(np.uint8)
             stream = torch.cuda.current_stream(device)
             C_ = self.CHUNK
             offs = list(range(0, n, C_))
@@ -179,7 +185,10 @@ class _HostStager:
             def fill(slot, off, m, ev):
                 if ev is not None:
                     ev.synchronize()                             # the slot's previous chunk has left
-                self.ring_np[slot * C_:slot * C_ + m] = src[off:off + m]
+                if filler is not None:
+                    filler(self.ring_np[slot * C_:slot * C_ + m], off, m)
+                else:
+                    self.ring_np[slot * C_:slot * C_ + m] = src[off:off + m]
 
             fills = [None] * self.SLOTS
             for i in range(min(self.SLOTS, len(offs))):
@@ -432,6 +441,37 @@ class Engine:
             self._keep['row_ptr'] = self._to_dev(indptr, np.int32)
             self._keep['col_idx'] = self._to_dev(indices, np.int32)
             self._keep['score'] = self._to_dev(scores, np.uint16)
+        self.h2d_bytes = 4 * (self.N + 1) + 6 * self.A
+
+    def set_matrix_rows(self, indptr, indices, scores, rows, K):
+        """Upload the given rows (ascending global ids) of a HOST CSR matrix as the engine's matrix: a rank of a
+        sharded run holds only its own rows.  The rows are cut out while they are staged -- worker
+        threads copy each chunk of the compacted arrays straight from the host matrix into the pinned ring
+        (``gather_chunk``, csrc/ss_hostutil.c) -- so the host never holds a compacted copy."""
+        from . import hostutil
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        indptr = np.ascontiguousarray(indptr)
+        indices, scores = np.ascontiguousarray(indices), np.ascontiguousarray(scores)
+        if indices.dtype != np.int32 or scores.dtype != np.uint16:
+            return self.set_matrix(*hostutil.gather_rows(indptr, indices, scores, rows), K)     # converting route
+        ptr = hostutil.row_extents(indptr, rows)
+        self.N, self.K, self.A = len(rows), int(K), int(ptr[-1])
+        if self.A > 2 ** 31 - 1:
+            raise OverflowError(f'{self.A} alignments: the device layout uses int32 row pointers')
+        lib = hostutil.load()
+        with torch.cuda.device(self.device):
+            self._keep['row_ptr'] = self._to_dev(ptr, np.int32)
+            for name, arr in (('col_idx', indices), ('score', scores)):
+                isz = arr.dtype.itemsize
+                if self.A * isz <= PINNED_UPLOAD_LIMIT // 8:
+                    out = np.empty(self.A, dtype=arr.dtype)                    # small: one gather, one copy
+                    if self.A:
+                        lib.gather_chunk(indptr, arr, rows, ptr, 0, self.A, out)
+                    self._keep[name] = self._to_dev(out, arr.dtype.type)
+                else:
+                    def filler(dst, off, m, arr=arr, isz=isz):
+                        lib.gather_chunk(indptr, arr, rows, ptr, off // isz, (off + m) // isz, dst)
+                    self._keep[name] = _stager.push(None, self.device, filler=filler, shape=(self.A,), dtype=arr.dtype)
         self.h2d_bytes = 4 * (self.N + 1) + 6 * self.A
 
     def set_matrix_device(self, row_ptr, col_idx, score, K):

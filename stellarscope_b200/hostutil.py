@@ -106,3 +106,12 @@ def group_sizes(codes, n_groups):
     out = np.zeros(int(n_groups), dtype=np.int64)
     load().segment_alignments(np.zeros(0, dtype=np.int32), np.ascontiguousarray(codes, dtype=np.int32), out)
     return out
+
+
+def row_extents(indptr, rows):
+    """int64[n + 1]: prefix sums of the lengths of the given rows (the row pointers of the row-compacted matrix)."""
+    import numpy as np
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    ptr = np.empty(len(rows) + 1, dtype=np.int64)
+    load().row_extents(np.ascontiguousarray(indptr), rows, ptr)
+    return ptr

@@ -90,8 +90,7 @@ class TelescopeLikelihood(object):
             if device_matrix is not None and attempt == 0:
                 self._engine.set_matrix_device(*device_matrix, self.K)         # canonical copy of another model object
             elif self._row_ids is not None:
-                from . import hostutil
-                self._engine.set_matrix(*hostutil.gather_rows(m.indptr, m.indices, m.data, self._row_ids), self.K)
+                self._engine.set_matrix_rows(m.indptr, m.indices, m.data, self._row_ids, self.K)
             else:
                 self._engine.set_matrix(m.indptr, m.indices, m.data, self.K)    # H2D in flight ...
             if attempt == 0:
@@ -572,7 +571,8 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
         plan = parallel.plan_local_rows(m.indptr, row_segment, len(keys), world, rank,
                                         wide=getattr(opts, 'wide_models', None) or [],
                                         wide_cost=getattr(opts, 'wide_model_cost', 2_000_000),
-                                        row_cell=row_cell, cells_whole=umi_counts, all_assigned=not loose)
+                                        row_cell=row_cell, cells_whole=umi_counts, all_assigned=not loose,
+                                        collective=True)
         mine, wide, rows = plan['mine'], plan['wide'], plan['rows']
         _t.append(time.perf_counter())
         # every rank cuts ITS rows out of the host matrix and uploads only them (1/world of the H2D traffic)

@@ -195,7 +195,7 @@ def row_block(indptr, rank, world):
 # Rank-local rows of a sharded run and the gathers of its results
 # ---------------------------------------------------------------------------
 def plan_local_rows(indptr, row_segment, n_segments, world, rank, wide=None, wide_cost=2_000_000, row_cell=None,
-                    cells_whole=False, all_assigned=None):
+                    cells_whole=False, all_assigned=None, collective=False):
     """Which rows this rank holds when the models of a pooling mode are sharded over ``world`` ranks.
 
     Every row of the matrix goes to exactly ONE rank, so that whatever is computed per row (z, the reassignment
@@ -211,7 +211,8 @@ def plan_local_rows(indptr, row_segment, n_segments, world, rank, wide=None, wid
     Returns a dict: ``rows`` (ascending global row ids of this rank, int64), ``local_seg`` (int32 per local row:
     index into ``mine`` or -1), ``mine`` (global ids of the models packed onto this rank), ``wide`` (global ids of
     the wide models), ``wide_local`` (per wide model: bool mask over the LOCAL rows = this rank's block),
-    ``seg_A`` (alignments per model)."""
+    ``seg_A`` (alignments per model).  ``collective``: the call is made by all ranks of the default process group
+    at the same time (the per-model alignment counts are then computed in 1/world slices and all-reduced)."""
     indptr = np.asarray(indptr)
     row_segment = np.asarray(row_segment)
     N = len(row_segment)
@@ -222,7 +223,13 @@ def plan_local_rows(indptr, row_segment, n_segments, world, rank, wide=None, wid
         # the common case -- every row belongs to a packed model: three threaded passes in C instead of ~10 numpy
         # passes over per-row arrays (1.4x10^8 rows at atlas scale)
         from . import hostutil
-        seg_A = hostutil.segment_alignments(indptr, row_segment, n_segments)
+        if collective and world > 1:
+            # every rank counts the alignments per model over 1/world of the rows; the sums are all-reduced
+            r0, r1 = N * rank // world, N * (rank + 1) // world
+            part = hostutil.segment_alignments(indptr[r0:r1 + 1], row_segment[r0:r1], n_segments)
+            seg_A = allreduce_sum_host(part).astype(np.int64)
+        else:
+            seg_A = hostutil.segment_alignments(indptr, row_segment, n_segments)
         model_rank = hostutil.lpt_assign(seg_A, world)
         mine = np.flatnonzero(model_rank == rank).astype(np.int64)
         local_id = np.full(n_segments, -1, dtype=np.int32)
