@@ -171,7 +171,7 @@ __device__ __forceinline__ void dense_exchange(const DenseArgs& d, unsigned long
 
 // ---- peers mode: the whole fit in one cooperative kernel ---------------------------------------
 template <int THREADS, bool LNL>
-__global__ void __launch_bounds__(THREADS) em_dense_kernel(EmArgs a, DenseArgs d) {
+__global__ void __launch_bounds__(THREADS, LNL ? 1 : 2) em_dense_kernel(EmArgs a, DenseArgs d) {
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double s_red[64];
   __shared__ uint64_t s_bar;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(THREADS) em_dense_kernel(EmArgs a, DenseArgs d
   uint32_t n_use = 0u;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
-    stream_pipe_init(&s_pipe, THREADS / 32 - 1);
+    stream_pipe_init(&s_pipe, THREADS / 32 - STREAM_NPROD);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(THREADS) em_dense_kernel(EmArgs a, DenseArgs d
 
 // ---- hook mode: the same steps as separate launches --------------------------------------------
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) dense_pass_kernel(EmArgs a, DenseArgs d, int cur, int lnl_pass, int tail_buf) {
+__global__ void __launch_bounds__(THREADS, 2) dense_pass_kernel(EmArgs a, DenseArgs d, int cur, int lnl_pass, int tail_buf) {
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double s_red[64];
   __shared__ uint64_t s_bar;
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(THREADS) dense_pass_kernel(EmArgs a, DenseArgs
   uint32_t n_use = 0u;
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
-    stream_pipe_init(&s_pipe, THREADS / 32 - 1);
+    stream_pipe_init(&s_pipe, THREADS / 32 - STREAM_NPROD);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();

@@ -34,6 +34,9 @@ struct StreamArgs {
   const int* col_slot;   // [n_cols] absolute slot
   long long n_cols;
   int* ctl;              // [0] = number of active segments, [1 + i] = segment i done (iters)
+  const int* chunk_seg;  // [n_chunks] column chunks (SS_COL_CHUNK slots of one segment): segment ...
+  const int* chunk_j0;   // ... and first column of the chunk (segment-relative)
+  int n_chunks;
   StreamGeom geom;       // shared-memory geometry of the streaming tile pass
 };
 
@@ -1207,7 +1210,7 @@ __global__ void __launch_bounds__(THREADS) em_cluster_kernel(EmArgs a, ClusterAr
 // streaming kernel: cooperative grid over the tiles of multi-tile segments
 // ---------------------------------------------------------------------------
 template <int THREADS, bool LNL>
-__global__ void __launch_bounds__(THREADS) em_stream_kernel(EmArgs a, StreamArgs sa) {
+__global__ void __launch_bounds__(THREADS, LNL ? 1 : 2) em_stream_kernel(EmArgs a, StreamArgs sa) {
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double s_red[64];
   __shared__ uint64_t s_bar;
@@ -1223,7 +1226,7 @@ __global__ void __launch_bounds__(THREADS) em_stream_kernel(EmArgs a, StreamArgs
   uint32_t n_use = 0u;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
-    stream_pipe_init(&s_pipe, THREADS / 32 - 1);
+    stream_pipe_init(&s_pipe, THREADS / 32 - STREAM_NPROD);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -1235,38 +1238,48 @@ __global__ void __launch_bounds__(THREADS) em_stream_kernel(EmArgs a, StreamArgs
     lane_stream_pass<THREADS, SS_STREAM_FR, SS_STREAM_FC>(a.L, a.L.c_scol, sa.tiles, sa.n_tiles, a.F.seg_iters, ptg, a.F.sc_T, sa.geom, dsm,
                                     &s_pipe, n_use);
     grid.sync();
-    // ---- update pass over the columns of the active multi-tile segments ----
+    // ---- update pass over the columns of the active multi-tile segments: one warp per column chunk of one segment
+    //      (per-segment constants loaded once, coalesced column loads, four columns per lane in flight; a converged
+    //      segment costs one load per chunk) ----
     double* __restrict__ ptn = a.F.sc_pt[cur ^ 1];
-    for (long long x0 = (long long)blockIdx.x * THREADS; x0 < sa.n_cols; x0 += gthreads) {
-      const long long x = x0 + tid;
-      double d = 0.0;
-      int si = -1;
-      if (x < sa.n_cols) {
-        si = sa.col_seg[x];
-        const int seg = sa.segs[si];
-        if (a.F.seg_iters[seg] == 0) {
-          const int slot = sa.col_slot[x];
-          const double T = a.F.sc_T[slot];
-          const double th = (T + a.F.seg_thpw[seg]) * a.F.seg_inv_thd[seg];
-          const double pn = (a.L.sc_pisum0[slot] + T + a.F.seg_pipw[seg]) * a.F.seg_inv_pid[seg];
-          // pi of the previous iteration; pi_0 = 1/K for every locus (model.py:164)
-          const double pold = it == 1 ? 1.0 / (double)a.P.K : a.F.sc_pi[slot];
-          d = fabs(pn - pold);
-          a.F.sc_pi[slot] = pn;
-          a.F.sc_theta[slot] = th;
-          ptn[slot] = pn * th;
-          a.F.sc_T[slot] = 0.0;
-        } else {
-          si = -1;
+    {
+      const int gwarp = (int)(gtid >> 5), nwarps = (int)(gthreads >> 5);
+      for (int ci = gwarp; ci < sa.n_chunks; ci += nwarps) {
+        const int seg = sa.chunk_seg[ci];
+        if (a.F.seg_iters[seg] != 0) continue;
+        const int c0 = a.L.seg_col0[seg], nc = a.L.seg_ncol[seg];
+        const int jb = sa.chunk_j0[ci], je = min(nc, jb + SS_COL_CHUNK);
+        const double thpw = a.F.seg_thpw[seg], inv_thd = a.F.seg_inv_thd[seg];
+        const double pipw = a.F.seg_pipw[seg], inv_pid = a.F.seg_inv_pid[seg];
+        const double pi0 = 1.0 / (double)a.P.K;                  // pi_0 = 1/K for every locus (model.py:164)
+        double d = 0.0;
+        for (int j0 = jb; j0 < je; j0 += 128) {
+          double T[4], p0[4], po[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 32 * u + lane;
+            const bool ok = j < je;
+            T[u] = ok ? a.F.sc_T[c0 + j] : 0.0;
+            p0[u] = ok ? a.L.sc_pisum0[c0 + j] : 0.0;
+            po[u] = (ok && it > 1) ? a.F.sc_pi[c0 + j] : pi0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 32 * u + lane;
+            if (j < je) {
+              const int slot = c0 + j;
+              const double th = (T[u] + thpw) * inv_thd;
+              const double pn = (p0[u] + T[u] + pipw) * inv_pid;
+              d += fabs(pn - po[u]);
+              a.F.sc_pi[slot] = pn;
+              a.F.sc_theta[slot] = th;
+              ptn[slot] = pn * th;
+              a.F.sc_T[slot] = 0.0;
+            }
+          }
         }
-      }
-      // warp-aggregate when the whole warp works on one segment
-      const int s0 = __shfl_sync(0xffffffffu, si, 0);
-      if (__all_sync(0xffffffffu, si == s0)) {
         d = warp_sum(d);
-        if (lane == 0 && s0 >= 0) atomicAdd(&a.F.seg_diffacc[sa.segs[s0]], d);
-      } else if (si >= 0) {
-        atomicAdd(&a.F.seg_diffacc[sa.segs[si]], d);
+        if (lane == 0) atomicAdd(&a.F.seg_diffacc[seg], d);
       }
     }
     grid.sync();
@@ -1630,6 +1643,9 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     sa.col_slot = h->stream_col_slot;
     sa.n_cols = h->n_stream_cols;
     sa.ctl = h->stream_ctl;
+    sa.chunk_seg = h->stream_chunk_seg;
+    sa.chunk_j0 = h->stream_chunk_j0;
+    sa.n_chunks = h->n_stream_chunks;
     sa.geom = make_stream_geom(h->geom_stream, h->max_smem_optin - 2048);
     SS_CUDA_CHECK(h, cudaMemsetAsync(h->stream_ctl, 0, 4 * sizeof(int), sx));
     const size_t smem = std::max(h->stream_smem, stream_smem_bytes(sa.geom));

@@ -247,7 +247,8 @@ struct StreamGeom {
 };
 constexpr int STREAM_HDR_BYTES = 256;   // the tile header (HDR_WORDS * 8 = 192 B) travels with the tile
 constexpr int STREAM_DC_INTS = 24;      // lane-group boundaries of a tile (derived by the producer)
-constexpr int STREAM_MAX_ITEMS = 512;   // items of a CTA that the per-pass compaction handles (more: checked one by one)
+constexpr int STREAM_MAX_ITEMS = 1024;
+constexpr int STREAM_NPROD = 1;         // producer warps of a streaming CTA  // items of a CTA that the per-pass compaction handles (more: checked one by one)
 __host__ __device__ inline size_t stream_buf_bytes(const StreamGeom& g) {
   return STREAM_HDR_BYTES + 12 * (size_t)g.pe + 10 * (size_t)g.pr + 6 * (size_t)g.pc + 2 * (size_t)g.pj;
 }
@@ -343,7 +344,7 @@ struct StreamPipe {
   // global memory for every item it skips (late iterations of a celltype fit skip most of them)
   int n_active;
   int warp_cnt[32];
-  int items[STREAM_MAX_ITEMS];
+  uint16_t items[STREAM_MAX_ITEMS];   // ordinal j of the active item blockIdx + j * gridDim
 };
 __device__ __forceinline__ void stream_pipe_init(StreamPipe* p, int consumer_warps) {   // one thread, before a CTA barrier
   for (int b = 0; b < 2; ++b) {
@@ -514,7 +515,11 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
                                                  int n_items, const int* seg_done, const double* __restrict__ x,
                                                  double* __restrict__ T, const StreamGeom& g, unsigned char* dsm,
                                                  StreamPipe* pipe, uint32_t& n_use) {
-  constexpr int CONS = THREADS - 32;                     // consumer threads; the last warp produces
+  // producer warps (the last warps of the CTA).  Two producers, each filling every other use, were measured: the
+  // consumers' wait for a complete buffer did not shrink and the lost consumer warp cost 9 % on config 4 (2.87 against
+  // 2.63 ms): the wait is for the data, not for the producer's instructions
+  constexpr int NPROD = STREAM_NPROD;
+  constexpr int CONS = THREADS - 32 * NPROD;             // consumer threads
   const int tid = threadIdx.x, lane = tid & 31;
   const size_t bb = stream_buf_bytes(g);
   const int nbuf = g.nbuf;
@@ -522,10 +527,10 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
   double* val0 = reinterpret_cast<double*>(dsm + (size_t)nbuf * bb);           // nval scratch arrays of pe + 8
   double* xs0 = val0 + (size_t)g.nval * (g.pe + 8);                            // nbuf tile-local x arrays of pc
   uint32_t n = n_use;
-  // ---- active items of this CTA (all threads) ----
+  // ---- active items of this CTA (all threads): items[k] = ordinal j of the k-th active item blockIdx + j * gridDim ----
   const int n_mine = (int)blockIdx.x < n_items ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const bool compact = seg_done != nullptr && n_mine <= STREAM_MAX_ITEMS;
-  if (compact) {
+  const bool listed = seg_done != nullptr && n_mine <= STREAM_MAX_ITEMS;
+  if (listed) {
     for (int j0 = 0; j0 < n_mine; j0 += THREADS) {                   // one round for up to THREADS items
       const int j = j0 + tid;
       bool act = false;
@@ -540,7 +545,7 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
       __syncthreads();
       int before = pipe->n_active;
       for (int w = 0; w < (tid >> 5); ++w) before += pipe->warp_cnt[w];
-      if (act) pipe->items[before + __popc(m & ((1u << lane) - 1u))] = (int)blockIdx.x + j * (int)gridDim.x;
+      if (act) pipe->items[before + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
       __syncthreads();
       if (tid == 0) {
         int tot = pipe->n_active;
@@ -550,43 +555,52 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
       __syncthreads();
     }
   }
+  // number of tiles of this pass when it is known up front (list, or no segment can drop out); -1: the single
+  // producer finds out by walking (more items than the list holds)
+  const int M = listed ? pipe->n_active : (seg_done == nullptr ? n_mine : -1);
   if (tid >= CONS) {
-    // ------------------------------ producer warp ------------------------------
-    const int n_list = compact ? pipe->n_active : 0;
-    int li = 0;                                                       // position in the compacted list
-    auto next_item = [&](int i) {
-      if (compact) return li < n_list ? pipe->items[li++] : n_items;
-      while (i < n_items) {
-        const int t = tiles ? tiles[i] : i;
+    // ------------------------------ producer warps ------------------------------
+    // producer p fills the uses k = p, p + 2, ... of this pass (with two buffers: always the same buffer), so a
+    // producer has two consumer tile times for one tile's copies + x gather; use M is the end marker
+    const int p = (tid - CONS) >> 5;
+    const int kstep = M >= 0 ? NPROD : 1;
+    int i = (int)blockIdx.x;                                          // walking producer only
+    auto skip_done = [&](int ii) {
+      while (ii < n_items) {
+        const int t = tiles ? tiles[ii] : ii;
         if (!seg_done || ((volatile const int*)seg_done)[(int)L.tile_hdr[(long long)HDR_WORDS * t + H_SEG]] == 0) break;
-        i += gridDim.x;
+        ii += gridDim.x;
       }
-      return i;
+      return ii;
     };
-    int i = next_item(blockIdx.x);
-    while (true) {
-      const int slot = nbuf == 2 ? (int)(n & 1u) : 0;
-      const uint32_t k = nbuf == 2 ? (n >> 1) : n;
-      if (k >= 1) mbar_wait(&pipe->empty[slot], (k - 1) & 1u);       // the consumers have released this buffer
-      if (i >= n_items) {
+    if (M < 0) i = skip_done(i);
+    uint32_t n_end = n;                                               // first use after this pass (walking producer)
+    for (int k = p; M >= 0 ? k <= M : p == 0; k += kstep) {
+      const uint32_t nk = n + (uint32_t)k;
+      const int slot = nbuf == 2 ? (int)(nk & 1u) : 0;
+      const uint32_t kk = nbuf == 2 ? (nk >> 1) : nk;
+      if (kk >= 1) mbar_wait(&pipe->empty[slot], (kk - 1) & 1u);      // the consumers have released this buffer
+      const bool last = M >= 0 ? k == M : i >= n_items;
+      if (last) {
         if (lane == 0) {
           pipe->tile[slot] = -1;
           mbar_arrive(&pipe->full[slot]);
           mbar_arrive(&pipe->mapf[slot]);
           mbar_arrive(&pipe->ready[slot]);
         }
-        ++n;
+        n_end = nk + 1;
         break;
       }
-      const int t = tiles ? tiles[i] : i;
+      const int item = M >= 0 ? (int)blockIdx.x + (listed ? (int)pipe->items[k] : k) * (int)gridDim.x : i;
+      const int t = tiles ? tiles[item] : item;
       const TileView v = load_tile_view(L.tile_hdr, t);
       const StreamBuf b = carve_stream(dsm + (size_t)slot * bb, g);
       if (lane == 0) {
         fence_proxy_async();
         stream_issue_loads2(L, colmap, t, v, b, &pipe->full[slot], &pipe->mapf[slot]);
       }
-      const int i_next = next_item(i + gridDim.x);                   // overlaps the flight of the copies
-      mbar_wait(&pipe->mapf[slot], k & 1u);                          // the column map is in; the big arrays still fly
+      if (M < 0) i = skip_done(i + gridDim.x);                        // overlaps the flight of the copies
+      mbar_wait(&pipe->mapf[slot], kk & 1u);                          // the column map is in; the big arrays still fly
       // tile-local x: 8 loads in flight per lane
       double* xs = xs0 + (size_t)slot * g.pc;
       for (int c0 = 0; c0 < v.ncol; c0 += 256) {
@@ -602,7 +616,7 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
           if (c < v.ncol) xs[c] = xv[u];
         }
       }
-      mbar_wait(&pipe->full[slot], k & 1u);
+      mbar_wait(&pipe->full[slot], kk & 1u);
       if (lane == 0) {
         xs[v.ncol] = 0.0;
         stream_boundaries(b.hdr, v.nrows, v.ncol, FR * CONS, FC * CONS, pipe->dc[slot]);
@@ -610,8 +624,12 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&pipe->ready[slot]);                // release: x, boundaries, tile id
-      ++n;
-      i = i_next;
+    }
+    // every thread leaves with the same use count: the consumers count theirs, the producers take it from the pass
+    if (M >= 0) n = n + (uint32_t)M + 1u;
+    else if (p == 0) n = n_end;
+    if (M < 0) {                                                      // the idle second producer learns it from the first
+      if (p == 0 && lane == 0) pipe->n_active = (int)(n_end - n_use);
     }
   } else {
     // ------------------------------ consumer warps ------------------------------
@@ -639,6 +657,8 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
       if (lane == 0) mbar_arrive(&pipe->empty[slot]);
     }
   }
+  __syncthreads();
+  if (M < 0 && tid >= CONS) n = n_use + (uint32_t)pipe->n_active;     // walking mode: uses counted by producer 0
   n_use = n;
   __syncthreads();
 }

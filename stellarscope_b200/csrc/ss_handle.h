@@ -72,6 +72,9 @@ struct ss_handle_s {
   int* stream_col_seg = nullptr;  // device: for every column of a multi-tile segment, index into stream_segs
   int* stream_col_slot = nullptr; // device: its absolute slot
   long long n_stream_cols = 0;
+  int* stream_chunk_seg = nullptr;   // device: column chunks (SS_COL_CHUNK slots) of the streamed segments: segment ...
+  int* stream_chunk_j0 = nullptr;    // ... and first column (segment-relative)
+  int n_stream_chunks = 0;
   // column chunks (SS_COL_CHUNK slots of one segment each): the per-column work of prepare / finalize runs one
   // warp per chunk, so a segment with many columns does not serialise on one warp; partial sums are combined
   // per segment in chunk order (deterministic)

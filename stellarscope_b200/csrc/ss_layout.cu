@@ -27,6 +27,7 @@ void free_layout(ss_handle_s* h) {
     h->cls_smem[c] = 0;
   }
   h->stream_tiles = h->stream_segs = h->stream_col_seg = h->stream_col_slot = nullptr;
+  h->stream_chunk_seg = h->stream_chunk_j0 = nullptr; h->n_stream_chunks = 0;
   h->n_stream_tiles = h->n_stream_segs = 0;
   h->n_stream_cols = 0;
   h->all_tiles = nullptr;
@@ -265,6 +266,18 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
         col_slot.push_back(seg_col0[s] + j);
       }
     }
+  }
+  // column chunks of the streamed segments: the update pass of the streaming kernel runs one warp per chunk
+  {
+    std::vector<int> sch_seg, sch_j0;
+    for (int s2 : segs)
+      for (int j = 0; j < seg_ncol[s2]; j += SS_COL_CHUNK) {
+        sch_seg.push_back(s2);
+        sch_j0.push_back(j);
+      }
+    h->n_stream_chunks = (int)sch_seg.size();
+    SS_CUDA_CHECK(h, upload(pool, &h->stream_chunk_seg, (const int*)sch_seg.data(), sch_seg.size(), st));
+    SS_CUDA_CHECK(h, upload(pool, &h->stream_chunk_j0, (const int*)sch_j0.data(), sch_j0.size(), st));
   }
   h->n_stream_segs = (int)segs.size();
   h->n_stream_cols = (long long)col_seg.size();

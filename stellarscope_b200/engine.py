@@ -211,7 +211,8 @@ _TORCH_NP = {torch.uint8: np.uint8, torch.int8: np.int8, torch.int16: np.int16, 
              torch.bool: np.bool_}
 _NP_TORCH = {v: k for k, v in _TORCH_NP.items()}
 _stager = _HostStager()
-PINNED_UPLOAD_LIMIT = 256 << 20      # larger uploads go through the staging ring instead of a pinned copy
+PINNED_UPLOAD_LIMIT = 256 << 20      # set_matrix_rows: smaller arrays are gathered on the host in one piece
+RING_UPLOAD_MIN = 1 << 20            # uploads from this size on go through the pinned staging ring
 
 
 def write_all(fh, mv):
@@ -311,12 +312,11 @@ class Engine:
 
     def _to_dev(self, arr, dtype, pinned=True):
         a = _np(arr, dtype)
-        if a.nbytes > PINNED_UPLOAD_LIMIT and a.dtype.type in _NP_TORCH:
+        if a.nbytes >= RING_UPLOAD_MIN and a.dtype.type in _NP_TORCH:
+            # through the persistent pinned ring: pin_memory() allocates page-locked memory on every call
+            # (~1 ms per array, more than the transfer of a few MB; for a multi-GB matrix more than the upload)
             return _stager.push(a, self.device)
-        t = torch.from_numpy(a)
-        if pinned and a.nbytes:
-            t = t.pin_memory()
-        return t.to(self.device, non_blocking=True)
+        return torch.from_numpy(a).to(self.device)
 
     @staticmethod
     def _p(t):
