@@ -58,7 +58,10 @@ TIE_TOL = 1e-9
 # dram__bytes_read.sum + dram__bytes_write.sum of the EM kernels of ONE fit, from ncu --set full captures
 # (profiles/): config -> (bytes per fit at scale 1.0 or None, source)
 NCU_TRAFFIC = {
-    'cfg2': (111.0e6, 'profiles/r1e_em_full_ncu.csv (one fit, sum over the 16 EM kernels)'),
+    ('cfg2', 1.0): (111.0e6, 'profiles/r1e_em_full_ncu.csv (one fit, sum over the 16 EM kernels)'),
+    ('cfg5', 0.1): (8.762e9, 'profiles/r2i_cfg5_x0.1_em_ncu.csv (one fit at scale 0.1, sum over the 21 EM kernels: '
+                             '7.5 GB of it is em_stream_kernel re-reading the tiles of the 92 largest cells every '
+                             'iteration; lane + cluster kernels read their tiles once: 1.2 GB)'),
 }
 
 
@@ -680,9 +683,11 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         cpu_rate, cpu_units, cpu_dt, cpu_n, cpu_used, cpu_aln = cpu_sample_rate(d, mode, cores, args.cpu_budget_aln, seed=1)
         asw = reference_as_written(d, mode, cores) if args.ref_as_written else None
-        traffic, traffic_src = NCU_TRAFFIC.get(cfg, (None, None))
-        if traffic is not None and (args.scale != 1.0 or world != 1):
+        traffic, traffic_src = NCU_TRAFFIC.get((cfg, float(args.scale)), (None, None))
+        if world != 1:
             traffic = None
+        if traffic is None:
+            traffic_src = {f'{k[0]} x{k[1]}': dict(bytes_per_fit=v[0], source=v[1]) for k, v in NCU_TRAFFIC.items()}
         fitted = seg_A > 0
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,

@@ -541,8 +541,16 @@ int em_fit_dense(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
   EmArgs a;
   a.L = L; a.F = F; a.P = h->P; a.z_out = nullptr; a.tile_list = nullptr; a.n_list = 0;
   const bool lnl = P.use_likelihood != 0;
-  d.geom = make_stream_geom(h->geom_all, h->max_smem_optin - 2048);
-  const size_t smem = std::max<size_t>(std::max(h->all_smem, stream_smem_bytes(d.geom)), 1024);
+  int occ_pick = 0;
+  const void* pick_fn = h->dn_persistent ? (lnl ? (const void*)em_dense_kernel<DN_THREADS, true> : (const void*)em_dense_kernel<DN_THREADS, false>)
+                                         : (const void*)dense_pass_kernel<DN_THREADS>;
+  // the final lnL pass (every mode) carves a whole tile out of the same dynamic shared memory (h->all_smem)
+  const size_t smem = std::max<size_t>(pick_stream_geom(h->geom_all, h->max_smem_optin - 2048, h->all_smem,
+                                                        pick_fn, DN_THREADS, &d.geom, &occ_pick), 1024);
+  if (occ_pick < 1) {
+    h->set_error("dense kernel does not fit on an SM");
+    return SS_ERR_CAPACITY;
+  }
   const int nK = d.Kp + SS_DN_TAIL;
   dense_init_kernel<<<(nK + 255) / 256, 256, 0, st>>>(d);
   h->launches++;

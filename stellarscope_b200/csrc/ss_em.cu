@@ -1646,17 +1646,16 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     sa.chunk_seg = h->stream_chunk_seg;
     sa.chunk_j0 = h->stream_chunk_j0;
     sa.n_chunks = h->n_stream_chunks;
-    sa.geom = make_stream_geom(h->geom_stream, h->max_smem_optin - 2048);
     SS_CUDA_CHECK(h, cudaMemsetAsync(h->stream_ctl, 0, 4 * sizeof(int), sx));
-    const size_t smem = std::max(h->stream_smem, stream_smem_bytes(sa.geom));
     void* fn = lnl ? (void*)em_stream_kernel<STREAM_THREADS, true> : (void*)em_stream_kernel<STREAM_THREADS, false>;
-    SS_CUDA_CHECK(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    SS_CUDA_CHECK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, STREAM_THREADS, smem));
+    const size_t smem = pick_stream_geom(h->geom_stream, h->max_smem_optin - 2048, lnl ? h->stream_smem : 0, fn, STREAM_THREADS,
+                                         &sa.geom, &occ);
     if (occ < 1) {
       h->set_error("streaming kernel does not fit on an SM");
       return SS_ERR_CAPACITY;
     }
+    SS_CUDA_CHECK(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = std::min(h->n_stream_tiles, occ * h->num_sms);
     a.tile_list = h->stream_tiles;
     a.n_list = h->n_stream_tiles;

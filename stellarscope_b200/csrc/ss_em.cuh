@@ -244,6 +244,8 @@ struct StreamGeom {
   int nbuf;             // 2: double buffered, 1: the largest tile leaves no room for a second buffer
   int nval;             // column-major scratch arrays: one per buffer when two CTAs still share an SM with that
                         // (no end-of-tile barrier among the consumers), else one (and the barrier)
+  int nxs;              // tile-local x arrays: one per buffer, or ONE when only that keeps two CTAs on an SM (the
+                        // producer then gathers the next tile's x after the consumers have left the current tile)
 };
 constexpr int STREAM_HDR_BYTES = 256;   // the tile header (HDR_WORDS * 8 = 192 B) travels with the tile
 constexpr int STREAM_DC_INTS = 24;      // lane-group boundaries of a tile (derived by the producer)
@@ -255,20 +257,35 @@ __host__ __device__ inline size_t stream_buf_bytes(const StreamGeom& g) {
 // per buffer: tile arrays + tile-local x + the column-major scratch (a scratch per buffer lets a warp start the next
 // tile's row phase while slower warps are still in this tile's column phase: ONE consumer barrier per tile)
 __host__ __device__ inline size_t stream_smem_bytes(const StreamGeom& g) {
-  return (size_t)g.nbuf * (stream_buf_bytes(g) + 8 * (size_t)g.pc) + (size_t)g.nval * 8 * ((size_t)g.pe + 8) + 128;
+  return (size_t)g.nbuf * stream_buf_bytes(g) + (size_t)g.nxs * 8 * (size_t)g.pc + (size_t)g.nval * 8 * ((size_t)g.pe + 8) + 128;
 }
 
-// double buffered when two buffers + scratch fit `limit` bytes of shared memory
-inline StreamGeom make_stream_geom(const int* gm, size_t limit) {
+// Shared-memory configuration of a streaming kernel `fn` (CTA of `threads`) for tiles of geometry gm: the richest
+// one that still lets TWO CTAs share an SM (asked of the occupancy calculator, not estimated: the kernels' static
+// shared memory and the per-CTA reservation count) -- two scratch arrays + two x arrays, then one scratch, then one x
+// array as well; if no configuration reaches two CTAs, the richest that fits one.  `floor_smem`: other users of the
+// dynamic shared memory in the same kernel (likelihood pass).  Returns the dynamic shared memory to launch with.
+inline size_t pick_stream_geom(const int* gm, size_t limit, size_t floor_smem, const void* fn, int threads, StreamGeom* out,
+                               int* occ_out) {
+  static const int cand[4][3] = {{2, 2, 2}, {2, 1, 2}, {2, 1, 1}, {1, 1, 1}};      // nbuf, nval, nxs
   StreamGeom g;
   g.pe = gm[0]; g.pr = gm[1]; g.pc = gm[2]; g.pj = gm[3];
-  g.nbuf = 2;
-  g.nval = 2;
-  // two CTAs per SM (228 KB, 1 KB reserved per CTA, ~4 KB of static shared memory each) is worth more than the
-  // barrier the second scratch saves
-  if (stream_smem_bytes(g) > (size_t)109 * 1024) g.nval = 1;
-  if (stream_smem_bytes(g) > limit) g.nbuf = 1;
-  return g;
+  StreamGeom best = g;
+  size_t best_smem = 0;
+  int best_occ = 0;
+  for (int pass = 0; pass < 2 && best_occ == 0; ++pass)          // pass 0: two CTAs per SM; pass 1: anything that fits
+    for (int c = 0; c < 4; ++c) {
+      g.nbuf = cand[c][0]; g.nval = cand[c][1]; g.nxs = cand[c][2];
+      const size_t smem = stream_smem_bytes(g) > floor_smem ? stream_smem_bytes(g) : floor_smem;
+      if (smem > limit) continue;
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) continue;
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem) != cudaSuccess) continue;
+      if (occ >= (pass == 0 ? 2 : 1)) { best = g; best_smem = smem; best_occ = occ; break; }
+    }
+  *out = best;
+  *occ_out = best_occ;
+  return best_smem;
 }
 
 struct StreamBuf {
@@ -525,7 +542,8 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
   const int nbuf = g.nbuf;
   const int nval = g.nbuf == 2 ? g.nval : 1;
   double* val0 = reinterpret_cast<double*>(dsm + (size_t)nbuf * bb);           // nval scratch arrays of pe + 8
-  double* xs0 = val0 + (size_t)g.nval * (g.pe + 8);                            // nbuf tile-local x arrays of pc
+  double* xs0 = val0 + (size_t)g.nval * (g.pe + 8);                            // nxs tile-local x arrays of pc
+  const int nxs = g.nxs;
   uint32_t n = n_use;
   // ---- active items of this CTA (all threads): items[k] = ordinal j of the k-th active item blockIdx + j * gridDim ----
   const int n_mine = (int)blockIdx.x < n_items ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -601,8 +619,13 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
       }
       if (M < 0) i = skip_done(i + gridDim.x);                        // overlaps the flight of the copies
       mbar_wait(&pipe->mapf[slot], kk & 1u);                          // the column map is in; the big arrays still fly
+      if (nxs == 1 && nbuf == 2 && nk >= 1) {
+        // one x array for both buffers: the consumers must have left the PREVIOUS tile (use nk - 1, other buffer)
+        const uint32_t np_ = nk - 1;
+        mbar_wait(&pipe->empty[(int)(np_ & 1u)], (np_ >> 1) & 1u);
+      }
       // tile-local x: 8 loads in flight per lane
-      double* xs = xs0 + (size_t)slot * g.pc;
+      double* xs = xs0 + (size_t)(nxs == 2 ? slot : 0) * g.pc;
       for (int c0 = 0; c0 < v.ncol; c0 += 256) {
         double xv[8];
 #pragma unroll
@@ -647,7 +670,7 @@ __device__ __forceinline__ void lane_stream_pass(const Layout& L, const int* __r
       }
       const StreamBuf b = carve_stream(dsm + (size_t)slot * bb, g);
       const TileView v = load_tile_view(b.hdr, 0);                   // the header arrived with the tile
-      lane_tile_compute<CONS, FR, FC>(v, b, T, xs0 + (size_t)slot * g.pc, val0 + (size_t)(nval == 2 ? slot : 0) * (g.pe + 8),
+      lane_tile_compute<CONS, FR, FC>(v, b, T, xs0 + (size_t)(nxs == 2 ? slot : 0) * g.pc, val0 + (size_t)(nval == 2 ? slot : 0) * (g.pe + 8),
                                       pipe->dc[slot]);
       if (nval != 2) consumer_bar<CONS>();                           // one scratch: everybody has left the column phase
       // this warp is done with the buffer (tile arrays, x, scratch); the producer refills it when all warps are.

@@ -163,3 +163,41 @@ def test_streamed_models_2M_alignments_vs_oracle(mode):
     _assert_counts(gpu, exact, tol)
     assert gpu.sum() > 0.5 * d.N
     tl.close()
+
+
+def test_rank_local_rows_equal_the_full_fit():
+    """A rank of a sharded run holds only its rows (``row_ids``): the rows are cut out of the host matrix while they
+    are staged for the upload (``Engine.set_matrix_rows`` -- at this size through the pinned ring with the chunked
+    gather).  The models fitted from the cut equal the same models of the full fit, the device matrix equals the
+    host-side cut, and the rank-local reassignment matrix has the global shape with the other rows empty."""
+    import scipy.sparse as sp
+    from stellarscope_b200 import hostutil, model, synth
+    d = synth.generate(n_cells=3000, n_alignments=20_000_000, n_loci=28_000, seed=11)
+    st, opts = _st_opts(d, 'individual')
+    full, pool = model._fit_pooling_model(st, opts)
+    it_full = np.array([pool.models_info[s].n_iterations for s in range(d.n_cells)])
+    lnl_full = np.array([pool.models_info[s].final_lnl for s in range(d.n_cells)])
+    full.close()
+    mine = np.arange(1, d.n_cells, 2)                                   # "this rank's" cells: every second one
+    local_id = np.full(d.n_cells, -1, dtype=np.int32)
+    local_id[mine] = np.arange(len(mine), dtype=np.int32)
+    rows = np.flatnonzero(local_id[d.row_cell] >= 0).astype(np.int64)
+    m = sp.csr_matrix((d.scores, d.indices, d.indptr), shape=(d.N, d.K))
+    tl = model.TelescopeLikelihood(m, opts, row_segment=local_id[d.row_cell[rows]], n_segments=len(mine), row_ids=rows)
+    assert tl._engine.N == len(rows) and tl.N == d.N
+    ptr, idx, dat = hostutil.gather_rows(d.indptr, d.indices, d.scores, rows)
+    assert idx.nbytes > (32 << 20)                                       # the chunked ring route was taken
+    k = tl._engine._keep
+    assert np.array_equal(k['row_ptr'].cpu().numpy(), ptr.astype(np.int32))
+    assert np.array_equal(k['col_idx'].cpu().numpy(), idx)
+    assert np.array_equal(k['score'].cpu().numpy().view(np.uint16), dat)
+    infos = tl.fit_segments()
+    assert np.array_equal(np.array([infos[i].n_iterations for i in range(len(mine))]), it_full[mine])
+    assert np.allclose(np.array([infos[i].final_lnl for i in range(len(mine))]), lnl_full[mine], rtol=1e-12, atol=0)
+    mat, rinfo = tl.reassign('best_exclude')
+    assert mat.shape == (d.N, d.K)
+    lens = np.diff(mat.indptr)
+    other = np.ones(d.N, dtype=bool)
+    other[rows] = False
+    assert lens[other].sum() == 0 and lens[rows].sum() == rinfo.assigned
+    tl.close()
