@@ -732,6 +732,15 @@ def run_ours(args):
                                'bandwidth per iteration',
                           binding_resource='shared-memory pipe / issue slots for lane + cluster kernels (on-chip '
                                            'resident), HBM + L2 for the streaming kernel',
+                          ncu_utilisation=dict(
+                              source='profiles/r2i_cfg5_x0.1_em_ncu.csv, profiles/r2h_stream_final_cfg4_ncu.csv (ncu --set full; '
+                                     'percent of peak sustained)',
+                              em_clane_kernel=dict(share_of_em_time_cfg5=0.71, issue_slots='25-28', shared_memory_pipe='21-32',
+                                                   registers=128, warps_per_sm=16),
+                              em_lane_kernel=dict(share_of_em_time_cfg5=0.10, issue_slots='31-45', shared_memory_pipe='44-57',
+                                                  registers=128, warps_per_sm='12-16 (32 for the 1024-thread class)'),
+                              em_stream_kernel=dict(share_of_em_time_cfg5=0.19, issue_slots=55, shared_memory_pipe=51,
+                                                    dram_pct_of_measured_peak=38.8, registers=64, warps_per_sm=32)),
                           peak_source=peak_src, kernel_ms=em_max, algorithmic_bytes=alg_all,
                           lane_bytes=lane_all, cluster_bytes=clu_all, stream_bytes=str_all),
             parity_sample=dict(cells=int(par_cells), max_rel_pi=float(pmax.item()), counts_equal=bool(pmin[0].item() >= 1),

@@ -392,12 +392,13 @@ def _em_wrapper(tl: TelescopeLikelihood):
     return tl.z, tl.fitinfo
 
 
-def pooling_row_segments(st, opts):
+def pooling_row_segments(st, opts, collective=False):
     """Row -> model map of a pooling mode (model.py:701-743).  Returns
     ``(row_segment int32[N], keys)`` where ``keys[i]`` is the key of model i in
     ``PoolInfo.models_info`` (model.py:766, 791).  The reference's containers
     (``bcode_ridx_map``: barcode -> set of row ids) are walked by the C helper
-    ``csrc/ss_hostutil.c``."""
+    ``csrc/ss_hostutil.c``.  ``collective``: all ranks of the default process group make this call together (passes
+    over per-row arrays may then be done in 1/world slices and combined)."""
     from . import hostutil
     N = st.shape[0]
     if opts.pooling_mode == 'pseudobulk':
@@ -406,7 +407,7 @@ def pooling_row_segments(st, opts):
         from . import checkpoint
         table = checkpoint.row_table(st)
         if table is not None:
-            return _row_segments_from_table(st, opts, table)
+            return _row_segments_from_table(st, opts, table, collective)
     seg = np.full(N, -1, dtype=np.int32)
     groups, ids = [], []
     i = 0
@@ -442,14 +443,24 @@ def pooling_row_segments(st, opts):
     return seg, list(range(i))
 
 
-def _row_segments_from_table(st, opts, table):
+def _row_segments_from_table(st, opts, table, collective=False):
     """``pooling_row_segments`` for an object loaded from a side-car checkpoint (``checkpoint.RowTable``): the
     barcode code of every row is already an array, no container is walked."""
     code = table.row_bcode
     nb = len(table.bcodes)
-    all_coded = len(code) == 0 or int(code.min()) >= 0            # every row belongs to a barcode (the usual case)
     from . import hostutil
-    counts = hostutil.group_sizes(code, nb)
+    world, rank = _dist_info() if collective else (1, 0)
+    if world > 1:
+        # every rank looks at 1/world of the rows; the sums (and the "a row without a barcode exists" flag) are combined
+        from . import parallel
+        n = len(code)
+        part = code[n * rank // world: n * (rank + 1) // world]
+        loc = np.concatenate([hostutil.group_sizes(part, nb), [int(len(part) > 0 and int(part.min()) < 0)]])
+        tot = parallel.allreduce_sum_host(loc.astype(np.int64))
+        counts, all_coded = tot[:nb], int(tot[nb]) == 0
+    else:
+        all_coded = len(code) == 0 or int(code.min()) >= 0        # every row belongs to a barcode (the usual case)
+        counts = hostutil.group_sizes(code, nb)
     if opts.pooling_mode == 'individual':
         has = counts > 0
         if all_coded and has.all():
@@ -558,7 +569,7 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
         # simply not fitted here
         from . import parallel
         _t = [time.perf_counter()]
-        row_segment, keys = pooling_row_segments(st, opts)
+        row_segment, keys = pooling_row_segments(st, opts, collective=True)
         _t.append(time.perf_counter())
         m = fullmat if scipy.sparse.isspmatrix_csr(fullmat) else scipy.sparse.csr_matrix(fullmat)
         # a model much larger than a rank's fair share (a dominant cell type on 8 GPUs) cannot be balanced by packing
