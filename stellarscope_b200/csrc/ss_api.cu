@@ -48,10 +48,11 @@ int ss_create(int device, ss_handle_t* out) {
     const int v = atoi(e);
     if (v >= 1 && v <= STREAM_SEG_TILES) h->small_tile_thr = v;
   }
-  if (const char* e = getenv("SS_CLANE_THREADS")) {
+  if (const char* e = getenv("SS_CLUSTER_TILE")) {
     const int v = atoi(e);
-    if (v == 256 || v == 512) h->clane_threads = v;
+    if (v >= 512 && v <= E_HARD) h->cluster_tile = v;
   }
+  if (const char* e = getenv("SS_CLANE_LIGHT")) h->clane_light = atoi(e) != 0;
   *out = h;
   return SS_OK;
 }
@@ -93,8 +94,8 @@ const char* ss_last_error(ss_handle_t h) { return h ? h->err.c_str() : "null han
 int ss_layout_build(ss_handle_t h, void* stream, int32_t n_rows, int32_t n_cols, int64_t nnz, const int32_t* row_ptr,
                     const int32_t* col_idx, const uint16_t* score, const int32_t* row_segment, int32_t n_segments) {
   SS_REQUIRE_HANDLE(h);
-  if (n_rows < 0 || n_cols <= 0 || nnz < 0 || n_segments < 0 || !row_ptr || !row_segment ||
-      (nnz > 0 && (!col_idx || !score))) {
+  if (n_rows < 0 || n_cols <= 0 || nnz < 0 || n_segments < 0 || !row_ptr || (n_rows > 0 && !row_segment) ||
+      (nnz > 0 && (!col_idx || !score))) {          // n_rows == 0: a rank of a sharded run without rows of its own
     h->set_error("ss_layout_build: bad argument");
     return SS_ERR_ARG;
   }

@@ -151,20 +151,27 @@ __global__ void key_to_seg_kernel(int n, const unsigned long long* __restrict__ 
   if (i < n) seg[i] = (int)(key[i] >> 32);
 }
 
-// rows of a segment are cut into tiles every `chunk` alignments; segments that will be streamed
-// (more than STREAM_SEG_TILES large tiles) use the small tile size
-__host__ __device__ inline int seg_chunk(long long a_amb, int chunk_big, int chunk_small, int thr) {
-  return a_amb > (long long)thr * chunk_big ? chunk_small : chunk_big;
+// rows of a segment are cut into tiles every `chunk` alignments.  Segments that will be streamed (more than
+// STREAM_SEG_TILES large tiles) use the small tile size; a segment that fits ONE large tile is one tile; the
+// segments in between (2..8 tiles: one thread-block cluster per segment) are cut into EQUAL tiles of about `target`
+// alignments -- all CTAs of a cluster wait for the slowest one at the cluster barrier of every iteration, so a
+// 5000-alignment cell runs as 2 x 2500 rather than 4080 + 920 (layout_host.py: seg_chunk)
+__host__ __device__ inline int seg_chunk(long long a_amb, int chunk_big, int chunk_small, int thr, int target) {
+  if (a_amb > (long long)thr * chunk_big) return chunk_small;
+  if (a_amb <= chunk_big) return chunk_big;
+  long long nt = (a_amb + target - 1) / target;
+  if (nt > thr) nt = thr;                      // a_amb <= thr * chunk_big: the tiles still fit
+  return (int)((a_amb + nt - 1) / nt);
 }
 
 // per segment: first sorted ambiguous row, first entry offset, number of tiles
 __global__ void seg_tiles_kernel(int n_seg, int n_amb, const long long* __restrict__ seg_row0 /* exclusive scan of namb */,
                                  const int* __restrict__ seg_namb, const long long* __restrict__ pre /* n_amb+1 */,
-                                 int chunk_big, int chunk_small, int small_thr, const long long* __restrict__ seg_Aamb,
+                                 int chunk_big, int chunk_small, int small_thr, int target, const long long* __restrict__ seg_Aamb,
                                  long long* __restrict__ seg_ntiles64, long long* __restrict__ seg_ent0) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_seg) return;
-  const int chunk = seg_chunk(seg_Aamb[s], chunk_big, chunk_small, small_thr);
+  const int chunk = seg_chunk(seg_Aamb[s], chunk_big, chunk_small, small_thr, target);
   const long long r0 = seg_row0[s];
   const int n = seg_namb[s];
   const long long e0 = pre[min(r0, (long long)n_amb)];
@@ -180,12 +187,12 @@ __global__ void seg_tiles_kernel(int n_seg, int n_amb, const long long* __restri
 // tile of every sorted ambiguous row and the first row of every tile
 __global__ void row_tile_kernel(int n_amb, const int* __restrict__ aseg, const long long* __restrict__ pre,
                                 const long long* __restrict__ seg_ent0, const long long* __restrict__ seg_tile0,
-                                int chunk_big, int chunk_small, int small_thr, const long long* __restrict__ seg_Aamb,
+                                int chunk_big, int chunk_small, int small_thr, int target, const long long* __restrict__ seg_Aamb,
                                 int* __restrict__ rtile) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_amb) return;
   const int s = aseg[k];
-  const int chunk = seg_chunk(seg_Aamb[s], chunk_big, chunk_small, small_thr);
+  const int chunk = seg_chunk(seg_Aamb[s], chunk_big, chunk_small, small_thr, target);
   rtile[k] = (int)(seg_tile0[s] + (pre[k] - seg_ent0[s]) / chunk);
 }
 __global__ void tile_heads_kernel(int n_amb, int n_tiles, const int* __restrict__ rtile, int* __restrict__ tile_row0) {
@@ -794,7 +801,7 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
     widen_int_kernel<<<grid_for(S), 256, 0, st>>>(S, L.seg_namb, seg_namb64);
     h->launches++;
     CUB_CALL(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, seg_namb64, seg_row0, S, st));
-    seg_tiles_kernel<<<grid_for(S), 256, 0, st>>>(S, n_amb, seg_row0, L.seg_namb, pre, chunk, chunk_small, h->small_tile_thr, L.seg_Aamb,
+    seg_tiles_kernel<<<grid_for(S), 256, 0, st>>>(S, n_amb, seg_row0, L.seg_namb, pre, chunk, chunk_small, h->small_tile_thr, std::min(chunk, h->cluster_tile), L.seg_Aamb,
                                                   seg_ntiles64, seg_ent0);
     h->launches++;
     CUB_CALL(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, seg_ntiles64, seg_tile0_64, S, st));
@@ -809,7 +816,7 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
     SS_CUDA_CHECK(h, tmp.get(&rtile, (size_t)n_amb));
     SS_CUDA_CHECK(h, tmp.get(&tile_row0, (size_t)n_tiles + 1));
     row_tile_kernel<<<grid_for(n_amb), 256, 0, st>>>(n_amb, aseg, pre, seg_ent0, seg_tile0_64, chunk, chunk_small, h->small_tile_thr,
-                                                     L.seg_Aamb, rtile);
+                                                     std::min(chunk, h->cluster_tile), L.seg_Aamb, rtile);
     tile_heads_kernel<<<grid_for(n_amb), 256, 0, st>>>(n_amb, n_tiles, rtile, tile_row0);
     h->launches += 2;
   }

@@ -19,6 +19,10 @@ constexpr int E_HARD = 4096;     // hard cap on alignments per tile (worst case 
 constexpr int E_STREAM = SS_E_STREAM;   // tile size of segments that are streamed (more than STREAM_SEG_TILES large tiles):
                                  // small tiles let 2-3 CTAs share an SM, so one CTA's loads / atomics overlap another's compute
 constexpr int STREAM_SEG_TILES = 8;
+#ifndef SS_E_CLUSTER
+#define SS_E_CLUSTER 3072
+#endif
+constexpr int E_CLUSTER = SS_E_CLUSTER; // target tile size of segments of 2..STREAM_SEG_TILES tiles (thread-block clusters): equal tiles
 constexpr int ALIGN_ELEMS = 8;   // per-tile slices start at multiples of 8 elements (16 B for u16)
 constexpr int LONG_COL = 32;     // tile columns with more rows than this are reduced by a warp
 constexpr int HDR_WORDS = 24;    // int64 words per tile header

@@ -256,8 +256,8 @@ struct TmpPool {
 int count_cells(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, int n_cells, const int* row_ptr, const int* col_idx,
                 const uint8_t* flag, const int* nbest, const int* row_cell, long long cap, long long* out_ptr, int* out_col,
                 int* out_cnt, double* out_val, long long* n_out) {
-  if (!row_ptr || !col_idx || !flag || !row_cell || !out_ptr || !n_out || n_cells < 0 || n_cols <= 0 ||
-      (out_val && out_cnt)) {
+  if (!out_ptr || !n_out || n_cells < 0 || n_cols <= 0 || (out_val && out_cnt) ||
+      (n_rows > 0 && (!row_ptr || !col_idx || !flag || !row_cell))) {
     h->set_error("ss_count_cells: bad argument");
     return SS_ERR_ARG;
   }

@@ -606,50 +606,86 @@ __global__ void __maxnreg__(MAXREG) em_lane_kernel(EmArgs a) {
 }
 
 // ---------------------------------------------------------------------------
-// cluster lane kernel: one thread-block CLUSTER per segment of 2..16 tiles (a cell with more than
+// cluster lane kernel: one thread-block CLUSTER per segment of 2..8 tiles (a cell with more than
 // one tile of alignments).  Every CTA keeps the rows of its tile in registers like the lane kernel
-// (FR row fragments per lane); per iteration
+// (FR row fragments per lane).  There is NO cluster-wide barrier inside the iteration: what the CTAs
+// exchange -- the partial sums of the columns several tiles hold, and one |delta pi| partial per
+// CTA -- is PUSHED into the consumers' shared memory with st.async, which signals the consumer's
+// mbarrier (complete_tx); a CTA waits only for the bytes it expects.  (A cluster barrier per
+// iteration costs MEMBAR.ALL.GPU + the barrier + CCTL.IVALL -- the L1 invalidation turns every
+// register spill into an L2 round trip -- and an exchange through L2 one more round trip; ncu /
+// clock64 profile: half of an iteration.)  Per iteration
 //   phase A   local rows: r_i = sum_j Q_ij x_j, scatter Q_ij w_i / r_i into the column-major scratch
-//   phase B1  local partial column sums (lane fragments, xor-shuffle groups) -> part[parity][c]
-//   cluster barrier                                   <- the ONE cluster-wide barrier of an iteration
-//   phase B2  every CTA adds, for each of ITS columns, the partial sums of all tiles that contain the
-//             column straight from its peers' shared memory (DSMEM loads, fixed tile order, so all
-//             CTAs that hold a column compute bit-identical theta', pi', x') -- no owner, no second
-//             exchange.  |delta pi| is summed over the columns a CTA is the first holder of and
-//             PUSHED into every peer's shared memory.
-// The cluster-wide |delta pi| of iteration k is therefore complete one barrier later: convergence of
-// iteration k is detected after the barrier of iteration k+1 (whose phase A / B1 ran speculatively
-// and is discarded); x of iterations k-1 and k are still in the ping-pong buffers, theta of
-// iteration k in `th`.  No global memory traffic and no atomics inside the loop.
+//   phase B   column sums (lane fragments, xor-shuffle groups).  A column held by this tile alone
+//             (the common case: the builder orders the rows by locus, so tiles overlap in few
+//             columns) is finished right there by its leader lane: theta', pi', x' = pi' theta',
+//             |delta pi|.  The partial sum of a shared column is pushed to the other holders.
+//   wait      for the mbarrier of this pass: the partial sums of my shared columns from their other
+//             holders and the |delta pi| partials of the previous iteration have arrived
+//   shared    every holder of a shared column adds the partial sums in tile order (bit-identical
+//             theta', pi', x' in all holders -- no owner, no second exchange); |delta pi| is summed
+//             by the first holder.
+// The cluster-wide |delta pi| of iteration k is therefore complete one pass later: convergence of
+// iteration k is detected in pass k+1 (whose phases A / B ran speculatively and are discarded: x is
+// triple-buffered so that x_{k-1} and x_k survive); one more pass repeats iteration k from x_{k-1}
+// -- the same sums in the same order -- and publishes pi and theta.  No global memory traffic and
+// no atomics inside the loop.  Buffers and mbarriers alternate with the pass parity; a CTA cannot
+// run two passes ahead of a peer because it needs the peer's |delta pi| partial of the pass before.
 // (The likelihood-convergence mode keeps the three-barrier kernel below.)
 // ---------------------------------------------------------------------------
 struct ClusterArgs {
   const int* segs;
   const uint16_t* xref;
   const long long* seg_xref_off;
-  double* part;                    // [2][part_total] partial column sums of the cluster tiles (global, L2)
-  const long long* tile_part_off;  // offset of a tile's columns in `part`
-  long long part_total;
 };
 
-#ifndef SS_CLANE_THREADS
-#define SS_CLANE_THREADS 512
-#define SS_CLANE_FR 4
-#define SS_CLANE_FC 6
-#define SS_CLANE_MAXREG 128
-#endif
 constexpr int SS_MAX_CLUSTER_TILES = 8;
-constexpr int CLANE_THREADS = SS_CLANE_THREADS;
-constexpr int CLANE_FR = SS_CLANE_FR, CLANE_FC = SS_CLANE_FC;
 
-// THREADS: 512 (one CTA per SM, tiles of up to E_HARD alignments) or 256 (experiment: with SS_SMALL_TILE_THR=1 the
-// cluster segments are cut into E_STREAM tiles, two CTAs of different clusters share an SM and one cluster's barrier
-// / L2 exchange overlaps the other's phase A / B)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
+  return r;
+}
+// remote store of 8 bytes into a peer CTA's shared memory; completes 8 bytes on the peer's mbarrier
+__device__ __forceinline__ void st_async_f64(uint32_t raddr, double v, uint32_t rmbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr),
+               "l"(__double_as_longlong(v)), "r"(rmbar)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t ld_dsmem_u16(uint32_t raddr) {
+  uint16_t v;
+  asm volatile("ld.shared::cluster.u16 %0, [%1];" : "=h"(v) : "r"(raddr));
+  return v;
+}
+// wait for a phase of an mbarrier that peers complete with remote stores (st.async lands in THIS CTA's shared memory
+// before its complete_tx, so the default cta-scope acquire is what CUTLASS' cluster barriers use too; a cluster-scope
+// acquire makes ptxas add CCTL.IVALL -- an L1 invalidation per pass); a lost peer turns into a trap instead of a
+// hung GPU
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (unsigned long long spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spin > (1ull << 22)) __trap();
+  }
+}
+
+// Two instantiations (ss_handle.h): heavy <512, 4, 6, 128> -- one CTA owns its SM -- and light <512, 2, 3, 64> for
+// clusters whose tiles need at most 2 row-fragment slots per lane and at most half an SM's shared memory: two CTAs
+// (of different clusters) share an SM
 template <int THREADS, int FR_, int FC_, int MAXREG>
 __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double s_red[64];
-  __shared__ double s_dall[2][16];        // [parity][rank]: |delta pi| partial of every CTA of the cluster (pushed)
   constexpr int FR = FR_, FC = FC_;
   constexpr int NW = THREADS / 32;
   const unsigned full = 0xffffffffu;
@@ -662,23 +698,32 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
   const int t = t0 + rank;
   const long long* __restrict__ hd = a.L.tile_hdr + (long long)HDR_WORDS * t;
   const TileView v = load_tile_view(a.L.tile_hdr, t);
-  // the same carve in every CTA of the cluster: sizes of the segment's largest tile
-  int pemax = 0, pcmax = 0;
-  __shared__ long long part_off[SS_MAX_CLUSTER_TILES];
-  if (threadIdx.x < SS_MAX_CLUSTER_TILES) part_off[threadIdx.x] = (int)threadIdx.x < nt ? ca.tile_part_off[t0 + threadIdx.x] : 0;
+  // the same carve in every CTA of the cluster: sizes of the segment's largest tile; xmax bounds the partial sums a
+  // tile can receive per pass (sum over the tiles' columns - columns of the segment = sum_c (holders(c) - 1))
+  int pemax = 0, pcmax = 0, xsum = 0;
   for (int k = 0; k < nt; ++k) {
     const long long* hk = a.L.tile_hdr + (long long)HDR_WORDS * (t0 + k);
     pemax = max(pemax, pad8((int)hk[H_NENT]));
     pcmax = max(pcmax, pad8((int)hk[H_NCOL] + 1));
+    xsum += (int)hk[H_NCOL];
   }
-  double* pt = reinterpret_cast<double*>(dsm);         // x ping
-  double* pt2 = pt + pcmax;                            // x pong
-  double* spi = pt2 + pcmax;                           // pi
-  double* sth = spi + pcmax;                           // theta of the last update
-  double* spart = sth + pcmax;                         // this tile's partial column sums (the peers read the copy in L2)
-  double* val = spart + pcmax;                         // pemax + 8 (slot pe: scratch of the padding entries)
-  uint16_t* xr = reinterpret_cast<uint16_t*>(val + pemax + 8);   // [ncol][nt] local column of the same locus in tile k
-  uint8_t* shr = reinterpret_cast<uint8_t*>(xr + (size_t)nt * pcmax);   // [ncol] another tile holds the column too
+  const int xmax = pad8(xsum - a.L.seg_ncol[seg] + 1);
+  // x of three consecutive iterations (rotating: the convergence of iteration k is known one pass late, when the
+  // column lanes have already written x_{k+1}; x_{k-1} and x_k must survive), pi, the prior pseudo counts of the
+  // columns, the column-major scratch, the receive buffers of the two pass parities
+  double* xb0 = reinterpret_cast<double*>(dsm);
+  double* xb1 = xb0 + pcmax;
+  double* xb2 = xb1 + pcmax;
+  double* spi = xb2 + pcmax;                           // pi
+  double* sps0 = spi + pcmax;                          // pisum0 of the column (unique rows, model.py:191)
+  double* val = sps0 + pcmax;                          // pemax + 8 (slot pe: scratch of the padding entries)
+  double* rpart = val + pemax + 8;                     // [2][xmax] partial sums of my shared columns from their other holders
+  uint16_t* xr = reinterpret_cast<uint16_t*>(rpart + 2 * xmax);   // [ncol][nt]: see below
+  uint16_t* shl = xr + (size_t)nt * pcmax;             // the shared columns, ascending (bit 15: an earlier tile holds it too)
+  uint16_t* rb = shl + pcmax;                          // [ncol] first receive slot of a shared column
+  uint8_t* shr = reinterpret_cast<uint8_t*>(rb + pcmax);   // [ncol] another tile holds the column too
+  __shared__ __align__(8) uint64_t s_mbar[2];
+  __shared__ double s_dall[2][SS_MAX_CLUSTER_TILES];   // [parity][rank]: |delta pi| partial of every CTA of the cluster (pushed)
 
   const double* __restrict__ gq = a.L.e_q + v.eo;
   const uint32_t* __restrict__ gidx = a.L.e_idx + v.eo;
@@ -690,31 +735,95 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
   const int* __restrict__ scol = a.L.c_scol + v.co;
   const int col0 = a.L.seg_col0[seg];
   const uint16_t* __restrict__ gxref = ca.xref + ca.seg_xref_off[seg];
+  const bool has_uniq = a.L.seg_nuniq[seg] > 0;
 
   const double invK = 1.0 / (double)a.P.K;
   for (int c = tid; c < v.ncol; c += THREADS) {
     spi[c] = invK;
-    pt[c] = invK * invK;
-    const long long j = scol[c] - col0;
-    bool sh = false;
-    for (int k = 0; k < nt; ++k) {
-      const uint16_t x = gxref[j * nt + k];
-      xr[c * nt + k] = x;
-      sh |= k != rank && x != 0xffffu;
+    xb0[c] = invK * invK;
+    sps0[c] = has_uniq ? ps0[c] : 0.0;
+  }
+  // The shared columns as a list in ascending order, and for each of them the first of its receive slots -- the other
+  // holders' partial sums arrive in consecutive slots, in tile order (ordered compaction chunk by chunk: a packed
+  // warp scan of (shared ? 1 : 0) | (other holders << 16)).  xr[c][k] = local index of column c in tile k (0xffff:
+  // tile k does not hold it) for now.
+  __shared__ int s_wcnt[NW + 1];
+  int n_sh = 0, n_recv = 0;
+  {
+    int run = 0;                                           // packed totals of the chunks before
+    for (int c0 = 0; c0 < v.ncol; c0 += THREADS) {
+      const int c = c0 + tid;
+      int others = 0;
+      bool not_first = false;
+      if (c < v.ncol) {
+        const long long j = scol[c] - col0;
+        for (int k = 0; k < nt; ++k) {
+          const uint16_t x = gxref[j * nt + k];
+          xr[c * nt + k] = x;
+          const bool held = x != 0xffffu;
+          others += (k != rank && held) ? 1 : 0;
+          not_first |= k < rank && held;
+        }
+        shr[c] = others > 0 ? 1 : 0;
+      }
+      const int mine = others > 0 ? (1 | (others << 16)) : 0;
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(full, incl, o);
+        if (lane >= o) incl += up;
+      }
+      if (lane == 31) s_wcnt[warp] = incl;
+      __syncthreads();
+      int base = run, tot = 0;
+      for (int w = 0; w < NW; ++w) {
+        const int cw = s_wcnt[w];
+        if (w < warp) base += cw;
+        tot += cw;
+      }
+      if (others > 0) {
+        const int at = base + incl - mine;                 // exclusive prefix: list position | first receive slot << 16
+        shl[at & 0xffff] = (uint16_t)(c | (not_first ? 0x8000 : 0));
+        rb[c] = (uint16_t)(at >> 16);
+      }
+      run += tot;
+      __syncthreads();
     }
-    shr[c] = sh ? 1 : 0;
+    n_sh = run & 0xffff;
+    n_recv = run >> 16;
   }
   if (tid == 0) {
-    pt[v.ncol] = 0.0;
-    pt2[v.ncol] = 0.0;
+    xb0[v.ncol] = 0.0;
+    xb1[v.ncol] = 0.0;
+    xb2[v.ncol] = 0.0;
+    mbar_init(&s_mbar[0], 1);
+    mbar_init(&s_mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < 32) { s_dall[0][tid & 15] = 0.0; s_dall[1][tid & 15] = 0.0; }
+  if (tid < 2 * SS_MAX_CLUSTER_TILES) (&s_dall[0][0])[tid] = 0.0;
+  __syncthreads();
+  cluster.sync();                              // every CTA's lists and mbarriers are in place
+  // xr[c][k] := the slot of tile k's receive buffer that takes MY partial sum of column c (0xfffe: k is this tile,
+  // 0xffff: tile k does not hold the column): tile k's first slot of the column (read from its shared memory) + the
+  // number of holders before me other than k
+  for (int i = tid; i < n_sh; i += THREADS) {
+    const int c = shl[i] & 0x7fff;
+    uint16_t* xc_ = xr + c * nt;
+    int before = 0;                                        // holders j < rank
+    for (int k = 0; k < rank; ++k) before += xc_[k] != 0xffffu ? 1 : 0;
+    for (int k = 0; k < nt; ++k) {
+      const unsigned ck = xc_[k];
+      if (k == rank) { xc_[k] = 0xfffeu; continue; }
+      if (ck == 0xffffu) continue;
+      const uint32_t rbk = ld_dsmem_u16(mapa_u32(smem_u32(rb + ck), (uint32_t)k));
+      xc_[k] = (uint16_t)(rbk + before - (k < rank ? 1 : 0));
+    }
+  }
   const double thpw = a.F.seg_thpw[seg], pipw = a.F.seg_pipw[seg];
   const double inv_thd = a.F.seg_inv_thd[seg], inv_pid = a.F.seg_inv_pid[seg];
   const double diff1_extra = a.F.seg_diff1_extra[seg];
   const double eps = a.P.eps;
   const int max_iter = a.P.max_iter;
-  const bool has_uniq = a.L.seg_nuniq[seg] > 0;
   double* diffs = a.F.seg_diffs + (long long)seg * max_iter;
 
   // ---- row fragments (as in the lane kernel) ----
@@ -802,13 +911,17 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
     gB[j] = __reduce_max_sync(full, cgj);
   }
   __syncthreads();
-  cluster.sync();                              // every CTA's shared memory is initialised
 
-  double* pt_cur = pt;
-  double* pt_nxt = pt2;
+  double* x_prev = xb2;                        // x_{it-2}
+  double* x_cur = xb0;                         // x_{it-1}: what the E-step of iteration `it` reads
+  double* x_nxt = xb1;                         // x_it
   unsigned char* const vb = reinterpret_cast<unsigned char*>(val);
-  int it = 0, fin = 0, par = 0;
+  const uint32_t rpart_s = smem_u32(rpart), mbar_s = smem_u32(&s_mbar[0]), dall_s = smem_u32(&s_dall[0][0]);
+  int it = 0, fin = 0, par = 0, xc = 0;
   bool conv = false;
+  bool final_pass = false;                     // the pass that repeats iteration `fin` to publish its parameters
+  bool dsum_sent = false;                      // the previous pass pushed |delta pi| partials (they complete on this pass's mbarrier)
+  double dsum = 0.0;
 #ifdef SS_CLANE_PROFILE
   long long tA = 0, tB1 = 0, tS = 0, tB2 = 0, tR = 0, c0, c1;
 #define SS_TICK(acc) c1 = clock64(); acc += c1 - c0; c0 = c1;
@@ -816,13 +929,50 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
 #else
 #define SS_TICK(acc)
 #endif
+  // new parameters of tile column c from its column sum `tot` (model.py:240-246).  Iterating: pi' and x' = pi' theta'
+  // go to shared memory, |delta pi| is added up (`count`: this CTA is the first holder of the column).  Final pass:
+  // pi' and theta' of iteration `fin` go to the segment's column table.
+  auto update_col = [&](int c, double tot, const double* x_in, bool count) {
+    const double T = x_in[c] * tot;
+    const double th = (T + thpw) * inv_thd;
+    const double pn = (sps0[c] + T + pipw) * inv_pid;
+    if (!final_pass) {
+      if (count) dsum += fabs(pn - spi[c]);
+      spi[c] = pn;
+      x_nxt[c] = pn * th;
+    } else if (count) {
+      const int slot = scol[c];
+      a.F.sc_pi[slot] = pn;
+      a.F.sc_theta[slot] = th;
+    }
+  };
   while (true) {
-    ++it;
-    double* const gpart = ca.part + (long long)(it & 1) * ca.part_total;      // this iteration's exchange buffer
-    double* const mypart = gpart + ca.tile_part_off[t];
-    if (it <= max_iter) {
+    if (!final_pass) ++it;
+    ++xc;
+    const int pp = xc & 1;                                        // parity of this pass: receive buffer and mbarrier
+    const bool work = final_pass || it <= max_iter;               // phases A / B run (not in the pass after max_iter)
+    if (tid == 0) {
+      // arm this pass's mbarrier: the partial sums of my shared columns + the |delta pi| partials of the pass before
+      const uint32_t bytes = (work ? 8u * (uint32_t)n_recv : 0u) + (dsum_sent ? 8u * (uint32_t)(nt - 1) : 0u);
+      if (bytes) mbar_expect_tx(&s_mbar[pp], bytes);
+      else mbar_arrive(&s_mbar[pp]);
+    }
+    // my partial sum of shared column c: parked like the others, and pushed to the other holders
+    auto push_col = [&](int c, double asum) {
+      const uint16_t* xc_ = xr + c * nt;
+#pragma unroll
+      for (int k = 0; k < SS_MAX_CLUSTER_TILES; ++k)
+        if (k < nt) {
+          const unsigned sl = xc_[k];
+          if (sl < 0xfffeu)
+            st_async_f64(mapa_u32(rpart_s + 8u * (uint32_t)(pp * xmax + (int)sl), (uint32_t)k), asum,
+                         mapa_u32(mbar_s + 8u * (uint32_t)pp, (uint32_t)k));
+        }
+    };
+    const double* const x_in = final_pass ? x_prev : x_cur;
+    if (work) {
       // ---- phase A ----
-      const unsigned char* const xb = reinterpret_cast<const unsigned char*>(pt_cur);
+      const unsigned char* const xb = reinterpret_cast<const unsigned char*>(x_in);
 #pragma unroll
       for (int j = 0; j < FR; ++j) {
         if (nA[j] > 0) {
@@ -848,7 +998,7 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
           double acc = 0.0;
           for (int p = 0; p < len; ++p) {
             const int e = (int)gjptr[p] + rr;
-            acc = fma(gq[e], pt_cur[gidx[e] & 0xffffu], acc);
+            acc = fma(gq[e], x_in[gidx[e] & 0xffffu], acc);
           }
           const double sc = acc > 0.0 ? gw[rr] * (1.0 / acc) : 0.0;
           for (int p = 0; p < len; ++p) {
@@ -859,12 +1009,13 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
       }
       __syncthreads();
       SS_TICK(tA)
-      // ---- phase B1: local partial column sums ----
+      // ---- phase B: column sums.  The sum is parked in the column's first scratch slot; a column other tiles hold
+      // too is pushed to them first, the others are finished by the thread that parked them ----
 #pragma unroll
       for (int j = 0; j < FC; ++j) {
         if (nB[j] > 0) {
           double asum = 0.0;
-          const unsigned char* const cp = vb + cb[j];
+          unsigned char* const cp = vb + cb[j];
           const int cnj = cm[j] & 15;
 #pragma unroll
           for (int k = 0; k < FRAG; ++k)
@@ -874,8 +1025,12 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
           if (gB[j] > 1) asum = group_xor_sum(asum, (cm[j] >> 4) & 63, gB[j]);
           const int c1 = cm[j] >> 12;
           if (c1 > 0) {
-            spart[c1 - 1] = asum;
-            if (shr[c1 - 1]) mypart[c1 - 1] = asum;       // only shared columns travel through L2
+            if (shr[c1 - 1]) {
+              *reinterpret_cast<double*>(cp) = asum;
+              push_col(c1 - 1, asum);
+            } else {
+              update_col(c1 - 1, asum, x_in, true);
+            }
           }
         }
       }
@@ -883,74 +1038,76 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
         const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
         const double asum = col_sum_warp(val, b, n, lane);
         if (lane == 0) {
-          spart[c] = asum;
-          if (shr[c]) mypart[c] = asum;
+          if (shr[c]) {
+            val[b] = asum;
+            push_col(c, asum);
+          } else {
+            update_col(c, asum, x_in, true);
+          }
         }
       }
       for (int c = c_ovf + tid; c < v.ncol; c += THREADS) {       // columns beyond the register lanes
         const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
         const double asum = col_sum_thread(val, b, n);
-        spart[c] = asum;
-        if (shr[c]) mypart[c] = asum;
+        if (shr[c]) {
+          val[b] = asum;
+          push_col(c, asum);
+        } else {
+          update_col(c, asum, x_in, true);
+        }
       }
     }
     SS_TICK(tB1)
-    cluster.sync();                                               // barrier #it
+    __syncthreads();                                              // the parked sums of the shared columns are visible
+    mbar_wait_cluster(&s_mbar[pp], (uint32_t)((xc - 1) >> 1) & 1u);
     SS_TICK(tS)
-    if (it > 1) {
-      // ---- decision for iteration it-1 (all CTAs add the pushed partials in rank order) ----
+    if (!final_pass && it > 1) {
+      // ---- decision for iteration it-1 (all CTAs add the partials in rank order) ----
       double diff = 0.0;
-      for (int r = 0; r < nt; ++r) diff += s_dall[(it - 1) & 1][r];
+      for (int r = 0; r < nt; ++r) diff += s_dall[pp][r];
       if (it - 1 == 1) diff += diff1_extra;
       if (rank == 0 && tid == 0) diffs[it - 2] = diff;
       conv = diff < eps;                                          // model.py:351
       if (conv || it - 1 >= max_iter) {
+        // iteration fin = it-1 is final: x_fin = x_cur, the E-step that counts read x_prev.  What this pass wrote
+        // (x_nxt, pi of the unshared columns) is discarded; one more pass repeats iteration fin from x_prev -- the
+        // same sums in the same order -- and publishes pi and theta
         fin = it - 1;
-        break;
+        final_pass = true;
+        dsum_sent = false;
+        continue;
       }
     }
-    // ---- phase B2: gather the partial sums of my columns from every tile, new parameters ----
-    double dsum = 0.0;
-    // a column held by this tile alone (the common case: the builder orders the rows by locus, so tiles
-    // overlap in few columns) needs nothing but its own partial sum; a shared column adds the partial
-    // sums of all its holders in tile order, read from L2
-    for (int c = tid; c < v.ncol; c += THREADS) {
-      double tot;
-      bool first = true;
-      if (!shr[c]) {
-        tot = spart[c];
-      } else {
-        // all peer loads of the column are issued together (one L2 round trip, ~900 cycles, instead of
-        // one per holder: the slowest thread sets the pace of the whole CTA); added in tile order
-        const uint16_t* xc = xr + c * nt;
-        double pk[SS_MAX_CLUSTER_TILES];
+    // ---- shared columns: my partial sum and the ones the other holders pushed, added in tile order ----
+    if (work) {
+      const double* const rp = rpart + pp * xmax;
+      for (int i = tid; i < n_sh; i += THREADS) {
+        const int c = shl[i] & 0x7fff;
+        const bool first = (shl[i] & 0x8000) == 0;                // no earlier tile holds this column
+        const uint16_t* xc_ = xr + c * nt;
+        int sl = rb[c];
+        double tot = 0.0;
 #pragma unroll
-        for (int k = 0; k < SS_MAX_CLUSTER_TILES; ++k) {
-          pk[k] = 0.0;
+        for (int k = 0; k < SS_MAX_CLUSTER_TILES; ++k)
           if (k < nt) {
-            const unsigned ck = xc[k];
-            if (ck != 0xffffu) {
-              pk[k] = k == rank ? spart[ck] : __ldcg(gpart + part_off[k] + ck);
-              if (k < rank) first = false;                        // an earlier tile holds this column too
-            }
+            const unsigned e = xc_[k];
+            if (e == 0xfffeu) tot += val[gcptr[c]];
+            else if (e != 0xffffu) tot += rp[sl++];
           }
-        }
-        tot = 0.0;
-#pragma unroll
-        for (int k = 0; k < SS_MAX_CLUSTER_TILES; ++k) tot += pk[k];     // fixed tile order
+        update_col(c, tot, x_in, first);
       }
-      const double T = pt_cur[c] * tot;
-      const double th = (T + thpw) * inv_thd;                     // model.py:240
-      const double pn = ((has_uniq ? ps0[c] : 0.0) + T + pipw) * inv_pid;   // model.py:243-244
-      if (first) dsum += fabs(pn - spi[c]);
-      spi[c] = pn;
-      sth[c] = th;
-      pt_nxt[c] = pn * th;
     }
     SS_TICK(tB2)
-    dsum = block_sum<THREADS>(dsum, s_red, par++);                // barrier: publishes pt_nxt
-    if (tid < nt) cluster.map_shared_rank(&s_dall[it & 1][rank], tid)[0] = dsum;   // push to every CTA
-    double* tmp = pt_cur; pt_cur = pt_nxt; pt_nxt = tmp;
+    if (final_pass) break;
+    dsum = block_sum<THREADS>(dsum, s_red, par++);                // barrier: publishes x_nxt
+    if (tid < nt) {                                               // |delta pi| partial to every CTA; it completes on the NEXT pass's mbarrier
+      const uint32_t off = 8u * (uint32_t)((pp ^ 1) * SS_MAX_CLUSTER_TILES + rank);
+      if (tid == rank) s_dall[pp ^ 1][rank] = dsum;
+      else st_async_f64(mapa_u32(dall_s + off, (uint32_t)tid), dsum, mapa_u32(mbar_s + 8u * (uint32_t)(pp ^ 1), (uint32_t)tid));
+    }
+    dsum_sent = true;
+    dsum = 0.0;
+    double* tmp = x_prev; x_prev = x_cur; x_cur = x_nxt; x_nxt = tmp;
     SS_TICK(tR)
   }
 #ifdef SS_CLANE_PROFILE
@@ -959,13 +1116,11 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
            nt, v.nent, v.ncol, it, tA / it, tB1 / it, tS / it, tB2 / it, tR / it);
 #endif
 #undef SS_TICK
-  // ---- publish: iteration `fin` is final.  pt_cur = x_fin, pt_nxt = x_{fin-1} (the last E-step that counts) ----
+  // ---- publish: iteration `fin` is final.  x_cur = x_fin, x_prev = x_{fin-1} (the last E-step that counts) ----
   for (int c = tid; c < v.ncol; c += THREADS) {
     const int slot = scol[c];
-    a.F.sc_pi[slot] = spi[c];
-    a.F.sc_theta[slot] = sth[c];
-    a.F.sc_ptprev[slot] = pt_nxt[c];
-    a.F.sc_ptfin[slot] = pt_cur[c];
+    a.F.sc_ptprev[slot] = x_prev[c];
+    a.F.sc_ptfin[slot] = x_cur[c];
   }
   // final lnL: z of the last E-step (x_{fin-1}), final parameters (model.py:368-370)
   double l = 0.0;
@@ -974,14 +1129,14 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
     double acc = 0.0;
     for (int p = 0; p < len; ++p) {
       const int e = (int)gjptr[p] + r;
-      acc = fma(gq[e], pt_nxt[gidx[e] & 0xffffu], acc);
+      acc = fma(gq[e], x_prev[gidx[e] & 0xffffu], acc);
     }
     const double inv = acc > 0.0 ? 1.0 / acc : 0.0;
     for (int p = 0; p < len; ++p) {
       const int e = (int)gjptr[p] + r;
       const int c = gidx[e] & 0xffffu;
-      const double z = (gq[e] * pt_nxt[c]) * inv;
-      const double pn = pt_cur[c];
+      const double z = (gq[e] * x_prev[c]) * inv;
+      const double pn = x_cur[c];
       if (z > 0.0 && pn > 0.0) l = fma(z, log(gq[e] * pn), l);
     }
   }
@@ -1494,6 +1649,13 @@ void free_fit(ss_handle_s* h) {
 }
 
 
+// (a preferred shared-memory carveout of 100 % for all EM kernels was measured: no difference, the driver's choice
+// already lets two light cluster CTAs / two streaming CTAs share an SM)
+template <class F>
+static cudaError_t set_smem(F fn, size_t smem) {
+  return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
 template <int TT, int FR, int FC, int MAXREG>
 static cudaError_t launch_lane(ss_handle_s* h, cudaStream_t st, const EmArgs& a, int n, int threads, size_t smem,
                                bool lnl) {
@@ -1501,12 +1663,12 @@ static cudaError_t launch_lane(ss_handle_s* h, cudaStream_t st, const EmArgs& a,
   cudaError_t e;
   if (lnl) {
     auto fn = em_lane_kernel<TT, true, FR, FC, MAXREG>;
-    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_smem(fn, smem);
     if (e != cudaSuccess) return e;
     fn<<<n, threads, smem, st>>>(a);
   } else {
     auto fn = em_lane_kernel<TT, false, FR, FC, MAXREG>;
-    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_smem(fn, smem);
     if (e != cudaSuccess) return e;
     fn<<<n, threads, smem, st>>>(a);
   }
@@ -1655,7 +1817,7 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
       h->set_error("streaming kernel does not fit on an SM");
       return SS_ERR_CAPACITY;
     }
-    SS_CUDA_CHECK(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SS_CUDA_CHECK(h, set_smem(fn, smem));
     int grid = std::min(h->n_stream_tiles, occ * h->num_sms);
     a.tile_list = h->stream_tiles;
     a.n_list = h->n_stream_tiles;
@@ -1669,34 +1831,34 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     SS_CUDA_CHECK(h, cudaEventRecord(h->ev_join[SS_NUM_CLASSES], sx));
   }
   // clusters: segments of 2..8 tiles
-  for (int nt = ss_handle_s::MAX_CLUSTER; nt >= 2; --nt) {
-    if (h->clu_count[nt] == 0) continue;
-    const int si = SS_NUM_CLASSES + 1 + (nt - 2);
+  for (int pass = 0; pass < 2 * (ss_handle_s::MAX_CLUSTER - 1); ++pass) {
+    // heavy clusters first (their CTAs each need a whole SM), large ones first
+    const bool light = pass >= ss_handle_s::MAX_CLUSTER - 1;
+    const int nt = ss_handle_s::MAX_CLUSTER - pass % (ss_handle_s::MAX_CLUSTER - 1);
+    const int n_clu = light ? (lnl ? 0 : h->clu_count_light[nt]) : h->clu_count[nt] + (lnl ? h->clu_count_light[nt] : 0);
+    if (n_clu == 0) continue;
+    const int si = SS_NUM_CLASSES + 1 + (nt - 2) + (light ? ss_handle_s::MAX_CLUSTER - 1 : 0);
     cudaStream_t sx = h->aux[si];
     h->aux_used[si] = true;
     SS_CUDA_CHECK(h, cudaStreamWaitEvent(sx, h->ev_fork, 0));
     if (h->timing) SS_CUDA_CHECK(h, cudaEventRecord(h->tev_s[si], sx));
     ClusterArgs ca;
-    ca.segs = h->clu_segs[nt];
+    ca.segs = light ? h->clu_segs_light[nt] : h->clu_segs[nt];
     ca.xref = h->clu_xref;
     ca.seg_xref_off = h->seg_xref_off;
-    ca.part = h->clu_part;
-    ca.tile_part_off = h->tile_part_off;
-    ca.part_total = h->clu_part_total;
     a.tile_list = nullptr;
     a.n_list = 0;
     void (*kfn)(EmArgs, ClusterArgs) = nullptr;
     size_t smem = 0;
     int threads = CLUSTER_THREADS;
     if (!lnl) {
-      // one cluster barrier per iteration.  512 threads x 128 registers (4 row / 6 column fragment slots per lane);
-      // SS_CLANE_THREADS=256 goes with 2048-alignment tiles (SS_SMALL_TILE_THR=1: two CTAs per SM).  Measured and
-      // dropped: 1024 threads x 64 registers with half the slots (32 warps per SM) -- 53.2 ms against 52.3 ms on
-      // config 5 x0.1, the spills cost what the occupancy gains
-      threads = h->clane_threads == 256 ? 256 : CLANE_THREADS;
-      if (threads == 256) kfn = em_clane_kernel<256, CLANE_FR, CLANE_FC, SS_CLANE_MAXREG>;
+      // one cluster barrier per iteration.  512 threads x 128 registers (4 row / 6 column fragment slots per lane).
+      // Measured and dropped: 1024 threads x 64 registers with half the slots (32 warps per SM) -- 53.2 ms against
+      // 52.3 ms on config 5 x0.1; 256-thread CTAs on 2048-alignment tiles -- 55.8 ms (twice the cluster members)
+      if (light) kfn = em_clane_kernel<CLANE_LIGHT_THREADS, CLANE_LIGHT_FR, CLANE_LIGHT_FC, SS_CLANE_LIGHT_MAXREG>;
       else kfn = em_clane_kernel<CLANE_THREADS, CLANE_FR, CLANE_FC, SS_CLANE_MAXREG>;
-      smem = h->clu_smem_lane[nt] + 256;
+      threads = light ? CLANE_LIGHT_THREADS : CLANE_THREADS;
+      smem = (light ? h->clu_smem_light[nt] : h->clu_smem_lane[nt]) + 256;
     } else {
       switch (nt) {
 #define SS_CLU_CASE(N)                               \
@@ -1708,9 +1870,9 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
       }
       smem = h->clu_smem[nt] + 256;
     }
-    SS_CUDA_CHECK(h, cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SS_CUDA_CHECK(h, set_smem((const void*)kfn, smem));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(h->clu_count[nt] * nt));
+    cfg.gridDim = dim3((unsigned)(n_clu * nt));
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = sx;

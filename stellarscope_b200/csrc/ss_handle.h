@@ -37,7 +37,23 @@ constexpr int SS_FR = SS_FR_V, SS_FC = SS_FC_V, SS_MAXREG = SS_MAXREG_V;
 constexpr int SS_FR_BIG = SS_FR_BIG_V, SS_FC_BIG = SS_FC_BIG_V, SS_MAXREG_BIG = SS_MAXREG_BIG_V;
 constexpr int SS_CLS_THREADS[] = {SS_CLS_LIST, SS_BIG_THREADS_V};
 constexpr int SS_NUM_CLASSES = (int)(sizeof(SS_CLS_THREADS) / sizeof(int));
-constexpr int SS_NUM_AUX_STREAMS = SS_NUM_CLASSES + 1 + 7;   // size classes, streaming kernel, cluster sizes 2..8
+constexpr int SS_NUM_AUX_STREAMS = SS_NUM_CLASSES + 1 + 7 + 7;   // size classes, streaming kernel, cluster sizes 2..8 (heavy, light)
+// cluster lane kernel (csrc/ss_em.cu): CTA size, row / column fragment slots per lane, register cap.  Heavy: one CTA
+// owns its SM; light: two CTAs per SM (tiles whose row fragments fit 2 slots and whose shared memory is at most half
+// an SM's -- launch plan, ss_layout.cu)
+#ifndef SS_CLANE_THREADS
+#define SS_CLANE_THREADS 512
+#define SS_CLANE_FR 4
+#define SS_CLANE_FC 6
+#define SS_CLANE_MAXREG 128
+#endif
+#ifndef SS_CLANE_LIGHT_FR
+#define SS_CLANE_LIGHT_FR 2
+#define SS_CLANE_LIGHT_FC 3
+#define SS_CLANE_LIGHT_MAXREG 64
+#endif
+constexpr int CLANE_THREADS = SS_CLANE_THREADS, CLANE_FR = SS_CLANE_FR, CLANE_FC = SS_CLANE_FC;
+constexpr int CLANE_LIGHT_THREADS = 512, CLANE_LIGHT_FR = SS_CLANE_LIGHT_FR, CLANE_LIGHT_FC = SS_CLANE_LIGHT_FC;
 constexpr int SS_COL_CHUNK = 512;
 constexpr int SS_DN_MAXW = 8;   // ranks of a row-sharded (dense) fit: the GPUs of one NVSwitch domain
 constexpr int SS_DN_THREADS = 512;    // CTA size of the row-sharded kernels = columns per update chunk
@@ -51,9 +67,12 @@ struct ss_handle_s {
   long long launches = 0;
   // experiment knobs (environment, read by ss_create): SS_SMALL_TILE_THR = segments with more than this many
   // E_HARD tiles are cut into E_STREAM tiles (default STREAM_SEG_TILES: only the streamed ones; 1: every multi-tile
-  // segment); SS_CLANE_THREADS = CTA size of the cluster lane kernel (512 | 256)
+  // segment); SS_CLUSTER_TILE = target tile size of the segments that run as thread-block clusters (cut into equal
+  // tiles of about this many alignments, ss_build.cu seg_chunk); SS_CLANE_LIGHT=0 switches the two-CTAs-per-SM
+  // variant of the cluster lane kernel off
   int small_tile_thr = ss::STREAM_SEG_TILES;
-  int clane_threads = 512;
+  int cluster_tile = ss::E_CLUSTER;
+  bool clane_light = true;
 
   // ---- layout ----
   bool has_layout = false;
@@ -90,11 +109,14 @@ struct ss_handle_s {
   int clu_count[MAX_CLUSTER + 1] = {};
   size_t clu_smem[MAX_CLUSTER + 1] = {};       // three-barrier kernel (likelihood mode)
   size_t clu_smem_lane[MAX_CLUSTER + 1] = {};  // cluster lane kernel
+  // "light" clusters: every tile's row fragments fit 2 slots of a 512-thread CTA and the shared memory of a CTA is at
+  // most half an SM's, so two CTAs (of different clusters) share an SM -- one cluster's barrier / L2 exchange
+  // overlaps the other's row and column phases (em_clane_kernel<512, 2, 3, 64>)
+  int* clu_segs_light[MAX_CLUSTER + 1] = {};
+  int clu_count_light[MAX_CLUSTER + 1] = {};
+  size_t clu_smem_light[MAX_CLUSTER + 1] = {};
   uint16_t* clu_xref = nullptr;            // device: [segment column][tile of the segment] -> tile column or 0xffff
   long long* seg_xref_off = nullptr;       // device: offset of a segment's block in clu_xref (-1: none)
-  double* clu_part = nullptr;              // device: [2][clu_part_total] partial column sums of the cluster tiles (L2-resident exchange)
-  long long* tile_part_off = nullptr;      // device: offset of a tile's columns in clu_part (-1: not a cluster tile)
-  long long clu_part_total = 0;
   int n_cluster_tiles = 0, n_cluster_segs = 0;
   int* all_tiles = nullptr;       // device: 0 .. n_tiles-1
   size_t all_smem = 0;            // smem of the largest tile (likelihood-mode carve)

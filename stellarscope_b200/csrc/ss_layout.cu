@@ -35,9 +35,12 @@ void free_layout(ss_handle_s* h) {
   h->chunk_seg = h->chunk_j0 = h->seg_chunk0 = nullptr;
   h->chunk_part = nullptr;
   h->sc_inamb = nullptr;
-  for (int k = 0; k <= ss_handle_s::MAX_CLUSTER; ++k) { h->clu_segs[k] = nullptr; h->clu_count[k] = 0; h->clu_smem[k] = 0; }
+  for (int k = 0; k <= ss_handle_s::MAX_CLUSTER; ++k) {
+    h->clu_segs[k] = h->clu_segs_light[k] = nullptr;
+    h->clu_count[k] = h->clu_count_light[k] = 0;
+    h->clu_smem[k] = h->clu_smem_lane[k] = h->clu_smem_light[k] = 0;
+  }
   h->clu_xref = nullptr; h->seg_xref_off = nullptr; h->n_cluster_tiles = h->n_cluster_segs = 0;
-  h->clu_part = nullptr; h->tile_part_off = nullptr; h->clu_part_total = 0;
   h->has_layout = false;
 }
 
@@ -151,30 +154,41 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
   // segments of 2..8 tiles whose tiles (plus the owner arrays) fit shared memory run as clusters
   const int MAXC = ss_handle_s::MAX_CLUSTER;
   std::vector<char> seg_clustered((size_t)std::max(L.S, 1), 0);
-  std::vector<int> clu[ss_handle_s::MAX_CLUSTER + 1];
+  std::vector<int> clu[ss_handle_s::MAX_CLUSTER + 1], clu_light[ss_handle_s::MAX_CLUSTER + 1];
+  // shared memory a light CTA may use: half of an SM's (the opt-in maximum per CTA is the SM's minus 1 KB; every
+  // resident CTA reserves 1 KB), minus the kernel's static shared memory
+  const size_t light_cap = (h->max_smem_optin + 1024) / 2 - 1024 - 1536;
   std::vector<long long> xoff((size_t)std::max(L.S, 1), -1);
   long long xref_total = 0;
-  for (int k = 0; k <= MAXC; ++k) h->clu_smem[k] = h->clu_smem_lane[k] = 0;
+  for (int k = 0; k <= MAXC; ++k) h->clu_smem[k] = h->clu_smem_lane[k] = h->clu_smem_light[k] = 0;
   for (int sgm = 0; sgm < L.S; ++sgm) {
     const int nt = h->seg_ntiles_host[sgm];
     if (nt < 2 || nt > MAXC) continue;
     const size_t no_pad = (size_t)pad8((seg_ncol[sgm] + nt - 1) / nt + 1);
     const size_t owner_bytes = 8 * 4 * no_pad + 2 * no_pad * nt;
     size_t need = 0;
-    int pemax = 0, pcmax = 0;
+    int pemax = 0, pcmax = 0, xsum = 0;
+    long long rfmax = 0;
     for (int k = 0; k < nt; ++k) {
       const long long* hd = &h->hdr_host[(size_t)(h->seg_tile0_host[sgm] + k) * HDR_WORDS];
+      rfmax = std::max(rfmax, hd[H_RGT32] > 0 ? (long long)1 << 40 : hd[H_RFRAG]);   // no generic rows in a light tile
       need = std::max(need, tile_smem_bytes((int)hd[H_NENT], (int)hd[H_NROWS], (int)hd[H_NCOL], (int)hd[H_MAXLEN]) +
                                 owner_bytes);
       pemax = std::max(pemax, pad8((int)hd[H_NENT]));
       pcmax = std::max(pcmax, pad8((int)hd[H_NCOL] + 1));
+      xsum += (int)hd[H_NCOL];
     }
-    const size_t need_lane = clane_smem_bytes(pemax, pcmax, nt);
+    const size_t need_lane = clane_smem_bytes(pemax, pcmax, nt, pad8(xsum - seg_ncol[sgm] + 1));
     if (need + 2048 > h->max_smem_optin || need_lane + 2048 > h->max_smem_optin) continue;
     seg_clustered[sgm] = 1;
-    clu[nt].push_back(sgm);
     h->clu_smem[nt] = std::max(h->clu_smem[nt], need);
-    h->clu_smem_lane[nt] = std::max(h->clu_smem_lane[nt], need_lane);
+    if (h->clane_light && rfmax <= CLANE_LIGHT_FR * CLANE_LIGHT_THREADS && need_lane + 256 <= light_cap) {
+      clu_light[nt].push_back(sgm);
+      h->clu_smem_light[nt] = std::max(h->clu_smem_light[nt], need_lane);
+    } else {
+      clu[nt].push_back(sgm);
+      h->clu_smem_lane[nt] = std::max(h->clu_smem_lane[nt], need_lane);
+    }
     xoff[sgm] = xref_total;
     xref_total += (long long)seg_ncol[sgm] * nt;
   }
@@ -294,23 +308,18 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
       const long long eb = h->hdr_host[(size_t)(h->seg_tile0_host[b] + k - 1) * HDR_WORDS + H_NENT];
       return ea != eb ? ea > eb : a < b;
     });
+    std::sort(clu_light[k].begin(), clu_light[k].end(), [&](int a, int b) {
+      const long long ea = h->hdr_host[(size_t)(h->seg_tile0_host[a] + k - 1) * HDR_WORDS + H_NENT];
+      const long long eb = h->hdr_host[(size_t)(h->seg_tile0_host[b] + k - 1) * HDR_WORDS + H_NENT];
+      return ea != eb ? ea > eb : a < b;
+    });
     h->clu_count[k] = (int)clu[k].size();
-    h->n_cluster_segs += h->clu_count[k];
+    h->clu_count_light[k] = (int)clu_light[k].size();
+    h->n_cluster_segs += h->clu_count[k] + h->clu_count_light[k];
+    // one list per cluster size, heavy segments first: the likelihood-mode kernel takes them all
+    clu[k].insert(clu[k].end(), clu_light[k].begin(), clu_light[k].end());
     SS_CUDA_CHECK(h, upload(pool, &h->clu_segs[k], (const int*)clu[k].data(), clu[k].size(), st));
-  }
-  // exchange buffers of the cluster lane kernel: the partial column sums of every cluster tile, twice
-  // (iteration parity); they live in global memory on purpose -- L2 feeds an SM several times faster
-  // than the SM-to-SM network (DSMEM: ~20 B/cycle), and the working set of the active clusters is a few MB
-  {
-    std::vector<long long> poff((size_t)std::max(T, 1), -1);
-    long long tot = 0;
-    for (int t : cluster_tiles) {
-      poff[t] = tot;
-      tot += pad8((int)h->hdr_host[(size_t)t * HDR_WORDS + H_NCOL] + 1);
-    }
-    h->clu_part_total = tot;
-    SS_CUDA_CHECK(h, upload(pool, &h->tile_part_off, (const long long*)poff.data(), poff.size(), st));
-    SS_CUDA_CHECK(h, dev_alloc(pool, &h->clu_part, (size_t)std::max<long long>(2 * tot, 1)));
+    h->clu_segs_light[k] = h->clu_segs[k] + h->clu_count[k];
   }
   SS_CUDA_CHECK(h, upload(pool, &h->seg_xref_off, (const long long*)xoff.data(), xoff.size(), st));
   SS_CUDA_CHECK(h, dev_alloc(pool, &h->clu_xref, (size_t)std::max<long long>(xref_total, 1)));

@@ -108,7 +108,8 @@ int reassign(ss_handle_s* h, cudaStream_t st, int mode, double conf, double tol,
     return SS_ERR_MODEL;
   }
   const bool needs_z = mode <= SS_BEST_AVERAGE;
-  if ((needs_z && !z) || ((mode == SS_INITIAL_RANDOM) && !score) || !flag || !nbest || !info || !row_ptr) {
+  if (!info || (n_rows > 0 && ((needs_z && !z) || ((mode == SS_INITIAL_RANDOM) && !score) || !flag || !nbest ||
+                               !row_ptr))) {       // n_rows == 0: a rank of a sharded run without rows of its own
     h->set_error("ss_reassign: missing buffer");
     return SS_ERR_ARG;
   }
@@ -359,7 +360,7 @@ __global__ void select_count_kernel(int n_rows, const int* __restrict__ row_ptr,
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row > n_rows) return;
   int c = 0;
-  if (row < n_rows)
+  if (row < n_rows && flag)
     for (int k = row_ptr[row]; k < row_ptr[row + 1]; ++k) c += flag[k] != 0;
   per_row[row] = c;                                  // per_row[n_rows] = 0: the scan's last element is the total
 }
@@ -383,7 +384,8 @@ __global__ void select_fill_kernel(int n_rows, const int* __restrict__ row_ptr, 
 int reassign_csr(ss_handle_s* h, cudaStream_t st, int n_rows, const int* row_ptr, const int* col_idx, const uint8_t* flag,
                  const int* nbest, long long cap, long long* out_ptr, int* out_idx, double* out_val, long long* n_out) {
   *n_out = 0;
-  if (n_rows < 0 || !row_ptr || !col_idx || !flag || !out_ptr || (cap > 0 && !out_idx)) {
+  // a matrix without alignments (a rank of a sharded run without rows of its own) has empty col_idx / flag arrays
+  if (n_rows < 0 || !row_ptr || !out_ptr || (cap > 0 && !out_idx)) {
     h->set_error("ss_reassign_csr: bad argument");
     return SS_ERR_ARG;
   }
@@ -401,6 +403,10 @@ int reassign_csr(ss_handle_s* h, cudaStream_t st, int n_rows, const int* row_ptr
   if (total > cap) {
     h->set_error("ss_reassign_csr: output capacity too small");
     return SS_ERR_CAPACITY;
+  }
+  if (total > 0 && !col_idx) {
+    h->set_error("ss_reassign_csr: bad argument");
+    return SS_ERR_ARG;
   }
   if (total > 0 && n_rows > 0) {
     select_fill_kernel<<<(n_rows + B - 1) / B, B, 0, st>>>(n_rows, row_ptr, col_idx, flag, nbest, out_ptr, out_idx, out_val);

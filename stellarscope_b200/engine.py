@@ -333,14 +333,16 @@ class Engine:
         prepare, streaming kernel, resident kernels, emit, finalize."""
         thr = (C.c_int32 * 32)()
         nc = self.lib.ss_lane_classes(thr, 32)
-        n = 5 + nc + 8
+        n = 5 + nc + 15
         buf = (C.c_double * n)()
         self._check(self.lib.ss_get_timings(self.h, buf, n))
         out = {'prepare': buf[0], 'em': buf[1], 'emit': buf[3], 'finalize': buf[4], 'stream': buf[5 + nc]}
         for i in range(nc):
             out[f'lane{i}_{thr[i]}'] = buf[5 + i]
         out['resident'] = max(buf[5:5 + nc])
-        out['cluster'] = max(buf[5 + nc + 1:5 + nc + 8])
+        out['cluster'] = max(buf[5 + nc + 1:5 + nc + 15])
+        out['cluster_heavy'] = max(buf[5 + nc + 1:5 + nc + 8])
+        out['cluster_light'] = max(buf[5 + nc + 8:5 + nc + 15])
         return {k: float(v) for k, v in out.items()}
 
     # -- one model, rows sharded over ranks (pseudobulk; csrc/ss_dense.cu) ------------

@@ -35,6 +35,7 @@ import numpy as np
 E_HARD = 4096        # hard cap on alignments per tile (shared-memory budget, csrc/ss_common.cuh)
 E_STREAM = 2048      # tile size of streamed segments (more than STREAM_SEG_TILES large tiles)
 STREAM_SEG_TILES = 8
+E_CLUSTER = 3072     # target tile size of the segments that run as thread-block clusters (csrc/ss_common.cuh)
 ALIGN = 8            # every per-tile slice starts at a multiple of 8 elements
 
 
@@ -197,7 +198,11 @@ def build(indptr, indices, scores, row_seg, S, K, e_hard=E_HARD, long_col=32):
     chunk_small = E_STREAM - maxlen + 1 if (e_hard == E_HARD and maxlen <= E_STREAM // 2) else chunk
     seg_aamb = np.bincount(aseg, weights=alen, minlength=S).astype(np.int64) if len(ar) else np.zeros(S, dtype=np.int64)
     small_thr = int(os.environ.get('SS_SMALL_TILE_THR', STREAM_SEG_TILES))      # experiment knob, like the device builder
-    seg_chunk = np.where(seg_aamb > small_thr * chunk, chunk_small, chunk)
+    # segments of 2..small_thr large tiles (thread-block clusters) are cut into EQUAL tiles of about `target` alignments
+    target = min(chunk, int(os.environ.get('SS_CLUSTER_TILE', E_CLUSTER)))
+    nt_bal = np.minimum(-(-seg_aamb // target), small_thr)
+    seg_chunk = np.where(seg_aamb > small_thr * chunk, chunk_small,
+                         np.where(seg_aamb <= chunk, chunk, -(-seg_aamb // np.maximum(nt_bal, 1))))
     tin = o // seg_chunk[aseg] if len(ar) else o
     seg_ntiles = np.zeros(S, dtype=np.int32)
     if len(ar):

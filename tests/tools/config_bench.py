@@ -83,7 +83,8 @@ def main():
     units = float((seg_A * it).sum())
     alg = float(((12 * seg_Aamb + 4 * seg_namb + 16 * p['seg_ncol'].astype(np.int64)) * it).sum())
     em_s = best['em'] / 1e3
-    print(f'fit: em {best["em"]:.3f} ms (lane {best["resident"]:.3f} cluster {best["cluster"]:.3f} stream {best["stream"]:.3f}) '
+    print(f'fit: em {best["em"]:.3f} ms (lane {best["resident"]:.3f} cluster {best["cluster"]:.3f} [heavy {best["cluster_heavy"]:.3f} '
+          f'light {best["cluster_light"]:.3f}] stream {best["stream"]:.3f}) '
           f'mean iters {it[fitted].mean():.1f} max {it.max()}  rate {units / em_s / 1e9:.1f} G aln*iter/s  '
           f'algorithmic {alg / em_s / 1e9:.0f} GB/s', flush=True)
     # ---- properties ----
