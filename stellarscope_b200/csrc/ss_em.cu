@@ -637,6 +637,7 @@ struct ClusterArgs {
   const int* segs;
   const uint16_t* xref;
   const long long* seg_xref_off;
+  const int* seg_xmax;             // receive slots per tile (cluster lane kernel)
 };
 
 constexpr int SS_MAX_CLUSTER_TILES = 8;
@@ -698,16 +699,15 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
   const int t = t0 + rank;
   const long long* __restrict__ hd = a.L.tile_hdr + (long long)HDR_WORDS * t;
   const TileView v = load_tile_view(a.L.tile_hdr, t);
-  // the same carve in every CTA of the cluster: sizes of the segment's largest tile; xmax bounds the partial sums a
-  // tile can receive per pass (sum over the tiles' columns - columns of the segment = sum_c (holders(c) - 1))
-  int pemax = 0, pcmax = 0, xsum = 0;
+  // the same carve in every CTA of the cluster: sizes of the segment's largest tile; xmax (launch plan) bounds the
+  // partial sums a tile can receive per pass: sum over the segment's tile columns of (holders - 1)
+  int pemax = 0, pcmax = 0;
   for (int k = 0; k < nt; ++k) {
     const long long* hk = a.L.tile_hdr + (long long)HDR_WORDS * (t0 + k);
     pemax = max(pemax, pad8((int)hk[H_NENT]));
     pcmax = max(pcmax, pad8((int)hk[H_NCOL] + 1));
-    xsum += (int)hk[H_NCOL];
   }
-  const int xmax = pad8(xsum - a.L.seg_ncol[seg] + 1);
+  const int xmax = ca.seg_xmax[seg];
   // x of three consecutive iterations (rotating: the convergence of iteration k is known one pass late, when the
   // column lanes have already written x_{k+1}; x_{k-1} and x_k must survive), pi, the prior pseudo counts of the
   // columns, the column-major scratch, the receive buffers of the two pass parities
@@ -1846,6 +1846,7 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
     ca.segs = light ? h->clu_segs_light[nt] : h->clu_segs[nt];
     ca.xref = h->clu_xref;
     ca.seg_xref_off = h->seg_xref_off;
+    ca.seg_xmax = h->seg_xmax;
     a.tile_list = nullptr;
     a.n_list = 0;
     void (*kfn)(EmArgs, ClusterArgs) = nullptr;

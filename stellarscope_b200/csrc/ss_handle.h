@@ -117,6 +117,7 @@ struct ss_handle_s {
   size_t clu_smem_light[MAX_CLUSTER + 1] = {};
   uint16_t* clu_xref = nullptr;            // device: [segment column][tile of the segment] -> tile column or 0xffff
   long long* seg_xref_off = nullptr;       // device: offset of a segment's block in clu_xref (-1: none)
+  int* seg_xmax = nullptr;                 // device: receive slots per tile of the cluster lane kernel (padded sum over the segment's tile columns of holders - 1)
   int n_cluster_tiles = 0, n_cluster_segs = 0;
   int* all_tiles = nullptr;       // device: 0 .. n_tiles-1
   size_t all_smem = 0;            // smem of the largest tile (likelihood-mode carve)

@@ -40,7 +40,7 @@ void free_layout(ss_handle_s* h) {
     h->clu_count[k] = h->clu_count_light[k] = 0;
     h->clu_smem[k] = h->clu_smem_lane[k] = h->clu_smem_light[k] = 0;
   }
-  h->clu_xref = nullptr; h->seg_xref_off = nullptr; h->n_cluster_tiles = h->n_cluster_segs = 0;
+  h->clu_xref = nullptr; h->seg_xref_off = nullptr; h->seg_xmax = nullptr; h->n_cluster_tiles = h->n_cluster_segs = 0;
   h->has_layout = false;
 }
 
@@ -62,6 +62,18 @@ __global__ void cluster_xref_kernel(const int* __restrict__ tiles, int n, Layout
   const long long off = seg_xref_off[seg];
   for (int c = threadIdx.x; c < ncol; c += blockDim.x)
     xref[off + (long long)(L.c_scol[co + c] - col0) * nt + k] = (uint16_t)c;
+}
+
+// number of a segment's columns that a tile touches (the others belong to unique rows only); one warp per segment
+__global__ void seg_tile_cols_kernel(int S, const int* __restrict__ seg_col0, const int* __restrict__ seg_ncol,
+                                     const int8_t* __restrict__ sc_inamb, int* __restrict__ out) {
+  const int s = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (s >= S) return;
+  const int c0 = seg_col0[s], n = seg_ncol[s];
+  int cnt = 0;
+  for (int j = lane; j < n; j += 32) cnt += sc_inamb[c0 + j] != 0;
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) out[s] = cnt;
 }
 
 template <class T>
@@ -161,6 +173,17 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
   std::vector<long long> xoff((size_t)std::max(L.S, 1), -1);
   long long xref_total = 0;
   for (int k = 0; k <= MAXC; ++k) h->clu_smem[k] = h->clu_smem_lane[k] = h->clu_smem_light[k] = 0;
+  // columns of every segment that its tiles touch: sum over the tiles' columns minus this = sum over the columns of
+  // (holders - 1) = the partial sums a tile of the cluster lane kernel can receive per pass (its receive buffer)
+  std::vector<int> tile_cols((size_t)std::max(L.S, 1), 0), seg_xmax((size_t)std::max(L.S, 1), 0);
+  if (L.S > 0) {
+    int* d_cnt;
+    SS_CUDA_CHECK(h, dev_alloc(pool, &d_cnt, (size_t)L.S));
+    seg_tile_cols_kernel<<<(unsigned)(((long long)L.S * 32 + 255) / 256), 256, 0, st>>>(L.S, L.seg_col0, L.seg_ncol, h->sc_inamb, d_cnt);
+    h->launches++;
+    SS_CUDA_CHECK(h, cudaMemcpyAsync(tile_cols.data(), d_cnt, (size_t)L.S * 4, cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(h, cudaStreamSynchronize(st));
+  }
   for (int sgm = 0; sgm < L.S; ++sgm) {
     const int nt = h->seg_ntiles_host[sgm];
     if (nt < 2 || nt > MAXC) continue;
@@ -178,7 +201,8 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
       pcmax = std::max(pcmax, pad8((int)hd[H_NCOL] + 1));
       xsum += (int)hd[H_NCOL];
     }
-    const size_t need_lane = clane_smem_bytes(pemax, pcmax, nt, pad8(xsum - seg_ncol[sgm] + 1));
+    seg_xmax[sgm] = pad8(std::max(xsum - tile_cols[sgm], 0) + 1);
+    const size_t need_lane = clane_smem_bytes(pemax, pcmax, nt, seg_xmax[sgm]);
     if (need + 2048 > h->max_smem_optin || need_lane + 2048 > h->max_smem_optin) continue;
     seg_clustered[sgm] = 1;
     h->clu_smem[nt] = std::max(h->clu_smem[nt], need);
@@ -322,6 +346,7 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
     h->clu_segs_light[k] = h->clu_segs[k] + h->clu_count[k];
   }
   SS_CUDA_CHECK(h, upload(pool, &h->seg_xref_off, (const long long*)xoff.data(), xoff.size(), st));
+  SS_CUDA_CHECK(h, upload(pool, &h->seg_xmax, (const int*)seg_xmax.data(), seg_xmax.size(), st));
   SS_CUDA_CHECK(h, dev_alloc(pool, &h->clu_xref, (size_t)std::max<long long>(xref_total, 1)));
   if (xref_total > 0) {
     int* d_ct;
