@@ -5,7 +5,8 @@
 // (:701-743).  The construction is specified by stellarscope_b200/layout_host.py;
 // this file produces the same arrays on the device.  Device-wide sorts / scans use
 // CUB (library code, one-time build step); the per-tile work (JDS ordering, tile
-// column discovery, column-major slots) is a hand-written CTA-per-tile kernel.
+// column discovery, column-major slots) is a hand-written CTA-per-tile kernel (its three
+// block-wide sorts are CUB's BlockRadixSort).
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -213,56 +214,70 @@ __global__ void tile_sizes_kernel(int n_tiles, const int* __restrict__ tile_row0
 }
 
 // ---- block-wide helpers ----------------------------------------------------------
-// bitonic sort of n (power of two) 64-bit keys in shared memory, ascending
-__device__ void bitonic_sort(unsigned long long* keys, int n) {
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = keys[i], b = keys[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > b) == up) {
-            keys[i] = b;
-            keys[ixj] = a;
-          }
-        }
-      }
-      __syncthreads();
+// Stable sort of keys[0, n) (shared memory, capacity BT * ITEMS) by the bits [begin_bit, end_bit): the block-wide
+// radix sort of CUB (library code, like the device-wide sorts of this file) on a blocked arrangement in registers.
+// 15 four-bit passes per tile in all; the bitonic network this replaces took 210 compare-exchange steps and was 70 %
+// of the builder's instructions (ncu, profiles/r2l_tile_build_*).  Slots >= n take part as all-ones keys and, the
+// sort being stable, stay behind the keys proper.
+template <int BT, int ITEMS>
+struct TileSort {
+  using BRS = cub::BlockRadixSort<unsigned long long, BT, ITEMS>;
+  using Temp = typename BRS::TempStorage;
+  static __device__ __forceinline__ void sort(unsigned long long* keys, int n, int begin_bit, int end_bit, Temp& tmp) {
+    unsigned long long k[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int idx = (int)threadIdx.x * ITEMS + i;
+      k[i] = idx < n ? keys[idx] : ~0ull;
     }
+    __syncthreads();                                   // everything is read before the striped write-back below
+    BRS(tmp).SortBlockedToStriped(k, begin_bit, end_bit);
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) keys[i * BT + (int)threadIdx.x] = k[i];
+    __syncthreads();
   }
+};
+__host__ __device__ constexpr int ceil_log2(int n) {
+  int b = 0;
+  while ((1 << b) < n) ++b;
+  return b;
 }
-__device__ __forceinline__ int next_pow2(int n) {
-  int p = 1;
-  while (p < n) p <<= 1;
-  return p;
-}
-// exclusive scan of n ints in shared memory, in place; returns the total. scratch: blockDim.x ints
+// exclusive scan of n ints in shared memory, in place; returns the total. scratch: blockDim.x + 1 ints.  Every thread
+// sums a contiguous piece; the per-thread sums are scanned by warp shuffles (a thread-0 loop over 1024 partial sums
+// cost more than the sorts of a tile)
 __device__ int block_excl_scan(int* data, int n, int* scratch) {
-  const int T = blockDim.x, tid = threadIdx.x;
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
   const int per = (n + T - 1) / T;
   const int b = min(n, tid * per), e = min(n, b + per);
   int s = 0;
   for (int i = b; i < e; ++i) s += data[i];
-  scratch[tid] = s;
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) scratch[warp] = incl;
   __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int i = 0; i < T; ++i) {
-      const int v = scratch[i];
-      scratch[i] = run;
-      run += v;
+  if (warp == 0) {
+    int w = lane < nw ? scratch[lane] : 0;
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += up;
     }
-    scratch[T] = run;
+    if (lane < nw) scratch[lane] = wi - w;                  // exclusive prefix of the warp totals
+    if (lane == 31) scratch[T] = wi;                        // total (nw <= 32)
   }
   __syncthreads();
-  int run = scratch[tid];
+  int run = scratch[warp] + incl - s;
+  const int total = scratch[T];
   for (int i = b; i < e; ++i) {
     const int v = data[i];
     data[i] = run;
     run += v;
   }
-  const int total = scratch[T];
   __syncthreads();
   return total;
 }
@@ -293,6 +308,7 @@ struct TileBuildArgs {
   int* tmp_gcol;
   uint16_t* tmp_jptr;
   int jds_stride;
+  int gbits;                // bits of a column index (n_cols - 1)
   // per tile scalars
   int *t_ncol, *t_maxlen, *t_nlong, *t_seg, *t_nrows, *t_nent, *t_rfrag, *t_cfrag;
   int* t_gt;               // [n_tiles][10]: rows longer than 4/8/16/32, columns with more than 4..128 rows
@@ -330,23 +346,22 @@ __global__ void __launch_bounds__(BT) tile_build_kernel(TileBuildArgs a) {
   int* jptr = rlen + RCAP;                                                  // ECAP + 2 (a row may be as long as the tile)
   int* scratch = jptr + ECAP + 2;                                           // BT + 1
   __shared__ double s_red[32];
+  using SortE = TileSort<BT, ECAP / BT>;                                    // entries / columns: up to ECAP keys
+  using SortR = TileSort<BT, (RCAP + BT - 1) / BT>;                         // rows: up to RCAP keys
+  __shared__ union { typename SortE::Temp e; typename SortR::Temp r; } s_sort;
+  constexpr int LEN_BITS = ceil_log2(E_HARD) + 1;                           // E_HARD - len / - count; all-ones = padding sorts last
   const int seg = a.aseg[row0];
   const long long eo = a.ent_off[t], ro = a.row_off[t];
 
   // (a) JDS row order: (len desc, rank asc)
-  const int np2 = next_pow2(nrows);
   int lmax = 0;
-  for (int r = tid; r < np2; r += BT) {
-    if (r < nrows) {
-      const int row = a.ar[row0 + r];
-      const int len = a.row_ptr[row + 1] - a.row_ptr[row];
-      keys[r] = ((unsigned long long)(unsigned)(E_HARD - len) << 32) | (unsigned)r;
-    } else {
-      keys[r] = ~0ull;
-    }
+  for (int r = tid; r < nrows; r += BT) {
+    const int row = a.ar[row0 + r];
+    const int len = a.row_ptr[row + 1] - a.row_ptr[row];
+    keys[r] = ((unsigned long long)(unsigned)(E_HARD - len) << 32) | (unsigned)r;
   }
   __syncthreads();
-  bitonic_sort(keys, np2);
+  SortR::sort(keys, nrows, 32, 32 + LEN_BITS, s_sort.r);         // by length; stable: rank order inside a length
   for (int r = tid; r < nrows; r += BT) {
     const int rank = (int)(keys[r] & 0xffffffffu);
     const int len = E_HARD - (int)(keys[r] >> 32);
@@ -396,8 +411,6 @@ __global__ void __launch_bounds__(BT) tile_build_kernel(TileBuildArgs a) {
     double v = warp_sum(wsum);
     if ((tid & 31) == 0) s_red[tid >> 5] = v;
   }
-  const int ep2 = next_pow2(nent);
-  for (int e = nent + tid; e < ep2; e += BT) keys[e] = ~0ull;
   // zero the padding of the entry / row arrays
   for (int e = nent + tid; e < pad8(nent); e += BT) {
     a.e_q[eo + e] = 0.0; a.e_idx[eo + e] = 0u; a.e_opos[eo + e] = 0;
@@ -411,8 +424,9 @@ __global__ void __launch_bounds__(BT) tile_build_kernel(TileBuildArgs a) {
     for (int i = 0; i < BT / 32; ++i) tsum += s_red[i];
     a.t_wsum[t] = tsum;
   }
-  // (d) tile columns: sort by (locus, JDS row)
-  bitonic_sort(keys, ep2);
+  // (d) tile columns: sort by (locus, JDS row) -- least significant field first
+  SortE::sort(keys, nent, 16, 16 + ceil_log2(RCAP), s_sort.e);
+  SortE::sort(keys, nent, 32, 32 + a.gbits, s_sort.e);
   for (int i = tid; i < nent; i += BT)
     colidx[i] = (i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32)) ? 1 : 0;
   __syncthreads();
@@ -427,18 +441,13 @@ __global__ void __launch_bounds__(BT) tile_build_kernel(TileBuildArgs a) {
   if (tid == 0) colstart[ncol] = nent;
   __syncthreads();
   // order columns by (count desc, locus asc)
-  const int cp2 = next_pow2(ncol);
-  for (int c = tid; c < cp2; c += BT) {
-    if (c < ncol) {
-      const int cnt = colstart[c + 1] - colstart[c];
-      const unsigned long long g = keys[colstart[c]] >> 32;
-      ckeys[c] = ((unsigned long long)(unsigned)(E_HARD - cnt) << 48) | (g << 16) | (unsigned)c;
-    } else {
-      ckeys[c] = ~0ull;
-    }
+  for (int c = tid; c < ncol; c += BT) {
+    const int cnt = colstart[c + 1] - colstart[c];
+    const unsigned long long g = keys[colstart[c]] >> 32;
+    ckeys[c] = ((unsigned long long)(unsigned)(E_HARD - cnt) << 48) | (g << 16) | (unsigned)c;
   }
   __syncthreads();
-  bitonic_sort(ckeys, cp2);
+  SortE::sort(ckeys, ncol, 48, 48 + LEN_BITS, s_sort.e);         // by count; stable: the columns are in locus order
   int nlong_local = 0;
   const long long co_tmp = eo + 8LL * t;
   for (int lc = tid; lc < ncol; lc += BT) {
@@ -885,6 +894,8 @@ int layout_build(ss_handle_s* h, cudaStream_t st, int n_rows, int n_cols, long l
     a.e_q = L.e_q; a.e_idx = L.e_idx; a.e_opos = L.e_opos;
     a.r_len = L.r_len; a.r_w = L.r_w; a.r_orow = L.r_orow;
     a.tmp_cptr = tmp_cptr; a.tmp_gcol = tmp_gcol; a.tmp_jptr = tmp_jptr; a.jds_stride = jds_stride;
+    a.gbits = 1;
+    while ((1LL << a.gbits) < (long long)n_cols) ++a.gbits;
     a.t_ncol = t_ncol; a.t_maxlen = t_maxlen; a.t_nlong = t_nlong; a.t_seg = t_seg; a.t_nrows = t_nrows;
     a.t_nent = t_nent; a.t_wsum = t_wsum; a.t_rfrag = t_rfrag; a.t_cfrag = t_cfrag; a.t_gt = t_gt;
     // the three size classes work on disjoint tiles: run them side by side on internal streams
