@@ -62,6 +62,9 @@ NCU_TRAFFIC = {
     ('cfg5', 0.1): (8.762e9, 'profiles/r2i_cfg5_x0.1_em_ncu.csv (one fit at scale 0.1, sum over the 21 EM kernels: '
                              '7.5 GB of it is em_stream_kernel re-reading the tiles of the 92 largest cells every '
                              'iteration; lane + cluster kernels read their tiles once: 1.2 GB)'),
+    ('cfg5', 0.05): (0.621e9, 'profiles/r2l_cfg5_x0.05_em_ncu.csv (one fit at scale 0.05, sum over the 28 EM kernels; '
+                              'the tiles of the 46 streamed cells stay in L2 at this scale, every tile is read from '
+                              'DRAM about once)'),
 }
 
 
@@ -689,6 +692,18 @@ def run_ours(args):
         if traffic is None:
             traffic_src = {f'{k[0]} x{k[1]}': dict(bytes_per_fit=v[0], source=v[1]) for k, v in NCU_TRAFFIC.items()}
         fitted = seg_A > 0
+        # the resource that binds the on-chip kernels (lane / cluster): issue slots.  Warp instructions per unit from the
+        # ncu capture of one cfg5 fit (sum of smsp__inst_executed over the EM kernels / units of the fit)
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_hz = 1e6 * float((clocks or {}).get('sm_mhz') or 1965.0)
+        winst = 3.59 if mode == 'individual' else None
+        on_chip = None if winst is None else dict(
+            bound='issue_slots', warp_instructions_per_unit=winst,
+            achieved=winst * value / world / 1e9, peak=sm_count * 4 * sm_hz / 1e9, unit='G warp-instructions/s per GPU',
+            frac=winst * value / world / (sm_count * 4 * sm_hz),
+            source='profiles/r2l_cfg5_x0.05_em_ncu.csv: 8.72 G warp instructions for 2.43 G alignments x iterations; peak = '
+                   'SMs x 4 schedulers x SM clock (the kernels also wait on shared memory and barriers: 45-62 % of the '
+                   'issue slots is what the best of them reach)')
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=tmax_ms / args.steps, higher_is_better=True, scaling='strong', vs_baseline=None,
@@ -732,15 +747,19 @@ def run_ours(args):
                                'bandwidth per iteration',
                           binding_resource='shared-memory pipe / issue slots for lane + cluster kernels (on-chip '
                                            'resident), HBM + L2 for the streaming kernel',
+                          on_chip=on_chip,
                           ncu_utilisation=dict(
-                              source='profiles/r2i_cfg5_x0.1_em_ncu.csv, profiles/r2h_stream_final_cfg4_ncu.csv (ncu --set full; '
-                                     'percent of peak sustained)',
-                              em_clane_kernel=dict(share_of_em_time_cfg5=0.71, issue_slots='25-28', shared_memory_pipe='21-32',
-                                                   registers=128, warps_per_sm=16),
-                              em_lane_kernel=dict(share_of_em_time_cfg5=0.10, issue_slots='31-45', shared_memory_pipe='44-57',
+                              source='profiles/r2l_cfg5_x0.05_em_ncu.csv, profiles/r2h_stream_final_cfg4_ncu.csv (ncu --set full; '
+                                     'percent of peak sustained; shares = serialised kernel times of one cfg5 fit)',
+                              em_clane_kernel_light=dict(share_of_em_time_cfg5=0.52, issue_slots='32-39', shared_memory_pipe='24-41',
+                                                         registers=64, warps_per_sm='28-31 (two CTAs per SM)'),
+                              em_clane_kernel_heavy=dict(share_of_em_time_cfg5=0.20, issue_slots='26-33', shared_memory_pipe='15-22',
+                                                         registers=128, warps_per_sm=16),
+                              em_lane_kernel=dict(share_of_em_time_cfg5=0.12, issue_slots='31-45', shared_memory_pipe='39-56',
                                                   registers=128, warps_per_sm='12-16 (32 for the 1024-thread class)'),
-                              em_stream_kernel=dict(share_of_em_time_cfg5=0.19, issue_slots=55, shared_memory_pipe=51,
-                                                    dram_pct_of_measured_peak=38.8, registers=64, warps_per_sm=32)),
+                              em_stream_kernel=dict(share_of_em_time_cfg5=0.16, issue_slots='21 (cfg5 x0.05) / 55 (cfg4)',
+                                                    shared_memory_pipe='17 / 51', dram_pct_of_measured_peak=38.8,
+                                                    registers=64, warps_per_sm=32)),
                           peak_source=peak_src, kernel_ms=em_max, algorithmic_bytes=alg_all,
                           lane_bytes=lane_all, cluster_bytes=clu_all, stream_bytes=str_all),
             parity_sample=dict(cells=int(par_cells), max_rel_pi=float(pmax.item()), counts_equal=bool(pmin[0].item() >= 1),

@@ -1818,6 +1818,8 @@ int em_fit(ss_handle_s* h, cudaStream_t st, const FitParams& P) {
       return SS_ERR_CAPACITY;
     }
     SS_CUDA_CHECK(h, set_smem(fn, smem));
+    // (capping the cooperative grid at one CTA per SM while cluster / lane kernels run beside it was measured: config 5
+    // x0.1 45.5 -> 43.1 ms, x0.3 130.7 -> 140.2 ms -- dropped)
     int grid = std::min(h->n_stream_tiles, occ * h->num_sms);
     a.tile_list = h->stream_tiles;
     a.n_list = h->n_stream_tiles;
