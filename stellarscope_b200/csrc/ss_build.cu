@@ -347,8 +347,9 @@ __global__ void __launch_bounds__(BT) tile_build_kernel(TileBuildArgs a) {
   int* scratch = jptr + ECAP + 2;                                           // BT + 1
   __shared__ double s_red[32];
   using SortE = TileSort<BT, ECAP / BT>;                                    // entries / columns: up to ECAP keys
-  using SortR = TileSort<BT, (RCAP + BT - 1) / BT>;                         // rows: up to RCAP keys
+  using SortR = TileSort<BT, (RCAP + BT - 1) / BT>;                         // rows: up to RCAP keys; entries / columns of a half-full tile
   __shared__ union { typename SortE::Temp e; typename SortR::Temp r; } s_sort;
+  constexpr int HALF = BT * ((RCAP + BT - 1) / BT);                         // keys the small sorter takes (streamed tiles: 2048 of 4096)
   constexpr int LEN_BITS = ceil_log2(E_HARD) + 1;                           // E_HARD - len / - count; all-ones = padding sorts last
   const int seg = a.aseg[row0];
   const long long eo = a.ent_off[t], ro = a.row_off[t];
@@ -425,8 +426,13 @@ __global__ void __launch_bounds__(BT) tile_build_kernel(TileBuildArgs a) {
     a.t_wsum[t] = tsum;
   }
   // (d) tile columns: sort by (locus, JDS row) -- least significant field first
-  SortE::sort(keys, nent, 16, 16 + ceil_log2(RCAP), s_sort.e);
-  SortE::sort(keys, nent, 32, 32 + a.gbits, s_sort.e);
+  if (nent <= HALF) {
+    SortR::sort(keys, nent, 16, 16 + ceil_log2(RCAP), s_sort.r);
+    SortR::sort(keys, nent, 32, 32 + a.gbits, s_sort.r);
+  } else {
+    SortE::sort(keys, nent, 16, 16 + ceil_log2(RCAP), s_sort.e);
+    SortE::sort(keys, nent, 32, 32 + a.gbits, s_sort.e);
+  }
   for (int i = tid; i < nent; i += BT)
     colidx[i] = (i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32)) ? 1 : 0;
   __syncthreads();
@@ -447,7 +453,8 @@ __global__ void __launch_bounds__(BT) tile_build_kernel(TileBuildArgs a) {
     ckeys[c] = ((unsigned long long)(unsigned)(E_HARD - cnt) << 48) | (g << 16) | (unsigned)c;
   }
   __syncthreads();
-  SortE::sort(ckeys, ncol, 48, 48 + LEN_BITS, s_sort.e);         // by count; stable: the columns are in locus order
+  if (ncol <= HALF) SortR::sort(ckeys, ncol, 48, 48 + LEN_BITS, s_sort.r);    // by count; stable: the columns are in locus order
+  else SortE::sort(ckeys, ncol, 48, 48 + LEN_BITS, s_sort.e);
   int nlong_local = 0;
   const long long co_tmp = eo + 8LL * t;
   for (int lc = tid; lc < ncol; lc += BT) {

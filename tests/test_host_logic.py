@@ -213,3 +213,37 @@ def test_row_outputs_c_walk_equals_the_python_route():
     bad = types.SimpleNamespace(read_index={'nobody': 0}, read_bcode_map={}, read_umi_map={}, opts=types.SimpleNamespace(umi_counts=False))
     with pytest.raises(KeyError):
         model._row_outputs(bad, bc_pos)
+
+
+def test_cluster_segments_are_cut_into_equal_tiles():
+    """A segment of 2..8 large tiles (it runs as a thread-block cluster whose CTAs wait for the slowest one every
+    iteration) is cut into EQUAL tiles of about E_CLUSTER alignments; single-tile and streamed segments keep their cut
+    (csrc/ss_build.cu seg_chunk, mirrored by layout_host.build)."""
+    rng = np.random.default_rng(3)
+    sizes = [900, 4000, 5000, 9000, 20000, 30000, 40000]       # ambiguous alignments per cell (3 per row)
+    indptr, indices, seg = [0], [], []
+    for s, a in enumerate(sizes):
+        for _ in range(a // 3):
+            c = np.sort(rng.choice(400, size=3, replace=False)) + 1
+            indices.extend(c.tolist())
+            indptr.append(len(indices))
+            seg.append(s)
+    indptr = np.asarray(indptr, dtype=np.int32)
+    indices = np.asarray(indices, dtype=np.int32)
+    scores = rng.integers(140, 260, len(indices)).astype(np.uint16)
+    hl = layout_host.build(indptr, indices, scores, np.asarray(seg, dtype=np.int32), len(sizes), 401)
+    nent = {s: [] for s in range(len(sizes))}
+    for t in range(hl.n_tiles):
+        nent[int(hl.tile_hdr[t][0])].append(int(hl.tile_hdr[t][2]))
+    chunk = hl.chunk
+    for s, a in enumerate(sizes):
+        a = a // 3 * 3
+        assert sum(nent[s]) == a and max(nent[s]) <= layout_host.E_HARD
+        if a <= chunk:
+            assert len(nent[s]) == 1
+        elif a <= layout_host.STREAM_SEG_TILES * chunk:
+            want = min(-(-a // min(chunk, layout_host.E_CLUSTER)), layout_host.STREAM_SEG_TILES)
+            assert len(nent[s]) == want, (a, nent[s])
+            assert max(nent[s]) - min(nent[s]) <= 6, (a, nent[s])          # equal up to a row
+        else:
+            assert max(nent[s]) <= layout_host.E_STREAM                     # streamed: small tiles
