@@ -819,13 +819,9 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
       xc_[k] = (uint16_t)(rbk + before - (k < rank ? 1 : 0));
     }
   }
-  // per-segment constants of the column update live in shared memory: they are needed in the column phases only and
-  // must not take registers during the row phase (64-register variant)
-  __shared__ double s_k[4];
-  if (tid == 0) {
-    s_k[0] = a.F.seg_thpw[seg]; s_k[1] = a.F.seg_pipw[seg];
-    s_k[2] = a.F.seg_inv_thd[seg]; s_k[3] = a.F.seg_inv_pid[seg];
-  }
+  const double thpw = a.F.seg_thpw[seg], pipw = a.F.seg_pipw[seg];
+  const double inv_thd = a.F.seg_inv_thd[seg], inv_pid = a.F.seg_inv_pid[seg];
+  const double diff1_extra = a.F.seg_diff1_extra[seg];
   const double eps = a.P.eps;
   const int max_iter = a.P.max_iter;
   double* diffs = a.F.seg_diffs + (long long)seg * max_iter;
@@ -846,12 +842,12 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
   const uint32_t dummy_off = ((uint32_t)v.ncol << 3) | ((uint32_t)v.pe << 19);
   double fq[FR][FRAG], fw[FR];
   uint32_t fo[FR][FRAG];
-  int rd[FR];                                  // lanes of the row's group | warp maximum of the entries << 8 | of the groups << 16
+  int fg[FR], nA[FR], gA[FR];
 #pragma unroll
   for (int j = 0; j < FR; ++j) {
     const int vl = tid + j * THREADS;
-    int n = 0, fgj = 1;
-    fw[j] = 0.0;
+    int n = 0;
+    fg[j] = 1; fw[j] = 0.0;
 #pragma unroll
     for (int p = 0; p < FRAG; ++p) { fq[j][p] = 0.0; fo[j][p] = dummy_off; }
     if (vl < Vc) {
@@ -862,7 +858,7 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
       else { g = 1; r = n_huge + n8 + n4 + n2 + (vl - V2); k = 0; }
       const int len = grlen[r];
       n = max(0, min(FRAG, len - FRAG * k));
-      fgj = g; fw[j] = gw[r];
+      fg[j] = g; fw[j] = gw[r];
 #pragma unroll
       for (int p = 0; p < FRAG; ++p)
         if (p < n) {
@@ -872,7 +868,8 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
           fo[j][p] = ((ix & 0xffffu) << 3) | ((ix >> 16) << 19);
         }
     }
-    rd[j] = fgj | ((int)__reduce_max_sync(full, n) << 8) | ((int)__reduce_max_sync(full, fgj) << 16);
+    nA[j] = __reduce_max_sync(full, n);
+    gA[j] = __reduce_max_sync(full, fg[j]);
   }
   // ---- column fragments: descriptors only (the column state lives in shared memory) ----
   const int b128 = (int)hd[H_CGT128];
@@ -889,8 +886,11 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
   else if (Wc < W4) c_ovf = b16 + (Wc - W8) / 4;
   else if (Wc < W2) c_ovf = b8 + (Wc - W4) / 2;
   else c_ovf = b4 + (Wc - W2);
-  // byte offset of the first slot; #slots | group << 4 | (leader ? column + 1 : 0) << 12 | warp maximum of the slots << 25 | of the groups << 28
-  int cb[FC], cm[FC];
+  // byte offset of the first slot; #slots | group << 4 | (leader ? column + 1 : 0) << 12.  (Packing the warp maxima
+  // nB / gB into cm as well, the row descriptors fg / nA / gA into one word and parking the per-segment constants in
+  // shared memory was measured: the spill count of the 64-register variant did not move and the extra field
+  // extraction cost 3.5 % -- config 5 x0.2 90.2 against 87.1 ms, profiles/r2l_descriptor_packing_experiment.log)
+  int cb[FC], cm[FC], nB[FC], gB[FC];
 #pragma unroll
   for (int j = 0; j < FC; ++j) {
     const int vl = tid + j * THREADS;
@@ -910,8 +910,9 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
       cgj = g;
       ccj = k == 0 ? c : -1;
     }
-    cm[j] = cnj | (cgj << 4) | ((ccj + 1) << 12) | ((int)__reduce_max_sync(full, cnj) << 25) |
-            ((31 - __clz((int)__reduce_max_sync(full, cgj))) << 28);
+    cm[j] = cnj | (cgj << 4) | ((ccj + 1) << 12);
+    nB[j] = __reduce_max_sync(full, cnj);
+    gB[j] = __reduce_max_sync(full, cgj);
   }
   __syncthreads();
 
@@ -936,7 +937,6 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
   // go to shared memory, |delta pi| is added up (`count`: this CTA is the first holder of the column).  Final pass:
   // pi' and theta' of iteration `fin` go to the segment's column table.
   auto update_col = [&](int c, double tot, const double* x_in, bool count) {
-    const double thpw = s_k[0], pipw = s_k[1], inv_thd = s_k[2], inv_pid = s_k[3];
     const double T = x_in[c] * tot;
     const double th = (T + thpw) * inv_thd;
     const double pn = (sps0[c] + T + pipw) * inv_pid;
@@ -979,20 +979,19 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
       const unsigned char* const xb = reinterpret_cast<const unsigned char*>(x_in);
 #pragma unroll
       for (int j = 0; j < FR; ++j) {
-        const int nAj = (rd[j] >> 8) & 0xff;
-        if (nAj > 0) {
+        if (nA[j] > 0) {
           double acc = 0.0;
 #pragma unroll
           for (int p = 0; p < FRAG; ++p)
-            if (p < nAj) acc = fma(fq[j][p], *reinterpret_cast<const double*>(xb + (fo[j][p] & 0xffffu)), acc);
-          if ((rd[j] >> 16) > 1) acc = group_xor_sum(acc, rd[j] & 0xff, rd[j] >> 16);
+            if (p < nA[j]) acc = fma(fq[j][p], *reinterpret_cast<const double*>(xb + (fo[j][p] & 0xffffu)), acc);
+          if (gA[j] > 1) acc = group_xor_sum(acc, fg[j], gA[j]);
           const bool pos = acc > 0.0;
           double inv = 1.0 / (pos ? acc : 1.0);
           inv = pos ? inv : 0.0;
           const double sc = fw[j] * inv;
 #pragma unroll
           for (int p = 0; p < FRAG; ++p)
-            if (p < nAj) *reinterpret_cast<double*>(vb + (fo[j][p] >> 16)) = fq[j][p] * sc;
+            if (p < nA[j]) *reinterpret_cast<double*>(vb + (fo[j][p] >> 16)) = fq[j][p] * sc;
         }
       }
       if (generic_rows) {
@@ -1018,18 +1017,17 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
       // too is pushed to them first, the others are finished by the thread that parked them ----
 #pragma unroll
       for (int j = 0; j < FC; ++j) {
-        const int nBj = (cm[j] >> 25) & 7;
-        if (nBj > 0) {
+        if (nB[j] > 0) {
           double asum = 0.0;
           unsigned char* const cp = vb + cb[j];
           const int cnj = cm[j] & 15;
 #pragma unroll
           for (int k = 0; k < FRAG; ++k)
-            if (k < nBj) {
+            if (k < nB[j]) {
               if (k < cnj) asum += *reinterpret_cast<const double*>(cp + 8 * k);
             }
-          if ((cm[j] >> 28) > 0) asum = group_xor_sum(asum, (cm[j] >> 4) & 63, 1 << (cm[j] >> 28));
-          const int c1 = (cm[j] >> 12) & 0x1fff;
+          if (gB[j] > 1) asum = group_xor_sum(asum, (cm[j] >> 4) & 63, gB[j]);
+          const int c1 = cm[j] >> 12;
           if (c1 > 0) {
             if (shr[c1 - 1]) {
               *reinterpret_cast<double*>(cp) = asum;
@@ -1071,7 +1069,7 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
       // ---- decision for iteration it-1 (all CTAs add the partials in rank order) ----
       double diff = 0.0;
       for (int r = 0; r < nt; ++r) diff += s_dall[pp][r];
-      if (it - 1 == 1) diff += a.F.seg_diff1_extra[seg];
+      if (it - 1 == 1) diff += diff1_extra;
       if (rank == 0 && tid == 0) diffs[it - 2] = diff;
       conv = diff < eps;                                          // model.py:351
       if (conv || it - 1 >= max_iter) {
