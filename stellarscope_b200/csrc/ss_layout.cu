@@ -64,6 +64,20 @@ __global__ void cluster_xref_kernel(const int* __restrict__ tiles, int n, Layout
     xref[off + (long long)(L.c_scol[co + c] - col0) * nt + k] = (uint16_t)c;
 }
 
+// per-column lists of the streamed segments: index of the segment in the list of streamed segments, absolute slot of
+// the column.  One CTA per streamed segment.
+__global__ void stream_cols_kernel(const int* __restrict__ segs, const long long* __restrict__ first,
+                                   const int* __restrict__ seg_col0, const int* __restrict__ seg_ncol,
+                                   int* __restrict__ col_seg, int* __restrict__ col_slot) {
+  const int si = blockIdx.x, s = segs[si];
+  const long long o = first[si];
+  const int c0 = seg_col0[s], n = seg_ncol[s];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    col_seg[o + j] = si;
+    col_slot[o + j] = c0 + j;
+  }
+}
+
 // number of a segment's columns that a tile touches (the others belong to unique rows only); one warp per segment
 __global__ void seg_tile_cols_kernel(int S, const int* __restrict__ seg_col0, const int* __restrict__ seg_ncol,
                                      const int8_t* __restrict__ sc_inamb, int* __restrict__ out) {
@@ -264,16 +278,22 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
     }
   }
   h->all_smem = all_smem;
-  auto by_size = [&](int a, int b) {
-    const long long ea = h->hdr_host[(size_t)a * HDR_WORDS + H_NENT], eb = h->hdr_host[(size_t)b * HDR_WORDS + H_NENT];
-    return ea != eb ? ea > eb : a < b;
+  // largest first, ties by id: sorted as packed integer keys (a comparator that looks the sizes up in the 40 MB header
+  // table misses the cache on every comparison)
+  auto sort_by_size = [&](std::vector<int>& v, auto size_of) {
+    std::vector<unsigned long long> keys(v.size());
+    for (size_t i = 0; i < v.size(); ++i)
+      keys[i] = ((unsigned long long)(unsigned)(0x7fffffff - (int)size_of(v[i])) << 32) | (unsigned)v[i];
+    std::sort(keys.begin(), keys.end());
+    for (size_t i = 0; i < v.size(); ++i) v[i] = (int)(keys[i] & 0xffffffffu);
   };
+  auto tile_nent = [&](int t) { return h->hdr_host[(size_t)t * HDR_WORDS + H_NENT]; };
   for (int c = 0; c < SS_NUM_CLASSES; ++c) {
-    std::sort(cls[c].begin(), cls[c].end(), by_size);
+    sort_by_size(cls[c], tile_nent);
     h->cls_count[c] = (int)cls[c].size();
     SS_CUDA_CHECK(h, upload(pool, &h->cls_tiles[c], (const int*)cls[c].data(), cls[c].size(), st));
   }
-  std::sort(stream.begin(), stream.end(), by_size);
+  sort_by_size(stream, tile_nent);
   h->n_stream_tiles = (int)stream.size();
   SS_CUDA_CHECK(h, upload(pool, &h->stream_tiles, (const int*)stream.data(), stream.size(), st));
   SS_CUDA_CHECK(h, upload(pool, &h->all_tiles, (const int*)all.data(), all.size(), st));
@@ -294,15 +314,16 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
     SS_CUDA_CHECK(h, dev_alloc(pool, &h->chunk_part, (size_t)std::max(2 * h->n_col_chunks, 1)));
   }
   // multi-tile segments and their columns
-  std::vector<int> segs, col_seg, col_slot;
+  // (the per-column lists -- 10^7 entries for the ~900 streamed cells of the atlas configuration -- are filled on
+  // the device: stream_cols_kernel)
+  std::vector<int> segs;
+  std::vector<long long> seg_first;                      // first entry of a streamed segment in the column lists
+  long long n_stream_cols = 0;
   for (int s = 0; s < L.S; ++s) {
     if (h->seg_ntiles_host[s] > 1 && !seg_clustered[s]) {
-      const int si = (int)segs.size();
       segs.push_back(s);
-      for (int j = 0; j < seg_ncol[s]; ++j) {
-        col_seg.push_back(si);
-        col_slot.push_back(seg_col0[s] + j);
-      }
+      seg_first.push_back(n_stream_cols);
+      n_stream_cols += seg_ncol[s];
     }
   }
   // column chunks of the streamed segments: the update pass of the streaming kernel runs one warp per chunk
@@ -318,25 +339,26 @@ int layout_plan(ss_handle_s* h, cudaStream_t st, const std::vector<int>& seg_nco
     SS_CUDA_CHECK(h, upload(pool, &h->stream_chunk_j0, (const int*)sch_j0.data(), sch_j0.size(), st));
   }
   h->n_stream_segs = (int)segs.size();
-  h->n_stream_cols = (long long)col_seg.size();
+  h->n_stream_cols = n_stream_cols;
   SS_CUDA_CHECK(h, upload(pool, &h->stream_segs, (const int*)segs.data(), segs.size(), st));
-  SS_CUDA_CHECK(h, upload(pool, &h->stream_col_seg, (const int*)col_seg.data(), col_seg.size(), st));
-  SS_CUDA_CHECK(h, upload(pool, &h->stream_col_slot, (const int*)col_slot.data(), col_slot.size(), st));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &h->stream_col_seg, (size_t)n_stream_cols));
+  SS_CUDA_CHECK(h, dev_alloc(pool, &h->stream_col_slot, (size_t)n_stream_cols));
+  if (!segs.empty()) {
+    long long* d_first;
+    SS_CUDA_CHECK(h, upload(pool, &d_first, (const long long*)seg_first.data(), seg_first.size(), st));
+    stream_cols_kernel<<<(unsigned)segs.size(), 256, 0, st>>>(h->stream_segs, d_first, L.seg_col0, L.seg_ncol, h->stream_col_seg,
+                                                              h->stream_col_slot);
+    h->launches++;
+    SS_CUDA_CHECK(h, cudaGetLastError());
+  }
   // cluster segments
   h->n_cluster_tiles = (int)cluster_tiles.size();
   h->n_cluster_segs = 0;
   for (int k = 2; k <= MAXC; ++k) {
     // big segments first
-    std::sort(clu[k].begin(), clu[k].end(), [&](int a, int b) {
-      const long long ea = h->hdr_host[(size_t)(h->seg_tile0_host[a] + k - 1) * HDR_WORDS + H_NENT];
-      const long long eb = h->hdr_host[(size_t)(h->seg_tile0_host[b] + k - 1) * HDR_WORDS + H_NENT];
-      return ea != eb ? ea > eb : a < b;
-    });
-    std::sort(clu_light[k].begin(), clu_light[k].end(), [&](int a, int b) {
-      const long long ea = h->hdr_host[(size_t)(h->seg_tile0_host[a] + k - 1) * HDR_WORDS + H_NENT];
-      const long long eb = h->hdr_host[(size_t)(h->seg_tile0_host[b] + k - 1) * HDR_WORDS + H_NENT];
-      return ea != eb ? ea > eb : a < b;
-    });
+    auto last_tile_nent = [&](int sg) { return h->hdr_host[(size_t)(h->seg_tile0_host[sg] + k - 1) * HDR_WORDS + H_NENT]; };
+    sort_by_size(clu[k], last_tile_nent);
+    sort_by_size(clu_light[k], last_tile_nent);
     h->clu_count[k] = (int)clu[k].size();
     h->clu_count_light[k] = (int)clu_light[k].size();
     h->n_cluster_segs += h->clu_count[k] + h->clu_count_light[k];
