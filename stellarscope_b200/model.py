@@ -392,13 +392,14 @@ def _em_wrapper(tl: TelescopeLikelihood):
     return tl.z, tl.fitinfo
 
 
-def pooling_row_segments(st, opts, collective=False):
+def pooling_row_segments(st, opts, collective=False, info=None):
     """Row -> model map of a pooling mode (model.py:701-743).  Returns
     ``(row_segment int32[N], keys)`` where ``keys[i]`` is the key of model i in
     ``PoolInfo.models_info`` (model.py:766, 791).  The reference's containers
     (``bcode_ridx_map``: barcode -> set of row ids) are walked by the C helper
     ``csrc/ss_hostutil.c``.  ``collective``: all ranks of the default process group make this call together (passes
-    over per-row arrays may then be done in 1/world slices and combined)."""
+    over per-row arrays may then be done in 1/world slices and combined).  ``info`` (a dict) receives
+    ``all_assigned`` when the call knows without another pass whether every row belongs to a model."""
     from . import hostutil
     N = st.shape[0]
     if opts.pooling_mode == 'pseudobulk':
@@ -407,7 +408,7 @@ def pooling_row_segments(st, opts, collective=False):
         from . import checkpoint
         table = checkpoint.row_table(st)
         if table is not None:
-            return _row_segments_from_table(st, opts, table, collective)
+            return _row_segments_from_table(st, opts, table, collective, info)
     seg = np.full(N, -1, dtype=np.int32)
     groups, ids = [], []
     i = 0
@@ -443,7 +444,7 @@ def pooling_row_segments(st, opts, collective=False):
     return seg, list(range(i))
 
 
-def _row_segments_from_table(st, opts, table, collective=False):
+def _row_segments_from_table(st, opts, table, collective=False, info=None):
     """``pooling_row_segments`` for an object loaded from a side-car checkpoint (``checkpoint.RowTable``): the
     barcode code of every row is already an array, no container is walked."""
     code = table.row_bcode
@@ -464,6 +465,8 @@ def _row_segments_from_table(st, opts, table, collective=False):
     if opts.pooling_mode == 'individual':
         has = counts > 0
         if all_coded and has.all():
+            if info is not None:
+                info['all_assigned'] = True
             return code, list(range(nb))                          # model of a row = its barcode code: no pass at all
         model_of = np.where(has, np.cumsum(has) - 1, -1).astype(np.int32)   # barcodes without reads get no model
         for b in np.flatnonzero(~has):
@@ -492,6 +495,8 @@ def _row_segments_from_table(st, opts, table, collective=False):
         seg = model_of[code]
     else:
         seg = np.where(code >= 0, model_of[np.maximum(code, 0)], -1).astype(np.int32)
+    if info is not None:                                          # rows of a barcode without a model are loose
+        info['all_assigned'] = bool(all_coded and not np.any((counts > 0) & (model_of < 0)))
     return seg, list(range(n_models))
 
 
@@ -569,7 +574,8 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
         # simply not fitted here
         from . import parallel
         _t = [time.perf_counter()]
-        row_segment, keys = pooling_row_segments(st, opts, collective=True)
+        seg_info = {}
+        row_segment, keys = pooling_row_segments(st, opts, collective=True, info=seg_info)
         _t.append(time.perf_counter())
         m = fullmat if scipy.sparse.isspmatrix_csr(fullmat) else scipy.sparse.csr_matrix(fullmat)
         # a model much larger than a rank's fair share (a dominant cell type on 8 GPUs) cannot be balanced by packing
@@ -577,7 +583,9 @@ def _fit_pooling_model(st, opts, processes: int = 1, progress: int = 100):
         # opts.wide_models: None (default: pack whole models), 'auto' (parallel.wide_models) or a list of model indices;
         # opts.wide_model_cost: lockstep overhead of one wide model in alignments of single-GPU work
         umi_counts = bool(getattr(opts, 'umi_counts', False))
-        loose = len(row_segment) > 0 and int(row_segment.min()) < 0
+        # (a pass over 10^8 rows on every rank when the row -> model map did not already tell)
+        loose = (not seg_info['all_assigned']) if 'all_assigned' in seg_info else \
+            (len(row_segment) > 0 and int(row_segment.min()) < 0)
         row_cell = _row_cells(st) if (loose or (umi_counts and getattr(opts, 'wide_models', None))) else None
         plan = parallel.plan_local_rows(m.indptr, row_segment, len(keys), world, rank,
                                         wide=getattr(opts, 'wide_models', None) or [],

@@ -123,9 +123,12 @@ def test_hot_path_arrays_from_table_equal_dict_route(tmp_path):
     for mode in ('individual', 'celltype', 'pseudobulk'):
         opts = types.SimpleNamespace(pooling_mode=mode)
         ld = checkpoint.load(f)
-        seg_t, keys_t = model.pooling_row_segments(ld, opts)
+        info = {}
+        seg_t, keys_t = model.pooling_row_segments(ld, opts, info=info)
         seg_d, keys_d = model.pooling_row_segments(st, opts)
         assert np.array_equal(seg_t, seg_d) and keys_t == keys_d, mode
+        if 'all_assigned' in info:             # what the sharded fit takes instead of a pass over the rows
+            assert info['all_assigned'] == bool(len(seg_t) == 0 or seg_t.min() >= 0), mode
         assert checkpoint.row_table(ld) is not None and not ld.read_index.materialised
     ld = checkpoint.load(f)
     assert np.array_equal(model._row_cells(ld), model._row_cells(st))
