@@ -721,7 +721,8 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
   uint16_t* xr = reinterpret_cast<uint16_t*>(rpart + 2 * xmax);   // [ncol][nt]: see below
   uint16_t* shl = xr + (size_t)nt * pcmax;             // the shared columns, ascending (bit 15: an earlier tile holds it too)
   uint16_t* rb = shl + pcmax;                          // [ncol] first receive slot of a shared column
-  uint8_t* shr = reinterpret_cast<uint8_t*>(rb + pcmax);   // [ncol] another tile holds the column too
+  uint16_t* shp = rb + pcmax;                          // per list entry: the scratch slot its column sum is parked in
+  uint8_t* shr = reinterpret_cast<uint8_t*>(shp + pcmax);   // [ncol] another tile holds the column too
   __shared__ __align__(8) uint64_t s_mbar[2];
   __shared__ double s_dall[2][SS_MAX_CLUSTER_TILES];   // [parity][rank]: |delta pi| partial of every CTA of the cluster (pushed)
 
@@ -784,6 +785,7 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
       if (others > 0) {
         const int at = base + incl - mine;                 // exclusive prefix: list position | first receive slot << 16
         shl[at & 0xffff] = (uint16_t)(c | (not_first ? 0x8000 : 0));
+        shp[at & 0xffff] = gcptr[c];
         rb[c] = (uint16_t)(at >> 16);
       }
       run += tot;
@@ -961,7 +963,7 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
       if (bytes) mbar_expect_tx(&s_mbar[pp], bytes);
       else mbar_arrive(&s_mbar[pp]);
     }
-    // my partial sum of shared column c: parked like the others, and pushed to the other holders
+    // my partial sum of shared column c goes to the other holders
     auto push_col = [&](int c, double asum) {
       const uint16_t* xc_ = xr + c * nt;
 #pragma unroll
@@ -1029,12 +1031,8 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
           if (gB[j] > 1) asum = group_xor_sum(asum, (cm[j] >> 4) & 63, gB[j]);
           const int c1 = cm[j] >> 12;
           if (c1 > 0) {
-            if (shr[c1 - 1]) {
-              *reinterpret_cast<double*>(cp) = asum;
-              push_col(c1 - 1, asum);
-            } else {
-              update_col(c1 - 1, asum, x_in, true);
-            }
+            if (shr[c1 - 1]) *reinterpret_cast<double*>(cp) = asum;
+            else update_col(c1 - 1, asum, x_in, true);
           }
         }
       }
@@ -1042,27 +1040,24 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
         const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
         const double asum = col_sum_warp(val, b, n, lane);
         if (lane == 0) {
-          if (shr[c]) {
-            val[b] = asum;
-            push_col(c, asum);
-          } else {
-            update_col(c, asum, x_in, true);
-          }
+          if (shr[c]) val[b] = asum;
+          else update_col(c, asum, x_in, true);
         }
       }
       for (int c = c_ovf + tid; c < v.ncol; c += THREADS) {       // columns beyond the register lanes
         const int b = gcptr[c], n = (int)gcptr[c + 1] - b;
         const double asum = col_sum_thread(val, b, n);
-        if (shr[c]) {
-          val[b] = asum;
-          push_col(c, asum);
-        } else {
-          update_col(c, asum, x_in, true);
-        }
+        if (shr[c]) val[b] = asum;
+        else update_col(c, asum, x_in, true);
       }
     }
     SS_TICK(tB1)
     __syncthreads();                                              // the parked sums of the shared columns are visible
+    // push the sums of the shared columns to their other holders: one lane per list entry.  (Pushing from the column
+    // lanes as soon as a sum is known put ~20 instructions per holder and slot into EVERY warp -- nearly all warps have
+    // a shared column among their 96 -- about a quarter of the kernel's instructions.)
+    if (work)
+      for (int i = tid; i < n_sh; i += THREADS) push_col(shl[i] & 0x7fff, val[shp[i]]);
     mbar_wait_cluster(&s_mbar[pp], (uint32_t)((xc - 1) >> 1) & 1u);
     SS_TICK(tS)
     if (!final_pass && it > 1) {
@@ -1095,7 +1090,7 @@ __global__ void __maxnreg__(MAXREG) em_clane_kernel(EmArgs a, ClusterArgs ca) {
         for (int k = 0; k < SS_MAX_CLUSTER_TILES; ++k)
           if (k < nt) {
             const unsigned e = xc_[k];
-            if (e == 0xfffeu) tot += val[gcptr[c]];
+            if (e == 0xfffeu) tot += val[shp[i]];
             else if (e != 0xffffu) tot += rp[sl++];
           }
         update_col(c, tot, x_in, first);

@@ -129,9 +129,9 @@ __host__ __device__ inline size_t lane_smem_bytes(int nent, int ncol) {
 // shared memory of the cluster lane kernel (ss_em.cu): x of three iterations, pi, pisum0: 5 pcmax doubles; scratch:
 // pemax + 8 doubles; receive buffers of the two pass parities: 2 xmax doubles (xmax = padded sum over the segment's
 // columns of (holders - 1): what a tile can receive per pass); cross reference: nt * pcmax u16; list of the shared
-// columns and their first receive slots: 2 pcmax u16; shared-column flags: pcmax bytes
+// columns, their first receive slots and their park slots: 3 pcmax u16; shared-column flags: pcmax bytes
 __host__ __device__ inline size_t clane_smem_bytes(int pemax, int pcmax, int nt, int xmax) {
-  return 8 * (5 * (size_t)pcmax + (size_t)pemax + 8 + 2 * (size_t)xmax) + 2 * (size_t)(nt + 2) * (size_t)pcmax +
+  return 8 * (5 * (size_t)pcmax + (size_t)pemax + 8 + 2 * (size_t)xmax) + 2 * (size_t)(nt + 3) * (size_t)pcmax +
          (size_t)pcmax + 64;
 }
 
