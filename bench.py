@@ -701,7 +701,8 @@ def run_ours(args):
             bound='issue_slots', warp_instructions_per_unit=winst,
             achieved=winst * value / world / 1e9, peak=sm_count * 4 * sm_hz / 1e9, unit='G warp-instructions/s per GPU',
             frac=winst * value / world / (sm_count * 4 * sm_hz),
-            source='profiles/r2l_cfg5_x0.05_em_ncu.csv: 8.72 G warp instructions for 2.43 G alignments x iterations; peak = '
+            source='profiles/r2l_cfg5_x0.05_em_ncu.csv: 8.72 G warp instructions for 2.43 G alignments x iterations (captured '
+                   'before the pushes of the cluster kernel moved into a compact loop: a few percent fewer since); peak = '
                    'SMs x 4 schedulers x SM clock (the kernels also wait on shared memory and barriers: 45-62 % of the '
                    'issue slots is what the best of them reach)')
         line = dict(
