@@ -902,11 +902,69 @@ done:
 static PyObject* count_rows(PyObject* self, PyObject* args) { return select_rows_impl(args, 0); }
 static PyObject* fill_rows(PyObject* self, PyObject* args) { return select_rows_impl(args, 1); }
 
+/* fill_ranges(starts, ends, offsets, rows, local_seg): the rows of model i of a rank are [starts[i], ends[i]) (row -> model
+ * map sorted by model: parallel.plan_local_rows); rows[offsets[i] + k] = starts[i] + k, local_seg[...] = i.  Threaded
+ * over the models in blocks of equal row count. */
+typedef struct { const int64_t *st, *en, *off; int64_t* rows; int32_t* lseg; Py_ssize_t m0, m1; } range_t;
+static void* range_main(void* arg) {
+  range_t* w = (range_t*)arg;
+  for (Py_ssize_t i = w->m0; i < w->m1; ++i) {
+    int64_t o = w->off[i];
+    for (int64_t r = w->st[i]; r < w->en[i]; ++r, ++o) { w->rows[o] = r; w->lseg[o] = (int32_t)i; }
+  }
+  return NULL;
+}
+static PyObject* fill_ranges(PyObject* self, PyObject* args) {
+  Py_buffer st, en, off, rows, lseg;
+  if (!PyArg_ParseTuple(args, "y*y*y*w*w*", &st, &en, &off, &rows, &lseg)) return NULL;
+  PyObject* result = NULL;
+  const Py_ssize_t m = st.len / 8, n = rows.len / 8;
+  if (st.itemsize != 8 || en.itemsize != 8 || off.itemsize != 8 || rows.itemsize != 8 || lseg.itemsize != 4 ||
+      en.len / 8 != m || off.len / 8 != m + 1 || lseg.len / 4 != n || (m > 0 && ((const int64_t*)off.buf)[m] != n)) {
+    PyErr_SetString(PyExc_TypeError, "fill_ranges: starts / ends int64 [m], offsets int64 [m + 1], rows int64 [n], local_seg int32 [n]");
+    goto done;
+  }
+  {
+    int nt = host_threads();
+    if (n < 2000000) nt = 1;
+    if (nt > 16) nt = 16;
+    range_t w[16];
+    pthread_t th[16];
+    const int64_t* o = (const int64_t*)off.buf;
+    Py_BEGIN_ALLOW_THREADS
+    Py_ssize_t m0 = 0;
+    for (int i = 0; i < nt; ++i) {
+      /* models up to the one that holds row (i + 1) n / nt */
+      const int64_t want = (int64_t)((__int128)n * (i + 1) / nt);
+      Py_ssize_t m1 = m0;
+      if (i == nt - 1) m1 = m;
+      else while (m1 < m && o[m1 + 1] <= want) ++m1;
+      w[i].st = (const int64_t*)st.buf; w[i].en = (const int64_t*)en.buf; w[i].off = o;
+      w[i].rows = (int64_t*)rows.buf; w[i].lseg = (int32_t*)lseg.buf; w[i].m0 = m0; w[i].m1 = m1;
+      m0 = m1;
+    }
+    int started = 0;
+    for (int i = 1; i < nt; ++i) {
+      if (pthread_create(&th[i], NULL, range_main, &w[i]) != 0) break;
+      ++started;
+    }
+    range_main(&w[0]);
+    for (int i = 1; i <= started; ++i) pthread_join(th[i], NULL);
+    for (int i = started + 1; i < nt; ++i) range_main(&w[i]);
+    Py_END_ALLOW_THREADS
+    result = PyLong_FromSsize_t(n);
+  }
+done:
+  PyBuffer_Release(&st); PyBuffer_Release(&en); PyBuffer_Release(&off); PyBuffer_Release(&rows); PyBuffer_Release(&lseg);
+  return result;
+}
+
 static PyMethodDef methods[] = {
     {"segment_alignments", segment_alignments, METH_VARARGS, "segment_alignments(indptr, row_segment, seg_A): alignments per model"},
     {"lpt_assign", lpt_assign, METH_VARARGS, "lpt_assign(seg_A, world, model_rank): longest-processing-time packing"},
     {"count_rows", count_rows, METH_VARARGS, "count_rows(row_segment, model_rank, rank, counts): rows of a rank per row chunk"},
     {"fill_rows", fill_rows, METH_VARARGS, "fill_rows(row_segment, model_rank, local_id, rank, offsets, rows, local_seg)"},
+    {"fill_ranges", fill_ranges, METH_VARARGS, "fill_ranges(starts, ends, offsets, rows, local_seg): rows of consecutive-row models"},
     {"gather_chunk", gather_chunk, METH_VARARGS,
      "gather_chunk(indptr, src, rows, out_ptr, e0, e1, dst): a range of the row-compacted copy of src, written to dst"},
     {"row_extents", row_extents, METH_VARARGS, "row_extents(indptr, rows, out_ptr): prefix sums of the lengths of the given rows"},

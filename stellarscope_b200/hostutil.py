@@ -99,6 +99,21 @@ def rows_of_rank(row_segment, model_rank, local_id, rank):
     return rows, lseg
 
 
+def rows_of_ranges(starts, ends):
+    """(rows int64[n], local_seg int32[n]) for models whose rows are the ranges ``[starts[i], ends[i])`` (ascending,
+    disjoint): the rows in order and the index of their model."""
+    import numpy as np
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    ends = np.ascontiguousarray(ends, dtype=np.int64)
+    off = np.zeros(len(starts) + 1, dtype=np.int64)
+    np.cumsum(ends - starts, out=off[1:])
+    n = int(off[-1])
+    rows = np.empty(n, dtype=np.int64)
+    lseg = np.empty(n, dtype=np.int32)
+    load().fill_ranges(starts, ends, off, rows, lseg)
+    return rows, lseg
+
+
 def group_sizes(codes, n_groups):
     """int64[n_groups]: number of rows with every code (negative codes count nowhere) -- ``np.bincount`` without
     the int64 copy of 10^8 codes, on a few threads."""

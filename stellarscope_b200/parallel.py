@@ -223,6 +223,17 @@ def plan_local_rows(indptr, row_segment, n_segments, world, rank, wide=None, wid
         # the common case -- every row belongs to a packed model: three threaded passes in C instead of ~10 numpy
         # passes over per-row arrays (1.4x10^8 rows at atlas scale)
         from . import hostutil
+        if N > 0 and _sorted_by_segment(row_segment, world, rank, collective):
+            # the rows of every model are consecutive (reads of a barcode-sorted BAM, `stellarscope cellsort`; the row ->
+            # model map is then non-decreasing): the plan needs no pass over the rows at all -- the first row of every
+            # model by binary search, its alignments from the row pointers there, and the rank's rows as ranges
+            bounds = np.searchsorted(row_segment, np.arange(n_segments + 1, dtype=row_segment.dtype)).astype(np.int64)
+            seg_A = (indptr[bounds[1:]].astype(np.int64) - indptr[bounds[:-1]].astype(np.int64))
+            model_rank = hostutil.lpt_assign(seg_A, world)
+            mine = np.flatnonzero(model_rank == rank).astype(np.int64)
+            rows, local_seg = hostutil.rows_of_ranges(bounds[mine], bounds[mine + 1])
+            return dict(rows=rows, local_seg=local_seg, mine=mine, wide=np.zeros(0, dtype=np.int64), wide_local=[],
+                        seg_A=seg_A)
         if collective and world > 1:
             # every rank counts the alignments per model over 1/world of the rows; the sums are all-reduced
             r0, r1 = N * rank // world, N * (rank + 1) // world
@@ -276,6 +287,23 @@ def plan_local_rows(indptr, row_segment, n_segments, world, rank, wide=None, wid
         wide_local.append(m)
     return dict(rows=rows, local_seg=local_seg, mine=mine, wide=np.asarray(wide_ids, dtype=np.int64),
                 wide_local=wide_local, seg_A=seg_A)
+
+
+def _sorted_by_segment(row_segment, world, rank, collective):
+    """True when the row -> model map is non-decreasing.  ``collective``: every rank looks at 1/world of the rows (and
+    the first row of the next slice) and the verdicts are combined -- all ranks get the same answer."""
+    N = len(row_segment)
+    if collective and world > 1:
+        r0, r1 = N * rank // world, min(N, N * (rank + 1) // world + 1)
+        part = row_segment[r0:r1]
+        bad = int(len(part) > 1 and bool(np.any(part[1:] < part[:-1])))
+        return int(allreduce_sum_host(np.array([bad], dtype=np.int64))[0]) == 0
+    step = 1 << 24                                            # in pieces: no temporary of the size of the map
+    for a in range(0, max(N - 1, 0), step):
+        b = min(N, a + step + 1)
+        if np.any(row_segment[a + 1:b] < row_segment[a:b - 1]):
+            return False
+    return True
 
 
 def _comm_device(group=None):

@@ -339,3 +339,68 @@ def test_gather_concat_world2_gloo():
         assert g['counts'] == [3, 5]
         assert x == [0, 1, 2, 3] and xc == [0, 4]
         assert s == [3, 20]
+
+
+def _plan_inputs():
+    d = H.small_synth(seed=21, n_cells=60, n_alignments=15000, n_loci=300)
+    seg_sorted = d.row_cell.astype(np.int32)                     # rows of a cell are consecutive, cells ascending
+    perm = np.random.default_rng(5).permutation(d.n_cells).astype(np.int32)
+    seg_mixed = perm[d.row_cell]                                 # consecutive but not ascending: the generic route
+    return d, seg_sorted, seg_mixed
+
+
+def test_plan_of_a_sorted_row_map_equals_the_generic_plan(monkeypatch):
+    """Row -> model map sorted by model (barcode-sorted input): the plan comes from binary searches and row ranges and
+    is the one the passes over all rows give."""
+    d, seg_sorted, seg_mixed = _plan_inputs()
+    for world in (1, 2, 3, 8):
+        for rank in range(world):
+            fast = parallel.plan_local_rows(d.indptr, seg_sorted, d.n_cells, world, rank)
+            with monkeypatch.context() as m:
+                m.setattr(parallel, '_sorted_by_segment', lambda *a, **k: False)
+                slow = parallel.plan_local_rows(d.indptr, seg_sorted, d.n_cells, world, rank)
+            for k in ('rows', 'local_seg', 'mine', 'seg_A'):
+                assert np.array_equal(fast[k], slow[k]), (world, rank, k)
+    assert not parallel._sorted_by_segment(seg_mixed, 1, 0, False)
+    assert parallel._sorted_by_segment(seg_sorted, 1, 0, False)
+
+
+def _plan_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    d, seg_sorted, seg_mixed = _plan_inputs()
+    out = {}
+    for name, seg in (('sorted', seg_sorted), ('mixed', seg_mixed)):
+        verdict = parallel._sorted_by_segment(seg, world, rank, True)
+        p = parallel.plan_local_rows(d.indptr, seg, d.n_cells, world, rank, collective=True)
+        ref = parallel.plan_local_rows(d.indptr, seg, d.n_cells, world, rank, collective=False)
+        out[name] = (bool(verdict), all(np.array_equal(p[k], ref[k]) for k in ('rows', 'local_seg', 'mine', 'seg_A')),
+                     p['rows'].tolist())
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_collective_plan_world2_gloo():
+    """The collective form of the plan (1/world slices + all-reduce; sortedness verdict combined over the ranks) gives
+    every rank the plan of the stand-alone call, and the ranks' rows partition the matrix."""
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_plan_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    d, _, _ = _plan_inputs()
+    for name, want_sorted in (('sorted', True), ('mixed', False)):
+        assert got[0][name][0] == got[1][name][0] == want_sorted
+        assert got[0][name][1] and got[1][name][1]
+        rows = np.sort(np.concatenate([got[0][name][2], got[1][name][2]]))
+        assert np.array_equal(rows, np.arange(d.N))
